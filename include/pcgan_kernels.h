@@ -1,0 +1,294 @@
+/*
+ * pcgan_kernels.h — C ABI of libpcgan_kernels.so (B200 / sm_100a).
+ *
+ * This is the whole drop-in boundary of the wsgan_emb hot path: plain pointers,
+ * sizes and POD structs; no torch types.  The Python host side
+ * (pcgan_b200/_lib.py) binds it with ctypes.  Every entry point names the piece
+ * of the reference it replaces (paths relative to phymhan/pc-gan).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative pcgan_status; the text
+ *     of the last failure on the calling thread is pcgan_last_error()
+ *   - the caller owns all device memory (inputs, outputs, statistics); the
+ *     library allocates no device memory and keeps no pointer past return,
+ *     except TMA descriptors cached inside an igemm plan (re-encoded when the
+ *     pointers change)
+ *   - every launch goes to the stream handed in; no call synchronises; all
+ *     calls are CUDA-graph capturable
+ *   - the current CUDA device must be the one that owns the pointers
+ *   - activations are NHWC bf16 in *physically padded* buffers
+ *     [N][H+2p][W+2p][C]; the halo (zeros or a reflection of the interior) is
+ *     written by the kernel that produces the buffer, so padding never costs a
+ *     pass of its own and every convolution is a "valid" one
+ */
+#ifndef PCGAN_KERNELS_H_
+#define PCGAN_KERNELS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGAN_ABI_VERSION 3
+#define PCGAN_MAX_TAPS 64
+
+typedef void* pcgan_stream_t; /* a cudaStream_t */
+
+typedef enum {
+  PCGAN_OK = 0,
+  PCGAN_ERR_INVALID = -1,     /* bad argument / inconsistent descriptor      */
+  PCGAN_ERR_UNSUPPORTED = -2, /* shape outside what the kernels implement    */
+  PCGAN_ERR_CUDA = -3         /* CUDA runtime / driver error (text in last_error) */
+} pcgan_status;
+
+typedef enum { PCGAN_ACT_NONE = 0, PCGAN_ACT_RELU = 1, PCGAN_ACT_LRELU = 2, PCGAN_ACT_TANH = 3, PCGAN_ACT_SIGMOID = 4 } pcgan_act;
+typedef enum { PCGAN_DT_BF16 = 0, PCGAN_DT_F32 = 1 } pcgan_dtype;
+typedef enum { PCGAN_HALO_ZERO = 0, PCGAN_HALO_REFLECT = 1 } pcgan_halo;
+typedef enum { PCGAN_IGEMM_KMAJOR = 0, PCGAN_IGEMM_WGRAD = 1 } pcgan_igemm_kind;
+typedef enum { PCGAN_STATS_NONE = 0, PCGAN_STATS_ON = 1 } pcgan_stats_mode;
+typedef enum { PCGAN_LOSS_BCE = 0, PCGAN_LOSS_MSE = 1, PCGAN_LOSS_L1 = 2, PCGAN_LOSS_ELO_NLL = 3 } pcgan_loss_kind;
+
+int pcgan_abi_version(void);
+const char* pcgan_last_error(void);
+/* sizeof() of an ABI struct by name (-1 if unknown): lets a binding check its mirror of the layout. */
+int64_t pcgan_sizeof(const char* struct_name);
+
+/* ------------------------------------------------------------------------- *
+ * Implicit-GEMM convolution engine (tcgen05 + TMEM + TMA)
+ *
+ * Replaces every nn.Conv2d / nn.ConvTranspose2d forward, data-gradient and
+ * weight-gradient on the path: models/networks.py:578-605 (ResnetGenerator),
+ * :621-648 (ResnetBlock), :747-775 (NLayerDiscriminator), :1014-1027
+ * (SiameseFeature head), models/resnet.py:20-28,134 (ResNet-18 trunk), which
+ * the reference dispatches to cuDNN / oneDNN through ATen.
+ *
+ * One kernel family, described by data: the host planner (pcgan_b200/plan.py)
+ * turns a convolution into
+ *   A : a <=5-D TMA view of a padded NHWC activation buffer (dim 0 = channels)
+ *   B : a <=5-D TMA view of a packed bf16 weight matrix [rows][K]
+ *   a tap table: per filter tap, the coordinate offsets of the A box
+ *   an output map: how a row of the 128-row tile becomes an output address
+ * KMAJOR  D[M=pixels][N=Cout] = sum_taps A_tap[M][Cin] * B_tap[N][Cin]^T
+ *         (forward and data-gradient; transposed convs and strided dgrads run
+ *          one launch per sub-pixel phase)
+ * WGRAD   D[M=Cout][N=Cin]    = sum_pixels dY[pix][M]^T * X_tap[pix][N]
+ *         (both operands MN-major in shared memory; split-K with fp32 atomics)
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t dims[5];    /* extent per dimension, dim 0 innermost (contiguous) */
+  uint64_t strides[5]; /* bytes; strides[0] is ignored (elements are packed) */
+  uint32_t box[5];     /* TMA box; box[0] must be 64 (one 128-byte swizzle row) */
+} pcgan_tmap;
+
+typedef struct {
+  int32_t lo, hi;  /* component valid iff lo <= c < hi                   */
+  int64_t stride;  /* output elements per unit of (c - lo)              */
+} pcgan_comp;
+
+typedef struct {
+  int32_t kind;    /* pcgan_igemm_kind */
+  int32_t block_n; /* UMMA N: 16..256, multiple of 16 (WGRAD: multiple of 64) */
+  pcgan_tmap a, b;
+
+  /* Tiles.  KMAJOR: one tile = one A box = 128 (or fewer) output pixels.
+   * WGRAD: one "tile" = one K block of 64 pixels (A = dY box, B = X box).
+   * The tile index is mixed-radix over t_count (digit 0 fastest); the box
+   * coordinate of outer dim d (d = 0..3 <-> tensor dims 1..4) is
+   *   A: a_base[d] + sum_j t_j*a_step[j][d]   (+ tap_off[tap][d] for KMAJOR)
+   *   B: b_base[d] + sum_j t_j*b_step[j][d] + tap_off[tap][d]   (WGRAD only;
+   *      KMAJOR B is the weight matrix: coords (k, n_tile*block_n, 0,0,0)). */
+  int32_t t_count[4];
+  int32_t a_base[4], a_step[4][4];
+  int32_t b_base[4], b_step[4][4];
+  int32_t n_tiles; /* tiles along N (KMAJOR: Cout/block_n; WGRAD: Cin blocks) */
+  int32_t m_tiles; /* WGRAD: tiles of 128 along Cout; KMAJOR: ignored      */
+  int32_t ksplit;  /* WGRAD: split of the pixel loop across CTAs; KMAJOR: 1 */
+
+  /* K loop = num_taps x cchunks chunks of 64 elements.
+   * KMAJOR: A dim-0 coordinate = tap_c0[tap] + 64*cc, B k-coordinate =
+   * tap_bk[tap] + 64*cc.  WGRAD: B outer coords get tap_off, B dim-0
+   * coordinate = tap_c0[tap] + nt*block_n, output column base = tap_bk[tap]. */
+  int32_t num_taps, cchunks;
+  int32_t tap_off[PCGAN_MAX_TAPS][4];
+  int32_t tap_c0[PCGAN_MAX_TAPS];
+  int32_t tap_bk[PCGAN_MAX_TAPS];
+
+  /* Epilogue.  KMAJOR: row r of a tile has box-local index (i1..i4) over
+   * a.box[1..4]; g_d = e_base[d] + sum_j t_j*e_step[j][d] + i_d is split into
+   * c0 = g / p1, c1 = (g % p1) / p2, c2 = g % p2 (p1 == 0: c0 = 0 and the
+   * remainder is g; p2 == 0: c1 = remainder, c2 = 0); the row is stored iff
+   * every component is inside [lo,hi) and lands at
+   * out + sum (c - lo)*stride + channel*out_cstride. */
+  int32_t e_base[4], e_step[4][4], e_p1[4], e_p2[4];
+  pcgan_comp e_comp[4][3];
+  int32_t out_dtype;   /* pcgan_dtype (WGRAD: always f32, accumulated with atomics) */
+  int32_t act;         /* pcgan_act applied after bias                     */
+  float act_slope;
+  int32_t n_valid;     /* real output channels (columns >= n_valid are dropped)  */
+  int64_t out_cstride; /* elements between channels: 1 = NHWC, H*W = NCHW  */
+  int32_t stats_mode;  /* per-channel sum / sum-of-squares of (acc + bias) of the
+                          stored rows, atomically added to stats[group][n_valid][2] */
+  int32_t stats_dim, stats_comp; /* group index = that component of row 0 of the tile; stats_dim < 0: group 0 */
+  /* WGRAD only */
+  int32_t m_valid;     /* Cout                                             */
+  int32_t wg_ncols;    /* valid columns per tap (Cin or packed row width)  */
+  int64_t ldo;         /* output row pitch in elements                     */
+} pcgan_igemm_desc;
+
+typedef struct pcgan_igemm_plan pcgan_igemm_plan;
+
+/* Validates the descriptor (host only, no GPU needed) and copies it. */
+int pcgan_igemm_plan_create(const pcgan_igemm_desc* desc, pcgan_igemm_plan** plan);
+void pcgan_igemm_plan_destroy(pcgan_igemm_plan* plan);
+/* a, b: operand base pointers (16-byte aligned); out: output base; bias: f32
+ * [n_valid] or NULL; stats: f32 [groups][n_valid][2] or NULL. */
+int pcgan_igemm_run(pcgan_igemm_plan* plan, const void* a, const void* b, void* out,
+                    const float* bias, float* stats, pcgan_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Layout / packing kernels
+ * ------------------------------------------------------------------------- */
+/* dst[i] = idx[i] >= 0 ? bf16(src[idx[i]]) : 0.  Packs OIHW fp32 master weights
+ * (nn.Conv2d.weight, IOHW for ConvTranspose2d: networks.py:595) into the
+ * [rows][K] bf16 operand of a plan. */
+int pcgan_gather_cast_bf16(const float* src, const int32_t* idx, void* dst_bf16, int64_t n, pcgan_stream_t stream);
+/* dst[idx[i]] (+)= src[i] for idx[i] >= 0: packed fp32 weight gradient -> .grad in OIHW. */
+int pcgan_scatter_f32(const float* src, const int32_t* idx, float* dst, int64_t n, int32_t accumulate, pcgan_stream_t stream);
+
+/* NCHW fp32 image [N][Cs][H][W] (+ optional per-sample scalar z[N] appended as
+ * channel Cs: networks.py:610-611, :780-782 torch.cat((input, z_img), 1)),
+ * optionally bilinearly resized to Ho x Wo with align_corners=True
+ * (util/util.py:111-117) and multiplied by (1 - t*t) of a second NCHW tensor
+ * (tanh backward), -> padded NHWC bf16 [N][Ho+2p][Wo+2p][Cd].
+ * Under reflect halo the z plane stays constant; under zero halo it is 0 in the
+ * halo, exactly as ReflectionPad2d / Conv2d(padding=1) see it. */
+typedef struct {
+  const float* src; const float* z; const float* tanh_out;
+  void* dst;
+  int32_t n, cs, h, w;     /* source geometry                                  */
+  int32_t ho, wo;          /* destination interior (== h,w when not resizing)  */
+  int32_t cd, pad, halo;   /* destination channels (multiple of 8), pad, mode  */
+  int64_t dst_n_stride;    /* elements between samples (0: packed)             */
+} pcgan_pack_args;
+int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t stream);
+
+/* Adjoint of the bilinear resize above, reading an NHWC bf16 gradient
+ * [N][Hs+2p][Ws+2p][C] (interior only) and writing / accumulating NCHW fp32
+ * [N][Cd][H][W] (first Cd channels). */
+typedef struct {
+  const void* g; float* dst;
+  int32_t n, c, hs, ws, pad; /* gradient geometry (resized size)        */
+  int32_t cd, h, w;          /* destination                              */
+  int32_t accumulate;
+  float scale;
+} pcgan_unpack_args;
+int pcgan_unpack_resize_bwd(const pcgan_unpack_args* a, pcgan_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Normalisation (+ activation, residual) — nn.InstanceNorm2d(affine=False,
+ * track_running_stats=True) and nn.BatchNorm2d in training mode
+ * (networks.py:22-34; used at :580-581,:588-589,:601-602,:633,:646,:759,:768,
+ * resnet.py:47-65,136; networks.py:1021).
+ * ------------------------------------------------------------------------- */
+/* stats[g][c][2] = (sum, sum of squares) over `count` elements ->
+ * mean/rstd [g][c], scale = gamma*rstd, shift = beta - mean*scale, and the
+ * running-stat EMA (momentum, unbiased variance; for instance norm the batch
+ * mean of the per-instance statistics).  gamma/beta/running_* may be NULL. */
+typedef struct {
+  const float* stats; int32_t groups, c; float count, eps, momentum;
+  const float* gamma; const float* beta;
+  float* mean; float* rstd; float* scale; float* shift;
+  float* running_mean; float* running_var;
+} pcgan_norm_finalize_args;
+int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stream_t stream);
+
+/* y = act(scale*x + shift [+ res_scale*res + res_shift]) written into the
+ * interior AND halo of a padded NHWC bf16 buffer.  x: NHWC bf16 with its own
+ * pad (interior read).  scale/shift are [groups][C] with groups = N (instance)
+ * or 1 (batch), or NULL (identity).  Optional channel-dropout mask[N][C] (f32, already scaled by
+ * 1/(1-p)) multiplies x first (nn.Dropout2d, resnet.py:58-65). */
+typedef struct {
+  const void* x; int32_t x_pad;
+  const void* res; int32_t res_pad;
+  void* y; int32_t y_pad; int32_t y_halo;
+  int32_t n, h, w, c;
+  const float* scale; const float* shift; int32_t groups;
+  const float* res_scale; const float* res_shift; int32_t res_groups;
+  const float* drop_mask;
+  int32_t act; float act_slope;
+} pcgan_norm_apply_args;
+int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t stream);
+
+/* out[N][H][W][C] (pad out_pad, zero halo kept) = fold(gpad) [+ add]: folds the gradient of a padded
+ * buffer (reflect: halo gradients are added onto their mirror pixels; zero: halo
+ * dropped) back onto the interior — the adjoint of the halo write above
+ * (nn.ReflectionPad2d backward). */
+typedef struct {
+  const void* gpad; int32_t g_pad; int32_t halo;
+  const void* add; int32_t add_pad;
+  void* out; int32_t out_pad;
+  int32_t n, h, w, c;
+} pcgan_fold_args;
+int pcgan_halo_fold(const pcgan_fold_args* a, pcgan_stream_t stream);
+
+/* Backward of y = act(scale*x + shift (+res...)): with g = dy * act'(y),
+ * pass 1 accumulates sums[g][c][2] = (sum g, sum g*xhat); pass 2 writes
+ * dx = scale*(g - sum_g/count - xhat*sum_gxhat/count) (count == 0: plain
+ * dx = scale*g, i.e. no normalisation) into a zero-haloed padded buffer and, if
+ * asked, g itself (gradient of the residual branch). y is recomputed from x. */
+typedef struct {
+  const void* dy; int32_t dy_pad;       /* NHWC bf16 gradient wrt y (interior) */
+  const void* x; int32_t x_pad;         /* saved pre-norm activations          */
+  const void* res; int32_t res_pad;     /* residual input (to recompute y)     */
+  const float* mean; const float* rstd; const float* scale; const float* shift; int32_t groups;
+  const float* res_scale; const float* res_shift; int32_t res_groups;
+  const float* drop_mask;
+  int32_t act; float act_slope;
+  int32_t n, h, w, c;
+  float count;                          /* elements per statistic; 0 = no norm  */
+  float* sums;                          /* [groups][c][2], zeroed by the caller */
+  void* dx; int32_t dx_pad;             /* pass 2 outputs                       */
+  void* dres; int32_t dres_pad;         /* optional: g (masked dy)              */
+} pcgan_norm_bwd_args;
+int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
+int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
+
+/* 3x3 stride-2 pad-1 max pooling on padded NHWC bf16 (resnet.py:137); idx keeps the
+ * window position (0..8) of the maximum for the backward pass. */
+typedef struct {
+  const void* x; int32_t x_pad; void* y; int32_t y_pad; uint8_t* idx;
+  int32_t n, h, w, c; /* input geometry; output is ceil(h/2) x ceil(w/2) */
+} pcgan_maxpool_args;
+int pcgan_maxpool3x3s2_fwd(const pcgan_maxpool_args* a, pcgan_stream_t stream);
+/* dx (input geometry, pad x_pad, zero halo) from dy (output geometry, pad y_pad). */
+int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint8_t* idx, void* dx, int32_t dx_pad,
+                           int32_t n, int32_t h, int32_t w, int32_t c, pcgan_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Losses: vectorised, coalesced reductions (GANLoss networks.py:386-420 ->
+ * nn.BCELoss with log clamped at -100 / nn.MSELoss; nn.L1Loss and nn.MSELoss in
+ * wsgan_emb_model.py:149,402,430; BinaryNLLLoss networks.py:473-482).
+ *   BCE     mean(-(t*max(log p,-100) + (1-t)*max(log(1-p),-100)))
+ *   MSE     mean((p-t)^2)          L1  mean(|p-t|)
+ *   ELO_NLL mean(-(t*log(p+1e-20) + (1-t)*log(1-p+1e-20)))
+ * target: either a full tensor t[n] (per_sample = 0) or one value per sample
+ * t[n / per_sample].  loss is atomically accumulated (*loss += weight*mean).
+ * grad (optional) = weight * dmean/dp, same shape as p. */
+typedef struct {
+  int32_t kind; const float* p; const float* target; int64_t n; int64_t per_sample;
+  float weight; float* loss; float* grad;
+} pcgan_loss_args;
+int pcgan_loss(const pcgan_loss_args* a, pcgan_stream_t stream);
+
+/* Fused Adam step over one flat fp32 parameter (torch.optim.Adam semantics,
+ * wsgan_emb_model.py:153-154): step count and lr are read from device memory
+ * so the launch is graph-capturable. */
+int pcgan_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1, float beta2,
+               float eps, const float* step, pcgan_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGAN_KERNELS_H_ */

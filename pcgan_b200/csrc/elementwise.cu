@@ -1,0 +1,675 @@
+// HBM-bound kernels of the wsgan_emb step: layout packing, normalisation forward and
+// backward, halo folding, pooling, losses, Adam.  All activations are NHWC bf16 in
+// physically padded buffers; every kernel moves 16-byte vectors (8 channels) per
+// thread with consecutive threads on consecutive channel vectors (coalesced), and
+// grids are sized in whole waves of the SM count.
+#include "common.cuh"
+
+namespace pcgan {
+
+static constexpr int kThreads = 256;
+
+static inline int grid_for(int64_t work_items, int per_block = kThreads, int waves = 8) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = static_cast<int64_t>(sm_count() > 0 ? sm_count() : 148) * waves;
+  if (blocks > cap) blocks = cap;  // grid-stride loops cover the rest
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+// element offset of interior pixel (n,y,x), channel 0, in a padded NHWC buffer
+__device__ __forceinline__ int64_t pix_off(int n, int y, int x, int h, int w, int c, int pad) {
+  const int64_t hp = h + 2 * pad, wp = w + 2 * pad;
+  return ((static_cast<int64_t>(n) * hp + (y + pad)) * wp + (x + pad)) * c;
+}
+
+// ------------------------------------------------------------ gather / scatter
+__global__ void gather_cast_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
+  }
+}
+__global__ void scatter_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
+                               int64_t n, int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    if (j >= 0) dst[j] = accumulate ? dst[j] + src[i] : src[i];
+  }
+}
+
+// ------------------------------------------------------------------ pack_nchw
+__device__ __forceinline__ void bilinear_setup(int o, int in, int out, int& i0, int& i1, float& l0, float& l1) {
+  // torch.nn.functional.interpolate(mode='bilinear', align_corners=True): util/util.py:117
+  const float scale = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  const float s = scale * static_cast<float>(o);
+  i0 = static_cast<int>(s);
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 < in - 1 ? i0 + 1 : i0;
+  l1 = s - static_cast<float>(i0);
+  l0 = 1.f - l1;
+}
+
+__global__ void pack_nchw_kernel(pcgan_pack_args a) {
+  const int hp = a.ho + 2 * a.pad, wp = a.wo + 2 * a.pad;
+  const int64_t total = static_cast<int64_t>(a.n) * hp * wp;
+  const int64_t nstride = a.dst_n_stride ? a.dst_n_stride : static_cast<int64_t>(hp) * wp * a.cd;
+  const bool resize = (a.ho != a.h) || (a.wo != a.w);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int px = static_cast<int>(i % wp);
+    const int py = static_cast<int>((i / wp) % hp);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(wp) * hp));
+    int y = py - a.pad, x = px - a.pad;
+    const bool halo = y < 0 || y >= a.ho || x < 0 || x >= a.wo;
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(a.dst) + n * nstride + (static_cast<int64_t>(py) * wp + px) * a.cd;
+    if (halo && a.halo == PCGAN_HALO_ZERO) {
+      for (int c = 0; c < a.cd; c += 8) *reinterpret_cast<uint4*>(d + c) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    y = reflect_idx(y, a.ho);
+    x = reflect_idx(x, a.wo);
+    int y0 = y, y1 = y, x0 = x, x1 = x;
+    float ly0 = 1.f, ly1 = 0.f, lx0 = 1.f, lx1 = 0.f;
+    if (resize) {
+      bilinear_setup(y, a.h, a.ho, y0, y1, ly0, ly1);
+      bilinear_setup(x, a.w, a.wo, x0, x1, lx0, lx1);
+    }
+    for (int c = 0; c < a.cd; ++c) {
+      float v = 0.f;
+      if (c < a.cs) {
+        const float* s = a.src + (static_cast<int64_t>(n) * a.cs + c) * a.h * a.w;
+        if (resize) {
+          v = ly0 * (lx0 * s[y0 * a.w + x0] + lx1 * s[y0 * a.w + x1]) +
+              ly1 * (lx0 * s[y1 * a.w + x0] + lx1 * s[y1 * a.w + x1]);
+        } else {
+          v = s[y * a.w + x];
+          if (a.tanh_out) {
+            const float t = a.tanh_out[(static_cast<int64_t>(n) * a.cs + c) * a.h * a.w + y * a.w + x];
+            v *= 1.f - t * t;
+          }
+        }
+      } else if (c == a.cs && a.z != nullptr) {
+        v = a.z[n];
+      }
+      d[c] = __float2bfloat16(v);
+    }
+  }
+}
+
+__global__ void unpack_resize_bwd_kernel(pcgan_unpack_args a) {
+  const int64_t total = static_cast<int64_t>(a.n) * a.h * a.w;
+  const int hsp = a.hs + 2 * a.pad, wsp = a.ws + 2 * a.pad;
+  const bool resize = (a.hs != a.h) || (a.ws != a.w);
+  const float sy = a.hs > 1 ? static_cast<float>(a.h - 1) / static_cast<float>(a.hs - 1) : 0.f;
+  const float sx = a.ws > 1 ? static_cast<float>(a.w - 1) / static_cast<float>(a.ws - 1) : 0.f;
+  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(a.g);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % a.w);
+    const int y = static_cast<int>((i / a.w) % a.h);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(a.w) * a.h));
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    if (!resize) {
+      const __nv_bfloat16* p = g + ((static_cast<int64_t>(n) * hsp + y + a.pad) * wsp + x + a.pad) * a.c;
+      for (int c = 0; c < a.cd; ++c) acc[c] = __bfloat162float(p[c]);
+    } else {
+      // adjoint of the bilinear gather: visit every resized pixel whose footprint touches (y, x)
+      int ylo = sy > 0.f ? static_cast<int>(floorf((y - 1) / sy)) : 0;
+      int yhi = sy > 0.f ? static_cast<int>(ceilf((y + 1) / sy)) : a.hs - 1;
+      int xlo = sx > 0.f ? static_cast<int>(floorf((x - 1) / sx)) : 0;
+      int xhi = sx > 0.f ? static_cast<int>(ceilf((x + 1) / sx)) : a.ws - 1;
+      ylo = max(ylo, 0); xlo = max(xlo, 0); yhi = min(yhi, a.hs - 1); xhi = min(xhi, a.ws - 1);
+      for (int yy = ylo; yy <= yhi; ++yy) {
+        int y0, y1; float l0, l1;
+        bilinear_setup(yy, a.h, a.hs, y0, y1, l0, l1);
+        const float wy = (y0 == y ? l0 : 0.f) + (y1 == y ? l1 : 0.f);
+        if (wy == 0.f) continue;
+        for (int xx = xlo; xx <= xhi; ++xx) {
+          int x0, x1; float m0, m1;
+          bilinear_setup(xx, a.w, a.ws, x0, x1, m0, m1);
+          const float wx = (x0 == x ? m0 : 0.f) + (x1 == x ? m1 : 0.f);
+          if (wx == 0.f) continue;
+          const __nv_bfloat16* p = g + ((static_cast<int64_t>(n) * hsp + yy + a.pad) * wsp + xx + a.pad) * a.c;
+          const float wgt = wy * wx;
+          for (int c = 0; c < a.cd; ++c) acc[c] += wgt * __bfloat162float(p[c]);
+        }
+      }
+    }
+    for (int c = 0; c < a.cd; ++c) {
+      float* d = a.dst + ((static_cast<int64_t>(n) * a.cd + c) * a.h + y) * a.w + x;
+      const float v = acc[c] * a.scale;
+      *d = a.accumulate ? *d + v : v;
+    }
+  }
+}
+
+// -------------------------------------------------------------- norm finalize
+__global__ void norm_finalize_kernel(pcgan_norm_finalize_args a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.c) return;
+  float mean_acc = 0.f, var_acc = 0.f;
+  const float gam = a.gamma ? a.gamma[c] : 1.f;
+  const float bet = a.beta ? a.beta[c] : 0.f;
+  for (int g = 0; g < a.groups; ++g) {
+    const float s1 = a.stats[(static_cast<int64_t>(g) * a.c + c) * 2 + 0];
+    const float s2 = a.stats[(static_cast<int64_t>(g) * a.c + c) * 2 + 1];
+    const float mean = s1 / a.count;
+    float var = s2 / a.count - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    const float rstd = rsqrtf(var + a.eps);
+    const int64_t o = static_cast<int64_t>(g) * a.c + c;
+    if (a.mean) a.mean[o] = mean;
+    if (a.rstd) a.rstd[o] = rstd;
+    if (a.scale) a.scale[o] = gam * rstd;
+    if (a.shift) a.shift[o] = bet - mean * gam * rstd;
+    mean_acc += mean;
+    var_acc += var;
+  }
+  if (a.running_mean) {
+    const float m = mean_acc / a.groups;
+    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * m;
+  }
+  if (a.running_var) {
+    const float unbias = a.count > 1.f ? a.count / (a.count - 1.f) : 1.f;
+    const float v = var_acc / a.groups * unbias;
+    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * v;
+  }
+}
+
+// ----------------------------------------------------------------- norm apply
+// pre-activation of one 8-channel vector at interior pixel (n, y, x)
+struct NormCtx {
+  const __nv_bfloat16* x; int x_pad;
+  const __nv_bfloat16* res; int res_pad;
+  const float* scale; const float* shift; int groups;
+  const float* res_scale; const float* res_shift; int res_groups;
+  const float* drop_mask;
+  int n, h, w, c;
+};
+__device__ __forceinline__ void norm_pre(const NormCtx& k, int n, int y, int x, int c0, float (&xv)[8], float (&pre)[8]) {
+  load8(k.x + pix_off(n, y, x, k.h, k.w, k.c, k.x_pad) + c0, xv);
+  if (k.drop_mask) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] *= k.drop_mask[static_cast<int64_t>(n) * k.c + c0 + j];
+  }
+  if (k.scale) {
+    const int64_t so = static_cast<int64_t>(k.groups > 1 ? n : 0) * k.c + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[j] = k.scale[so + j] * xv[j] + k.shift[so + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[j] = xv[j];
+  }
+  if (k.res) {
+    float rv[8];
+    load8(k.res + pix_off(n, y, x, k.h, k.w, k.c, k.res_pad) + c0, rv);
+    if (k.res_scale) {
+      const int64_t ro = static_cast<int64_t>(k.res_groups > 1 ? n : 0) * k.c + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[j] += k.res_scale[ro + j] * rv[j] + k.res_shift[ro + j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[j] += rv[j];
+    }
+  }
+}
+
+__global__ void norm_apply_kernel(pcgan_norm_apply_args a) {
+  NormCtx k{reinterpret_cast<const __nv_bfloat16*>(a.x), a.x_pad, reinterpret_cast<const __nv_bfloat16*>(a.res), a.res_pad,
+            a.scale, a.shift, a.groups, a.res_scale, a.res_shift, a.res_groups, a.drop_mask, a.n, a.h, a.w, a.c};
+  const int cv = a.c >> 3;
+  const int hp = a.h + 2 * a.y_pad, wp = a.w + 2 * a.y_pad;
+  const int64_t total = static_cast<int64_t>(a.n) * hp * wp * cv;
+  __nv_bfloat16* yout = reinterpret_cast<__nv_bfloat16*>(a.y);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t p = i / cv;
+    const int px = static_cast<int>(p % wp); p /= wp;
+    const int py = static_cast<int>(p % hp);
+    const int n = static_cast<int>(p / hp);
+    int y = py - a.y_pad, x = px - a.y_pad;
+    __nv_bfloat16* d = yout + ((static_cast<int64_t>(n) * hp + py) * wp + px) * a.c + c0;
+    const bool halo = y < 0 || y >= a.h || x < 0 || x >= a.w;
+    if (halo && a.y_halo == PCGAN_HALO_ZERO) {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    y = reflect_idx(y, a.h);
+    x = reflect_idx(x, a.w);
+    float xv[8], pre[8];
+    norm_pre(k, n, y, x, c0, xv, pre);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[j] = apply_act(pre[j], a.act, a.act_slope);
+    store8(d, pre);
+  }
+}
+
+// ------------------------------------------------------------------ halo fold
+__global__ void halo_fold_kernel(pcgan_fold_args a) {
+  const int cv = a.c >> 3;
+  const int64_t total = static_cast<int64_t>(a.n) * a.h * a.w * cv;
+  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(a.gpad);
+  const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(a.add);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const int p = a.g_pad;
+  const int hp = a.h + 2 * p, wp = a.w + 2 * p;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % a.w); q /= a.w;
+    const int y = static_cast<int>(q % a.h);
+    const int n = static_cast<int>(q / a.h);
+    // padded rows / cols that mirror onto (y, x)
+    int ys[3], xs[3], ny = 1, nx = 1;
+    ys[0] = y + p; xs[0] = x + p;
+    if (a.halo == PCGAN_HALO_REFLECT) {
+      if (y >= 1 && y <= p) ys[ny++] = p - y;
+      if (y <= a.h - 2 && y >= a.h - 1 - p) ys[ny++] = p + 2 * (a.h - 1) - y;
+      if (x >= 1 && x <= p) xs[nx++] = p - x;
+      if (x <= a.w - 2 && x >= a.w - 1 - p) xs[nx++] = p + 2 * (a.w - 1) - x;
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nx; ++ix) {
+        float v[8];
+        load8(g + ((static_cast<int64_t>(n) * hp + ys[iy]) * wp + xs[ix]) * a.c + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    if (add) {
+      float v[8];
+      load8(add + pix_off(n, y, x, a.h, a.w, a.c, a.add_pad) + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    store8(out + pix_off(n, y, x, a.h, a.w, a.c, a.out_pad) + c0, acc);
+  }
+}
+
+// -------------------------------------------------------------- norm backward
+__device__ __forceinline__ void norm_bwd_g(const pcgan_norm_bwd_args& a, const NormCtx& k, int n, int y, int x, int c0,
+                                           float (&g)[8], float (&xhat)[8]) {
+  float xv[8], pre[8], dy[8];
+  norm_pre(k, n, y, x, c0, xv, pre);
+  load8(reinterpret_cast<const __nv_bfloat16*>(a.dy) + pix_off(n, y, x, a.h, a.w, a.c, a.dy_pad) + c0, dy);
+  const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float d = 1.f;
+    if (a.act == PCGAN_ACT_RELU) d = pre[j] > 0.f ? 1.f : 0.f;
+    else if (a.act == PCGAN_ACT_LRELU) d = pre[j] > 0.f ? 1.f : a.act_slope;
+    g[j] = dy[j] * d;
+    xhat[j] = a.mean ? (xv[j] - a.mean[so + j]) * a.rstd[so + j] : 0.f;
+  }
+}
+
+__global__ void norm_bwd_reduce_kernel(pcgan_norm_bwd_args a, int pix_per_block) {
+  NormCtx k{reinterpret_cast<const __nv_bfloat16*>(a.x), a.x_pad, reinterpret_cast<const __nv_bfloat16*>(a.res), a.res_pad,
+            a.scale, a.shift, a.groups, a.res_scale, a.res_shift, a.res_groups, a.drop_mask, a.n, a.h, a.w, a.c};
+  __shared__ float red[kThreads * 16];
+  const int cv = a.c >> 3;             // power of two, <= 256
+  const int lanes = kThreads / cv;     // pixel lanes per block
+  const int myc = threadIdx.x % cv, myl = threadIdx.x / cv;
+  const int n = blockIdx.y;
+  const int hw = a.h * a.w;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int p = p0 + myl; p < p1; p += lanes) {
+    float g[8], xh[8];
+    norm_bwd_g(a, k, n, p / a.w, p % a.w, myc << 3, g, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] += g[j] * xh[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  __syncthreads();
+  // threads [0, cv*16): one (channel-vector, slot) each, summed over the pixel lanes
+  for (int t = threadIdx.x; t < cv * 16; t += kThreads) {
+    const int c = t / 16, slot = t % 16;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(l * cv + c) * 16 + slot];
+    const int ch = (c << 3) + (slot & 7);
+    const int64_t o = (static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + ch) * 2 + (slot >> 3);
+    atomicAdd(a.sums + o, s);
+  }
+}
+
+__global__ void norm_bwd_apply_kernel(pcgan_norm_bwd_args a) {
+  NormCtx k{reinterpret_cast<const __nv_bfloat16*>(a.x), a.x_pad, reinterpret_cast<const __nv_bfloat16*>(a.res), a.res_pad,
+            a.scale, a.shift, a.groups, a.res_scale, a.res_shift, a.res_groups, a.drop_mask, a.n, a.h, a.w, a.c};
+  const int cv = a.c >> 3;
+  const int64_t total = static_cast<int64_t>(a.n) * a.h * a.w * cv;
+  const float inv = a.count > 0.f ? 1.f / a.count : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % a.w); q /= a.w;
+    const int y = static_cast<int>(q % a.h);
+    const int n = static_cast<int>(q / a.h);
+    float g[8], xh[8];
+    norm_bwd_g(a, k, n, y, x, c0, g, xh);
+    if (a.dres) store8(reinterpret_cast<__nv_bfloat16*>(a.dres) + pix_off(n, y, x, a.h, a.w, a.c, a.dres_pad) + c0, g);
+    if (a.dx) {
+      const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+      float dx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = a.scale ? a.scale[so + j] : 1.f;
+        float v = g[j];
+        if (a.count > 0.f) v -= a.sums[(so + j) * 2] * inv + xh[j] * a.sums[(so + j) * 2 + 1] * inv;
+        v *= sc;
+        if (a.drop_mask) v *= a.drop_mask[static_cast<int64_t>(n) * a.c + c0 + j];
+        dx[j] = v;
+      }
+      store8(reinterpret_cast<__nv_bfloat16*>(a.dx) + pix_off(n, y, x, a.h, a.w, a.c, a.dx_pad) + c0, dx);
+    }
+  }
+}
+
+// -------------------------------------------------------------------- maxpool
+__global__ void maxpool_fwd_kernel(pcgan_maxpool_args a) {
+  const int ho = (a.h + 1) / 2, wo = (a.w + 1) / 2, cv = a.c >> 3;
+  const int64_t total = static_cast<int64_t>(a.n) * ho * wo * cv;
+  const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  __nv_bfloat16* yout = reinterpret_cast<__nv_bfloat16*>(a.y);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int ox = static_cast<int>(q % wo); q /= wo;
+    const int oy = static_cast<int>(q % ho);
+    const int n = static_cast<int>(q / ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 4; }
+    for (int r = 0; r < 3; ++r) {
+      const int y = 2 * oy - 1 + r;
+      if (y < 0 || y >= a.h) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int x = 2 * ox - 1 + s;
+        if (x < 0 || x >= a.w) continue;
+        float v[8];
+        load8(xin + pix_off(n, y, x, a.h, a.w, a.c, a.x_pad) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = r * 3 + s; }
+      }
+    }
+    store8(yout + pix_off(n, oy, ox, ho, wo, a.c, a.y_pad) + c0, best);
+    uint8_t* ip = a.idx + ((static_cast<int64_t>(n) * ho + oy) * wo + ox) * a.c + c0;
+    uint2 packed;
+    packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(ip) = packed;
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pad, const uint8_t* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dx, int dx_pad, int n_, int h, int w, int c) {
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2, cv = c >> 3;
+  const int64_t total = static_cast<int64_t>(n_) * h * w * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % w); q /= w;
+    const int y = static_cast<int>(q % h);
+    const int n = static_cast<int>(q / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = y / 2; oy <= (y + 1) / 2; ++oy) {
+      if (oy >= ho) continue;
+      const int r = y - (2 * oy - 1);
+      if (r < 0 || r > 2) continue;
+      for (int ox = x / 2; ox <= (x + 1) / 2; ++ox) {
+        if (ox >= wo) continue;
+        const int s = x - (2 * ox - 1);
+        if (s < 0 || s > 2) continue;
+        const int pos = r * 3 + s;
+        const uint2 packed = *reinterpret_cast<const uint2*>(idx + ((static_cast<int64_t>(n) * ho + oy) * wo + ox) * c + c0);
+        float g[8];
+        load8(dy + pix_off(n, oy, ox, ho, wo, c, dy_pad) + c0, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t word = j < 4 ? packed.x : packed.y;
+          if (static_cast<int>((word >> (8 * (j & 3))) & 0xff) == pos) acc[j] += g[j];
+        }
+      }
+    }
+    store8(dx + pix_off(n, y, x, h, w, c, dx_pad) + c0, acc);
+  }
+}
+
+// ----------------------------------------------------------------------- loss
+__global__ void loss_kernel(pcgan_loss_args a) {
+  __shared__ float red[kThreads / 32];
+  float acc = 0.f;
+  const float invn = 1.f / static_cast<float>(a.n);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = a.p[i];
+    const float t = a.per_sample > 0 ? a.target[i / a.per_sample] : a.target[i];
+    float l, g;
+    switch (a.kind) {
+      case PCGAN_LOSS_BCE: {
+        // nn.BCELoss: log terms clamped at -100; grad (p - t) / max(p (1 - p), 1e-12)
+        const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+        l = -(t * lp + (1.f - t) * lq);
+        g = (p - t) / fmaxf(p * (1.f - p), 1e-12f);
+        break;
+      }
+      case PCGAN_LOSS_MSE: l = (p - t) * (p - t); g = 2.f * (p - t); break;
+      case PCGAN_LOSS_L1: l = fabsf(p - t); g = p > t ? 1.f : (p < t ? -1.f : 0.f); break;
+      default: {  // PCGAN_LOSS_ELO_NLL, networks.py:479-481 with MAGIC_EPS = 1e-20
+        const float e = 1e-20f;
+        l = -(t * logf(p + e) + (1.f - t) * logf(1.f - p + e));
+        g = -(t / (p + e) - (1.f - t) / (1.f - p + e));
+        break;
+      }
+    }
+    acc += l;
+    if (a.grad) a.grad[i] = a.weight * g * invn;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0 && a.loss) atomicAdd(a.loss, a.weight * v * invn);
+  }
+}
+
+// ----------------------------------------------------------------------- adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, const float* lr_p, float b1, float b2, float eps,
+                            const float* step_p) {
+  const float lr = *lr_p, step = *step_p;
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  const float step_size = lr / bc1, rsq_bc2 = rsqrtf(bc2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * rsq_bc2 + eps);
+  }
+}
+
+}  // namespace pcgan
+
+using namespace pcgan;
+#define STREAM(s) static_cast<cudaStream_t>(s)
+
+extern "C" int pcgan_gather_cast_bf16(const float* src, const int32_t* idx, void* dst, int64_t n, pcgan_stream_t s) {
+  if (!src || !idx || !dst || n < 0) return fail(PCGAN_ERR_INVALID, "gather_cast: bad argument");
+  if (n == 0) return PCGAN_OK;
+  gather_cast_kernel<<<grid_for(n), kThreads, 0, STREAM(s)>>>(src, idx, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  PCGAN_LAUNCH_OK("gather_cast_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_scatter_f32(const float* src, const int32_t* idx, float* dst, int64_t n, int32_t accumulate,
+                                 pcgan_stream_t s) {
+  if (!src || !idx || !dst || n < 0) return fail(PCGAN_ERR_INVALID, "scatter: bad argument");
+  if (n == 0) return PCGAN_OK;
+  scatter_kernel<<<grid_for(n), kThreads, 0, STREAM(s)>>>(src, idx, dst, n, accumulate);
+  PCGAN_LAUNCH_OK("scatter_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t s) {
+  if (!a || !a->src || !a->dst) return fail(PCGAN_ERR_INVALID, "pack_nchw: null argument");
+  if (a->cd % 8 != 0 || a->cd < a->cs + (a->z ? 1 : 0)) return fail(PCGAN_ERR_INVALID, "pack_nchw: cd=%d must be a multiple of 8 holding %d channels", a->cd, a->cs + (a->z ? 1 : 0));
+  if (a->n < 1 || a->h < 1 || a->w < 1 || a->ho < 1 || a->wo < 1 || a->pad < 0) return fail(PCGAN_ERR_INVALID, "pack_nchw: bad geometry");
+  if (a->halo == PCGAN_HALO_REFLECT && (a->pad >= a->ho || a->pad >= a->wo)) return fail(PCGAN_ERR_INVALID, "pack_nchw: reflect pad too large");
+  if (a->tanh_out && (a->ho != a->h || a->wo != a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "pack_nchw: tanh_out with resize");
+  const int64_t total = static_cast<int64_t>(a->n) * (a->ho + 2 * a->pad) * (a->wo + 2 * a->pad);
+  pack_nchw_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("pack_nchw_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_unpack_resize_bwd(const pcgan_unpack_args* a, pcgan_stream_t s) {
+  if (!a || !a->g || !a->dst) return fail(PCGAN_ERR_INVALID, "unpack: null argument");
+  if (a->cd < 1 || a->cd > 8 || a->cd > a->c) return fail(PCGAN_ERR_UNSUPPORTED, "unpack: cd=%d (1..8, <= c)", a->cd);
+  const int64_t total = static_cast<int64_t>(a->n) * a->h * a->w;
+  unpack_resize_bwd_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("unpack_resize_bwd_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stream_t s) {
+  if (!a || !a->stats || a->groups < 1 || a->c < 1 || a->count <= 0.f) return fail(PCGAN_ERR_INVALID, "norm_finalize: bad argument");
+  norm_finalize_kernel<<<(a->c + 127) / 128, 128, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("norm_finalize_kernel");
+  return PCGAN_OK;
+}
+
+static int check_cvec(int c, const char* who) {
+  if (c < 8 || c % 8 != 0) return fail(PCGAN_ERR_UNSUPPORTED, "%s: channels=%d must be a multiple of 8", who, c);
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s) {
+  if (!a || !a->x || !a->y) return fail(PCGAN_ERR_INVALID, "norm_apply: null argument");
+  int rc = check_cvec(a->c, "norm_apply");
+  if (rc) return rc;
+  if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(PCGAN_ERR_INVALID, "norm_apply: scale and shift go together");
+  if (a->y_halo == PCGAN_HALO_REFLECT && (a->y_pad >= a->h || a->y_pad >= a->w)) return fail(PCGAN_ERR_INVALID, "norm_apply: reflect pad too large");
+  const int64_t total = static_cast<int64_t>(a->n) * (a->h + 2 * a->y_pad) * (a->w + 2 * a->y_pad) * (a->c / 8);
+  norm_apply_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("norm_apply_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_halo_fold(const pcgan_fold_args* a, pcgan_stream_t s) {
+  if (!a || !a->gpad || !a->out) return fail(PCGAN_ERR_INVALID, "halo_fold: null argument");
+  int rc = check_cvec(a->c, "halo_fold");
+  if (rc) return rc;
+  if (a->halo == PCGAN_HALO_REFLECT && (2 * a->g_pad + 1 > a->h || 2 * a->g_pad + 1 > a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "halo_fold: image smaller than 2*pad+1");
+  const int64_t total = static_cast<int64_t>(a->n) * a->h * a->w * (a->c / 8);
+  halo_fold_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("halo_fold_kernel");
+  return PCGAN_OK;
+}
+
+static int check_bwd(const pcgan_norm_bwd_args* a) {
+  if (!a || !a->dy || !a->x) return fail(PCGAN_ERR_INVALID, "norm_bwd: null argument");
+  int rc = check_cvec(a->c, "norm_bwd");
+  if (rc) return rc;
+  const int cv = a->c / 8;
+  if (cv > kThreads || (cv & (cv - 1)) != 0) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd: channels/8=%d must be a power of two <= %d", cv, kThreads);
+  if (a->count > 0.f && (!a->mean || !a->rstd || !a->sums)) return fail(PCGAN_ERR_INVALID, "norm_bwd: statistics missing");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_t s) {
+  int rc = check_bwd(a);
+  if (rc) return rc;
+  if (!a->sums) return fail(PCGAN_ERR_INVALID, "norm_bwd_reduce: sums is null");
+  const int hw = a->h * a->w;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  // about four waves of blocks over (pixel chunks, samples)
+  int chunks = (4 * sms + a->n - 1) / a->n;
+  if (chunks < 1) chunks = 1;
+  int ppb = (hw + chunks - 1) / chunks;
+  const int lanes = kThreads / (a->c / 8);
+  if (ppb < lanes * 4) ppb = lanes * 4;
+  chunks = (hw + ppb - 1) / ppb;
+  norm_bwd_reduce_kernel<<<dim3(chunks, a->n), kThreads, 0, STREAM(s)>>>(*a, ppb);
+  PCGAN_LAUNCH_OK("norm_bwd_reduce_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t s) {
+  int rc = check_bwd(a);
+  if (rc) return rc;
+  if (!a->dx && !a->dres) return fail(PCGAN_ERR_INVALID, "norm_bwd_apply: no output");
+  const int64_t total = static_cast<int64_t>(a->n) * a->h * a->w * (a->c / 8);
+  norm_bwd_apply_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("norm_bwd_apply_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_maxpool3x3s2_fwd(const pcgan_maxpool_args* a, pcgan_stream_t s) {
+  if (!a || !a->x || !a->y || !a->idx) return fail(PCGAN_ERR_INVALID, "maxpool: null argument");
+  int rc = check_cvec(a->c, "maxpool");
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(a->n) * ((a->h + 1) / 2) * ((a->w + 1) / 2) * (a->c / 8);
+  maxpool_fwd_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("maxpool_fwd_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint8_t* idx, void* dx, int32_t dx_pad,
+                                      int32_t n, int32_t h, int32_t w, int32_t c, pcgan_stream_t s) {
+  if (!dy || !idx || !dx) return fail(PCGAN_ERR_INVALID, "maxpool_bwd: null argument");
+  int rc = check_cvec(c, "maxpool_bwd");
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
+  maxpool_bwd_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_pad, idx,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dx), dx_pad, n, h, w, c);
+  PCGAN_LAUNCH_OK("maxpool_bwd_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_loss(const pcgan_loss_args* a, pcgan_stream_t s) {
+  if (!a || !a->p || !a->target || a->n < 1) return fail(PCGAN_ERR_INVALID, "loss: bad argument");
+  if (a->kind < PCGAN_LOSS_BCE || a->kind > PCGAN_LOSS_ELO_NLL) return fail(PCGAN_ERR_INVALID, "loss: bad kind");
+  loss_kernel<<<grid_for(a->n, kThreads, 2), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_LAUNCH_OK("loss_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1,
+                          float beta2, float eps, const float* step, pcgan_stream_t s) {
+  if (!p || !g || !m || !v || !lr || !step || n < 0) return fail(PCGAN_ERR_INVALID, "adam: bad argument");
+  if (n == 0) return PCGAN_OK;
+  adam_kernel<<<grid_for(n), kThreads, 0, STREAM(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step);
+  PCGAN_LAUNCH_OK("adam_kernel");
+  return PCGAN_OK;
+}

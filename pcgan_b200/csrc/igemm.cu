@@ -1,0 +1,572 @@
+// Implicit-GEMM convolution engine for sm_100a: TMA -> 128B-swizzled shared memory ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+//
+// One persistent, warp-specialised kernel, two operand arrangements:
+//   KMAJOR (forward / data-gradient): A = activation box [<=128 pixels][64 ch] per
+//     (tap, channel chunk), B = weights [block_n][64]; both K-major.
+//   WGRAD (weight-gradient): A = dY box [64 pixels][128 cout], B = X box
+//     [64 pixels][block_n cin]; both MN-major, K = pixels, split across CTAs.
+// Everything that distinguishes one convolution from another (padding mode, stride,
+// transposed phases, reflect halos, packed stems) is data in pcgan_igemm_desc.
+//
+// Warp roles (256 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
+// (MMA <-> epilogue), persistent tile loop with a static stride schedule.
+#include <cuda.h>
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pcgan {
+
+static constexpr int kStages = 4;
+static constexpr int kAStageBytes = 128 * 128;     // 128 rows x 128 B (or 2 MN-major boxes of 64x128 B)
+static constexpr int kBStageBytes = 256 * 128;     // 256 rows x 128 B (or 4 MN-major boxes)
+static constexpr int kBoxBytesMN = 64 * 128;       // one MN-major box: 64 K-rows x 128 B
+static constexpr int kTmemCols = 512;              // 2 accumulator stages x 256 fp32 columns
+static constexpr int kAccCols = 256;
+static constexpr int kNumThreads = 256;
+static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 4096 /*barriers, stats*/;
+
+struct DevParams {
+  int32_t kind, block_n, a_rows;
+  int32_t t_count[4];
+  int32_t a_base[4], a_step[4][4];
+  int32_t b_base[4], b_step[4][4];
+  int32_t n_tiles, m_tiles, ksplit, num_m_tiles, total_tiles;
+  int32_t num_taps, cchunks;
+  int32_t tap_off[PCGAN_MAX_TAPS][4];
+  int32_t tap_c0[PCGAN_MAX_TAPS];
+  int32_t tap_bk[PCGAN_MAX_TAPS];
+  int32_t box[4];
+  int32_t e_base[4], e_step[4][4], e_p1[4], e_p2[4];
+  pcgan_comp e_comp[4][3];
+  int32_t out_dtype, act;
+  float act_slope;
+  int32_t n_valid;
+  int64_t out_cstride;
+  int32_t stats_mode, stats_dim, stats_comp;
+  int32_t m_valid, wg_ncols;
+  int64_t ldo;
+  void* out;
+  const float* bias;
+  float* stats;
+};
+
+struct Digits {
+  int32_t t[4];
+};
+__device__ __forceinline__ Digits decompose(int32_t idx, const int32_t (&count)[4]) {
+  Digits d;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int32_t c = count[j];
+    d.t[j] = idx % c;
+    idx /= c;
+  }
+  return d;
+}
+__device__ __forceinline__ int32_t coord(const Digits& d, const int32_t (&base)[4], const int32_t (&step)[4][4],
+                                         int dim) {
+  return base[dim] + d.t[0] * step[0][dim] + d.t[1] * step[1][dim] + d.t[2] * step[2][dim] + d.t[3] * step[3][dim];
+}
+
+// Column sums over the 32 rows held by a warp (row = lane, v[c] = column c):
+// after the butterfly, lane l holds the sum of column l in v[0].  31 shuffles.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], uint32_t lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = upper ? v[i] : v[i + off];
+      float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const __grid_constant__ DevParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kAStageBytes;
+  uint8_t* tail = smem_b + kStages * kBStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(tail + 256);  // [256 channels][2]
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const bool wgrad = P.kind == PCGAN_IGEMM_WGRAD;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 128) {
+    for (int i = threadIdx.x - 128; i < 512; i += 128) s_stats[i] = 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int32_t k_chunks_fwd = P.num_taps * P.cchunks;
+  const int32_t total_kb = P.t_count[0] * P.t_count[1] * P.t_count[2] * P.t_count[3];  // WGRAD: pixel blocks
+  const int32_t kb_per_split = wgrad ? (total_kb + P.ksplit - 1) / P.ksplit : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        if (!wgrad) {
+          const int32_t mt = tile / P.n_tiles, nt = tile % P.n_tiles;
+          const Digits d = decompose(mt, P.t_count);
+          int32_t c[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
+          const uint32_t bytes = P.a_rows * 128 + P.block_n * 128;
+          for (int32_t tap = 0; tap < P.num_taps; ++tap) {
+            const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
+                          o3 = P.tap_off[tap][3];
+            const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
+            for (int32_t cc = 0; cc < P.cchunks; ++cc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              tma_load_5d(smem_a + stage * kAStageBytes, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0,
+                          c[1] + o1, c[2] + o2, c[3] + o3);
+              tma_load_5d(smem_b + stage * kBStageBytes, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0,
+                          0, 0);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          int32_t t = tile;
+          const int32_t ks = t % P.ksplit; t /= P.ksplit;
+          const int32_t nt = t % P.n_tiles; t /= P.n_tiles;
+          const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
+          const int32_t tap = t;
+          const int32_t kb0 = ks * kb_per_split;
+          const int32_t kb1 = min(kb0 + kb_per_split, total_kb);
+          const int32_t nb = P.block_n >> 6;
+          const uint32_t bytes = (2 + nb) * kBoxBytesMN;
+          const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2], o3 = P.tap_off[tap][3];
+          const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
+          for (int32_t kb = kb0; kb < kb1; ++kb) {
+            const Digits d = decompose(kb, P.t_count);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
+                          a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
+            const int32_t b0 = coord(d, P.b_base, P.b_step, 0) + o0, b1 = coord(d, P.b_base, P.b_step, 1) + o1,
+                          b2 = coord(d, P.b_base, P.b_step, 2) + o2, b3 = coord(d, P.b_base, P.b_step, 3) + o3;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_5d(smem_a + stage * kAStageBytes + j * kBoxBytesMN, &tma_a, &full_bar[stage],
+                          mt * 128 + j * 64, a0, a1, a2, a3);
+            for (int j = 0; j < nb; ++j)
+              tma_load_5d(smem_b + stage * kBStageBytes + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64,
+                          b0, b1, b2, b3);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
+      // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the swizzled row.
+      // MN-major: 64-element column groups one box (8192 B) apart, 8 K-rows = 1024 B; UMMA_K = 16 rows = 2048 B.
+      const uint32_t lbo = wgrad ? kBoxBytesMN : 16;
+      const uint32_t sbo = 1024;
+      const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        int32_t nk;
+        if (!wgrad) {
+          nk = k_chunks_fwd;
+        } else {
+          const int32_t ks = tile % P.ksplit;
+          const int32_t kb0 = ks * kb_per_split;
+          nk = max(min(kb0 + kb_per_split, total_kb) - kb0, 0);
+        }
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccCols;
+        for (int32_t kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kAStageBytes), lbo, sbo);
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kBStageBytes), lbo, sbo);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k)
+            umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
+          tcgen05_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const uint32_t q = warp & 3;
+    const uint32_t row = q * 32 + lane;
+    const uint32_t et = threadIdx.x - 128;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      bool valid;
+      int64_t off = 0;
+      int32_t group = 0;
+      int32_t nt, col_base = 0;
+      bool has_k = true;
+      if (!wgrad) {
+        const int32_t mt = tile / P.n_tiles;
+        nt = tile % P.n_tiles;
+        const Digits d = decompose(mt, P.t_count);
+        valid = row < static_cast<uint32_t>(P.a_rows);
+        uint32_t r = row;
+#pragma unroll
+        for (int dim = 0; dim < 4; ++dim) {
+          const int32_t bx = P.box[dim];
+          const int32_t i = r % bx;
+          r /= bx;
+          const int32_t gbase = coord(d, P.e_base, P.e_step, dim);
+          const int32_t g = gbase + i;
+          int32_t c0 = 0, rem = g, c1, c2 = 0;
+          if (P.e_p1[dim] > 0) { c0 = g / P.e_p1[dim]; rem = g % P.e_p1[dim]; }
+          if (P.e_p2[dim] > 0) { c1 = rem / P.e_p2[dim]; c2 = rem % P.e_p2[dim]; } else { c1 = rem; }
+          const pcgan_comp& k0 = P.e_comp[dim][0];
+          const pcgan_comp& k1 = P.e_comp[dim][1];
+          const pcgan_comp& k2 = P.e_comp[dim][2];
+          valid = valid && g >= 0 && c0 >= k0.lo && c0 < k0.hi && c1 >= k1.lo && c1 < k1.hi && c2 >= k2.lo && c2 < k2.hi;
+          off += (c0 - k0.lo) * k0.stride + (c1 - k1.lo) * k1.stride + (c2 - k2.lo) * k2.stride;
+          if (dim == P.stats_dim) {
+            // group of the tile = component of the tile's first row along this dim
+            const int32_t g0 = gbase;
+            int32_t s0 = 0, srem = g0, s1;
+            if (P.e_p1[dim] > 0) { s0 = g0 / P.e_p1[dim]; srem = g0 % P.e_p1[dim]; }
+            if (P.e_p2[dim] > 0) { s1 = srem / P.e_p2[dim]; } else { s1 = srem; }
+            group = P.stats_comp == 0 ? s0 : s1;
+          }
+        }
+      } else {
+        int32_t t = tile;
+        const int32_t ks = t % P.ksplit; t /= P.ksplit;
+        nt = t % P.n_tiles; t /= P.n_tiles;
+        const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
+        const int32_t tap = t;
+        const int32_t grow = mt * 128 + row;
+        valid = grow < P.m_valid;
+        off = static_cast<int64_t>(grow) * P.ldo + P.tap_bk[tap];
+        col_base = 0;
+        has_k = ks * kb_per_split < total_kb;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
+      const int32_t ncol_limit = wgrad ? min(P.wg_ncols - nt * P.block_n, P.block_n) : min(P.n_valid - nt * P.block_n, P.block_n);
+      for (int32_t c0 = 0; c0 < P.block_n; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + c0, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        const int32_t ncols = min(ncol_limit - c0, 32);  // valid columns in this chunk (may be <= 0)
+        const int32_t gcol = nt * P.block_n + c0;        // first global column of the chunk
+        if (wgrad) {
+          if (valid && has_k && ncols > 0) {
+            float* o = reinterpret_cast<float*>(P.out) + off + gcol;
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3])
+                             : "memory");
+            } else {
+              for (int i = 0; i < ncols; ++i) atomicAdd(o + i, v[i]);
+            }
+          }
+          continue;
+        }
+        if (P.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) v[i] += __ldg(P.bias + gcol + i);
+        }
+        if (P.stats_mode != PCGAN_STATS_NONE && ncols > 0) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = valid ? v[i] : 0.f;
+            s1[i] = x;
+            s2[i] = x * x;
+          }
+          const float cs1 = warp_transpose_sum(s1, lane);
+          const float cs2 = warp_transpose_sum(s2, lane);
+          if (static_cast<int32_t>(lane) < ncols) {
+            atomicAdd(&s_stats[(c0 + lane) * 2 + 0], cs1);
+            atomicAdd(&s_stats[(c0 + lane) * 2 + 1], cs2);
+          }
+        }
+        if (valid && ncols > 0) {
+          if (P.act != PCGAN_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.act_slope);
+          }
+          if (P.out_dtype == PCGAN_DT_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + off + gcol * P.out_cstride;
+            if (P.out_cstride == 1 && ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+                w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+                w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                o4[i] = w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols) o[i * P.out_cstride] = __float2bfloat16(v[i]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(P.out) + off + gcol * P.out_cstride;
+            if (P.out_cstride == 1 && ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols) o[i * P.out_cstride] = v[i];
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (!wgrad && P.stats_mode != PCGAN_STATS_NONE) {
+        named_bar_sync(1, 128);
+        float* gs = P.stats + static_cast<int64_t>(group) * P.n_valid * 2;
+        for (int32_t i = et; i < P.block_n * 2; i += 128) {
+          const int32_t ch = nt * P.block_n + (i >> 1);
+          const float s = s_stats[i];
+          if (ch < P.n_valid && s != 0.f) atomicAdd(gs + ch * 2 + (i & 1), s);
+          s_stats[i] = 0.f;
+        }
+        named_bar_sync(1, 128);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(PCGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5];
+  for (int i = 0; i < 5; ++i) {
+    dims[i] = t.dims[i];
+    box[i] = t.box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < 4; ++i) strides[i] = t.strides[i + 1];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PCGAN_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): dims=[%llu,%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu,%llu] "
+                "box=[%u,%u,%u,%u,%u] base=%p",
+                (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], (unsigned long long)dims[4], (unsigned long long)strides[0],
+                (unsigned long long)strides[1], (unsigned long long)strides[2], (unsigned long long)strides[3],
+                box[0], box[1], box[2], box[3], box[4], base);
+  return PCGAN_OK;
+}
+
+}  // namespace pcgan
+
+struct pcgan_igemm_plan {
+  pcgan_igemm_desc desc;
+  pcgan::DevParams dev;
+  std::mutex mu;
+  const void* cached_a = nullptr;
+  const void* cached_b = nullptr;
+  CUtensorMap map_a, map_b;
+  int grid = 0;
+};
+
+using namespace pcgan;
+
+static int validate_tmap(const pcgan_tmap& t, const char* name) {
+  if (t.box[0] != 64) return fail(PCGAN_ERR_INVALID, "%s.box[0] must be 64 (one 128-byte swizzle row)", name);
+  for (int i = 0; i < 5; ++i) {
+    if (t.dims[i] == 0 || t.dims[i] > (1ull << 32)) return fail(PCGAN_ERR_INVALID, "%s.dims[%d] out of range", name, i);
+    if (t.box[i] == 0 || t.box[i] > 256) return fail(PCGAN_ERR_INVALID, "%s.box[%d] out of range", name, i);
+    if (i > 0 && (t.strides[i] % 16 != 0 || t.strides[i] == 0 || t.strides[i] >= (1ull << 40)))
+      return fail(PCGAN_ERR_INVALID, "%s.strides[%d]=%llu must be a non-zero multiple of 16 bytes", name, i,
+                  (unsigned long long)t.strides[i]);
+  }
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_plan** out) {
+  if (!d || !out) return fail(PCGAN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->kind != PCGAN_IGEMM_KMAJOR && d->kind != PCGAN_IGEMM_WGRAD) return fail(PCGAN_ERR_INVALID, "bad kind");
+  const bool wg = d->kind == PCGAN_IGEMM_WGRAD;
+  if (d->block_n < 16 || d->block_n > 256 || d->block_n % 16 != 0)
+    return fail(PCGAN_ERR_UNSUPPORTED, "block_n=%d must be a multiple of 16 in [16,256]", d->block_n);
+  if (wg && d->block_n % 64 != 0) return fail(PCGAN_ERR_UNSUPPORTED, "WGRAD block_n=%d must be a multiple of 64", d->block_n);
+  int rc;
+  if ((rc = validate_tmap(d->a, "a")) != PCGAN_OK) return rc;
+  if ((rc = validate_tmap(d->b, "b")) != PCGAN_OK) return rc;
+  const int64_t a_rows = (int64_t)d->a.box[1] * d->a.box[2] * d->a.box[3] * d->a.box[4];
+  const int64_t b_rows = (int64_t)d->b.box[1] * d->b.box[2] * d->b.box[3] * d->b.box[4];
+  if (!wg) {
+    if (a_rows < 1 || a_rows > 128) return fail(PCGAN_ERR_INVALID, "A box has %lld rows (1..128)", (long long)a_rows);
+    if (b_rows != d->block_n) return fail(PCGAN_ERR_INVALID, "B box rows %lld != block_n %d", (long long)b_rows, d->block_n);
+    if (d->ksplit != 1) return fail(PCGAN_ERR_INVALID, "KMAJOR needs ksplit == 1");
+    if (d->n_valid < 1 || d->n_valid > d->n_tiles * d->block_n) return fail(PCGAN_ERR_INVALID, "n_valid out of range");
+    if (d->out_dtype != PCGAN_DT_BF16 && d->out_dtype != PCGAN_DT_F32) return fail(PCGAN_ERR_INVALID, "bad out_dtype");
+    if (d->stats_mode != PCGAN_STATS_NONE && d->stats_dim >= 4) return fail(PCGAN_ERR_INVALID, "bad stats_dim");
+  } else {
+    if (a_rows != 64 || b_rows != 64) return fail(PCGAN_ERR_INVALID, "WGRAD boxes must hold exactly 64 pixels (got %lld, %lld)", (long long)a_rows, (long long)b_rows);
+    if (d->ksplit < 1 || d->m_tiles < 1) return fail(PCGAN_ERR_INVALID, "WGRAD needs ksplit >= 1 and m_tiles >= 1");
+    if (d->m_valid < 1 || d->m_valid > d->m_tiles * 128) return fail(PCGAN_ERR_INVALID, "m_valid out of range");
+    if (d->wg_ncols < 1 || d->wg_ncols > d->n_tiles * d->block_n) return fail(PCGAN_ERR_INVALID, "wg_ncols out of range");
+    if (d->ldo < 1) return fail(PCGAN_ERR_INVALID, "ldo must be positive");
+  }
+  if (d->num_taps < 1 || d->num_taps > PCGAN_MAX_TAPS) return fail(PCGAN_ERR_UNSUPPORTED, "num_taps=%d (1..%d)", d->num_taps, PCGAN_MAX_TAPS);
+  if (d->cchunks < 1 || d->n_tiles < 1) return fail(PCGAN_ERR_INVALID, "cchunks / n_tiles must be >= 1");
+  int64_t tiles = 1;
+  for (int j = 0; j < 4; ++j) {
+    if (d->t_count[j] < 1) return fail(PCGAN_ERR_INVALID, "t_count[%d] must be >= 1", j);
+    tiles *= d->t_count[j];
+  }
+  int64_t total = wg ? (int64_t)d->num_taps * d->m_tiles * d->n_tiles * d->ksplit : tiles * d->n_tiles;
+  if (total < 1 || total > 0x7fffffff) return fail(PCGAN_ERR_INVALID, "tile count out of range");
+
+  pcgan_igemm_plan* p = new pcgan_igemm_plan();
+  p->desc = *d;
+  DevParams& v = p->dev;
+  memset(&v, 0, sizeof(v));
+  v.kind = d->kind; v.block_n = d->block_n; v.a_rows = (int32_t)a_rows;
+  memcpy(v.t_count, d->t_count, sizeof(v.t_count));
+  memcpy(v.a_base, d->a_base, sizeof(v.a_base)); memcpy(v.a_step, d->a_step, sizeof(v.a_step));
+  memcpy(v.b_base, d->b_base, sizeof(v.b_base)); memcpy(v.b_step, d->b_step, sizeof(v.b_step));
+  v.n_tiles = d->n_tiles; v.m_tiles = wg ? d->m_tiles : 1; v.ksplit = wg ? d->ksplit : 1;
+  v.num_m_tiles = (int32_t)tiles; v.total_tiles = (int32_t)total;
+  v.num_taps = d->num_taps; v.cchunks = d->cchunks;
+  memcpy(v.tap_off, d->tap_off, sizeof(v.tap_off)); memcpy(v.tap_c0, d->tap_c0, sizeof(v.tap_c0));
+  memcpy(v.tap_bk, d->tap_bk, sizeof(v.tap_bk));
+  for (int i = 0; i < 4; ++i) v.box[i] = d->a.box[i + 1];
+  memcpy(v.e_base, d->e_base, sizeof(v.e_base)); memcpy(v.e_step, d->e_step, sizeof(v.e_step));
+  memcpy(v.e_p1, d->e_p1, sizeof(v.e_p1)); memcpy(v.e_p2, d->e_p2, sizeof(v.e_p2));
+  memcpy(v.e_comp, d->e_comp, sizeof(v.e_comp));
+  v.out_dtype = d->out_dtype; v.act = d->act; v.act_slope = d->act_slope; v.n_valid = d->n_valid;
+  v.out_cstride = d->out_cstride; v.stats_mode = d->stats_mode; v.stats_dim = d->stats_dim; v.stats_comp = d->stats_comp;
+  v.m_valid = d->m_valid; v.wg_ncols = d->wg_ncols; v.ldo = d->ldo;
+  *out = p;
+  return PCGAN_OK;
+}
+
+extern "C" void pcgan_igemm_plan_destroy(pcgan_igemm_plan* p) { delete p; }
+
+extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b, void* out, const float* bias,
+                               float* stats, pcgan_stream_t stream) {
+  if (!p || !a || !b || !out) return fail(PCGAN_ERR_INVALID, "null argument");
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
+    return fail(PCGAN_ERR_INVALID, "operand pointers must be 16-byte aligned");
+  if (p->desc.kind == PCGAN_IGEMM_KMAJOR && p->desc.stats_mode != PCGAN_STATS_NONE && !stats)
+    return fail(PCGAN_ERR_INVALID, "stats_mode set but stats pointer is null");
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, []() {
+    attr_err = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  CUtensorMap ma, mb;
+  DevParams dev;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (p->cached_a != a) {
+      int rc = encode_tmap(&p->map_a, p->desc.a, a);
+      if (rc != PCGAN_OK) return rc;
+      p->cached_a = a;
+    }
+    if (p->cached_b != b) {
+      int rc = encode_tmap(&p->map_b, p->desc.b, b);
+      if (rc != PCGAN_OK) return rc;
+      p->cached_b = b;
+    }
+    if (p->grid == 0) {
+      int sms = sm_count();
+      if (sms <= 0) return fail(PCGAN_ERR_CUDA, "cannot query SM count");
+      p->grid = p->dev.total_tiles < sms ? p->dev.total_tiles : sms;
+    }
+    ma = p->map_a; mb = p->map_b; dev = p->dev;
+  }
+  dev.out = out; dev.bias = bias; dev.stats = stats;
+  igemm_kernel<<<p->grid, kNumThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, dev);
+  PCGAN_LAUNCH_OK("igemm_kernel");
+  return PCGAN_OK;
+}

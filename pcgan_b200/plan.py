@@ -1,0 +1,549 @@
+"""Host-side planner: turns a convolution (forward, data-gradient, weight-gradient,
+transposed) over padded NHWC bf16 buffers into pcgan_igemm_desc data for the
+tcgen05 implicit-GEMM kernel (include/pcgan_kernels.h).
+
+Nothing here touches the GPU: a plan is pure data (TMA views, tap tables, output
+maps, weight index maps), so it is validated on the CPU by the emulator in
+oracle/igemm_emulator.py against torch.nn.functional convolutions.
+
+Geometry vocabulary
+  Geom(n, h, w, c, pad): a padded NHWC buffer [n][h+2*pad][w+2*pad][c]; "interior"
+  is the h x w image, the halo is written by the producer kernel (zeros or
+  reflection).  All element offsets below are in bf16 elements.
+
+Reference semantics implemented (phymhan/pc-gan):
+  nn.Conv2d / nn.ConvTranspose2d as used in models/networks.py:578-605, :621-648,
+  :747-775, :1014-1027 and models/resnet.py:20-28,134.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+MAX_TAPS = L.MAX_TAPS
+
+
+@dataclass(frozen=True)
+class Geom:
+    n: int
+    h: int
+    w: int
+    c: int
+    pad: int
+
+    @property
+    def hp(self):
+        return self.h + 2 * self.pad
+
+    @property
+    def wp(self):
+        return self.w + 2 * self.pad
+
+    @property
+    def numel(self):
+        return self.n * self.hp * self.wp * self.c
+
+    def off(self, n, y, x):
+        """element offset of interior pixel (n, y, x), channel 0"""
+        return ((n * self.hp + y + self.pad) * self.wp + x + self.pad) * self.c
+
+
+SLACK = 512  # elements appended to every activation buffer (packed-row windows read past the end)
+
+
+@dataclass
+class OutMap:
+    """Where output pixel (n, y, x), channel ch lands: base + n*sn + y*sy + x*sx + ch*sc (elements)."""
+    base: int
+    sn: int
+    sy: int
+    sx: int
+    sc: int = 1
+    dtype: int = L.DT_BF16
+
+    @staticmethod
+    def nhwc(g: Geom, dtype=L.DT_BF16, ystep=1, xstep=1, y0=0, x0=0):
+        """interior of a padded NHWC buffer; (ystep, y0) write every ystep-th row starting at y0 (sub-pixel phases)"""
+        return OutMap(base=g.off(0, y0, x0), sn=g.hp * g.wp * g.c, sy=g.wp * g.c * ystep, sx=g.c * xstep, sc=1, dtype=dtype)
+
+    @staticmethod
+    def nchw(n, c, h, w, dtype=L.DT_F32):
+        return OutMap(base=0, sn=c * h * w, sy=w, sx=1, sc=h * w, dtype=dtype)
+
+
+@dataclass
+class IgemmSpec:
+    kind: int = L.IGEMM_KMAJOR
+    block_n: int = 64
+    a_dims: List[int] = field(default_factory=lambda: [1] * 5)
+    a_strides: List[int] = field(default_factory=lambda: [0] * 5)  # bytes
+    a_box: List[int] = field(default_factory=lambda: [64, 1, 1, 1, 1])
+    b_dims: List[int] = field(default_factory=lambda: [1] * 5)
+    b_strides: List[int] = field(default_factory=lambda: [0] * 5)
+    b_box: List[int] = field(default_factory=lambda: [64, 1, 1, 1, 1])
+    t_count: List[int] = field(default_factory=lambda: [1] * 4)
+    a_base: List[int] = field(default_factory=lambda: [0] * 4)
+    a_step: List[List[int]] = field(default_factory=lambda: [[0] * 4 for _ in range(4)])
+    b_base: List[int] = field(default_factory=lambda: [0] * 4)
+    b_step: List[List[int]] = field(default_factory=lambda: [[0] * 4 for _ in range(4)])
+    n_tiles: int = 1
+    m_tiles: int = 1
+    ksplit: int = 1
+    cchunks: int = 1
+    tap_off: List[List[int]] = field(default_factory=list)
+    tap_c0: List[int] = field(default_factory=list)
+    tap_bk: List[int] = field(default_factory=list)
+    e_base: List[int] = field(default_factory=lambda: [0] * 4)
+    e_step: List[List[int]] = field(default_factory=lambda: [[0] * 4 for _ in range(4)])
+    e_p1: List[int] = field(default_factory=lambda: [0] * 4)
+    e_p2: List[int] = field(default_factory=lambda: [0] * 4)
+    # e_comp[d][k] = (lo, hi, stride)
+    e_comp: List[List[Tuple[int, int, int]]] = field(
+        default_factory=lambda: [[(0, 1, 0), (0, 1 << 30, 0), (0, 1, 0)] for _ in range(4)])
+    out_dtype: int = L.DT_BF16
+    act: int = L.ACT_NONE
+    act_slope: float = 0.0
+    n_valid: int = 1
+    out_cstride: int = 1
+    stats_mode: int = L.STATS_NONE
+    stats_dim: int = -1
+    stats_comp: int = 1
+    m_valid: int = 1
+    wg_ncols: int = 1
+    ldo: int = 1
+    # host-side extras (not part of the C struct)
+    a_elem_offset: int = 0     # added to the A base pointer (elements)
+    b_elem_offset: int = 0
+    out_elem_offset: int = 0   # added to the output base pointer (elements)
+    b_rows: int = 0            # packed weight matrix shape [b_rows][b_k] (KMAJOR) / wgrad output [m][ldo]
+    b_k: int = 0
+    flops: int = 0             # 2*MACs actually issued (incl. padding waste), for bookkeeping
+    note: str = ""
+
+    @property
+    def num_taps(self):
+        return len(self.tap_off)
+
+    def to_desc(self) -> L.IgemmDesc:
+        d = L.IgemmDesc()
+        d.kind, d.block_n = self.kind, self.block_n
+        for i in range(5):
+            d.a.dims[i], d.a.strides[i], d.a.box[i] = self.a_dims[i], self.a_strides[i], self.a_box[i]
+            d.b.dims[i], d.b.strides[i], d.b.box[i] = self.b_dims[i], self.b_strides[i], self.b_box[i]
+        for j in range(4):
+            d.t_count[j] = self.t_count[j]
+            d.a_base[j], d.b_base[j], d.e_base[j] = self.a_base[j], self.b_base[j], self.e_base[j]
+            d.e_p1[j], d.e_p2[j] = self.e_p1[j], self.e_p2[j]
+            for k in range(4):
+                d.a_step[j][k], d.b_step[j][k], d.e_step[j][k] = self.a_step[j][k], self.b_step[j][k], self.e_step[j][k]
+            for k in range(3):
+                lo, hi, st = self.e_comp[j][k]
+                d.e_comp[j][k].lo, d.e_comp[j][k].hi, d.e_comp[j][k].stride = lo, hi, st
+        d.n_tiles, d.m_tiles, d.ksplit = self.n_tiles, self.m_tiles, self.ksplit
+        if self.num_taps > MAX_TAPS:
+            raise ValueError("too many taps: %d" % self.num_taps)
+        d.num_taps, d.cchunks = self.num_taps, self.cchunks
+        for t in range(self.num_taps):
+            for k in range(4):
+                d.tap_off[t][k] = self.tap_off[t][k]
+            d.tap_c0[t], d.tap_bk[t] = self.tap_c0[t], self.tap_bk[t]
+        d.out_dtype, d.act, d.act_slope, d.n_valid = self.out_dtype, self.act, self.act_slope, self.n_valid
+        d.out_cstride = self.out_cstride
+        d.stats_mode, d.stats_dim, d.stats_comp = self.stats_mode, self.stats_dim, self.stats_comp
+        d.m_valid, d.wg_ncols, d.ldo = self.m_valid, self.wg_ncols, self.ldo
+        return d
+
+
+def _ceil(a, b):
+    return -(-a // b)
+
+
+def _block_n(cout):
+    """UMMA N for `cout` output columns: multiple of 16, <= 256, minimising padded columns."""
+    if cout <= 256:
+        return max(16, _ceil(cout, 16) * 16)
+    best = None
+    for bn in (256, 192, 128):
+        waste = _ceil(cout, bn) * bn - cout
+        if best is None or waste < best[0]:
+            best = (waste, bn)
+    return best[1]
+
+
+ANY = (0, 1 << 30, 0)
+ONE = (0, 1, 0)
+
+
+def _set_weights_tmap(s: IgemmSpec, rows: int, k: int):
+    s.b_dims = [k, rows, 1, 1, 1]
+    s.b_strides = [0, k * 2, k * 2 * max(rows, 1), k * 2 * max(rows, 1), k * 2 * max(rows, 1)]
+    s.b_box = [64, s.block_n, 1, 1, 1]
+    s.b_rows, s.b_k = rows, k
+
+
+# ------------------------------------------------------------------------------------------
+# KMAJOR plans: forward / data-gradient
+# ------------------------------------------------------------------------------------------
+def _choose_box(wo, ho, n, single_image):
+    bw = min(wo, 128)
+    bh = max(1, min(ho, 128 // bw))
+    bn = 1
+    if not single_image and bh == ho and bw == wo:
+        bn = max(1, min(n, 128 // (bw * bh)))
+    return bw, bh, bn
+
+
+def plan_box(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, ho: int, wo: int, stride: int,
+             out: OutMap, *, act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False,
+             note="") -> IgemmSpec:
+    """Generic "box" plan.  Output pixel (n, y, x) = sum over taps (dy, dx, kidx) and channels of
+    Xpadded[n][stride*y + dy][stride*x + dx][:] . Wpacked[:, kidx*cin : (kidx+1)*cin]   (dy, dx >= 0 are
+    coordinates in the PADDED buffer).  Requires cin % 64 == 0 and xg.c == cin.
+    stride 1 uses a 4-D view (c, x, y, n); stride 2 a 5-D phase view (c, px, X, py, Y*n).
+    """
+    assert xg.c == cin and cin % 64 == 0, (xg, cin)
+    assert stride in (1, 2)
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
+    s.block_n = _block_n(cout)
+    s.n_tiles = _ceil(cout, s.block_n)
+    s.n_valid = cout
+    s.cchunks = cin // 64
+    C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
+    bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride == 2)
+    tx, ty, tn = _ceil(wo, bw), _ceil(ho, bh), _ceil(N, bn)
+    s.t_count = [tx, ty, tn, 1]
+    if stride == 1:
+        s.a_dims = [C, Wp, Hp, N, 1]
+        s.a_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
+        s.a_box = [64, bw, bh, bn, 1]
+        s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
+        for (dy, dx, kidx) in taps:
+            s.tap_off.append([dx, dy, 0, 0])
+            s.tap_c0.append(0)
+            s.tap_bk.append(kidx * cin)
+        # epilogue: box-local dims are (x, y, n, -)
+        s.e_step[0][0], s.e_step[1][1], s.e_step[2][2] = bw, bh, bn
+        s.e_comp = [[ONE, (0, wo, out.sx), ONE], [ONE, (0, ho, out.sy), ONE], [ONE, (0, N, out.sn), ONE], [ONE, ANY, ONE]]
+        if stats:
+            s.stats_mode = L.STATS_ON
+            s.stats_dim, s.stats_comp = (2, 1) if per_sample_stats else (-1, 1)
+    else:
+        assert Hp % 2 == 0 and Wp % 2 == 0, "stride-2 phase view needs even padded extents"
+        s.a_dims = [C, 2, Wp // 2, 2, (Hp // 2) * N]
+        s.a_strides = [0, C * 2, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2]
+        s.a_box = [64, 1, bw, 1, bh]
+        # outer dims: d0 = px, d1 = X, d2 = py, d3 = Y (+ n * Hp/2)
+        s.a_step[0][1] = bw
+        s.a_step[1][3] = bh
+        s.a_step[2][3] = Hp // 2
+        for (dy, dx, kidx) in taps:
+            s.tap_off.append([dx % 2, dx // 2, dy % 2, dy // 2])
+            s.tap_c0.append(0)
+            s.tap_bk.append(kidx * cin)
+        period = ty * bh
+        s.e_step[0][1] = bw
+        s.e_step[1][3] = bh
+        s.e_step[2][3] = period
+        s.e_p1[3] = period
+        s.e_comp = [[ONE, ANY, ONE], [ONE, (0, wo, out.sx), ONE], [ONE, ANY, ONE], [(0, N, out.sn), (0, ho, out.sy), ONE]]
+        if stats:
+            s.stats_mode = L.STATS_ON
+            s.stats_dim, s.stats_comp = (3, 0) if per_sample_stats else (-1, 1)
+    ktot = (max(k for _, _, k in taps) + 1) * cin
+    _set_weights_tmap(s, cout, ktot)
+    s.out_dtype, s.out_cstride, s.out_elem_offset = out.dtype, out.sc, out.base
+    s.act, s.act_slope = act, act_slope
+    s.flops = 2 * tx * ty * tn * 128 * s.n_tiles * s.block_n * len(taps) * cin
+    return s
+
+
+def plan_flat(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, out: OutMap,
+              yr: Tuple[int, int], xr: Tuple[int, int], *, act=L.ACT_NONE, act_slope=0.0, stats=False,
+              note="") -> IgemmSpec:
+    """"Flat" plan over the flattened padded grid of xg: for every padded position q = (n, Y, X)
+    out(q) = sum over taps (dy, dx, kidx) of Xpadded[q + dy*Wp + dx] . W[:, kidx*cin:...]   (dy, dx may be
+    negative; rows wrap into neighbouring rows/images, which is harmless when the wrapped reads hit a zero
+    halo or the wrapped outputs are masked).  Only positions with yr[0] <= Y < yr[1], xr[0] <= X < xr[1] are
+    stored, at out(n, Y - yr[0], X - xr[0]).  Statistics are per channel over all stored rows (batch norm)."""
+    assert xg.c == cin and cin % 64 == 0
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
+    s.block_n = _block_n(cout)
+    s.n_tiles = _ceil(cout, s.block_n)
+    s.n_valid = cout
+    s.cchunks = cin // 64
+    C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
+    P = N * Hp * Wp
+    s.a_dims = [C, P, 1, 1, 1]
+    s.a_strides = [0, C * 2, P * C * 2, P * C * 2, P * C * 2]
+    s.a_box = [64, 128, 1, 1, 1]
+    # only tiles that intersect stored rows: positions from first valid to last valid
+    q_lo = yr[0] * Wp + xr[0]
+    q_hi = (N - 1) * Hp * Wp + (yr[1] - 1) * Wp + xr[1]
+    first = q_lo // 128
+    tiles = _ceil(q_hi, 128) - first
+    s.t_count = [tiles, 1, 1, 1]
+    s.a_base[0] = first * 128
+    s.a_step[0][0] = 128
+    for (dy, dx, kidx) in taps:
+        s.tap_off.append([dy * Wp + dx, 0, 0, 0])
+        s.tap_c0.append(0)
+        s.tap_bk.append(kidx * cin)
+    s.e_base[0] = first * 128
+    s.e_step[0][0] = 128
+    s.e_p1[0], s.e_p2[0] = Hp * Wp, Wp
+    s.e_comp = [[(0, N, out.sn), (yr[0], yr[1], out.sy), (xr[0], xr[1], out.sx)], [ONE, ANY, ONE], [ONE, ANY, ONE], [ONE, ANY, ONE]]
+    if stats:
+        s.stats_mode, s.stats_dim = L.STATS_ON, -1
+    ktot = (max(k for _, _, k in taps) + 1) * cin
+    _set_weights_tmap(s, cout, ktot)
+    s.out_dtype, s.out_cstride, s.out_elem_offset = out.dtype, out.sc, out.base
+    s.act, s.act_slope = act, act_slope
+    s.flops = 2 * tiles * 128 * s.n_tiles * s.block_n * len(taps) * cin
+    return s
+
+
+def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho: int, wo: int, out: OutMap, *,
+                act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, note="") -> IgemmSpec:
+    """Small-Cin plan ("packed rows"): one K chunk covers a whole filter row, because in NHWC the kw taps x C
+    channels of a row are contiguous: window = Xpadded[n][stride*y + r + off][stride*x + off ...][0 : kw*C].
+    The A view has overlapping strides (dim 1 advances by stride pixels, dim 0 spans 64*cchunks elements).
+    Packed weights: W[co][r][s*C + c], zero beyond kw*C.  xg.c in {8, 16, 32}."""
+    C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
+    assert C % 8 == 0 and C < 64
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
+    s.block_n = _block_n(cout)
+    s.n_tiles = _ceil(cout, s.block_n)
+    s.n_valid = cout
+    win = _ceil(kw * C, 64) * 64
+    s.cchunks = win // 64
+    bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride == 2)
+    tx, ty, tn = _ceil(wo, bw), _ceil(ho, bh), _ceil(N, bn)
+    s.t_count = [tx, ty, tn, 1]
+    if stride == 1:
+        s.a_dims = [win, Wp, Hp, N, 1]
+        s.a_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
+        s.a_box = [64, bw, bh, bn, 1]
+        s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
+        for r in range(kh):
+            s.tap_off.append([off, r + off, 0, 0])
+            s.tap_c0.append(0)
+            s.tap_bk.append(r * win)
+        s.e_step[0][0], s.e_step[1][1], s.e_step[2][2] = bw, bh, bn
+        s.e_comp = [[ONE, (0, wo, out.sx), ONE], [ONE, (0, ho, out.sy), ONE], [ONE, (0, N, out.sn), ONE], [ONE, ANY, ONE]]
+        if stats:
+            s.stats_mode = L.STATS_ON
+            s.stats_dim, s.stats_comp = (2, 1) if per_sample_stats else (-1, 1)
+    else:
+        assert stride == 2 and Hp % 2 == 0
+        # dims: (window, X [2 pixels per step], py, Y (+ n*Hp/2)); the x offset `off` goes into the base pointer
+        s.a_dims = [win, Wp // 2, 2, (Hp // 2) * N, 1]
+        s.a_strides = [0, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2, (Hp // 2) * N * 2 * Wp * C * 2]
+        s.a_box = [64, bw, 1, bh, 1]
+        s.a_elem_offset = off * C
+        s.a_step[0][0] = bw
+        s.a_step[1][2] = bh
+        s.a_step[2][2] = Hp // 2
+        for r in range(kh):
+            s.tap_off.append([0, (r + off) % 2, (r + off) // 2, 0])
+            s.tap_c0.append(0)
+            s.tap_bk.append(r * win)
+        period = ty * bh
+        s.e_step[0][0] = bw
+        s.e_step[1][2] = bh
+        s.e_step[2][2] = period
+        s.e_p1[2] = period
+        s.e_comp = [[ONE, (0, wo, out.sx), ONE], [ONE, ANY, ONE], [(0, N, out.sn), (0, ho, out.sy), ONE], [ONE, ANY, ONE]]
+        if stats:
+            s.stats_mode = L.STATS_ON
+            s.stats_dim, s.stats_comp = (2, 0) if per_sample_stats else (-1, 1)
+    _set_weights_tmap(s, cout, kh * win)
+    s.out_dtype, s.out_cstride, s.out_elem_offset = out.dtype, out.sc, out.base
+    s.act, s.act_slope = act, act_slope
+    s.flops = 2 * tx * ty * tn * 128 * s.n_tiles * s.block_n * kh * win
+    return s
+
+
+# ------------------------------------------------------------------------------------------
+# WGRAD plans
+# ------------------------------------------------------------------------------------------
+def _next_pow2(v):
+    b = 1
+    while b < v:
+        b *= 2
+    return b
+
+
+def _pix_box64(w, h):
+    """(bw, bh) with bw*bh == 64 covering a w x h pixel grid in ceil(w/bw) x ceil(h/bh) boxes of one sample.
+    Boxes may over-cover: the M-side tensor is zero outside its interior (zero halo / TMA zero fill)."""
+    bw = min(64, _next_pow2(w))
+    bh = 64 // bw
+    return bw, bh
+
+
+def _ksplit_for(total_kb, out_tiles, sms=148):
+    ks = max(1, min(total_kb, sms // max(out_tiles, 1)))
+    # keep at least 8 K blocks per split so the pipeline fills
+    while ks > 1 and total_kb // ks < 8:
+        ks -= 1
+    return ks
+
+
+def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[int, int, int]], ph: int, pw: int,
+                   n_stride: int, *, m_origin=(0, 0), n_packed_win: int = 0, note="") -> IgemmSpec:
+    """Weight gradient over a ph x pw pixel grid per sample.
+    M side: tensor mg (padded NHWC), pixel (n, y, x) read at padded (y + m_origin[0], x + m_origin[1]), m_ch channels.
+    N side: tensor ng, pixel read at padded (n_stride*y + dy, n_stride*x + dx) for tap (dy, dx, kidx);
+            n_ch channels (or, if n_packed_win > 0, the packed-row window of that many elements).
+    Output fp32 [m_ch][ldo] with column = kidx*ncols + channel."""
+    s = IgemmSpec(kind=L.IGEMM_WGRAD, note=note)
+    bw, bh = _pix_box64(pw, ph)
+    bn = 1
+    assert mg.c % 8 == 0 and ng.c % 8 == 0
+    ncols = n_packed_win if n_packed_win else n_ch
+    s.block_n = min(256, _ceil(ncols, 64) * 64)
+    s.n_tiles = _ceil(ncols, s.block_n)
+    s.m_tiles = _ceil(m_ch, 128)
+    s.m_valid, s.wg_ncols = m_ch, ncols
+    N = mg.n
+    tx, ty, tn = _ceil(pw, bw), _ceil(ph, bh), N
+    s.t_count = [tx, ty, tn, 1]
+    # M-side view (c, x, y, n)
+    s.a_dims = [mg.c, mg.wp, mg.hp, N, 1]
+    s.a_strides = [0, mg.c * 2, mg.wp * mg.c * 2, mg.hp * mg.wp * mg.c * 2, N * mg.hp * mg.wp * mg.c * 2]
+    s.a_box = [64, bw, bh, bn, 1]
+    s.a_base = [m_origin[1], m_origin[0], 0, 0]
+    s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
+    C, Hp, Wp = ng.c, ng.hp, ng.wp
+    d0 = n_packed_win if n_packed_win else C
+    if n_stride == 1:
+        s.b_dims = [d0, Wp, Hp, N, 1]
+        s.b_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
+        s.b_box = [64, bw, bh, bn, 1]
+        s.b_step[0][0], s.b_step[1][1], s.b_step[2][2] = bw, bh, bn
+        for (dy, dx, kidx) in taps:
+            s.tap_off.append([dx, dy, 0, 0])
+            s.tap_c0.append(0)
+            s.tap_bk.append(kidx * ncols)
+    else:
+        assert n_stride == 2 and Hp % 2 == 0 and bn == 1
+        if n_packed_win:
+            s.b_dims = [d0, Wp // 2, 2, (Hp // 2) * N, 1]
+            s.b_strides = [0, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2, (Hp // 2) * N * 2 * Wp * C * 2]
+            s.b_box = [64, bw, 1, bh, 1]
+            s.b_step[0][0], s.b_step[1][2], s.b_step[2][2] = bw, bh, Hp // 2
+            xoffs = set(dx for _, dx, _ in taps)
+            assert len(xoffs) == 1
+            s.b_elem_offset = xoffs.pop() * C
+            for (dy, dx, kidx) in taps:
+                s.tap_off.append([0, dy % 2, dy // 2, 0])
+                s.tap_c0.append(0)
+                s.tap_bk.append(kidx * ncols)
+        else:
+            assert Wp % 2 == 0
+            s.b_dims = [d0, 2, Wp // 2, 2, (Hp // 2) * N]
+            s.b_strides = [0, C * 2, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2]
+            s.b_box = [64, 1, bw, 1, bh]
+            s.b_step[0][1], s.b_step[1][3], s.b_step[2][3] = bw, bh, Hp // 2
+            for (dy, dx, kidx) in taps:
+                s.tap_off.append([dx % 2, dx // 2, dy % 2, dy // 2])
+                s.tap_c0.append(0)
+                s.tap_bk.append(kidx * ncols)
+    nk = max(k for _, _, k in taps) + 1
+    s.ldo = nk * ncols
+    s.b_rows, s.b_k = m_ch, s.ldo
+    total_kb = tx * ty * tn
+    s.ksplit = _ksplit_for(total_kb, len(taps) * s.m_tiles * s.n_tiles)
+    s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
+    return s
+
+
+def plan_wgrad_flat(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[int, int, int]], *, note="") -> IgemmSpec:
+    """Weight gradient over the flattened padded grid shared by both tensors (same n, hp, wp):
+    out[m][kidx*n_ch + c] = sum_q M[q][m] * Nt[q + dy*Wp + dx][c].  M must be zero wherever it is not a real
+    output-gradient (zero halo), so wrapped / out-of-range positions contribute nothing."""
+    assert (mg.n, mg.hp, mg.wp) == (ng.n, ng.hp, ng.wp)
+    s = IgemmSpec(kind=L.IGEMM_WGRAD, note=note)
+    P = mg.n * mg.hp * mg.wp
+    s.block_n = min(256, _ceil(n_ch, 64) * 64)
+    s.n_tiles = _ceil(n_ch, s.block_n)
+    s.m_tiles = _ceil(m_ch, 128)
+    s.m_valid, s.wg_ncols = m_ch, n_ch
+    s.a_dims = [mg.c, P, 1, 1, 1]
+    s.a_strides = [0, mg.c * 2, P * mg.c * 2, P * mg.c * 2, P * mg.c * 2]
+    s.a_box = [64, 64, 1, 1, 1]
+    s.b_dims = [ng.c, P, 1, 1, 1]
+    s.b_strides = [0, ng.c * 2, P * ng.c * 2, P * ng.c * 2, P * ng.c * 2]
+    s.b_box = [64, 64, 1, 1, 1]
+    kb = _ceil(P, 64)
+    s.t_count = [kb, 1, 1, 1]
+    s.a_step[0][0] = 64
+    s.b_step[0][0] = 64
+    for (dy, dx, kidx) in taps:
+        s.tap_off.append([dy * ng.wp + dx, 0, 0, 0])
+        s.tap_c0.append(0)
+        s.tap_bk.append(kidx * n_ch)
+    nk = max(k for _, _, k in taps) + 1
+    s.ldo = nk * n_ch
+    s.b_rows, s.b_k = m_ch, s.ldo
+    s.ksplit = _ksplit_for(kb, len(taps) * s.m_tiles * s.n_tiles)
+    s.flops = 2 * kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
+    return s
+
+
+# ------------------------------------------------------------------------------------------
+# Weight index maps: packed[i] = W.flatten()[idx[i]] (or 0 when idx[i] < 0)
+# ------------------------------------------------------------------------------------------
+def index_map(shape, fn, rows, k) -> torch.Tensor:
+    """Build an int32 [rows*k] gather map by calling fn(row, col) -> flat index into a tensor of `shape` or -1.
+    Slow generic path, used once per layer at construction."""
+    idx = torch.full((rows, k), -1, dtype=torch.int32)
+    for r in range(rows):
+        for c in range(k):
+            idx[r, c] = fn(r, c)
+    return idx.reshape(-1)
+
+
+def wmap_taps(w_shape, rows, taps, cin, *, transposed_layout=False, swap=False) -> torch.Tensor:
+    """Vectorised map for per-tap layouts: packed[row][kidx*cin + c] = W[...] with taps = [(r, s, kidx)].
+    OIHW weights (nn.Conv2d): row = o, c = i  (swap=False)  -> W[o][i][r][s]
+                              row = i, c = o  (swap=True)   -> W[o][i][r][s]   (data-gradient operand)
+    IOHW weights (nn.ConvTranspose2d, transposed_layout=True): W[i][o][r][s]; row = o, c = i when swap=False
+    (forward operand: contraction over the in-channels i), row = i, c = o when swap=True."""
+    d0, d1, kh, kw = w_shape
+    nk = max(k for _, _, k in taps) + 1
+    idx = torch.full((rows, nk * cin), -1, dtype=torch.int64)
+    rr = torch.arange(rows).view(-1, 1)
+    cc = torch.arange(cin).view(1, -1)
+    for (r, s_, kidx) in taps:
+        if not transposed_layout:
+            o, i = (cc, rr) if swap else (rr, cc)
+            valid = (o < d0) & (i < d1)
+            flat = ((o * d1 + i) * kh + r) * kw + s_
+        else:
+            # stored [i][o][kh][kw]
+            o, i = (cc, rr) if swap else (rr, cc)
+            valid = (i < d0) & (o < d1)
+            flat = ((i * d1 + o) * kh + r) * kw + s_
+        idx[:, kidx * cin:(kidx + 1) * cin] = torch.where(valid, flat, torch.full_like(flat, -1))
+    return idx.reshape(-1).to(torch.int32)
+
+
+def wmap_packed(w_shape, rows, kh, kw, c_buf, win, *, flip=False, swap=False) -> torch.Tensor:
+    """Map for packed-row layouts: packed[row][r*win + s*c_buf + c] = W[row][c][r][s] (swap=False, OIHW)
+    or W[c][row][kh-1-r][kw-1-s] (swap=True with flip: data-gradient through a stride-1 conv)."""
+    d0, d1, _, _ = w_shape
+    idx = torch.full((rows, kh * win), -1, dtype=torch.int64)
+    rr = torch.arange(rows).view(-1, 1)
+    cc = torch.arange(c_buf).view(1, -1)
+    for r in range(kh):
+        for s_ in range(kw):
+            wr, ws = (kh - 1 - r, kw - 1 - s_) if flip else (r, s_)
+            o, i = (cc, rr) if swap else (rr, cc)
+            valid = (o < d0) & (i < d1)
+            flat = ((o * d1 + i) * kh + wr) * kw + ws
+            base = r * win + s_ * c_buf
+            idx[:, base:base + c_buf] = torch.where(valid, flat, torch.full_like(flat, -1))
+    return idx.reshape(-1).to(torch.int32)

@@ -1,0 +1,221 @@
+"""Planner validated on the CPU: every plan is executed by the igemm emulator (oracle/igemm_emulator.py,
+which follows the kernel contract in include/pcgan_kernels.h) and compared with torch.nn.functional
+convolutions (the arithmetic the reference dispatches: models/networks.py:578-605, :747-775)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import igemm_emulator as emu
+from oracle.layout import bf16_round, from_padded_nhwc, to_padded_nhwc
+from pcgan_b200 import _lib as L
+from pcgan_b200 import conv as CV
+from pcgan_b200.plan import Geom, OutMap
+
+
+def pack_weights(w, wmap, rows, k):
+    flat = bf16_round(w).reshape(-1)
+    idx = wmap.long()
+    out = torch.where(idx >= 0, flat[idx.clamp(min=0)], torch.zeros(()))
+    return out.reshape(rows * k)
+
+
+def run_fwd(plans, xflat, w, out_numel, bias=None, stats=None, groups=1):
+    out = torch.zeros(out_numel)
+    for sp, wm in plans:
+        sp.to_desc()  # exercises the ctypes conversion
+        b = pack_weights(w, wm, sp.b_rows, sp.b_k)
+        view = out[sp.out_elem_offset:]
+        emu.run_kmajor(sp, xflat[sp.a_elem_offset:], b, view, bias=bias, stats=stats)
+    return out
+
+
+def rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+FWD_CASES = [
+    # name, cin, cin_buf, cout, k, stride, cp, halo, xpad, H, W, N
+    ("res3x3_reflect", 64, 64, 64, 3, 1, 1, "reflect", 1, 32, 32, 2),
+    ("res3x3_reflect_small", 128, 128, 32, 3, 1, 1, "reflect", 1, 8, 8, 3),
+    ("down3x3_s2", 64, 64, 128, 3, 2, 1, "zero", 1, 16, 16, 2),
+    ("d4x4_s2", 64, 64, 128, 4, 2, 1, "zero", 1, 16, 16, 2),
+    ("d4x4_s1", 64, 64, 80, 4, 1, 1, "zero", 1, 9, 9, 2),
+    ("stem7x7_packed", 4, 8, 64, 7, 1, 3, "reflect", 3, 16, 16, 2),
+    ("dstem4x4_s2_packed", 4, 8, 64, 4, 2, 1, "zero", 1, 16, 16, 2),
+    ("estem7x7_s2_packed", 3, 8, 64, 7, 2, 3, "zero", 3, 32, 32, 2),
+    ("head7x7_n3", 64, 64, 3, 7, 1, 3, "reflect", 3, 16, 16, 1),
+    ("e3x3_14", 64, 64, 64, 3, 1, 1, "zero", 1, 14, 14, 3),
+    ("e3x3_7", 128, 128, 64, 3, 1, 1, "zero", 1, 7, 7, 5),
+    ("e1x1_s2", 64, 64, 128, 1, 2, 0, "zero", 1, 8, 8, 2),
+    ("tail3x3_c32_packed", 32, 32, 1, 3, 1, 1, "zero", 1, 7, 7, 3),
+    ("wide_n512", 64, 64, 512, 3, 1, 1, "zero", 1, 8, 8, 1),
+]
+
+
+@pytest.mark.parametrize("case", FWD_CASES, ids=[c[0] for c in FWD_CASES])
+def test_conv_forward_plan(case):
+    _, cin, cbuf, cout, k, stride, cp, halo, xpad, H, W, N = case
+    torch.manual_seed(0)
+    x = torch.randn(N, cin, H, W)
+    w = torch.randn(cout, cin, k, k) * 0.1
+    bias = torch.randn(cout)
+    xg = Geom(N, H, W, cbuf, xpad)
+    ho, wo = CV.out_size(H, k, stride, cp), CV.out_size(W, k, stride, cp)
+    og = Geom(N, ho, wo, max(8, -(-cout // 8) * 8), 1)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, stride, cp, OutMap.nhwc(og, dtype=L.DT_F32), stats=True)
+    xflat = to_padded_nhwc(x, xpad, halo, cbuf)
+    stats = torch.zeros(1, cout, 2)
+    out = run_fwd(plans, xflat, w, og.numel, bias=bias, stats=stats)
+    got = from_padded_nhwc(out, N, ho, wo, og.c, 1)[:, :cout]
+    xr = bf16_round(x)
+    if xpad > cp or halo == "reflect":
+        xr = F.pad(xr, (cp,) * 4, mode="reflect" if halo == "reflect" else "constant")
+        ref = F.conv2d(xr, bf16_round(w), bias, stride=stride)
+    else:
+        ref = F.conv2d(xr, bf16_round(w), bias, stride=stride, padding=cp)
+    assert rel(got, ref) < 1e-5
+    # halo of the output buffer untouched
+    full = out[: og.numel].view(N, ho + 2, wo + 2, og.c)
+    assert float(full[:, 0].abs().max()) == 0 and float(full[:, :, 0].abs().max()) == 0
+    assert rel(stats[0, :, 0], ref.sum((0, 2, 3))) < 1e-4
+    assert rel(stats[0, :, 1], (ref * ref).sum((0, 2, 3))) < 1e-4
+
+
+def test_per_sample_stats_and_nchw_out():
+    torch.manual_seed(1)
+    N, C, H = 3, 64, 16
+    x, w = torch.randn(N, C, H, H), torch.randn(64, C, 3, 3) * 0.1
+    xg = Geom(N, H, H, C, 1)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, 1, 1, OutMap.nchw(N, 64, H, H), stats=True, per_sample_stats=True, act=L.ACT_TANH)
+    stats = torch.zeros(N, 64, 2)
+    out = run_fwd(plans, to_padded_nhwc(x, 1, "reflect"), w, N * 64 * H * H, stats=stats)
+    pre = F.conv2d(F.pad(bf16_round(x), (1,) * 4, mode="reflect"), bf16_round(w))
+    assert rel(out.view(N, 64, H, H), torch.tanh(pre)) < 1e-5
+    assert rel(stats[..., 0], pre.sum((2, 3))) < 1e-4
+    assert rel(stats[..., 1], (pre * pre).sum((2, 3))) < 1e-4
+
+
+def test_conv_transpose_forward_plan():
+    torch.manual_seed(2)
+    N, cin, cout, H = 2, 128, 64, 8
+    x, w = torch.randn(N, cin, H, H), torch.randn(cin, cout, 3, 3) * 0.1
+    xg = Geom(N, H, H, cin, 1)
+    og = Geom(N, 2 * H, 2 * H, cout, 0)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, 2, 1, OutMap.nhwc(og, dtype=L.DT_F32), transposed=True, output_padding=1,
+                              stats=True, per_sample_stats=True)
+    assert len(plans) == 4 and sorted(len(p[0].tap_off) for p in plans) == [1, 2, 2, 4]
+    stats = torch.zeros(N, cout, 2)
+    out = run_fwd(plans, to_padded_nhwc(x, 1, "zero"), w, og.numel, stats=stats)
+    ref = F.conv_transpose2d(bf16_round(x), bf16_round(w), stride=2, padding=1, output_padding=1)
+    assert rel(from_padded_nhwc(out, N, 2 * H, 2 * H, cout, 0), ref) < 1e-5
+    assert rel(stats[..., 0], ref.sum((2, 3))) < 1e-4
+
+
+DGRAD_CASES = [
+    # name, cin, cout, cout_buf, k, stride, cp, xpad, full_padded, H, N, dypad
+    ("res3x3_flat_full", 64, 64, 64, 3, 1, 1, 1, True, 16, 2, 1),
+    ("res3x3_flat_interior", 64, 64, 64, 3, 1, 1, 1, False, 16, 2, 1),
+    ("head7x7_packed_full", 64, 3, 8, 7, 1, 3, 3, True, 16, 2, 6),
+    ("dhead4x4_packed", 64, 1, 8, 4, 1, 1, 1, False, 9, 2, 2),
+    ("d4x4_s1_box", 64, 64, 64, 4, 1, 1, 1, False, 9, 2, 0),
+    ("down3x3_s2", 64, 128, 128, 3, 2, 1, 1, False, 16, 2, 0),
+    ("d4x4_s2", 64, 128, 128, 4, 2, 1, 1, False, 16, 2, 1),
+    ("dstem4x4_s2_to4", 4, 64, 64, 4, 2, 1, 1, False, 16, 2, 0),
+    ("estem7x7_s2_to3", 3, 64, 64, 7, 2, 3, 3, False, 32, 1, 0),
+    ("e1x1_s2", 64, 128, 128, 1, 2, 0, 1, False, 8, 2, 0),
+    ("stem7x7_to4_full", 4, 64, 64, 7, 1, 3, 3, True, 16, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=[c[0] for c in DGRAD_CASES])
+def test_conv_dgrad_plan(case):
+    _, cin, cout, cobuf, k, stride, cp, xpad, full, H, N, dypad = case
+    torch.manual_seed(3)
+    w = torch.randn(cout, cin, k, k) * 0.1
+    ho = CV.out_size(H, k, stride, cp)
+    dy = torch.randn(N, cout, ho, ho)
+    cibuf = max(8, -(-cin // 8) * 8)
+    xg = Geom(N, H, H, cibuf, xpad)
+    flat_same = stride == 1 and ho == H and cobuf >= 64
+    dyg = Geom(N, ho, ho, cobuf, xpad if flat_same else dypad)
+    if full:
+        og = Geom(N, H + 2 * xpad, H + 2 * xpad, cibuf, 0)
+    else:
+        og = Geom(N, H, H, cibuf, 0)
+    plans = CV.conv_dgrad_plans(tuple(w.shape), dyg, xg, stride, cp, OutMap.nhwc(og, dtype=L.DT_F32), full_padded=full)
+    out = run_fwd(plans, to_padded_nhwc(dy, dyg.pad, "zero", cobuf), w, og.numel)
+    got = from_padded_nhwc(out, N, og.h, og.w, cibuf, 0)[:, :cin]
+    # reference: autograd of the padded-input convolution
+    xp = torch.zeros(N, cin, H + 2 * xpad, H + 2 * xpad, requires_grad=True)
+    o = xpad - cp
+    xin = xp[:, :, o:H + 2 * xpad - o, o:H + 2 * xpad - o] if o > 0 else xp
+    y = F.conv2d(xin, bf16_round(w), stride=stride)
+    y.backward(bf16_round(dy))
+    ref = xp.grad if full else xp.grad[:, :, xpad:xpad + H, xpad:xpad + H]
+    assert rel(got, ref) < 1e-5
+
+
+def test_conv_transpose_dgrad_plan():
+    torch.manual_seed(4)
+    N, cin, cout, H = 2, 128, 64, 8
+    w = torch.randn(cin, cout, 3, 3) * 0.1
+    dy = torch.randn(N, cout, 2 * H, 2 * H)
+    dyg, xg = Geom(N, 2 * H, 2 * H, cout, 1), Geom(N, H, H, cin, 1)
+    og = Geom(N, H, H, cin, 0)
+    plans = CV.conv_dgrad_plans(tuple(w.shape), dyg, xg, 2, 1, OutMap.nhwc(og, dtype=L.DT_F32), transposed=True)
+    out = run_fwd(plans, to_padded_nhwc(dy, 1, "zero"), w, og.numel)
+    x = torch.zeros(N, cin, H, H, requires_grad=True)
+    F.conv_transpose2d(x, bf16_round(w), stride=2, padding=1, output_padding=1).backward(bf16_round(dy))
+    assert rel(from_padded_nhwc(out, N, H, H, cin, 0), x.grad) < 1e-5
+
+
+WGRAD_CASES = [
+    # name, cin, cin_buf, cout, cout_buf, k, stride, cp, halo, xpad, H, N, dypad
+    ("res3x3", 64, 64, 64, 64, 3, 1, 1, "reflect", 1, 16, 2, 1),
+    ("res3x3_c256", 256, 256, 128, 128, 3, 1, 1, "reflect", 1, 8, 2, 0),
+    ("down3x3_s2", 64, 64, 192, 192, 3, 2, 1, "zero", 1, 16, 2, 0),
+    ("d4x4_s2", 64, 64, 128, 128, 4, 2, 1, "zero", 1, 16, 3, 1),
+    ("d4x4_s1_odd", 64, 64, 64, 64, 4, 1, 1, "zero", 1, 9, 2, 1),
+    ("stem7x7_packed", 4, 8, 64, 64, 7, 1, 3, "reflect", 3, 16, 2, 0),
+    ("dstem4x4_s2_packed", 4, 8, 64, 64, 4, 2, 1, "zero", 1, 16, 2, 0),
+    ("head7x7_cout3", 64, 64, 3, 8, 7, 1, 3, "reflect", 3, 16, 2, 6),
+    ("dhead4x4_cout1", 64, 64, 1, 8, 4, 1, 1, "zero", 1, 9, 2, 2),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=[c[0] for c in WGRAD_CASES])
+def test_conv_wgrad_plan(case):
+    _, cin, cbuf, cout, cobuf, k, stride, cp, halo, xpad, H, N, dypad = case
+    torch.manual_seed(5)
+    x = torch.randn(N, cin, H, H)
+    ho = CV.out_size(H, k, stride, cp)
+    dy = torch.randn(N, cout, ho, ho)
+    xg, dyg = Geom(N, H, H, cbuf, xpad), Geom(N, ho, ho, cobuf, dypad)
+    sp, wm = CV.conv_wgrad_plan((cout, cin, k, k), dyg, xg, stride, cp)
+    sp.to_desc()
+    packed = torch.zeros(sp.b_rows * sp.b_k)
+    emu.run_wgrad(sp, to_padded_nhwc(dy, dypad, "zero", cobuf)[sp.a_elem_offset:], to_padded_nhwc(x, xpad, halo, cbuf)[sp.b_elem_offset:], packed)
+    dw = torch.zeros(cout * cin * k * k)
+    idx = wm.long()
+    dw[idx[idx >= 0]] = packed[idx >= 0]
+    xr = F.pad(bf16_round(x), (cp,) * 4, mode="reflect" if halo == "reflect" else "constant")
+    wref = torch.zeros(cout, cin, k, k, requires_grad=True)
+    F.conv2d(xr, wref, stride=stride).backward(bf16_round(dy))
+    assert rel(dw.view(cout, cin, k, k), wref.grad) < 1e-5
+    # every packed element that maps nowhere must be exactly zero-weight in forward; nothing to check here
+
+
+def test_conv_transpose_wgrad_plan():
+    torch.manual_seed(6)
+    N, cin, cout, H = 2, 128, 64, 8
+    x, dy = torch.randn(N, cin, H, H), torch.randn(N, cout, 2 * H, 2 * H)
+    xg, dyg = Geom(N, H, H, cin, 1), Geom(N, 2 * H, 2 * H, cout, 1)
+    sp, wm = CV.conv_wgrad_plan((cin, cout, 3, 3), dyg, xg, 2, 1, transposed=True)
+    packed = torch.zeros(sp.b_rows * sp.b_k)
+    emu.run_wgrad(sp, to_padded_nhwc(x, 1, "zero"), to_padded_nhwc(dy, 1, "zero"), packed)
+    dw = torch.zeros(cin * cout * 9)
+    idx = wm.long()
+    dw[idx[idx >= 0]] = packed[idx >= 0]
+    wref = torch.zeros(cin, cout, 3, 3, requires_grad=True)
+    F.conv_transpose2d(bf16_round(x), wref, stride=2, padding=1, output_padding=1).backward(bf16_round(dy))
+    assert rel(dw.view(cin, cout, 3, 3), wref.grad) < 1e-5
