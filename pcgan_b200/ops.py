@@ -1,0 +1,142 @@
+"""Thin Python wrappers over the C ABI (include/pcgan_kernels.h): torch tensors in, raw
+pointers out.  torch is used only for device memory and streams; every computation is a
+launch of a kernel from libpcgan_kernels.so.  No fallback: a missing library or a
+non-CUDA tensor raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .plan import Geom, IgemmSpec, SLACK
+
+
+def _ptr(t, elem_offset=0):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L.PcganError("pcgan ops need CUDA tensors (no CPU fallback); got %s" % t.device)
+    return t.data_ptr() + elem_offset * t.element_size()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Igemm:
+    """A planned implicit GEMM (one kernel launch per run)."""
+
+    def __init__(self, spec: IgemmSpec):
+        self.spec = spec
+        self.lib = L.load()
+        self._h = C.c_void_p()
+        desc = spec.to_desc()
+        L.check(self.lib.pcgan_igemm_plan_create(C.byref(desc), C.byref(self._h)), "igemm_plan_create(%s)" % spec.note)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.pcgan_igemm_plan_destroy(self._h)
+        except Exception:
+            pass
+
+    def run(self, a, b, out, bias=None, stats=None):
+        s = self.spec
+        L.check(self.lib.pcgan_igemm_run(self._h, _ptr(a, s.a_elem_offset), _ptr(b, s.b_elem_offset),
+                                         _ptr(out, s.out_elem_offset), _ptr(bias), _ptr(stats), _stream()),
+                "igemm_run(%s)" % s.note)
+
+
+def alloc_act(g: Geom, device, zero=True):
+    """Padded NHWC bf16 activation buffer (flat, with slack for packed-row windows)."""
+    n = g.numel + SLACK
+    return torch.zeros(n, dtype=torch.bfloat16, device=device) if zero else torch.empty(n, dtype=torch.bfloat16, device=device)
+
+
+def gather_cast_bf16(src, idx, dst):
+    L.check(L.load().pcgan_gather_cast_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_cast_bf16")
+
+
+def scatter_f32(src, idx, dst, accumulate=False):
+    L.check(L.load().pcgan_scatter_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), int(accumulate), _stream()), "scatter_f32")
+
+
+def pack_nchw(src, dst, g: Geom, *, z=None, tanh_out=None, halo=L.HALO_ZERO, src_hw=None):
+    """src: NCHW fp32 [n, cs, h, w] -> dst buffer of geometry g (resized to g.h x g.w when they differ)."""
+    n, cs, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    a = L.PackArgs(src=_ptr(src), z=_ptr(z), tanh_out=_ptr(tanh_out), dst=_ptr(dst), n=n, cs=cs, h=h, w=w,
+                   ho=g.h, wo=g.w, cd=g.c, pad=g.pad, halo=halo, dst_n_stride=0)
+    L.check(L.load().pcgan_pack_nchw(C.byref(a), _stream()), "pack_nchw")
+
+
+def unpack_resize_bwd(gbuf, g: Geom, dst, *, accumulate=False, scale=1.0):
+    """gbuf: NHWC bf16 gradient of geometry g -> dst NCHW fp32 [n, cd, h, w] (adjoint of the resize if sizes differ)."""
+    n, cd, h, w = dst.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    a = L.UnpackArgs(g=_ptr(gbuf), dst=_ptr(dst), n=n, c=g.c, hs=g.h, ws=g.w, pad=g.pad, cd=cd, h=h, w=w,
+                     accumulate=int(accumulate), scale=scale)
+    L.check(L.load().pcgan_unpack_resize_bwd(C.byref(a), _stream()), "unpack_resize_bwd")
+
+
+def norm_finalize(stats, groups, c, count, *, eps=1e-5, momentum=0.1, gamma=None, beta=None, mean=None, rstd=None,
+                  scale=None, shift=None, running_mean=None, running_var=None):
+    a = L.NormFinalizeArgs(stats=_ptr(stats), groups=groups, c=c, count=float(count), eps=eps, momentum=momentum,
+                           gamma=_ptr(gamma), beta=_ptr(beta), mean=_ptr(mean), rstd=_ptr(rstd), scale=_ptr(scale),
+                           shift=_ptr(shift), running_mean=_ptr(running_mean), running_var=_ptr(running_var))
+    L.check(L.load().pcgan_norm_finalize(C.byref(a), _stream()), "norm_finalize")
+
+
+def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shift=None, groups=1, res=None, res_pad=0,
+               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0):
+    assert (xg.n, xg.h, xg.w, xg.c) == (yg.n, yg.h, yg.w, yg.c)
+    a = L.NormApplyArgs(x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad, y=_ptr(y), y_pad=yg.pad, y_halo=y_halo,
+                        n=xg.n, h=xg.h, w=xg.w, c=xg.c, scale=_ptr(scale), shift=_ptr(shift), groups=groups,
+                        res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
+                        drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope)
+    L.check(L.load().pcgan_norm_apply(C.byref(a), _stream()), "norm_apply")
+
+
+def halo_fold(gpad, gg: Geom, out, out_pad, *, halo=L.HALO_REFLECT, add=None, add_pad=0):
+    a = L.FoldArgs(gpad=_ptr(gpad), g_pad=gg.pad, halo=halo, add=_ptr(add), add_pad=add_pad, out=_ptr(out),
+                   out_pad=out_pad, n=gg.n, h=gg.h, w=gg.w, c=gg.c)
+    L.check(L.load().pcgan_halo_fold(C.byref(a), _stream()), "halo_fold")
+
+
+def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, scale=None, shift=None, groups=1,
+              res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, count=0.0,
+              sums=None, dx=None, dx_pad=0, dres=None, dres_pad=0):
+    return L.NormBwdArgs(dy=_ptr(dy), dy_pad=dy_pad, x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad,
+                         mean=_ptr(mean), rstd=_ptr(rstd), scale=_ptr(scale), shift=_ptr(shift), groups=groups,
+                         res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
+                         drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, n=xg.n, h=xg.h, w=xg.w, c=xg.c,
+                         count=float(count), sums=_ptr(sums), dx=_ptr(dx), dx_pad=dx_pad, dres=_ptr(dres), dres_pad=dres_pad)
+
+
+def norm_bwd_reduce(dy, dy_pad, x, xg, **kw):
+    a = _bwd_args(dy, dy_pad, x, xg, **kw)
+    L.check(L.load().pcgan_norm_bwd_reduce(C.byref(a), _stream()), "norm_bwd_reduce")
+
+
+def norm_bwd_apply(dy, dy_pad, x, xg, **kw):
+    a = _bwd_args(dy, dy_pad, x, xg, **kw)
+    L.check(L.load().pcgan_norm_bwd_apply(C.byref(a), _stream()), "norm_bwd_apply")
+
+
+def maxpool_fwd(x, xg: Geom, y, y_pad, idx):
+    a = L.MaxpoolArgs(x=_ptr(x), x_pad=xg.pad, y=_ptr(y), y_pad=y_pad, idx=_ptr(idx), n=xg.n, h=xg.h, w=xg.w, c=xg.c)
+    L.check(L.load().pcgan_maxpool3x3s2_fwd(C.byref(a), _stream()), "maxpool_fwd")
+
+
+def maxpool_bwd(dy, dy_pad, idx, dx, dx_pad, n, h, w, c):
+    L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, _stream()), "maxpool_bwd")
+
+
+def loss(kind, p, target, *, per_sample=0, weight=1.0, loss_out=None, grad=None):
+    a = L.LossArgs(kind=kind, p=_ptr(p), target=_ptr(target), n=p.numel(), per_sample=per_sample, weight=weight,
+                   loss=_ptr(loss_out), grad=_ptr(grad))
+    L.check(L.load().pcgan_loss(C.byref(a), _stream()), "loss")
+
+
+def adam(p, g, m, v, lr, beta1, beta2, eps, step):
+    L.check(L.load().pcgan_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(lr), beta1, beta2, eps, _ptr(step), _stream()), "adam")
