@@ -1,0 +1,173 @@
+"""Generates the golden fixtures in tests/golden/ by running the UNMODIFIED reference
+(/root/reference, phymhan/pc-gan) on the CPU of the authoring container.  The reference is
+not available on the GPU box, so the fixtures (seeds + small result tensors) are committed
+and replayed by tests/test_oracle_cpu.py through oracle/pcgan_oracle.py.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.pt
+"""
+import os
+import sys
+import tempfile
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import pcgan_oracle as O  # noqa: E402  (only fill_state_dict_/synthetic_batch: shared deterministic inputs)
+
+torch.set_num_threads(8)
+torch.manual_seed(0)
+
+
+def sub(t, step):
+    return t[..., ::step, ::step].clone()
+
+
+def golden_generator():
+    from models import networks
+    net = networks.define_G(3, 3, 1, 8, which_model_netG="resnet_9blocks", norm="instance", init_type="normal", gpu_ids=[])
+    O.fill_state_dict_(net.state_dict(), 11)
+    a, _, _ = O.synthetic_batch(2, 32, 101)
+    z = torch.tensor([0.3, -1.2]).view(2, 1, 1, 1)
+    a.requires_grad_(True)
+    out = net(a, z)
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    sd = net.state_dict()
+    fx = {"seed": 11, "ngf": 8, "x_seed": 101, "z": z, "out": out.detach(), "dx": a.grad.clone(),
+          "grads": {k: p.grad.clone() for k, p in net.named_parameters()
+                    if k in ("model.1.weight", "model.7.weight", "model.10.conv_block.1.weight", "model.18.conv_block.5.weight",
+                             "model.19.weight", "model.22.weight", "model.26.weight", "model.26.bias")},
+          "running": {k: sd[k].clone() for k in ("model.2.running_mean", "model.2.running_var", "model.11.conv_block.6.running_var", "model.2.num_batches_tracked")}}
+    torch.save(fx, os.path.join(HERE, "generator_small.pt"))
+    # full-size network, batch 1, subsampled output
+    net = networks.define_G(3, 3, 1, 64, which_model_netG="resnet_9blocks", norm="instance", init_type="normal", gpu_ids=[])
+    O.fill_state_dict_(net.state_dict(), 21)
+    a, _, _ = O.synthetic_batch(1, 128, 102)
+    with torch.no_grad():
+        out = net(a, torch.tensor([0.7]).view(1, 1, 1, 1))
+    torch.save({"seed": 21, "x_seed": 102, "z": 0.7, "out_sub": sub(out, 8), "out_mean": out.mean(), "out_std": out.std()},
+               os.path.join(HERE, "generator_full.pt"))
+
+
+def golden_discriminator():
+    from models import networks
+    net = networks.define_D(3, 1, 8, "n_layers", 3, "batch", True, "normal", gpu_ids=[])
+    O.fill_state_dict_(net.state_dict(), 12)
+    a, _, _ = O.synthetic_batch(3, 32, 103)
+    z = torch.tensor([0.5, -0.5, 1.5]).view(3, 1, 1, 1)
+    a.requires_grad_(True)
+    out = net(a, z)
+    loss = networks.GANLoss(use_lsgan=False)(out, [1, 0, 1])
+    loss.backward()
+    sd = net.state_dict()
+    fx = {"seed": 12, "ndf": 8, "x_seed": 103, "z": z, "out": out.detach(), "loss": loss.detach(), "dx": a.grad.clone(),
+          "grads": {k: p.grad.clone() for k, p in net.named_parameters()},
+          "running": {k: sd[k].clone() for k in sd if "running" in k or "tracked" in k}}
+    torch.save(fx, os.path.join(HERE, "discriminator_small.pt"))
+
+
+def golden_encoder():
+    from models import networks
+    net = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7,
+                            gpu_ids=[], noisy=False, bnn_dropout=0.0)
+    O.fill_state_dict_(net.state_dict(), 13)
+    a, _, _ = O.synthetic_batch(2, 64, 104)
+    a.requires_grad_(True)
+    y = net(a)
+    (y * torch.tensor([1.0, -2.0]).view(2, 1, 1, 1)).sum().backward()
+    sd = net.state_dict()
+    fx = {"seed": 13, "x_seed": 104, "y": y.detach(), "dx_sub": sub(a.grad, 4), "dx_norm": a.grad.norm(),
+          "running": {k: sd[k].clone() for k in ("base.model.bn1.running_mean", "base.model.layer4.1.bn2.running_var", "cnn.1.running_mean")},
+          "keys": list(sd.keys())}
+    torch.save(fx, os.path.join(HERE, "encoder.pt"))
+    # noisy twin head
+    net = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7,
+                            gpu_ids=[], noisy=True, bnn_dropout=0.0)
+    O.fill_state_dict_(net.state_dict(), 14)
+    with torch.no_grad():
+        y, lv = net(a.detach())
+    torch.save({"seed": 14, "x_seed": 104, "y": y, "logvar": lv, "keys": list(net.state_dict().keys())}, os.path.join(HERE, "encoder_noisy.pt"))
+
+
+def golden_losses():
+    from models import networks
+    p = torch.tensor([0.0, 1.0, 1e-30, 0.3, 0.9999999, 0.5, 0.2, 0.8]).view(2, 1, 2, 2).requires_grad_(True)
+    crit = networks.GANLoss(use_lsgan=False)
+    out = {}
+    for name, tgt in (("true", True), ("false", False), ("mixed", [1, 0])):
+        p.grad = None
+        l = crit(p, tgt)
+        l.backward()
+        out["bce_" + name] = (l.detach(), p.grad.clone())
+    p2 = torch.tensor([0.1, 0.7, 0.4, 1.2]).view(2, 1, 1, 2).requires_grad_(True)
+    l = networks.GANLoss(use_lsgan=True)(p2, [1, 0])
+    l.backward()
+    out["mse_mixed"] = (l.detach(), p2.grad.clone())
+    out["p"], out["p2"] = p.detach(), p2.detach()
+    # BinaryNLLLoss hard-codes .cuda() in __init__ (networks.py:477): construct it with .cuda() neutralised
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        nll = networks.BinaryNLLLoss()
+    finally:
+        torch.Tensor.cuda = orig
+    prob = torch.tensor([0.2, 0.5, 0.9, 0.0, 1.0]).view(5, 1, 1, 1)
+    label = torch.tensor([0, 1, 2, 2, 0])
+    out["elo_prob"], out["elo_label"], out["elo_loss"] = prob, label, nll(prob, label)
+    x = torch.linspace(-1, 1, 2 * 3 * 5 * 5).view(2, 3, 5, 5)
+    from util.util import upsample2d
+    out["up_in"], out["up_out"] = x, upsample2d(x, 9)
+    torch.save(out, os.path.join(HERE, "losses.pt"))
+
+
+def golden_step():
+    """Two full WSGANEmbModel.optimize_parameters() steps (train.py:33-34) at the benchmark architecture,
+    batch 2, 128 x 128, fineSize_E 224, lambda_IP 0."""
+    from models import networks
+    tmp = tempfile.mkdtemp()
+    e0 = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7, gpu_ids=[])
+    pth = os.path.join(tmp, "e.pth")
+    torch.save(e0.state_dict(), pth)
+    argv = sys.argv
+    sys.argv = ["x", "--model", "wsgan_emb", "--gpu_ids", "-1", "--which_model_netG", "resnet_9blocks", "--n_layers_D", "3",
+                "--batchSize", "2", "--lambda_IP", "0", "--pretrained_model_path_E", pth, "--sourcefile_A", pth, "--dataroot", tmp,
+                "--embedding_bins", "[-2,-1,0,1,2]", "--checkpoints_dir", tmp, "--name", "golden"]
+    try:
+        from options.train_options import TrainOptions
+        from models import create_model
+        opt = TrainOptions().parse()
+        model = create_model(opt)
+        model.setup(opt)
+    finally:
+        sys.argv = argv
+    O.fill_state_dict_(model.netG.state_dict(), 31)
+    O.fill_state_dict_(model.netD.state_dict(), 32)
+    O.fill_state_dict_(model.netE.state_dict(), 33)
+    steps = []
+    for it in range(2):
+        a, b, label = O.synthetic_batch(2, 128, 200 + it)
+        model.set_input({"A": a, "B": b, "label": label, "A_paths": ["a"] * 2, "B_paths": ["b"] * 2})
+        model.optimize_parameters()
+        steps.append({k: float(v) for k, v in model.get_current_losses().items()})
+        if it == 0:
+            extra = {"fake_b_sub": sub(model.fake_B.detach(), 8), "y_b": model.y_B.clone(),
+                     "g_w_after": model.netG.state_dict()["model.10.conv_block.1.weight"][:4, :4].clone(),
+                     "d_w_after": model.netD.state_dict()["model.2.weight"][:4, :4].clone()}
+    torch.save({"seeds": (31, 32, 33), "batch_seeds": (200, 201), "steps": steps, "extra": extra}, os.path.join(HERE, "step.pt"))
+    print(steps)
+
+
+if __name__ == "__main__":
+    golden_losses()
+    golden_generator()
+    golden_discriminator()
+    golden_encoder()
+    golden_step()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

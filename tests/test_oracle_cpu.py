@@ -1,0 +1,121 @@
+"""Pins oracle/pcgan_oracle.py to the reference: replays the golden fixtures produced by
+tests/golden/make_golden.py (which ran the unmodified phymhan/pc-gan modules and its
+WSGANEmbModel.optimize_parameters on the CPU) and requires fp32 agreement."""
+import os
+
+import pytest
+import torch
+
+from oracle import pcgan_oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(G, name), weights_only=False)
+
+
+def close(a, b, tol=2e-5):
+    a, b = torch.as_tensor(a, dtype=torch.float32), torch.as_tensor(b, dtype=torch.float32)
+    return float((a - b).norm()) <= tol * float(b.norm()) + 1e-7
+
+
+def test_generator_small_forward_backward_and_running_stats():
+    fx = load("generator_small.pt")
+    sd = O.make_state_dict(O.generator_keys(ngf=fx["ngf"]), fx["seed"], requires_grad=True)
+    a, _, _ = O.synthetic_batch(2, 32, fx["x_seed"])
+    a.requires_grad_(True)
+    out = O.generator_forward(sd, a, fx["z"])
+    assert close(out, fx["out"])
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    assert close(a.grad, fx["dx"], 1e-4)
+    for k, g in fx["grads"].items():
+        assert close(sd[k].grad, g, 1e-4), k
+    for k, v in fx["running"].items():
+        assert close(sd[k], v), k
+
+
+def test_generator_full_size():
+    fx = load("generator_full.pt")
+    sd = O.make_state_dict(O.generator_keys(), fx["seed"])
+    a, _, _ = O.synthetic_batch(1, 128, fx["x_seed"])
+    with torch.no_grad():
+        out = O.generator_forward(sd, a, torch.tensor([fx["z"]]).view(1, 1, 1, 1))
+    assert close(out[..., ::8, ::8], fx["out_sub"], 1e-4)
+    assert abs(float(out.std()) - float(fx["out_std"])) < 1e-5
+
+
+def test_discriminator_small_with_ganloss():
+    fx = load("discriminator_small.pt")
+    sd = O.make_state_dict(O.discriminator_keys(ndf=fx["ndf"]), fx["seed"], requires_grad=True)
+    a, _, _ = O.synthetic_batch(3, 32, fx["x_seed"])
+    a.requires_grad_(True)
+    out = O.discriminator_forward(sd, a, fx["z"])
+    assert close(out, fx["out"])
+    loss = O.gan_loss(out, [1, 0, 1])
+    assert close(loss, fx["loss"])
+    loss.backward()
+    assert close(a.grad, fx["dx"], 1e-4)
+    for k, g in fx["grads"].items():
+        assert close(sd[k].grad, g, 1e-4), k
+    for k, v in fx["running"].items():
+        assert close(sd[k].float(), v.float()), k
+
+
+def test_encoder_keys_forward_backward():
+    fx = load("encoder.pt")
+    keys = O.encoder_keys()
+    assert list(keys.keys()) == fx["keys"]
+    sd = O.make_state_dict(keys, fx["seed"])
+    a, _, _ = O.synthetic_batch(2, 64, fx["x_seed"])
+    a.requires_grad_(True)
+    y = O.encoder_forward(sd, a)
+    assert close(y, fx["y"], 1e-4)
+    (y * torch.tensor([1.0, -2.0]).view(2, 1, 1, 1)).sum().backward()
+    assert close(a.grad[..., ::4, ::4], fx["dx_sub"], 2e-4)
+    for k, v in fx["running"].items():
+        assert close(sd[k], v, 1e-4), k
+    fx = load("encoder_noisy.pt")
+    keys = O.encoder_keys(noisy=True)
+    assert list(keys.keys()) == fx["keys"]
+    sd = O.make_state_dict(keys, fx["seed"])
+    with torch.no_grad():
+        y, lv = O.encoder_forward(sd, a.detach(), noisy=True)
+    assert close(y, fx["y"], 1e-4) and close(lv, fx["logvar"], 1e-4)
+
+
+def test_losses_and_upsample():
+    fx = load("losses.pt")
+    for name, tgt in (("true", True), ("false", False), ("mixed", [1, 0])):
+        p = fx["p"].clone().requires_grad_(True)
+        l = O.gan_loss(p, tgt)
+        l.backward()
+        assert close(l, fx["bce_" + name][0]) and close(p.grad, fx["bce_" + name][1]), name
+    p2 = fx["p2"].clone().requires_grad_(True)
+    l = O.gan_loss(p2, [1, 0], use_lsgan=True)
+    l.backward()
+    assert close(l, fx["mse_mixed"][0]) and close(p2.grad, fx["mse_mixed"][1])
+    assert close(O.elo_nll(fx["elo_prob"], fx["elo_label"]), fx["elo_loss"])
+    assert close(O.upsample2d(fx["up_in"], 9), fx["up_out"])
+
+
+def test_two_training_steps_match_reference():
+    """The whole step (forward, backward_G + Adam, backward_D + Adam) against the reference's
+    optimize_parameters: all nine losses of two consecutive steps, and updated weights after step 1."""
+    fx = load("step.pt")
+    torch.set_num_threads(8)
+    sg, sd_, se = fx["seeds"]
+    m = O.WSGANEmbOracle(O.make_state_dict(O.generator_keys(), sg, requires_grad=True),
+                         O.make_state_dict(O.discriminator_keys(), sd_, requires_grad=True),
+                         O.make_state_dict(O.encoder_keys(), se))
+    for it, want in enumerate(fx["steps"]):
+        a, b, label = O.synthetic_batch(2, 128, fx["batch_seeds"][it])
+        got = m.optimize_parameters(a, b, label)
+        for k in ("G_GAN", "G_cycle", "z_rec", "D_real_right", "D_real_wrong", "D_fake"):
+            assert abs(got[k] - want[k]) <= 2e-4 * abs(want[k]) + 1e-7, (it, k, got[k], want[k])
+        if it == 0:
+            assert close(m.fake_b.detach()[..., ::8, ::8], fx["extra"]["fake_b_sub"], 1e-4)
+            assert close(m.y_b, fx["extra"]["y_b"], 1e-4)
+            assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["extra"]["g_w_after"], 1e-4)
+            assert close(m.d["model.2.weight"][:4, :4], fx["extra"]["d_w_after"], 1e-4)
