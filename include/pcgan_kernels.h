@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 3
+#define PCGAN_ABI_VERSION 4
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -160,12 +160,13 @@ int pcgan_scatter_f32(const float* src, const int32_t* idx, float* dst, int64_t 
 /* NCHW fp32 image [N][Cs][H][W] (+ optional per-sample scalar z[N] appended as
  * channel Cs: networks.py:610-611, :780-782 torch.cat((input, z_img), 1)),
  * optionally bilinearly resized to Ho x Wo with align_corners=True
- * (util/util.py:111-117) and multiplied by (1 - t*t) of a second NCHW tensor
- * (tanh backward), -> padded NHWC bf16 [N][Ho+2p][Wo+2p][Cd].
+ * (util/util.py:111-117) and multiplied by act'(t) of a second NCHW tensor t holding the
+ * activation's OUTPUT (mul_kind PCGAN_ACT_TANH: 1 - t*t, PCGAN_ACT_SIGMOID: t*(1-t); the
+ * backward of nn.Tanh / nn.Sigmoid), -> padded NHWC bf16 [N][Ho+2p][Wo+2p][Cd].
  * Under reflect halo the z plane stays constant; under zero halo it is 0 in the
  * halo, exactly as ReflectionPad2d / Conv2d(padding=1) see it. */
 typedef struct {
-  const float* src; const float* z; const float* tanh_out;
+  const float* src; const float* z; const float* mul_out; int32_t mul_kind;
   void* dst;
   int32_t n, cs, h, w;     /* source geometry                                  */
   int32_t ho, wo;          /* destination interior (== h,w when not resizing)  */
@@ -173,6 +174,12 @@ typedef struct {
   int64_t dst_n_stride;    /* elements between samples (0: packed)             */
 } pcgan_pack_args;
 int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t stream);
+
+/* Bilinear resize with align_corners=True of NCHW fp32 planes [planes][h][w] -> [planes][ho][wo]
+ * (util.upsample2d, util/util.py:111-117) and its adjoint (dst[planes][h][w] = sum of the
+ * resized-grid gradients weighted by their interpolation coefficients). */
+int pcgan_resize_nchw_fwd(const float* src, float* dst, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo, pcgan_stream_t stream);
+int pcgan_resize_nchw_bwd(const float* gdst, float* gsrc, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo, pcgan_stream_t stream);
 
 /* Adjoint of the bilinear resize above, reading an NHWC bf16 gradient
  * [N][Hs+2p][Ws+2p][C] (interior only) and writing / accumulating NCHW fp32
@@ -278,7 +285,8 @@ int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint8_t* idx, v
  * grad (optional) = weight * dmean/dp, same shape as p. */
 typedef struct {
   int32_t kind; const float* p; const float* target; int64_t n; int64_t per_sample;
-  float weight; float* loss; float* grad;
+  float weight; const float* weight_dev; /* optional device scalar multiplied into weight */
+  float* loss; float* grad;
 } pcgan_loss_args;
 int pcgan_loss(const pcgan_loss_args* a, pcgan_stream_t stream);
 

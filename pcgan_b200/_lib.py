@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -51,7 +51,7 @@ class IgemmDesc(C.Structure):
 
 
 class PackArgs(C.Structure):
-    _fields_ = [("src", vp), ("z", vp), ("tanh_out", vp), ("dst", vp),
+    _fields_ = [("src", vp), ("z", vp), ("mul_out", vp), ("mul_kind", i32), ("dst", vp),
                 ("n", i32), ("cs", i32), ("h", i32), ("w", i32), ("ho", i32), ("wo", i32),
                 ("cd", i32), ("pad", i32), ("halo", i32), ("dst_n_stride", i64)]
 
@@ -95,7 +95,7 @@ class MaxpoolArgs(C.Structure):
 
 class LossArgs(C.Structure):
     _fields_ = [("kind", i32), ("p", vp), ("target", vp), ("n", i64), ("per_sample", i64),
-                ("weight", f32), ("loss", vp), ("grad", vp)]
+                ("weight", f32), ("weight_dev", vp), ("loss", vp), ("grad", vp)]
 
 
 _STRUCTS = {
@@ -116,6 +116,8 @@ SYMBOLS = {
     "pcgan_gather_cast_bf16": (C.c_int, [vp, vp, vp, i64, vp]),
     "pcgan_scatter_f32": (C.c_int, [vp, vp, vp, i64, i32, vp]),
     "pcgan_pack_nchw": (C.c_int, [C.POINTER(PackArgs), vp]),
+    "pcgan_resize_nchw_fwd": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp]),
+    "pcgan_resize_nchw_bwd": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "pcgan_unpack_resize_bwd": (C.c_int, [C.POINTER(UnpackArgs), vp]),
     "pcgan_norm_finalize": (C.c_int, [C.POINTER(NormFinalizeArgs), vp]),
     "pcgan_norm_apply": (C.c_int, [C.POINTER(NormApplyArgs), vp]),

@@ -100,9 +100,9 @@ __global__ void pack_nchw_kernel(pcgan_pack_args a) {
               ly1 * (lx0 * s[y1 * a.w + x0] + lx1 * s[y1 * a.w + x1]);
         } else {
           v = s[y * a.w + x];
-          if (a.tanh_out) {
-            const float t = a.tanh_out[(static_cast<int64_t>(n) * a.cs + c) * a.h * a.w + y * a.w + x];
-            v *= 1.f - t * t;
+          if (a.mul_out) {
+            const float t = a.mul_out[(static_cast<int64_t>(n) * a.cs + c) * a.h * a.w + y * a.w + x];
+            v *= a.mul_kind == PCGAN_ACT_SIGMOID ? t * (1.f - t) : 1.f - t * t;
           }
         }
       } else if (c == a.cs && a.z != nullptr) {
@@ -158,6 +158,53 @@ __global__ void unpack_resize_bwd_kernel(pcgan_unpack_args a) {
       const float v = acc[c] * a.scale;
       *d = a.accumulate ? *d + v : v;
     }
+  }
+}
+
+__global__ void resize_nchw_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t planes, int h, int w,
+                                       int ho, int wo) {
+  const int64_t total = planes * ho * wo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % wo);
+    const int y = static_cast<int>((i / wo) % ho);
+    const int64_t pl = i / (static_cast<int64_t>(wo) * ho);
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    bilinear_setup(y, h, ho, y0, y1, ly0, ly1);
+    bilinear_setup(x, w, wo, x0, x1, lx0, lx1);
+    const float* s = src + pl * h * w;
+    dst[i] = ly0 * (lx0 * s[y0 * w + x0] + lx1 * s[y0 * w + x1]) + ly1 * (lx0 * s[y1 * w + x0] + lx1 * s[y1 * w + x1]);
+  }
+}
+
+__global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __restrict__ gsrc, int64_t planes, int h, int w,
+                                       int ho, int wo) {
+  const int64_t total = planes * h * w;
+  const float sy = ho > 1 ? static_cast<float>(h - 1) / static_cast<float>(ho - 1) : 0.f;
+  const float sx = wo > 1 ? static_cast<float>(w - 1) / static_cast<float>(wo - 1) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const int64_t pl = i / (static_cast<int64_t>(w) * h);
+    int ylo = sy > 0.f ? static_cast<int>(floorf((y - 1) / sy)) : 0;
+    int yhi = sy > 0.f ? static_cast<int>(ceilf((y + 1) / sy)) : ho - 1;
+    int xlo = sx > 0.f ? static_cast<int>(floorf((x - 1) / sx)) : 0;
+    int xhi = sx > 0.f ? static_cast<int>(ceilf((x + 1) / sx)) : wo - 1;
+    ylo = max(ylo, 0); xlo = max(xlo, 0); yhi = min(yhi, ho - 1); xhi = min(xhi, wo - 1);
+    const float* g = gdst + pl * ho * wo;
+    float acc = 0.f;
+    for (int yy = ylo; yy <= yhi; ++yy) {
+      int y0, y1; float l0, l1;
+      bilinear_setup(yy, h, ho, y0, y1, l0, l1);
+      const float wy = (y0 == y ? l0 : 0.f) + (y1 == y ? l1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int xx = xlo; xx <= xhi; ++xx) {
+        int x0, x1; float m0, m1;
+        bilinear_setup(xx, w, wo, x0, x1, m0, m1);
+        const float wx = (x0 == x ? m0 : 0.f) + (x1 == x ? m1 : 0.f);
+        if (wx != 0.f) acc += wy * wx * g[yy * wo + xx];
+      }
+    }
+    gsrc[i] = acc;
   }
 }
 
@@ -468,6 +515,7 @@ __global__ void loss_kernel(pcgan_loss_args a) {
   __shared__ float red[kThreads / 32];
   float acc = 0.f;
   const float invn = 1.f / static_cast<float>(a.n);
+  const float wgt = a.weight * (a.weight_dev ? *a.weight_dev : 1.f);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     const float p = a.p[i];
     const float t = a.per_sample > 0 ? a.target[i / a.per_sample] : a.target[i];
@@ -490,7 +538,7 @@ __global__ void loss_kernel(pcgan_loss_args a) {
       }
     }
     acc += l;
-    if (a.grad) a.grad[i] = a.weight * g * invn;
+    if (a.grad) a.grad[i] = wgt * g * invn;
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -498,7 +546,7 @@ __global__ void loss_kernel(pcgan_loss_args a) {
   if (threadIdx.x < 32) {
     float v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.f;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0 && a.loss) atomicAdd(a.loss, a.weight * v * invn);
+    if (threadIdx.x == 0 && a.loss) atomicAdd(a.loss, wgt * v * invn);
   }
 }
 
@@ -546,10 +594,26 @@ extern "C" int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t s) {
   if (a->cd % 8 != 0 || a->cd < a->cs + (a->z ? 1 : 0)) return fail(PCGAN_ERR_INVALID, "pack_nchw: cd=%d must be a multiple of 8 holding %d channels", a->cd, a->cs + (a->z ? 1 : 0));
   if (a->n < 1 || a->h < 1 || a->w < 1 || a->ho < 1 || a->wo < 1 || a->pad < 0) return fail(PCGAN_ERR_INVALID, "pack_nchw: bad geometry");
   if (a->halo == PCGAN_HALO_REFLECT && (a->pad >= a->ho || a->pad >= a->wo)) return fail(PCGAN_ERR_INVALID, "pack_nchw: reflect pad too large");
-  if (a->tanh_out && (a->ho != a->h || a->wo != a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "pack_nchw: tanh_out with resize");
+  if (a->mul_out && (a->ho != a->h || a->wo != a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "pack_nchw: mul_out with resize");
   const int64_t total = static_cast<int64_t>(a->n) * (a->ho + 2 * a->pad) * (a->wo + 2 * a->pad);
   pack_nchw_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
   PCGAN_LAUNCH_OK("pack_nchw_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_resize_nchw_fwd(const float* src, float* dst, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo,
+                                     pcgan_stream_t s) {
+  if (!src || !dst || planes < 1 || h < 1 || w < 1 || ho < 1 || wo < 1) return fail(PCGAN_ERR_INVALID, "resize_fwd: bad argument");
+  resize_nchw_fwd_kernel<<<grid_for(planes * ho * wo), kThreads, 0, STREAM(s)>>>(src, dst, planes, h, w, ho, wo);
+  PCGAN_LAUNCH_OK("resize_nchw_fwd_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_resize_nchw_bwd(const float* gdst, float* gsrc, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo,
+                                     pcgan_stream_t s) {
+  if (!gdst || !gsrc || planes < 1 || h < 1 || w < 1 || ho < 1 || wo < 1) return fail(PCGAN_ERR_INVALID, "resize_bwd: bad argument");
+  resize_nchw_bwd_kernel<<<grid_for(planes * h * w), kThreads, 0, STREAM(s)>>>(gdst, gsrc, planes, h, w, ho, wo);
+  PCGAN_LAUNCH_OK("resize_nchw_bwd_kernel");
   return PCGAN_OK;
 }
 

@@ -1,0 +1,128 @@
+"""Execution engine shared by the three networks of the wsgan_emb step.
+
+A network at a fixed input geometry is a static program over padded NHWC bf16 buffers:
+  ConvRT   one convolution layer: packed bf16 operands + tcgen05 igemm plans for forward,
+           data-gradient and weight-gradient (pcgan_b200/conv.py plans them)
+  NormRT   one normalisation layer (instance or batch statistics come out of the conv
+           epilogue; finalize + apply + backward are the HBM-bound kernels)
+  Workspace all buffers one forward/backward pair needs, pooled per geometry so that a
+           training step allocates nothing after warm-up
+Only torch tensors (device memory) and the C ABI are used; there is no fallback path.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import conv as CV
+from . import ops
+from .plan import Geom, OutMap, SLACK
+
+
+class ConvRT:
+    """Runtime of one convolution at a fixed geometry.
+
+    weight: the reference-layout fp32 master parameter (OIHW; IOHW if transposed).
+    xg: geometry of the input buffer; out: OutMap of the forward output.
+    dyg: geometry of the output-gradient buffer used by the backward plans."""
+
+    def __init__(self, name, weight, bias, xg: Geom, stride, cp, out: OutMap, *, transposed=False, output_padding=0,
+                 act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, dyg: Optional[Geom] = None,
+                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True):
+        self.name, self.weight, self.bias = name, weight, bias
+        dev = weight.device
+        self.dev = dev
+        shape = tuple(weight.shape)
+        self._wver = None
+        self.fwd = []
+        for sp, wm in CV.conv_fwd_plans(shape, xg, stride, cp, out, transposed=transposed, output_padding=output_padding,
+                                        act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats,
+                                        note=name + ".fwd"):
+            self.fwd.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=torch.bfloat16, device=dev)))
+        self.dgrad = []
+        if want_dgrad and dyg is not None and dx_out is not None:
+            for sp, wm in CV.conv_dgrad_plans(shape, dyg, xg, stride, cp, dx_out, transposed=transposed,
+                                              full_padded=full_padded, note=name + ".dgrad"):
+                self.dgrad.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=torch.bfloat16, device=dev)))
+        self.wgrad = None
+        if want_wgrad and dyg is not None:
+            sp, wm = CV.conv_wgrad_plan(shape, dyg, xg, stride, cp, transposed=transposed, note=name + ".wgrad")
+            self.wgrad = (ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k, dtype=torch.float32, device=dev))
+        self.transposed = transposed
+        self.flops_fwd = sum(g.spec.flops for g, _, _ in self.fwd)
+
+    def pack(self):
+        """Refresh the packed bf16 operands when the master weight changed (optimizer step / load_state_dict)."""
+        v = (self.weight._version, self.weight.data_ptr())
+        if v == self._wver:
+            return
+        w = self.weight.detach()
+        for _, wm, buf in self.fwd:
+            ops.gather_cast_bf16(w, wm, buf)
+        for _, wm, buf in self.dgrad:
+            ops.gather_cast_bf16(w, wm, buf)
+        self._wver = v
+
+    def forward(self, xbuf, out, stats=None):
+        self.pack()
+        b = self.bias.detach() if self.bias is not None else None
+        for g, _, wbuf in self.fwd:
+            g.run(xbuf, wbuf, out, b, stats)
+
+    def backward_data(self, dybuf, dxout):
+        self.pack()
+        for g, _, wbuf in self.dgrad:
+            g.run(dybuf, wbuf, dxout)
+
+    def backward_weight(self, dybuf, xbuf):
+        """Accumulates into weight.grad (allocated on first use)."""
+        g, wm, packed = self.wgrad
+        packed.zero_()
+        if self.transposed:
+            g.run(xbuf, dybuf, packed)     # M side = input activations, N side = dY
+        else:
+            g.run(dybuf, xbuf, packed)
+        if self.weight.grad is None:
+            self.weight.grad = torch.zeros_like(self.weight)
+        ops.scatter_f32(packed, wm, self.weight.grad, accumulate=True)
+
+
+class NormState:
+    """Per-call statistics of one normalisation layer: [groups][C] each (groups = N for instance norm, 1 for batch norm)."""
+
+    def __init__(self, groups, c, dev):
+        self.groups, self.c = groups, c
+        self.stats = torch.zeros(groups, c, 2, device=dev)
+        self.mean = torch.empty(groups, c, device=dev)
+        self.rstd = torch.empty(groups, c, device=dev)
+        self.scale = torch.empty(groups, c, device=dev)
+        self.shift = torch.empty(groups, c, device=dev)
+        self.sums = torch.zeros(groups, c, 2, device=dev)
+
+
+def accumulate_grad(p, g):
+    """p.grad += g (allocating on first use); parameters that are frozen are skipped by the callers."""
+    if p.grad is None:
+        p.grad = g.clone()
+    else:
+        p.grad.add_(g)
+
+
+class Pool:
+    """Workspaces keyed by geometry; a network call takes one and gives it back when its backward has run
+    (or right away when no gradient is needed)."""
+
+    def __init__(self, factory):
+        self.factory = factory
+        self.free: Dict[tuple, list] = {}
+
+    def take(self, key):
+        lst = self.free.setdefault(key, [])
+        return lst.pop() if lst else self.factory(key)
+
+    def give(self, key, ws):
+        self.free.setdefault(key, []).append(ws)
+
+
+def zeros_act(g: Geom, dev):
+    return torch.zeros(g.numel + SLACK, dtype=torch.bfloat16, device=dev)

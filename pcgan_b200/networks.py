@@ -1,0 +1,1021 @@
+"""B200-native drop-ins for the network factory of phymhan/pc-gan (models/networks.py):
+define_G / define_D / define_E / GANLoss with the reference's signatures, forward
+signatures and state_dict key names, whose forward and backward run entirely on the
+hand-written sm_100a kernels behind the C ABI (include/pcgan_kernels.h).
+
+Scope (BASELINE.json north_star): ResnetGenerator (networks.py:565-652),
+NLayerDiscriminator (:737-783), SiameseFeature over ResNetFeature/resnet18
+(:1008-1083, :1310-1359; models/resnet.py), GANLoss (:386-420).  Other values of
+which_model_* raise NotImplementedError.  There is no CPU path: modules must live on a
+CUDA device (gpu_ids non-empty), otherwise forward raises.
+"""
+import functools
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+from . import _lib as L
+from . import ops
+from .engine import ConvRT, NormState, Pool, accumulate_grad, zeros_act
+from .plan import Geom, OutMap
+
+EPS = 1e-5
+MOMENTUM = 0.1
+
+
+# ---------------------------------------------------------------------------------------
+# small shared pieces
+# ---------------------------------------------------------------------------------------
+def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, *, gamma=None, beta=None, rmean=None, rvar=None):
+    """conv (+bias) with statistics in the epilogue, then the tiny finalize kernel."""
+    ns.stats.zero_()
+    conv.forward(xbuf, rbuf, ns.stats)
+    ops.norm_finalize(ns.stats, ns.groups, ns.c, count, eps=EPS, momentum=MOMENTUM, gamma=gamma, beta=beta,
+                      mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, running_mean=rmean, running_var=rvar)
+
+
+def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count, dx, dx_pad, *, res=None, res_pad=0,
+                   res_scale=None, res_shift=None, res_groups=1, dres=None, dres_pad=0):
+    kw = dict(res=res, res_pad=res_pad, mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, groups=ns.groups,
+              res_scale=res_scale, res_shift=res_shift, res_groups=res_groups, act=act, act_slope=slope, count=count,
+              sums=ns.sums)
+    ns.sums.zero_()
+    ops.norm_bwd_reduce(gy, gy_pad, rbuf, rg, **kw)
+    ops.norm_bwd_apply(gy, gy_pad, rbuf, rg, dx=dx, dx_pad=dx_pad, dres=dres, dres_pad=dres_pad, **kw)
+
+
+class _Scratch:
+    """Backward-only buffers of a program, created on first use and reused by every call (one backward at a time)."""
+
+    def __init__(self, dev):
+        self.dev, self.bufs = dev, {}
+
+    def get(self, g: Geom, tag=""):
+        k = (g, tag)
+        if k not in self.bufs:
+            self.bufs[k] = zeros_act(g, self.dev)
+        return self.bufs[k]
+
+
+def _require_cuda(t, who):
+    if not t.is_cuda:
+        raise L.PcganError("%s: pcgan_b200 modules run only on a CUDA device (no CPU fallback); input is on %s" % (who, t.device))
+
+
+# ---------------------------------------------------------------------------------------
+# ResnetGenerator
+# ---------------------------------------------------------------------------------------
+class _GenWorkspace:
+    pass
+
+
+class _GenProgram:
+    """ResnetGenerator at fixed (N, S): reflect-pad 7x7 stem, two stride-2 convs, n_blocks ResnetBlocks,
+    two transposed convs, reflect-pad 7x7 head with tanh (networks.py:578-605), InstanceNorm + ReLU between."""
+
+    def __init__(self, mod, N, S):
+        self.mod, self.N, self.S = mod, N, S
+        dev = mod.model[1].weight.device
+        self.dev = dev
+        ngf, nb = mod.ngf, mod.n_blocks
+        C1, C2, C3 = ngf, 2 * ngf, 4 * ngf
+        h2, h4 = S // 2, S // 4
+        m = mod.model
+        G = Geom
+        self.g_x0 = G(N, S, S, 8, 3)
+        self.g_r1, self.g_a1 = G(N, S, S, C1, 0), G(N, S, S, C1, 1)
+        self.g_r2, self.g_a2 = G(N, h2, h2, C2, 0), G(N, h2, h2, C2, 1)
+        self.g_r3, self.g_b = G(N, h4, h4, C3, 0), G(N, h4, h4, C3, 1)
+        self.g_bfull = G(N, h4 + 2, h4 + 2, C3, 0)
+        self.g_u1r, self.g_u1 = G(N, h2, h2, C2, 0), G(N, h2, h2, C2, 1)
+        self.g_u2r, self.g_u2 = G(N, S, S, C1, 0), G(N, S, S, C1, 3)
+        self.g_u2full = G(N, S + 6, S + 6, C1, 0)
+        self.g_x0full = G(N, S + 6, S + 6, 8, 0)
+        self.g_dyh = G(N, S, S, 8, 6)
+        ps = dict(stats=True, per_sample_stats=True)
+        self.stem = ConvRT("G.model.1", m[1].weight, m[1].bias, self.g_x0, 1, 3, OutMap.nhwc(self.g_r1), dyg=G(N, S, S, C1, 3),
+                           dx_out=OutMap.nhwc(self.g_x0full), full_padded=True, **ps)
+        self.down1 = ConvRT("G.model.4", m[4].weight, m[4].bias, self.g_a1, 2, 1, OutMap.nhwc(self.g_r2), dyg=self.g_r2,
+                            dx_out=OutMap.nhwc(self.g_r1), **ps)
+        self.down2 = ConvRT("G.model.7", m[7].weight, m[7].bias, self.g_a2, 2, 1, OutMap.nhwc(self.g_r3), dyg=self.g_r3,
+                            dx_out=OutMap.nhwc(self.g_r2), **ps)
+        self.blocks = []
+        for i in range(nb):
+            cb = m[10 + i].conv_block
+            ca = ConvRT("G.model.%d.conv_block.1" % (10 + i), cb[1].weight, cb[1].bias, self.g_b, 1, 1, OutMap.nhwc(self.g_r3),
+                        dyg=self.g_b, dx_out=OutMap.nhwc(self.g_bfull), full_padded=True, **ps)
+            cbb = ConvRT("G.model.%d.conv_block.5" % (10 + i), cb[5].weight, cb[5].bias, self.g_b, 1, 1, OutMap.nhwc(self.g_r3),
+                         dyg=self.g_b, dx_out=OutMap.nhwc(self.g_bfull), full_padded=True, **ps)
+            self.blocks.append((ca, cbb, cb[2], cb[6]))
+        b = 10 + nb
+        self.i_up1, self.i_up2, self.i_head = b, b + 3, b + 7
+        self.up1 = ConvRT("G.model.%d" % b, m[b].weight, m[b].bias, self.g_b, 2, 1, OutMap.nhwc(self.g_u1r), transposed=True,
+                          output_padding=1, dyg=self.g_u1, dx_out=OutMap.nhwc(self.g_r3), **ps)
+        self.up2 = ConvRT("G.model.%d" % (b + 3), m[b + 3].weight, m[b + 3].bias, self.g_u1, 2, 1, OutMap.nhwc(self.g_u2r),
+                          transposed=True, output_padding=1, dyg=self.g_a1, dx_out=OutMap.nhwc(self.g_u1r), **ps)
+        self.head = ConvRT("G.model.%d" % (b + 7), m[b + 7].weight, m[b + 7].bias, self.g_u2, 1, 3,
+                           OutMap.nchw(N, mod.output_nc, S, S), act=L.ACT_TANH, dyg=self.g_dyh,
+                           dx_out=OutMap.nhwc(self.g_u2full), full_padded=True)
+        self.scratch = _Scratch(dev)
+        self.pool = Pool(lambda key: self._new_ws())
+        self.convs = [self.stem, self.down1, self.down2] + [c for blk in self.blocks for c in blk[:2]] + [self.up1, self.up2, self.head]
+
+    def _new_ws(self):
+        ws, dev, N = _GenWorkspace(), self.dev, self.N
+        z = lambda g: zeros_act(g, dev)
+        ws.x0, ws.r1, ws.a1, ws.r2, ws.a2, ws.r3 = z(self.g_x0), z(self.g_r1), z(self.g_a1), z(self.g_r2), z(self.g_a2), z(self.g_r3)
+        ws.b = [z(self.g_b) for _ in range(len(self.blocks) + 1)]
+        ws.ra = [z(self.g_r3) for _ in self.blocks]
+        ws.h = [z(self.g_b) for _ in self.blocks]
+        ws.rb = [z(self.g_r3) for _ in self.blocks]
+        ws.u1r, ws.u1, ws.u2r, ws.u2 = z(self.g_u1r), z(self.g_u1), z(self.g_u2r), z(self.g_u2)
+        C1, C2, C3 = self.g_r1.c, self.g_r2.c, self.g_r3.c
+        ws.n1, ws.n2, ws.n3 = NormState(N, C1, dev), NormState(N, C2, dev), NormState(N, C3, dev)
+        ws.na = [NormState(N, C3, dev) for _ in self.blocks]
+        ws.nb = [NormState(N, C3, dev) for _ in self.blocks]
+        ws.nu1, ws.nu2 = NormState(N, C2, dev), NormState(N, C1, dev)
+        return ws
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x, z):
+        m, S, N = self.mod.model, self.S, self.N
+        ws = self.pool.take(0)
+        h2, h4 = S // 2, S // 4
+        ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_REFLECT)
+        _unit_forward(self.stem, ws.x0, ws.r1, ws.n1, S * S, rmean=m[2].running_mean, rvar=m[2].running_var)
+        ops.norm_apply(ws.r1, self.g_r1, ws.a1, self.g_a1, y_halo=L.HALO_ZERO, scale=ws.n1.scale, shift=ws.n1.shift, groups=N, act=L.ACT_RELU)
+        _unit_forward(self.down1, ws.a1, ws.r2, ws.n2, h2 * h2, rmean=m[5].running_mean, rvar=m[5].running_var)
+        ops.norm_apply(ws.r2, self.g_r2, ws.a2, self.g_a2, y_halo=L.HALO_ZERO, scale=ws.n2.scale, shift=ws.n2.shift, groups=N, act=L.ACT_RELU)
+        _unit_forward(self.down2, ws.a2, ws.r3, ws.n3, h4 * h4, rmean=m[8].running_mean, rvar=m[8].running_var)
+        nblk = len(self.blocks)
+        ops.norm_apply(ws.r3, self.g_r3, ws.b[0], self.g_b, y_halo=L.HALO_REFLECT if nblk else L.HALO_ZERO, scale=ws.n3.scale,
+                       shift=ws.n3.shift, groups=N, act=L.ACT_RELU)
+        for i, (ca, cb, na_mod, nb_mod) in enumerate(self.blocks):
+            _unit_forward(ca, ws.b[i], ws.ra[i], ws.na[i], h4 * h4, rmean=na_mod.running_mean, rvar=na_mod.running_var)
+            ops.norm_apply(ws.ra[i], self.g_r3, ws.h[i], self.g_b, y_halo=L.HALO_REFLECT, scale=ws.na[i].scale, shift=ws.na[i].shift,
+                           groups=N, act=L.ACT_RELU)
+            _unit_forward(cb, ws.h[i], ws.rb[i], ws.nb[i], h4 * h4, rmean=nb_mod.running_mean, rvar=nb_mod.running_var)
+            last = i == nblk - 1
+            # x + conv_block(x) (networks.py:650-652): residual added after the norm, no activation
+            ops.norm_apply(ws.rb[i], self.g_r3, ws.b[i + 1], self.g_b, y_halo=L.HALO_ZERO if last else L.HALO_REFLECT,
+                           scale=ws.nb[i].scale, shift=ws.nb[i].shift, groups=N, res=ws.b[i], res_pad=1, act=L.ACT_NONE)
+        _unit_forward(self.up1, ws.b[nblk], ws.u1r, ws.nu1, h2 * h2, rmean=m[self.i_up1 + 1].running_mean, rvar=m[self.i_up1 + 1].running_var)
+        ops.norm_apply(ws.u1r, self.g_u1r, ws.u1, self.g_u1, y_halo=L.HALO_ZERO, scale=ws.nu1.scale, shift=ws.nu1.shift, groups=N, act=L.ACT_RELU)
+        _unit_forward(self.up2, ws.u1, ws.u2r, ws.nu2, S * S, rmean=m[self.i_up2 + 1].running_mean, rvar=m[self.i_up2 + 1].running_var)
+        ops.norm_apply(ws.u2r, self.g_u2r, ws.u2, self.g_u2, y_halo=L.HALO_REFLECT, scale=ws.nu2.scale, shift=ws.nu2.shift, groups=N, act=L.ACT_RELU)
+        out = torch.empty(N, self.mod.output_nc, S, S, device=self.dev)
+        self.head.forward(ws.u2, out)
+        return out, ws
+
+    # --------------------------------------------------------------- backward
+    def backward(self, ws, out, dout, need_dx, need_w):
+        S, N, sc = self.S, self.N, self.scratch
+        h2, h4 = S // 2, S // 4
+        m = self.mod.model
+        nblk = len(self.blocks)
+        R, Z = L.ACT_RELU, L.ACT_NONE
+        # head: d(pre-tanh) = dout * (1 - out^2)
+        dyh = sc.get(self.g_dyh)
+        ops.pack_nchw(dout, dyh, self.g_dyh, mul_out=out, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO)
+        if need_w:
+            self.head.backward_weight(dyh, ws.u2)
+            hs = torch.zeros(1, 8, 2, device=self.dev)
+            ops.norm_bwd_reduce(dyh, 6, dyh, self.g_dyh, sums=hs, count=0.0)
+            accumulate_grad(self.head.bias, hs[0, : self.mod.output_nc, 0])
+        dfull = sc.get(self.g_u2full)
+        self.head.backward_data(dyh, dfull)
+        g = sc.get(self.g_u2r, "g")
+        ops.halo_fold(dfull, self.g_u2, g, 0, halo=L.HALO_REFLECT)
+        # up2 unit
+        dy = sc.get(self.g_a1, "dy")
+        _norm_backward(g, 0, ws.u2r, self.g_u2r, ws.nu2, R, 0.0, S * S, dy, 1)
+        if need_w:
+            self.up2.backward_weight(dy, ws.u1)
+        g = sc.get(self.g_u1r, "g")
+        self.up2.backward_data(dy, g)
+        # up1 unit
+        dy = sc.get(self.g_u1, "dy")
+        _norm_backward(g, 0, ws.u1r, self.g_u1r, ws.nu1, R, 0.0, h2 * h2, dy, 1)
+        if need_w:
+            self.up1.backward_weight(dy, ws.b[nblk])
+        gb = sc.get(self.g_r3, "gb0")
+        self.up1.backward_data(dy, gb)
+        # residual blocks, last to first; gb = gradient of the block output
+        for i in range(nblk - 1, -1, -1):
+            ca, cb, _, _ = self.blocks[i]
+            dyb = sc.get(self.g_b, "dyb")
+            _norm_backward(gb, 0, ws.rb[i], self.g_r3, ws.nb[i], Z, 0.0, h4 * h4, dyb, 1, res=ws.b[i], res_pad=1)
+            if need_w:
+                cb.backward_weight(dyb, ws.h[i])
+            dfull = sc.get(self.g_bfull, "dfull")
+            cb.backward_data(dyb, dfull)
+            gh = sc.get(self.g_r3, "gh")
+            ops.halo_fold(dfull, self.g_b, gh, 0, halo=L.HALO_REFLECT)
+            dya = sc.get(self.g_b, "dya")
+            _norm_backward(gh, 0, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1)
+            if need_w:
+                ca.backward_weight(dya, ws.b[i])
+            ca.backward_data(dya, dfull)
+            gprev = sc.get(self.g_r3, "gb%d" % ((nblk - i) % 2))
+            ops.halo_fold(dfull, self.g_b, gprev, 0, halo=L.HALO_REFLECT, add=gb, add_pad=0)
+            gb = gprev
+        # down2 unit (its output buffer ws.b[0])
+        dy = sc.get(self.g_r3, "dy3")
+        _norm_backward(gb, 0, ws.r3, self.g_r3, ws.n3, R, 0.0, h4 * h4, dy, 0)
+        if need_w:
+            self.down2.backward_weight(dy, ws.a2)
+        g = sc.get(self.g_r2, "g")
+        self.down2.backward_data(dy, g)
+        dy = sc.get(self.g_r2, "dy2")
+        _norm_backward(g, 0, ws.r2, self.g_r2, ws.n2, R, 0.0, h2 * h2, dy, 0)
+        if need_w:
+            self.down1.backward_weight(dy, ws.a1)
+        g = sc.get(self.g_r1, "g")
+        self.down1.backward_data(dy, g)
+        # stem unit
+        dy = sc.get(Geom(N, S, S, self.g_r1.c, 3), "dy1")
+        _norm_backward(g, 0, ws.r1, self.g_r1, ws.n1, R, 0.0, S * S, dy, 3)
+        if need_w:
+            self.stem.backward_weight(dy, ws.x0)
+        dx = None
+        if need_dx:
+            dfull = sc.get(self.g_x0full)
+            self.stem.backward_data(dy, dfull)
+            gx = sc.get(Geom(N, S, S, 8, 0), "gx")
+            ops.halo_fold(dfull, self.g_x0, gx, 0, halo=L.HALO_REFLECT)
+            dx = torch.empty(N, self.mod.input_nc_img, S, S, device=self.dev)
+            ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dx)
+        if need_w:
+            # biases in front of an affine-less InstanceNorm have exactly zero gradient
+            for c in self.convs[:-1]:
+                if c.bias is not None and c.bias.grad is None:
+                    c.bias.grad = torch.zeros_like(c.bias)
+        return dx
+
+
+class _GenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, z, *params):
+        prog = mod._program(x.shape[0], x.shape[2])
+        out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
+        # needs_input_grad already folds in the global grad mode (forward itself runs with grad disabled)
+        if ctx.needs_input_grad[1] or any(ctx.needs_input_grad[3:]):
+            ctx.prog, ctx.ws = prog, ws
+            ctx.save_for_backward(out)
+            ctx.need_w = any(ctx.needs_input_grad[3:])
+        else:
+            prog.pool.give(0, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        prog, ws = ctx.prog, ctx.ws
+        dx = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w)
+        prog.pool.give(0, ws)
+        ctx.ws = None
+        return (None, dx, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+
+
+class _ResnetBlockHolder(nn.Module):
+    """Parameter holder with the reference's names: conv_block.{1,5} convs, conv_block.{2,6} norms (networks.py:621-648)."""
+
+    def __init__(self, dim, norm_layer, use_bias):
+        super().__init__()
+        self.conv_block = nn.Sequential(
+            nn.Identity(), nn.Conv2d(dim, dim, 3, bias=use_bias), norm_layer(dim), nn.Identity(),
+            nn.Identity(), nn.Conv2d(dim, dim, 3, bias=use_bias), norm_layer(dim))
+
+
+class ResnetGenerator(nn.Module):
+    """Same constructor, forward signature and state_dict keys as models/networks.py:565-612; `model` only holds the
+    parameters and running statistics (its torch forward is never called) — the math runs in _GenProgram."""
+
+    def __init__(self, input_nc, output_nc, nz=0, ngf=64, norm_layer=nn.BatchNorm2d, dropout=0, n_blocks=6, padding_type="reflect"):
+        super().__init__()
+        func = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
+        if func is not nn.InstanceNorm2d or padding_type != "reflect" or dropout:
+            raise NotImplementedError("pcgan_b200 ResnetGenerator: instance norm, reflect padding, no dropout (the wsgan_emb configuration)")
+        if ngf % 64 != 0:
+            raise NotImplementedError("pcgan_b200 ResnetGenerator needs ngf to be a multiple of 64 (tcgen05 K chunk); got %d" % ngf)
+        if input_nc + nz > 8 or output_nc > 8:
+            raise NotImplementedError("input_nc + nz and output_nc must be <= 8")
+        self.input_nc_img, self.input_nc, self.output_nc, self.ngf, self.n_blocks, self.nz = input_nc, input_nc + nz, output_nc, ngf, n_blocks, nz
+        layers = [nn.Identity(), nn.Conv2d(input_nc + nz, ngf, 7), norm_layer(ngf), nn.Identity()]
+        for i in range(2):
+            c = ngf * 2 ** i
+            layers += [nn.Conv2d(c, 2 * c, 3, stride=2, padding=1), norm_layer(2 * c), nn.Identity()]
+        for _ in range(n_blocks):
+            layers.append(_ResnetBlockHolder(4 * ngf, norm_layer, True))
+        for i in range(2):
+            c = ngf * 2 ** (2 - i)
+            layers += [nn.ConvTranspose2d(c, c // 2, 3, stride=2, padding=1, output_padding=1), norm_layer(c // 2), nn.Identity()]
+        layers += [nn.Identity(), nn.Conv2d(ngf, output_nc, 7), nn.Identity()]
+        self.model = nn.Sequential(*layers)
+        self._programs = {}
+
+    def _program(self, n, s):
+        k = (n, s, self.model[1].weight.device)
+        if k not in self._programs:
+            self._programs[k] = _GenProgram(self, n, s)
+        return self._programs[k]
+
+    def forward(self, input, z=None):
+        _require_cuda(input, "ResnetGenerator")
+        if input.shape[2] != input.shape[3] or input.shape[2] % 4:
+            raise NotImplementedError("square inputs with side a multiple of 4")
+        if z is None or self.nz != 1:
+            raise NotImplementedError("ResnetGenerator needs the 1-channel embedding z (nz=1)")
+        if z.requires_grad:
+            raise NotImplementedError("gradient w.r.t. the embedding z (lr_E > 0) is not implemented")
+        return _GenFn.apply(self, input, z, *self.parameters())
+
+
+# ---------------------------------------------------------------------------------------
+# NLayerDiscriminator
+# ---------------------------------------------------------------------------------------
+class _DiscWorkspace:
+    pass
+
+
+class _DiscProgram:
+    """NLayerDiscriminator(n_layers=3) at fixed (N, S): conv4x4s2+LReLU, 2x (conv4x4s2 + BN + LReLU),
+    conv4x4s1 + BN + LReLU, conv4x4s1 -> 1 (+ sigmoid) (networks.py:745-777)."""
+
+    def __init__(self, mod, N, S):
+        self.mod, self.N, self.S = mod, N, S
+        m = mod.model
+        dev = m[0].weight.device
+        self.dev = dev
+        ndf = mod.ndf
+        G = Geom
+        self.g_x0 = G(N, S, S, 8, 1)
+        sizes, chans = [S // 2], [ndf]
+        self.idx = [0]
+        i = 2
+        for n in range(1, mod.n_layers):
+            sizes.append(sizes[-1] // 2); chans.append(ndf * min(2 ** n, 8)); self.idx.append(i); i += 3
+        sizes.append(sizes[-1] - 1); chans.append(ndf * min(2 ** mod.n_layers, 8)); self.idx.append(i); i += 3
+        self.i_head = i
+        self.sizes, self.chans = sizes, chans
+        self.g_y = [G(N, s, s, c, 1) for s, c in zip(sizes, chans)]      # activations (zero halo, pad 1)
+        self.g_r = [G(N, s, s, c, 0) for s, c in zip(sizes, chans)]      # raw conv outputs / gradients
+        so = sizes[-1] - 1
+        self.so = so
+        self.convs = []
+        # layer 0: bias + LeakyReLU in the epilogue, written straight into the next padded buffer
+        self.convs.append(ConvRT("D.model.0", m[0].weight, m[0].bias, self.g_x0, 2, 1, OutMap.nhwc(self.g_y[0]), act=L.ACT_LRELU,
+                                 act_slope=0.2, dyg=self.g_r[0], dx_out=OutMap.nhwc(G(N, S, S, 8, 0))))
+        for li in range(1, len(sizes)):
+            stride = 2 if li < len(sizes) - 1 else 1
+            self.convs.append(ConvRT("D.model.%d" % self.idx[li], m[self.idx[li]].weight, None, self.g_y[li - 1], stride, 1,
+                                     OutMap.nhwc(self.g_r[li]), stats=True, dyg=self.g_r[li], dx_out=OutMap.nhwc(self.g_r[li - 1])))
+        self.g_dyh = G(N, so, so, 8, 2)
+        self.head = ConvRT("D.model.%d" % self.i_head, m[self.i_head].weight, m[self.i_head].bias, self.g_y[-1], 1, 1,
+                           OutMap.nchw(N, 1, so, so), act=L.ACT_SIGMOID if mod.use_sigmoid else L.ACT_NONE, dyg=self.g_dyh,
+                           dx_out=OutMap.nhwc(self.g_r[-1]))
+        self.scratch = _Scratch(dev)
+        self.pool = Pool(lambda key: self._new_ws())
+
+    def _new_ws(self):
+        ws, dev = _DiscWorkspace(), self.dev
+        ws.x0 = zeros_act(self.g_x0, dev)
+        ws.y = [zeros_act(g, dev) for g in self.g_y]
+        ws.r = [None] + [zeros_act(g, dev) for g in self.g_r[1:]]
+        ws.ns = [None] + [NormState(1, c, dev) for c in self.chans[1:]]
+        return ws
+
+    def forward(self, x, z):
+        m, N = self.mod.model, self.N
+        ws = self.pool.take(0)
+        ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_ZERO)
+        self.convs[0].forward(ws.x0, ws.y[0])
+        for li in range(1, len(self.sizes)):
+            bn = m[self.idx[li] + 1]
+            cnt = N * self.sizes[li] ** 2
+            _unit_forward(self.convs[li], ws.y[li - 1], ws.r[li], ws.ns[li], cnt, gamma=bn.weight.detach(), beta=bn.bias.detach(),
+                          rmean=bn.running_mean, rvar=bn.running_var)
+            bn.num_batches_tracked += 1
+            ops.norm_apply(ws.r[li], self.g_r[li], ws.y[li], self.g_y[li], y_halo=L.HALO_ZERO, scale=ws.ns[li].scale,
+                           shift=ws.ns[li].shift, groups=1, act=L.ACT_LRELU, act_slope=0.2)
+        out = torch.empty(N, 1, self.so, self.so, device=self.dev)
+        self.head.forward(ws.y[-1], out)
+        return out, ws
+
+    def backward(self, ws, out, dout, need_dx, need_w):
+        m, N, sc = self.mod.model, self.N, self.scratch
+        dyh = sc.get(self.g_dyh)
+        if self.mod.use_sigmoid:
+            ops.pack_nchw(dout, dyh, self.g_dyh, mul_out=out, mul_kind=L.ACT_SIGMOID, halo=L.HALO_ZERO)
+        else:
+            ops.pack_nchw(dout, dyh, self.g_dyh, halo=L.HALO_ZERO)
+        if need_w:
+            self.head.backward_weight(dyh, ws.y[-1])
+            hs = torch.zeros(1, 8, 2, device=self.dev)
+            ops.norm_bwd_reduce(dyh, 2, dyh, self.g_dyh, sums=hs, count=0.0)
+            accumulate_grad(self.head.bias, hs[0, :1, 0])
+        g = sc.get(self.g_r[-1], "g%d" % (len(self.sizes) - 1))
+        self.head.backward_data(dyh, g)
+        for li in range(len(self.sizes) - 1, 0, -1):
+            bn = m[self.idx[li] + 1]
+            cnt = N * self.sizes[li] ** 2
+            dy = sc.get(self.g_r[li], "dy%d" % li)
+            _norm_backward(g, 0, ws.r[li], self.g_r[li], ws.ns[li], L.ACT_LRELU, 0.2, cnt, dy, 0)
+            if need_w:
+                accumulate_grad(bn.weight, ws.ns[li].sums[0, :, 1])
+                accumulate_grad(bn.bias, ws.ns[li].sums[0, :, 0])
+                self.convs[li].backward_weight(dy, ws.y[li - 1])
+            g = sc.get(self.g_r[li - 1], "g%d" % (li - 1))
+            self.convs[li].backward_data(dy, g)
+        # layer 0: LeakyReLU backward from the sign of the stored output, bias gradient = sum
+        dy = sc.get(self.g_r[0], "dy0")
+        s0 = torch.zeros(1, self.chans[0], 2, device=self.dev)
+        kw = dict(act=L.ACT_LRELU, act_slope=0.2, count=0.0, sums=s0)
+        ops.norm_bwd_reduce(g, 0, ws.y[0], self.g_y[0], **kw)
+        ops.norm_bwd_apply(g, 0, ws.y[0], self.g_y[0], dx=dy, dx_pad=0, **kw)
+        if need_w:
+            accumulate_grad(self.convs[0].bias, s0[0, :, 0])
+            self.convs[0].backward_weight(dy, ws.x0)
+        dx = None
+        if need_dx:
+            gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
+            self.convs[0].backward_data(dy, gx)
+            dx = torch.empty(N, self.mod.input_nc_img, self.S, self.S, device=self.dev)
+            ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dx)
+        return dx
+
+
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, z, *params):
+        prog = mod._program(x.shape[0], x.shape[2])
+        out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
+        # needs_input_grad already folds in the global grad mode (forward itself runs with grad disabled)
+        if ctx.needs_input_grad[1] or any(ctx.needs_input_grad[3:]):
+            ctx.prog, ctx.ws = prog, ws
+            ctx.save_for_backward(out)
+            ctx.need_w = any(ctx.needs_input_grad[3:])
+        else:
+            prog.pool.give(0, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        prog, ws = ctx.prog, ctx.ws
+        dx = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w)
+        prog.pool.give(0, ws)
+        ctx.ws = None
+        return (None, dx, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+
+
+class NLayerDiscriminator(nn.Module):
+    """Same constructor / forward / state_dict keys as models/networks.py:737-783 (BatchNorm2d, conditional z channel)."""
+
+    def __init__(self, input_nc, nz, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_sigmoid=False):
+        super().__init__()
+        func = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
+        if func is not nn.BatchNorm2d:
+            raise NotImplementedError("pcgan_b200 NLayerDiscriminator: batch norm (the wsgan_emb configuration)")
+        if ndf % 64 != 0 or input_nc + nz > 8 or nz != 1:
+            raise NotImplementedError("ndf must be a multiple of 64, nz == 1, input_nc + nz <= 8")
+        self.input_nc_img, self.ndf, self.n_layers, self.use_sigmoid = input_nc, ndf, n_layers, use_sigmoid
+        seq = [nn.Conv2d(input_nc + nz, ndf, 4, stride=2, padding=1), nn.Identity()]
+        prev = ndf
+        for n in range(1, n_layers + 1):
+            cur = ndf * min(2 ** n, 8)
+            seq += [nn.Conv2d(prev, cur, 4, stride=2 if n < n_layers else 1, padding=1, bias=False), norm_layer(cur), nn.Identity()]
+            prev = cur
+        seq += [nn.Conv2d(prev, 1, 4, stride=1, padding=1)]
+        if use_sigmoid:
+            seq += [nn.Identity()]
+        self.model = nn.Sequential(*seq)
+        self._programs = {}
+
+    def _program(self, n, s):
+        k = (n, s, self.model[0].weight.device)
+        if k not in self._programs:
+            self._programs[k] = _DiscProgram(self, n, s)
+        return self._programs[k]
+
+    def forward(self, input, z=None):
+        _require_cuda(input, "NLayerDiscriminator")
+        if z is None:
+            raise NotImplementedError("NLayerDiscriminator needs the embedding z")
+        if input.shape[2] != input.shape[3] or input.shape[2] % (2 ** self.n_layers):
+            raise NotImplementedError("square inputs with side a multiple of %d" % 2 ** self.n_layers)
+        return _DiscFn.apply(self, input, z.detach(), *self.parameters())
+
+
+# ---------------------------------------------------------------------------------------
+# GANLoss and the scalar losses of the step
+# ---------------------------------------------------------------------------------------
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kind, pred, target, per_sample):
+        p = pred.contiguous().float()
+        out = torch.zeros((), device=p.device)
+        ops.loss(kind, p, target, per_sample=per_sample, loss_out=out)
+        ctx.kind, ctx.per_sample = kind, per_sample
+        ctx.save_for_backward(p, target)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        p, target = ctx.saved_tensors
+        grad = torch.empty_like(p)
+        ops.loss(ctx.kind, p, target, per_sample=ctx.per_sample, weight=1.0, weight_dev=gout.contiguous().float(), grad=grad)
+        return None, grad, None, None
+
+
+def l1_loss(a, b):
+    """nn.L1Loss() (wsgan_emb_model.py:142,149): mean |a - b|; gradient flows to `a` only (b is data)."""
+    return _LossFn.apply(L.LOSS_L1, a, b.detach().contiguous().float(), 0)
+
+
+def mse_loss(a, b):
+    """nn.MSELoss() (wsgan_emb_model.py:148): mean (a - b)^2; gradient flows to `a` only."""
+    return _LossFn.apply(L.LOSS_MSE, a, b.detach().contiguous().float(), 0)
+
+
+class GANLoss(nn.Module):
+    """GANLoss (networks.py:386-420): per-sample targets (bool / int / list of them, one per batch element) expanded
+    over the prediction map; nn.BCELoss on the sigmoid output (log clamped at -100) or nn.MSELoss when use_lsgan."""
+
+    def __init__(self, use_lsgan=True, tensor=torch.FloatTensor):
+        super().__init__()
+        self.kind = L.LOSS_MSE if use_lsgan else L.LOSS_BCE
+        self.Tensor = tensor
+
+    def get_target_tensor(self, input, target_label):
+        if not isinstance(target_label, list):
+            target_label = [target_label]
+        vals = [float(int(t)) for t in target_label]
+        return torch.tensor(np.array(vals, dtype=np.float32), device=input.device)
+
+    def __call__(self, inputs, target_label):
+        if not isinstance(inputs, list):
+            inputs = [inputs]
+        loss = 0.0
+        for inp in inputs:
+            if inp.dim() < 4:
+                inp = inp.view(inp.size(0), -1, 1, 1)
+            _require_cuda(inp, "GANLoss")
+            t = self.get_target_tensor(inp, target_label)
+            n = inp.size(0)
+            if t.numel() == 1 and n > 1:
+                t = t.expand(n).contiguous()
+            loss = loss + _LossFn.apply(self.kind, inp, t, inp.numel() // n)
+        return loss
+
+
+class BinaryNLLLoss(nn.Module):
+    """Elo pairwise loss (networks.py:473-482): target LUT[label] in {0, .5, 1}, -mean(t log(p+1e-20) + (1-t) log(1-p+1e-20))."""
+
+    def __call__(self, prob, label):
+        lut = torch.tensor([0.0, 0.5, 1.0], device=prob.device)
+        t = lut[label.to(prob.device)].contiguous()
+        return _LossFn.apply(L.LOSS_ELO_NLL, prob, t, prob.numel() // prob.size(0))
+
+
+# ---------------------------------------------------------------------------------------
+# factory (networks.py:22-34, 72-175)
+# ---------------------------------------------------------------------------------------
+class IdentityMapping(nn.Module):
+    def __init__(self, *args):
+        super().__init__()
+
+    def forward(self, x):
+        return x
+
+
+def get_norm_layer(norm_type="instance"):
+    if norm_type == "batch":
+        return functools.partial(nn.BatchNorm2d, affine=True)
+    if norm_type == "instance":
+        return functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=True)
+    raise NotImplementedError("normalization layer [%s] is outside the wsgan_emb hot path" % norm_type)
+
+
+def init_weights(net, init_type="normal", gain=0.02):
+    """init_weights (networks.py:72-93): Conv/Linear weights by init_type, biases 0, BatchNorm2d weight N(1, gain)."""
+    def init_func(m):
+        cn = m.__class__.__name__
+        if hasattr(m, "weight") and (cn.find("Conv") != -1 or cn.find("Linear") != -1):
+            if init_type == "normal":
+                init.normal_(m.weight.data, 0.0, gain)
+            elif init_type == "xavier":
+                init.xavier_normal_(m.weight.data, gain=gain)
+            elif init_type == "kaiming":
+                init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "orthogonal":
+                init.orthogonal_(m.weight.data, gain=gain)
+            else:
+                raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+            if getattr(m, "bias", None) is not None:
+                init.constant_(m.bias.data, 0.0)
+        elif cn.find("BatchNorm2d") != -1:
+            init.normal_(m.weight.data, 1.0, gain)
+            init.constant_(m.bias.data, 0.0)
+
+    print("initialize network with %s" % init_type)
+    net.apply(init_func)
+
+
+class LocalDataParallel(torch.nn.DataParallel):
+    """What init_net returns for a non-empty gpu_ids (networks.py:96-102): the reference wraps every network in
+    nn.DataParallel and tests isinstance(net, DataParallel) / unwraps .module (base_model.py:104,127;
+    wsgan_emb_model.py:118,132).  This subclass keeps those call sites working with one process per GPU: it runs the
+    module on its single device; gradient averaging across ranks is done by pcgan_b200.dist.GradSync."""
+
+    def __init__(self, module, device_ids):
+        super().__init__(module, device_ids=[device_ids[0]])
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)
+
+
+def init_net(net, init_type="normal", gpu_ids=[]):
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.to(gpu_ids[0])
+        net = LocalDataParallel(net, gpu_ids)
+    init_weights(net, init_type)
+    return net
+
+
+def define_G(input_nc, output_nc, nz, ngf, which_model_netG="unet_128", norm="batch", nl="relu", dropout=0, init_type="xavier",
+             gpu_ids=[], upsample="bilinear", size=512, embed_size=256, n_layers_G=7):
+    norm_layer = get_norm_layer(norm_type=norm)
+    if which_model_netG == "resnet_9blocks":
+        net = ResnetGenerator(input_nc, output_nc, nz, ngf, norm_layer=norm_layer, dropout=dropout, n_blocks=9)
+    elif which_model_netG == "resnet_6blocks":
+        net = ResnetGenerator(input_nc, output_nc, nz, ngf, norm_layer=norm_layer, dropout=dropout, n_blocks=6)
+    else:
+        raise NotImplementedError("Generator [%s] is outside the wsgan_emb hot path (resnet_9blocks / resnet_6blocks)" % which_model_netG)
+    return init_net(net, init_type, gpu_ids)
+
+
+def define_D(input_nc, nz, ndf, which_model_netD, n_layers_D=3, norm="batch", use_sigmoid=False, init_type="normal", num_Ds=1,
+             gpu_ids=[], use_projection=True, size=512, embed_size=256, num_classes=1):
+    norm_layer = get_norm_layer(norm_type=norm)
+    if which_model_netD == "basic":
+        net = NLayerDiscriminator(input_nc, nz, ndf, n_layers=3, norm_layer=norm_layer, use_sigmoid=use_sigmoid)
+    elif which_model_netD == "n_layers":
+        net = NLayerDiscriminator(input_nc, nz, ndf, n_layers_D, norm_layer=norm_layer, use_sigmoid=use_sigmoid)
+    else:
+        raise NotImplementedError("Discriminator [%s] is outside the wsgan_emb hot path (basic / n_layers)" % which_model_netD)
+    return init_net(net, init_type, gpu_ids)
+
+
+# ---------------------------------------------------------------------------------------
+# Elo / siamese encoder: SiameseFeature(ResNetFeature(resnet18)) (networks.py:1008-1083, :1310-1359; resnet.py)
+# ---------------------------------------------------------------------------------------
+class _EncWorkspace:
+    pass
+
+
+class _EncBlock:
+    """One BasicBlock (resnet.py:31-73) at fixed geometry: conv3x3(stride) BN ReLU conv3x3 BN (+ 1x1 stride-s conv BN) add ReLU."""
+
+    def __init__(self, name, holder, N, hin, cin, c, stride):
+        G = Geom
+        h = hin // stride
+        self.name, self.holder, self.N, self.hin, self.cin, self.h, self.c, self.stride = name, holder, N, hin, cin, h, c, stride
+        self.g_x, self.g_xr = G(N, hin, hin, cin, 1), G(N, hin, hin, cin, 0)
+        self.g_r, self.g_y = G(N, h, h, c, 0), G(N, h, h, c, 1)
+        dy1 = self.g_y if stride == 1 else self.g_r
+        self.c1 = ConvRT(name + ".conv1", holder.conv1.weight, None, self.g_x, stride, 1, OutMap.nhwc(self.g_r), stats=True,
+                         dyg=dy1, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
+        self.c2 = ConvRT(name + ".conv2", holder.conv2.weight, None, self.g_y, 1, 1, OutMap.nhwc(self.g_r), stats=True,
+                         dyg=self.g_y, dx_out=OutMap.nhwc(self.g_r), want_wgrad=False)
+        self.dy1_pad = dy1.pad
+        self.ds = None
+        if holder.downsample is not None:
+            self.ds = ConvRT(name + ".downsample.0", holder.downsample[0].weight, None, self.g_x, stride, 0, OutMap.nhwc(self.g_r),
+                             stats=True, dyg=self.g_r, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
+
+    def new_ws(self, dev):
+        w = _EncWorkspace()
+        w.ra, w.h, w.rb, w.y = zeros_act(self.g_r, dev), zeros_act(self.g_y, dev), zeros_act(self.g_r, dev), zeros_act(self.g_y, dev)
+        w.na, w.nb = NormState(1, self.c, dev), NormState(1, self.c, dev)
+        if self.ds is not None:
+            w.rd, w.nd = zeros_act(self.g_r, dev), NormState(1, self.c, dev)
+        return w
+
+    def forward(self, xbuf, w):
+        hd, cnt = self.holder, self.N * self.h * self.h
+        _unit_forward(self.c1, xbuf, w.ra, w.na, cnt, gamma=hd.bn1.weight.detach(), beta=hd.bn1.bias.detach(),
+                      rmean=hd.bn1.running_mean, rvar=hd.bn1.running_var)
+        hd.bn1.num_batches_tracked += 1
+        ops.norm_apply(w.ra, self.g_r, w.h, self.g_y, y_halo=L.HALO_ZERO, scale=w.na.scale, shift=w.na.shift, groups=1, act=L.ACT_RELU)
+        _unit_forward(self.c2, w.h, w.rb, w.nb, cnt, gamma=hd.bn2.weight.detach(), beta=hd.bn2.bias.detach(),
+                      rmean=hd.bn2.running_mean, rvar=hd.bn2.running_var)
+        hd.bn2.num_batches_tracked += 1
+        if self.ds is not None:
+            bnd = hd.downsample[1]
+            _unit_forward(self.ds, xbuf, w.rd, w.nd, cnt, gamma=bnd.weight.detach(), beta=bnd.bias.detach(),
+                          rmean=bnd.running_mean, rvar=bnd.running_var)
+            bnd.num_batches_tracked += 1
+            ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, scale=w.nb.scale, shift=w.nb.shift, groups=1,
+                           res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1, act=L.ACT_RELU)
+        else:
+            ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, scale=w.nb.scale, shift=w.nb.shift, groups=1,
+                           res=xbuf, res_pad=1, act=L.ACT_RELU)
+        return w.y
+
+    def backward(self, xbuf, w, gy, sc):
+        """gy: gradient of the block output (unpadded).  Returns the gradient of the block input (unpadded)."""
+        cnt = self.N * self.h * self.h
+        dyb = sc.get(self.g_y, self.name + "dyb")
+        gres = sc.get(self.g_r, self.name + "gres")
+        if self.ds is not None:
+            res_kw = dict(res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1)
+        else:
+            res_kw = dict(res=xbuf, res_pad=1)
+        _norm_backward(gy, 0, w.rb, self.g_r, w.nb, L.ACT_RELU, 0.0, cnt, dyb, 1, dres=gres, dres_pad=0, **res_kw)
+        gh = sc.get(self.g_r, self.name + "gh")
+        self.c2.backward_data(dyb, gh)
+        dya = sc.get(self.g_y if self.stride == 1 else self.g_r, self.name + "dya")
+        _norm_backward(gh, 0, w.ra, self.g_r, w.na, L.ACT_RELU, 0.0, cnt, dya, self.dy1_pad)
+        gx1 = sc.get(self.g_xr, self.name + "gx1")
+        self.c1.backward_data(dya, gx1)
+        gx = sc.get(self.g_xr, self.name + "gx")
+        if self.ds is not None:
+            dyd = sc.get(self.g_r, self.name + "dyd")
+            _norm_backward(gres, 0, w.rd, self.g_r, w.nd, L.ACT_NONE, 0.0, cnt, dyd, 0)
+            gx2 = sc.get(self.g_xr, self.name + "gx2")  # odd phases of a 1x1 stride-2 conv receive nothing: stay zero
+            self.ds.backward_data(dyd, gx2)
+            ops.halo_fold(gx1, self.g_xr, gx, 0, halo=L.HALO_ZERO, add=gx2, add_pad=0)
+        else:
+            ops.halo_fold(gx1, self.g_xr, gx, 0, halo=L.HALO_ZERO, add=gres, add_pad=0)
+        return gx
+
+
+class _EncProgram:
+    def __init__(self, mod, N, S):
+        if S % 32:
+            raise NotImplementedError("encoder input side must be a multiple of 32 (got %d)" % S)
+        self.mod, self.N, self.S = mod, N, S
+        rn = mod.base.model
+        dev = rn.conv1.weight.device
+        self.dev = dev
+        G = Geom
+        s2, s4 = S // 2, S // 4
+        self.g_x0 = G(N, S, S, 8, 3)
+        self.g_r0, self.g_a0 = G(N, s2, s2, 64, 0), G(N, s2, s2, 64, 0)
+        self.g_p, self.g_pr = G(N, s4, s4, 64, 1), G(N, s4, s4, 64, 0)
+        self.stem = ConvRT("E.conv1", rn.conv1.weight, None, self.g_x0, 2, 3, OutMap.nhwc(self.g_r0), stats=True, dyg=self.g_r0,
+                           dx_out=OutMap.nhwc(G(N, S, S, 8, 0)), want_wgrad=False)
+        self.blocks = []
+        hin, cin = s4, 64
+        for li, c in enumerate((64, 128, 256, 512), start=1):
+            layer = getattr(rn, "layer%d" % li)
+            for bi in range(2):
+                stride = 2 if (li > 1 and bi == 0) else 1
+                blk = _EncBlock("E.layer%d.%d" % (li, bi), layer[bi], N, hin, cin, c, stride)
+                self.blocks.append(blk)
+                hin, cin = hin // stride, c
+        self.hf = hin
+        nf = mod.cnn[0].weight.shape[0]
+        self.nf = nf
+        self.g_f = G(N, hin, hin, 512, 1)
+        self.g_rh, self.g_hh = G(N, hin, hin, nf, 0), G(N, hin, hin, nf, 1)
+        self.g_fin = G(N, hin, hin, 8, 0)
+        self.g_dyfin = G(N, hin, hin, 8, 1)
+        self.head1 = ConvRT("E.cnn.0", mod.cnn[0].weight, mod.cnn[0].bias, self.g_f, 1, 1, OutMap.nhwc(self.g_rh), stats=True,
+                            dyg=self.g_hh, dx_out=OutMap.nhwc(G(N, hin, hin, 512, 0)), want_wgrad=False)
+        # last conv: the global average pool is its per-sample statistics (sum over the map) / (h*w)
+        self.head2 = ConvRT("E.cnn.4", mod.cnn[4].weight, mod.cnn[4].bias, self.g_hh, 1, 1, OutMap.nhwc(self.g_fin), stats=True,
+                            per_sample_stats=True, dyg=self.g_dyfin, dx_out=OutMap.nhwc(self.g_rh), want_wgrad=False)
+        self.scratch = _Scratch(dev)
+        self.pool = Pool(lambda key: self._new_ws())
+
+    def _new_ws(self):
+        ws, dev, N = _EncWorkspace(), self.dev, self.N
+        ws.x0, ws.r0, ws.a0, ws.p = zeros_act(self.g_x0, dev), zeros_act(self.g_r0, dev), zeros_act(self.g_a0, dev), zeros_act(self.g_p, dev)
+        ws.idx = torch.zeros(self.g_pr.numel, dtype=torch.uint8, device=dev)
+        ws.n0 = NormState(1, 64, dev)
+        ws.blk = [b.new_ws(dev) for b in self.blocks]
+        ws.rh, ws.hh, ws.fin = zeros_act(self.g_rh, dev), zeros_act(self.g_hh, dev), zeros_act(self.g_fin, dev)
+        ws.nh = NormState(1, self.nf, dev)
+        ws.nfin = NormState(N, 1, dev)
+        return ws
+
+    def forward(self, x):
+        mod, N = self.mod, self.N
+        rn = mod.base.model
+        ws = self.pool.take(0)
+        ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
+        s2 = self.S // 2
+        _unit_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, gamma=rn.bn1.weight.detach(), beta=rn.bn1.bias.detach(),
+                      rmean=rn.bn1.running_mean, rvar=rn.bn1.running_var)
+        rn.bn1.num_batches_tracked += 1
+        ops.norm_apply(ws.r0, self.g_r0, ws.a0, self.g_a0, scale=ws.n0.scale, shift=ws.n0.shift, groups=1, act=L.ACT_RELU)
+        ops.maxpool_fwd(ws.a0, self.g_a0, ws.p, 1, ws.idx)
+        cur = ws.p
+        for blk, w in zip(self.blocks, ws.blk):
+            cur = blk.forward(cur, w)
+        hf = self.hf
+        bn = mod.cnn[1]
+        _unit_forward(self.head1, cur, ws.rh, ws.nh, N * hf * hf, gamma=bn.weight.detach(), beta=bn.bias.detach(),
+                      rmean=bn.running_mean, rvar=bn.running_var)
+        bn.num_batches_tracked += 1
+        ops.norm_apply(ws.rh, self.g_rh, ws.hh, self.g_hh, y_halo=L.HALO_ZERO, scale=ws.nh.scale, shift=ws.nh.shift, groups=1,
+                       act=L.ACT_LRELU, act_slope=mod.cnn_relu_slope)
+        ws.nfin.stats.zero_()
+        self.head2.forward(ws.hh, ws.fin, ws.nfin.stats)
+        y = (ws.nfin.stats[:, 0, 0] / float(hf * hf)).view(N, 1, 1, 1)
+        return y, ws
+
+    def backward(self, ws, gy):
+        mod, N, sc, hf = self.mod, self.N, self.scratch, self.hf
+        gmap = (gy.view(N, 1, 1, 1) / float(hf * hf)).expand(N, 1, hf, hf).contiguous()
+        dyf = sc.get(self.g_dyfin)
+        ops.pack_nchw(gmap, dyf, self.g_dyfin, halo=L.HALO_ZERO)
+        ghh = sc.get(self.g_rh, "ghh")
+        self.head2.backward_data(dyf, ghh)
+        dyh = sc.get(self.g_hh, "dyh")
+        _norm_backward(ghh, 0, ws.rh, self.g_rh, ws.nh, L.ACT_LRELU, mod.cnn_relu_slope, N * hf * hf, dyh, 1)
+        g = sc.get(Geom(N, hf, hf, 512, 0), "gf")
+        self.head1.backward_data(dyh, g)
+        inputs = [ws.p] + [w.y for w in ws.blk[:-1]]
+        for blk, w, xin in zip(reversed(self.blocks), reversed(ws.blk), reversed(inputs)):
+            g = blk.backward(xin, w, g, sc)
+        s2 = self.S // 2
+        ga0 = sc.get(self.g_a0, "ga0")
+        ops.maxpool_bwd(g, 0, ws.idx, ga0, 0, N, s2, s2, 64)
+        dy0 = sc.get(self.g_r0, "dy0")
+        _norm_backward(ga0, 0, ws.r0, self.g_r0, ws.n0, L.ACT_RELU, 0.0, N * s2 * s2, dy0, 0)
+        gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
+        self.stem.backward_data(dy0, gx)
+        dx = torch.empty(N, 3, self.S, self.S, device=self.dev)
+        ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dx)
+        return dx
+
+
+class _EncFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        prog = mod._program(x.shape[0], x.shape[2])
+        y, ws = prog.forward(x.contiguous().float())
+        if any(ctx.needs_input_grad[2:]):
+            raise NotImplementedError("training the Elo encoder inside wsgan_emb (lr_E > 0) is not implemented: freeze it "
+                                      "(set_requires_grad(netE, False), wsgan_emb_model.py:164-165)")
+        if ctx.needs_input_grad[1]:
+            ctx.prog, ctx.ws = prog, ws
+        else:
+            prog.pool.give(0, ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        prog, ws = ctx.prog, ctx.ws
+        dx = prog.backward(ws, gy.contiguous().float())
+        prog.pool.give(0, ws)
+        ctx.ws = None
+        return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class _BasicBlockHolder(nn.Module):
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=1, bias=False)
+        self.drop1 = IdentityMapping()
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.Identity()
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.drop2 = IdentityMapping()
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+
+class _ResNet18Holder(nn.Module):
+    """Parameter layout of models/resnet.py ResNet(BasicBlock, [2, 2, 2, 2]) without fc (deleted at networks.py:1337)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu, self.maxpool = nn.Identity(), nn.Identity()
+        inpl = 64
+        for li, planes in enumerate((64, 128, 256, 512), start=1):
+            stride = 1 if li == 1 else 2
+            ds = None
+            if stride != 1 or inpl != planes:
+                ds = nn.Sequential(nn.Conv2d(inpl, planes, 1, stride=stride, bias=False), nn.BatchNorm2d(planes))
+            setattr(self, "layer%d" % li, nn.Sequential(_BasicBlockHolder(inpl, planes, stride, ds), _BasicBlockHolder(planes, planes)))
+            inpl = planes
+        self.avgpool = nn.Identity()
+
+
+class ResNetFeature(nn.Module):
+    def __init__(self, input_nc=3, which_model="resnet18", dropout=0.0):
+        super().__init__()
+        if which_model != "resnet18" or input_nc != 3:
+            raise NotImplementedError("pcgan_b200 ResNetFeature: resnet18 on RGB input (the wsgan_emb configuration)")
+        if dropout > 0:
+            raise NotImplementedError("MC-dropout (Bayesian encoder, --bnn_dropout > 0) is not implemented yet")
+        self.model = _ResNet18Holder()
+        self.feature_dim = 512
+
+    def load_pretrained(self, state_dict):
+        if isinstance(state_dict, str):
+            state_dict = torch.load(state_dict)
+        self.model.load_state_dict(state_dict, strict=False)
+
+
+class SiameseFeature(nn.Module):
+    """Same constructor / forward / load_pretrained / state_dict keys as models/networks.py:1008-1083 (pooling 'avg',
+    cnn_dim = [nf, 1]).  Always runs with batch statistics, as the reference does (no .eval() on the train path)."""
+
+    def __init__(self, base=None, pooling="avg", cnn_dim=[], cnn_pad=1, cnn_relu_slope=0.2, noisy=False, drop_layer=None):
+        super().__init__()
+        if pooling != "avg" or len(cnn_dim) != 2 or cnn_dim[1] != 1 or cnn_pad != 1 or cnn_dim[0] % 8 or cnn_dim[0] >= 64:
+            raise NotImplementedError("pcgan_b200 SiameseFeature: pooling='avg', cnn_dim=[nf<64 (multiple of 8), 1], cnn_pad=1")
+        if noisy:
+            raise NotImplementedError("the aleatoric twin head (--noisy true) is not implemented yet")
+        self.pooling, self.base, self._noisy, self.cnn_relu_slope = pooling, base, noisy, cnn_relu_slope
+        nf = cnn_dim[0]
+        self.cnn = nn.Sequential(nn.Conv2d(base.feature_dim, nf, 3, padding=cnn_pad), nn.BatchNorm2d(nf), IdentityMapping(),
+                                 nn.Identity(), nn.Conv2d(nf, 1, 3, padding=cnn_pad))
+        self.feature_dim = 1
+        self._programs = {}
+
+    def _program(self, n, s):
+        k = (n, s, self.cnn[0].weight.device)
+        if k not in self._programs:
+            self._programs[k] = _EncProgram(self, n, s)
+        return self._programs[k]
+
+    def forward(self, x):
+        _require_cuda(x, "SiameseFeature")
+        if x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise NotImplementedError("square RGB inputs")
+        return _EncFn.apply(self, x, *self.parameters())
+
+    def load_pretrained(self, state_dict):
+        if isinstance(state_dict, str):
+            state_dict = torch.load(state_dict)
+        for key in list(state_dict.keys()):
+            if key.startswith("cxn") or key.startswith("fc"):
+                state_dict.pop(key)
+        self.load_state_dict(state_dict, strict=True)
+
+    def load_base(self, state_dict):
+        self.base.load_pretrained(state_dict)
+
+
+def get_dropout_layer(dropout=0.0):
+    if dropout > 0:
+        return functools.partial(nn.Dropout2d, p=dropout)
+    return IdentityMapping
+
+
+def define_E(which_model_netE, input_nc=3, init_type="kaiming", pooling="max", cnn_dim=[], cnn_pad=1, cnn_relu_slope=0.2,
+             gpu_ids=[], fine_size_E=224, noisy=False, bnn_dropout=0.0):
+    if "resnet" not in which_model_netE:
+        raise NotImplementedError("Encoder [%s] is outside the wsgan_emb hot path (resnet18)" % which_model_netE)
+    base = ResNetFeature(input_nc=input_nc, which_model=which_model_netE, dropout=bnn_dropout)
+    net = SiameseFeature(base, pooling=pooling, cnn_dim=cnn_dim, cnn_pad=cnn_pad, cnn_relu_slope=cnn_relu_slope, noisy=noisy,
+                         drop_layer=get_dropout_layer(bnn_dropout))
+    return init_net(net, init_type, gpu_ids)
+
+
+class Normalize(nn.Module):
+    """networks.py:2421-2439 as called by WSGANEmbModel: `mean or std` is truthy, so it is the identity."""
+
+    def __init__(self, mean=[], std=[]):
+        super().__init__()
+        self.identity_mapping = mean or std
+        if not self.identity_mapping:
+            raise NotImplementedError("Normalize with empty mean and std is unreachable in the reference")
+
+    def __call__(self, input):
+        return input
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        x = x.contiguous().float()
+        out = torch.empty(x.shape[0], x.shape[1], size, size, device=x.device)
+        ops.resize_nchw_fwd(x, out)
+        ctx.in_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gi = torch.empty(ctx.in_shape, device=g.device)
+        ops.resize_nchw_bwd(g.contiguous().float(), gi)
+        return gi, None
+
+
+def upsample2d(inputTensor, targetSize):
+    """util.upsample2d (util/util.py:111-117): bilinear, align_corners=True; identity when sizes match."""
+    if targetSize <= 0 or inputTensor.size(2) == targetSize:
+        return inputTensor
+    _require_cuda(inputTensor, "upsample2d")
+    return _UpsampleFn.apply(inputTensor, targetSize)

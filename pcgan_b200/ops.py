@@ -61,11 +61,11 @@ def scatter_f32(src, idx, dst, accumulate=False):
     L.check(L.load().pcgan_scatter_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), int(accumulate), _stream()), "scatter_f32")
 
 
-def pack_nchw(src, dst, g: Geom, *, z=None, tanh_out=None, halo=L.HALO_ZERO, src_hw=None):
+def pack_nchw(src, dst, g: Geom, *, z=None, mul_out=None, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO):
     """src: NCHW fp32 [n, cs, h, w] -> dst buffer of geometry g (resized to g.h x g.w when they differ)."""
     n, cs, h, w = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
-    a = L.PackArgs(src=_ptr(src), z=_ptr(z), tanh_out=_ptr(tanh_out), dst=_ptr(dst), n=n, cs=cs, h=h, w=w,
+    a = L.PackArgs(src=_ptr(src), z=_ptr(z), mul_out=_ptr(mul_out), mul_kind=mul_kind, dst=_ptr(dst), n=n, cs=cs, h=h, w=w,
                    ho=g.h, wo=g.w, cd=g.c, pad=g.pad, halo=halo, dst_n_stride=0)
     L.check(L.load().pcgan_pack_nchw(C.byref(a), _stream()), "pack_nchw")
 
@@ -132,9 +132,19 @@ def maxpool_bwd(dy, dy_pad, idx, dx, dx_pad, n, h, w, c):
     L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, _stream()), "maxpool_bwd")
 
 
-def loss(kind, p, target, *, per_sample=0, weight=1.0, loss_out=None, grad=None):
+def resize_nchw_fwd(src, dst):
+    n, c, h, w = src.shape
+    L.check(L.load().pcgan_resize_nchw_fwd(_ptr(src), _ptr(dst), n * c, h, w, dst.shape[2], dst.shape[3], _stream()), "resize_nchw_fwd")
+
+
+def resize_nchw_bwd(gdst, gsrc):
+    n, c, h, w = gsrc.shape
+    L.check(L.load().pcgan_resize_nchw_bwd(_ptr(gdst), _ptr(gsrc), n * c, h, w, gdst.shape[2], gdst.shape[3], _stream()), "resize_nchw_bwd")
+
+
+def loss(kind, p, target, *, per_sample=0, weight=1.0, weight_dev=None, loss_out=None, grad=None):
     a = L.LossArgs(kind=kind, p=_ptr(p), target=_ptr(target), n=p.numel(), per_sample=per_sample, weight=weight,
-                   loss=_ptr(loss_out), grad=_ptr(grad))
+                   weight_dev=_ptr(weight_dev), loss=_ptr(loss_out), grad=_ptr(grad))
     L.check(L.load().pcgan_loss(C.byref(a), _stream()), "loss")
 
 
