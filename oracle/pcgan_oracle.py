@@ -142,19 +142,79 @@ def make_state_dict(keys, seed, device="cpu", requires_grad=False):
     return out
 
 
+# ------------------------------------------------------------- bf16 emulation (tests only) ----
+class _GradRound(torch.autograd.Function):
+    """identity forward; rounds the gradient to bf16 in backward (a gradient stored in a bf16 buffer)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class Quant:
+    """Rounding model of the bf16 pipeline, applied to the fp32 restatement so that kernel bugs can be told from
+    bf16 noise: operands of every convolution (activations, weights) and every stored activation / gradient are
+    rounded to bf16 exactly where the kernels store bf16; accumulation, statistics, biases and weight gradients
+    stay fp32.  `Quant(False)` is the exact fp32 reference arithmetic."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def fwd(self, t):      # value rounded to bf16 as stored; gradient passes unchanged
+        return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach() if self.on else t
+
+    def grad(self, t):     # gradient rounded to bf16 as stored
+        return _GradRound.apply(t) if self.on else t
+
+    def act(self, t):      # an activation buffer: value and incoming gradient are both bf16
+        return self.grad(self.fwd(t)) if self.on else t
+
+    def w(self, t):        # packed bf16 weight operand; the fp32 master weight receives an fp32 gradient
+        return self.fwd(t)
+
+
+EXACT = Quant(False)
+
+
 # --------------------------------------------------------------------------- layers ----
-def _inorm(x, sd, name, tap=None):
+def _inorm(x, sd, name, q=EXACT):
     """nn.InstanceNorm2d(affine=False, track_running_stats=True) in training mode (networks.py:25-26):
-    instance statistics normalise; running stats get the EMA of the batch-mean of the instance stats."""
-    y = F.instance_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], None, None, True, MOMENTUM, EPS)
-    return y
+    instance statistics normalise; running stats get the EMA of the batch-mean of the instance stats.
+    Under bf16 emulation the statistics come from the fp32 accumulator and are applied to its bf16 copy."""
+    if not q.on:
+        return F.instance_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], None, None, True, MOMENTUM, EPS)
+    x = q.grad(x)
+    mean = x.mean((2, 3), keepdim=True)
+    var = x.var((2, 3), unbiased=False, keepdim=True)
+    with torch.no_grad():
+        n = x.size(2) * x.size(3)
+        sd[name + ".running_mean"].mul_(1 - MOMENTUM).add_(MOMENTUM * mean.mean(0).flatten())
+        sd[name + ".running_var"].mul_(1 - MOMENTUM).add_(MOMENTUM * (var.mean(0).flatten() * n / (n - 1)))
+    return (q.fwd(x) - mean) * torch.rsqrt(var + EPS)
 
 
-def _bnorm(x, sd, name):
+def _bnorm(x, sd, name, q=EXACT):
     """nn.BatchNorm2d in training mode (never .eval()'d on the train path: SURVEY appendix A.1)."""
     sd[name + ".num_batches_tracked"] += 1
-    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
-                        True, MOMENTUM, EPS)
+    if not q.on:
+        return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                            True, MOMENTUM, EPS)
+    x = q.grad(x)
+    mean = x.mean((0, 2, 3), keepdim=True)
+    var = x.var((0, 2, 3), unbiased=False, keepdim=True)
+    with torch.no_grad():
+        n = x.numel() // x.size(1)
+        sd[name + ".running_mean"].mul_(1 - MOMENTUM).add_(MOMENTUM * mean.flatten())
+        sd[name + ".running_var"].mul_(1 - MOMENTUM).add_(MOMENTUM * (var.flatten() * n / (n - 1)))
+    return (q.fwd(x) - mean) * torch.rsqrt(var + EPS) * sd[name + ".weight"].view(1, -1, 1, 1) + sd[name + ".bias"].view(1, -1, 1, 1)
+
+
+def _rpad(h, p, q):
+    return q.grad(F.pad(h, (p,) * 4, mode="reflect"))
 
 
 def _zcat(x, z):
@@ -163,7 +223,7 @@ def _zcat(x, z):
     return torch.cat((x, zi), 1)
 
 
-def generator_forward(sd, x, z, n_blocks=9, taps=None):
+def generator_forward(sd, x, z, n_blocks=9, taps=None, q=EXACT):
     """ResnetGenerator.forward (networks.py:609-612) with the Sequential of :578-605 and ResnetBlock :621-652.
     taps (optional dict) receives the output of every conv and of every block for per-layer checks."""
     def rec(name, t):
@@ -171,90 +231,94 @@ def generator_forward(sd, x, z, n_blocks=9, taps=None):
             taps[name] = t
         return t
 
-    h = _zcat(x, z)
-    h = rec("model.1", F.conv2d(F.pad(h, (3,) * 4, mode="reflect"), sd["model.1.weight"], sd["model.1.bias"]))
-    h = F.relu(_inorm(h, sd, "model.2"))
-    h = rec("model.4", F.conv2d(h, sd["model.4.weight"], sd["model.4.bias"], stride=2, padding=1))
-    h = F.relu(_inorm(h, sd, "model.5"))
-    h = rec("model.7", F.conv2d(h, sd["model.7.weight"], sd["model.7.bias"], stride=2, padding=1))
-    h = F.relu(_inorm(h, sd, "model.8"))
+    W = lambda k: q.w(sd[k])
+    h = q.act(_zcat(x, z))
+    h = rec("model.1", F.conv2d(_rpad(h, 3, q), W("model.1.weight"), sd["model.1.bias"]))
+    h = q.act(F.relu(_inorm(h, sd, "model.2", q)))
+    h = rec("model.4", F.conv2d(h, W("model.4.weight"), sd["model.4.bias"], stride=2, padding=1))
+    h = q.act(F.relu(_inorm(h, sd, "model.5", q)))
+    h = rec("model.7", F.conv2d(h, W("model.7.weight"), sd["model.7.bias"], stride=2, padding=1))
+    h = rec("act.model.8", q.act(F.relu(_inorm(h, sd, "model.8", q))))
     for i in range(n_blocks):
         p = "model.%d.conv_block" % (10 + i)
-        r = rec(p + ".1", F.conv2d(F.pad(h, (1,) * 4, mode="reflect"), sd[p + ".1.weight"], sd[p + ".1.bias"]))
-        r = F.relu(_inorm(r, sd, p + ".2"))
-        r = rec(p + ".5", F.conv2d(F.pad(r, (1,) * 4, mode="reflect"), sd[p + ".5.weight"], sd[p + ".5.bias"]))
-        r = _inorm(r, sd, p + ".6")
-        h = rec("model.%d" % (10 + i), h + r)
+        r = rec(p + ".1", F.conv2d(_rpad(h, 1, q), W(p + ".1.weight"), sd[p + ".1.bias"]))
+        r = rec("act." + p + ".2", q.act(F.relu(_inorm(r, sd, p + ".2", q))))
+        r = rec(p + ".5", F.conv2d(_rpad(r, 1, q), W(p + ".5.weight"), sd[p + ".5.bias"]))
+        r = _inorm(r, sd, p + ".6", q)
+        h = rec("model.%d" % (10 + i), q.act(h + r))
     b = 10 + n_blocks
-    h = rec("model.%d" % b, F.conv_transpose2d(h, sd["model.%d.weight" % b], sd["model.%d.bias" % b], stride=2, padding=1, output_padding=1))
-    h = F.relu(_inorm(h, sd, "model.%d" % (b + 1)))
-    h = rec("model.%d" % (b + 3), F.conv_transpose2d(h, sd["model.%d.weight" % (b + 3)], sd["model.%d.bias" % (b + 3)], stride=2, padding=1, output_padding=1))
-    h = F.relu(_inorm(h, sd, "model.%d" % (b + 4)))
-    h = rec("model.%d" % (b + 7), F.conv2d(F.pad(h, (3,) * 4, mode="reflect"), sd["model.%d.weight" % (b + 7)], sd["model.%d.bias" % (b + 7)]))
-    return torch.tanh(h)
+    h = rec("model.%d" % b, F.conv_transpose2d(h, W("model.%d.weight" % b), sd["model.%d.bias" % b], stride=2, padding=1, output_padding=1))
+    h = q.act(F.relu(_inorm(h, sd, "model.%d" % (b + 1), q)))
+    h = rec("model.%d" % (b + 3), F.conv_transpose2d(h, W("model.%d.weight" % (b + 3)), sd["model.%d.bias" % (b + 3)], stride=2, padding=1, output_padding=1))
+    h = q.act(F.relu(_inorm(h, sd, "model.%d" % (b + 4), q)))
+    h = rec("model.%d" % (b + 7), F.conv2d(_rpad(h, 3, q), W("model.%d.weight" % (b + 7)), sd["model.%d.bias" % (b + 7)]))
+    return torch.tanh(q.grad(h))
 
 
-def discriminator_forward(sd, x, z=None, n_layers=3, use_sigmoid=True, taps=None):
+def discriminator_forward(sd, x, z=None, n_layers=3, use_sigmoid=True, taps=None, q=EXACT):
     """NLayerDiscriminator.forward (networks.py:779-783) over the Sequential of :745-777."""
     def rec(name, t):
         if taps is not None:
             taps[name] = t
         return t
 
-    h = _zcat(x, z) if z is not None else x
-    h = F.leaky_relu(rec("model.0", F.conv2d(h, sd["model.0.weight"], sd["model.0.bias"], stride=2, padding=1)), 0.2)
+    W = lambda k: q.w(sd[k])
+    h = q.act(_zcat(x, z) if z is not None else x)
+    h = q.act(F.leaky_relu(q.grad(rec("model.0", F.conv2d(h, W("model.0.weight"), sd["model.0.bias"], stride=2, padding=1))), 0.2))
     idx = 2
     for n in range(1, n_layers + 1):
         stride = 2 if n < n_layers else 1
-        h = rec("model.%d" % idx, F.conv2d(h, sd["model.%d.weight" % idx], None, stride=stride, padding=1))
-        h = F.leaky_relu(_bnorm(h, sd, "model.%d" % (idx + 1)), 0.2)
+        h = rec("model.%d" % idx, F.conv2d(h, W("model.%d.weight" % idx), None, stride=stride, padding=1))
+        h = q.act(F.leaky_relu(_bnorm(h, sd, "model.%d" % (idx + 1), q), 0.2))
         idx += 3
-    h = rec("model.%d" % idx, F.conv2d(h, sd["model.%d.weight" % idx], sd["model.%d.bias" % idx], stride=1, padding=1))
+    h = q.grad(rec("model.%d" % idx, F.conv2d(h, W("model.%d.weight" % idx), sd["model.%d.bias" % idx], stride=1, padding=1)))
     return torch.sigmoid(h) if use_sigmoid else h
 
 
-def _basic_block(sd, p, x, stride, drop=None):
+def _basic_block(sd, p, x, stride, drop=None, q=EXACT):
     """BasicBlock.forward (models/resnet.py:55-73): conv-[drop]-bn-relu-conv-[drop]-bn (+downsample) add relu."""
-    out = F.conv2d(x, sd[p + ".conv1.weight"], None, stride=stride, padding=1)
+    W = lambda k: q.w(sd[k])
+    out = F.conv2d(x, W(p + ".conv1.weight"), None, stride=stride, padding=1)
     if drop is not None:
         out = drop(out)
-    out = F.relu(_bnorm(out, sd, p + ".bn1"))
-    out = F.conv2d(out, sd[p + ".conv2.weight"], None, stride=1, padding=1)
+    out = q.act(F.relu(_bnorm(out, sd, p + ".bn1", q)))
+    out = F.conv2d(out, W(p + ".conv2.weight"), None, stride=1, padding=1)
     if drop is not None:
         out = drop(out)
-    out = _bnorm(out, sd, p + ".bn2")
+    out = _bnorm(out, sd, p + ".bn2", q)
     if (p + ".downsample.0.weight") in sd:
-        idn = _bnorm(F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride=stride), sd, p + ".downsample.1")
+        idn = _bnorm(F.conv2d(x, W(p + ".downsample.0.weight"), None, stride=stride), sd, p + ".downsample.1", q)
     else:
         idn = x
-    return F.relu(out + idn)
+    return q.act(F.relu(out + idn))
 
 
-def encoder_forward(sd, x, cnn_dim=(32, 1), cnn_relu_slope=0.7, noisy=False, drop=None, taps=None):
+def encoder_forward(sd, x, cnn_dim=(32, 1), cnn_relu_slope=0.7, noisy=False, drop=None, taps=None, q=EXACT):
     """SiameseFeature.forward (networks.py:1051-1068) over ResNetFeature.forward (:1344-1354) and the ResNet-18
     trunk (resnet.py:134-138,163-179); pooling='avg' -> nn.AvgPool2d(full size).  `drop`, if given, is a callable
     applied where the reference places nn.Dropout2d (resnet.py:58,63; networks.py:1022)."""
-    h = F.conv2d(x, sd["base.model.conv1.weight"], None, stride=2, padding=3)
-    h = F.relu(_bnorm(h, sd, "base.model.bn1"))
-    h = F.max_pool2d(h, 3, 2, 1)
+    W = lambda k: q.w(sd[k])
+    h = F.conv2d(q.act(x), W("base.model.conv1.weight"), None, stride=2, padding=3)
+    h = q.act(F.relu(_bnorm(h, sd, "base.model.bn1", q)))
+    h = q.act(F.max_pool2d(h, 3, 2, 1))
     if taps is not None:
         taps["stem"] = h
     for li in range(1, 5):
         for bi in range(2):
-            h = _basic_block(sd, "base.model.layer%d.%d" % (li, bi), h, 2 if (li > 1 and bi == 0) else 1, drop)
+            h = _basic_block(sd, "base.model.layer%d.%d" % (li, bi), h, 2 if (li > 1 and bi == 0) else 1, drop, q)
         if taps is not None:
             taps["layer%d" % li] = h
 
     def head(prefix, t):
         idx = 0
         for _ in cnn_dim[:-1]:
-            t = F.conv2d(t, sd["%s.%d.weight" % (prefix, idx)], sd["%s.%d.bias" % (prefix, idx)], padding=1)
-            t = _bnorm(t, sd, "%s.%d" % (prefix, idx + 1))
+            t = F.conv2d(t, W("%s.%d.weight" % (prefix, idx)), sd["%s.%d.bias" % (prefix, idx)], padding=1)
+            t = _bnorm(t, sd, "%s.%d" % (prefix, idx + 1), q)
             if drop is not None:
                 t = drop(t)
-            t = F.leaky_relu(t, cnn_relu_slope)
+            t = q.act(F.leaky_relu(t, cnn_relu_slope))
             idx += 4
-        t = F.conv2d(t, sd["%s.%d.weight" % (prefix, idx)], sd["%s.%d.bias" % (prefix, idx)], padding=1)
+        t = q.grad(F.conv2d(t, W("%s.%d.weight" % (prefix, idx)), sd["%s.%d.bias" % (prefix, idx)], padding=1))
         return F.avg_pool2d(t, t.size(2))
 
     y = head("cnn", h)
