@@ -1,0 +1,280 @@
+"""WSGANEmbModel on the B200-native networks: the same public surface train.py drives
+(models/base_model.py:43-159, models/wsgan_emb_model.py:82-497 of phymhan/pc-gan) —
+initialize / setup / set_input / forward / optimize_parameters / get_current_losses /
+get_current_visuals / save_networks / load_networks / update_learning_rate — with the
+step's arithmetic running on libpcgan_kernels.so.
+
+What stays PyTorch: parameter storage, torch.optim.Adam, LR schedulers,
+checkpoint I/O, control flow.  One process per GPU; gradients are averaged across ranks by
+pcgan_b200.dist.GradSync (the reference's nn.DataParallel replaced by NCCL all-reduce).
+
+Supported flags: the default wsgan_emb configuration with --which_model_netG resnet_9blocks
+(or resnet_6blocks), --which_model_netD n_layers/basic, --lambda_IP 0, plus --lambda_L1,
+--lambda_A_GAN, --detach_fake_B, --use_real_A, --no_mixed_label_D.  The Bayesian / noisy
+encoder modes and lr_E > 0 raise NotImplementedError (SURVEY §8f / later rounds).
+"""
+import os
+from argparse import Namespace
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch.optim import lr_scheduler
+
+from . import networks
+from .dist import GradSync
+from .networks import upsample2d
+
+
+def default_options(**overrides):
+    """The flags WSGANEmbModel reads, with the reference's defaults under `--model wsgan_emb`
+    (options/base_options.py:14-62, options/train_options.py:4-29, wsgan_emb_model.py:21-78) and the
+    north-star overrides (--which_model_netG resnet_9blocks --n_layers_D 3 --lambda_IP 0)."""
+    opt = Namespace(
+        isTrain=True, gpu_ids=[0], checkpoints_dir="./checkpoints", name="experiment_name", transforms="resize_and_crop",
+        batchSize=10, loadSize=128, fineSize=128, input_nc=3, output_nc=3, ngf=64, ndf=64,
+        which_model_netG="resnet_9blocks", which_model_netD="n_layers", n_layers_D=3, n_layers_G=7,
+        norm_G="instance", norm_D="batch", nl="relu", dropout=0.0, init_type="normal", upsample="bilinear", num_Ds=1,
+        embedding_nc=1, which_model_netE="resnet18", pooling_E="avg", cnn_dim_E=[32, 1], no_cnn_E=False, cnn_pad_E=1,
+        cnn_relu_slope_E=0.7, fineSize_E=224, pretrained_model_path_E="", embedding_mean=[0.0], embedding_std=[1.0],
+        embedding_bins="[]", display_visuals=False, noisy=False, noisy_D=True, noisy_rec=True, noisy_var_type="",
+        bayesian=False, bnn_dropout=0.0, bnn_T=10, attr_bins=[],
+        lambda_L1=0.0, lambda_IP=0.0, lambda_z=1.0, lambda_A=0.5, lambda_A_GAN=0.0, lr_E=0.0, use_real_A=False,
+        relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False,
+        no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5, lr_policy="lambda", niter=50, niter_decay=50, epoch_count=1,
+        lr_decay_iters=50, continue_train=False, which_epoch="latest", load_model_names=[], verbose=False)
+    for k, v in overrides.items():
+        setattr(opt, k, v)
+    return opt
+
+
+def get_scheduler(optimizer, opt):
+    """networks.get_scheduler (networks.py:57-69)."""
+    if opt.lr_policy == "lambda":
+        def rule(epoch):
+            return 1.0 - max(0, epoch + 1 + opt.epoch_count - opt.niter) / float(opt.niter_decay + 1)
+        return lr_scheduler.LambdaLR(optimizer, lr_lambda=rule)
+    if opt.lr_policy == "step":
+        return lr_scheduler.StepLR(optimizer, step_size=opt.lr_decay_iters, gamma=0.1)
+    if opt.lr_policy == "plateau":
+        return lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=0.2, threshold=0.01, patience=5)
+    raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+
+
+class BaseModel:
+    """models/base_model.py:7-159."""
+
+    def name(self):
+        return "BaseModel"
+
+    def initialize(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        if not self.gpu_ids or not torch.cuda.is_available():
+            raise RuntimeError("pcgan_b200 has no CPU path: run with --gpu_ids <local device> on a CUDA machine")
+        self.isTrain = opt.isTrain
+        self.device = torch.device("cuda:{}".format(self.gpu_ids[0]))
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self.loss_names, self.model_names, self.load_model_names, self.visual_names, self.image_paths = [], [], [], [], []
+        self.current_iter = 0
+        self.current_batch_size = opt.batchSize
+
+    def setup(self, opt, parser=None):
+        if self.isTrain:
+            self.schedulers = [get_scheduler(o, opt) for o in self.optimizers]
+        if not self.isTrain or opt.continue_train:
+            self.load_networks(opt.which_epoch)
+
+    def update_learning_rate(self):
+        for s in self.schedulers:
+            s.step()
+
+    def get_current_visuals(self):
+        return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str))
+
+    def get_current_losses(self):
+        out = OrderedDict()
+        for n in self.loss_names:
+            if isinstance(n, str):
+                out[n] = float(getattr(self, "loss_" + n))
+        return out
+
+    def _unwrap(self, net):
+        return net.module if isinstance(net, torch.nn.DataParallel) else net
+
+    def save_networks(self, which_epoch):
+        os.makedirs(self.save_dir, exist_ok=True)
+        for n in self.model_names:
+            if isinstance(n, str):
+                path = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, n))
+                sd = {k: v.detach().cpu() for k, v in self._unwrap(getattr(self, "net" + n)).state_dict().items()}
+                torch.save(sd, path)
+
+    def load_networks(self, which_epoch):
+        for n in (self.load_model_names or self.model_names):
+            if isinstance(n, str):
+                path = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, n))
+                sd = torch.load(path, map_location=str(self.device))
+                self._unwrap(getattr(self, "net" + n)).load_state_dict(sd)
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        if not isinstance(nets, list):
+            nets = [nets]
+        for net in nets:
+            if net is not None:
+                for p in net.parameters():
+                    p.requires_grad = requires_grad
+
+
+class WSGANEmbModel(BaseModel):
+    def name(self):
+        return "WSGANEmbModel"
+
+    def initialize(self, opt):
+        BaseModel.initialize(self, opt)
+        assert opt.input_nc == opt.output_nc
+        if opt.bayesian or opt.noisy or opt.noisy_var_type:
+            raise NotImplementedError("Bayesian / noisy encoder modes (BASELINE config 4) are not implemented yet")
+        if opt.isTrain and opt.lr_E > 0.0:
+            raise NotImplementedError("lr_E > 0 (training the encoder inside wsgan_emb) is not implemented")
+        if opt.isTrain and opt.lambda_IP > 0.0:
+            raise NotImplementedError("the identity-preserving AlexNet loss (netIP) is outside the named hot path: use --lambda_IP 0")
+        if opt.no_cnn_E:
+            opt.cnn_dim_E = []
+        self.loss_names = ["G_GAN", "G_GAN_cycle", "G_IP", "G_L1", "G_cycle", "z_rec", "D_real_right", "D_real_wrong", "D_fake"]
+        self.visual_names = ["real_A", "fake_B", "real_B", "rec_A"] if self.isTrain else ["real_A"]
+        self.model_names = ["G", "D", "E"] if self.isTrain else ["G", "E"]
+        self.load_model_names = opt.load_model_names
+        self.netG = networks.define_G(opt.input_nc, opt.output_nc, opt.embedding_nc, opt.ngf, which_model_netG=opt.which_model_netG,
+                                      norm=opt.norm_G, nl=opt.nl, dropout=opt.dropout, init_type=opt.init_type, gpu_ids=self.gpu_ids,
+                                      upsample=opt.upsample, n_layers_G=opt.n_layers_G)
+        self.netE = networks.define_E(opt.which_model_netE, 3, init_type=opt.init_type, pooling=opt.pooling_E, cnn_dim=opt.cnn_dim_E,
+                                      cnn_pad=opt.cnn_pad_E, cnn_relu_slope=opt.cnn_relu_slope_E, gpu_ids=self.gpu_ids,
+                                      fine_size_E=opt.fineSize_E, noisy=opt.noisy, bnn_dropout=opt.bnn_dropout)
+        if self.isTrain and not opt.continue_train and opt.pretrained_model_path_E:
+            self._unwrap(self.netE).load_pretrained(opt.pretrained_model_path_E)
+        if self.isTrain:
+            self.netD = networks.define_D(opt.output_nc, opt.embedding_nc, opt.ndf, opt.which_model_netD, opt.n_layers_D, opt.norm_D,
+                                          opt.no_lsgan, opt.init_type, num_Ds=opt.num_Ds, gpu_ids=self.gpu_ids)
+            assert opt.pool_size == 0
+            self.criterionGAN = networks.GANLoss(use_lsgan=not opt.no_lsgan)
+            self.criterionL1 = networks.l1_loss
+            self.criterionRec = networks.mse_loss
+            self.criterionCycle = networks.l1_loss
+            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
+            self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
+            self.optimizers = [self.optimizer_G, self.optimizer_D]
+            self.set_requires_grad(self.netE, False)   # wsgan_emb_model.py:164-165 (E stays in train mode: SURVEY A.1)
+            # one process per GPU: flat gradient buffers, averaged over ranks with one NCCL all-reduce per network
+            self.sync_G = GradSync(list(self.netG.parameters()))
+            self.sync_D = GradSync(list(self.netD.parameters()))
+            self.relabel_D = opt.relabel_D
+            if len(opt.weight_label_D) > 0:
+                assert len(opt.weight_label_D) == len(opt.relabel_D)
+                self.weight_label_D = [w / sum(opt.weight_label_D) for w in opt.weight_label_D]
+            else:
+                self.weight_label_D = None
+        self.embedding_normalize = lambda x: (x - opt.embedding_mean[0]) / opt.embedding_std[0]
+        self.transform_E = networks.Normalize((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))
+
+    # ------------------------------------------------------------------ data
+    def set_input(self, input):
+        """wsgan_emb_model.py:193-212."""
+        if self.isTrain:
+            if not self.opt.no_mixed_label_D:
+                self.real_A = input["A"].to(self.device, non_blocking=True)
+                self.real_B = input["B"].to(self.device, non_blocking=True)
+                self.image_paths = input.get("B_paths", [])
+                self.label_AB = input["label"]
+            else:
+                self.label_AB = [np.random.choice(range(len(self.relabel_D)), p=self.weight_label_D)]
+                k = str(self.label_AB[0])
+                self.real_A = input[k + "_A"].to(self.device, non_blocking=True)
+                self.real_B = input[k + "_B"].to(self.device, non_blocking=True)
+                self.image_paths = input.get(k + "_B_paths", [])
+        else:
+            self.real_A = input["A"].to(self.device)
+            self.image_paths = input.get("A_paths", [])
+            if "B" in input:
+                self.real_B = input["B"].to(self.device)
+        self.current_iter += 1
+        self.current_batch_size = int(self.real_A.size(0))
+
+    # --------------------------------------------------------------- forward
+    def forward(self):
+        """wsgan_emb_model.py:214-259, plain-encoder branch with lr_E <= 0."""
+        opt = self.opt
+        self.real_A_E = upsample2d(self.real_A, opt.fineSize_E)
+        self.real_B_E = upsample2d(self.real_B, opt.fineSize_E)
+        y_A = self.netE(self.transform_E(self.real_A_E))
+        y_B = self.netE(self.transform_E(self.real_B_E))
+        self.y_A, self.y_B = y_A.detach(), y_B.detach()
+        self.embedding_A = self.embedding_normalize(self.y_A).detach()
+        self.embedding_B = self.embedding_normalize(self.y_B).detach()
+        self.fake_B = self.netG(self.real_A, self.embedding_B)
+        self.fake_B_E = upsample2d(self.fake_B, opt.fineSize_E)
+        src = self.fake_B.detach() if opt.detach_fake_B else self.fake_B
+        self.rec_A = self.netG(src, self.embedding_A)
+
+    def test(self):
+        with torch.no_grad():
+            if hasattr(self, "real_B"):
+                y_B = self.netE(self.transform_E(upsample2d(self.real_B, self.opt.fineSize_E)))
+                self.embedding_B = self.embedding_normalize(y_B.detach())
+                self.fake_B = self.netG(self.real_A, self.embedding_B)
+
+    # -------------------------------------------------------------- backward
+    def backward_D(self):
+        """wsgan_emb_model.py:300-329."""
+        opt = self.opt
+        pred_fake = self.netD(self.fake_B.detach(), self.embedding_B)
+        self.loss_D_fake = self.criterionGAN(pred_fake, False)
+        img = self.real_A if opt.use_real_A else self.real_B
+        emb_right, emb_wrong = (self.embedding_A, self.embedding_B) if opt.use_real_A else (self.embedding_B, self.embedding_A)
+        self.loss_D_real_right = self.criterionGAN(self.netD(img, emb_right), True)
+        target_label = [self.relabel_D[int(l)] for l in self.label_AB]
+        self.loss_D_real_wrong = self.criterionGAN(self.netD(img, emb_wrong), target_label)
+        self.loss_D = (self.loss_D_fake + (self.loss_D_real_right + self.loss_D_real_wrong) * 0.5) * 0.5
+        self.loss_D.backward()
+
+    def backward_G(self):
+        """wsgan_emb_model.py:371-437 with lambda_IP = 0 and the plain encoder."""
+        opt = self.opt
+        self.loss_G_GAN = self.criterionGAN(self.netD(self.fake_B, self.embedding_B), True)
+        if opt.lambda_A_GAN > 0.0:
+            self.loss_G_GAN_cycle = self.criterionGAN(self.netD(self.rec_A, self.embedding_A), True) * opt.lambda_A_GAN
+        else:
+            self.loss_G_GAN_cycle = 0.0
+        self.loss_G_L1 = self.criterionL1(self.fake_B, self.real_A) * opt.lambda_L1 if opt.lambda_L1 > 0.0 else 0.0
+        self.loss_G_IP = 0.0
+        self.loss_G_cycle = self.criterionCycle(self.rec_A, self.real_A) * opt.lambda_A if opt.lambda_A > 0.0 else 0.0
+        if opt.lambda_z > 0.0:
+            pred_y = self.netE(self.transform_E(self.fake_B_E))
+            self.loss_z_rec = self.criterionRec(pred_y, self.y_B) * opt.lambda_z
+        else:
+            self.loss_z_rec = 0.0
+        self.loss_G = self.loss_G_GAN + self.loss_G_IP + self.loss_G_L1 + self.loss_G_cycle + self.loss_z_rec + self.loss_G_GAN_cycle
+        self.loss_G.backward()
+
+    def update_D(self):
+        self.set_requires_grad(self.netD, True)
+        self.sync_D.zero()                 # optimizer_D.zero_grad()
+        self.backward_D()
+        self.sync_D.all_reduce()
+        self.optimizer_D.step()
+
+    def update_G(self):
+        self.set_requires_grad(self.netD, False)
+        self.sync_G.zero()                 # optimizer_G.zero_grad()
+        self.backward_G()
+        self.sync_G.all_reduce()
+        self.optimizer_G.step()
+
+    def optimize_parameters(self):
+        """wsgan_emb_model.py:478-484."""
+        self.forward()
+        self.update_G()
+        self.update_D()
+
+    def get_current_visuals(self):
+        return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str) and hasattr(self, n))
