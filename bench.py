@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--ref-batch", type=int, default=2, help="pairs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-igemm", default="", help="write the per-plan igemm timing table of the roofline pass to this file")
     return ap.parse_args()
 
 
@@ -227,6 +228,14 @@ def main():
         torch.cuda.synchronize()
         ev = ops.Stats.igemm_events
         ops.Stats.igemm_events = None
+        if args.dump_igemm:
+            agg = {}
+            for note, f, a, b in ev:
+                d = agg.setdefault(note, [0, 0.0, 0])
+                d[0] += 1; d[1] += a.elapsed_time(b); d[2] += f
+            with open(args.dump_igemm, "w") as fh:
+                for note, (n, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    fh.write("%-40s n=%3d  %8.3f ms/step  issued %7.1f TFLOP/s\n" % (note, n / nprof, t / nprof, f / max(t, 1e-9) / 1e9))
         tot_ms = sum(a.elapsed_time(b) for _, _, a, b in ev) / nprof
         n_ig = len(ev) / nprof
         issued = sum(f for _, f, _, _ in ev) / nprof

