@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 4
+#define PCGAN_ABI_VERSION 5
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -258,6 +258,11 @@ typedef struct {
   float* sums;                          /* [groups][c][2], zeroed by the caller */
   void* dx; int32_t dx_pad;             /* pass 2 outputs                       */
   void* dres; int32_t dres_pad;         /* optional: g (masked dy)              */
+  int32_t dy_fold;                      /* 0: dy is read at its interior; 2: dy is the gradient of a reflect-padded
+                                           buffer (pad dy_pad) whose halo is folded onto the mirror pixels while
+                                           reading (nn.ReflectionPad2d backward fused into this pass); 1: halo dropped */
+  int32_t affine;                       /* 0: scale == rstd and shift == -mean*rstd exactly (no gamma / beta), so
+                                           xhat is the pre-activation itself (InstanceNorm2d(affine=False)); 1: general */
 } pcgan_norm_bwd_args;
 int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
 int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -85,7 +85,7 @@ class NormBwdArgs(C.Structure):
                 ("mean", vp), ("rstd", vp), ("scale", vp), ("shift", vp), ("groups", i32),
                 ("res_scale", vp), ("res_shift", vp), ("res_groups", i32), ("drop_mask", vp),
                 ("act", i32), ("act_slope", f32), ("n", i32), ("h", i32), ("w", i32), ("c", i32),
-                ("count", f32), ("sums", vp), ("dx", vp), ("dx_pad", i32), ("dres", vp), ("dres_pad", i32)]
+                ("count", f32), ("sums", vp), ("dx", vp), ("dx_pad", i32), ("dres", vp), ("dres_pad", i32), ("dy_fold", i32), ("affine", i32)]
 
 
 class MaxpoolArgs(C.Structure):

@@ -183,4 +183,27 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(h);
 }
 
+// 8 bf16 channels <-> 8 floats (one 16-byte vector)
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+// element offset of interior pixel (n,y,x), channel 0, in a padded NHWC buffer
+__device__ __forceinline__ int64_t pix_off(int n, int y, int x, int h, int w, int c, int pad) {
+  const int64_t hp = h + 2 * pad, wp = w + 2 * pad;
+  return ((static_cast<int64_t>(n) * hp + (y + pad)) * wp + (x + pad)) * c;
+}
+
 }  // namespace pcgan

@@ -17,28 +17,6 @@ static inline int grid_for(int64_t work_items, int per_block = kThreads, int wav
   return static_cast<int>(blocks);
 }
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-}
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
-  uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-__device__ __forceinline__ int reflect_idx(int i, int n) {
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * (n - 1) - i;
-  return i;
-}
-// element offset of interior pixel (n,y,x), channel 0, in a padded NHWC buffer
-__device__ __forceinline__ int64_t pix_off(int n, int y, int x, int h, int w, int c, int pad) {
-  const int64_t hp = h + 2 * pad, wp = w + 2 * pad;
-  return ((static_cast<int64_t>(n) * hp + (y + pad)) * wp + (x + pad)) * c;
-}
-
 // ------------------------------------------------------------ gather / scatter
 __global__ void gather_cast_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -205,234 +183,6 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __
       }
     }
     gsrc[i] = acc;
-  }
-}
-
-// -------------------------------------------------------------- norm finalize
-__global__ void norm_finalize_kernel(pcgan_norm_finalize_args a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.c) return;
-  float mean_acc = 0.f, var_acc = 0.f;
-  const float gam = a.gamma ? a.gamma[c] : 1.f;
-  const float bet = a.beta ? a.beta[c] : 0.f;
-  for (int g = 0; g < a.groups; ++g) {
-    const float s1 = a.stats[(static_cast<int64_t>(g) * a.c + c) * 2 + 0];
-    const float s2 = a.stats[(static_cast<int64_t>(g) * a.c + c) * 2 + 1];
-    const float mean = s1 / a.count;
-    float var = s2 / a.count - mean * mean;
-    var = var > 0.f ? var : 0.f;
-    const float rstd = rsqrtf(var + a.eps);
-    const int64_t o = static_cast<int64_t>(g) * a.c + c;
-    if (a.mean) a.mean[o] = mean;
-    if (a.rstd) a.rstd[o] = rstd;
-    if (a.scale) a.scale[o] = gam * rstd;
-    if (a.shift) a.shift[o] = bet - mean * gam * rstd;
-    mean_acc += mean;
-    var_acc += var;
-  }
-  if (a.running_mean) {
-    const float m = mean_acc / a.groups;
-    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * m;
-  }
-  if (a.running_var) {
-    const float unbias = a.count > 1.f ? a.count / (a.count - 1.f) : 1.f;
-    const float v = var_acc / a.groups * unbias;
-    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * v;
-  }
-}
-
-// ----------------------------------------------------------------- norm apply
-// pre-activation of one 8-channel vector at interior pixel (n, y, x)
-struct NormCtx {
-  const __nv_bfloat16* x; int x_pad;
-  const __nv_bfloat16* res; int res_pad;
-  const float* scale; const float* shift; int groups;
-  const float* res_scale; const float* res_shift; int res_groups;
-  const float* drop_mask;
-  int n, h, w, c;
-};
-__device__ __forceinline__ void norm_pre(const NormCtx& k, int n, int y, int x, int c0, float (&xv)[8], float (&pre)[8]) {
-  load8(k.x + pix_off(n, y, x, k.h, k.w, k.c, k.x_pad) + c0, xv);
-  if (k.drop_mask) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] *= k.drop_mask[static_cast<int64_t>(n) * k.c + c0 + j];
-  }
-  if (k.scale) {
-    const int64_t so = static_cast<int64_t>(k.groups > 1 ? n : 0) * k.c + c0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pre[j] = k.scale[so + j] * xv[j] + k.shift[so + j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pre[j] = xv[j];
-  }
-  if (k.res) {
-    float rv[8];
-    load8(k.res + pix_off(n, y, x, k.h, k.w, k.c, k.res_pad) + c0, rv);
-    if (k.res_scale) {
-      const int64_t ro = static_cast<int64_t>(k.res_groups > 1 ? n : 0) * k.c + c0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pre[j] += k.res_scale[ro + j] * rv[j] + k.res_shift[ro + j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pre[j] += rv[j];
-    }
-  }
-}
-
-__global__ void norm_apply_kernel(pcgan_norm_apply_args a) {
-  NormCtx k{reinterpret_cast<const __nv_bfloat16*>(a.x), a.x_pad, reinterpret_cast<const __nv_bfloat16*>(a.res), a.res_pad,
-            a.scale, a.shift, a.groups, a.res_scale, a.res_shift, a.res_groups, a.drop_mask, a.n, a.h, a.w, a.c};
-  const int cv = a.c >> 3;
-  const int hp = a.h + 2 * a.y_pad, wp = a.w + 2 * a.y_pad;
-  const int64_t total = static_cast<int64_t>(a.n) * hp * wp * cv;
-  __nv_bfloat16* yout = reinterpret_cast<__nv_bfloat16*>(a.y);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = static_cast<int>(i % cv) << 3;
-    int64_t p = i / cv;
-    const int px = static_cast<int>(p % wp); p /= wp;
-    const int py = static_cast<int>(p % hp);
-    const int n = static_cast<int>(p / hp);
-    int y = py - a.y_pad, x = px - a.y_pad;
-    __nv_bfloat16* d = yout + ((static_cast<int64_t>(n) * hp + py) * wp + px) * a.c + c0;
-    const bool halo = y < 0 || y >= a.h || x < 0 || x >= a.w;
-    if (halo && a.y_halo == PCGAN_HALO_ZERO) {
-      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    y = reflect_idx(y, a.h);
-    x = reflect_idx(x, a.w);
-    float xv[8], pre[8];
-    norm_pre(k, n, y, x, c0, xv, pre);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pre[j] = apply_act(pre[j], a.act, a.act_slope);
-    store8(d, pre);
-  }
-}
-
-// ------------------------------------------------------------------ halo fold
-__global__ void halo_fold_kernel(pcgan_fold_args a) {
-  const int cv = a.c >> 3;
-  const int64_t total = static_cast<int64_t>(a.n) * a.h * a.w * cv;
-  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(a.gpad);
-  const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(a.add);
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-  const int p = a.g_pad;
-  const int hp = a.h + 2 * p, wp = a.w + 2 * p;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = static_cast<int>(i % cv) << 3;
-    int64_t q = i / cv;
-    const int x = static_cast<int>(q % a.w); q /= a.w;
-    const int y = static_cast<int>(q % a.h);
-    const int n = static_cast<int>(q / a.h);
-    // padded rows / cols that mirror onto (y, x)
-    int ys[3], xs[3], ny = 1, nx = 1;
-    ys[0] = y + p; xs[0] = x + p;
-    if (a.halo == PCGAN_HALO_REFLECT) {
-      if (y >= 1 && y <= p) ys[ny++] = p - y;
-      if (y <= a.h - 2 && y >= a.h - 1 - p) ys[ny++] = p + 2 * (a.h - 1) - y;
-      if (x >= 1 && x <= p) xs[nx++] = p - x;
-      if (x <= a.w - 2 && x >= a.w - 1 - p) xs[nx++] = p + 2 * (a.w - 1) - x;
-    }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int iy = 0; iy < ny; ++iy)
-      for (int ix = 0; ix < nx; ++ix) {
-        float v[8];
-        load8(g + ((static_cast<int64_t>(n) * hp + ys[iy]) * wp + xs[ix]) * a.c + c0, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += v[j];
-      }
-    if (add) {
-      float v[8];
-      load8(add + pix_off(n, y, x, a.h, a.w, a.c, a.add_pad) + c0, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += v[j];
-    }
-    store8(out + pix_off(n, y, x, a.h, a.w, a.c, a.out_pad) + c0, acc);
-  }
-}
-
-// -------------------------------------------------------------- norm backward
-__device__ __forceinline__ void norm_bwd_g(const pcgan_norm_bwd_args& a, const NormCtx& k, int n, int y, int x, int c0,
-                                           float (&g)[8], float (&xhat)[8]) {
-  float xv[8], pre[8], dy[8];
-  norm_pre(k, n, y, x, c0, xv, pre);
-  load8(reinterpret_cast<const __nv_bfloat16*>(a.dy) + pix_off(n, y, x, a.h, a.w, a.c, a.dy_pad) + c0, dy);
-  const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float d = 1.f;
-    if (a.act == PCGAN_ACT_RELU) d = pre[j] > 0.f ? 1.f : 0.f;
-    else if (a.act == PCGAN_ACT_LRELU) d = pre[j] > 0.f ? 1.f : a.act_slope;
-    g[j] = dy[j] * d;
-    xhat[j] = a.mean ? (xv[j] - a.mean[so + j]) * a.rstd[so + j] : 0.f;
-  }
-}
-
-__global__ void norm_bwd_reduce_kernel(pcgan_norm_bwd_args a, int pix_per_block) {
-  NormCtx k{reinterpret_cast<const __nv_bfloat16*>(a.x), a.x_pad, reinterpret_cast<const __nv_bfloat16*>(a.res), a.res_pad,
-            a.scale, a.shift, a.groups, a.res_scale, a.res_shift, a.res_groups, a.drop_mask, a.n, a.h, a.w, a.c};
-  __shared__ float red[kThreads * 16];
-  const int cv = a.c >> 3;             // power of two, <= 256
-  const int lanes = kThreads / cv;     // pixel lanes per block
-  const int myc = threadIdx.x % cv, myl = threadIdx.x / cv;
-  const int n = blockIdx.y;
-  const int hw = a.h * a.w;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(p0 + pix_per_block, hw);
-  float s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  for (int p = p0 + myl; p < p1; p += lanes) {
-    float g[8], xh[8];
-    norm_bwd_g(a, k, n, p / a.w, p % a.w, myc << 3, g, xh);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] += g[j] * xh[j]; }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
-  __syncthreads();
-  // threads [0, cv*16): one (channel-vector, slot) each, summed over the pixel lanes
-  for (int t = threadIdx.x; t < cv * 16; t += kThreads) {
-    const int c = t / 16, slot = t % 16;
-    float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red[(l * cv + c) * 16 + slot];
-    const int ch = (c << 3) + (slot & 7);
-    const int64_t o = (static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + ch) * 2 + (slot >> 3);
-    atomicAdd(a.sums + o, s);
-  }
-}
-
-__global__ void norm_bwd_apply_kernel(pcgan_norm_bwd_args a) {
-  NormCtx k{reinterpret_cast<const __nv_bfloat16*>(a.x), a.x_pad, reinterpret_cast<const __nv_bfloat16*>(a.res), a.res_pad,
-            a.scale, a.shift, a.groups, a.res_scale, a.res_shift, a.res_groups, a.drop_mask, a.n, a.h, a.w, a.c};
-  const int cv = a.c >> 3;
-  const int64_t total = static_cast<int64_t>(a.n) * a.h * a.w * cv;
-  const float inv = a.count > 0.f ? 1.f / a.count : 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = static_cast<int>(i % cv) << 3;
-    int64_t q = i / cv;
-    const int x = static_cast<int>(q % a.w); q /= a.w;
-    const int y = static_cast<int>(q % a.h);
-    const int n = static_cast<int>(q / a.h);
-    float g[8], xh[8];
-    norm_bwd_g(a, k, n, y, x, c0, g, xh);
-    if (a.dres) store8(reinterpret_cast<__nv_bfloat16*>(a.dres) + pix_off(n, y, x, a.h, a.w, a.c, a.dres_pad) + c0, g);
-    if (a.dx) {
-      const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
-      float dx[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float sc = a.scale ? a.scale[so + j] : 1.f;
-        float v = g[j];
-        if (a.count > 0.f) v -= a.sums[(so + j) * 2] * inv + xh[j] * a.sums[(so + j) * 2 + 1] * inv;
-        v *= sc;
-        if (a.drop_mask) v *= a.drop_mask[static_cast<int64_t>(n) * a.c + c0 + j];
-        dx[j] = v;
-      }
-      store8(reinterpret_cast<__nv_bfloat16*>(a.dx) + pix_off(n, y, x, a.h, a.w, a.c, a.dx_pad) + c0, dx);
-    }
   }
 }
 
@@ -626,76 +376,8 @@ extern "C" int pcgan_unpack_resize_bwd(const pcgan_unpack_args* a, pcgan_stream_
   return PCGAN_OK;
 }
 
-extern "C" int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stream_t s) {
-  if (!a || !a->stats || a->groups < 1 || a->c < 1 || a->count <= 0.f) return fail(PCGAN_ERR_INVALID, "norm_finalize: bad argument");
-  norm_finalize_kernel<<<(a->c + 127) / 128, 128, 0, STREAM(s)>>>(*a);
-  PCGAN_LAUNCH_OK("norm_finalize_kernel");
-  return PCGAN_OK;
-}
-
 static int check_cvec(int c, const char* who) {
   if (c < 8 || c % 8 != 0) return fail(PCGAN_ERR_UNSUPPORTED, "%s: channels=%d must be a multiple of 8", who, c);
-  return PCGAN_OK;
-}
-
-extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s) {
-  if (!a || !a->x || !a->y) return fail(PCGAN_ERR_INVALID, "norm_apply: null argument");
-  int rc = check_cvec(a->c, "norm_apply");
-  if (rc) return rc;
-  if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(PCGAN_ERR_INVALID, "norm_apply: scale and shift go together");
-  if (a->y_halo == PCGAN_HALO_REFLECT && (a->y_pad >= a->h || a->y_pad >= a->w)) return fail(PCGAN_ERR_INVALID, "norm_apply: reflect pad too large");
-  const int64_t total = static_cast<int64_t>(a->n) * (a->h + 2 * a->y_pad) * (a->w + 2 * a->y_pad) * (a->c / 8);
-  norm_apply_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
-  PCGAN_LAUNCH_OK("norm_apply_kernel");
-  return PCGAN_OK;
-}
-
-extern "C" int pcgan_halo_fold(const pcgan_fold_args* a, pcgan_stream_t s) {
-  if (!a || !a->gpad || !a->out) return fail(PCGAN_ERR_INVALID, "halo_fold: null argument");
-  int rc = check_cvec(a->c, "halo_fold");
-  if (rc) return rc;
-  if (a->halo == PCGAN_HALO_REFLECT && (2 * a->g_pad + 1 > a->h || 2 * a->g_pad + 1 > a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "halo_fold: image smaller than 2*pad+1");
-  const int64_t total = static_cast<int64_t>(a->n) * a->h * a->w * (a->c / 8);
-  halo_fold_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
-  PCGAN_LAUNCH_OK("halo_fold_kernel");
-  return PCGAN_OK;
-}
-
-static int check_bwd(const pcgan_norm_bwd_args* a) {
-  if (!a || !a->dy || !a->x) return fail(PCGAN_ERR_INVALID, "norm_bwd: null argument");
-  int rc = check_cvec(a->c, "norm_bwd");
-  if (rc) return rc;
-  const int cv = a->c / 8;
-  if (cv > kThreads || (cv & (cv - 1)) != 0) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd: channels/8=%d must be a power of two <= %d", cv, kThreads);
-  if (a->count > 0.f && (!a->mean || !a->rstd || !a->sums)) return fail(PCGAN_ERR_INVALID, "norm_bwd: statistics missing");
-  return PCGAN_OK;
-}
-
-extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_t s) {
-  int rc = check_bwd(a);
-  if (rc) return rc;
-  if (!a->sums) return fail(PCGAN_ERR_INVALID, "norm_bwd_reduce: sums is null");
-  const int hw = a->h * a->w;
-  const int sms = sm_count() > 0 ? sm_count() : 148;
-  // about four waves of blocks over (pixel chunks, samples)
-  int chunks = (4 * sms + a->n - 1) / a->n;
-  if (chunks < 1) chunks = 1;
-  int ppb = (hw + chunks - 1) / chunks;
-  const int lanes = kThreads / (a->c / 8);
-  if (ppb < lanes * 4) ppb = lanes * 4;
-  chunks = (hw + ppb - 1) / ppb;
-  norm_bwd_reduce_kernel<<<dim3(chunks, a->n), kThreads, 0, STREAM(s)>>>(*a, ppb);
-  PCGAN_LAUNCH_OK("norm_bwd_reduce_kernel");
-  return PCGAN_OK;
-}
-
-extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t s) {
-  int rc = check_bwd(a);
-  if (rc) return rc;
-  if (!a->dx && !a->dres) return fail(PCGAN_ERR_INVALID, "norm_bwd_apply: no output");
-  const int64_t total = static_cast<int64_t>(a->n) * a->h * a->w * (a->c / 8);
-  norm_bwd_apply_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
-  PCGAN_LAUNCH_OK("norm_bwd_apply_kernel");
   return PCGAN_OK;
 }
 

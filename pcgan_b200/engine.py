@@ -87,17 +87,69 @@ class ConvRT:
         ops.scatter_f32(packed, wm, self.weight.grad, accumulate=True)
 
 
-class NormState:
-    """Per-call statistics of one normalisation layer: [groups][C] each (groups = N for instance norm, 1 for batch norm)."""
+class Arena:
+    """Flat fp32 device buffer handed out in slices: every accumulator of a workspace (forward statistics, backward
+    sums) lives in one, so a pass clears all of them with a single memset instead of one per layer."""
 
-    def __init__(self, groups, c, dev):
+    def __init__(self, dev):
+        self.dev, self.size, self.flat, self.pending = dev, 0, None, []
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= d
+        n = (n + 3) // 4 * 4          # keep every slice 16-byte aligned
+        holder = _Slice(self, self.size, tuple(shape))
+        self.size += n
+        self.pending.append(holder)
+        return holder
+
+    def finalize(self):
+        self.flat = torch.zeros(max(self.size, 4), device=self.dev)
+        for h in self.pending:
+            n = 1
+            for d in h.shape:
+                n *= d
+            h.t = self.flat[h.off:h.off + n].view(h.shape)
+        self.pending = []
+
+    def zero(self):
+        self.flat.zero_()
+
+
+class _Slice:
+    def __init__(self, arena, off, shape):
+        self.arena, self.off, self.shape, self.t = arena, off, shape, None
+
+
+class NormState:
+    """Per-call statistics of one normalisation layer: [groups][C] each (groups = N for instance norm, 1 for batch norm).
+    With arenas, `stats` / `sums` are slices of the workspace's accumulator arenas (cleared once per pass by the program);
+    without, they are private tensors the caller clears."""
+
+    def __init__(self, groups, c, dev, stats_arena=None, sums_arena=None):
         self.groups, self.c = groups, c
-        self.stats = torch.zeros(groups, c, 2, device=dev)
+        self.affine = True
+        self._stats = stats_arena.take((groups, c, 2)) if stats_arena is not None else None
+        self._sums = sums_arena.take((groups, c, 2)) if sums_arena is not None else None
+        self._own_stats = torch.zeros(groups, c, 2, device=dev) if stats_arena is None else None
+        self._own_sums = torch.zeros(groups, c, 2, device=dev) if sums_arena is None else None
         self.mean = torch.empty(groups, c, device=dev)
         self.rstd = torch.empty(groups, c, device=dev)
         self.scale = torch.empty(groups, c, device=dev)
         self.shift = torch.empty(groups, c, device=dev)
-        self.sums = torch.zeros(groups, c, 2, device=dev)
+
+    @property
+    def stats(self):
+        return self._own_stats if self._stats is None else self._stats.t
+
+    @property
+    def sums(self):
+        return self._own_sums if self._sums is None else self._sums.t
+
+    @property
+    def pooled(self):
+        return self._stats is not None
 
 
 def accumulate_grad(p, g):

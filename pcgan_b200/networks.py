@@ -18,7 +18,7 @@ from torch.nn import init
 
 from . import _lib as L
 from . import ops
-from .engine import ConvRT, NormState, Pool, accumulate_grad, zeros_act
+from .engine import Arena, ConvRT, NormState, Pool, accumulate_grad, zeros_act
 from .plan import Geom, OutMap
 
 EPS = 1e-5
@@ -30,18 +30,23 @@ MOMENTUM = 0.1
 # ---------------------------------------------------------------------------------------
 def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, *, gamma=None, beta=None, rmean=None, rvar=None):
     """conv (+bias) with statistics in the epilogue, then the tiny finalize kernel."""
-    ns.stats.zero_()
+    if not ns.pooled:
+        ns.stats.zero_()
+    ns.affine = gamma is not None
     conv.forward(xbuf, rbuf, ns.stats)
     ops.norm_finalize(ns.stats, ns.groups, ns.c, count, eps=EPS, momentum=MOMENTUM, gamma=gamma, beta=beta,
                       mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, running_mean=rmean, running_var=rvar)
 
 
 def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count, dx, dx_pad, *, res=None, res_pad=0,
-                   res_scale=None, res_shift=None, res_groups=1, dres=None, dres_pad=0):
+                   res_scale=None, res_shift=None, res_groups=1, dres=None, dres_pad=0, dy_fold=0):
+    """Backward of one norm + activation unit.  dy_fold=2: `gy` is the gradient of the reflect-padded buffer (pad gy_pad)
+    straight out of the data-gradient kernel; its halo is folded onto the interior while it is read."""
     kw = dict(res=res, res_pad=res_pad, mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, groups=ns.groups,
               res_scale=res_scale, res_shift=res_shift, res_groups=res_groups, act=act, act_slope=slope, count=count,
-              sums=ns.sums)
-    ns.sums.zero_()
+              sums=ns.sums, dy_fold=dy_fold, affine=ns.affine)
+    if not ns.pooled:
+        ns.sums.zero_()
     ops.norm_bwd_reduce(gy, gy_pad, rbuf, rg, **kw)
     ops.norm_bwd_apply(gy, gy_pad, rbuf, rg, dx=dx, dx_pad=dx_pad, dres=dres, dres_pad=dres_pad, **kw)
 
@@ -132,10 +137,15 @@ class _GenProgram:
         ws.rb = [z(self.g_r3) for _ in self.blocks]
         ws.u1r, ws.u1, ws.u2r, ws.u2 = z(self.g_u1r), z(self.g_u1), z(self.g_u2r), z(self.g_u2)
         C1, C2, C3 = self.g_r1.c, self.g_r2.c, self.g_r3.c
-        ws.n1, ws.n2, ws.n3 = NormState(N, C1, dev), NormState(N, C2, dev), NormState(N, C3, dev)
-        ws.na = [NormState(N, C3, dev) for _ in self.blocks]
-        ws.nb = [NormState(N, C3, dev) for _ in self.blocks]
-        ws.nu1, ws.nu2 = NormState(N, C2, dev), NormState(N, C1, dev)
+        ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
+        NS = lambda c: NormState(N, c, dev, ws.stats_arena, ws.sums_arena)
+        ws.n1, ws.n2, ws.n3 = NS(C1), NS(C2), NS(C3)
+        ws.na = [NS(C3) for _ in self.blocks]
+        ws.nb = [NS(C3) for _ in self.blocks]
+        ws.nu1, ws.nu2 = NS(C2), NS(C1)
+        ws.head_sums = ws.sums_arena.take((1, 8, 2))
+        ws.stats_arena.finalize()
+        ws.sums_arena.finalize()
         return ws
 
     # ---------------------------------------------------------------- forward
@@ -143,6 +153,7 @@ class _GenProgram:
         m, S, N = self.mod.model, self.S, self.N
         ws = self.pool.take(0)
         h2, h4 = S // 2, S // 4
+        ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_REFLECT)
         _unit_forward(self.stem, ws.x0, ws.r1, ws.n1, S * S, rmean=m[2].running_mean, rvar=m[2].running_var)
         ops.norm_apply(ws.r1, self.g_r1, ws.a1, self.g_a1, y_halo=L.HALO_ZERO, scale=ws.n1.scale, shift=ws.n1.shift, groups=N, act=L.ACT_RELU)
@@ -176,21 +187,20 @@ class _GenProgram:
         m = self.mod.model
         nblk = len(self.blocks)
         R, Z = L.ACT_RELU, L.ACT_NONE
+        ws.sums_arena.zero()
         # head: d(pre-tanh) = dout * (1 - out^2)
         dyh = sc.get(self.g_dyh)
         ops.pack_nchw(dout, dyh, self.g_dyh, mul_out=out, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO)
         if need_w:
             self.head.backward_weight(dyh, ws.u2)
-            hs = torch.zeros(1, 8, 2, device=self.dev)
+            hs = ws.head_sums.t
             ops.norm_bwd_reduce(dyh, 6, dyh, self.g_dyh, sums=hs, count=0.0)
             accumulate_grad(self.head.bias, hs[0, : self.mod.output_nc, 0])
         dfull = sc.get(self.g_u2full)
         self.head.backward_data(dyh, dfull)
-        g = sc.get(self.g_u2r, "g_u2")
-        ops.halo_fold(dfull, self.g_u2, g, 0, halo=L.HALO_REFLECT)
-        # up2 unit
+        # up2 unit; the reflect-pad fold of the head's data gradient happens while it is read
         dy = sc.get(self.g_a1, "dy")
-        _norm_backward(g, 0, ws.u2r, self.g_u2r, ws.nu2, R, 0.0, S * S, dy, 1)
+        _norm_backward(dfull, 3, ws.u2r, self.g_u2r, ws.nu2, R, 0.0, S * S, dy, 1, dy_fold=2)
         if need_w:
             self.up2.backward_weight(dy, ws.u1)
         g = sc.get(self.g_u1r, "g_u1")
@@ -211,10 +221,8 @@ class _GenProgram:
                 cb.backward_weight(dyb, ws.h[i])
             dfull = sc.get(self.g_bfull, "dfull")
             cb.backward_data(dyb, dfull)
-            gh = sc.get(self.g_r3, "gh")
-            ops.halo_fold(dfull, self.g_b, gh, 0, halo=L.HALO_REFLECT)
             dya = sc.get(self.g_b, "dya")
-            _norm_backward(gh, 0, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1)
+            _norm_backward(dfull, 1, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1, dy_fold=2)
             if need_w:
                 ca.backward_weight(dya, ws.b[i])
             ca.backward_data(dya, dfull)
@@ -384,12 +392,18 @@ class _DiscProgram:
         ws.x0 = zeros_act(self.g_x0, dev)
         ws.y = [zeros_act(g, dev) for g in self.g_y]
         ws.r = [None] + [zeros_act(g, dev) for g in self.g_r[1:]]
-        ws.ns = [None] + [NormState(1, c, dev) for c in self.chans[1:]]
+        ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
+        ws.ns = [None] + [NormState(1, c, dev, ws.stats_arena, ws.sums_arena) for c in self.chans[1:]]
+        ws.head_sums = ws.sums_arena.take((1, 8, 2))
+        ws.l0_sums = ws.sums_arena.take((1, self.chans[0], 2))
+        ws.stats_arena.finalize()
+        ws.sums_arena.finalize()
         return ws
 
     def forward(self, x, z):
         m, N = self.mod.model, self.N
         ws = self.pool.take(0)
+        ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_ZERO)
         self.convs[0].forward(ws.x0, ws.y[0])
         for li in range(1, len(self.sizes)):
@@ -406,6 +420,7 @@ class _DiscProgram:
 
     def backward(self, ws, out, dout, need_dx, need_w):
         m, N, sc = self.mod.model, self.N, self.scratch
+        ws.sums_arena.zero()
         dyh = sc.get(self.g_dyh)
         if self.mod.use_sigmoid:
             ops.pack_nchw(dout, dyh, self.g_dyh, mul_out=out, mul_kind=L.ACT_SIGMOID, halo=L.HALO_ZERO)
@@ -413,7 +428,7 @@ class _DiscProgram:
             ops.pack_nchw(dout, dyh, self.g_dyh, halo=L.HALO_ZERO)
         if need_w:
             self.head.backward_weight(dyh, ws.y[-1])
-            hs = torch.zeros(1, 8, 2, device=self.dev)
+            hs = ws.head_sums.t
             ops.norm_bwd_reduce(dyh, 2, dyh, self.g_dyh, sums=hs, count=0.0)
             accumulate_grad(self.head.bias, hs[0, :1, 0])
         g = sc.get(self.g_r[-1], "g%d" % (len(self.sizes) - 1))
@@ -431,7 +446,7 @@ class _DiscProgram:
             self.convs[li].backward_data(dy, g)
         # layer 0: LeakyReLU backward from the sign of the stored output, bias gradient = sum
         dy = sc.get(self.g_r[0], "dy0")
-        s0 = torch.zeros(1, self.chans[0], 2, device=self.dev)
+        s0 = ws.l0_sums.t
         kw = dict(act=L.ACT_LRELU, act_slope=0.2, count=0.0, sums=s0)
         ops.norm_bwd_reduce(g, 0, ws.y[0], self.g_y[0], **kw)
         ops.norm_bwd_apply(g, 0, ws.y[0], self.g_y[0], dx=dy, dx_pad=0, **kw)
@@ -697,12 +712,12 @@ class _EncBlock:
             self.ds = ConvRT(name + ".downsample.0", holder.downsample[0].weight, None, self.g_x, stride, 0, OutMap.nhwc(self.g_r),
                              stats=True, dyg=self.g_r, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
 
-    def new_ws(self, dev):
+    def new_ws(self, dev, stats_arena=None, sums_arena=None):
         w = _EncWorkspace()
         w.ra, w.h, w.rb, w.y = zeros_act(self.g_r, dev), zeros_act(self.g_y, dev), zeros_act(self.g_r, dev), zeros_act(self.g_y, dev)
-        w.na, w.nb = NormState(1, self.c, dev), NormState(1, self.c, dev)
+        w.na, w.nb = NormState(1, self.c, dev, stats_arena, sums_arena), NormState(1, self.c, dev, stats_arena, sums_arena)
         if self.ds is not None:
-            w.rd, w.nd = zeros_act(self.g_r, dev), NormState(1, self.c, dev)
+            w.rd, w.nd = zeros_act(self.g_r, dev), NormState(1, self.c, dev, stats_arena, sums_arena)
         return w
 
     def forward(self, xbuf, w):
@@ -797,17 +812,21 @@ class _EncProgram:
         ws, dev, N = _EncWorkspace(), self.dev, self.N
         ws.x0, ws.r0, ws.a0, ws.p = zeros_act(self.g_x0, dev), zeros_act(self.g_r0, dev), zeros_act(self.g_a0, dev), zeros_act(self.g_p, dev)
         ws.idx = torch.zeros(self.g_pr.numel, dtype=torch.uint8, device=dev)
-        ws.n0 = NormState(1, 64, dev)
-        ws.blk = [b.new_ws(dev) for b in self.blocks]
+        ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
+        ws.n0 = NormState(1, 64, dev, ws.stats_arena, ws.sums_arena)
+        ws.blk = [b.new_ws(dev, ws.stats_arena, ws.sums_arena) for b in self.blocks]
         ws.rh, ws.hh, ws.fin = zeros_act(self.g_rh, dev), zeros_act(self.g_hh, dev), zeros_act(self.g_fin, dev)
-        ws.nh = NormState(1, self.nf, dev)
-        ws.nfin = NormState(N, 1, dev)
+        ws.nh = NormState(1, self.nf, dev, ws.stats_arena, ws.sums_arena)
+        ws.nfin = NormState(N, 1, dev, ws.stats_arena, ws.sums_arena)
+        ws.stats_arena.finalize()
+        ws.sums_arena.finalize()
         return ws
 
     def forward(self, x):
         mod, N = self.mod, self.N
         rn = mod.base.model
         ws = self.pool.take(0)
+        ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
         s2 = self.S // 2
         _unit_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, gamma=rn.bn1.weight.detach(), beta=rn.bn1.bias.detach(),
@@ -825,13 +844,13 @@ class _EncProgram:
         bn.num_batches_tracked += 1
         ops.norm_apply(ws.rh, self.g_rh, ws.hh, self.g_hh, y_halo=L.HALO_ZERO, scale=ws.nh.scale, shift=ws.nh.shift, groups=1,
                        act=L.ACT_LRELU, act_slope=mod.cnn_relu_slope)
-        ws.nfin.stats.zero_()
         self.head2.forward(ws.hh, ws.fin, ws.nfin.stats)
         y = (ws.nfin.stats[:, 0, 0] / float(hf * hf)).view(N, 1, 1, 1)
         return y, ws
 
     def backward(self, ws, gy):
         mod, N, sc, hf = self.mod, self.N, self.scratch, self.hf
+        ws.sums_arena.zero()
         gmap = (gy.view(N, 1, 1, 1) / float(hf * hf)).expand(N, 1, hf, hf).contiguous()
         dyf = sc.get(self.g_dyfin)
         ops.pack_nchw(gmap, dyf, self.g_dyfin, halo=L.HALO_ZERO)

@@ -134,12 +134,13 @@ def halo_fold(gpad, gg: Geom, out, out_pad, *, halo=L.HALO_REFLECT, add=None, ad
 
 def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, scale=None, shift=None, groups=1,
               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, count=0.0,
-              sums=None, dx=None, dx_pad=0, dres=None, dres_pad=0):
+              sums=None, dx=None, dx_pad=0, dres=None, dres_pad=0, dy_fold=0, affine=1):
     return L.NormBwdArgs(dy=_ptr(dy), dy_pad=dy_pad, x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad,
                          mean=_ptr(mean), rstd=_ptr(rstd), scale=_ptr(scale), shift=_ptr(shift), groups=groups,
                          res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
                          drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, n=xg.n, h=xg.h, w=xg.w, c=xg.c,
-                         count=float(count), sums=_ptr(sums), dx=_ptr(dx), dx_pad=dx_pad, dres=_ptr(dres), dres_pad=dres_pad)
+                         count=float(count), sums=_ptr(sums), dx=_ptr(dx), dx_pad=dx_pad, dres=_ptr(dres), dres_pad=dres_pad,
+                         dy_fold=dy_fold, affine=int(affine))
 
 
 def norm_bwd_reduce(dy, dy_pad, x, xg, **kw):

@@ -99,8 +99,7 @@ def test_generator_backward_chain_teacher_forced():
     # fold of the reflect-padded gradient
     xi = torch.zeros(N, 64, S, S, device=DEV, requires_grad=True)
     F.pad(xi, (3,) * 4, mode="reflect").backward(full(sc.get(P.g_u2full), P.g_u2full))
-    g_u2 = inner(sc.get(P.g_u2r, "g_u2"), P.g_u2r)
-    check("head.fold", g_u2, xi.grad, T_ACT, log)
+    g_u2 = xi.grad.detach()   # the fold itself is fused into the up2 norm backward (dy_fold=2): checked through up2.norm.bwd
     # ---- up2: ConvT + IN + ReLU
     norm_stage("up2.norm", inner(ws.u2r, P.g_u2r), g_u2, inner(ws.u2, P.g_u2), inner(sc.get(P.g_a1, "dy"), P.g_a1))
     dy = inner(sc.get(P.g_a1, "dy"), P.g_a1)
@@ -130,8 +129,7 @@ def test_generator_backward_chain_teacher_forced():
     check("block.conv2.wgrad", grad(p + ".5.weight"), w.grad, T_LIN, log)
     xi = torch.zeros(N, 256, S // 4, S // 4, device=DEV, requires_grad=True)
     F.pad(xi, (1,) * 4, mode="reflect").backward(bf(x.grad))
-    gh = inner(sc.get(P.g_r3, "gh"), P.g_r3)
-    check("block.conv2.dgrad+fold", gh, xi.grad, T_LIN, log)
+    gh = xi.grad.detach()     # fold fused into block.norm1's backward (dy_fold=2)
     norm_stage("block.norm1", inner(ws.ra[0], P.g_r3), gh, inner(ws.h[0], P.g_b), inner(sc.get(P.g_b, "dya"), P.g_b))
     dya = inner(sc.get(P.g_b, "dya"), P.g_b)
     x = full(ws.b[0], P.g_b).clone().requires_grad_(True)

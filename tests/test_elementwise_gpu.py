@@ -205,3 +205,50 @@ def test_teacher_forced_generator_unit():
     e_dx, e_dw = rel(from_buf(gxb, gr), xr.grad), rel(w.grad, wr.grad)
     print("teacher-forced unit: fwd %.3e dgrad %.3e wgrad %.3e" % (e_fwd, e_dx, e_dw))
     assert e_fwd < 2e-2 and e_dx < 2e-2 and e_dw < 2e-2
+
+
+@pytest.mark.parametrize("C,H,pad", [(64, 16, 3), (256, 8, 1), (128, 12, 1)])
+def test_norm_backward_fused_fold_and_lean_variant(C, H, pad):
+    """norm_bwd with dy_fold=2 (reflect-pad gradient folded while it is read) == halo_fold followed by norm_bwd, and the
+    lean InstanceNorm variant (affine=0: xhat is the pre-activation) == the general one, against fp32 autograd of
+    relu(instance_norm(x)) fed the folded gradient (nn.ReflectionPad2d backward + nn.InstanceNorm2d backward)."""
+    from pcgan_b200.engine import NormState
+    torch.manual_seed(11)
+    N = 3
+    gr, gp = Geom(N, H, H, C, 0), Geom(N, H, H, C, pad)
+    gfull = Geom(N, H + 2 * pad, H + 2 * pad, C, 0)
+    r = bf(torch.randn(N, C, H, H, device=DEV) * 1.5 + 0.3)
+    rbuf = to_buf(r, 0)
+    gpad = bf(torch.randn(N, C, H + 2 * pad, H + 2 * pad, device=DEV))
+    gbuf = to_buf(gpad, 0)
+    ns = NormState(N, C, DEV)
+    st = torch.stack([r.sum((2, 3)), (r * r).sum((2, 3))], -1).contiguous()
+    ops.norm_finalize(st, N, C, H * H, mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift)
+    # reference
+    rr = r.clone().requires_grad_(True)
+    y = torch.relu(F.instance_norm(rr))
+    xi = torch.zeros(N, C, H, H, device=DEV, requires_grad=True)
+    F.pad(xi, (pad,) * 4, mode="reflect").backward(gpad)
+    y.backward(xi.grad)
+    outs = {}
+    for name, affine, fold in (("general+fold", 1, 2), ("lean+fold", 0, 2), ("lean, separate fold", 0, 0)):
+        ns.sums.zero_()
+        dx = torch.zeros(gp.numel + 512, dtype=torch.bfloat16, device=DEV)
+        kw = dict(mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, groups=N, act=L.ACT_RELU, count=H * H, sums=ns.sums,
+                  affine=affine)
+        if fold:
+            ops.norm_bwd_reduce(gbuf, pad, rbuf, gr, dy_fold=2, **kw)
+            ops.norm_bwd_apply(gbuf, pad, rbuf, gr, dx=dx, dx_pad=pad, dy_fold=2, **kw)
+        else:
+            gf = torch.zeros(gr.numel + 512, dtype=torch.bfloat16, device=DEV)
+            ops.halo_fold(gbuf, gp, gf, 0, halo=L.HALO_REFLECT)
+            ops.norm_bwd_reduce(gf, 0, rbuf, gr, **kw)
+            ops.norm_bwd_apply(gf, 0, rbuf, gr, dx=dx, dx_pad=pad, **kw)
+        outs[name] = from_buf(dx, gp)
+        halo = dx[: gp.numel].view(N, H + 2 * pad, H + 2 * pad, C).float()
+        halo[:, pad:pad + H, pad:pad + H] = 0
+        assert float(halo.abs().max()) == 0.0, "the halo of dx must stay zero"
+    for name, got in outs.items():
+        e = rel(got, rr.grad)
+        print("%s: %.3e" % (name, e))
+        assert e < (2e-2 if "separate" in name else 1e-2), name   # the separate fold rounds the folded gradient to bf16 once more
