@@ -193,8 +193,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host = time.perf_counter()
     for i in range(K):
         step(resident[i % pool])
+    host_ms = 1e3 * (time.perf_counter() - t_host) / K     # CPU time to enqueue one step (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -259,7 +261,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 2 * B * 3 * S * S * 4, "d2h_bytes_per_step": 9 * 4,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(round(launches * K)), "gpu_launches_per_step": launches,
+                "gpu_launches": int(round(launches * K)), "gpu_launches_per_step": launches, "host_enqueue_ms_per_step": host_ms,
                 "roofline": roof, "last_losses": last}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(S)

@@ -23,7 +23,7 @@ import torch
 
 from . import _lib as L
 from .plan import (ANY, ONE, Geom, IgemmSpec, OutMap, plan_box, plan_flat, plan_packed, plan_wgrad_box,
-                   wmap_packed, wmap_taps, _ceil)
+                   plan_wgrad_small_cout, wmap_packed, wmap_small_cout, wmap_taps, _ceil)
 
 
 def out_size(h, k, stride, cp, transposed=False, output_padding=0):
@@ -167,6 +167,9 @@ def conv_wgrad_plan(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, *, trans
     o = xg.pad - cp
     ho, wo = out_size(xg.h, k, stride, cp), out_size(xg.w, k, stride, cp)
     assert (dyg.h, dyg.w) == (ho, wo) or (dyg.h >= ho and dyg.w >= wo)
+    if (stride == 1 and xg.c == 64 and cin == 64 and cout <= 8 and dyg.c == 8 and k <= 8 and dyg.pad >= o + k - 1
+            and 2 * xg.pad - o <= dyg.pad and (dyg.h, dyg.w) == (ho, wo)):
+        return plan_wgrad_small_cout(xg, cin, dyg, k, o, note=note), wmap_small_cout(w_shape, k)
     if xg.c >= 64:
         assert xg.c == cin
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]

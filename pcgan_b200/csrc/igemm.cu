@@ -17,6 +17,7 @@
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -27,13 +28,15 @@ static constexpr int kDataBytes = 192 * 1024;      // operand ring: num_stages x
 static constexpr int kBoxBytesMN = 64 * 128;       // one MN-major box: 64 K-rows x 128 B
 static constexpr int kTmemCols = 512;              // 2 accumulator stages x 256 fp32 columns
 static constexpr int kAccCols = 256;
-static constexpr int kNumThreads = 256;
-// tail after the ring: barriers (512 B) | bias [256] f32 | per-warp stats accumulators [4][256][2] f32 |
-// per-warp transpose tiles [4][32][33] f32
+static constexpr int kNumThreads = 384;            // warps 0-3: TMA / MMA / TMEM alloc / idle; 4-7 and 8-11: two epilogue groups
+static constexpr int kEpiGroups = 2;               // group g drains TMEM stage g (every other tile of the CTA)
+// tail after the ring: barriers (512 B) | bias [2 groups][256] f32 | statistics accumulators [2 groups][256][2] f32 |
+// per-warp transpose tiles [8 warps][32][17] f32
 static constexpr int kTailBias = 512;
-static constexpr int kTailAcc = kTailBias + 256 * 4;
-static constexpr int kTailTr = kTailAcc + 4 * 256 * 2 * 4;
-static constexpr int kTailBytes = kTailTr + 4 * 32 * 33 * 4;
+static constexpr int kTailAcc = kTailBias + kEpiGroups * 256 * 4;
+static constexpr int kTailTr = kTailAcc + kEpiGroups * 256 * 2 * 4;
+static constexpr int kTailBytes = kTailTr + 8 * 32 * 17 * 4;
+static_assert(kDataBytes + 1024 + kTailBytes <= 227 * 1024, "shared memory budget");
 static constexpr int kSmemBytes = kDataBytes + 1024 /*align*/ + kTailBytes;
 
 struct DevParams {
@@ -91,6 +94,254 @@ __device__ __forceinline__ int32_t tile_group(const DevParams& P, const Digits& 
   return P.stats_comp == 0 ? s0 : s1;
 }
 
+struct EpiShared {
+  float* s_bias;       // this group's [256]
+  float* s_acc;        // this group's [256][2]
+  float* s_tr;         // this warp's [32][17]
+  uint64_t* tmem_full; // barrier of this group's TMEM stage
+  uint64_t* tmem_empty;
+  uint32_t group;      // 0 / 1: also the TMEM stage and the parity of the CTA-local tile index it handles
+};
+
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x, float slope) {
+  if (ACT == PCGAN_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == PCGAN_ACT_LRELU) return x > 0.f ? x : x * slope;
+  if (ACT == PCGAN_ACT_TANH) return tanhf(x);
+  if (ACT == PCGAN_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  return x;
+}
+
+// Forward / data-gradient epilogue of one epilogue group (4 warps = 128 accumulator rows): TMEM -> registers ->
+// (+bias, statistics, activation) -> global.  Thread = one accumulator row (output pixel), 32 fp32 columns per
+// tcgen05.ld.  The two groups of a CTA alternate tiles, each on its own TMEM stage.
+template <int ACT, bool BF16, bool STATS>
+__device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiShared es, uint32_t tmem_base, int32_t tile_begin,
+                                                int32_t tile_end) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = warp & 3;
+  const uint32_t row = q * 32 + lane;
+  const uint32_t et = (threadIdx.x - 128) & 127;
+  const uint32_t bar_stats = 1 + es.group, bar_bias = 3 + es.group;
+  float* my_tr = es.s_tr;
+  const int32_t block_n = P.block_n, n_tiles = P.n_tiles, n_valid = P.n_valid;
+  const int64_t cs = P.out_cstride;
+  const float* bias = P.bias;
+  const float slope = P.act_slope;
+  float* s_bias = es.s_bias;
+  float* s_acc = es.s_acc;
+  uint32_t acc_phase = 0;
+  int32_t cur_nt = -1, cur_group = -1;
+
+  // box-local index of this row along the four outer box dims (tile-invariant)
+  int32_t il[4];
+  {
+    uint32_t r = row;
+#pragma unroll
+    for (int dim = 0; dim < 4; ++dim) {
+      const int32_t bx = P.box[dim];
+      il[dim] = 0;
+      if (bx > 1) { il[dim] = r % bx; r /= bx; }
+    }
+  }
+  const bool row_in_box = row < static_cast<uint32_t>(P.a_rows);
+
+  auto flush_stats = [&](int32_t group, int32_t nt) {
+    named_bar_sync(bar_stats, 128);
+    float* gs = P.stats + static_cast<int64_t>(group) * n_valid * 2;
+    for (int32_t i = et; i < block_n * 2; i += 128) {
+      const int32_t ch = nt * block_n + (i >> 1);
+      const float v = s_acc[i];
+      s_acc[i] = 0.f;
+      if (ch < n_valid && v != 0.f) atomicAdd(gs + ch * 2 + (i & 1), v);
+    }
+    named_bar_sync(bar_stats, 128);
+  };
+
+  for (int32_t tile = tile_begin + static_cast<int32_t>(es.group); tile < tile_end; tile += kEpiGroups) {
+    const int32_t mt = tile / n_tiles;
+    const int32_t nt = tile - mt * n_tiles;
+    const Digits d = decompose(mt, P.t_count);
+    bool valid = row_in_box;
+    int64_t off = 0;
+#pragma unroll
+    for (int dim = 0; dim < 4; ++dim) {
+      const int32_t g = coord(d, P.e_base, P.e_step, dim) + il[dim];
+      int32_t k0 = 0, rem = g, k1, k2 = 0;
+      if (P.e_p1[dim] > 0) { k0 = g / P.e_p1[dim]; rem = g - k0 * P.e_p1[dim]; }
+      if (P.e_p2[dim] > 0) { k1 = rem / P.e_p2[dim]; k2 = rem - k1 * P.e_p2[dim]; } else { k1 = rem; }
+      const pcgan_comp& m0 = P.e_comp[dim][0];
+      const pcgan_comp& m1 = P.e_comp[dim][1];
+      const pcgan_comp& m2 = P.e_comp[dim][2];
+      valid = valid && g >= 0 && k0 >= m0.lo && k0 < m0.hi && k1 >= m1.lo && k1 < m1.hi && k2 >= m2.lo && k2 < m2.hi;
+      off += (k0 - m0.lo) * m0.stride + (k1 - m1.lo) * m1.stride + (k2 - m2.lo) * m2.stride;
+    }
+    if (STATS) {
+      const int32_t group = tile_group(P, d);
+      if (cur_group >= 0 && (group != cur_group || nt != cur_nt)) flush_stats(cur_group, cur_nt);
+      cur_group = group;
+    }
+    if (nt != cur_nt) {
+      if (bias != nullptr) {
+        named_bar_sync(bar_bias, 128);   // everybody in the group is done with the previous tile's bias
+        for (int32_t i = et; i < block_n; i += 128) {
+          const int32_t ch = nt * block_n + i;
+          s_bias[i] = ch < n_valid ? __ldg(bias + ch) : 0.f;
+        }
+        named_bar_sync(bar_bias, 128);
+      }
+      cur_nt = nt;
+    }
+    const int32_t ncol_limit = min(n_valid - nt * block_n, block_n);
+    using OutT = typename std::conditional<BF16, __nv_bfloat16, float>::type;
+    OutT* orow = reinterpret_cast<OutT*>(P.out) + off + static_cast<int64_t>(nt) * block_n * cs;
+    const bool fast_rows = cs == 1 && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
+
+    mbar_wait(es.tmem_full, acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols;
+
+    for (int32_t c0 = 0; c0 < ncol_limit; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + c0, raw);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      if (bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[i];
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      }
+      if (STATS) {
+        // column sums over the warp's 32 rows, 16 columns at a time through a [32][17] shared tile: lane l sums
+        // 16 rows of column l % 16, the two half sums meet with one shuffle
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) my_tr[lane * 17 + i] = valid ? v[16 * h + i] : 0.f;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+          const float* col = my_tr + (lane >> 4) * (16 * 17) + (lane & 15);
+#pragma unroll
+          for (int r2 = 0; r2 < 16; ++r2) {
+            const float x = col[r2 * 17];
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (lane < 16) {
+            atomicAdd(&s_acc[(c0 + 16 * h + lane) * 2 + 0], s1);
+            atomicAdd(&s_acc[(c0 + 16 * h + lane) * 2 + 1], s2);
+          }
+        }
+      }
+      if (valid) {
+        const int32_t ncols = ncol_limit - c0;
+        if (fast_rows && ncols >= 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i], slope);
+          if (BF16) {
+            uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              o4[i] = w;
+            }
+          } else {
+            float4* o4 = reinterpret_cast<float4*>(orow + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        } else {
+          OutT* o = orow + static_cast<int64_t>(c0) * cs;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < ncols) {
+              const float y = act_ct<ACT>(v[i], slope);
+              if (BF16) o[i * cs] = __float2bfloat16(y);
+              else o[i * cs] = y;
+            }
+          }
+        }
+      }
+    }
+    // accumulator drained: hand the TMEM stage back to the MMA warp
+    tcgen05_fence_before();
+    mbar_arrive(es.tmem_empty);
+    acc_phase ^= 1;
+  }
+  if (STATS && cur_group >= 0) flush_stats(cur_group, cur_nt);
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_dispatch(bool bf16, bool stats, const DevParams& P, const EpiShared& es, uint32_t tmem_base,
+                                             int32_t tile_begin, int32_t tile_end) {
+  if (bf16) {
+    if (stats) epilogue_kmajor<ACT, true, true>(P, es, tmem_base, tile_begin, tile_end);
+    else epilogue_kmajor<ACT, true, false>(P, es, tmem_base, tile_begin, tile_end);
+  } else {
+    if (stats) epilogue_kmajor<ACT, false, true>(P, es, tmem_base, tile_begin, tile_end);
+    else epilogue_kmajor<ACT, false, false>(P, es, tmem_base, tile_begin, tile_end);
+  }
+}
+
+// Weight-gradient epilogue: fp32 partial tiles added into the packed gradient with vector reductions.
+__device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShared es, uint32_t tmem_base, int32_t tile_begin,
+                                               int32_t tile_end, int32_t total_kb, int32_t kb_per_split) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = warp & 3;
+  const uint32_t row = q * 32 + lane;
+  const int32_t block_n = P.block_n;
+  uint32_t acc_phase = 0;
+  for (int32_t tile = tile_begin + static_cast<int32_t>(es.group); tile < tile_end; tile += kEpiGroups) {
+    int32_t t = tile;
+    const int32_t ks = t % P.ksplit; t /= P.ksplit;
+    const int32_t nt = t % P.n_tiles; t /= P.n_tiles;
+    const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
+    const int32_t tap = t;
+    const int32_t grow = mt * 128 + row;
+    const bool valid = grow < P.m_valid && ks * kb_per_split < total_kb;
+    const int32_t ncol_limit = min(P.wg_ncols - nt * block_n, block_n);
+    float* orow = reinterpret_cast<float*>(P.out) + static_cast<int64_t>(grow) * P.ldo + P.tap_bk[tap] + nt * block_n;
+    const bool aligned = (reinterpret_cast<uintptr_t>(orow) & 15) == 0;
+    mbar_wait(es.tmem_full, acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols;
+    for (int32_t c0 = 0; c0 < ncol_limit; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + c0, raw);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int32_t ncols = ncol_limit - c0;
+      float* o = orow + c0;
+      if (ncols >= 32 && aligned) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "r"(raw[i]), "r"(raw[i + 1]),
+                       "r"(raw[i + 2]), "r"(raw[i + 3])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncols) atomicAdd(o + i, __uint_as_float(raw[i]));
+      }
+    }
+    tcgen05_fence_before();
+    mbar_arrive(es.tmem_empty);
+    acc_phase ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ DevParams P) {
@@ -103,8 +354,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tail + kTailBias);
-  float* s_acc = reinterpret_cast<float*>(tail + kTailAcc);   // [4 warps][256][2]
-  float* s_tr = reinterpret_cast<float*>(tail + kTailTr);     // [4 warps][32][33]
+  float* s_acc = reinterpret_cast<float*>(tail + kTailAcc);   // [2 groups][256][2]
+  float* s_tr = reinterpret_cast<float*>(tail + kTailTr);     // [8 warps][32][17]
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -130,7 +381,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tmem_relinquish();
   }
   if (threadIdx.x >= 128) {
-    for (int i = threadIdx.x - 128; i < 4 * 256 * 2; i += 128) s_acc[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < kEpiGroups * 256 * 2; i += kNumThreads - 128) s_acc[i] = 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -243,173 +494,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    const uint32_t q = warp & 3;
-    const uint32_t row = q * 32 + lane;
-    const uint32_t et = threadIdx.x - 128;
-    const bool do_stats = !wgrad && P.stats_mode != PCGAN_STATS_NONE;
-    float* my_acc = s_acc + q * 512;
-    float* my_tr = s_tr + q * (32 * 33);
-    uint32_t acc = 0, acc_phase = 0;
-    int32_t cur_nt = -1, cur_group = -1;
-
-    auto flush_stats = [&](int32_t group, int32_t nt) {
-      named_bar_sync(1, 128);
-      float* gs = P.stats + static_cast<int64_t>(group) * P.n_valid * 2;
-      for (int32_t i = et; i < P.block_n * 2; i += 128) {
-        const int32_t ch = nt * P.block_n + (i >> 1);
-        const float s = s_acc[i] + s_acc[512 + i] + s_acc[1024 + i] + s_acc[1536 + i];
-        s_acc[i] = 0.f; s_acc[512 + i] = 0.f; s_acc[1024 + i] = 0.f; s_acc[1536 + i] = 0.f;
-        if (ch < P.n_valid && s != 0.f) atomicAdd(gs + ch * 2 + (i & 1), s);
+    const uint32_t eg = (warp - 4) >> 2;
+    EpiShared es{s_bias + eg * 256, s_acc + eg * 512, s_tr + (warp - 4) * (32 * 17), &tmem_full[eg], &tmem_empty[eg], eg};
+    if (wgrad) {
+      epilogue_wgrad(P, es, tmem_base, tile_begin, tile_end, total_kb, kb_per_split);
+    } else {
+      const bool bf = P.out_dtype == PCGAN_DT_BF16;
+      const bool st = P.stats_mode != PCGAN_STATS_NONE;
+      // one specialised copy of the tile loop per (activation, output type, statistics): the per-element code is
+      // straight-line, nothing about the layer is decided inside the column loops
+      switch (P.act) {
+        case PCGAN_ACT_RELU: epi_dispatch<PCGAN_ACT_RELU>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
+        case PCGAN_ACT_LRELU: epi_dispatch<PCGAN_ACT_LRELU>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
+        case PCGAN_ACT_TANH: epi_dispatch<PCGAN_ACT_TANH>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
+        case PCGAN_ACT_SIGMOID: epi_dispatch<PCGAN_ACT_SIGMOID>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
+        default: epi_dispatch<PCGAN_ACT_NONE>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
       }
-      named_bar_sync(1, 128);
-    };
-
-    for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
-      bool valid;
-      int64_t off = 0;
-      int32_t group = 0;
-      int32_t nt;
-      bool has_k = true;
-      if (!wgrad) {
-        const int32_t mt = tile / P.n_tiles;
-        nt = tile % P.n_tiles;
-        const Digits d = decompose(mt, P.t_count);
-        valid = row < static_cast<uint32_t>(P.a_rows);
-        uint32_t r = row;
-#pragma unroll
-        for (int dim = 0; dim < 4; ++dim) {
-          const int32_t bx = P.box[dim];
-          const int32_t i = r % bx;
-          r /= bx;
-          const int32_t g = coord(d, P.e_base, P.e_step, dim) + i;
-          int32_t c0 = 0, rem = g, c1, c2 = 0;
-          if (P.e_p1[dim] > 0) { c0 = g / P.e_p1[dim]; rem = g % P.e_p1[dim]; }
-          if (P.e_p2[dim] > 0) { c1 = rem / P.e_p2[dim]; c2 = rem % P.e_p2[dim]; } else { c1 = rem; }
-          const pcgan_comp& k0 = P.e_comp[dim][0];
-          const pcgan_comp& k1 = P.e_comp[dim][1];
-          const pcgan_comp& k2 = P.e_comp[dim][2];
-          valid = valid && g >= 0 && c0 >= k0.lo && c0 < k0.hi && c1 >= k1.lo && c1 < k1.hi && c2 >= k2.lo && c2 < k2.hi;
-          off += (c0 - k0.lo) * k0.stride + (c1 - k1.lo) * k1.stride + (c2 - k2.lo) * k2.stride;
-        }
-        if (do_stats) {
-          group = tile_group(P, d);
-          if (cur_group >= 0 && (group != cur_group || nt != cur_nt)) flush_stats(cur_group, cur_nt);
-          cur_group = group;
-        }
-        if (nt != cur_nt) {
-          if (P.bias != nullptr) {
-            named_bar_sync(2, 128);   // everybody is done with the previous tile's bias
-            for (int32_t i = et; i < P.block_n; i += 128) {
-              const int32_t ch = nt * P.block_n + i;
-              s_bias[i] = ch < P.n_valid ? __ldg(P.bias + ch) : 0.f;
-            }
-            named_bar_sync(2, 128);
-          }
-          cur_nt = nt;
-        }
-      } else {
-        int32_t t = tile;
-        const int32_t ks = t % P.ksplit; t /= P.ksplit;
-        nt = t % P.n_tiles; t /= P.n_tiles;
-        const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
-        const int32_t tap = t;
-        const int32_t grow = mt * 128 + row;
-        valid = grow < P.m_valid;
-        off = static_cast<int64_t>(grow) * P.ldo + P.tap_bk[tap];
-        has_k = ks * kb_per_split < total_kb;
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
-      const int32_t ncol_limit = wgrad ? min(P.wg_ncols - nt * P.block_n, P.block_n) : min(P.n_valid - nt * P.block_n, P.block_n);
-      for (int32_t c0 = 0; c0 < P.block_n; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + c0, raw);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const int32_t ncols = min(ncol_limit - c0, 32);  // valid columns in this chunk (may be <= 0)
-        const int32_t gcol = nt * P.block_n + c0;        // first global column of the chunk
-        if (wgrad) {
-          if (valid && has_k && ncols > 0) {
-            float* o = reinterpret_cast<float*>(P.out) + off + gcol;
-            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]),
-                             "f"(v[i + 2]), "f"(v[i + 3])
-                             : "memory");
-            } else {
-              for (int i = 0; i < ncols; ++i) atomicAdd(o + i, v[i]);
-            }
-          }
-          continue;
-        }
-        if (ncols <= 0) continue;
-        if (P.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += s_bias[c0 + i];
-        }
-        if (do_stats) {
-          // per-warp transpose through shared memory: lane l sums column l over the warp's 32 rows
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) my_tr[lane * 33 + i] = valid ? v[i] : 0.f;
-          __syncwarp();
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int r2 = 0; r2 < 32; ++r2) {
-            const float x = my_tr[r2 * 33 + lane];
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-          }
-          my_acc[(c0 + lane) * 2 + 0] += s1;
-          my_acc[(c0 + lane) * 2 + 1] += s2;
-        }
-        if (valid) {
-          if (P.act != PCGAN_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], P.act, P.act_slope);
-          }
-          if (P.out_dtype == PCGAN_DT_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + off + gcol * P.out_cstride;
-            if (P.out_cstride == 1 && ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-              uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 w;
-                w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                o4[i] = w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols) o[i * P.out_cstride] = __float2bfloat16(v[i]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(P.out) + off + gcol * P.out_cstride;
-            if (P.out_cstride == 1 && ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-              float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols) o[i * P.out_cstride] = v[i];
-            }
-          }
-        }
-      }
-      // accumulator drained: hand the TMEM stage back to the MMA warp
-      tcgen05_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (do_stats && cur_group >= 0) flush_stats(cur_group, cur_nt);
   }
 
   tcgen05_fence_before();

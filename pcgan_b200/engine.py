@@ -78,7 +78,7 @@ class ConvRT:
         """Accumulates into weight.grad (allocated on first use)."""
         g, wm, packed = self.wgrad
         packed.zero_()
-        if self.transposed:
+        if self.transposed or g.spec.swap_operands:
             g.run(xbuf, dybuf, packed)     # M side = input activations, N side = dY
         else:
             g.run(dybuf, xbuf, packed)

@@ -121,6 +121,7 @@ class IgemmSpec:
     b_k: int = 0
     flops: int = 0             # 2*MACs actually issued (incl. padding waste), for bookkeeping
     note: str = ""
+    swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
 
     @property
     def num_taps(self):
@@ -392,14 +393,19 @@ def _ksplit_for(total_kb, out_tiles, sms=148):
 
 
 def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[int, int, int]], ph: int, pw: int,
-                   n_stride: int, *, m_origin=(0, 0), n_packed_win: int = 0, note="") -> IgemmSpec:
+                   n_stride: int, *, m_origin=(0, 0), n_packed_win: int = 0, m_packed_win: int = 0, pix_box=None,
+                   note="") -> IgemmSpec:
     """Weight gradient over a ph x pw pixel grid per sample.
     M side: tensor mg (padded NHWC), pixel (n, y, x) read at padded (y + m_origin[0], x + m_origin[1]), m_ch channels.
     N side: tensor ng, pixel read at padded (n_stride*y + dy, n_stride*x + dx) for tap (dy, dx, kidx);
             n_ch channels (or, if n_packed_win > 0, the packed-row window of that many elements).
-    Output fp32 [m_ch][ldo] with column = kidx*ncols + channel."""
+    Output fp32 [m_ch][ldo] with column = kidx*ncols + channel.
+    m_packed_win > 0: the M side is read as a window of that many contiguous elements starting at the pixel (rows
+    beyond m_ch are the following pixels' channels; they are computed and dropped).  pix_box = (bw, bh) overrides
+    the 64-pixel box shape."""
     s = IgemmSpec(kind=L.IGEMM_WGRAD, note=note)
-    bw, bh = _pix_box64(pw, ph)
+    bw, bh = pix_box if pix_box else _pix_box64(pw, ph)
+    assert bw * bh == 64
     bn = 1
     assert mg.c % 8 == 0 and ng.c % 8 == 0
     ncols = n_packed_win if n_packed_win else n_ch
@@ -411,7 +417,7 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     tx, ty, tn = _ceil(pw, bw), _ceil(ph, bh), N
     s.t_count = [tx, ty, tn, 1]
     # M-side view (c, x, y, n)
-    s.a_dims = [mg.c, mg.wp, mg.hp, N, 1]
+    s.a_dims = [m_packed_win if m_packed_win else mg.c, mg.wp, mg.hp, N, 1]
     s.a_strides = [0, mg.c * 2, mg.wp * mg.c * 2, mg.hp * mg.wp * mg.c * 2, N * mg.hp * mg.wp * mg.c * 2]
     s.a_box = [64, bw, bh, bn, 1]
     s.a_base = [m_origin[1], m_origin[0], 0, 0]
@@ -458,6 +464,39 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     s.ksplit = _ksplit_for(total_kb, len(taps) * s.m_tiles * s.n_tiles)
     s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
     return s
+
+
+def plan_wgrad_small_cout(xg: Geom, cin: int, dyg: Geom, k: int, o: int, *, note="") -> IgemmSpec:
+    """Weight gradient of a stride-1 k x k convolution with very few output channels (the generator head,
+    networks.py:603-604: 64 -> 3): putting dY on the M side would pad 3 rows to 128, so the operands are swapped and the
+    8-channel dY buffer is read as a packed window of 8 pixels x 8 channels on the N side:
+        out[ci][r*64 + j*8 + co] = sum_{n, y', t} Xp[n][y'][t][ci] * dYp[n][y' + PD - r - o][t + PD - o - (k-1) + j][co]
+                                 = dW[co][ci][r][k-1-j]                      (j < k; Xp, dYp: padded buffers, PD = dyg.pad)
+    i.e. one MMA column block covers all k horizontal taps of a filter row as 8 pixel shifts of dY.  The M side is the
+    channel vector of pixel t (window of 128 elements = 2 pixels; the second pixel's rows are dropped: m_valid = cin).
+    o = xg.pad - conv padding.  Requires cin == xg.c == 64, dyg.c == 8, k <= 8, dyg.pad >= o + k - 1 and zero halos."""
+    assert xg.c == cin == 64 and dyg.c == 8 and k <= 8
+    PD = dyg.pad
+    assert PD >= o + k - 1 and xg.pad * 2 - o <= PD, (PD, o, k, xg.pad)
+    taps = [(PD - r - o, PD - o - (k - 1), r) for r in range(k)]
+    s = plan_wgrad_box(xg, cin, dyg, 8, taps, xg.hp, xg.wp, 1, m_origin=(0, 0), n_packed_win=64, m_packed_win=128,
+                       pix_box=(8, 8), note=note)
+    s.swap_operands = True
+    return s
+
+
+def wmap_small_cout(w_shape, k: int) -> torch.Tensor:
+    """Scatter map of plan_wgrad_small_cout: packed[ci][r*64 + j*8 + co] -> W[co][ci][r][k-1-j]."""
+    cout, cin = w_shape[0], w_shape[1]
+    idx = torch.full((cin, k, 8, 8), -1, dtype=torch.int64)
+    ci = torch.arange(cin).view(-1, 1, 1, 1)
+    r = torch.arange(k).view(1, -1, 1, 1)
+    j = torch.arange(8).view(1, 1, -1, 1)
+    co = torch.arange(8).view(1, 1, 1, -1)
+    flat = ((co * cin + ci) * k + r) * k + (k - 1 - j)
+    valid = (j < k) & (co < cout)
+    idx = torch.where(valid, flat, torch.full_like(flat, -1)).expand(cin, k, 8, 8)
+    return idx.reshape(-1).to(torch.int32)
 
 
 def plan_wgrad_flat(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[int, int, int]], *, note="") -> IgemmSpec:

@@ -159,7 +159,8 @@ def test_conv_wgrad(case):
     dy = torch.randn(N, cout, ho, ho)
     xg, dyg = Geom(N, H, H, cbuf, xpad), Geom(N, ho, ho, cobuf, dypad)
     sp, wm = CV.conv_wgrad_plan((cout, cin, k, k), dyg, xg, stride, cp)
-    dw = _wgrad(sp, wm, to_padded_nhwc(dy, dypad, "zero", cobuf), to_padded_nhwc(x, xpad, halo, cbuf), cout * cin * k * k)
+    dyb, xb = to_padded_nhwc(dy, dypad, "zero", cobuf), to_padded_nhwc(x, xpad, halo, cbuf)
+    dw = _wgrad(sp, wm, xb, dyb, cout * cin * k * k) if sp.swap_operands else _wgrad(sp, wm, dyb, xb, cout * cin * k * k)
     xr = F.pad(bf16_round(x), (cp,) * 4, mode="reflect" if halo == "reflect" else "constant")
     wref = torch.zeros(cout, cin, k, k, requires_grad=True)
     F.conv2d(xr, wref, stride=stride).backward(bf16_round(dy))

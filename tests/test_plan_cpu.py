@@ -194,7 +194,11 @@ def test_conv_wgrad_plan(case):
     sp, wm = CV.conv_wgrad_plan((cout, cin, k, k), dyg, xg, stride, cp)
     sp.to_desc()
     packed = torch.zeros(sp.b_rows * sp.b_k)
-    emu.run_wgrad(sp, to_padded_nhwc(dy, dypad, "zero", cobuf)[sp.a_elem_offset:], to_padded_nhwc(x, xpad, halo, cbuf)[sp.b_elem_offset:], packed)
+    dyb, xb = to_padded_nhwc(dy, dypad, "zero", cobuf), to_padded_nhwc(x, xpad, halo, cbuf)
+    if sp.swap_operands:   # few output channels: activations on the M side, dY (packed window) on the N side
+        emu.run_wgrad(sp, xb[sp.a_elem_offset:], dyb[sp.b_elem_offset:], packed)
+    else:
+        emu.run_wgrad(sp, dyb[sp.a_elem_offset:], xb[sp.b_elem_offset:], packed)
     dw = torch.zeros(cout * cin * k * k)
     idx = wm.long()
     dw[idx[idx >= 0]] = packed[idx >= 0]
