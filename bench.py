@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--ref-batch", type=int, default=2, help="pairs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step from Python instead of replaying a CUDA graph")
     ap.add_argument("--dump-igemm", default="", help="write the per-plan igemm timing table of the roofline pass to this file")
     return ap.parse_args()
 
@@ -152,9 +153,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, S, K, W = args.batch, args.size, args.steps, max(args.warmup, 3)
+    W_eff = W + (4 if not args.no_graph else 0)   # graph mode: 3 eager steps + the capture step come before the W replayed warm-ups
 
     torch.manual_seed(1234 + rank)
-    opt = default_options(batchSize=B, gpu_ids=[local], fineSize=S, loadSize=S)
+    opt = default_options(batchSize=B, gpu_ids=[local], fineSize=S, loadSize=S, cuda_graph=not args.no_graph)
     model = WSGANEmbModel()
     model.initialize(opt)
     model.setup(opt)
@@ -181,15 +183,18 @@ def main():
         model.set_input(batch)
         model.optimize_parameters()
 
-    for i in range(W):
+    launches_per_step = None
+    for i in range(W_eff):
+        l_before = ops.Stats.launches
         step(resident[i % pool])
+        if i == 1:   # an eager step (graph mode captures after 3 of them): the kernels one step launches
+            launches_per_step = ops.Stats.launches - l_before
     barrier()
 
     # ---- timed region 1: device-resident inputs -> `value`
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ops.Stats.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -200,7 +205,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = (ops.Stats.launches - l0) / K
+    launches = float(launches_per_step)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D of the batch + D2H of the losses)
@@ -225,9 +230,11 @@ def main():
     if rank == 0:
         ops.Stats.igemm_events = []
         nprof = 2
+        was_graph, model.use_graph = model.use_graph, False     # per-launch events need the launches to come from Python
         for i in range(nprof):
             step(resident[i % pool])
         torch.cuda.synchronize()
+        model.use_graph = was_graph
         ev = ops.Stats.igemm_events
         ops.Stats.igemm_events = None
         if args.dump_igemm:
@@ -257,11 +264,13 @@ def main():
                 "config": {"workload": "wsgan_emb optimize_parameters, 128x128, ResNet-9 G + 3-layer PatchGAN D + ResNet-18 Elo E@224, lambda_IP 0 (BASELINE configs[2])",
                            "batch_per_gpu": B, "global_batch": world * B, "size": S, "parallelism": "dp%d" % world,
                            "l2": "4 distinct input batches; ~5 GB of activations per step >> 126 MB L2, no flush needed",
+                           "launch": "CUDA graph replay of the captured step" if model.use_graph else "per-kernel launches from Python",
                            "flops_per_image": GFLOP_PER_IMAGE * 1e9},
                 "clocks": clocks,
                 "e2e": {"value": img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 2 * B * 3 * S * S * 4, "d2h_bytes_per_step": 9 * 4,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(round(launches * K)), "gpu_launches_per_step": launches, "host_enqueue_ms_per_step": host_ms,
+                "cuda_graph": bool(model.use_graph),
                 "roofline": roof, "last_losses": last}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(S)

@@ -563,10 +563,19 @@ class GANLoss(nn.Module):
         super().__init__()
         self.kind = L.LOSS_MSE if use_lsgan else L.LOSS_BCE
         self.Tensor = tensor
+        self._const = {}
 
     def get_target_tensor(self, input, target_label):
+        """One target value per sample (networks.py:395-405).  bool / int: a cached device constant; list: uploaded;
+        a float device tensor (already per sample) is used as is, so a captured step needs no host-to-device copy."""
+        if isinstance(target_label, torch.Tensor):
+            return target_label.to(device=input.device, dtype=torch.float32).reshape(-1).contiguous()
         if not isinstance(target_label, list):
-            target_label = [target_label]
+            key = (float(int(target_label)), input.size(0), input.device)
+            t = self._const.get(key)
+            if t is None:
+                t = self._const[key] = torch.full((input.size(0),), key[0], device=input.device)
+            return t
         vals = [float(int(t)) for t in target_label]
         return torch.tensor(np.array(vals, dtype=np.float32), device=input.device)
 

@@ -42,7 +42,8 @@ def default_options(**overrides):
         lambda_L1=0.0, lambda_IP=0.0, lambda_z=1.0, lambda_A=0.5, lambda_A_GAN=0.0, lr_E=0.0, use_real_A=False,
         relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False,
         no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5, lr_policy="lambda", niter=50, niter_decay=50, epoch_count=1,
-        lr_decay_iters=50, continue_train=False, which_epoch="latest", load_model_names=[], verbose=False)
+        lr_decay_iters=50, continue_train=False, which_epoch="latest", load_model_names=[], verbose=False,
+        cuda_graph=False, cuda_graph_warmup=3)
     for k, v in overrides.items():
         setattr(opt, k, v)
     return opt
@@ -161,14 +162,25 @@ class WSGANEmbModel(BaseModel):
             self.criterionL1 = networks.l1_loss
             self.criterionRec = networks.mse_loss
             self.criterionCycle = networks.l1_loss
-            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
-            self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
+            # --cuda_graph: the whole optimize_parameters() (about 950 kernel launches) is captured once and replayed, so
+            # the step costs one graph launch of host time.  Adam then keeps lr / step on the device (capturable).
+            self.use_graph = bool(getattr(opt, "cuda_graph", False))
+            self._graphs, self._eager_steps, self._side = {}, 0, None
+            adam_kw = dict(betas=(opt.beta1, 0.999))
+            if self.use_graph:
+                adam_kw.update(capturable=True, foreach=True)
+            lr = torch.tensor(float(opt.lr), device=self.device) if self.use_graph else opt.lr
+            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=lr, **adam_kw)
+            lr = torch.tensor(float(opt.lr), device=self.device) if self.use_graph else opt.lr
+            self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=lr, **adam_kw)
             self.optimizers = [self.optimizer_G, self.optimizer_D]
             self.set_requires_grad(self.netE, False)   # wsgan_emb_model.py:164-165 (E stays in train mode: SURVEY A.1)
             # one process per GPU: flat gradient buffers, averaged over ranks with one NCCL all-reduce per network
             self.sync_G = GradSync(list(self.netG.parameters()))
             self.sync_D = GradSync(list(self.netD.parameters()))
             self.relabel_D = opt.relabel_D
+            self._relabel_lut = torch.tensor([float(v) for v in opt.relabel_D], device=self.device)
+            self._static = {}
             if len(opt.weight_label_D) > 0:
                 assert len(opt.weight_label_D) == len(opt.relabel_D)
                 self.weight_label_D = [w / sum(opt.weight_label_D) for w in opt.weight_label_D]
@@ -178,20 +190,37 @@ class WSGANEmbModel(BaseModel):
         self.transform_E = networks.Normalize((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))
 
     # ------------------------------------------------------------------ data
+    def _stage(self, name, src):
+        """Copy a batch tensor into a persistent device buffer (one per name and shape): the captured step reads fixed
+        addresses, and the eager step simply uses the same buffers."""
+        src = torch.as_tensor(src)
+        key = (name, tuple(src.shape), src.dtype)
+        buf = self._static.get(key)
+        if buf is None:
+            buf = self._static[key] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+        buf.copy_(src, non_blocking=True)
+        return buf
+
     def set_input(self, input):
-        """wsgan_emb_model.py:193-212."""
+        """wsgan_emb_model.py:193-212.  The pair labels stay on the host in the reference (:199) and are turned into
+        discriminator targets with a Python list comprehension (:324); here they are uploaded once with the images so
+        that the step itself issues no host-to-device copy."""
         if self.isTrain:
             if not self.opt.no_mixed_label_D:
-                self.real_A = input["A"].to(self.device, non_blocking=True)
-                self.real_B = input["B"].to(self.device, non_blocking=True)
+                self.real_A = self._stage("A", input["A"])
+                self.real_B = self._stage("B", input["B"])
                 self.image_paths = input.get("B_paths", [])
                 self.label_AB = input["label"]
             else:
                 self.label_AB = [np.random.choice(range(len(self.relabel_D)), p=self.weight_label_D)]
                 k = str(self.label_AB[0])
-                self.real_A = input[k + "_A"].to(self.device, non_blocking=True)
-                self.real_B = input[k + "_B"].to(self.device, non_blocking=True)
+                self.real_A = self._stage("A", input[k + "_A"])
+                self.real_B = self._stage("B", input[k + "_B"])
                 self.image_paths = input.get(k + "_B_paths", [])
+            lab = torch.as_tensor(self.label_AB).to(torch.int64).reshape(-1)
+            if lab.numel() == 1 and self.real_A.size(0) > 1:
+                lab = lab.expand(self.real_A.size(0)).contiguous()
+            self._label_dev = self._stage("label", lab)
         else:
             self.real_A = input["A"].to(self.device)
             self.image_paths = input.get("A_paths", [])
@@ -232,7 +261,7 @@ class WSGANEmbModel(BaseModel):
         img = self.real_A if opt.use_real_A else self.real_B
         emb_right, emb_wrong = (self.embedding_A, self.embedding_B) if opt.use_real_A else (self.embedding_B, self.embedding_A)
         self.loss_D_real_right = self.criterionGAN(self.netD(img, emb_right), True)
-        target_label = [self.relabel_D[int(l)] for l in self.label_AB]
+        target_label = self._relabel_lut[self._label_dev]      # [relabel_D[l] for l in label_AB] (:324), on the device
         self.loss_D_real_wrong = self.criterionGAN(self.netD(img, emb_wrong), target_label)
         self.loss_D = (self.loss_D_fake + (self.loss_D_real_right + self.loss_D_real_wrong) * 0.5) * 0.5
         self.loss_D.backward()
@@ -270,11 +299,39 @@ class WSGANEmbModel(BaseModel):
         self.sync_G.all_reduce()
         self.optimizer_G.step()
 
-    def optimize_parameters(self):
-        """wsgan_emb_model.py:478-484."""
+    def _step(self):
         self.forward()
         self.update_G()
         self.update_D()
+
+    def optimize_parameters(self):
+        """wsgan_emb_model.py:478-484.  With --cuda_graph the step is captured after a few eager steps (plans built,
+        workspaces pooled, Adam state allocated) and replayed from then on; one graph per batch shape."""
+        if not self.use_graph:
+            return self._step()
+        key = (tuple(self.real_A.shape), tuple(self.real_B.shape))
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+            return
+        # Eager warm-up and capture run on one side stream: autograd ties every parameter's gradient accumulator to the
+        # stream of its first use, and a capture may only depend on work of the capturing stream.
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        if self._eager_steps < int(getattr(self.opt, "cuda_graph_warmup", 3)):
+            self._eager_steps += 1
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._step()
+            cur.wait_stream(self._side)
+            return
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._side):
+            self._step()
+        self._graphs[key] = g
+        g.replay()      # the capture itself executes nothing: run the step that was asked for
 
     def get_current_visuals(self):
         return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str) and hasattr(self, n))
