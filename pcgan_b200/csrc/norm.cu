@@ -6,6 +6,8 @@
 // so all index arithmetic is 32-bit (one division per vector), the per-channel constants of a thread are loaded
 // once (256 % (C/8) == 0: a thread always sees the same 8 channels), and each thread keeps kU independent
 // 16-byte loads in flight.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pcgan {
@@ -62,18 +64,116 @@ __global__ void __launch_bounds__(kT) norm_finalize_kernel(pcgan_norm_finalize_a
   }
 }
 
+// ------------------------------------------------------------- stream pipeline
+// The three hot kernels (norm_apply, norm_bwd_reduce, norm_bwd_apply) stream their inputs through shared memory
+// with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx): a producer warp keeps kStages segments of every
+// input stream in flight per block, independent of registers, which is what an HBM-bound kernel on B200 needs
+// (~45 KB in flight per SM at full bandwidth).  A segment = seg_px consecutive pixels of one image row
+// (<= 8 KB per stream); 8 consumer warps process it (thread = 16-byte vector, fixed 8 channels) and hand the stage
+// back through an "empty" mbarrier.
+static constexpr int kConsumers = 256;                    // consumer threads
+static constexpr int kStreamThreads = kConsumers + 32;    // + producer warp
+static constexpr int kStages = 4;
+static constexpr int kSegBytes = 8192;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct SegGeom {
+  int32_t seg_px, segs_per_row, seg_vec;   // pixels and 16-byte vectors per segment
+};
+
+// One input stream: element offset of interior pixel (y, x) of sample n is base + ((y + pad) * wp + x + pad) * c
+struct StreamSrc {
+  const __nv_bfloat16* base;   // sample base (already offset by n)
+  int32_t pad, wp;
+};
+
+template <int NT>
+struct Pipe {
+  uint64_t* full;    // [kStages]
+  uint64_t* empty;   // [kStages]
+  uint8_t* data;     // [kStages][NT][kSegBytes]
+  __device__ __forceinline__ const uint4* stage(int s, int t) const {
+    return reinterpret_cast<const uint4*>(data + (static_cast<size_t>(s) * NT + t) * kSegBytes);
+  }
+};
+
+template <int NT>
+__device__ __forceinline__ Pipe<NT> pipe_init(uint8_t* smem) {
+  Pipe<NT> p;
+  p.data = smem;
+  p.full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kStages) * NT * kSegBytes);
+  p.empty = p.full + kStages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&p.full[i], 1);
+      mbar_init(&p.empty[i], kConsumers / 32);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  return p;
+}
+
+// producer: lane 0 of the last warp; segments [g0, g1) of one sample
+template <int NT>
+__device__ __forceinline__ void pipe_produce(const Pipe<NT>& p, const SegGeom& sg, const StreamSrc (&src)[NT], int32_t c, int32_t g0,
+                                             int32_t g1) {
+  const uint32_t bytes = static_cast<uint32_t>(sg.seg_vec) * 16u;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int32_t g = g0; g < g1; ++g) {
+    const int32_t y = g / sg.segs_per_row;
+    const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
+    mbar_wait(&p.empty[s], ph ^ 1);
+    mbar_arrive_expect_tx(&p.full[s], bytes * NT);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const __nv_bfloat16* gsrc = src[t].base + (static_cast<int64_t>(y + src[t].pad) * src[t].wp + x0 + src[t].pad) * c;
+      bulk_load(const_cast<uint4*>(p.stage(s, t)), gsrc, bytes, &p.full[s]);
+    }
+    if (++s == kStages) { s = 0; ph ^= 1; }
+  }
+}
+
+// consumer side of one segment: wait, run body(stage index), release
+#define PIPE_CONSUME_BEGIN(p, s, ph) mbar_wait(&(p).full[s], ph)
+#define PIPE_CONSUME_END(p, s, ph)                           \
+  do {                                                       \
+    __syncwarp();                                            \
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&(p).empty[s]); \
+    if (++s == kStages) { s = 0; ph ^= 1; }                  \
+  } while (0)
+
 // ----------------------------------------------------------------- norm apply
-// y = act(sc*x + sh [+ rsc*res + rsh]) over the whole padded grid of y (interior + halo).
+// y = act(sc*x + sh [+ rsc*res + rsh]) into the interior of y; under reflect halo every interior pixel within `pad`
+// of a border is also stored at its mirror positions (a zero halo is never written: the buffer is allocated zeroed
+// and only interiors are ever stored).
 template <bool RES>
-__global__ void __launch_bounds__(kT, 3) norm_apply_kernel(pcgan_norm_apply_args a, int rows_per_block, int lcv) {
-  constexpr int kU = RES ? 2 : 4;
+__global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_apply_args a, SegGeom sg, int segs_per_block, int lcv) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NT = RES ? 2 : 1;
+  Pipe<NT> pipe = pipe_init<NT>(smem_raw);
   const int n = blockIdx.y;
+  const int32_t total_segs = a.h * sg.segs_per_row;
+  const int32_t g0 = blockIdx.x * segs_per_block, g1 = min(g0 + segs_per_block, total_segs);
   const int cv = a.c >> 3;
-  const int hp = a.h + 2 * a.y_pad, wp = a.w + 2 * a.y_pad;
-  const int rowvec = wp * cv;
-  const int row0 = blockIdx.x * rows_per_block;
-  const int nrows = min(rows_per_block, hp - row0);
-  const int total = nrows * rowvec;
+  StreamSrc src[NT];
+  src[0].pad = a.x_pad; src[0].wp = a.w + 2 * a.x_pad;
+  src[0].base = reinterpret_cast<const __nv_bfloat16*>(a.x) + static_cast<int64_t>(n) * (a.h + 2 * a.x_pad) * src[0].wp * a.c;
+  if constexpr (RES) {
+    src[1].pad = a.res_pad; src[1].wp = a.w + 2 * a.res_pad;
+    src[1].base = reinterpret_cast<const __nv_bfloat16*>(a.res) + static_cast<int64_t>(n) * (a.h + 2 * a.res_pad) * src[1].wp * a.c;
+  }
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
+    return;
+  }
   const int c0 = (threadIdx.x & (cv - 1)) << 3;
   float sc[8], sh[8], rsc[RES ? 8 : 1], rsh[RES ? 8 : 1];
 #pragma unroll
@@ -91,7 +191,6 @@ __global__ void __launch_bounds__(kT, 3) norm_apply_kernel(pcgan_norm_apply_args
 #pragma unroll
     for (int j = 0; j < 8; ++j) sc[j] *= m[j];
   }
-  constexpr bool has_res = RES;
   if constexpr (RES) {
     if (a.res_scale) {
       const int64_t ro = static_cast<int64_t>(a.res_groups > 1 ? n : 0) * a.c + c0;
@@ -99,71 +198,70 @@ __global__ void __launch_bounds__(kT, 3) norm_apply_kernel(pcgan_norm_apply_args
       load_f8(a.res_shift + ro, rsh);
     }
   }
-  const int wxp = a.w + 2 * a.x_pad, wrp = a.w + 2 * a.res_pad;
-  const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(a.x) +
-                            static_cast<int64_t>(n) * (a.h + 2 * a.x_pad) * wxp * a.c + c0;
-  const __nv_bfloat16* rs = has_res ? reinterpret_cast<const __nv_bfloat16*>(a.res) +
-                                          static_cast<int64_t>(n) * (a.h + 2 * a.res_pad) * wrp * a.c + c0
-                                    : nullptr;
-  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + (static_cast<int64_t>(n) * hp + row0) * wp * a.c;
-  const bool zero_halo = a.y_halo == PCGAN_HALO_ZERO;
-
-  for (int v0 = threadIdx.x; v0 < total; v0 += kT * kU) {
-    uint4 xv[kU], rv[RES ? kU : 1];
-    int st[kU];   // 0: out of range, 1: zero halo, 2: value
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int v = v0 + u * kT;
-      st[u] = 0;
-      if (v < total) {
-        const int r = v / rowvec;
-        const int px = (v - r * rowvec) >> lcv;
-        int y = row0 + r - a.y_pad, x = px - a.y_pad;
-        const bool halo = y < 0 || y >= a.h || x < 0 || x >= a.w;
-        if (halo && zero_halo) {
-          st[u] = 1;
-        } else {
-          st[u] = 2;
-          y = reflect_idx(y, a.h);
-          x = reflect_idx(x, a.w);
-          xv[u] = ldg16(xs + ((y + a.x_pad) * wxp + x + a.x_pad) * a.c);
-          if constexpr (RES) rv[u] = ldg16(rs + ((y + a.res_pad) * wrp + x + a.res_pad) * a.c);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      if (st[u] == 0) continue;
-      __nv_bfloat16* d = ys + static_cast<int64_t>(v0 + u * kT) * 8;
-      if (st[u] == 1) {
-        *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-        continue;
-      }
+  const int p = a.y_pad, wp = a.w + 2 * p;
+  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + static_cast<int64_t>(n) * (a.h + 2 * p) * wp * a.c + c0;
+  const bool reflect = a.y_halo == PCGAN_HALO_REFLECT && p > 0;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int32_t g = g0; g < g1; ++g) {
+    const int32_t y = g / sg.segs_per_row;
+    const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
+    // padded rows this image row is stored to: itself and (reflect) its mirrors
+    const int ya = y + p;
+    const int yb = (reflect && y >= 1 && y <= p) ? p - y : -1;
+    const int yc = (reflect && y <= a.h - 2 && y >= a.h - 1 - p) ? p + 2 * (a.h - 1) - y : -1;
+    PIPE_CONSUME_BEGIN(pipe, s, ph);
+    const uint4* sx = pipe.stage(s, 0);
+    const uint4* sr = RES ? pipe.stage(s, 1) : nullptr;
+    for (int v = threadIdx.x; v < sg.seg_vec; v += kConsumers) {
       float x8[8], o[8];
-      unpack8(xv[u], x8);
+      unpack8(sx[v], x8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], x8[j], sh[j]);
       if constexpr (RES) {
         float r8[8];
-        unpack8(rv[u], r8);
+        unpack8(sr[v], r8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += fmaf(rsc[j], r8[j], rsh[j]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = apply_act(o[j], a.act, a.act_slope);
-      store8(d, o);
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      const int x = x0 + (v >> lcv);
+      const int xa = x + p;
+      *reinterpret_cast<uint4*>(ys + (ya * wp + xa) * a.c) = w;
+      if (reflect) {
+        const int xb = (x >= 1 && x <= p) ? p - x : -1;
+        const int xc = (x <= a.w - 2 && x >= a.w - 1 - p) ? p + 2 * (a.w - 1) - x : -1;
+        if ((yb & yc & xb & xc) != -1) {
+#pragma unroll
+          for (int iy = 0; iy < 3; ++iy) {
+            const int yy = iy == 0 ? ya : (iy == 1 ? yb : yc);
+            if (yy < 0) continue;
+#pragma unroll
+            for (int ix = 0; ix < 3; ++ix) {
+              const int xx = ix == 0 ? xa : (ix == 1 ? xb : xc);
+              if (xx < 0 || (iy == 0 && ix == 0)) continue;
+              *reinterpret_cast<uint4*>(ys + (yy * wp + xx) * a.c) = w;
+            }
+          }
+        }
+      }
     }
+    PIPE_CONSUME_END(pipe, s, ph);
   }
 }
 
 // ------------------------------------------------------------------ halo fold
 // 16-byte vector of the gradient at interior pixel (y, x) of a padded-grid gradient, halo folded onto its mirror
-// (a pixel within p of a border also receives the halo rows / columns that ReflectionPad2d copied from it)
+// (a pixel within p of a border also receives the halo rows / columns that ReflectionPad2d copied from it).
+// `have_center`: acc already holds the pixel's own value (streamed), only the mirrors are added.
 __device__ __forceinline__ void folded_load(const __nv_bfloat16* g, int y, int x, int h, int w, int p, int c, bool reflect,
-                                            float (&acc)[8]) {
+                                            float (&acc)[8], bool have_center = false) {
   const int wp = w + 2 * p;
   const int ya = y + p, xa = x + p;
-  unpack8(ldg16(g + (ya * wp + xa) * c), acc);
+  if (!have_center) unpack8(ldg16(g + (ya * wp + xa) * c), acc);
   if (!reflect) return;
   const int yb = (y >= 1 && y <= p) ? p - y : -1;
   const int yc = (y <= h - 2 && y >= h - 1 - p) ? p + 2 * (h - 1) - y : -1;
@@ -237,13 +335,13 @@ __global__ void __launch_bounds__(kT) halo_fold_kernel(pcgan_fold_args a, int ve
 // residual not needed for the activation mask): scale == rstd and shift == -mean*rstd, so the normalised value xhat IS
 // the pre-activation sc*x + sh.  GEN = true carries mean / rstd / mask separately (BatchNorm with gamma, beta);
 // RES adds the residual branch to the pre-activation (ResNet BasicBlock: relu(bn(x) + shortcut)).
+// Streams: 0 = dy, 1 = x, 2 = residual (RES).
 template <bool GEN, bool RES>
 struct BwdCtx {
   float sc[8], sh[8];                               // pre = sc*(x*mask) + sh (+ residual)
   float mean[GEN ? 8 : 1], rstd[GEN ? 8 : 1], mk[GEN ? 8 : 1];
   float rsc[RES ? 8 : 1], rsh[RES ? 8 : 1];
-  const __nv_bfloat16* dy; const __nv_bfloat16* x; const __nv_bfloat16* res;
-  int wdp, wxp, wrp;
+  const __nv_bfloat16* dyg;                         // sample base of dy (+c0) for the mirror loads of a folded gradient
   int fold;                                         // 0 plain, 2 reflect fold
 
   __device__ __forceinline__ void init(const pcgan_norm_bwd_args& a, int n, int c0) {
@@ -259,31 +357,22 @@ struct BwdCtx {
       if (a.mean) { load_f8(a.mean + so, mean); load_f8(a.rstd + so, rstd); }
       if (a.drop_mask) load_f8(a.drop_mask + static_cast<int64_t>(n) * a.c + c0, mk);
     }
-    wdp = a.w + 2 * a.dy_pad; wxp = a.w + 2 * a.x_pad; wrp = a.w + 2 * a.res_pad;
-    dy = reinterpret_cast<const __nv_bfloat16*>(a.dy) + static_cast<int64_t>(n) * (a.h + 2 * a.dy_pad) * wdp * a.c + c0;
-    x = reinterpret_cast<const __nv_bfloat16*>(a.x) + static_cast<int64_t>(n) * (a.h + 2 * a.x_pad) * wxp * a.c + c0;
-    res = nullptr;
     if constexpr (RES) {
-      res = reinterpret_cast<const __nv_bfloat16*>(a.res) + static_cast<int64_t>(n) * (a.h + 2 * a.res_pad) * wrp * a.c + c0;
       if (a.res_scale) {
         const int64_t ro = static_cast<int64_t>(a.res_groups > 1 ? n : 0) * a.c + c0;
         load_f8(a.res_scale + ro, rsc);
         load_f8(a.res_shift + ro, rsh);
       }
     }
+    dyg = reinterpret_cast<const __nv_bfloat16*>(a.dy) + static_cast<int64_t>(n) * (a.h + 2 * a.dy_pad) * (a.w + 2 * a.dy_pad) * a.c + c0;
     fold = a.dy_fold;
   }
 
-  __device__ __forceinline__ void load(const pcgan_norm_bwd_args& a, int y, int xx, float (&dyv)[8], uint4& xraw, uint4& rraw) const {
-    if (fold) folded_load(dy, y, xx, a.h, a.w, a.dy_pad, a.c, fold == 2, dyv);
-    else unpack8(ldg16(dy + ((y + a.dy_pad) * wdp + xx + a.dy_pad) * a.c), dyv);
-    xraw = ldg16(x + ((y + a.x_pad) * wxp + xx + a.x_pad) * a.c);
-    if constexpr (RES) rraw = ldg16(res + ((y + a.res_pad) * wrp + xx + a.res_pad) * a.c);
-  }
-
-  // g = dy * act'(pre) (in place in dyv) and xhat
-  __device__ __forceinline__ void grad(const pcgan_norm_bwd_args& a, float (&dyv)[8], const uint4 xraw, const uint4 rraw,
-                                       float (&xh)[8]) const {
+  // g = dy * act'(pre) (returned in dyv) and xhat, from the streamed vectors
+  __device__ __forceinline__ void grad(const pcgan_norm_bwd_args& a, int y, int x, const uint4 dyraw, const uint4 xraw,
+                                       const uint4 rraw, float (&dyv)[8], float (&xh)[8]) const {
+    unpack8(dyraw, dyv);
+    if (fold == 2) folded_load(dyg, y, x, a.h, a.w, a.dy_pad, a.c, true, dyv, true);
     float x8[8], pre[8];
     unpack8(xraw, x8);
 #pragma unroll
@@ -313,64 +402,91 @@ struct BwdCtx {
   }
 };
 
-template <bool GEN, bool RES>
-__global__ void __launch_bounds__(kT, GEN ? 2 : 3) norm_bwd_reduce_kernel(pcgan_norm_bwd_args a, int vec_per_block, int lcv) {
-  __shared__ float red[kT * 16];
-  const int n = blockIdx.y;
-  const int cv = a.c >> 3;
-  const int total = a.h * a.w * cv;
-  const int vb = blockIdx.x * vec_per_block, ve = min(vb + vec_per_block, total);
-  const int c0 = (threadIdx.x & (cv - 1)) << 3;
-  BwdCtx<GEN, RES> k;
-  k.init(a, n, c0);
-  float s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  for (int v0 = vb + threadIdx.x; v0 < ve; v0 += kT * 2) {
-    float g[2][8];
-    uint4 xr[2], rr[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int v = v0 + u * kT;
-      if (v < ve) {
-        const int pix = v >> lcv;
-        const int y = pix / a.w;
-        k.load(a, y, pix - y * a.w, g[u], xr[u], rr[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (v0 + u * kT < ve) {
-        float xh[8];
-        k.grad(a, g[u], xr[u], rr[u], xh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += g[u][j]; s2[j] = fmaf(g[u][j], xh[j], s2[j]); }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
-  __syncthreads();
-  const int lanes = kT / cv;
-  for (int t = threadIdx.x; t < cv * 16; t += kT) {
-    const int c = t >> 4, slot = t & 15;
-    float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red[(l * cv + c) * 16 + slot];
-    const int ch = (c << 3) + (slot & 7);
-    const int64_t o = (static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + ch) * 2 + (slot >> 3);
-    atomicAdd(a.sums + o, s);
+template <bool RES>
+__device__ __forceinline__ void bwd_sources(const pcgan_norm_bwd_args& a, int n, StreamSrc (&src)[RES ? 3 : 2]) {
+  src[0].pad = a.dy_pad; src[0].wp = a.w + 2 * a.dy_pad;
+  src[0].base = reinterpret_cast<const __nv_bfloat16*>(a.dy) + static_cast<int64_t>(n) * (a.h + 2 * a.dy_pad) * src[0].wp * a.c;
+  src[1].pad = a.x_pad; src[1].wp = a.w + 2 * a.x_pad;
+  src[1].base = reinterpret_cast<const __nv_bfloat16*>(a.x) + static_cast<int64_t>(n) * (a.h + 2 * a.x_pad) * src[1].wp * a.c;
+  if constexpr (RES) {
+    src[2].pad = a.res_pad; src[2].wp = a.w + 2 * a.res_pad;
+    src[2].base = reinterpret_cast<const __nv_bfloat16*>(a.res) + static_cast<int64_t>(n) * (a.h + 2 * a.res_pad) * src[2].wp * a.c;
   }
 }
 
 template <bool GEN, bool RES>
-__global__ void __launch_bounds__(kT, GEN ? 2 : 3) norm_bwd_apply_kernel(pcgan_norm_bwd_args a, int vec_per_block, int lcv) {
+__global__ void __launch_bounds__(kStreamThreads) norm_bwd_reduce_kernel(pcgan_norm_bwd_args a, SegGeom sg, int segs_per_block, int lcv) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NT = RES ? 3 : 2;
+  Pipe<NT> pipe = pipe_init<NT>(smem_raw);
+  const int n = blockIdx.y;
+  const int32_t total_segs = a.h * sg.segs_per_row;
+  const int32_t g0 = blockIdx.x * segs_per_block, g1 = min(g0 + segs_per_block, total_segs);
+  const int cv = a.c >> 3;
+  StreamSrc src[NT];
+  bwd_sources<RES>(a, n, src);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
+  } else {
+    const int c0 = (threadIdx.x & (cv - 1)) << 3;
+    BwdCtx<GEN, RES> k;
+    k.init(a, n, c0);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int32_t g = g0; g < g1; ++g) {
+      const int32_t y = g / sg.segs_per_row;
+      const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
+      PIPE_CONSUME_BEGIN(pipe, s, ph);
+      const uint4* sd = pipe.stage(s, 0);
+      const uint4* sx = pipe.stage(s, 1);
+      const uint4* sr = RES ? pipe.stage(s, 2) : sx;
+      for (int v = threadIdx.x; v < sg.seg_vec; v += kConsumers) {
+        float gv[8], xh[8];
+        k.grad(a, y, x0 + (v >> lcv), sd[v], sx[v], sr[v], gv, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += gv[j]; s2[j] = fmaf(gv[j], xh[j], s2[j]); }
+      }
+      PIPE_CONSUME_END(pipe, s, ph);
+    }
+    // all segments consumed: the ring is free, reuse its first 16 KB for the block reduction
+    named_bar_sync(1, kConsumers);
+    float* red = reinterpret_cast<float*>(smem_raw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+    named_bar_sync(1, kConsumers);
+    const int lanes = kConsumers / cv;
+    for (int t = threadIdx.x; t < cv * 16; t += kConsumers) {
+      const int c = t >> 4, slot = t & 15;
+      float sum = 0.f;
+      for (int l = 0; l < lanes; ++l) sum += red[(l * cv + c) * 16 + slot];
+      const int ch = (c << 3) + (slot & 7);
+      const int64_t o = (static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + ch) * 2 + (slot >> 3);
+      atomicAdd(a.sums + o, sum);
+    }
+  }
+}
+
+template <bool GEN, bool RES>
+__global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_norm_bwd_args a, SegGeom sg, int segs_per_block, int lcv) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NT = RES ? 3 : 2;
+  Pipe<NT> pipe = pipe_init<NT>(smem_raw);
   // blocks walk the samples (and chunks) in the opposite order to the reduce pass: what that pass read last is
   // still in L2 when this one starts
   const int n = gridDim.y - 1 - blockIdx.y;
   const int bx = gridDim.x - 1 - blockIdx.x;
+  const int32_t total_segs = a.h * sg.segs_per_row;
+  const int32_t g0 = bx * segs_per_block, g1 = min(g0 + segs_per_block, total_segs);
   const int cv = a.c >> 3;
-  const int total = a.h * a.w * cv;
-  const int vb = bx * vec_per_block, ve = min(vb + vec_per_block, total);
+  StreamSrc src[NT];
+  bwd_sources<RES>(a, n, src);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
+    return;
+  }
   const int c0 = (threadIdx.x & (cv - 1)) << 3;
   BwdCtx<GEN, RES> k;
   k.init(a, n, c0);
@@ -393,39 +509,33 @@ __global__ void __launch_bounds__(kT, GEN ? 2 : 3) norm_bwd_apply_kernel(pcgan_n
   const int wop = a.w + 2 * a.dx_pad, wsp = a.w + 2 * a.dres_pad;
   __nv_bfloat16* dx = a.dx ? reinterpret_cast<__nv_bfloat16*>(a.dx) + static_cast<int64_t>(n) * (a.h + 2 * a.dx_pad) * wop * a.c + c0 : nullptr;
   __nv_bfloat16* dres = a.dres ? reinterpret_cast<__nv_bfloat16*>(a.dres) + static_cast<int64_t>(n) * (a.h + 2 * a.dres_pad) * wsp * a.c + c0 : nullptr;
-  for (int v0 = vb + threadIdx.x; v0 < ve; v0 += kT * 2) {
-    float g[2][8];
-    uint4 xr[2], rr[2];
-    int yy[2], xx[2];
+  int s = 0;
+  uint32_t ph = 0;
+  for (int32_t g = g0; g < g1; ++g) {
+    const int32_t y = g / sg.segs_per_row;
+    const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
+    PIPE_CONSUME_BEGIN(pipe, s, ph);
+    const uint4* sd = pipe.stage(s, 0);
+    const uint4* sx = pipe.stage(s, 1);
+    const uint4* sr = RES ? pipe.stage(s, 2) : sx;
+    for (int v = threadIdx.x; v < sg.seg_vec; v += kConsumers) {
+      float gv[8], xh[8];
+      const int x = x0 + (v >> lcv);
+      k.grad(a, y, x, sd[v], sx[v], sr[v], gv, xh);
+      if (dres) store8(dres + ((y + a.dres_pad) * wsp + x + a.dres_pad) * a.c, gv);
+      if (dx) {
+        float o[8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int v = v0 + u * kT;
-      if (v < ve) {
-        const int pix = v >> lcv;
-        yy[u] = pix / a.w;
-        xx[u] = pix - yy[u] * a.w;
-        k.load(a, yy[u], xx[u], g[u], xr[u], rr[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (v0 + u * kT < ve) {
-        float xh[8];
-        k.grad(a, g[u], xr[u], rr[u], xh);
-        if (dres) store8(dres + ((yy[u] + a.dres_pad) * wsp + xx[u] + a.dres_pad) * a.c, g[u]);
-        if (dx) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = g[u][j] - A[j] - xh[j] * B[j];
-            if (scaled) t *= k.sc[j];
-            if constexpr (GEN) t *= k.mk[j];
-            o[j] = t;
-          }
-          store8(dx + ((yy[u] + a.dx_pad) * wop + xx[u] + a.dx_pad) * a.c, o);
+        for (int j = 0; j < 8; ++j) {
+          float t = gv[j] - A[j] - xh[j] * B[j];
+          if (scaled) t *= k.sc[j];
+          if constexpr (GEN) t *= k.mk[j];
+          o[j] = t;
         }
+        store8(dx + ((y + a.dx_pad) * wop + x + a.dx_pad) * a.c, o);
       }
     }
+    PIPE_CONSUME_END(pipe, s, ph);
   }
 }
 
@@ -455,6 +565,55 @@ static int chunking(int64_t vec_per_sample, int n, int unit, int* per_block) {
   return static_cast<int>((vec_per_sample + per - 1) / per);
 }
 
+// Segments of the stream pipeline: the largest divisor of the row width whose bytes fit one stage.
+static SegGeom seg_geom(int w, int c) {
+  SegGeom sg;
+  int best = 1;
+  for (int d = 1; d <= w; ++d)
+    if (w % d == 0 && static_cast<int64_t>(d) * c * 2 <= kSegBytes) best = d;
+  sg.seg_px = best;
+  sg.segs_per_row = w / best;
+  sg.seg_vec = best * (c / 8);
+  return sg;
+}
+// segments per block: about two waves of blocks at `blocks_per_sm` resident blocks, at least one ring of segments each
+static int seg_chunking(int total_segs, int n, int blocks_per_sm, int* segs_per_block) {
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const int64_t want_blocks = static_cast<int64_t>(sms) * blocks_per_sm * 2;
+  int64_t chunks = (want_blocks + n - 1) / n;
+  int64_t per = (total_segs + chunks - 1) / chunks;
+  if (per < 2 * kStages) per = 2 * kStages;
+  if (per > total_segs) per = total_segs;
+  *segs_per_block = static_cast<int>(per);
+  return static_cast<int>((total_segs + per - 1) / per);
+}
+template <int NT>
+static constexpr size_t pipe_smem() { return static_cast<size_t>(kStages) * NT * kSegBytes + 2 * kStages * sizeof(uint64_t); }
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", name, cudaGetErrorString(e));
+  return PCGAN_OK;
+}
+// one-time opt-in to > 48 KB of dynamic shared memory for every instantiation
+static int norm_kernels_ready() {
+  static std::once_flag once;
+  static int rc = PCGAN_OK;
+  std::call_once(once, []() {
+    int r;
+    if ((r = set_smem(norm_apply_kernel<false>, pipe_smem<1>(), "norm_apply<0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<true>, pipe_smem<2>(), "norm_apply<1>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_reduce_kernel<false, false>, pipe_smem<2>(), "norm_bwd_reduce<0,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_reduce_kernel<true, false>, pipe_smem<2>(), "norm_bwd_reduce<1,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_reduce_kernel<true, true>, pipe_smem<3>(), "norm_bwd_reduce<1,1>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_apply_kernel<false, false>, pipe_smem<2>(), "norm_bwd_apply<0,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_apply_kernel<true, false>, pipe_smem<2>(), "norm_bwd_apply<1,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_apply_kernel<true, true>, pipe_smem<3>(), "norm_bwd_apply<1,1>"))) { rc = r; return; }
+  });
+  return rc;
+}
+
 }  // namespace pcgan
 
 using namespace pcgan;
@@ -472,17 +631,17 @@ extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s
   int lcv, rc = check_c(a->c, "norm_apply", &lcv);
   if (rc) return rc;
   if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(PCGAN_ERR_INVALID, "norm_apply: scale and shift go together");
-  if (a->y_halo == PCGAN_HALO_REFLECT && (a->y_pad >= a->h || a->y_pad >= a->w)) return fail(PCGAN_ERR_INVALID, "norm_apply: reflect pad too large");
+  if (a->y_halo == PCGAN_HALO_REFLECT && (2 * a->y_pad + 1 > a->h || 2 * a->y_pad + 1 > a->w)) return fail(PCGAN_ERR_INVALID, "norm_apply: image smaller than 2*pad+1 under reflect halo");
   if (a->n < 1 || a->n > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: n=%d (1..65535)", a->n);
-  const int hp = a->h + 2 * a->y_pad, wp = a->w + 2 * a->y_pad;
-  const int64_t rowvec = static_cast<int64_t>(wp) * (a->c / 8);
-  if (rowvec * hp >= (1ll << 28)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: sample too large");
+  const int mp = a->y_pad > a->x_pad ? (a->y_pad > a->res_pad ? a->y_pad : a->res_pad) : (a->x_pad > a->res_pad ? a->x_pad : a->res_pad);
+  if (static_cast<int64_t>(a->h + 2 * mp) * (a->w + 2 * mp) * a->c >= (1ll << 31)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: sample too large");
+  if ((rc = norm_kernels_ready())) return rc;
+  const SegGeom sg = seg_geom(a->w, a->c);
   int per;
-  chunking(rowvec * hp, a->n, static_cast<int>(rowvec), &per);
-  const int rows = per / static_cast<int>(rowvec);
-  const dim3 grid((hp + rows - 1) / rows, a->n);
-  if (a->res) norm_apply_kernel<true><<<grid, kT, 0, STREAM(s)>>>(*a, rows, lcv);
-  else norm_apply_kernel<false><<<grid, kT, 0, STREAM(s)>>>(*a, rows, lcv);
+  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, a->res ? 3 : 6, &per);
+  const dim3 grid(chunks, a->n);
+  if (a->res) norm_apply_kernel<true><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
+  else norm_apply_kernel<false><<<grid, kStreamThreads, pipe_smem<1>(), STREAM(s)>>>(*a, sg, per, lcv);
   PCGAN_LAUNCH_OK("norm_apply_kernel");
   return PCGAN_OK;
 }
@@ -511,23 +670,26 @@ static int check_bwd(const pcgan_norm_bwd_args* a, int* lcv) {
   if (a->n < 1 || a->n > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd: n=%d (1..65535)", a->n);
   if (a->dy_fold < 0 || a->dy_fold > 2) return fail(PCGAN_ERR_INVALID, "norm_bwd: dy_fold must be 0 (plain), 1 (zero halo dropped) or 2 (reflect fold)");
   if (a->dy_fold == 2 && (2 * a->dy_pad + 1 > a->h || 2 * a->dy_pad + 1 > a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd: image smaller than 2*pad+1");
-  const int mp = a->dy_pad > a->x_pad ? a->dy_pad : a->x_pad;
+  int mp = a->dy_pad > a->x_pad ? a->dy_pad : a->x_pad;
+  if (a->res_pad > mp) mp = a->res_pad;
+  if (a->dx_pad > mp) mp = a->dx_pad;
   if (static_cast<int64_t>(a->h + 2 * mp) * (a->w + 2 * mp) * a->c >= (1ll << 31)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd: sample too large");
-  return PCGAN_OK;
+  return norm_kernels_ready();
 }
 
 extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_t s) {
   int lcv, rc = check_bwd(a, &lcv);
   if (rc) return rc;
   if (!a->sums) return fail(PCGAN_ERR_INVALID, "norm_bwd_reduce: sums is null");
-  int per;
-  const int chunks = chunking(static_cast<int64_t>(a->h) * a->w * (a->c / 8), a->n, kT, &per);
-  const dim3 grid(chunks, a->n);
   const bool res = a->res != nullptr && a->act != PCGAN_ACT_NONE;   // the residual only matters through the activation mask
   const bool gen = a->affine != 0 || a->drop_mask != nullptr || res;
-  if (!gen) norm_bwd_reduce_kernel<false, false><<<grid, kT, 0, STREAM(s)>>>(*a, per, lcv);
-  else if (!res) norm_bwd_reduce_kernel<true, false><<<grid, kT, 0, STREAM(s)>>>(*a, per, lcv);
-  else norm_bwd_reduce_kernel<true, true><<<grid, kT, 0, STREAM(s)>>>(*a, per, lcv);
+  const SegGeom sg = seg_geom(a->w, a->c);
+  int per;
+  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
+  const dim3 grid(chunks, a->n);
+  if (!gen) norm_bwd_reduce_kernel<false, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
+  else if (!res) norm_bwd_reduce_kernel<true, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
+  else norm_bwd_reduce_kernel<true, true><<<grid, kStreamThreads, pipe_smem<3>(), STREAM(s)>>>(*a, sg, per, lcv);
   PCGAN_LAUNCH_OK("norm_bwd_reduce_kernel");
   return PCGAN_OK;
 }
@@ -536,14 +698,15 @@ extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t
   int lcv, rc = check_bwd(a, &lcv);
   if (rc) return rc;
   if (!a->dx && !a->dres) return fail(PCGAN_ERR_INVALID, "norm_bwd_apply: no output");
-  int per;
-  const int chunks = chunking(static_cast<int64_t>(a->h) * a->w * (a->c / 8), a->n, kT, &per);
-  const dim3 grid(chunks, a->n);
   const bool res = a->res != nullptr && a->act != PCGAN_ACT_NONE;
   const bool gen = a->affine != 0 || a->drop_mask != nullptr || res;
-  if (!gen) norm_bwd_apply_kernel<false, false><<<grid, kT, 0, STREAM(s)>>>(*a, per, lcv);
-  else if (!res) norm_bwd_apply_kernel<true, false><<<grid, kT, 0, STREAM(s)>>>(*a, per, lcv);
-  else norm_bwd_apply_kernel<true, true><<<grid, kT, 0, STREAM(s)>>>(*a, per, lcv);
+  const SegGeom sg = seg_geom(a->w, a->c);
+  int per;
+  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
+  const dim3 grid(chunks, a->n);
+  if (!gen) norm_bwd_apply_kernel<false, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
+  else if (!res) norm_bwd_apply_kernel<true, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
+  else norm_bwd_apply_kernel<true, true><<<grid, kStreamThreads, pipe_smem<3>(), STREAM(s)>>>(*a, sg, per, lcv);
   PCGAN_LAUNCH_OK("norm_bwd_apply_kernel");
   return PCGAN_OK;
 }
