@@ -398,99 +398,107 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int32_t stage = 0;
-      uint32_t phase = 0;
-      for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
-        if (!wgrad) {
-          const int32_t mt = tile / P.n_tiles, nt = tile % P.n_tiles;
-          const Digits d = decompose(mt, P.t_count);
-          int32_t c[4];
+    // The whole warp walks the (uniform) schedule; one elected lane issues the copies.
+    int32_t stage = 0;
+    uint32_t phase = 0;
+    for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
+      if (!wgrad) {
+        const int32_t mt = tile / P.n_tiles, nt = tile % P.n_tiles;
+        const Digits d = decompose(mt, P.t_count);
+        int32_t c[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
-          const uint32_t bytes = P.a_rows * 128 + P.block_n * 128;
-          for (int32_t tap = 0; tap < P.num_taps; ++tap) {
-            const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
-                          o3 = P.tap_off[tap][3];
-            const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
-            for (int32_t cc = 0; cc < P.cchunks; ++cc) {
-              uint8_t* sa = smem + stage * P.stage_bytes;
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+        for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
+        const uint32_t bytes = P.a_rows * 128 + P.block_n * 128;
+        for (int32_t tap = 0; tap < P.num_taps; ++tap) {
+          const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
+                        o3 = P.tap_off[tap][3];
+          const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
+          for (int32_t cc = 0; cc < P.cchunks; ++cc) {
+            uint8_t* sa = smem + stage * P.stage_bytes;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full_bar[stage], bytes);
               tma_load_5d(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
               tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
-              if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
-        } else {
-          int32_t t = tile;
-          const int32_t ks = t % P.ksplit; t /= P.ksplit;
-          const int32_t nt = t % P.n_tiles; t /= P.n_tiles;
-          const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
-          const int32_t tap = t;
-          const int32_t kb0 = ks * kb_per_split;
-          const int32_t kb1 = min(kb0 + kb_per_split, total_kb);
-          const int32_t nb = P.block_n >> 6;
-          const uint32_t bytes = (2 + nb) * kBoxBytesMN;
-          const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2], o3 = P.tap_off[tap][3];
-          const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
-          for (int32_t kb = kb0; kb < kb1; ++kb) {
-            const Digits d = decompose(kb, P.t_count);
-            uint8_t* sa = smem + stage * P.stage_bytes;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+        }
+      } else {
+        int32_t t = tile;
+        const int32_t ks = t % P.ksplit; t /= P.ksplit;
+        const int32_t nt = t % P.n_tiles; t /= P.n_tiles;
+        const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
+        const int32_t tap = t;
+        const int32_t kb0 = ks * kb_per_split;
+        const int32_t kb1 = min(kb0 + kb_per_split, total_kb);
+        const int32_t nb = P.block_n >> 6;
+        const uint32_t bytes = (2 + nb) * kBoxBytesMN;
+        const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2], o3 = P.tap_off[tap][3];
+        const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
+        for (int32_t kb = kb0; kb < kb1; ++kb) {
+          const Digits d = decompose(kb, P.t_count);
+          uint8_t* sa = smem + stage * P.stage_bytes;
+          const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
+                        a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
+          const int32_t b0 = coord(d, P.b_base, P.b_step, 0) + o0, b1 = coord(d, P.b_base, P.b_step, 1) + o1,
+                        b2 = coord(d, P.b_base, P.b_step, 2) + o2, b3 = coord(d, P.b_base, P.b_step, 3) + o3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
-                          a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
-            const int32_t b0 = coord(d, P.b_base, P.b_step, 0) + o0, b1 = coord(d, P.b_base, P.b_step, 1) + o1,
-                          b2 = coord(d, P.b_base, P.b_step, 2) + o2, b3 = coord(d, P.b_base, P.b_step, 3) + o3;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
             for (int j = 0; j < nb; ++j)
               tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3);
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
-      // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the swizzled row.
-      // MN-major: 64-element column groups one box (8192 B) apart, 8 K-rows = 1024 B; UMMA_K = 16 rows = 2048 B.
-      const uint32_t lbo = wgrad ? kBoxBytesMN : 16;
-      const uint32_t sbo = 1024;
-      const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
-      int32_t stage = 0;
-      uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
-        int32_t nk;
-        if (!wgrad) {
-          nk = k_chunks_fwd;
-        } else {
-          const int32_t ks = tile % P.ksplit;
-          const int32_t kb0 = ks * kb_per_split;
-          nk = max(min(kb0 + kb_per_split, total_kb) - kb0, 0);
-        }
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // Converged warp, one elected lane issues tcgen05.mma / commit (always the same lane, so the commits track its MMAs).
+    const uint32_t idesc = make_idesc_bf16(128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
+    // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the swizzled row.
+    // MN-major: 64-element column groups one box (8192 B) apart, 8 K-rows = 1024 B; UMMA_K = 16 rows = 2048 B.
+    const uint32_t lbo = wgrad ? kBoxBytesMN : 16;
+    const uint32_t sbo = 1024;
+    const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
+    int32_t stage = 0;
+    uint32_t phase = 0, acc = 0, acc_phase = 0;
+    for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
+      int32_t nk;
+      if (!wgrad) {
+        nk = k_chunks_fwd;
+      } else {
+        const int32_t ks = tile % P.ksplit;
+        const int32_t kb0 = ks * kb_per_split;
+        nk = max(min(kb0 + kb_per_split, total_kb) - kb0, 0);
+      }
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kAccCols;
+      for (int32_t kc = 0; kc < nk; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * kAccCols;
-        for (int32_t kc = 0; kc < nk; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
-          const uint64_t da = make_smem_desc(sa, lbo, sbo);
-          const uint64_t db = make_smem_desc(sa + P.a_alloc, lbo, sbo);
+        const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
+        const uint64_t da = make_smem_desc(sa, lbo, sbo);
+        const uint64_t db = make_smem_desc(sa + P.a_alloc, lbo, sbo);
+        if (elect_one_sync()) {
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k)
             umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
           tcgen05_commit(&empty_bar[stage]);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) tcgen05_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue

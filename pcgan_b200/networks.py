@@ -225,9 +225,10 @@ class _GenProgram:
             _norm_backward(dfull, 1, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1, dy_fold=2)
             if need_w:
                 ca.backward_weight(dya, ws.b[i])
-            ca.backward_data(dya, dfull)
+            dfull2 = sc.get(self.g_bfull, "dfull2")
+            ca.backward_data(dya, dfull2)
             gprev = sc.get(self.g_r3, "gb%d" % ((nblk - i) % 2))
-            ops.halo_fold(dfull, self.g_b, gprev, 0, halo=L.HALO_REFLECT, add=gb, add_pad=0)
+            ops.halo_fold(dfull2, self.g_b, gprev, 0, halo=L.HALO_REFLECT, add=gb, add_pad=0)
             gb = gprev
         # down2 unit (its output buffer ws.b[0])
         dy = sc.get(self.g_r3, "dy3")

@@ -130,9 +130,10 @@ def test_generator_backward_chain_teacher_forced():
     y.backward(dyb)
     check("block.conv2.fwd", inner(ws.rb[0], P.g_r3), y, T_ACT, log)
     check("block.conv2.wgrad", grad(p + ".5.weight"), w.grad, T_LIN, log)
+    check("block.conv2.dgrad(padded grid)", full(sc.get(P.g_bfull, "dfull"), P.g_bfull), x.grad, T_LIN, log)
     xi = torch.zeros(N, 256, S // 4, S // 4, device=DEV, requires_grad=True)
-    F.pad(xi, (1,) * 4, mode="reflect").backward(bf(x.grad))
-    gh = xi.grad.detach()     # fold fused into block.norm1's backward (dy_fold=2)
+    F.pad(xi, (1,) * 4, mode="reflect").backward(full(sc.get(P.g_bfull, "dfull"), P.g_bfull))
+    gh = xi.grad.detach()     # the fold of the kernels' own padded-grid gradient: fused into block.norm1's backward (dy_fold=2)
     norm_stage("block.norm1", inner(ws.ra[0], P.g_r3), gh, inner(ws.h[0], P.g_b), inner(sc.get(P.g_b, "dya"), P.g_b))
     dya = inner(sc.get(P.g_b, "dya"), P.g_b)
     x = full(ws.b[0], P.g_b).clone().requires_grad_(True)
