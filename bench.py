@@ -138,6 +138,9 @@ def cpu_baseline(size, seconds_budget=25.0):
 
 def main():
     args = parse()
+    # a stuck collective or capture must not hang the caller: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -225,16 +228,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    # ---- roofline pass (rank 0): every igemm launch bracketed by CUDA events on its stream
+    # ---- roofline pass: every igemm launch of rank 0 bracketed by CUDA events on its stream.  All ranks run the steps
+    # (they contain the gradient all-reduces); only rank 0 records.
     roof = None
+    nprof = 2
     if rank == 0:
         ops.Stats.igemm_events = []
-        nprof = 2
-        was_graph, model.use_graph = model.use_graph, False     # per-launch events need the launches to come from Python
-        for i in range(nprof):
-            step(resident[i % pool])
-        torch.cuda.synchronize()
-        model.use_graph = was_graph
+    was_graph, model.use_graph = model.use_graph, False     # per-launch events need the launches to come from Python
+    for i in range(nprof):
+        step(resident[i % pool])
+    barrier()
+    model.use_graph = was_graph
+    if rank == 0:
         ev = ops.Stats.igemm_events
         ops.Stats.igemm_events = None
         if args.dump_igemm:

@@ -43,7 +43,7 @@ def default_options(**overrides):
         relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False,
         no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5, lr_policy="lambda", niter=50, niter_decay=50, epoch_count=1,
         lr_decay_iters=50, continue_train=False, which_epoch="latest", load_model_names=[], verbose=False,
-        cuda_graph=False, cuda_graph_warmup=3)
+        cuda_graph=False, cuda_graph_warmup=3, cuda_graph_segments=None)
     for k, v in overrides.items():
         setattr(opt, k, v)
     return opt
@@ -304,15 +304,43 @@ class WSGANEmbModel(BaseModel):
         self.update_G()
         self.update_D()
 
+    # The step as three collective-free segments (multi-GPU graph mode): the two gradient all-reduces run between
+    # them as ordinary NCCL calls, so no collective is ever part of a captured graph.
+    def _seg_forward_backward_G(self):
+        self.forward()
+        self.set_requires_grad(self.netD, False)
+        self.sync_G.zero()
+        self.backward_G()
+
+    def _seg_step_G_backward_D(self):
+        self.optimizer_G.step()
+        self.set_requires_grad(self.netD, True)
+        self.sync_D.zero()
+        self.backward_D()
+
+    def _seg_step_D(self):
+        self.optimizer_D.step()
+
+    def _run_segments(self, segs):
+        segs[0]()
+        self.sync_G.all_reduce()
+        segs[1]()
+        self.sync_D.all_reduce()
+        segs[2]()
+
     def optimize_parameters(self):
         """wsgan_emb_model.py:478-484.  With --cuda_graph the step is captured after a few eager steps (plans built,
-        workspaces pooled, Adam state allocated) and replayed from then on; one graph per batch shape."""
+        workspaces pooled, Adam state allocated) and replayed from then on; one capture per batch shape.  On one GPU
+        the whole step is one graph; with several ranks it is three graphs with the NCCL all-reduces between them."""
         if not self.use_graph:
             return self._step()
         key = (tuple(self.real_A.shape), tuple(self.real_B.shape))
         g = self._graphs.get(key)
         if g is not None:
-            g.replay()
+            if isinstance(g, list):
+                self._run_segments([x.replay for x in g])
+            else:
+                g.replay()
             return
         # Eager warm-up and capture run on one side stream: autograd ties every parameter's gradient accumulator to the
         # stream of its first use, and a capture may only depend on work of the capturing stream.
@@ -327,11 +355,32 @@ class WSGANEmbModel(BaseModel):
             cur.wait_stream(self._side)
             return
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self._side):
-            self._step()
-        self._graphs[key] = g
-        g.replay()      # the capture itself executes nothing: run the step that was asked for
+        segmented = getattr(self.opt, "cuda_graph_segments", None)
+        if segmented is None:
+            segmented = self.sync_G.world_size() > 1
+        if not segmented:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._side):
+                self._step()
+            self._graphs[key] = g
+            g.replay()      # the capture itself executes nothing: run the step that was asked for
+            return
+        # several ranks: capture each segment, then run it (the next segment's capture needs its side effects in place:
+        # the all-reduced gradients, the updated weights), sharing one memory pool so tensors live across segments
+        graphs, pool = [], None
+        fns = (self._seg_forward_backward_G, self._seg_step_G_backward_D, self._seg_step_D)
+        for i, fn in enumerate(fns):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._side, pool=pool):
+                fn()
+            pool = g.pool()
+            g.replay()
+            if i == 0:
+                self.sync_G.all_reduce()
+            elif i == 1:
+                self.sync_D.all_reduce()
+            graphs.append(g)
+        self._graphs[key] = graphs
 
     def get_current_visuals(self):
         return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str) and hasattr(self, n))
