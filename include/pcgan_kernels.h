@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 5
+#define PCGAN_ABI_VERSION 6
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -48,7 +48,7 @@ typedef enum { PCGAN_DT_BF16 = 0, PCGAN_DT_F32 = 1 } pcgan_dtype;
 typedef enum { PCGAN_HALO_ZERO = 0, PCGAN_HALO_REFLECT = 1 } pcgan_halo;
 typedef enum { PCGAN_IGEMM_KMAJOR = 0, PCGAN_IGEMM_WGRAD = 1 } pcgan_igemm_kind;
 typedef enum { PCGAN_STATS_NONE = 0, PCGAN_STATS_ON = 1 } pcgan_stats_mode;
-typedef enum { PCGAN_LOSS_BCE = 0, PCGAN_LOSS_MSE = 1, PCGAN_LOSS_L1 = 2, PCGAN_LOSS_ELO_NLL = 3 } pcgan_loss_kind;
+typedef enum { PCGAN_LOSS_BCE = 0, PCGAN_LOSS_MSE = 1, PCGAN_LOSS_L1 = 2, PCGAN_LOSS_ELO_NLL = 3, PCGAN_LOSS_ELO_NLL_SCORE = 4 } pcgan_loss_kind;
 
 int pcgan_abi_version(void);
 const char* pcgan_last_error(void);
@@ -208,6 +208,10 @@ typedef struct {
   const float* gamma; const float* beta;
   float* mean; float* rstd; float* scale; float* shift;
   float* running_mean; float* running_var;
+  /* Channel dropout in front of a BatchNorm (nn.Dropout2d before bn, resnet.py:58-65): the convolution emits
+   * per-sample statistics stats[in_groups = N][c][2]; with drop_mask[N][c] (0 or 1/(1-p)) the batch statistics of the
+   * masked tensor are sum_n m*S1 and sum_n m*m*S2.  in_groups == 0: stats has `groups` groups (no combination). */
+  const float* drop_mask; int32_t in_groups;
 } pcgan_norm_finalize_args;
 int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stream_t stream);
 
@@ -225,6 +229,8 @@ typedef struct {
   const float* res_scale; const float* res_shift; int32_t res_groups;
   const float* drop_mask;
   int32_t act; float act_slope;
+  const float* post_mask; /* optional [N][C]: multiplies the activation's output (nn.Dropout2d between BatchNorm and
+                             LeakyReLU, networks.py:1021-1023: lrelu(m*v) == m*lrelu(v) for m >= 0) */
 } pcgan_norm_apply_args;
 int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t stream);
 
@@ -261,6 +267,7 @@ typedef struct {
   int32_t dy_fold;                      /* 0: dy is read at its interior; 2: dy is the gradient of a reflect-padded
                                            buffer (pad dy_pad) whose halo is folded onto the mirror pixels while
                                            reading (nn.ReflectionPad2d backward fused into this pass); 1: halo dropped */
+  const float* post_mask;               /* optional [N][C]: the forward multiplied the activation output by it */
   int32_t affine;                       /* 0: scale == rstd and shift == -mean*rstd exactly (no gamma / beta), so
                                            xhat is the pre-activation itself (InstanceNorm2d(affine=False)); 1: general */
 } pcgan_norm_bwd_args;
@@ -285,6 +292,8 @@ int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint8_t* idx, v
  *   BCE     mean(-(t*max(log p,-100) + (1-t)*max(log(1-p),-100)))
  *   MSE     mean((p-t)^2)          L1  mean(|p-t|)
  *   ELO_NLL mean(-(t*log(p+1e-20) + (1-t)*log(1-p+1e-20)))
+ *   ELO_NLL_SCORE the same with p = sigmoid(input): the input is the rating difference (siamese.py:674-676), the
+ *           gradient is taken with respect to it
  * target: either a full tensor t[n] (per_sample = 0) or one value per sample
  * t[n / per_sample].  loss is atomically accumulated (*loss += weight*mean).
  * grad (optional) = weight * dmean/dp, same shape as p. */

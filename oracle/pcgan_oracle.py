@@ -358,7 +358,16 @@ class WSGANEmbOracle:
 
     def __init__(self, sd_g, sd_d, sd_e, *, lr=2e-4, beta1=0.5, lambda_z=1.0, lambda_a=0.5, lambda_l1=0.0,
                  lambda_a_gan=0.0, fine_size_e=224, relabel_d=(0, 1, 0), emb_mean=0.0, emb_std=1.0, n_blocks=9,
-                 n_layers_d=3, detach_fake_b=False):
+                 n_layers_d=3, detach_fake_b=False, bayesian=False, noisy=False, noisy_var_type="", bnn_T=10,
+                 noisy_d=True, noisy_rec=True, dropout=False, drop_masks=None, eps_queue=None):
+        """bayesian / noisy / noisy_var_type / bnn_T / noisy_D / noisy_rec: the encoder modes of forward() (:218-240)
+        and backward_G (:408-430).  Randomness is injected, never drawn: `drop_masks` is a list of Dropout2d masks
+        [N, C] consumed in module order (dropout=True places them where the reference has nn.Dropout2d), `eps_queue`
+        the standard-normal draws of util.resample (util/util.py:136-139) in call order."""
+        self.bayesian, self.noisy, self.nvt, self.T = bayesian, noisy, noisy_var_type, bnn_T
+        self.noisy_d, self.noisy_rec, self.dropout = noisy_d, noisy_rec, dropout
+        self.drop_masks = drop_masks if drop_masks is not None else []
+        self.eps_queue = eps_queue if eps_queue is not None else []
         self.g, self.d, self.e = sd_g, sd_d, sd_e
         self.pg = [t for t in sd_g.values() if t.requires_grad]
         self.pd = [t for t in sd_d.values() if t.requires_grad]
@@ -371,18 +380,62 @@ class WSGANEmbOracle:
         self.nb, self.nld, self.detach_fake_b = n_blocks, n_layers_d, detach_fake_b
         self.losses = {}
 
+    def _drop(self, t):
+        m = self.drop_masks.pop(0).to(t.device, t.dtype)
+        return t * m.view(t.size(0), t.size(1), 1, 1)
+
     def _E(self, x):
-        return encoder_forward(self.e, x)
+        return encoder_forward(self.e, x, noisy=self.noisy, drop=self._drop if self.dropout else None)
+
+    def _mu_var(self, x):
+        """util.compute_mu_and_var (util/util.py:153-171)"""
+        y_mu, y_sq, s2_mu = 0.0, 0.0, 0.0
+        for _ in range(self.T):
+            out = self._E(x)
+            y, logs2 = out if self.noisy else (out, None)
+            y_mu = y_mu + 1.0 / self.T * y
+            y_sq = y_sq + 1.0 / self.T * y ** 2
+            if self.noisy:
+                s2_mu = s2_mu + 1.0 / self.T * torch.exp(logs2)
+        return (y_mu, y_sq - y_mu ** 2, s2_mu) if self.noisy else (y_mu, y_sq - y_mu ** 2)
+
+    def _encode(self, x):
+        """(y, resampling variance or None): the four branches of forward() (:218-240)"""
+        var = None
+        if not self.bayesian and not self.noisy:
+            y = self._E(x)
+        elif not self.bayesian and self.noisy:
+            y, logvar = self._E(x)
+            if "a" in self.nvt:
+                var = torch.exp(logvar)
+        elif self.bayesian and not self.noisy:
+            y, y_var = self._mu_var(x)
+            if "e" in self.nvt:
+                var = y_var
+        else:
+            y, y_var, y_s2 = self._mu_var(x)
+            if "a" in self.nvt:
+                var = y_s2 + y_var
+        return y, var
+
+    def _resample(self, mu, var):
+        eps = self.eps_queue.pop(0).to(mu.device, mu.dtype)
+        return mu + eps.view_as(mu) * torch.sqrt(var)
 
     def _norm(self, y):
         return (y - self.mean) / self.std
 
     def forward(self, real_a, real_b):
-        """WSGANEmbModel.forward (:214-259), branch `not bayesian and not noisy`, lr_E <= 0."""
+        """WSGANEmbModel.forward (:214-259), lr_E <= 0."""
         with torch.no_grad():
-            self.y_a = self._E(upsample2d(real_a, self.fe))
-            self.y_b = self._E(upsample2d(real_b, self.fe))
+            self.real_a_e = upsample2d(real_a, self.fe)
+            self.y_a, var_a = self._encode(self.real_a_e)
+            self.y_b, var_b = self._encode(upsample2d(real_b, self.fe))
+            if var_a is not None:
+                self.res_a = self._norm(self._resample(self.y_a, var_a))
+                self.res_b = self._norm(self._resample(self.y_b, var_b))
         self.emb_a, self.emb_b = self._norm(self.y_a), self._norm(self.y_b)
+        self.cond_b = self.res_b if (self.nvt and self.noisy_d) else self.emb_b
         self.real_a, self.real_b = real_a, real_b
         self.fake_b = generator_forward(self.g, real_a, self.emb_b, self.nb)
         src = self.fake_b.detach() if self.detach_fake_b else self.fake_b
@@ -394,7 +447,7 @@ class WSGANEmbOracle:
             t.requires_grad_(False)   # set_requires_grad(netD, False) (:458)
         self.opt_g.zero_grad()
         L = {}
-        pred = discriminator_forward(self.d, self.fake_b, self.emb_b, self.nld)
+        pred = discriminator_forward(self.d, self.fake_b, self.cond_b, self.nld)
         L["G_GAN"] = gan_loss(pred, True)
         total = L["G_GAN"]
         if self.lag > 0:
@@ -407,8 +460,30 @@ class WSGANEmbOracle:
             L["G_cycle"] = F.l1_loss(self.rec_a, self.real_a) * self.la
             total = total + L["G_cycle"]
         if self.lz > 0:
-            pred_y = self._E(upsample2d(self.fake_b, self.fe))
-            L["z_rec"] = F.mse_loss(pred_y, self.y_b) * self.lz
+            fake_e = upsample2d(self.fake_b, self.fe)
+            y_var = y_logvar = None
+            if not self.bayesian and not self.noisy:
+                pred_y = self._E(fake_e)
+            elif not self.bayesian and self.noisy:
+                pred_y, y_logvar = self._E(fake_e)
+                if "a" in self.nvt:
+                    y_var = torch.exp(y_logvar)
+            elif self.bayesian and not self.noisy:
+                pred_y, y_var = self._mu_var(fake_e)
+                if "e" in self.nvt:
+                    y_logvar = torch.log(y_var + MAGIC_EPS)
+            else:   # (:418-425) the reference feeds real_A_E here
+                pred_y, y_var_, y_s2_ = self._mu_var(self.real_a_e)
+                y_var = torch.zeros_like(pred_y)
+                if "a" in self.nvt:
+                    y_var = y_var + y_s2_
+                if "e" in self.nvt:
+                    y_var = y_var + y_var_
+                y_logvar = torch.log(y_var + MAGIC_EPS)
+            if self.nvt and self.noisy_rec:
+                L["z_rec"] = ((pred_y - self.y_b).pow(2) / y_var.detach() + y_logvar.detach()).sum() / pred_y.size(0) * 0.5 * self.lz
+            else:
+                L["z_rec"] = F.mse_loss(pred_y, self.y_b) * self.lz
             total = total + L["z_rec"]
         total.backward()
         self.opt_g.step()
@@ -420,7 +495,7 @@ class WSGANEmbOracle:
         """WSGANEmbModel.backward_D (:300-329)."""
         self.opt_d.zero_grad()
         L = {}
-        L["D_fake"] = gan_loss(discriminator_forward(self.d, self.fake_b.detach(), self.emb_b, self.nld), False)
+        L["D_fake"] = gan_loss(discriminator_forward(self.d, self.fake_b.detach(), self.cond_b, self.nld), False)
         L["D_real_right"] = gan_loss(discriminator_forward(self.d, self.real_b, self.emb_b, self.nld), True)
         target = [self.relabel[int(l)] for l in label]
         L["D_real_wrong"] = gan_loss(discriminator_forward(self.d, self.real_b, self.emb_a, self.nld), target)
@@ -436,6 +511,27 @@ class WSGANEmbOracle:
         L.update(self.backward_d(label))
         self.losses = {k: float(v) for k, v in L.items()}
         return self.losses
+
+
+class SiameseOracle:
+    """The Elo rating trainer's step (siamese.py:590-686, plain branch :673-678) on SiameseNetwork(resnet18, cnn_dim=[32, 1],
+    fc_dim=[]) (networks.py:971-992): two encoder passes with separate BatchNorm batches, score = f1 - f2, sigmoid,
+    BinaryNLLLoss, Adam(lr) over every parameter (siamese.py:544-551)."""
+
+    def __init__(self, sd, lr=2e-4, cnn_relu_slope=0.7):
+        self.sd, self.slope = sd, cnn_relu_slope
+        self.params = [t for t in sd.values() if t.requires_grad]
+        self.opt = torch.optim.Adam(self.params, lr=lr)
+
+    def step(self, img0, img1, label):
+        self.opt.zero_grad()
+        f1 = encoder_forward(self.sd, img0, cnn_relu_slope=self.slope)
+        f2 = encoder_forward(self.sd, img1, cnn_relu_slope=self.slope)
+        prob = torch.sigmoid(f1 - f2)
+        loss = elo_nll(prob, label)
+        loss.backward()
+        self.opt.step()
+        return float(loss), prob.detach()
 
 
 def synthetic_batch(batch, size, seed, device="cpu"):

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -20,7 +20,7 @@ DT_BF16, DT_F32 = 0, 1
 HALO_ZERO, HALO_REFLECT = 0, 1
 IGEMM_KMAJOR, IGEMM_WGRAD = 0, 1
 STATS_NONE, STATS_ON = 0, 1
-LOSS_BCE, LOSS_MSE, LOSS_L1, LOSS_ELO_NLL = 0, 1, 2, 3
+LOSS_BCE, LOSS_MSE, LOSS_L1, LOSS_ELO_NLL, LOSS_ELO_NLL_SCORE = 0, 1, 2, 3, 4
 
 i32, i64, u32, u64, f32, vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_void_p
 
@@ -64,7 +64,7 @@ class UnpackArgs(C.Structure):
 class NormFinalizeArgs(C.Structure):
     _fields_ = [("stats", vp), ("groups", i32), ("c", i32), ("count", f32), ("eps", f32), ("momentum", f32),
                 ("gamma", vp), ("beta", vp), ("mean", vp), ("rstd", vp), ("scale", vp), ("shift", vp),
-                ("running_mean", vp), ("running_var", vp)]
+                ("running_mean", vp), ("running_var", vp), ("drop_mask", vp), ("in_groups", i32)]
 
 
 class NormApplyArgs(C.Structure):
@@ -72,7 +72,7 @@ class NormApplyArgs(C.Structure):
                 ("n", i32), ("h", i32), ("w", i32), ("c", i32),
                 ("scale", vp), ("shift", vp), ("groups", i32),
                 ("res_scale", vp), ("res_shift", vp), ("res_groups", i32),
-                ("drop_mask", vp), ("act", i32), ("act_slope", f32)]
+                ("drop_mask", vp), ("act", i32), ("act_slope", f32), ("post_mask", vp)]
 
 
 class FoldArgs(C.Structure):
@@ -85,7 +85,7 @@ class NormBwdArgs(C.Structure):
                 ("mean", vp), ("rstd", vp), ("scale", vp), ("shift", vp), ("groups", i32),
                 ("res_scale", vp), ("res_shift", vp), ("res_groups", i32), ("drop_mask", vp),
                 ("act", i32), ("act_slope", f32), ("n", i32), ("h", i32), ("w", i32), ("c", i32),
-                ("count", f32), ("sums", vp), ("dx", vp), ("dx_pad", i32), ("dres", vp), ("dres_pad", i32), ("dy_fold", i32), ("affine", i32)]
+                ("count", f32), ("sums", vp), ("dx", vp), ("dx_pad", i32), ("dres", vp), ("dres_pad", i32), ("dy_fold", i32), ("post_mask", vp), ("affine", i32)]
 
 
 class MaxpoolArgs(C.Structure):

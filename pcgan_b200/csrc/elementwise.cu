@@ -280,6 +280,13 @@ __global__ void loss_kernel(pcgan_loss_args a) {
       }
       case PCGAN_LOSS_MSE: l = (p - t) * (p - t); g = 2.f * (p - t); break;
       case PCGAN_LOSS_L1: l = fabsf(p - t); g = p > t ? 1.f : (p < t ? -1.f : 0.f); break;
+      case PCGAN_LOSS_ELO_NLL_SCORE: {  // p is the rating difference: prob = sigmoid(p) (siamese.py:675), then as below
+        const float e = 1e-20f;
+        const float pr = 1.f / (1.f + expf(-p));
+        l = -(t * logf(pr + e) + (1.f - t) * logf(1.f - pr + e));
+        g = -(t / (pr + e) - (1.f - t) / (1.f - pr + e)) * pr * (1.f - pr);
+        break;
+      }
       default: {  // PCGAN_LOSS_ELO_NLL, networks.py:479-481 with MAGIC_EPS = 1e-20
         const float e = 1e-20f;
         l = -(t * logf(p + e) + (1.f - t) * logf(1.f - p + e));
@@ -405,7 +412,7 @@ extern "C" int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint
 
 extern "C" int pcgan_loss(const pcgan_loss_args* a, pcgan_stream_t s) {
   if (!a || !a->p || !a->target || a->n < 1) return fail(PCGAN_ERR_INVALID, "loss: bad argument");
-  if (a->kind < PCGAN_LOSS_BCE || a->kind > PCGAN_LOSS_ELO_NLL) return fail(PCGAN_ERR_INVALID, "loss: bad kind");
+  if (a->kind < PCGAN_LOSS_BCE || a->kind > PCGAN_LOSS_ELO_NLL_SCORE) return fail(PCGAN_ERR_INVALID, "loss: bad kind");
   loss_kernel<<<grid_for(a->n, kThreads, 2), kThreads, 0, STREAM(s)>>>(*a);
   PCGAN_LAUNCH_OK("loss_kernel");
   return PCGAN_OK;

@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(kT) norm_finalize_kernel(pcgan_norm_finalize_a
   __shared__ float sm[8][33], sv[8][33];
   const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  const bool combine = a.in_groups > a.groups;   // per-sample statistics folded into one batch statistic (groups == 1)
   float macc = 0.f, vacc = 0.f;
-  if (c < a.c) {
+  if (c < a.c && !combine) {
     const float gam = a.gamma ? a.gamma[c] : 1.f;
     const float bet = a.beta ? a.beta[c] : 0.f;
     for (int g = gl; g < a.groups; g += 8) {
@@ -49,18 +50,43 @@ __global__ void __launch_bounds__(kT) norm_finalize_kernel(pcgan_norm_finalize_a
       vacc += var;
     }
   }
+  if (c < a.c && combine) {
+    for (int g = gl; g < a.in_groups; g += 8) {
+      const int64_t o = static_cast<int64_t>(g) * a.c + c;
+      const float2 s = reinterpret_cast<const float2*>(a.stats)[o];
+      const float m = a.drop_mask ? a.drop_mask[o] : 1.f;
+      macc += m * s.x;        // here: partial sums, not means
+      vacc += m * m * s.y;
+    }
+  }
   sm[gl][cl] = macc;
   sv[gl][cl] = vacc;
   __syncthreads();
-  if (gl == 0 && c < a.c && (a.running_mean || a.running_var)) {
-    float m = 0.f, v = 0.f;
+  if (gl != 0 || c >= a.c) return;
+  float m = 0.f, v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { m += sm[i][cl]; v += sv[i][cl]; }
-    if (a.running_mean) a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (m / a.groups);
-    if (a.running_var) {
-      const float unbias = a.count > 1.f ? a.count / (a.count - 1.f) : 1.f;
-      a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (v / a.groups * unbias);
-    }
+  for (int i = 0; i < 8; ++i) { m += sm[i][cl]; v += sv[i][cl]; }
+  if (combine) {
+    const float gam = a.gamma ? a.gamma[c] : 1.f;
+    const float bet = a.beta ? a.beta[c] : 0.f;
+    const float mean = m / a.count;
+    float var = v / a.count - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    const float rstd = rsqrtf(var + a.eps);
+    if (a.mean) a.mean[c] = mean;
+    if (a.rstd) a.rstd[c] = rstd;
+    if (a.scale) a.scale[c] = gam * rstd;
+    if (a.shift) a.shift[c] = bet - mean * gam * rstd;
+    m = mean;
+    v = var;
+  } else {
+    m /= a.groups;
+    v /= a.groups;
+  }
+  if (a.running_mean) a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * m;
+  if (a.running_var) {
+    const float unbias = a.count > 1.f ? a.count / (a.count - 1.f) : 1.f;
+    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (v * unbias);
   }
 }
 
@@ -198,6 +224,11 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
       load_f8(a.res_shift + ro, rsh);
     }
   }
+  float pm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pm[j] = 1.f;
+  const bool has_pm = a.post_mask != nullptr;
+  if (has_pm) load_f8(a.post_mask + static_cast<int64_t>(n) * a.c + c0, pm);
   const int p = a.y_pad, wp = a.w + 2 * p;
   __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + static_cast<int64_t>(n) * (a.h + 2 * p) * wp * a.c + c0;
   const bool reflect = a.y_halo == PCGAN_HALO_REFLECT && p > 0;
@@ -226,6 +257,10 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = apply_act(o[j], a.act, a.act_slope);
+      if (has_pm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] *= pm[j];
+      }
       uint4 w;
       w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
       const int x = x0 + (v >> lcv);
@@ -339,7 +374,7 @@ __global__ void __launch_bounds__(kT) halo_fold_kernel(pcgan_fold_args a, int ve
 template <bool GEN, bool RES>
 struct BwdCtx {
   float sc[8], sh[8];                               // pre = sc*(x*mask) + sh (+ residual)
-  float mean[GEN ? 8 : 1], rstd[GEN ? 8 : 1], mk[GEN ? 8 : 1];
+  float mean[GEN ? 8 : 1], rstd[GEN ? 8 : 1], mk[GEN ? 8 : 1], pm[GEN ? 8 : 1];
   float rsc[RES ? 8 : 1], rsh[RES ? 8 : 1];
   const __nv_bfloat16* dyg;                         // sample base of dy (+c0) for the mirror loads of a folded gradient
   int fold;                                         // 0 plain, 2 reflect fold
@@ -348,7 +383,7 @@ struct BwdCtx {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < (GEN ? 8 : 1); ++j) { mean[j] = 0.f; rstd[j] = 0.f; mk[j] = 1.f; }
+    for (int j = 0; j < (GEN ? 8 : 1); ++j) { mean[j] = 0.f; rstd[j] = 0.f; mk[j] = 1.f; pm[j] = 1.f; }
 #pragma unroll
     for (int j = 0; j < (RES ? 8 : 1); ++j) { rsc[j] = 1.f; rsh[j] = 0.f; }
     const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
@@ -356,6 +391,7 @@ struct BwdCtx {
     if constexpr (GEN) {
       if (a.mean) { load_f8(a.mean + so, mean); load_f8(a.rstd + so, rstd); }
       if (a.drop_mask) load_f8(a.drop_mask + static_cast<int64_t>(n) * a.c + c0, mk);
+      if (a.post_mask) load_f8(a.post_mask + static_cast<int64_t>(n) * a.c + c0, pm);
     }
     if constexpr (RES) {
       if (a.res_scale) {
@@ -373,6 +409,10 @@ struct BwdCtx {
                                        const uint4 rraw, float (&dyv)[8], float (&xh)[8]) const {
     unpack8(dyraw, dyv);
     if (fold == 2) folded_load(dyg, y, x, a.h, a.w, a.dy_pad, a.c, true, dyv, true);
+    if constexpr (GEN) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dyv[j] *= pm[j];
+    }
     float x8[8], pre[8];
     unpack8(xraw, x8);
 #pragma unroll
@@ -621,6 +661,8 @@ using namespace pcgan;
 
 extern "C" int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stream_t s) {
   if (!a || !a->stats || a->groups < 1 || a->c < 1 || a->count <= 0.f) return fail(PCGAN_ERR_INVALID, "norm_finalize: bad argument");
+  if (a->in_groups > a->groups && a->groups != 1) return fail(PCGAN_ERR_INVALID, "norm_finalize: per-sample statistics combine into exactly one group");
+  if (a->drop_mask && a->in_groups <= a->groups) return fail(PCGAN_ERR_INVALID, "norm_finalize: drop_mask needs per-sample statistics (in_groups = N)");
   norm_finalize_kernel<<<(a->c + 31) / 32, kT, 0, STREAM(s)>>>(*a);
   PCGAN_LAUNCH_OK("norm_finalize_kernel");
   return PCGAN_OK;
@@ -682,7 +724,7 @@ extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_
   if (rc) return rc;
   if (!a->sums) return fail(PCGAN_ERR_INVALID, "norm_bwd_reduce: sums is null");
   const bool res = a->res != nullptr && a->act != PCGAN_ACT_NONE;   // the residual only matters through the activation mask
-  const bool gen = a->affine != 0 || a->drop_mask != nullptr || res;
+  const bool gen = a->affine != 0 || a->drop_mask != nullptr || a->post_mask != nullptr || res;
   const SegGeom sg = seg_geom(a->w, a->c);
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
@@ -699,7 +741,7 @@ extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t
   if (rc) return rc;
   if (!a->dx && !a->dres) return fail(PCGAN_ERR_INVALID, "norm_bwd_apply: no output");
   const bool res = a->res != nullptr && a->act != PCGAN_ACT_NONE;
-  const bool gen = a->affine != 0 || a->drop_mask != nullptr || res;
+  const bool gen = a->affine != 0 || a->drop_mask != nullptr || a->post_mask != nullptr || res;
   const SegGeom sg = seg_geom(a->w, a->c);
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);

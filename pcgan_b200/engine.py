@@ -45,11 +45,21 @@ class ConvRT:
                                               full_padded=full_padded, note=name + ".dgrad"):
                 self.dgrad.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=torch.bfloat16, device=dev)))
         self.wgrad = None
+        self._wg_args = (shape, dyg, xg, stride, cp, transposed, name)
         if want_wgrad and dyg is not None:
-            sp, wm = CV.conv_wgrad_plan(shape, dyg, xg, stride, cp, transposed=transposed, note=name + ".wgrad")
-            self.wgrad = (ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k, dtype=torch.float32, device=dev))
+            self.ensure_wgrad()
         self.transposed = transposed
         self.flops_fwd = sum(g.spec.flops for g, _, _ in self.fwd)
+
+    def ensure_wgrad(self):
+        """Weight-gradient plan and its packed fp32 accumulator, built on first need (a frozen network never pays)."""
+        if self.wgrad is None:
+            shape, dyg, xg, stride, cp, transposed, name = self._wg_args
+            if dyg is None:
+                raise L.PcganError("%s: no output-gradient geometry was planned, cannot build a weight gradient" % name)
+            sp, wm = CV.conv_wgrad_plan(shape, dyg, xg, stride, cp, transposed=transposed, note=name + ".wgrad")
+            self.wgrad = (ops.Igemm(sp), wm.to(self.dev), torch.zeros(sp.b_rows * sp.b_k, dtype=torch.float32, device=self.dev))
+        return self.wgrad
 
     def pack(self):
         """Refresh the packed bf16 operands when the master weight changed (optimizer step / load_state_dict)."""
@@ -76,7 +86,7 @@ class ConvRT:
 
     def backward_weight(self, dybuf, xbuf):
         """Accumulates into weight.grad (allocated on first use)."""
-        g, wm, packed = self.wgrad
+        g, wm, packed = self.ensure_wgrad()
         packed.zero_()
         if self.transposed or g.spec.swap_operands:
             g.run(xbuf, dybuf, packed)     # M side = input activations, N side = dY
@@ -127,12 +137,15 @@ class NormState:
     With arenas, `stats` / `sums` are slices of the workspace's accumulator arenas (cleared once per pass by the program);
     without, they are private tensors the caller clears."""
 
-    def __init__(self, groups, c, dev, stats_arena=None, sums_arena=None):
+    def __init__(self, groups, c, dev, stats_arena=None, sums_arena=None, stats_groups=None):
+        """stats_groups > groups: the convolution emits per-sample statistics that the finalize kernel folds (with the
+        channel-dropout mask) into one batch statistic."""
         self.groups, self.c = groups, c
+        self.stats_groups = stats_groups or groups
         self.affine = True
-        self._stats = stats_arena.take((groups, c, 2)) if stats_arena is not None else None
+        self._stats = stats_arena.take((self.stats_groups, c, 2)) if stats_arena is not None else None
         self._sums = sums_arena.take((groups, c, 2)) if sums_arena is not None else None
-        self._own_stats = torch.zeros(groups, c, 2, device=dev) if stats_arena is None else None
+        self._own_stats = torch.zeros(self.stats_groups, c, 2, device=dev) if stats_arena is None else None
         self._own_sums = torch.zeros(groups, c, 2, device=dev) if sums_arena is None else None
         self.mean = torch.empty(groups, c, device=dev)
         self.rstd = torch.empty(groups, c, device=dev)

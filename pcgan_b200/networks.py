@@ -39,12 +39,12 @@ def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, *, gamma=None,
 
 
 def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count, dx, dx_pad, *, res=None, res_pad=0,
-                   res_scale=None, res_shift=None, res_groups=1, dres=None, dres_pad=0, dy_fold=0):
+                   res_scale=None, res_shift=None, res_groups=1, dres=None, dres_pad=0, dy_fold=0, drop_mask=None, post_mask=None):
     """Backward of one norm + activation unit.  dy_fold=2: `gy` is the gradient of the reflect-padded buffer (pad gy_pad)
     straight out of the data-gradient kernel; its halo is folded onto the interior while it is read."""
     kw = dict(res=res, res_pad=res_pad, mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, groups=ns.groups,
               res_scale=res_scale, res_shift=res_shift, res_groups=res_groups, act=act, act_slope=slope, count=count,
-              sums=ns.sums, dy_fold=dy_fold, affine=ns.affine)
+              sums=ns.sums, dy_fold=dy_fold, affine=ns.affine, drop_mask=drop_mask, post_mask=post_mask)
     if not ns.pooled:
         ns.sums.zero_()
     ops.norm_bwd_reduce(gy, gy_pad, rbuf, rg, **kw)
@@ -62,6 +62,33 @@ class _Scratch:
         if k not in self.bufs:
             self.bufs[k] = zeros_act(g, self.dev)
         return self.bufs[k]
+
+
+class _Lease:
+    """A workspace borrowed by one forward call whose backward is still to come.  It goes back to the pool right after
+    that backward, or — if the graph is dropped without a backward, or the module keeps workspaces for a second backward
+    through the same graph (retain_workspaces: loss.backward(retain_graph=True), wsgan_emb_model.py:369) — when the
+    autograd node that holds the lease dies."""
+
+    def __init__(self, prog, ws):
+        self.prog, self.ws = prog, ws
+
+    def release(self):
+        if self.ws is not None:
+            self.prog.pool.give(0, self.ws)
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def _release(ctx, prog, ws):
+    if not getattr(prog.mod, "retain_workspaces", False):
+        ctx.lease.release()
+        ctx.ws = None
 
 
 def _require_cuda(t, who):
@@ -181,7 +208,7 @@ class _GenProgram:
         return out, ws
 
     # --------------------------------------------------------------- backward
-    def backward(self, ws, out, dout, need_dx, need_w):
+    def backward(self, ws, out, dout, need_dx, need_w, need_dz=False):
         S, N, sc = self.S, self.N, self.scratch
         h2, h4 = S // 2, S // 4
         m = self.mod.model
@@ -248,20 +275,24 @@ class _GenProgram:
         _norm_backward(g, 0, ws.r1, self.g_r1, ws.n1, R, 0.0, S * S, dy, 3)
         if need_w:
             self.stem.backward_weight(dy, ws.x0)
-        dx = None
-        if need_dx:
+        dx = dz = None
+        if need_dx or need_dz:
             dfull = sc.get(self.g_x0full)
             self.stem.backward_data(dy, dfull)
             gx = sc.get(Geom(N, S, S, 8, 0), "gx")
             ops.halo_fold(dfull, self.g_x0, gx, 0, halo=L.HALO_REFLECT)
-            dx = torch.empty(N, self.mod.input_nc_img, S, S, device=self.dev)
-            ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dx)
+            # channels [0, input_nc) are the image, channel input_nc is the constant embedding plane (networks.py:610-611)
+            nc = self.mod.input_nc_img
+            dxz = torch.empty(N, nc + 1, S, S, device=self.dev)
+            ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dxz)
+            dx = dxz[:, :nc].contiguous() if need_dx else None
+            dz = dxz[:, nc].sum((1, 2)) if need_dz else None
         if need_w:
             # biases in front of an affine-less InstanceNorm have exactly zero gradient
             for c in self.convs[:-1]:
                 if c.bias is not None and c.bias.grad is None:
                     c.bias.grad = torch.zeros_like(c.bias)
-        return dx
+        return dx, dz
 
 
 class _GenFn(torch.autograd.Function):
@@ -270,10 +301,11 @@ class _GenFn(torch.autograd.Function):
         prog = mod._program(x.shape[0], x.shape[2])
         out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
         # needs_input_grad already folds in the global grad mode (forward itself runs with grad disabled)
-        if ctx.needs_input_grad[1] or any(ctx.needs_input_grad[3:]):
-            ctx.prog, ctx.ws = prog, ws
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:]):
+            ctx.prog, ctx.ws, ctx.lease = prog, ws, _Lease(prog, ws)
             ctx.save_for_backward(out)
             ctx.need_w = any(ctx.needs_input_grad[3:])
+            ctx.z_shape = z.shape
         else:
             prog.pool.give(0, ws)
         return out
@@ -282,10 +314,11 @@ class _GenFn(torch.autograd.Function):
     def backward(ctx, dout):
         (out,) = ctx.saved_tensors
         prog, ws = ctx.prog, ctx.ws
-        dx = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w)
-        prog.pool.give(0, ws)
-        ctx.ws = None
-        return (None, dx, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+        dx, dz = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w, ctx.needs_input_grad[2])
+        _release(ctx, prog, ws)
+        if dz is not None:
+            dz = dz.view(ctx.z_shape)
+        return (None, dx, dz) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 class _ResnetBlockHolder(nn.Module):
@@ -337,8 +370,6 @@ class ResnetGenerator(nn.Module):
             raise NotImplementedError("square inputs with side a multiple of 4")
         if z is None or self.nz != 1:
             raise NotImplementedError("ResnetGenerator needs the 1-channel embedding z (nz=1)")
-        if z.requires_grad:
-            raise NotImplementedError("gradient w.r.t. the embedding z (lr_E > 0) is not implemented")
         return _GenFn.apply(self, input, z, *self.parameters())
 
 
@@ -419,7 +450,7 @@ class _DiscProgram:
         self.head.forward(ws.y[-1], out)
         return out, ws
 
-    def backward(self, ws, out, dout, need_dx, need_w):
+    def backward(self, ws, out, dout, need_dx, need_w, need_dz=False):
         m, N, sc = self.mod.model, self.N, self.scratch
         ws.sums_arena.zero()
         dyh = sc.get(self.g_dyh)
@@ -454,13 +485,16 @@ class _DiscProgram:
         if need_w:
             accumulate_grad(self.convs[0].bias, s0[0, :, 0])
             self.convs[0].backward_weight(dy, ws.x0)
-        dx = None
-        if need_dx:
+        dx = dz = None
+        if need_dx or need_dz:
             gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
             self.convs[0].backward_data(dy, gx)
-            dx = torch.empty(N, self.mod.input_nc_img, self.S, self.S, device=self.dev)
-            ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dx)
-        return dx
+            nc = self.mod.input_nc_img      # channel nc is the embedding plane (networks.py:780-782)
+            dxz = torch.empty(N, nc + 1, self.S, self.S, device=self.dev)
+            ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dxz)
+            dx = dxz[:, :nc].contiguous() if need_dx else None
+            dz = dxz[:, nc].sum((1, 2)) if need_dz else None
+        return dx, dz
 
 
 class _DiscFn(torch.autograd.Function):
@@ -469,10 +503,11 @@ class _DiscFn(torch.autograd.Function):
         prog = mod._program(x.shape[0], x.shape[2])
         out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
         # needs_input_grad already folds in the global grad mode (forward itself runs with grad disabled)
-        if ctx.needs_input_grad[1] or any(ctx.needs_input_grad[3:]):
-            ctx.prog, ctx.ws = prog, ws
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:]):
+            ctx.prog, ctx.ws, ctx.lease = prog, ws, _Lease(prog, ws)
             ctx.save_for_backward(out)
             ctx.need_w = any(ctx.needs_input_grad[3:])
+            ctx.z_shape = z.shape
         else:
             prog.pool.give(0, ws)
         return out
@@ -481,10 +516,11 @@ class _DiscFn(torch.autograd.Function):
     def backward(ctx, dout):
         (out,) = ctx.saved_tensors
         prog, ws = ctx.prog, ctx.ws
-        dx = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w)
-        prog.pool.give(0, ws)
-        ctx.ws = None
-        return (None, dx, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+        dx, dz = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w, ctx.needs_input_grad[2])
+        _release(ctx, prog, ws)
+        if dz is not None:
+            dz = dz.view(ctx.z_shape)
+        return (None, dx, dz) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 class NLayerDiscriminator(nn.Module):
@@ -522,7 +558,7 @@ class NLayerDiscriminator(nn.Module):
             raise NotImplementedError("NLayerDiscriminator needs the embedding z")
         if input.shape[2] != input.shape[3] or input.shape[2] % (2 ** self.n_layers):
             raise NotImplementedError("square inputs with side a multiple of %d" % 2 ** self.n_layers)
-        return _DiscFn.apply(self, input, z.detach(), *self.parameters())
+        return _DiscFn.apply(self, input, z, *self.parameters())
 
 
 # ---------------------------------------------------------------------------------------
@@ -597,12 +633,24 @@ class GANLoss(nn.Module):
 
 
 class BinaryNLLLoss(nn.Module):
-    """Elo pairwise loss (networks.py:473-482): target LUT[label] in {0, .5, 1}, -mean(t log(p+1e-20) + (1-t) log(1-p+1e-20))."""
+    """Elo pairwise loss (networks.py:473-482): target LUT[label] in {0, .5, 1}, -mean(t log(p+1e-20) + (1-t) log(1-p+1e-20)).
+    from_score fuses the torch.sigmoid the trainer applies first (siamese.py:675) into the same reduction kernel."""
+
+    def __init__(self):
+        super().__init__()
+        self._lut = {}
+
+    def _target(self, ref, label):
+        lut = self._lut.get(ref.device)
+        if lut is None:
+            lut = self._lut[ref.device] = torch.tensor([0.0, 0.5, 1.0], device=ref.device)
+        return lut[label.to(ref.device)].contiguous()
 
     def __call__(self, prob, label):
-        lut = torch.tensor([0.0, 0.5, 1.0], device=prob.device)
-        t = lut[label.to(prob.device)].contiguous()
-        return _LossFn.apply(L.LOSS_ELO_NLL, prob, t, prob.numel() // prob.size(0))
+        return _LossFn.apply(L.LOSS_ELO_NLL, prob, self._target(prob, label), prob.numel() // prob.size(0))
+
+    def from_score(self, score, label):
+        return _LossFn.apply(L.LOSS_ELO_NLL_SCORE, score, self._target(score, label), score.numel() // score.size(0))
 
 
 # ---------------------------------------------------------------------------------------
@@ -702,20 +750,47 @@ class _EncWorkspace:
     pass
 
 
-class _EncBlock:
-    """One BasicBlock (resnet.py:31-73) at fixed geometry: conv3x3(stride) BN ReLU conv3x3 BN (+ 1x1 stride-s conv BN) add ReLU."""
+def _bn_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, bn, mask=None):
+    """conv -> [Dropout2d mask] -> BatchNorm2d statistics (training mode, running stats updated, resnet.py:57-59).
+    With a mask the convolution emits per-sample statistics that the finalize kernel combines with the mask."""
+    ns.affine = True
+    if not ns.pooled:
+        ns.stats.zero_()
+    conv.forward(xbuf, rbuf, ns.stats)
+    kw = dict(eps=EPS, momentum=MOMENTUM, gamma=bn.weight.detach(), beta=bn.bias.detach(), mean=ns.mean, rstd=ns.rstd,
+              scale=ns.scale, shift=ns.shift, running_mean=bn.running_mean, running_var=bn.running_var)
+    if ns.stats_groups > ns.groups:
+        ops.norm_finalize(ns.stats, 1, ns.c, count, drop_mask=mask, in_groups=ns.stats_groups, **kw)
+    else:
+        assert mask is None
+        ops.norm_finalize(ns.stats, ns.groups, ns.c, count, **kw)
+    bn.num_batches_tracked += 1
 
-    def __init__(self, name, holder, N, hin, cin, c, stride):
+
+def _bn_param_grads(bn, ns: NormState):
+    """dgamma = sum g*xhat, dbeta = sum g: by-products of the backward reduction."""
+    if bn.weight.requires_grad:
+        accumulate_grad(bn.weight, ns.sums[0, :, 1])
+    if bn.bias.requires_grad:
+        accumulate_grad(bn.bias, ns.sums[0, :, 0])
+
+
+class _EncBlock:
+    """One BasicBlock (resnet.py:31-73) at fixed geometry: conv3x3(stride) [drop] BN ReLU conv3x3 [drop] BN
+    (+ 1x1 stride-s conv BN) add ReLU.  dropout=True plans per-sample statistics for the two dropped convolutions."""
+
+    def __init__(self, name, holder, N, hin, cin, c, stride, dropout=False):
         G = Geom
         h = hin // stride
         self.name, self.holder, self.N, self.hin, self.cin, self.h, self.c, self.stride = name, holder, N, hin, cin, h, c, stride
+        self.dropout = dropout
         self.g_x, self.g_xr = G(N, hin, hin, cin, 1), G(N, hin, hin, cin, 0)
         self.g_r, self.g_y = G(N, h, h, c, 0), G(N, h, h, c, 1)
         dy1 = self.g_y if stride == 1 else self.g_r
         self.c1 = ConvRT(name + ".conv1", holder.conv1.weight, None, self.g_x, stride, 1, OutMap.nhwc(self.g_r), stats=True,
-                         dyg=dy1, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
+                         per_sample_stats=dropout, dyg=dy1, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
         self.c2 = ConvRT(name + ".conv2", holder.conv2.weight, None, self.g_y, 1, 1, OutMap.nhwc(self.g_r), stats=True,
-                         dyg=self.g_y, dx_out=OutMap.nhwc(self.g_r), want_wgrad=False)
+                         per_sample_stats=dropout, dyg=self.g_y, dx_out=OutMap.nhwc(self.g_r), want_wgrad=False)
         self.dy1_pad = dy1.pad
         self.ds = None
         if holder.downsample is not None:
@@ -725,58 +800,124 @@ class _EncBlock:
     def new_ws(self, dev, stats_arena=None, sums_arena=None):
         w = _EncWorkspace()
         w.ra, w.h, w.rb, w.y = zeros_act(self.g_r, dev), zeros_act(self.g_y, dev), zeros_act(self.g_r, dev), zeros_act(self.g_y, dev)
-        w.na, w.nb = NormState(1, self.c, dev, stats_arena, sums_arena), NormState(1, self.c, dev, stats_arena, sums_arena)
+        sg = self.N if self.dropout else None
+        w.na = NormState(1, self.c, dev, stats_arena, sums_arena, stats_groups=sg)
+        w.nb = NormState(1, self.c, dev, stats_arena, sums_arena, stats_groups=sg)
+        w.m1 = w.m2 = None
         if self.ds is not None:
             w.rd, w.nd = zeros_act(self.g_r, dev), NormState(1, self.c, dev, stats_arena, sums_arena)
         return w
 
-    def forward(self, xbuf, w):
+    def forward(self, xbuf, w, masks=None):
         hd, cnt = self.holder, self.N * self.h * self.h
-        _unit_forward(self.c1, xbuf, w.ra, w.na, cnt, gamma=hd.bn1.weight.detach(), beta=hd.bn1.bias.detach(),
-                      rmean=hd.bn1.running_mean, rvar=hd.bn1.running_var)
-        hd.bn1.num_batches_tracked += 1
-        ops.norm_apply(w.ra, self.g_r, w.h, self.g_y, y_halo=L.HALO_ZERO, scale=w.na.scale, shift=w.na.shift, groups=1, act=L.ACT_RELU)
-        _unit_forward(self.c2, w.h, w.rb, w.nb, cnt, gamma=hd.bn2.weight.detach(), beta=hd.bn2.bias.detach(),
-                      rmean=hd.bn2.running_mean, rvar=hd.bn2.running_var)
-        hd.bn2.num_batches_tracked += 1
+        w.m1, w.m2 = masks if masks is not None else (None, None)
+        _bn_forward(self.c1, xbuf, w.ra, w.na, cnt, hd.bn1, w.m1)
+        ops.norm_apply(w.ra, self.g_r, w.h, self.g_y, y_halo=L.HALO_ZERO, scale=w.na.scale, shift=w.na.shift, groups=1,
+                       drop_mask=w.m1, act=L.ACT_RELU)
+        _bn_forward(self.c2, w.h, w.rb, w.nb, cnt, hd.bn2, w.m2)
         if self.ds is not None:
-            bnd = hd.downsample[1]
-            _unit_forward(self.ds, xbuf, w.rd, w.nd, cnt, gamma=bnd.weight.detach(), beta=bnd.bias.detach(),
-                          rmean=bnd.running_mean, rvar=bnd.running_var)
-            bnd.num_batches_tracked += 1
+            _bn_forward(self.ds, xbuf, w.rd, w.nd, cnt, hd.downsample[1])
             ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, scale=w.nb.scale, shift=w.nb.shift, groups=1,
-                           res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1, act=L.ACT_RELU)
+                           drop_mask=w.m2, res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1, act=L.ACT_RELU)
         else:
             ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, scale=w.nb.scale, shift=w.nb.shift, groups=1,
-                           res=xbuf, res_pad=1, act=L.ACT_RELU)
+                           drop_mask=w.m2, res=xbuf, res_pad=1, act=L.ACT_RELU)
         return w.y
 
-    def backward(self, xbuf, w, gy, sc):
-        """gy: gradient of the block output (unpadded).  Returns the gradient of the block input (unpadded)."""
-        cnt = self.N * self.h * self.h
+    def backward(self, xbuf, w, gy, sc, need_w=False):
+        """gy: gradient of the block output (unpadded).  Returns the gradient of the block input (unpadded);
+        need_w: also accumulate the weight / BatchNorm parameter gradients."""
+        hd, cnt = self.holder, self.N * self.h * self.h
         dyb = sc.get(self.g_y, self.name + "dyb")
         gres = sc.get(self.g_r, self.name + "gres")
         if self.ds is not None:
             res_kw = dict(res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1)
         else:
             res_kw = dict(res=xbuf, res_pad=1)
-        _norm_backward(gy, 0, w.rb, self.g_r, w.nb, L.ACT_RELU, 0.0, cnt, dyb, 1, dres=gres, dres_pad=0, **res_kw)
+        _norm_backward(gy, 0, w.rb, self.g_r, w.nb, L.ACT_RELU, 0.0, cnt, dyb, 1, dres=gres, dres_pad=0, drop_mask=w.m2, **res_kw)
+        if need_w:
+            _bn_param_grads(hd.bn2, w.nb)
+            self.c2.backward_weight(dyb, w.h)
         gh = sc.get(self.g_r, self.name + "gh")
         self.c2.backward_data(dyb, gh)
         dya = sc.get(self.g_y if self.stride == 1 else self.g_r, self.name + "dya")
-        _norm_backward(gh, 0, w.ra, self.g_r, w.na, L.ACT_RELU, 0.0, cnt, dya, self.dy1_pad)
+        _norm_backward(gh, 0, w.ra, self.g_r, w.na, L.ACT_RELU, 0.0, cnt, dya, self.dy1_pad, drop_mask=w.m1)
+        if need_w:
+            _bn_param_grads(hd.bn1, w.na)
+            self.c1.backward_weight(dya, xbuf)
         gx1 = sc.get(self.g_xr, self.name + "gx1")
         self.c1.backward_data(dya, gx1)
         gx = sc.get(self.g_xr, self.name + "gx")
         if self.ds is not None:
             dyd = sc.get(self.g_r, self.name + "dyd")
             _norm_backward(gres, 0, w.rd, self.g_r, w.nd, L.ACT_NONE, 0.0, cnt, dyd, 0)
+            if need_w:
+                _bn_param_grads(hd.downsample[1], w.nd)
+                self.ds.backward_weight(dyd, xbuf)
             gx2 = sc.get(self.g_xr, self.name + "gx2")  # odd phases of a 1x1 stride-2 conv receive nothing: stay zero
             self.ds.backward_data(dyd, gx2)
             ops.halo_fold(gx1, self.g_xr, gx, 0, halo=L.HALO_ZERO, add=gx2, add_pad=0)
         else:
             ops.halo_fold(gx1, self.g_xr, gx, 0, halo=L.HALO_ZERO, add=gres, add_pad=0)
         return gx
+
+
+class _EncHead:
+    """conv3x3 512->nf (+bias) BN [drop] LeakyReLU conv3x3 nf->1 (+bias) global average pool (networks.py:1014-1027,
+    1056-1057); instantiated for `cnn` and, in noisy mode, for the twin `cnn_logvar` (:1034-1049, 1060-1066)."""
+
+    def __init__(self, name, seq, N, hf, slope):
+        G = Geom
+        self.name, self.seq, self.N, self.hf, self.slope = name, seq, N, hf, slope
+        nf = seq[0].weight.shape[0]
+        self.nf = nf
+        self.g_f = G(N, hf, hf, 512, 1)
+        self.g_rh, self.g_hh = G(N, hf, hf, nf, 0), G(N, hf, hf, nf, 1)
+        self.g_fin, self.g_dyfin = G(N, hf, hf, 8, 0), G(N, hf, hf, 8, 1)
+        self.c1 = ConvRT(name + ".0", seq[0].weight, seq[0].bias, self.g_f, 1, 1, OutMap.nhwc(self.g_rh), stats=True,
+                         dyg=self.g_hh, dx_out=OutMap.nhwc(G(N, hf, hf, 512, 0)), want_wgrad=False)
+        # last conv: the global average pool is its per-sample statistics (sum over the map) / (h*w)
+        self.c2 = ConvRT(name + ".4", seq[4].weight, seq[4].bias, self.g_hh, 1, 1, OutMap.nhwc(self.g_fin), stats=True,
+                         per_sample_stats=True, dyg=self.g_dyfin, dx_out=OutMap.nhwc(self.g_rh), want_wgrad=False)
+
+    def new_ws(self, dev, stats_arena, sums_arena):
+        w = _EncWorkspace()
+        w.rh, w.hh, w.fin = zeros_act(self.g_rh, dev), zeros_act(self.g_hh, dev), zeros_act(self.g_fin, dev)
+        w.nh = NormState(1, self.nf, dev, stats_arena, sums_arena)
+        w.nfin = NormState(self.N, 1, dev, stats_arena, sums_arena)
+        w.pm = None
+        return w
+
+    def forward(self, fbuf, w, mask=None):
+        N, hf = self.N, self.hf
+        w.pm = mask
+        _bn_forward(self.c1, fbuf, w.rh, w.nh, N * hf * hf, self.seq[1])
+        ops.norm_apply(w.rh, self.g_rh, w.hh, self.g_hh, y_halo=L.HALO_ZERO, scale=w.nh.scale, shift=w.nh.shift, groups=1,
+                       act=L.ACT_LRELU, act_slope=self.slope, post_mask=mask)
+        self.c2.forward(w.hh, w.fin, w.nfin.stats)
+        return (w.nfin.stats[:, 0, 0] / float(hf * hf)).view(N, 1, 1, 1)
+
+    def backward(self, fbuf, w, gy, sc, gf_out, need_w=False):
+        """gy [N,1,1,1] -> gradient of the trunk features written to gf_out (unpadded [N, hf, hf, 512])."""
+        N, hf = self.N, self.hf
+        gmap = (gy.reshape(N, 1, 1, 1) / float(hf * hf)).expand(N, 1, hf, hf).contiguous()
+        dyf = sc.get(self.g_dyfin, self.name + "dyf")
+        ops.pack_nchw(gmap, dyf, self.g_dyfin, halo=L.HALO_ZERO)
+        if need_w:
+            self.c2.backward_weight(dyf, w.hh)
+            if self.seq[4].bias.requires_grad:
+                accumulate_grad(self.seq[4].bias, gy.reshape(N).sum().reshape(1))
+        ghh = sc.get(self.g_rh, self.name + "ghh")
+        self.c2.backward_data(dyf, ghh)
+        dyh = sc.get(self.g_hh, self.name + "dyh")
+        _norm_backward(ghh, 0, w.rh, self.g_rh, w.nh, L.ACT_LRELU, self.slope, N * hf * hf, dyh, 1, post_mask=w.pm)
+        if need_w:
+            _bn_param_grads(self.seq[1], w.nh)
+            self.c1.backward_weight(dyh, fbuf)
+            b = self.seq[0].bias      # feeds a BatchNorm: its gradient is exactly zero
+            if b.requires_grad and b.grad is None:
+                b.grad = torch.zeros_like(b)
+        self.c1.backward_data(dyh, gf_out)
 
 
 class _EncProgram:
@@ -787,6 +928,8 @@ class _EncProgram:
         rn = mod.base.model
         dev = rn.conv1.weight.device
         self.dev = dev
+        self.p_drop = float(mod.base.dropout)
+        drop = self.p_drop > 0
         G = Geom
         s2, s4 = S // 2, S // 4
         self.g_x0 = G(N, S, S, 8, 3)
@@ -800,37 +943,39 @@ class _EncProgram:
             layer = getattr(rn, "layer%d" % li)
             for bi in range(2):
                 stride = 2 if (li > 1 and bi == 0) else 1
-                blk = _EncBlock("E.layer%d.%d" % (li, bi), layer[bi], N, hin, cin, c, stride)
+                blk = _EncBlock("E.layer%d.%d" % (li, bi), layer[bi], N, hin, cin, c, stride, dropout=drop)
                 self.blocks.append(blk)
                 hin, cin = hin // stride, c
         self.hf = hin
-        nf = mod.cnn[0].weight.shape[0]
-        self.nf = nf
-        self.g_f = G(N, hin, hin, 512, 1)
-        self.g_rh, self.g_hh = G(N, hin, hin, nf, 0), G(N, hin, hin, nf, 1)
-        self.g_fin = G(N, hin, hin, 8, 0)
-        self.g_dyfin = G(N, hin, hin, 8, 1)
-        self.head1 = ConvRT("E.cnn.0", mod.cnn[0].weight, mod.cnn[0].bias, self.g_f, 1, 1, OutMap.nhwc(self.g_rh), stats=True,
-                            dyg=self.g_hh, dx_out=OutMap.nhwc(G(N, hin, hin, 512, 0)), want_wgrad=False)
-        # last conv: the global average pool is its per-sample statistics (sum over the map) / (h*w)
-        self.head2 = ConvRT("E.cnn.4", mod.cnn[4].weight, mod.cnn[4].bias, self.g_hh, 1, 1, OutMap.nhwc(self.g_fin), stats=True,
-                            per_sample_stats=True, dyg=self.g_dyfin, dx_out=OutMap.nhwc(self.g_rh), want_wgrad=False)
+        self.g_ff = G(N, hin, hin, 512, 0)
+        self.heads = [_EncHead("E.cnn", mod.cnn, N, hin, mod.cnn_relu_slope)]
+        if mod._noisy:
+            self.heads.append(_EncHead("E.cnn_logvar", mod.cnn_logvar, N, hin, mod.cnn_relu_slope))
+        self.head_drop = mod.head_dropout > 0
         self.scratch = _Scratch(dev)
         self.pool = Pool(lambda key: self._new_ws())
 
     def _new_ws(self):
-        ws, dev, N = _EncWorkspace(), self.dev, self.N
+        ws, dev = _EncWorkspace(), self.dev
         ws.x0, ws.r0, ws.a0, ws.p = zeros_act(self.g_x0, dev), zeros_act(self.g_r0, dev), zeros_act(self.g_a0, dev), zeros_act(self.g_p, dev)
         ws.idx = torch.zeros(self.g_pr.numel, dtype=torch.uint8, device=dev)
         ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
         ws.n0 = NormState(1, 64, dev, ws.stats_arena, ws.sums_arena)
         ws.blk = [b.new_ws(dev, ws.stats_arena, ws.sums_arena) for b in self.blocks]
-        ws.rh, ws.hh, ws.fin = zeros_act(self.g_rh, dev), zeros_act(self.g_hh, dev), zeros_act(self.g_fin, dev)
-        ws.nh = NormState(1, self.nf, dev, ws.stats_arena, ws.sums_arena)
-        ws.nfin = NormState(N, 1, dev, ws.stats_arena, ws.sums_arena)
+        ws.heads = [h.new_ws(dev, ws.stats_arena, ws.sums_arena) for h in self.heads]
         ws.stats_arena.finalize()
         ws.sums_arena.finalize()
         return ws
+
+    def _mask(self, c, p):
+        """nn.Dropout2d(p) in training mode: one Bernoulli(1-p) draw per (sample, channel), kept channels scaled by
+        1/(1-p).  Tests inject the draws through SiameseFeature.dropout_masks (consumed in module order)."""
+        q = self.mod.dropout_masks
+        if q:
+            m = q.pop(0).to(self.dev, torch.float32).reshape(self.N, c).contiguous()
+            return m
+        keep = torch.full((self.N, c), 1.0 - p, device=self.dev)
+        return torch.bernoulli(keep) / (1.0 - p)
 
     def forward(self, x):
         mod, N = self.mod, self.N
@@ -839,45 +984,51 @@ class _EncProgram:
         ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
         s2 = self.S // 2
-        _unit_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, gamma=rn.bn1.weight.detach(), beta=rn.bn1.bias.detach(),
-                      rmean=rn.bn1.running_mean, rvar=rn.bn1.running_var)
-        rn.bn1.num_batches_tracked += 1
+        _bn_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, rn.bn1)
         ops.norm_apply(ws.r0, self.g_r0, ws.a0, self.g_a0, scale=ws.n0.scale, shift=ws.n0.shift, groups=1, act=L.ACT_RELU)
         ops.maxpool_fwd(ws.a0, self.g_a0, ws.p, 1, ws.idx)
         cur = ws.p
         for blk, w in zip(self.blocks, ws.blk):
-            cur = blk.forward(cur, w)
-        hf = self.hf
-        bn = mod.cnn[1]
-        _unit_forward(self.head1, cur, ws.rh, ws.nh, N * hf * hf, gamma=bn.weight.detach(), beta=bn.bias.detach(),
-                      rmean=bn.running_mean, rvar=bn.running_var)
-        bn.num_batches_tracked += 1
-        ops.norm_apply(ws.rh, self.g_rh, ws.hh, self.g_hh, y_halo=L.HALO_ZERO, scale=ws.nh.scale, shift=ws.nh.shift, groups=1,
-                       act=L.ACT_LRELU, act_slope=mod.cnn_relu_slope)
-        self.head2.forward(ws.hh, ws.fin, ws.nfin.stats)
-        y = (ws.nfin.stats[:, 0, 0] / float(hf * hf)).view(N, 1, 1, 1)
-        return y, ws
+            masks = (self._mask(blk.c, self.p_drop), self._mask(blk.c, self.p_drop)) if self.p_drop > 0 else None
+            cur = blk.forward(cur, w, masks)
+        outs = []
+        for h, w in zip(self.heads, ws.heads):
+            outs.append(h.forward(cur, w, self._mask(h.nf, mod.head_dropout) if self.head_drop else None))
+        return outs, ws
 
-    def backward(self, ws, gy):
-        mod, N, sc, hf = self.mod, self.N, self.scratch, self.hf
+    def backward(self, ws, gys, need_dx, need_w):
+        """gys: one gradient (or None) per head output."""
+        N, sc, hf = self.N, self.scratch, self.hf
+        rn = self.mod.base.model
         ws.sums_arena.zero()
-        gmap = (gy.view(N, 1, 1, 1) / float(hf * hf)).expand(N, 1, hf, hf).contiguous()
-        dyf = sc.get(self.g_dyfin)
-        ops.pack_nchw(gmap, dyf, self.g_dyfin, halo=L.HALO_ZERO)
-        ghh = sc.get(self.g_rh, "ghh")
-        self.head2.backward_data(dyf, ghh)
-        dyh = sc.get(self.g_hh, "dyh")
-        _norm_backward(ghh, 0, ws.rh, self.g_rh, ws.nh, L.ACT_LRELU, mod.cnn_relu_slope, N * hf * hf, dyh, 1)
-        g = sc.get(Geom(N, hf, hf, 512, 0), "gf")
-        self.head1.backward_data(dyh, g)
+        feats = ws.blk[-1].y
+        g = None
+        for i, (h, w, gy) in enumerate(zip(self.heads, ws.heads, gys)):
+            if gy is None:
+                continue
+            gf = sc.get(self.g_ff, "gf%d" % i)
+            h.backward(feats, w, gy.contiguous().float(), sc, gf, need_w)
+            if g is None:
+                g = gf
+            else:
+                gsum = sc.get(self.g_ff, "gfsum")
+                ops.halo_fold(g, self.g_ff, gsum, 0, halo=L.HALO_ZERO, add=gf, add_pad=0)
+                g = gsum
+        if g is None:
+            return None
         inputs = [ws.p] + [w.y for w in ws.blk[:-1]]
         for blk, w, xin in zip(reversed(self.blocks), reversed(ws.blk), reversed(inputs)):
-            g = blk.backward(xin, w, g, sc)
+            g = blk.backward(xin, w, g, sc, need_w)
         s2 = self.S // 2
         ga0 = sc.get(self.g_a0, "ga0")
         ops.maxpool_bwd(g, 0, ws.idx, ga0, 0, N, s2, s2, 64)
         dy0 = sc.get(self.g_r0, "dy0")
         _norm_backward(ga0, 0, ws.r0, self.g_r0, ws.n0, L.ACT_RELU, 0.0, N * s2 * s2, dy0, 0)
+        if need_w:
+            _bn_param_grads(rn.bn1, ws.n0)
+            self.stem.backward_weight(dy0, ws.x0)
+        if not need_dx:
+            return None
         gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
         self.stem.backward_data(dy0, gx)
         dx = torch.empty(N, 3, self.S, self.S, device=self.dev)
@@ -889,22 +1040,21 @@ class _EncFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, *params):
         prog = mod._program(x.shape[0], x.shape[2])
-        y, ws = prog.forward(x.contiguous().float())
-        if any(ctx.needs_input_grad[2:]):
-            raise NotImplementedError("training the Elo encoder inside wsgan_emb (lr_E > 0) is not implemented: freeze it "
-                                      "(set_requires_grad(netE, False), wsgan_emb_model.py:164-165)")
-        if ctx.needs_input_grad[1]:
-            ctx.prog, ctx.ws = prog, ws
+        outs, ws = prog.forward(x.contiguous().float())
+        ctx.set_materialize_grads(False)     # an unused head (logvar) then gets None instead of a zero gradient
+        ctx.need_w = any(ctx.needs_input_grad[2:])
+        if ctx.needs_input_grad[1] or ctx.need_w:
+            ctx.prog, ctx.ws, ctx.lease = prog, ws, _Lease(prog, ws)
         else:
             prog.pool.give(0, ws)
-        return y
+        ctx.n_out = len(outs)
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, *gys):
         prog, ws = ctx.prog, ctx.ws
-        dx = prog.backward(ws, gy.contiguous().float())
-        prog.pool.give(0, ws)
-        ctx.ws = None
+        dx = prog.backward(ws, list(gys), ctx.needs_input_grad[1], ctx.need_w)
+        _release(ctx, prog, ws)
         return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
@@ -941,14 +1091,16 @@ class _ResNet18Holder(nn.Module):
 
 
 class ResNetFeature(nn.Module):
+    """networks.py:1310-1359 for resnet18; dropout > 0 = nn.Dropout2d after every BasicBlock convolution (resnet.py:40-49),
+    always live (the reference never calls .eval(): that is how its MC-dropout works)."""
+
     def __init__(self, input_nc=3, which_model="resnet18", dropout=0.0):
         super().__init__()
         if which_model != "resnet18" or input_nc != 3:
             raise NotImplementedError("pcgan_b200 ResNetFeature: resnet18 on RGB input (the wsgan_emb configuration)")
-        if dropout > 0:
-            raise NotImplementedError("MC-dropout (Bayesian encoder, --bnn_dropout > 0) is not implemented yet")
         self.model = _ResNet18Holder()
         self.feature_dim = 512
+        self.dropout = float(dropout)
 
     def load_pretrained(self, state_dict):
         if isinstance(state_dict, str):
@@ -956,21 +1108,31 @@ class ResNetFeature(nn.Module):
         self.model.load_state_dict(state_dict, strict=False)
 
 
+def _head_holder(feature_dim, nf, cnn_pad):
+    return nn.Sequential(nn.Conv2d(feature_dim, nf, 3, padding=cnn_pad), nn.BatchNorm2d(nf), IdentityMapping(),
+                         nn.Identity(), nn.Conv2d(nf, 1, 3, padding=cnn_pad))
+
+
 class SiameseFeature(nn.Module):
     """Same constructor / forward / load_pretrained / state_dict keys as models/networks.py:1008-1083 (pooling 'avg',
-    cnn_dim = [nf, 1]).  Always runs with batch statistics, as the reference does (no .eval() on the train path)."""
+    cnn_dim = [nf, 1]).  Always runs with batch statistics, as the reference does (no .eval() on the train path).
+    noisy=True adds the twin `cnn_logvar` head and forward returns (y, logvar); drop_layer = nn.Dropout2d partial puts a
+    channel dropout between the head's BatchNorm and LeakyReLU (networks.py:1021-1023)."""
 
     def __init__(self, base=None, pooling="avg", cnn_dim=[], cnn_pad=1, cnn_relu_slope=0.2, noisy=False, drop_layer=None):
         super().__init__()
         if pooling != "avg" or len(cnn_dim) != 2 or cnn_dim[1] != 1 or cnn_pad != 1 or cnn_dim[0] % 8 or cnn_dim[0] >= 64:
             raise NotImplementedError("pcgan_b200 SiameseFeature: pooling='avg', cnn_dim=[nf<64 (multiple of 8), 1], cnn_pad=1")
-        if noisy:
-            raise NotImplementedError("the aleatoric twin head (--noisy true) is not implemented yet")
-        self.pooling, self.base, self._noisy, self.cnn_relu_slope = pooling, base, noisy, cnn_relu_slope
+        self.pooling, self.base, self._noisy, self.cnn_relu_slope = pooling, base, bool(noisy), cnn_relu_slope
+        self.head_dropout = 0.0
+        if isinstance(drop_layer, functools.partial) and drop_layer.func is nn.Dropout2d:
+            self.head_dropout = float(drop_layer.keywords.get("p", 0.5))
         nf = cnn_dim[0]
-        self.cnn = nn.Sequential(nn.Conv2d(base.feature_dim, nf, 3, padding=cnn_pad), nn.BatchNorm2d(nf), IdentityMapping(),
-                                 nn.Identity(), nn.Conv2d(nf, 1, 3, padding=cnn_pad))
+        self.cnn = _head_holder(base.feature_dim, nf, cnn_pad)
+        if self._noisy:
+            self.cnn_logvar = _head_holder(base.feature_dim, nf, cnn_pad)
         self.feature_dim = 1
+        self.dropout_masks = []      # test hook: explicit Dropout2d draws, consumed in module order
         self._programs = {}
 
     def _program(self, n, s):
@@ -979,11 +1141,15 @@ class SiameseFeature(nn.Module):
             self._programs[k] = _EncProgram(self, n, s)
         return self._programs[k]
 
-    def forward(self, x):
+    def _run(self, x):
         _require_cuda(x, "SiameseFeature")
         if x.shape[1] != 3 or x.shape[2] != x.shape[3]:
             raise NotImplementedError("square RGB inputs")
         return _EncFn.apply(self, x, *self.parameters())
+
+    def forward(self, x):
+        outs = self._run(x)
+        return (outs[0], outs[1]) if self._noisy else outs[0]
 
     def load_pretrained(self, state_dict):
         if isinstance(state_dict, str):
@@ -995,6 +1161,40 @@ class SiameseFeature(nn.Module):
 
     def load_base(self, state_dict):
         self.base.load_pretrained(state_dict)
+
+
+class SiameseNetwork(SiameseFeature):
+    """The Elo rating trainer's network (networks.py:872-1005) in the configuration siamese.py builds by default
+    (:445-449: cnn_dim=[32, 1], fc_dim=[], no cxn): two passes of the shared encoder, each with its own BatchNorm batch,
+    score = rating(input1) - rating(input2) (:971-992).  Same state_dict keys as SiameseFeature (base.*, cnn.*)."""
+
+    def __init__(self, base=None, pooling="avg", cnn_dim=[], cnn_pad=1, cnn_relu_slope=0.5, fc_dim=[], fc_relu_slope=0.2,
+                 fc_residual=True, dropout=0.5, use_cxn=False, noisy=False, drop_layer=None, rsample=False):
+        if fc_dim or use_cxn:
+            raise NotImplementedError("pcgan_b200 SiameseNetwork: fc_dim=[] and use_cxn=False (the siamese.py default)")
+        super().__init__(base, pooling, cnn_dim, cnn_pad, cnn_relu_slope, noisy, drop_layer)
+        self._rsample = rsample
+
+    def forward_once(self, x):
+        outs = self._run(x)
+        return (outs[0], outs[1]) if self._noisy else (outs[0], None)
+
+    def forward(self, input1, input2):
+        feature1, logvar1 = self.forward_once(input1)
+        feature2, logvar2 = self.forward_once(input2)
+        output = feature1 - feature2
+        if self._noisy and self._rsample:
+            return feature1, feature2, logvar1, logvar2
+        if self._noisy:
+            std_ = torch.sqrt(torch.exp(logvar1) + torch.exp(logvar2))
+            return feature1, feature2, output, std_
+        return feature1, feature2, output
+
+    def load_pretrained(self, state_dict):
+        self.base.load_pretrained(state_dict)
+
+    def get_finetune_parameters(self):
+        return self.cnn.parameters()
 
 
 def get_dropout_layer(dropout=0.0):
@@ -1048,3 +1248,39 @@ def upsample2d(inputTensor, targetSize):
         return inputTensor
     _require_cuda(inputTensor, "upsample2d")
     return _UpsampleFn.apply(inputTensor, targetSize)
+
+
+NOISE_QUEUE = []   # test hook: explicit standard-normal draws for resample(), consumed in call order
+
+
+def resample(mu=0.0, var=0.0):
+    """util.resample (util/util.py:136-139): mu + randn * sqrt(var)."""
+    std = torch.sqrt(var)
+    eps = NOISE_QUEUE.pop(0).to(std.device, std.dtype).view_as(std) if NOISE_QUEUE else torch.randn_like(std)
+    return mu + eps * std
+
+
+def reparameterize(mu, logvar):
+    """util.reparameterize (util/util.py:130-133)."""
+    std = torch.exp(0.5 * logvar)
+    return mu + torch.randn_like(std) * std
+
+
+def compute_mu_and_var(E, x, T, noisy=False):
+    """util.compute_mu_and_var (util/util.py:153-171): Monte-Carlo dropout statistics over T stochastic passes of the
+    encoder: mean, E[y^2] - E[y]^2 and (noisy) the mean of exp(logvar)."""
+    y_mu = 0.0
+    y_sq = 0.0
+    if not noisy:
+        for _ in range(T):
+            y = E(x)
+            y_mu = y_mu + 1.0 / T * y
+            y_sq = y_sq + 1.0 / T * y ** 2
+        return y_mu, y_sq - y_mu ** 2
+    s2_mu = 0.0
+    for _ in range(T):
+        y, logs2 = E(x)
+        y_mu = y_mu + 1.0 / T * y
+        y_sq = y_sq + 1.0 / T * y ** 2
+        s2_mu = s2_mu + 1.0 / T * torch.exp(logs2)
+    return y_mu, y_sq - y_mu ** 2, s2_mu

@@ -106,21 +106,22 @@ def unpack_resize_bwd(gbuf, g: Geom, dst, *, accumulate=False, scale=1.0):
 
 
 def norm_finalize(stats, groups, c, count, *, eps=1e-5, momentum=0.1, gamma=None, beta=None, mean=None, rstd=None,
-                  scale=None, shift=None, running_mean=None, running_var=None):
+                  scale=None, shift=None, running_mean=None, running_var=None, drop_mask=None, in_groups=0):
     a = L.NormFinalizeArgs(stats=_ptr(stats), groups=groups, c=c, count=float(count), eps=eps, momentum=momentum,
                            gamma=_ptr(gamma), beta=_ptr(beta), mean=_ptr(mean), rstd=_ptr(rstd), scale=_ptr(scale),
-                           shift=_ptr(shift), running_mean=_ptr(running_mean), running_var=_ptr(running_var))
+                           shift=_ptr(shift), running_mean=_ptr(running_mean), running_var=_ptr(running_var),
+                           drop_mask=_ptr(drop_mask), in_groups=in_groups)
     _count()
     L.check(L.load().pcgan_norm_finalize(C.byref(a), _stream()), "norm_finalize")
 
 
 def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shift=None, groups=1, res=None, res_pad=0,
-               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0):
+               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, post_mask=None):
     assert (xg.n, xg.h, xg.w, xg.c) == (yg.n, yg.h, yg.w, yg.c)
     a = L.NormApplyArgs(x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad, y=_ptr(y), y_pad=yg.pad, y_halo=y_halo,
                         n=xg.n, h=xg.h, w=xg.w, c=xg.c, scale=_ptr(scale), shift=_ptr(shift), groups=groups,
                         res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
-                        drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope)
+                        drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, post_mask=_ptr(post_mask))
     _count()
     L.check(L.load().pcgan_norm_apply(C.byref(a), _stream()), "norm_apply")
 
@@ -134,13 +135,13 @@ def halo_fold(gpad, gg: Geom, out, out_pad, *, halo=L.HALO_REFLECT, add=None, ad
 
 def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, scale=None, shift=None, groups=1,
               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, count=0.0,
-              sums=None, dx=None, dx_pad=0, dres=None, dres_pad=0, dy_fold=0, affine=1):
+              sums=None, dx=None, dx_pad=0, dres=None, dres_pad=0, dy_fold=0, affine=1, post_mask=None):
     return L.NormBwdArgs(dy=_ptr(dy), dy_pad=dy_pad, x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad,
                          mean=_ptr(mean), rstd=_ptr(rstd), scale=_ptr(scale), shift=_ptr(shift), groups=groups,
                          res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
                          drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, n=xg.n, h=xg.h, w=xg.w, c=xg.c,
                          count=float(count), sums=_ptr(sums), dx=_ptr(dx), dx_pad=dx_pad, dres=_ptr(dres), dres_pad=dres_pad,
-                         dy_fold=dy_fold, affine=int(affine))
+                         dy_fold=dy_fold, post_mask=_ptr(post_mask), affine=int(affine))
 
 
 def norm_bwd_reduce(dy, dy_pad, x, xg, **kw):

@@ -8,10 +8,11 @@ What stays PyTorch: parameter storage, torch.optim.Adam, LR 
 checkpoint I/O, control flow.  One process per GPU; gradients are averaged across ranks by
 pcgan_b200.dist.GradSync (the reference's nn.DataParallel replaced by NCCL all-reduce).
 
-Supported flags: the default wsgan_emb configuration with --which_model_netG resnet_9blocks
-(or resnet_6blocks), --which_model_netD n_layers/basic, --lambda_IP 0, plus --lambda_L1,
---lambda_A_GAN, --detach_fake_B, --use_real_A, --no_mixed_label_D.  The Bayesian / noisy
-encoder modes and lr_E > 0 raise NotImplementedError (SURVEY §8f / later rounds).
+Supported flags: the wsgan_emb configuration with --which_model_netG resnet_9blocks (or
+resnet_6blocks), --which_model_netD n_layers/basic, --lambda_IP 0, plus --lambda_L1,
+--lambda_A_GAN, --detach_fake_B, --use_real_A, --no_mixed_label_D, the four encoder modes
+(--bayesian / --noisy with --noisy_var_type, --bnn_dropout, --bnn_T, --noisy_D, --noisy_rec) and
+--lr_E > 0 (update_G_and_E).
 """
 import os
 from argparse import Namespace
@@ -23,7 +24,7 @@ from torch.optim import lr_scheduler
 
 from . import networks
 from .dist import GradSync
-from .networks import upsample2d
+from .networks import compute_mu_and_var, resample, upsample2d
 
 
 def default_options(**overrides):
@@ -134,10 +135,6 @@ class WSGANEmbModel(BaseModel):
     def initialize(self, opt):
         BaseModel.initialize(self, opt)
         assert opt.input_nc == opt.output_nc
-        if opt.bayesian or opt.noisy or opt.noisy_var_type:
-            raise NotImplementedError("Bayesian / noisy encoder modes (BASELINE config 4) are not implemented yet")
-        if opt.isTrain and opt.lr_E > 0.0:
-            raise NotImplementedError("lr_E > 0 (training the encoder inside wsgan_emb) is not implemented")
         if opt.isTrain and opt.lambda_IP > 0.0:
             raise NotImplementedError("the identity-preserving AlexNet loss (netIP) is outside the named hot path: use --lambda_IP 0")
         if opt.no_cnn_E:
@@ -174,10 +171,22 @@ class WSGANEmbModel(BaseModel):
             lr = torch.tensor(float(opt.lr), device=self.device) if self.use_graph else opt.lr
             self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=lr, **adam_kw)
             self.optimizers = [self.optimizer_G, self.optimizer_D]
-            self.set_requires_grad(self.netE, False)   # wsgan_emb_model.py:164-165 (E stays in train mode: SURVEY A.1)
             # one process per GPU: flat gradient buffers, averaged over ranks with one NCCL all-reduce per network
             self.sync_G = GradSync(list(self.netG.parameters()))
             self.sync_D = GradSync(list(self.netD.parameters()))
+            self.sync_E = None
+            if opt.lr_E > 0.0:      # wsgan_emb_model.py:159-163
+                if self.use_graph:
+                    raise NotImplementedError("--cuda_graph with --lr_E > 0 (two generator updates per step) is not supported")
+                self.optimizer_E = torch.optim.Adam(self.netE.parameters(), lr=opt.lr_E, betas=(opt.beta1, 0.999))
+                self.optimizers.append(self.optimizer_E)
+                self.sync_E = GradSync(list(self.netE.parameters()))
+                # backward_GE keeps the graph (retain_graph=True, :369) and backward_G_alone walks G's first pass and
+                # E(real_B) again: their workspaces must outlive the first backward
+                for net in (self.netG, self.netE):
+                    self._unwrap(net).retain_workspaces = True
+            else:
+                self.set_requires_grad(self.netE, False)   # :164-165 (E stays in train mode: SURVEY A.1)
             self.relabel_D = opt.relabel_D
             self._relabel_lut = torch.tensor([float(v) for v in opt.relabel_D], device=self.device)
             self._static = {}
@@ -230,16 +239,46 @@ class WSGANEmbModel(BaseModel):
         self.current_batch_size = int(self.real_A.size(0))
 
     # --------------------------------------------------------------- forward
+    def _encode(self, x_E):
+        """The four encoder modes of forward() (:218-240): returns y and, when --noisy_var_type asks for it, the variance
+        the embedding is resampled with."""
+        opt = self.opt
+        x = self.transform_E(x_E)
+        var = None
+        if not opt.bayesian and not opt.noisy:
+            y = self.netE(x)
+        elif not opt.bayesian and opt.noisy:
+            y, logvar = self.netE(x)
+            if "a" in opt.noisy_var_type:
+                var = torch.exp(logvar)
+        elif opt.bayesian and not opt.noisy:
+            y, y_var = compute_mu_and_var(self.netE, x, opt.bnn_T, False)
+            if "e" in opt.noisy_var_type:
+                var = y_var
+        else:
+            y, y_var, y_s2 = compute_mu_and_var(self.netE, x, opt.bnn_T, True)
+            if "a" in opt.noisy_var_type:
+                var = y_s2 + y_var
+        return y, var
+
     def forward(self):
-        """wsgan_emb_model.py:214-259, plain-encoder branch with lr_E <= 0."""
+        """wsgan_emb_model.py:214-259."""
         opt = self.opt
         self.real_A_E = upsample2d(self.real_A, opt.fineSize_E)
         self.real_B_E = upsample2d(self.real_B, opt.fineSize_E)
-        y_A = self.netE(self.transform_E(self.real_A_E))
-        y_B = self.netE(self.transform_E(self.real_B_E))
-        self.y_A, self.y_B = y_A.detach(), y_B.detach()
-        self.embedding_A = self.embedding_normalize(self.y_A).detach()
-        self.embedding_B = self.embedding_normalize(self.y_B).detach()
+        y_A, var_A = self._encode(self.real_A_E)
+        y_B, var_B = self._encode(self.real_B_E)
+        if var_A is not None:
+            self.resample_A = self.embedding_normalize(resample(y_A, var_A))
+            self.resample_B = self.embedding_normalize(resample(y_B, var_B))
+        self.y_A, self.y_B = y_A, y_B
+        self.embedding_A = self.embedding_normalize(self.y_A)
+        self.embedding_B = self.embedding_normalize(self.y_B)
+        if opt.lr_E <= 0.0:
+            self.y_A, self.y_B = self.y_A.detach(), self.y_B.detach()
+            self.embedding_A, self.embedding_B = self.embedding_A.detach(), self.embedding_B.detach()
+            if opt.noisy_var_type:
+                self.resample_A, self.resample_B = self.resample_A.detach(), self.resample_B.detach()
         self.fake_B = self.netG(self.real_A, self.embedding_B)
         self.fake_B_E = upsample2d(self.fake_B, opt.fineSize_E)
         src = self.fake_B.detach() if opt.detach_fake_B else self.fake_B
@@ -248,28 +287,32 @@ class WSGANEmbModel(BaseModel):
     def test(self):
         with torch.no_grad():
             if hasattr(self, "real_B"):
-                y_B = self.netE(self.transform_E(upsample2d(self.real_B, self.opt.fineSize_E)))
+                y_B, _ = self._encode(upsample2d(self.real_B, self.opt.fineSize_E))
                 self.embedding_B = self.embedding_normalize(y_B.detach())
                 self.fake_B = self.netG(self.real_A, self.embedding_B)
 
     # -------------------------------------------------------------- backward
+    def _cond_B(self):
+        """what D is conditioned on for the fake image (:303-306, 373-376)"""
+        return self.resample_B if (self.opt.noisy_var_type and self.opt.noisy_D) else self.embedding_B
+
     def backward_D(self):
         """wsgan_emb_model.py:300-329."""
         opt = self.opt
-        pred_fake = self.netD(self.fake_B.detach(), self.embedding_B)
+        pred_fake = self.netD(self.fake_B.detach(), self._cond_B().detach())
         self.loss_D_fake = self.criterionGAN(pred_fake, False)
         img = self.real_A if opt.use_real_A else self.real_B
         emb_right, emb_wrong = (self.embedding_A, self.embedding_B) if opt.use_real_A else (self.embedding_B, self.embedding_A)
-        self.loss_D_real_right = self.criterionGAN(self.netD(img, emb_right), True)
+        self.loss_D_real_right = self.criterionGAN(self.netD(img, emb_right.detach()), True)
         target_label = self._relabel_lut[self._label_dev]      # [relabel_D[l] for l in label_AB] (:324), on the device
-        self.loss_D_real_wrong = self.criterionGAN(self.netD(img, emb_wrong), target_label)
+        self.loss_D_real_wrong = self.criterionGAN(self.netD(img, emb_wrong.detach()), target_label)
         self.loss_D = (self.loss_D_fake + (self.loss_D_real_right + self.loss_D_real_wrong) * 0.5) * 0.5
         self.loss_D.backward()
 
-    def backward_G(self):
-        """wsgan_emb_model.py:371-437 with lambda_IP = 0 and the plain encoder."""
+    def _generator_losses(self):
+        """the terms backward_G and backward_GE share (:333-364, 372-404), lambda_IP = 0"""
         opt = self.opt
-        self.loss_G_GAN = self.criterionGAN(self.netD(self.fake_B, self.embedding_B), True)
+        self.loss_G_GAN = self.criterionGAN(self.netD(self.fake_B, self._cond_B()), True)
         if opt.lambda_A_GAN > 0.0:
             self.loss_G_GAN_cycle = self.criterionGAN(self.netD(self.rec_A, self.embedding_A), True) * opt.lambda_A_GAN
         else:
@@ -277,13 +320,59 @@ class WSGANEmbModel(BaseModel):
         self.loss_G_L1 = self.criterionL1(self.fake_B, self.real_A) * opt.lambda_L1 if opt.lambda_L1 > 0.0 else 0.0
         self.loss_G_IP = 0.0
         self.loss_G_cycle = self.criterionCycle(self.rec_A, self.real_A) * opt.lambda_A if opt.lambda_A > 0.0 else 0.0
+        return self.loss_G_GAN + self.loss_G_IP + self.loss_G_L1 + self.loss_G_cycle + self.loss_G_GAN_cycle
+
+    def backward_G(self):
+        """wsgan_emb_model.py:371-437 with lambda_IP = 0."""
+        opt = self.opt
+        partial = self._generator_losses()
         if opt.lambda_z > 0.0:
-            pred_y = self.netE(self.transform_E(self.fake_B_E))
-            self.loss_z_rec = self.criterionRec(pred_y, self.y_B) * opt.lambda_z
+            y_var = y_logvar = None
+            if not opt.bayesian and not opt.noisy:
+                pred_y = self.netE(self.transform_E(self.fake_B_E))
+            elif not opt.bayesian and opt.noisy:
+                pred_y, y_logvar = self.netE(self.transform_E(self.fake_B_E))
+                if "a" in opt.noisy_var_type:
+                    y_var = torch.exp(y_logvar)
+            elif opt.bayesian and not opt.noisy:
+                pred_y, y_var = compute_mu_and_var(self.netE, self.transform_E(self.fake_B_E), opt.bnn_T, False)
+                if "e" in opt.noisy_var_type:
+                    y_logvar = torch.log(y_var + 1e-20)
+            else:
+                # bayesian and noisy: the reference evaluates the encoder on real_A_E here (:419), so this term carries
+                # no gradient to G; reproduced as is (SURVEY appendix A.10)
+                pred_y, y_var_, y_s2_ = compute_mu_and_var(self.netE, self.transform_E(self.real_A_E), opt.bnn_T, True)
+                y_var = torch.zeros_like(pred_y)
+                if "a" in opt.noisy_var_type:
+                    y_var = y_var + y_s2_
+                if "e" in opt.noisy_var_type:
+                    y_var = y_var + y_var_
+                y_logvar = torch.log(y_var + 1e-20)
+            if opt.noisy_var_type and opt.noisy_rec:
+                self.loss_z_rec = ((pred_y - self.y_B).pow(2) / y_var.detach() + y_logvar.detach()).sum() / pred_y.size(0) * 0.5 * opt.lambda_z
+            else:
+                self.loss_z_rec = self.criterionRec(pred_y, self.y_B) * opt.lambda_z
         else:
             self.loss_z_rec = 0.0
-        self.loss_G = self.loss_G_GAN + self.loss_G_IP + self.loss_G_L1 + self.loss_G_cycle + self.loss_z_rec + self.loss_G_GAN_cycle
-        self.loss_G.backward()
+        self.loss_G = partial + self.loss_z_rec
+        if torch.is_tensor(self.loss_G) and self.loss_G.requires_grad:
+            self.loss_G.backward()
+
+    def backward_GE(self):
+        """wsgan_emb_model.py:331-369: the generator terms with the graph kept, gradients reach E through the embeddings."""
+        self.loss_G = self._generator_losses()
+        self.loss_G.backward(retain_graph=True)
+
+    def backward_G_alone(self):
+        """wsgan_emb_model.py:439-449."""
+        opt = self.opt
+        if opt.lambda_z > 0.0:
+            out = self.netE(self.transform_E(self.fake_B_E))
+            pred_embedding = self.embedding_normalize(out[0] if opt.noisy else out)
+            self.loss_z_rec = self.criterionRec(pred_embedding, self.embedding_B.detach()) * opt.lambda_z
+            self.loss_z_rec.backward()
+        else:
+            self.loss_z_rec = 0.0
 
     def update_D(self):
         self.set_requires_grad(self.netD, True)
@@ -299,9 +388,29 @@ class WSGANEmbModel(BaseModel):
         self.sync_G.all_reduce()
         self.optimizer_G.step()
 
+    def update_G_and_E(self):
+        """wsgan_emb_model.py:463-476."""
+        self.set_requires_grad(self.netD, False)
+        self.sync_G.zero()
+        self.sync_E.zero()
+        self.backward_GE()
+        self.sync_G.all_reduce()
+        self.sync_E.all_reduce()
+        self.optimizer_G.step()
+        self.optimizer_E.step()
+        if self.opt.lambda_z > 0.0:
+            self.sync_G.zero()
+            self.sync_E.zero()
+            self.backward_G_alone()
+            self.sync_G.all_reduce()
+            self.optimizer_G.step()
+
     def _step(self):
         self.forward()
-        self.update_G()
+        if self.opt.lr_E > 0.0:
+            self.update_G_and_E()
+        else:
+            self.update_G()
         self.update_D()
 
     # The step as three collective-free segments (multi-GPU graph mode): the two gradient all-reduces run between

@@ -162,12 +162,138 @@ def golden_step():
     print(steps)
 
 
+def _record_dropout(net, masks):
+    """Forward hooks on every nn.Dropout2d: the mask of each call, [N, C], in call order."""
+    def hook(mod, inp, out):
+        x = inp[0]
+        nz = x.abs().amax((2, 3)) > 0
+        ratio = torch.where(nz, out.abs().amax((2, 3)) / x.abs().amax((2, 3)).clamp_min(1e-30), torch.full_like(nz, 1.0 / (1 - mod.p), dtype=x.dtype))
+        masks.append(ratio.detach().clone())
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.register_forward_hook(hook)
+
+
+def golden_encoder_dropout():
+    """SiameseFeature with the noisy twin head and live nn.Dropout2d (bnn_dropout 0.2: resnet.py:58-65, networks.py:1022),
+    masks recorded so the oracle / kernels replay the same draws."""
+    from models import networks
+    net = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7,
+                            gpu_ids=[], noisy=True, bnn_dropout=0.2)
+    O.fill_state_dict_(net.state_dict(), 15)
+    masks = []
+    _record_dropout(net, masks)
+    a, _, _ = O.synthetic_batch(2, 64, 105)
+    a.requires_grad_(True)
+    torch.manual_seed(5)
+    y, lv = net(a)
+    (y * torch.tensor([1.0, -2.0]).view(2, 1, 1, 1) + lv * torch.tensor([0.5, 0.25]).view(2, 1, 1, 1)).sum().backward()
+    torch.save({"seed": 15, "x_seed": 105, "masks": masks, "y": y.detach(), "logvar": lv.detach(), "dx_sub": sub(a.grad, 4),
+                "dx_norm": a.grad.norm()}, os.path.join(HERE, "encoder_dropout.pt"))
+    print("encoder_dropout: %d masks" % len(masks))
+
+
+def golden_siamese_step():
+    """Two steps of the Elo rating trainer (siamese.py:590-686, plain branch): SiameseNetwork(resnet18, cnn_dim=[32, 1],
+    fc_dim=[]), BinaryNLLLoss, Adam(lr 2e-4) over base + cnn (siamese.py:544-551)."""
+    from models import networks
+    base = networks.ResNetFeature(input_nc=3, which_model="resnet18", dropout=0.0)
+    net = networks.SiameseNetwork(base, pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7, fc_dim=[],
+                                  drop_layer=networks.get_dropout_layer(0.0))
+    O.fill_state_dict_(net.state_dict(), 16)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        crit = networks.BinaryNLLLoss()
+    finally:
+        torch.Tensor.cuda = orig
+    import itertools
+    opt = torch.optim.Adam(itertools.chain(net.base.parameters(), net.cnn.parameters()), lr=2e-4)
+    steps = []
+    for it in range(2):
+        a, b, label = O.synthetic_batch(4, 64, 300 + it)
+        opt.zero_grad()
+        f1, f2, score = net(a, b)
+        prob = torch.sigmoid(score)
+        loss = crit(prob, label)
+        loss.backward()
+        if it == 0:
+            grads = {k: (p.grad[:6].clone() if p.grad.dim() == 4 else p.grad.clone()) for k, p in net.named_parameters()
+                     if k in ("base.model.conv1.weight", "base.model.layer2.0.downsample.0.weight", "base.model.layer4.1.bn2.weight",
+                              "cnn.0.weight", "cnn.1.bias", "cnn.4.weight", "cnn.4.bias")}
+        opt.step()
+        steps.append({"loss": float(loss), "prob": prob.detach().clone()})
+    sd = net.state_dict()
+    torch.save({"seed": 16, "batch_seeds": (300, 301), "steps": steps, "grads": grads,
+                "w_after": sd["base.model.layer1.0.conv1.weight"][:4, :4].clone(), "keys": list(sd.keys())},
+               os.path.join(HERE, "siamese_step.pt"))
+    print("siamese:", [s_["loss"] for s_ in steps])
+
+
+def golden_step_bayesian():
+    """One WSGANEmbModel.optimize_parameters() in the Bayesian + noisy encoder mode (BASELINE config 4:
+    --bayesian true --noisy true --noisy_var_type ae --bnn_dropout 0.2) at a small size (64 x 64, fineSize_E 64, T = 2,
+    resnet_6blocks) with every random draw recorded: the Dropout2d masks and the util.resample normals."""
+    from models import networks
+    tmp = tempfile.mkdtemp()
+    e0 = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7, gpu_ids=[],
+                           noisy=True, bnn_dropout=0.2)
+    pth = os.path.join(tmp, "e.pth")
+    torch.save(e0.state_dict(), pth)
+    argv = sys.argv
+    sys.argv = ["x", "--model", "wsgan_emb", "--gpu_ids", "-1", "--which_model_netG", "resnet_6blocks", "--n_layers_D", "3",
+                "--batchSize", "2", "--lambda_IP", "0", "--pretrained_model_path_E", pth, "--sourcefile_A", pth, "--dataroot", tmp,
+                "--embedding_bins", "[-2,-1,0,1,2]", "--checkpoints_dir", tmp, "--name", "golden_b", "--fineSize", "64", "--loadSize", "64",
+                "--fineSize_E", "64", "--bayesian", "true", "--noisy", "true", "--noisy_var_type", "ae", "--bnn_dropout", "0.2", "--bnn_T", "2"]
+    try:
+        from options.train_options import TrainOptions
+        from models import create_model
+        opt = TrainOptions().parse()
+        model = create_model(opt)
+        model.setup(opt)
+    finally:
+        sys.argv = argv
+    O.fill_state_dict_(model.netG.state_dict(), 41)
+    O.fill_state_dict_(model.netD.state_dict(), 42)
+    O.fill_state_dict_(model.netE.state_dict(), 43)
+    masks, eps = [], []
+    _record_dropout(model.netE, masks)
+    orig_randn_like = torch.randn_like
+
+    def rec_randn_like(t, *a, **k):
+        e = orig_randn_like(t, *a, **k)
+        eps.append(e.detach().clone())
+        return e
+    torch.manual_seed(7)
+    a, b, label = O.synthetic_batch(2, 64, 400)
+    torch.randn_like = rec_randn_like
+    try:
+        model.set_input({"A": a, "B": b, "label": label, "A_paths": ["a"] * 2, "B_paths": ["b"] * 2})
+        model.optimize_parameters()
+    finally:
+        torch.randn_like = orig_randn_like
+    losses = {k: float(v) for k, v in model.get_current_losses().items()}
+    torch.save({"seeds": (41, 42, 43), "batch_seed": 400, "masks": masks, "eps": eps, "losses": losses, "y_b": model.y_B.clone(),
+                "fake_b_sub": sub(model.fake_B.detach(), 4),
+                "g_w_after": model.netG.state_dict()["model.10.conv_block.1.weight"][:4, :4].clone()},
+               os.path.join(HERE, "step_bayesian.pt"))
+    print("bayesian step:", losses, len(masks), "masks", len(eps), "eps")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "new":     # only the fixtures added later (the others are unchanged)
+        golden_encoder_dropout()
+        golden_siamese_step()
+        golden_step_bayesian()
+        sys.exit(0)
     golden_losses()
     golden_generator()
     golden_discriminator()
     golden_encoder()
     golden_step()
+    golden_encoder_dropout()
+    golden_siamese_step()
+    golden_step_bayesian()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -221,7 +221,8 @@ def test_encoder_basic_block_teacher_forced(stride, cin, c, h):
     ybuf = blk.forward(xbuf, w)
     ho = h // stride
     y = ybuf[: blk.g_y.numel].view(N, ho + 2, ho + 2, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float()
-    sd = {"b." + k: v.detach().clone() for k, v in holder.state_dict().items()}
+    sd = {"b." + k: (v.detach().clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k else v.detach().clone())
+          for k, v in holder.state_dict().items()}
     for k in sd:
         if "running_mean" in k: sd[k].zero_()
         if "running_var" in k: sd[k].fill_(1)
@@ -231,8 +232,17 @@ def test_encoder_basic_block_teacher_forced(stride, cin, c, h):
     gy = bf(torch.randn_like(yr))
     yr.backward(gy)
     gybuf = torch.cat([gy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).reshape(-1), torch.zeros(512, dtype=torch.bfloat16, device=DEV)])
-    gx = blk.backward(xbuf, w, gybuf, _Scratch(DEV))
+    for q in holder.parameters():
+        q.requires_grad_(True)
+    gx = blk.backward(xbuf, w, gybuf, _Scratch(DEV), need_w=True)
     gxt = gx[: N * h * h * cin].view(N, h, h, cin).permute(0, 3, 1, 2).float()
     e_f, e_b = rel(y, yr), rel(gxt, xr.grad)
     print("BasicBlock stride %d %d->%d: fwd %.3e dgrad %.3e" % (stride, cin, c, e_f, e_b))
     assert e_f < 1e-2 and e_b < 8e-2   # backward: ReLU-mask flips from the bf16 rounding of the stored pre-activations (sqrt law)
+    # weight and BatchNorm-parameter gradients of the same block (the siamese trainer's backward, siamese.py:677)
+    ref = {k[2:]: v for k, v in sd.items()}
+    wk = {}
+    for name, q in holder.named_parameters():
+        wk[name] = rel(q.grad, ref[name].grad)
+    print({k: "%.2e" % v for k, v in wk.items()})
+    assert max(wk.values()) < 8e-2, wk

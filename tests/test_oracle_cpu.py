@@ -119,3 +119,61 @@ def test_two_training_steps_match_reference():
             assert close(m.y_b, fx["extra"]["y_b"], 1e-4)
             assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["extra"]["g_w_after"], 1e-4)
             assert close(m.d["model.2.weight"][:4, :4], fx["extra"]["d_w_after"], 1e-4)
+
+
+def test_encoder_with_dropout_and_noisy_head():
+    """Live nn.Dropout2d (resnet.py:58-65, networks.py:1022) + cnn_logvar twin head: the reference's recorded masks
+    replayed through the oracle."""
+    fx = load("encoder_dropout.pt")
+    sd = O.make_state_dict(O.encoder_keys(noisy=True), fx["seed"])
+    a, _, _ = O.synthetic_batch(2, 64, fx["x_seed"])
+    a.requires_grad_(True)
+    masks = [m.clone() for m in fx["masks"]]
+
+    def drop(t):
+        return t * masks.pop(0).view(t.size(0), t.size(1), 1, 1)
+
+    y, lv = O.encoder_forward(sd, a, cnn_relu_slope=0.7, noisy=True, drop=drop)
+    assert not masks, "every recorded mask must be consumed"
+    assert close(y, fx["y"], 1e-4) and close(lv, fx["logvar"], 1e-4)
+    (y * torch.tensor([1.0, -2.0]).view(2, 1, 1, 1) + lv * torch.tensor([0.5, 0.25]).view(2, 1, 1, 1)).sum().backward()
+    assert close(a.grad[..., ::4, ::4], fx["dx_sub"], 1e-3) and close(a.grad.norm(), fx["dx_norm"], 1e-3)
+
+
+def test_siamese_elo_training_steps_match_reference():
+    """siamese.py:590-686 (plain branch): two Adam steps of SiameseNetwork + BinaryNLLLoss."""
+    fx = load("siamese_step.pt")
+    sd = O.make_state_dict(O.encoder_keys(), fx["seed"], requires_grad=True)
+    assert list(sd.keys()) == fx["keys"]
+    m = O.SiameseOracle(sd, lr=2e-4, cnn_relu_slope=0.7)
+    for it, want in enumerate(fx["steps"]):
+        a, b, label = O.synthetic_batch(4, 64, fx["batch_seeds"][it])
+        loss, prob = m.step(a, b, label)
+        assert abs(loss - want["loss"]) <= 1e-4 * abs(want["loss"]), (it, loss, want["loss"])
+        assert close(prob, want["prob"], 1e-3)
+        if it == 0:   # .grad still holds the first step's gradients (Adam does not clear them)
+            for k, g in fx["grads"].items():
+                mine = sd[k].grad[:6] if sd[k].grad.dim() == 4 else sd[k].grad
+                assert close(mine, g, 2e-3), k
+    assert close(sd["base.model.layer1.0.conv1.weight"][:4, :4], fx["w_after"], 1e-3)
+
+
+def test_bayesian_noisy_step_matches_reference():
+    """BASELINE config 4 (--bayesian true --noisy true --noisy_var_type ae --bnn_dropout 0.2) at 64 x 64, T = 2: every
+    Dropout2d mask and resample draw of the reference replayed through the oracle."""
+    fx = load("step_bayesian.pt")
+    sg, sdd, se = fx["seeds"]
+    m = O.WSGANEmbOracle(O.make_state_dict(O.generator_keys(n_blocks=6), sg, requires_grad=True),
+                         O.make_state_dict(O.discriminator_keys(), sdd, requires_grad=True),
+                         O.make_state_dict(O.encoder_keys(noisy=True), se), n_blocks=6, fine_size_e=64, bayesian=True, noisy=True,
+                         noisy_var_type="ae", bnn_T=2, dropout=True, drop_masks=[x.clone() for x in fx["masks"]],
+                         eps_queue=[x.clone() for x in fx["eps"]])
+    a, b, label = O.synthetic_batch(2, 64, fx["batch_seed"])
+    got = m.optimize_parameters(a, b, label)
+    assert not m.drop_masks and not m.eps_queue
+    for k, v in fx["losses"].items():
+        if k in got:
+            assert abs(got[k] - v) <= 2e-3 * abs(v) + 1e-5, (k, got[k], v)
+    assert close(m.y_b, fx["y_b"], 1e-3)
+    assert close(m.fake_b.detach()[..., ::4, ::4], fx["fake_b_sub"], 1e-3)
+    assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["g_w_after"], 1e-3)
