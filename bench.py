@@ -234,6 +234,7 @@ def main():
     nprof = 2
     if rank == 0:
         ops.Stats.igemm_events = []
+        ops.Stats.op_events = [] if args.dump_igemm else None
     was_graph, model.use_graph = model.use_graph, False     # per-launch events need the launches to come from Python
     for i in range(nprof):
         step(resident[i % pool])
@@ -242,7 +243,17 @@ def main():
     if rank == 0:
         ev = ops.Stats.igemm_events
         ops.Stats.igemm_events = None
+        op_ev, ops.Stats.op_events = ops.Stats.op_events, None
         if args.dump_igemm:
+            oagg = {}
+            for name, a, b in op_ev:
+                d = oagg.setdefault(name, [0, 0.0])
+                d[0] += 1; d[1] += a.elapsed_time(b)
+            with open(args.dump_igemm + ".ops", "w") as fh:
+                tot = sum(v[1] for v in oagg.values()) / nprof
+                fh.write("# non-igemm kernels of one step, CUDA events around each launch (includes ~2 us of launch latency each): %.3f ms\n" % tot)
+                for name, (n, t) in sorted(oagg.items(), key=lambda kv: -kv[1][1]):
+                    fh.write("%-24s n=%4d  %8.3f ms/step\n" % (name, n / nprof, t / nprof))
             agg = {}
             for note, f, a, b in ev:
                 d = agg.setdefault(note, [0, 0.0, 0])

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 6
+#define PCGAN_ABI_VERSION 7
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -135,6 +135,11 @@ typedef struct {
   int32_t m_valid;     /* Cout                                             */
   int32_t wg_ncols;    /* valid columns per tap (Cin or packed row width)  */
   int64_t ldo;         /* output row pitch in elements                     */
+  /* 1: launch as thread-block clusters of two CTAs that take two M tiles of the same N tile (tap, K split) and share the
+   * B operand: each CTA fetches half of it and TMA-multicasts it into both, which cuts the L2 -> shared-memory traffic
+   * of a 128x256 tile from 48 to 32 KB per K chunk (the L2 read bandwidth, not the tensor pipe, bounds these tiles).
+   * KMAJOR: any shape (an odd M-tile count recomputes and drops one tile); WGRAD: m_tiles and block_n/64 must be even. */
+  int32_t pair;
 } pcgan_igemm_desc;
 
 typedef struct pcgan_igemm_plan pcgan_igemm_plan;

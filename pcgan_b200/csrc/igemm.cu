@@ -46,6 +46,8 @@ struct DevParams {
   int32_t a_base[4], a_step[4][4];
   int32_t b_base[4], b_step[4][4];
   int32_t n_tiles, m_tiles, ksplit, num_m_tiles, total_tiles;
+  int32_t pair;        // 1: launched as clusters of 2 CTAs that work on two M tiles of the same N tile and share the B operand
+  int32_t sched_items; // work items per CTA slot schedule: tiles, or pair-tiles when pair
   int32_t num_taps, cchunks;
   int32_t tap_off[PCGAN_MAX_TAPS][4];
   int32_t tap_c0[PCGAN_MAX_TAPS];
@@ -94,6 +96,41 @@ __device__ __forceinline__ int32_t tile_group(const DevParams& P, const Digits& 
   return P.stats_comp == 0 ? s0 : s1;
 }
 
+// ------------------------------------------------------------------ schedule
+// A CTA (or CTA pair) owns a contiguous range of work items.  Unpaired: item = tile.  Paired: item = two M tiles
+// (2*m2 + rank) of the same N tile [, tap, K split]; the odd one out of an odd M-tile count is computed twice and
+// dropped (`valid` false).
+struct Sched {
+  int32_t begin, end;
+  uint32_t rank;   // CTA rank in the pair (0 when unpaired)
+};
+__device__ __forceinline__ Sched make_sched(const DevParams& P) {
+  Sched s;
+  const int32_t slots = P.pair ? static_cast<int32_t>(gridDim.x >> 1) : static_cast<int32_t>(gridDim.x);
+  const int32_t slot = P.pair ? static_cast<int32_t>(blockIdx.x >> 1) : static_cast<int32_t>(blockIdx.x);
+  s.begin = static_cast<int32_t>(static_cast<int64_t>(P.sched_items) * slot / slots);
+  s.end = static_cast<int32_t>(static_cast<int64_t>(P.sched_items) * (slot + 1) / slots);
+  s.rank = P.pair ? cluster_ctarank() : 0u;
+  return s;
+}
+__device__ __forceinline__ void kmajor_item(const DevParams& P, const Sched& sc, int32_t item, int32_t& mt, int32_t& nt, bool& valid) {
+  const int32_t q = item / P.n_tiles;
+  nt = item - q * P.n_tiles;
+  mt = P.pair ? 2 * q + static_cast<int32_t>(sc.rank) : q;
+  valid = mt < P.num_m_tiles;
+  if (!valid) mt = P.num_m_tiles - 1;
+}
+__device__ __forceinline__ void wgrad_item(const DevParams& P, const Sched& sc, int32_t item, int32_t& ks, int32_t& nt, int32_t& mt,
+                                           int32_t& tap) {
+  int32_t t = item;
+  ks = t % P.ksplit; t /= P.ksplit;
+  nt = t % P.n_tiles; t /= P.n_tiles;
+  const int32_t mdiv = P.pair ? (P.m_tiles >> 1) : P.m_tiles;
+  const int32_t m2 = t % mdiv; t /= mdiv;
+  mt = P.pair ? 2 * m2 + static_cast<int32_t>(sc.rank) : m2;
+  tap = t;
+}
+
 struct EpiShared {
   float* s_bias;       // this group's [256]
   float* s_acc;        // this group's [256][2]
@@ -116,8 +153,7 @@ __device__ __forceinline__ float act_ct(float x, float slope) {
 // (+bias, statistics, activation) -> global.  Thread = one accumulator row (output pixel), 32 fp32 columns per
 // tcgen05.ld.  The two groups of a CTA alternate tiles, each on its own TMEM stage.
 template <int ACT, bool BF16, bool STATS>
-__device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiShared es, uint32_t tmem_base, int32_t tile_begin,
-                                                int32_t tile_end) {
+__device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiShared es, uint32_t tmem_base, const Sched sch) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q = warp & 3;
   const uint32_t row = q * 32 + lane;
@@ -158,11 +194,12 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
     named_bar_sync(bar_stats, 128);
   };
 
-  for (int32_t tile = tile_begin + static_cast<int32_t>(es.group); tile < tile_end; tile += kEpiGroups) {
-    const int32_t mt = tile / n_tiles;
-    const int32_t nt = tile - mt * n_tiles;
+  for (int32_t tile = sch.begin + static_cast<int32_t>(es.group); tile < sch.end; tile += kEpiGroups) {
+    int32_t mt, nt;
+    bool tile_valid;
+    kmajor_item(P, sch, tile, mt, nt, tile_valid);
     const Digits d = decompose(mt, P.t_count);
-    bool valid = row_in_box;
+    bool valid = row_in_box && tile_valid;
     int64_t off = 0;
 #pragma unroll
     for (int dim = 0; dim < 4; ++dim) {
@@ -285,30 +322,27 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
 
 template <int ACT>
 __device__ __forceinline__ void epi_dispatch(bool bf16, bool stats, const DevParams& P, const EpiShared& es, uint32_t tmem_base,
-                                             int32_t tile_begin, int32_t tile_end) {
+                                             const Sched& sch) {
   if (bf16) {
-    if (stats) epilogue_kmajor<ACT, true, true>(P, es, tmem_base, tile_begin, tile_end);
-    else epilogue_kmajor<ACT, true, false>(P, es, tmem_base, tile_begin, tile_end);
+    if (stats) epilogue_kmajor<ACT, true, true>(P, es, tmem_base, sch);
+    else epilogue_kmajor<ACT, true, false>(P, es, tmem_base, sch);
   } else {
-    if (stats) epilogue_kmajor<ACT, false, true>(P, es, tmem_base, tile_begin, tile_end);
-    else epilogue_kmajor<ACT, false, false>(P, es, tmem_base, tile_begin, tile_end);
+    if (stats) epilogue_kmajor<ACT, false, true>(P, es, tmem_base, sch);
+    else epilogue_kmajor<ACT, false, false>(P, es, tmem_base, sch);
   }
 }
 
 // Weight-gradient epilogue: fp32 partial tiles added into the packed gradient with vector reductions.
-__device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShared es, uint32_t tmem_base, int32_t tile_begin,
-                                               int32_t tile_end, int32_t total_kb, int32_t kb_per_split) {
+__device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShared es, uint32_t tmem_base, const Sched sch,
+                                               int32_t total_kb, int32_t kb_per_split) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q = warp & 3;
   const uint32_t row = q * 32 + lane;
   const int32_t block_n = P.block_n;
   uint32_t acc_phase = 0;
-  for (int32_t tile = tile_begin + static_cast<int32_t>(es.group); tile < tile_end; tile += kEpiGroups) {
-    int32_t t = tile;
-    const int32_t ks = t % P.ksplit; t /= P.ksplit;
-    const int32_t nt = t % P.n_tiles; t /= P.n_tiles;
-    const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
-    const int32_t tap = t;
+  for (int32_t tile = sch.begin + static_cast<int32_t>(es.group); tile < sch.end; tile += kEpiGroups) {
+    int32_t ks, nt, mt, tap;
+    wgrad_item(P, sch, tile, ks, nt, mt, tap);
     const int32_t grow = mt * 128 + row;
     const bool valid = grow < P.m_valid && ks * kb_per_split < total_kb;
     const int32_t ncol_limit = min(P.wg_ncols - nt * block_n, block_n);
@@ -367,7 +401,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], P.pair ? 2 : 1);   // paired: the peer multicasts into this stage too, both MMA warps release it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -385,30 +419,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (P.pair) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast or committed to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int32_t k_chunks_fwd = P.num_taps * P.cchunks;
   const int32_t total_kb = P.t_count[0] * P.t_count[1] * P.t_count[2] * P.t_count[3];  // WGRAD: pixel blocks
   const int32_t kb_per_split = wgrad ? (total_kb + P.ksplit - 1) / P.ksplit : 0;
-  // static schedule: every CTA owns one contiguous range of tiles (neighbouring tiles share halos in L2 and, for
+  // static schedule: every CTA (pair) owns one contiguous range of tiles (neighbouring tiles share halos in L2 and, for
   // per-sample statistics, usually the same sample, so the statistics are flushed once per sample, not per tile)
-  const int32_t tile_begin = static_cast<int32_t>(static_cast<int64_t>(P.total_tiles) * blockIdx.x / gridDim.x);
-  const int32_t tile_end = static_cast<int32_t>(static_cast<int64_t>(P.total_tiles) * (blockIdx.x + 1) / gridDim.x);
+  const Sched sch = make_sched(P);
+  const uint16_t pair_mask = 0x3;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the (uniform) schedule; one elected lane issues the copies.
     int32_t stage = 0;
     uint32_t phase = 0;
-    for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
+    for (int32_t tile = sch.begin; tile < sch.end; ++tile) {
       if (!wgrad) {
-        const int32_t mt = tile / P.n_tiles, nt = tile % P.n_tiles;
+        int32_t mt, nt;
+        bool tile_valid;
+        kmajor_item(P, sch, tile, mt, nt, tile_valid);
         const Digits d = decompose(mt, P.t_count);
         int32_t c[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
         const uint32_t bytes = P.a_rows * 128 + P.block_n * 128;
+        const int32_t half_rows = P.block_n >> 1;   // paired: this CTA fetches rows [rank*half, +half) of B for both
         for (int32_t tap = 0; tap < P.num_taps; ++tap) {
           const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
                         o3 = P.tap_off[tap][3];
@@ -419,18 +457,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full_bar[stage], bytes);
               tma_load_5d(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
-              tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+              if (P.pair)
+                tma_load_5d_multicast(sa + P.a_alloc + sch.rank * half_rows * 128, &tma_b, &full_bar[stage], bk0 + cc * 64,
+                                      nt * P.block_n + sch.rank * half_rows, 0, 0, 0, pair_mask);
+              else
+                tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
             }
             __syncwarp();
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       } else {
-        int32_t t = tile;
-        const int32_t ks = t % P.ksplit; t /= P.ksplit;
-        const int32_t nt = t % P.n_tiles; t /= P.n_tiles;
-        const int32_t mt = t % P.m_tiles; t /= P.m_tiles;
-        const int32_t tap = t;
+        int32_t ks, nt, mt, tap;
+        wgrad_item(P, sch, tile, ks, nt, mt, tap);
         const int32_t kb0 = ks * kb_per_split;
         const int32_t kb1 = min(kb0 + kb_per_split, total_kb);
         const int32_t nb = P.block_n >> 6;
@@ -450,8 +489,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
-            for (int j = 0; j < nb; ++j)
-              tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3);
+            if (P.pair) {   // the X boxes are the same for both M tiles: each CTA fetches every other one for both
+              for (int j = static_cast<int>(sch.rank); j < nb; j += 2)
+                tma_load_5d_multicast(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3,
+                                      pair_mask);
+            } else {
+              for (int j = 0; j < nb; ++j)
+                tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3);
+            }
           }
           __syncwarp();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -469,7 +514,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
     int32_t stage = 0;
     uint32_t phase = 0, acc = 0, acc_phase = 0;
-    for (int32_t tile = tile_begin; tile < tile_end; ++tile) {
+    for (int32_t tile = sch.begin; tile < sch.end; ++tile) {
       int32_t nk;
       if (!wgrad) {
         nk = k_chunks_fwd;
@@ -491,7 +536,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k)
             umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
-          tcgen05_commit(&empty_bar[stage]);
+          if (P.pair) tcgen05_commit_multicast(&empty_bar[stage], pair_mask);
+          else tcgen05_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -505,24 +551,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t eg = (warp - 4) >> 2;
     EpiShared es{s_bias + eg * 256, s_acc + eg * 512, s_tr + (warp - 4) * (32 * 17), &tmem_full[eg], &tmem_empty[eg], eg};
     if (wgrad) {
-      epilogue_wgrad(P, es, tmem_base, tile_begin, tile_end, total_kb, kb_per_split);
+      epilogue_wgrad(P, es, tmem_base, sch, total_kb, kb_per_split);
     } else {
       const bool bf = P.out_dtype == PCGAN_DT_BF16;
       const bool st = P.stats_mode != PCGAN_STATS_NONE;
       // one specialised copy of the tile loop per (activation, output type, statistics): the per-element code is
       // straight-line, nothing about the layer is decided inside the column loops
       switch (P.act) {
-        case PCGAN_ACT_RELU: epi_dispatch<PCGAN_ACT_RELU>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
-        case PCGAN_ACT_LRELU: epi_dispatch<PCGAN_ACT_LRELU>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
-        case PCGAN_ACT_TANH: epi_dispatch<PCGAN_ACT_TANH>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
-        case PCGAN_ACT_SIGMOID: epi_dispatch<PCGAN_ACT_SIGMOID>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
-        default: epi_dispatch<PCGAN_ACT_NONE>(bf, st, P, es, tmem_base, tile_begin, tile_end); break;
+        case PCGAN_ACT_RELU: epi_dispatch<PCGAN_ACT_RELU>(bf, st, P, es, tmem_base, sch); break;
+        case PCGAN_ACT_LRELU: epi_dispatch<PCGAN_ACT_LRELU>(bf, st, P, es, tmem_base, sch); break;
+        case PCGAN_ACT_TANH: epi_dispatch<PCGAN_ACT_TANH>(bf, st, P, es, tmem_base, sch); break;
+        case PCGAN_ACT_SIGMOID: epi_dispatch<PCGAN_ACT_SIGMOID>(bf, st, P, es, tmem_base, sch); break;
+        default: epi_dispatch<PCGAN_ACT_NONE>(bf, st, P, es, tmem_base, sch); break;
       }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (P.pair) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -634,6 +681,9 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   }
   int64_t total = wg ? (int64_t)d->num_taps * d->m_tiles * d->n_tiles * d->ksplit : tiles * d->n_tiles;
   if (total < 1 || total > 0x7fffffff) return fail(PCGAN_ERR_INVALID, "tile count out of range");
+  if (d->pair != 0 && d->pair != 1) return fail(PCGAN_ERR_INVALID, "pair must be 0 or 1");
+  if (d->pair && wg && (d->m_tiles % 2 != 0 || (d->block_n / 64) % 2 != 0))
+    return fail(PCGAN_ERR_INVALID, "paired WGRAD needs an even m_tiles and an even number of 64-column B boxes");
 
   pcgan_igemm_plan* p = new pcgan_igemm_plan();
   p->desc = *d;
@@ -655,6 +705,8 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   memcpy(v.b_base, d->b_base, sizeof(v.b_base)); memcpy(v.b_step, d->b_step, sizeof(v.b_step));
   v.n_tiles = d->n_tiles; v.m_tiles = wg ? d->m_tiles : 1; v.ksplit = wg ? d->ksplit : 1;
   v.num_m_tiles = (int32_t)tiles; v.total_tiles = (int32_t)total;
+  v.pair = d->pair;
+  v.sched_items = !d->pair ? (int32_t)total : (wg ? (int32_t)(total / 2) : (int32_t)(((tiles + 1) / 2) * d->n_tiles));
   v.num_taps = d->num_taps; v.cchunks = d->cchunks;
   memcpy(v.tap_off, d->tap_off, sizeof(v.tap_off)); memcpy(v.tap_c0, d->tap_c0, sizeof(v.tap_c0));
   memcpy(v.tap_bk, d->tap_bk, sizeof(v.tap_bk));
@@ -694,19 +746,43 @@ extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b
       p->cached_a = a;
     }
     if (p->cached_b != b) {
-      int rc = encode_tmap(&p->map_b, p->desc.b, b);
+      pcgan_tmap tb = p->desc.b;
+      if (p->desc.pair && p->desc.kind == PCGAN_IGEMM_KMAJOR) tb.box[1] = p->desc.block_n / 2;   // each CTA of a pair fetches half of B
+      int rc = encode_tmap(&p->map_b, tb, b);
       if (rc != PCGAN_OK) return rc;
       p->cached_b = b;
     }
     if (p->grid == 0) {
       int sms = sm_count();
       if (sms <= 0) return fail(PCGAN_ERR_CUDA, "cannot query SM count");
-      p->grid = p->dev.total_tiles < sms ? p->dev.total_tiles : sms;
+      if (!p->desc.pair) {
+        p->grid = p->dev.total_tiles < sms ? p->dev.total_tiles : sms;
+      } else {
+        const int pairs = p->dev.sched_items < sms / 2 ? p->dev.sched_items : sms / 2;
+        p->grid = 2 * pairs;
+      }
     }
     ma = p->map_a; mb = p->map_b; dev = p->dev;
   }
   dev.out = out; dev.bias = bias; dev.stats = stats;
-  igemm_kernel<<<p->grid, kNumThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, dev);
+  if (!p->desc.pair) {
+    igemm_kernel<<<p->grid, kNumThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, dev);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel, ma, mb, dev);
+    if (e != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaLaunchKernelEx(igemm_kernel, cluster 2): %s", cudaGetErrorString(e));
+  }
   PCGAN_LAUNCH_OK("igemm_kernel");
   return PCGAN_OK;
 }

@@ -30,10 +30,31 @@ class Stats:
     igemm_launches = 0
     igemm_events = None
     igemm_flops = 0
+    op_events = None
 
 
 def _count(n=1):
     Stats.launches += n
+
+
+class _Timed:
+    """When Stats.op_events is a list, every wrapped launch is bracketed by CUDA events (bench.py's per-kernel table)."""
+
+    def __init__(self, name):
+        self.name, self.e0 = name, None
+
+    def __enter__(self):
+        if Stats.op_events is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            Stats.op_events.append((self.name, self.e0, e1))
+        return False
 
 
 class Igemm:
@@ -77,12 +98,14 @@ def alloc_act(g: Geom, device, zero=True):
 
 def gather_cast_bf16(src, idx, dst):
     _count()
-    L.check(L.load().pcgan_gather_cast_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_cast_bf16")
+    with _Timed("gather_cast_bf16"):
+        L.check(L.load().pcgan_gather_cast_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_cast_bf16")
 
 
 def scatter_f32(src, idx, dst, accumulate=False):
     _count()
-    L.check(L.load().pcgan_scatter_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), int(accumulate), _stream()), "scatter_f32")
+    with _Timed("scatter_f32"):
+        L.check(L.load().pcgan_scatter_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), int(accumulate), _stream()), "scatter_f32")
 
 
 def pack_nchw(src, dst, g: Geom, *, z=None, mul_out=None, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO):
@@ -92,7 +115,8 @@ def pack_nchw(src, dst, g: Geom, *, z=None, mul_out=None, mul_kind=L.ACT_TANH, h
     a = L.PackArgs(src=_ptr(src), z=_ptr(z), mul_out=_ptr(mul_out), mul_kind=mul_kind, dst=_ptr(dst), n=n, cs=cs, h=h, w=w,
                    ho=g.h, wo=g.w, cd=g.c, pad=g.pad, halo=halo, dst_n_stride=0)
     _count()
-    L.check(L.load().pcgan_pack_nchw(C.byref(a), _stream()), "pack_nchw")
+    with _Timed("pack_nchw"):
+        L.check(L.load().pcgan_pack_nchw(C.byref(a), _stream()), "pack_nchw")
 
 
 def unpack_resize_bwd(gbuf, g: Geom, dst, *, accumulate=False, scale=1.0):
@@ -102,7 +126,8 @@ def unpack_resize_bwd(gbuf, g: Geom, dst, *, accumulate=False, scale=1.0):
     a = L.UnpackArgs(g=_ptr(gbuf), dst=_ptr(dst), n=n, c=g.c, hs=g.h, ws=g.w, pad=g.pad, cd=cd, h=h, w=w,
                      accumulate=int(accumulate), scale=scale)
     _count()
-    L.check(L.load().pcgan_unpack_resize_bwd(C.byref(a), _stream()), "unpack_resize_bwd")
+    with _Timed("unpack_resize_bwd"):
+        L.check(L.load().pcgan_unpack_resize_bwd(C.byref(a), _stream()), "unpack_resize_bwd")
 
 
 def norm_finalize(stats, groups, c, count, *, eps=1e-5, momentum=0.1, gamma=None, beta=None, mean=None, rstd=None,
@@ -112,7 +137,8 @@ def norm_finalize(stats, groups, c, count, *, eps=1e-5, momentum=0.1, gamma=None
                            shift=_ptr(shift), running_mean=_ptr(running_mean), running_var=_ptr(running_var),
                            drop_mask=_ptr(drop_mask), in_groups=in_groups)
     _count()
-    L.check(L.load().pcgan_norm_finalize(C.byref(a), _stream()), "norm_finalize")
+    with _Timed("norm_finalize"):
+        L.check(L.load().pcgan_norm_finalize(C.byref(a), _stream()), "norm_finalize")
 
 
 def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shift=None, groups=1, res=None, res_pad=0,
@@ -123,14 +149,16 @@ def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shif
                         res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
                         drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, post_mask=_ptr(post_mask))
     _count()
-    L.check(L.load().pcgan_norm_apply(C.byref(a), _stream()), "norm_apply")
+    with _Timed("norm_apply"):
+        L.check(L.load().pcgan_norm_apply(C.byref(a), _stream()), "norm_apply")
 
 
 def halo_fold(gpad, gg: Geom, out, out_pad, *, halo=L.HALO_REFLECT, add=None, add_pad=0):
     a = L.FoldArgs(gpad=_ptr(gpad), g_pad=gg.pad, halo=halo, add=_ptr(add), add_pad=add_pad, out=_ptr(out),
                    out_pad=out_pad, n=gg.n, h=gg.h, w=gg.w, c=gg.c)
     _count()
-    L.check(L.load().pcgan_halo_fold(C.byref(a), _stream()), "halo_fold")
+    with _Timed("halo_fold"):
+        L.check(L.load().pcgan_halo_fold(C.byref(a), _stream()), "halo_fold")
 
 
 def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, scale=None, shift=None, groups=1,
@@ -147,45 +175,53 @@ def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, s
 def norm_bwd_reduce(dy, dy_pad, x, xg, **kw):
     a = _bwd_args(dy, dy_pad, x, xg, **kw)
     _count()
-    L.check(L.load().pcgan_norm_bwd_reduce(C.byref(a), _stream()), "norm_bwd_reduce")
+    with _Timed("norm_bwd_reduce"):
+        L.check(L.load().pcgan_norm_bwd_reduce(C.byref(a), _stream()), "norm_bwd_reduce")
 
 
 def norm_bwd_apply(dy, dy_pad, x, xg, **kw):
     a = _bwd_args(dy, dy_pad, x, xg, **kw)
     _count()
-    L.check(L.load().pcgan_norm_bwd_apply(C.byref(a), _stream()), "norm_bwd_apply")
+    with _Timed("norm_bwd_apply"):
+        L.check(L.load().pcgan_norm_bwd_apply(C.byref(a), _stream()), "norm_bwd_apply")
 
 
 def maxpool_fwd(x, xg: Geom, y, y_pad, idx):
     a = L.MaxpoolArgs(x=_ptr(x), x_pad=xg.pad, y=_ptr(y), y_pad=y_pad, idx=_ptr(idx), n=xg.n, h=xg.h, w=xg.w, c=xg.c)
     _count()
-    L.check(L.load().pcgan_maxpool3x3s2_fwd(C.byref(a), _stream()), "maxpool_fwd")
+    with _Timed("maxpool_fwd"):
+        L.check(L.load().pcgan_maxpool3x3s2_fwd(C.byref(a), _stream()), "maxpool_fwd")
 
 
 def maxpool_bwd(dy, dy_pad, idx, dx, dx_pad, n, h, w, c):
     _count()
-    L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, _stream()), "maxpool_bwd")
+    with _Timed("maxpool_bwd"):
+        L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, _stream()), "maxpool_bwd")
 
 
 def resize_nchw_fwd(src, dst):
     n, c, h, w = src.shape
     _count()
-    L.check(L.load().pcgan_resize_nchw_fwd(_ptr(src), _ptr(dst), n * c, h, w, dst.shape[2], dst.shape[3], _stream()), "resize_nchw_fwd")
+    with _Timed("resize_nchw_fwd"):
+        L.check(L.load().pcgan_resize_nchw_fwd(_ptr(src), _ptr(dst), n * c, h, w, dst.shape[2], dst.shape[3], _stream()), "resize_nchw_fwd")
 
 
 def resize_nchw_bwd(gdst, gsrc):
     n, c, h, w = gsrc.shape
     _count()
-    L.check(L.load().pcgan_resize_nchw_bwd(_ptr(gdst), _ptr(gsrc), n * c, h, w, gdst.shape[2], gdst.shape[3], _stream()), "resize_nchw_bwd")
+    with _Timed("resize_nchw_bwd"):
+        L.check(L.load().pcgan_resize_nchw_bwd(_ptr(gdst), _ptr(gsrc), n * c, h, w, gdst.shape[2], gdst.shape[3], _stream()), "resize_nchw_bwd")
 
 
 def loss(kind, p, target, *, per_sample=0, weight=1.0, weight_dev=None, loss_out=None, grad=None):
     a = L.LossArgs(kind=kind, p=_ptr(p), target=_ptr(target), n=p.numel(), per_sample=per_sample, weight=weight,
                    weight_dev=_ptr(weight_dev), loss=_ptr(loss_out), grad=_ptr(grad))
     _count()
-    L.check(L.load().pcgan_loss(C.byref(a), _stream()), "loss")
+    with _Timed("loss"):
+        L.check(L.load().pcgan_loss(C.byref(a), _stream()), "loss")
 
 
 def adam(p, g, m, v, lr, beta1, beta2, eps, step):
     _count()
-    L.check(L.load().pcgan_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(lr), beta1, beta2, eps, _ptr(step), _stream()), "adam")
+    with _Timed("adam"):
+        L.check(L.load().pcgan_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(lr), beta1, beta2, eps, _ptr(step), _stream()), "adam")

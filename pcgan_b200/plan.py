@@ -121,6 +121,7 @@ class IgemmSpec:
     b_k: int = 0
     flops: int = 0             # 2*MACs actually issued (incl. padding waste), for bookkeeping
     note: str = ""
+    pair: int = 0              # CTA pairs sharing the B operand through TMA multicast (include/pcgan_kernels.h)
     swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
 
     @property
@@ -154,6 +155,7 @@ class IgemmSpec:
         d.out_cstride = self.out_cstride
         d.stats_mode, d.stats_dim, d.stats_comp = self.stats_mode, self.stats_dim, self.stats_comp
         d.m_valid, d.wg_ncols, d.ldo = self.m_valid, self.wg_ncols, self.ldo
+        d.pair = self.pair
         return d
 
 
@@ -162,7 +164,9 @@ def _ceil(a, b):
 
 
 def _block_n(cout):
-    """UMMA N for `cout` output columns: multiple of 16, <= 256, minimising padded columns."""
+    """UMMA N for `cout` output columns: multiple of 16, <= 256, minimising padded columns.  (128-wide tiles were
+    measured 25 % slower per FLOP than 256-wide ones on the 256 -> 256 3x3 convolution: the A operand is re-read from
+    shared memory for half as many columns.)"""
     if cout <= 256:
         return max(16, _ceil(cout, 16) * 16)
     best = None
@@ -171,6 +175,15 @@ def _block_n(cout):
         if best is None or waste < best[0]:
             best = (waste, bn)
     return best[1]
+
+
+PAIRING = True   # CTA pairs with a multicast B operand where it pays (large N tiles, enough M tiles)
+
+
+def _pair_kmajor(s: "IgemmSpec", m_tiles: int) -> int:
+    """Pair two M tiles when the shared B tile is at least as large as an A tile (block_n >= 128) and every SM still
+    gets work."""
+    return int(PAIRING and s.block_n >= 128 and m_tiles * s.n_tiles >= 2)
 
 
 ANY = (0, 1 << 30, 0)
@@ -257,6 +270,7 @@ def plan_box(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, ho
     s.out_dtype, s.out_cstride, s.out_elem_offset = out.dtype, out.sc, out.base
     s.act, s.act_slope = act, act_slope
     s.flops = 2 * tx * ty * tn * 128 * s.n_tiles * s.block_n * len(taps) * cin
+    s.pair = _pair_kmajor(s, tx * ty * tn)
     return s
 
 
@@ -302,6 +316,7 @@ def plan_flat(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, o
     s.out_dtype, s.out_cstride, s.out_elem_offset = out.dtype, out.sc, out.base
     s.act, s.act_slope = act, act_slope
     s.flops = 2 * tiles * 128 * s.n_tiles * s.block_n * len(taps) * cin
+    s.pair = _pair_kmajor(s, tiles)
     return s
 
 
@@ -463,6 +478,7 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     total_kb = tx * ty * tn
     s.ksplit = _ksplit_for(total_kb, len(taps) * s.m_tiles * s.n_tiles)
     s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
+    s.pair = int(PAIRING and s.m_tiles % 2 == 0 and (s.block_n // 64) % 2 == 0)
     return s
 
 
