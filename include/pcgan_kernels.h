@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 7
+#define PCGAN_ABI_VERSION 8
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -140,6 +140,13 @@ typedef struct {
    * of a 128x256 tile from 48 to 32 KB per K chunk (the L2 read bandwidth, not the tensor pipe, bounds these tiles).
    * KMAJOR: any shape (an odd M-tile count recomputes and drops one tile); WGRAD: m_tiles and block_n/64 must be even. */
   int32_t pair;
+  /* KMAJOR shift-sum epilogue (shift_taps > 0): for convolutions with very few output channels (generator head 64 -> 3,
+   * data gradients towards 3/4-channel images) the horizontal filter taps move from K to N: the accumulator's columns
+   * are shift_taps groups of shift_cpad channels and the stored value of tile row i, channel c is
+   *     sum_j acc[i + j][j*shift_cpad + c]        (rows i >= a_rows - (shift_taps - 1) store nothing; tiles overlap),
+   * so each activation row is fetched once per filter ROW instead of once per filter TAP.  n_valid <= shift_cpad <= 8,
+   * shift_taps*shift_cpad <= 32 = block_n, no statistics. */
+  int32_t shift_taps, shift_cpad;
 } pcgan_igemm_desc;
 
 typedef struct pcgan_igemm_plan pcgan_igemm_plan;

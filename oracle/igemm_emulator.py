@@ -100,6 +100,14 @@ def run_kmajor(s, a_flat, b_flat, out_flat, bias=None, stats=None):
                 bc = torch.tensor([[s.tap_bk[t] + cc * 64, nt * s.block_n, 0, 0, 0]], dtype=torch.int64)
                 B = tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, bc)[0]  # [block_n, 64]
                 acc[:, :a_rows] += A @ B.t()
+        if getattr(s, "shift_taps", 0):
+            # shift-sum epilogue: out[i][c] = sum_j acc[i + j][j*cpad + c]; the last shift_taps - 1 rows store nothing
+            kw, cp = s.shift_taps, s.shift_cpad
+            sh = torch.zeros(m_tiles, 128, s.block_n, dtype=torch.float32)
+            for j in range(kw):
+                sh[:, :128 - j, :cp] += acc[:, j:, j * cp:(j + 1) * cp]
+            acc = sh
+            valid = valid & (r < a_rows - (kw - 1)).view(1, 128)
         ncols = min(s.n_valid - nt * s.block_n, s.block_n)
         if ncols <= 0:
             continue

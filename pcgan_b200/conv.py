@@ -23,7 +23,7 @@ import torch
 
 from . import _lib as L
 from .plan import (ANY, ONE, Geom, IgemmSpec, OutMap, plan_box, plan_flat, plan_packed, plan_wgrad_box,
-                   plan_wgrad_small_cout, wmap_packed, wmap_small_cout, wmap_taps, _ceil)
+                   plan_shift_flat, plan_wgrad_small_cout, wmap_packed, wmap_shift, wmap_small_cout, wmap_taps, _ceil)
 
 
 def out_size(h, k, stride, cp, transposed=False, output_padding=0):
@@ -45,6 +45,11 @@ def conv_fwd_plans(w_shape, xg: Geom, stride: int, cp: int, out: OutMap, *, tran
         ho, wo = out_size(xg.h, k, stride, cp), out_size(xg.w, k, stride, cp)
         o = xg.pad - cp
         assert o >= 0, "input buffer pad %d < conv padding %d" % (xg.pad, cp)
+        if stride == 1 and xg.c == cin and cin % 64 == 0 and cout <= 4 and 2 <= k <= 8 and not stats:
+            # few output channels (generator head, networks.py:603-605): horizontal taps in N, shift-sum epilogue
+            sp = plan_shift_flat(xg, k, k, cin, cout, [(r + o, o, r) for r in range(k)], out, (o, o + ho), (o, o + wo),
+                                 act=act, act_slope=act_slope, note=note)
+            return [(sp, wmap_shift(w_shape, k, cin))]
         if xg.c >= 64:
             assert xg.c == cin
             taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
@@ -111,6 +116,12 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
             assert dyg.c == cout
             wt = [(r, s, r * k + s) for r in range(k) for s in range(k)]
             wm = wmap_taps(w_shape, cin, wt, cout, swap=True)
+            if same and 2 * cp == k - 1 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and out.sc == 1 and out.dtype == L.DT_BF16:
+                # gradient towards a 3/4-channel image (generator stem, networks.py:578-579): shift-sum form over the
+                # shared padded grid; row t of the GEMM feeds output position t + (k - 1 - cp)
+                sp = plan_shift_flat(dyg, k, k, cout, cin, [(-(r - cp), 0, r) for r in range(k)], out, (u0, u0 + hu), (v0, v0 + wu),
+                                     out_shift=k - 1 - cp, note=note)
+                return [(sp, wmap_shift(w_shape, k, cout, dgrad=True))]
             if same and 2 * cp == k - 1:
                 # flat form over the shared padded grid: dY pixel (y, x) sits at padded (y + pad, x + pad)
                 taps = [(-(r - cp), -(s - cp), r * k + s) for r in range(k) for s in range(k)]

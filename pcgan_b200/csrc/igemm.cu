@@ -46,6 +46,7 @@ struct DevParams {
   int32_t a_base[4], a_step[4][4];
   int32_t b_base[4], b_step[4][4];
   int32_t n_tiles, m_tiles, ksplit, num_m_tiles, total_tiles;
+  int32_t shift_taps, shift_cpad;   // shift-sum epilogue (include/pcgan_kernels.h)
   int32_t pair;        // 1: launched as clusters of 2 CTAs that work on two M tiles of the same N tile and share the B operand
   int32_t sched_items; // work items per CTA slot schedule: tiles, or pair-tiles when pair
   int32_t num_taps, cchunks;
@@ -320,9 +321,124 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
   if (STATS && cur_group >= 0) flush_stats(cur_group, cur_nt);
 }
 
+// Shift-sum epilogue (few output channels, horizontal taps in N): out[i][c] = sum_j acc[i + j][j*cpad + c].  The 128
+// accumulator rows of the group meet in a [128][17] shared tile, 16 columns at a time.
+template <int ACT, bool BF16>
+__device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShared es, uint32_t tmem_base, const Sched sch) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = warp & 3;
+  const uint32_t row = q * 32 + lane;
+  const uint32_t bar = 5 + es.group;
+  float* tr = es.s_tr - q * (32 * 17);     // the group's four warp tiles are contiguous: [128][17]
+  const int32_t kw = P.shift_taps, cp = P.shift_cpad, nv = P.n_valid;
+  const int32_t n_tiles = P.n_tiles;
+  const int64_t cs = P.out_cstride;
+  const float slope = P.act_slope;
+  float bias[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bias[c] = (P.bias != nullptr && c < nv) ? __ldg(P.bias + c) : 0.f;
+  int32_t il[4];
+  {
+    uint32_t r = row;
+#pragma unroll
+    for (int dim = 0; dim < 4; ++dim) {
+      const int32_t bx = P.box[dim];
+      il[dim] = 0;
+      if (bx > 1) { il[dim] = r % bx; r /= bx; }
+    }
+  }
+  const bool row_out = static_cast<int32_t>(row) < P.a_rows - (kw - 1);
+  uint32_t acc_phase = 0;
+  for (int32_t tile = sch.begin + static_cast<int32_t>(es.group); tile < sch.end; tile += kEpiGroups) {
+    int32_t mt, nt;
+    bool tile_valid;
+    kmajor_item(P, sch, tile, mt, nt, tile_valid);
+    const Digits d = decompose(mt, P.t_count);
+    bool valid = row_out && tile_valid;
+    int64_t off = 0;
+#pragma unroll
+    for (int dim = 0; dim < 4; ++dim) {
+      const int32_t g = coord(d, P.e_base, P.e_step, dim) + il[dim];
+      int32_t k0 = 0, rem = g, k1, k2 = 0;
+      if (P.e_p1[dim] > 0) { k0 = g / P.e_p1[dim]; rem = g - k0 * P.e_p1[dim]; }
+      if (P.e_p2[dim] > 0) { k1 = rem / P.e_p2[dim]; k2 = rem - k1 * P.e_p2[dim]; } else { k1 = rem; }
+      const pcgan_comp& m0 = P.e_comp[dim][0];
+      const pcgan_comp& m1 = P.e_comp[dim][1];
+      const pcgan_comp& m2 = P.e_comp[dim][2];
+      valid = valid && g >= 0 && k0 >= m0.lo && k0 < m0.hi && k1 >= m1.lo && k1 < m1.hi && k2 >= m2.lo && k2 < m2.hi;
+      off += (k0 - m0.lo) * m0.stride + (k1 - m1.lo) * m1.stride + (k2 - m2.lo) * m2.stride;
+    }
+    mbar_wait(es.tmem_full, acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols;
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr, raw);
+    tmem_ld_wait();
+    // the accumulator is in registers: hand the TMEM stage back before the exchange
+    tcgen05_fence_before();
+    mbar_arrive(es.tmem_empty);
+    acc_phase ^= 1;
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      named_bar_sync(bar, 128);       // everybody has read the previous half
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tr[row * 17 + i] = __uint_as_float(raw[16 * h + i]);
+      named_bar_sync(bar, 128);
+      if (row_out) {
+        if (cp == 4) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int32_t j = (16 * h + i) >> 2;             // static after unrolling: o[] stays in registers
+            if (j < kw) o[i & 3] += tr[(row + j) * 17 + i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int32_t j = (16 * h + i) >> 3;
+            if (j < kw) o[i & 7] += tr[(row + j) * 17 + i];
+          }
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = act_ct<ACT>(o[c] + bias[c], slope);
+      if (BF16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + off;
+        if (cs == 1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          // the destination is an 8-channel NHWC pixel: channels >= n_valid are written as zeros
+          uint4 w;
+          w.x = pack_bf16x2(nv > 0 ? o[0] : 0.f, nv > 1 ? o[1] : 0.f);
+          w.y = pack_bf16x2(nv > 2 ? o[2] : 0.f, nv > 3 ? o[3] : 0.f);
+          w.z = pack_bf16x2(nv > 4 ? o[4] : 0.f, nv > 5 ? o[5] : 0.f);
+          w.w = pack_bf16x2(nv > 6 ? o[6] : 0.f, nv > 7 ? o[7] : 0.f);
+          *reinterpret_cast<uint4*>(dst) = w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < nv) dst[c * cs] = __float2bfloat16(o[c]);
+        }
+      } else {
+        float* dst = reinterpret_cast<float*>(P.out) + off;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nv) dst[c * cs] = o[c];
+      }
+    }
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_dispatch(bool bf16, bool stats, const DevParams& P, const EpiShared& es, uint32_t tmem_base,
                                              const Sched& sch) {
+  if (P.shift_taps > 0) {
+    if (bf16) epilogue_shift<ACT, true>(P, es, tmem_base, sch);
+    else epilogue_shift<ACT, false>(P, es, tmem_base, sch);
+    return;
+  }
   if (bf16) {
     if (stats) epilogue_kmajor<ACT, true, true>(P, es, tmem_base, sch);
     else epilogue_kmajor<ACT, true, false>(P, es, tmem_base, sch);
@@ -682,6 +798,12 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   int64_t total = wg ? (int64_t)d->num_taps * d->m_tiles * d->n_tiles * d->ksplit : tiles * d->n_tiles;
   if (total < 1 || total > 0x7fffffff) return fail(PCGAN_ERR_INVALID, "tile count out of range");
   if (d->pair != 0 && d->pair != 1) return fail(PCGAN_ERR_INVALID, "pair must be 0 or 1");
+  if (d->shift_taps != 0) {
+    if (wg || d->shift_taps < 1 || d->shift_taps > 8 || (d->shift_cpad != 4 && d->shift_cpad != 8) || d->shift_taps * d->shift_cpad > 32 ||
+        d->block_n != 32 || d->n_tiles != 1 || d->n_valid > d->shift_cpad || d->stats_mode != PCGAN_STATS_NONE ||
+        a_rows <= d->shift_taps - 1)
+      return fail(PCGAN_ERR_INVALID, "shift-sum epilogue: KMAJOR, block_n == 32, one N tile, shift_taps*shift_cpad <= 32, n_valid <= shift_cpad in {4, 8}, no statistics");
+  }
   if (d->pair && wg && (d->m_tiles % 2 != 0 || (d->block_n / 64) % 2 != 0))
     return fail(PCGAN_ERR_INVALID, "paired WGRAD needs an even m_tiles and an even number of 64-column B boxes");
 
@@ -706,6 +828,7 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   v.n_tiles = d->n_tiles; v.m_tiles = wg ? d->m_tiles : 1; v.ksplit = wg ? d->ksplit : 1;
   v.num_m_tiles = (int32_t)tiles; v.total_tiles = (int32_t)total;
   v.pair = d->pair;
+  v.shift_taps = d->shift_taps; v.shift_cpad = d->shift_cpad;
   v.sched_items = !d->pair ? (int32_t)total : (wg ? (int32_t)(total / 2) : (int32_t)(((tiles + 1) / 2) * d->n_tiles));
   v.num_taps = d->num_taps; v.cchunks = d->cchunks;
   memcpy(v.tap_off, d->tap_off, sizeof(v.tap_off)); memcpy(v.tap_c0, d->tap_c0, sizeof(v.tap_c0));

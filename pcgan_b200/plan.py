@@ -121,6 +121,8 @@ class IgemmSpec:
     b_k: int = 0
     flops: int = 0             # 2*MACs actually issued (incl. padding waste), for bookkeeping
     note: str = ""
+    shift_taps: int = 0        # shift-sum epilogue: horizontal taps carried in N (include/pcgan_kernels.h)
+    shift_cpad: int = 0
     pair: int = 0              # CTA pairs sharing the B operand through TMA multicast (include/pcgan_kernels.h)
     swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
 
@@ -156,6 +158,7 @@ class IgemmSpec:
         d.stats_mode, d.stats_dim, d.stats_comp = self.stats_mode, self.stats_dim, self.stats_comp
         d.m_valid, d.wg_ncols, d.ldo = self.m_valid, self.wg_ncols, self.ldo
         d.pair = self.pair
+        d.shift_taps, d.shift_cpad = self.shift_taps, self.shift_cpad
         return d
 
 
@@ -318,6 +321,67 @@ def plan_flat(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, o
     s.flops = 2 * tiles * 128 * s.n_tiles * s.block_n * len(taps) * cin
     s.pair = _pair_kmajor(s, tiles)
     return s
+
+
+def plan_shift_flat(xg: Geom, kh: int, kw: int, cin: int, cout: int, row_taps: List[Tuple[int, int, int]], out: OutMap,
+                    yr: Tuple[int, int], xr: Tuple[int, int], *, out_shift=0, act=L.ACT_NONE, act_slope=0.0, note="") -> IgemmSpec:
+    """Few-output-channel convolution over the flattened padded grid of xg with the horizontal taps moved into N
+    ("shift-sum" epilogue): for GEMM row position t
+        partial[t][j*4 + c] = sum over filter rows (dy, dx, r) in row_taps and channels of
+                              Xpadded[t + dy*Wp + dx][:] . W[j*4 + c][r*cin : (r+1)*cin]
+    and the value stored at flat position g = t + out_shift is sum_j partial[t + j][j*4 + c], j < kw.  Tiles are 128 rows
+    stepping by 128 - (kw - 1).  Positions with yr[0] <= Y < yr[1], xr[0] <= X < xr[1] are stored at
+    out(n, Y - yr[0], X - xr[0]).  Every activation row is fetched kh times instead of kh*kw times."""
+    assert xg.c == cin and cin % 64 == 0 and cout <= 4 and kw * 4 <= 32
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
+    s.block_n, s.n_tiles, s.n_valid = 32, 1, cout
+    s.shift_taps, s.shift_cpad = kw, 4
+    s.cchunks = cin // 64
+    C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
+    P = N * Hp * Wp
+    S = 128 - (kw - 1)
+    s.a_dims = [C, P, 1, 1, 1]
+    s.a_strides = [0, C * 2, P * C * 2, P * C * 2, P * C * 2]
+    s.a_box = [64, 128, 1, 1, 1]
+    q_lo = yr[0] * Wp + xr[0]
+    q_hi = (N - 1) * Hp * Wp + (yr[1] - 1) * Wp + xr[1]
+    tiles = _ceil(q_hi - q_lo, S)
+    s.t_count = [tiles, 1, 1, 1]
+    s.a_base[0] = q_lo - out_shift
+    s.a_step[0][0] = S
+    for (dy, dx, r) in row_taps:
+        s.tap_off.append([dy * Wp + dx, 0, 0, 0])
+        s.tap_c0.append(0)
+        s.tap_bk.append(r * cin)
+    s.e_base[0] = q_lo
+    s.e_step[0][0] = S
+    s.e_p1[0], s.e_p2[0] = Hp * Wp, Wp
+    s.e_comp = [[(0, N, out.sn), (yr[0], yr[1], out.sy), (xr[0], xr[1], out.sx)], [ONE, ANY, ONE], [ONE, ANY, ONE], [ONE, ANY, ONE]]
+    _set_weights_tmap(s, 32, kh * cin)
+    s.out_dtype, s.out_cstride, s.out_elem_offset = out.dtype, out.sc, out.base
+    s.act, s.act_slope = act, act_slope
+    s.flops = 2 * tiles * 128 * 32 * kh * cin
+    return s
+
+
+def wmap_shift(w_shape, k: int, kdim: int, *, dgrad=False) -> torch.Tensor:
+    """Packed operand of plan_shift_flat, [32][k*kdim]: row j*4 + c, column r*kdim + q.
+    forward (OIHW, kdim = Cin):   W[c][q][r][j]
+    data gradient (kdim = Cout):  W[q][c][r][k-1-j]   (c = input channel receiving the gradient)"""
+    d0, d1 = w_shape[0], w_shape[1]
+    idx = torch.full((8, 4, k, kdim), -1, dtype=torch.int64)
+    j = torch.arange(8).view(-1, 1, 1, 1)
+    c = torch.arange(4).view(1, -1, 1, 1)
+    r = torch.arange(k).view(1, 1, -1, 1)
+    q = torch.arange(kdim).view(1, 1, 1, -1)
+    if not dgrad:
+        valid = (j < k) & (c < d0) & (q < d1)
+        flat = ((c * d1 + q) * k + r) * k + j
+    else:
+        valid = (j < k) & (c < d1) & (q < d0)
+        flat = ((q * d1 + c) * k + r) * k + (k - 1 - j)
+    idx = torch.where(valid, flat, torch.full_like(flat, -1)).expand(8, 4, k, kdim)
+    return idx.reshape(-1).to(torch.int32)
 
 
 def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho: int, wo: int, out: OutMap, *,
