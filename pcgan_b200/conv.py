@@ -116,7 +116,7 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
             assert dyg.c == cout
             wt = [(r, s, r * k + s) for r in range(k) for s in range(k)]
             wm = wmap_taps(w_shape, cin, wt, cout, swap=True)
-            if same and 2 * cp == k - 1 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and out.sc == 1 and out.dtype == L.DT_BF16:
+            if same and 2 * cp == k - 1 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and out.sc == 1:
                 # gradient towards a 3/4-channel image (generator stem, networks.py:578-579): shift-sum form over the
                 # shared padded grid; row t of the GEMM feeds output position t + (k - 1 - cp)
                 sp = plan_shift_flat(dyg, k, k, cout, cin, [(-(r - cp), 0, r) for r in range(k)], out, (u0, u0 + hu), (v0, v0 + wu),
@@ -139,6 +139,24 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
     # stride 2: input row iy = 2u + py receives taps r with (py + cp - r) even from dY row u + (py + cp - r)/2
     assert stride == 2 and dyg.c >= 64 and dyg.c == cout and not full_padded
     plans = []
+    reach = max(abs((p_ + cp - r) // 2) for p_ in range(2) for r in range(k) if (p_ + cp - r) % 2 == 0) if k > 1 else 0
+    if cin <= 4 and xg.c == 8 and 2 <= k <= 8 and dyg.pad >= max(reach, 1) and out.sc == 1:
+        # gradient towards a 3/4-channel image through a strided convolution (encoder stem, resnet.py:134): one
+        # shift-sum launch per sub-pixel phase over the zero-haloed dY grid
+        P = dyg.pad
+        for py in range(2):
+            for px in range(2):
+                rows = [r for r in range(k) if (py + cp - r) % 2 == 0]
+                cols = sorted((s for s in range(k) if (px + cp - s) % 2 == 0), key=lambda s: (px + cp - s) // 2)
+                dxo = [(px + cp - s) // 2 for s in cols]          # ascending horizontal offsets, consecutive integers
+                assert dxo == list(range(dxo[0], dxo[0] + len(dxo)))
+                hph, wph = _ceil(xg.h - py, 2), _ceil(xg.w - px, 2)
+                om = OutMap(base=out.base + py * out.sy + px * out.sx, sn=out.sn, sy=2 * out.sy, sx=2 * out.sx, sc=out.sc, dtype=out.dtype)
+                row_taps = [((py + cp - r) // 2, 0, i) for i, r in enumerate(rows)]
+                sp = plan_shift_flat(dyg, len(rows), len(cols), cout, cin, row_taps, om, (P, P + hph), (P, P + wph),
+                                     out_shift=-dxo[0], note=note)
+                plans.append((sp, wmap_shift(w_shape, k, cout, dgrad=True, rows=rows, cols=cols)))
+        return plans
     for py in range(2):
         for px in range(2):
             taps, wt = [], []

@@ -40,7 +40,7 @@ static_assert(kDataBytes + 1024 + kTailBytes <= 227 * 1024, "shared memory budge
 static constexpr int kSmemBytes = kDataBytes + 1024 /*align*/ + kTailBytes;
 
 struct DevParams {
-  int32_t kind, block_n, a_rows;
+  int32_t kind, block_n, a_rows, a_ch;
   int32_t num_stages, stage_bytes, a_alloc;
   int32_t t_count[4];
   int32_t a_base[4], a_step[4][4];
@@ -592,19 +592,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const uint32_t bytes = (2 + nb) * kBoxBytesMN;
         const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2], o3 = P.tap_off[tap][3];
         const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
+        // pixel blocks kb0 .. kb1-1 are consecutive: the mixed-radix digits are stepped, not re-divided, per block
+        Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count);
+        const int32_t a_boxes = (P.a_ch - mt * 128 + 63) / 64;   // 64-channel boxes of this M tile that exist (1 or 2)
         for (int32_t kb = kb0; kb < kb1; ++kb) {
-          const Digits d = decompose(kb, P.t_count);
           uint8_t* sa = smem + stage * P.stage_bytes;
           const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
                         a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
           const int32_t b0 = coord(d, P.b_base, P.b_step, 0) + o0, b1 = coord(d, P.b_base, P.b_step, 1) + o1,
                         b2 = coord(d, P.b_base, P.b_step, 2) + o2, b3 = coord(d, P.b_base, P.b_step, 3) + o3;
+          if (++d.t[0] == P.t_count[0]) {
+            d.t[0] = 0;
+            if (++d.t[1] == P.t_count[1]) {
+              d.t[1] = 0;
+              if (++d.t[2] == P.t_count[2]) { d.t[2] = 0; ++d.t[3]; }
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            // a box that lies entirely beyond the tensor's channels is not fetched: its rows of the tile are >= m_valid
+            // and never stored, whatever the shared memory holds
+            mbar_arrive_expect_tx(&full_bar[stage], a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
+              if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
             if (P.pair) {   // the X boxes are the same for both M tiles: each CTA fetches every other one for both
               for (int j = static_cast<int>(sch.rank); j < nb; j += 2)
                 tma_load_5d_multicast(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3,
@@ -811,7 +822,7 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   p->desc = *d;
   DevParams& v = p->dev;
   memset(&v, 0, sizeof(v));
-  v.kind = d->kind; v.block_n = d->block_n; v.a_rows = (int32_t)a_rows;
+  v.kind = d->kind; v.block_n = d->block_n; v.a_rows = (int32_t)a_rows; v.a_ch = (int32_t)d->a.dims[0];
   {
     // operand ring: as many stages as fit (small tiles get a deep ring, which is what hides the TMA latency
     // between the many short tiles of the tiny-K layers)

@@ -934,8 +934,9 @@ class _EncProgram:
         s2, s4 = S // 2, S // 4
         self.g_x0 = G(N, S, S, 8, 3)
         self.g_r0, self.g_a0 = G(N, s2, s2, 64, 0), G(N, s2, s2, 64, 0)
+        self.g_dy0 = G(N, s2, s2, 64, 2)     # zero-haloed: the stem's data gradient runs in shift-sum form over this grid
         self.g_p, self.g_pr = G(N, s4, s4, 64, 1), G(N, s4, s4, 64, 0)
-        self.stem = ConvRT("E.conv1", rn.conv1.weight, None, self.g_x0, 2, 3, OutMap.nhwc(self.g_r0), stats=True, dyg=self.g_r0,
+        self.stem = ConvRT("E.conv1", rn.conv1.weight, None, self.g_x0, 2, 3, OutMap.nhwc(self.g_r0), stats=True, dyg=self.g_dy0,
                            dx_out=OutMap.nhwc(G(N, S, S, 8, 0)), want_wgrad=False)
         self.blocks = []
         hin, cin = s4, 64
@@ -1022,8 +1023,8 @@ class _EncProgram:
         s2 = self.S // 2
         ga0 = sc.get(self.g_a0, "ga0")
         ops.maxpool_bwd(g, 0, ws.idx, ga0, 0, N, s2, s2, 64)
-        dy0 = sc.get(self.g_r0, "dy0")
-        _norm_backward(ga0, 0, ws.r0, self.g_r0, ws.n0, L.ACT_RELU, 0.0, N * s2 * s2, dy0, 0)
+        dy0 = sc.get(self.g_dy0, "dy0")
+        _norm_backward(ga0, 0, ws.r0, self.g_r0, ws.n0, L.ACT_RELU, 0.0, N * s2 * s2, dy0, self.g_dy0.pad)
         if need_w:
             _bn_param_grads(rn.bn1, ws.n0)
             self.stem.backward_weight(dy0, ws.x0)

@@ -364,23 +364,28 @@ def plan_shift_flat(xg: Geom, kh: int, kw: int, cin: int, cout: int, row_taps: L
     return s
 
 
-def wmap_shift(w_shape, k: int, kdim: int, *, dgrad=False) -> torch.Tensor:
-    """Packed operand of plan_shift_flat, [32][k*kdim]: row j*4 + c, column r*kdim + q.
-    forward (OIHW, kdim = Cin):   W[c][q][r][j]
-    data gradient (kdim = Cout):  W[q][c][r][k-1-j]   (c = input channel receiving the gradient)"""
+def wmap_shift(w_shape, k: int, kdim: int, *, dgrad=False, rows=None, cols=None) -> torch.Tensor:
+    """Packed operand of plan_shift_flat, [32][len(rows)*kdim]: row j*4 + c, column i*kdim + q, where filter row
+    r = rows[i] and filter column s = cols[j] (defaults: all k rows; forward cols[j] = j, data gradient cols[j] = k-1-j).
+    forward (OIHW, kdim = Cin):   W[c][q][r][s]
+    data gradient (kdim = Cout):  W[q][c][r][s]   (c = input channel receiving the gradient)"""
     d0, d1 = w_shape[0], w_shape[1]
-    idx = torch.full((8, 4, k, kdim), -1, dtype=torch.int64)
-    j = torch.arange(8).view(-1, 1, 1, 1)
-    c = torch.arange(4).view(1, -1, 1, 1)
-    r = torch.arange(k).view(1, 1, -1, 1)
-    q = torch.arange(kdim).view(1, 1, 1, -1)
-    if not dgrad:
-        valid = (j < k) & (c < d0) & (q < d1)
-        flat = ((c * d1 + q) * k + r) * k + j
-    else:
-        valid = (j < k) & (c < d1) & (q < d0)
-        flat = ((q * d1 + c) * k + r) * k + (k - 1 - j)
-    idx = torch.where(valid, flat, torch.full_like(flat, -1)).expand(8, 4, k, kdim)
+    rows = list(range(k)) if rows is None else list(rows)
+    if cols is None:
+        cols = list(range(k)) if not dgrad else [k - 1 - j for j in range(k)]
+    nr = len(rows)
+    idx = torch.full((8, 4, nr, kdim), -1, dtype=torch.int64)
+    c = torch.arange(4).view(-1, 1, 1)
+    r = torch.tensor(rows).view(1, -1, 1)
+    q = torch.arange(kdim).view(1, 1, -1)
+    for j, s_ in enumerate(cols):
+        if not dgrad:
+            valid = (c < d0) & (q < d1)
+            flat = ((c * d1 + q) * k + r) * k + s_
+        else:
+            valid = (c < d1) & (q < d0)
+            flat = ((q * d1 + c) * k + r) * k + s_
+        idx[j] = torch.where(valid, flat, torch.full_like(flat, -1)).expand(4, nr, kdim)
     return idx.reshape(-1).to(torch.int32)
 
 

@@ -122,6 +122,7 @@ DGRAD_CASES = [
     ("d4x4_s2", 64, 128, 128, 4, 2, 1, 1, False, 16, 2, 1),
     ("dstem4x4_s2_to4", 4, 64, 64, 4, 2, 1, 1, False, 16, 2, 0),
     ("estem7x7_s2_to3", 3, 64, 64, 7, 2, 3, 3, False, 32, 1, 0),
+    ("estem7x7_s2_to3_shift", 3, 64, 64, 7, 2, 3, 3, False, 32, 2, 2),      # zero-haloed dY: shift-sum phases
     ("e1x1_s2", 64, 128, 128, 1, 2, 0, 1, False, 8, 2, 0),
     ("stem7x7_to4_full", 4, 64, 64, 7, 1, 3, 3, True, 16, 1, 0),
 ]
