@@ -17,6 +17,7 @@ import torch.nn as nn
 from torch.nn import init
 
 from . import _lib as L
+from . import custom_ops as CO
 from . import ops
 from .engine import Arena, ConvRT, NormState, Pool, accumulate_grad, zeros_act
 from .plan import Geom, OutMap
@@ -62,33 +63,6 @@ class _Scratch:
         if k not in self.bufs:
             self.bufs[k] = zeros_act(g, self.dev)
         return self.bufs[k]
-
-
-class _Lease:
-    """A workspace borrowed by one forward call whose backward is still to come.  It goes back to the pool right after
-    that backward, or — if the graph is dropped without a backward, or the module keeps workspaces for a second backward
-    through the same graph (retain_workspaces: loss.backward(retain_graph=True), wsgan_emb_model.py:369) — when the
-    autograd node that holds the lease dies."""
-
-    def __init__(self, prog, ws):
-        self.prog, self.ws = prog, ws
-
-    def release(self):
-        if self.ws is not None:
-            self.prog.pool.give(0, self.ws)
-            self.ws = None
-
-    def __del__(self):
-        try:
-            self.release()
-        except Exception:
-            pass
-
-
-def _release(ctx, prog, ws):
-    if not getattr(prog.mod, "retain_workspaces", False):
-        ctx.lease.release()
-        ctx.ws = None
 
 
 def _require_cuda(t, who):
@@ -295,32 +269,6 @@ class _GenProgram:
         return dx, dz
 
 
-class _GenFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, x, z, *params):
-        prog = mod._program(x.shape[0], x.shape[2])
-        out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
-        # needs_input_grad already folds in the global grad mode (forward itself runs with grad disabled)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:]):
-            ctx.prog, ctx.ws, ctx.lease = prog, ws, _Lease(prog, ws)
-            ctx.save_for_backward(out)
-            ctx.need_w = any(ctx.needs_input_grad[3:])
-            ctx.z_shape = z.shape
-        else:
-            prog.pool.give(0, ws)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        (out,) = ctx.saved_tensors
-        prog, ws = ctx.prog, ctx.ws
-        dx, dz = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w, ctx.needs_input_grad[2])
-        _release(ctx, prog, ws)
-        if dz is not None:
-            dz = dz.view(ctx.z_shape)
-        return (None, dx, dz) + (None,) * (len(ctx.needs_input_grad) - 3)
-
-
 class _ResnetBlockHolder(nn.Module):
     """Parameter holder with the reference's names: conv_block.{1,5} convs, conv_block.{2,6} norms (networks.py:621-648)."""
 
@@ -357,6 +305,7 @@ class ResnetGenerator(nn.Module):
         layers += [nn.Identity(), nn.Conv2d(ngf, output_nc, 7), nn.Identity()]
         self.model = nn.Sequential(*layers)
         self._programs = {}
+        self._key = CO.register_module(self)
 
     def _program(self, n, s):
         k = (n, s, self.model[1].weight.device)
@@ -370,7 +319,9 @@ class ResnetGenerator(nn.Module):
             raise NotImplementedError("square inputs with side a multiple of 4")
         if z is None or self.nz != 1:
             raise NotImplementedError("ResnetGenerator needs the 1-channel embedding z (nz=1)")
-        return _GenFn.apply(self, input, z, *self.parameters())
+        out = torch.ops.pcgan.resnet_generator(input, z, list(self.parameters()), self._key)
+        CO.finish_forward(self._key, out)
+        return out
 
 
 # ---------------------------------------------------------------------------------------
@@ -497,32 +448,6 @@ class _DiscProgram:
         return dx, dz
 
 
-class _DiscFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, x, z, *params):
-        prog = mod._program(x.shape[0], x.shape[2])
-        out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
-        # needs_input_grad already folds in the global grad mode (forward itself runs with grad disabled)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:]):
-            ctx.prog, ctx.ws, ctx.lease = prog, ws, _Lease(prog, ws)
-            ctx.save_for_backward(out)
-            ctx.need_w = any(ctx.needs_input_grad[3:])
-            ctx.z_shape = z.shape
-        else:
-            prog.pool.give(0, ws)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        (out,) = ctx.saved_tensors
-        prog, ws = ctx.prog, ctx.ws
-        dx, dz = prog.backward(ws, out, dout.contiguous(), ctx.needs_input_grad[1], ctx.need_w, ctx.needs_input_grad[2])
-        _release(ctx, prog, ws)
-        if dz is not None:
-            dz = dz.view(ctx.z_shape)
-        return (None, dx, dz) + (None,) * (len(ctx.needs_input_grad) - 3)
-
-
 class NLayerDiscriminator(nn.Module):
     """Same constructor / forward / state_dict keys as models/networks.py:737-783 (BatchNorm2d, conditional z channel)."""
 
@@ -545,6 +470,14 @@ class NLayerDiscriminator(nn.Module):
             seq += [nn.Identity()]
         self.model = nn.Sequential(*seq)
         self._programs = {}
+        self._key = CO.register_module(self)
+
+    def out_size(self, s):
+        """side of the patch map for an s x s input: n_layers stride-2 convolutions, then two 4x4 stride-1 pad-1 ones"""
+        return s // (2 ** self.n_layers) - 2
+
+    def in_size(self, so):
+        return (so + 2) * (2 ** self.n_layers)
 
     def _program(self, n, s):
         k = (n, s, self.model[0].weight.device)
@@ -558,38 +491,22 @@ class NLayerDiscriminator(nn.Module):
             raise NotImplementedError("NLayerDiscriminator needs the embedding z")
         if input.shape[2] != input.shape[3] or input.shape[2] % (2 ** self.n_layers):
             raise NotImplementedError("square inputs with side a multiple of %d" % 2 ** self.n_layers)
-        return _DiscFn.apply(self, input, z, *self.parameters())
+        out = torch.ops.pcgan.nlayer_discriminator(input, z, list(self.parameters()), self._key)
+        CO.finish_forward(self._key, out)
+        return out
 
 
 # ---------------------------------------------------------------------------------------
 # GANLoss and the scalar losses of the step
 # ---------------------------------------------------------------------------------------
-class _LossFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, kind, pred, target, per_sample):
-        p = pred.contiguous().float()
-        out = torch.zeros((), device=p.device)
-        ops.loss(kind, p, target, per_sample=per_sample, loss_out=out)
-        ctx.kind, ctx.per_sample = kind, per_sample
-        ctx.save_for_backward(p, target)
-        return out
-
-    @staticmethod
-    def backward(ctx, gout):
-        p, target = ctx.saved_tensors
-        grad = torch.empty_like(p)
-        ops.loss(ctx.kind, p, target, per_sample=ctx.per_sample, weight=1.0, weight_dev=gout.contiguous().float(), grad=grad)
-        return None, grad, None, None
-
-
 def l1_loss(a, b):
     """nn.L1Loss() (wsgan_emb_model.py:142,149): mean |a - b|; gradient flows to `a` only (b is data)."""
-    return _LossFn.apply(L.LOSS_L1, a, b.detach().contiguous().float(), 0)
+    return torch.ops.pcgan.reduce_loss(L.LOSS_L1, a, b.detach().contiguous().float(), 0)
 
 
 def mse_loss(a, b):
     """nn.MSELoss() (wsgan_emb_model.py:148): mean (a - b)^2; gradient flows to `a` only."""
-    return _LossFn.apply(L.LOSS_MSE, a, b.detach().contiguous().float(), 0)
+    return torch.ops.pcgan.reduce_loss(L.LOSS_MSE, a, b.detach().contiguous().float(), 0)
 
 
 class GANLoss(nn.Module):
@@ -628,7 +545,7 @@ class GANLoss(nn.Module):
             n = inp.size(0)
             if t.numel() == 1 and n > 1:
                 t = t.expand(n).contiguous()
-            loss = loss + _LossFn.apply(self.kind, inp, t, inp.numel() // n)
+            loss = loss + torch.ops.pcgan.reduce_loss(self.kind, inp, t, inp.numel() // n)
         return loss
 
 
@@ -647,10 +564,10 @@ class BinaryNLLLoss(nn.Module):
         return lut[label.to(ref.device)].contiguous()
 
     def __call__(self, prob, label):
-        return _LossFn.apply(L.LOSS_ELO_NLL, prob, self._target(prob, label), prob.numel() // prob.size(0))
+        return torch.ops.pcgan.reduce_loss(L.LOSS_ELO_NLL, prob, self._target(prob, label), prob.numel() // prob.size(0))
 
     def from_score(self, score, label):
-        return _LossFn.apply(L.LOSS_ELO_NLL_SCORE, score, self._target(score, label), score.numel() // score.size(0))
+        return torch.ops.pcgan.reduce_loss(L.LOSS_ELO_NLL_SCORE, score, self._target(score, label), score.numel() // score.size(0))
 
 
 # ---------------------------------------------------------------------------------------
@@ -1037,28 +954,6 @@ class _EncProgram:
         return dx
 
 
-class _EncFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, mod, x, *params):
-        prog = mod._program(x.shape[0], x.shape[2])
-        outs, ws = prog.forward(x.contiguous().float())
-        ctx.set_materialize_grads(False)     # an unused head (logvar) then gets None instead of a zero gradient
-        ctx.need_w = any(ctx.needs_input_grad[2:])
-        if ctx.needs_input_grad[1] or ctx.need_w:
-            ctx.prog, ctx.ws, ctx.lease = prog, ws, _Lease(prog, ws)
-        else:
-            prog.pool.give(0, ws)
-        ctx.n_out = len(outs)
-        return tuple(outs)
-
-    @staticmethod
-    def backward(ctx, *gys):
-        prog, ws = ctx.prog, ctx.ws
-        dx = prog.backward(ws, list(gys), ctx.needs_input_grad[1], ctx.need_w)
-        _release(ctx, prog, ws)
-        return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
-
-
 class _BasicBlockHolder(nn.Module):
     def __init__(self, inplanes, planes, stride=1, downsample=None):
         super().__init__()
@@ -1135,6 +1030,8 @@ class SiameseFeature(nn.Module):
         self.feature_dim = 1
         self.dropout_masks = []      # test hook: explicit Dropout2d draws, consumed in module order
         self._programs = {}
+        self._key = CO.register_module(self)
+        self._last_size = 0
 
     def _program(self, n, s):
         k = (n, s, self.cnn[0].weight.device)
@@ -1146,7 +1043,10 @@ class SiameseFeature(nn.Module):
         _require_cuda(x, "SiameseFeature")
         if x.shape[1] != 3 or x.shape[2] != x.shape[3]:
             raise NotImplementedError("square RGB inputs")
-        return _EncFn.apply(self, x, *self.parameters())
+        self._last_size = int(x.shape[2])
+        y, lv = torch.ops.pcgan.siamese_feature(x, list(self.parameters()), self._key)
+        CO.finish_forward(self._key, y)
+        return (y, lv) if self._noisy else (y,)
 
     def forward(self, x):
         outs = self._run(x)
@@ -1227,28 +1127,12 @@ class Normalize(nn.Module):
         return input
 
 
-class _UpsampleFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, size):
-        x = x.contiguous().float()
-        out = torch.empty(x.shape[0], x.shape[1], size, size, device=x.device)
-        ops.resize_nchw_fwd(x, out)
-        ctx.in_shape = x.shape
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        gi = torch.empty(ctx.in_shape, device=g.device)
-        ops.resize_nchw_bwd(g.contiguous().float(), gi)
-        return gi, None
-
-
 def upsample2d(inputTensor, targetSize):
     """util.upsample2d (util/util.py:111-117): bilinear, align_corners=True; identity when sizes match."""
     if targetSize <= 0 or inputTensor.size(2) == targetSize:
         return inputTensor
     _require_cuda(inputTensor, "upsample2d")
-    return _UpsampleFn.apply(inputTensor, targetSize)
+    return torch.ops.pcgan.upsample_bilinear_ac(inputTensor, targetSize)
 
 
 NOISE_QUEUE = []   # test hook: explicit standard-normal draws for resample(), consumed in call order
