@@ -146,3 +146,32 @@ def test_cuda_graph_step_matches_eager(segments):
     bn_g, bn_e = graphed.netD.module.model[3], eager.netD.module.model[3]
     assert int(bn_g.num_batches_tracked) == int(bn_e.num_batches_tracked) == 6 * 4
     assert float((bn_g.running_mean - bn_e.running_mean).abs().max()) < 5e-2
+
+
+def test_step_at_256_and_odd_batch():
+    """BASELINE config 5 geometry (256 x 256, larger spatial tiles) and a ragged last batch (DataLoader has no drop_last,
+    SURVEY A.11): the programs are re-planned per (batch, size) and the losses match the oracle."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sds = [O.make_state_dict(k, s, device=DEV, requires_grad=rg) for k, s, rg in
+           ((O.generator_keys(), 31, True), (O.discriminator_keys(), 32, True), (O.encoder_keys(), 33, False))]
+    model = WSGANEmbModel()
+    opt = default_options(batchSize=2, gpu_ids=[0], fineSize=256, loadSize=256)
+    model.initialize(opt)
+    model.setup(opt)
+    for net, sd in zip((model.netG, model.netD, model.netE), sds):
+        net.module.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
+    oracle = O.WSGANEmbOracle(*sds)
+    for B, S, seed in ((2, 256, 900), (3, 128, 901)):
+        a, b, label = O.synthetic_batch(B, S, seed, device=DEV)
+        model.set_input({"A": a, "B": b, "label": label})
+        model.optimize_parameters()
+        got = model.get_current_losses()
+        want = oracle.optimize_parameters(a, b, label)
+        print("B=%d S=%d:" % (B, S), {k: "%.5f/%.5f" % (got[k], want[k]) for k in KEYS})
+        assert tuple(model.fake_B.shape) == (B, 3, S, S)
+        for k in KEYS:
+            if k == "z_rec":    # ~1e-3 of loss_G: the squared difference of two ~0.05 bf16 encoder outputs (see above)
+                assert abs(got[k] - want[k]) <= 0.6 * abs(want[k]) + 2e-3, (B, S, k, got[k], want[k])
+            else:
+                assert abs(got[k] - want[k]) <= 0.04 * abs(want[k]) + 1e-5, (B, S, k, got[k], want[k])
