@@ -20,6 +20,8 @@ static inline int grid_for(int64_t work_items, int per_block = kThreads, int wav
 // ------------------------------------------------------------ gather / scatter
 __global__ void gather_cast_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ dst, int64_t n) {
+  griddep_wait();
+  griddep_launch();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t j = idx[i];
     dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
@@ -27,6 +29,8 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, const int32_t*
 }
 __global__ void scatter_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
                                int64_t n, int accumulate) {
+  griddep_wait();
+  griddep_launch();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t j = idx[i];
     if (j >= 0) dst[j] = accumulate ? dst[j] + src[i] : src[i];
@@ -46,6 +50,8 @@ __device__ __forceinline__ void bilinear_setup(int o, int in, int out, int& i0, 
 }
 
 __global__ void pack_nchw_kernel(pcgan_pack_args a) {
+  griddep_wait();
+  griddep_launch();
   const int hp = a.ho + 2 * a.pad, wp = a.wo + 2 * a.pad;
   const int64_t total = static_cast<int64_t>(a.n) * hp * wp;
   const int64_t nstride = a.dst_n_stride ? a.dst_n_stride : static_cast<int64_t>(hp) * wp * a.cd;
@@ -92,6 +98,8 @@ __global__ void pack_nchw_kernel(pcgan_pack_args a) {
 }
 
 __global__ void unpack_resize_bwd_kernel(pcgan_unpack_args a) {
+  griddep_wait();
+  griddep_launch();
   const int64_t total = static_cast<int64_t>(a.n) * a.h * a.w;
   const int hsp = a.hs + 2 * a.pad, wsp = a.ws + 2 * a.pad;
   const bool resize = (a.hs != a.h) || (a.ws != a.w);
@@ -141,6 +149,8 @@ __global__ void unpack_resize_bwd_kernel(pcgan_unpack_args a) {
 
 __global__ void resize_nchw_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t planes, int h, int w,
                                        int ho, int wo) {
+  griddep_wait();
+  griddep_launch();
   const int64_t total = planes * ho * wo;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = static_cast<int>(i % wo);
@@ -156,6 +166,8 @@ __global__ void resize_nchw_fwd_kernel(const float* __restrict__ src, float* __r
 
 __global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __restrict__ gsrc, int64_t planes, int h, int w,
                                        int ho, int wo) {
+  griddep_wait();
+  griddep_launch();
   const int64_t total = planes * h * w;
   const float sy = ho > 1 ? static_cast<float>(h - 1) / static_cast<float>(ho - 1) : 0.f;
   const float sx = wo > 1 ? static_cast<float>(w - 1) / static_cast<float>(wo - 1) : 0.f;
@@ -188,6 +200,8 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __
 
 // -------------------------------------------------------------------- maxpool
 __global__ void maxpool_fwd_kernel(pcgan_maxpool_args a) {
+  griddep_wait();
+  griddep_launch();
   const int ho = (a.h + 1) / 2, wo = (a.w + 1) / 2, cv = a.c >> 3;
   const int64_t total = static_cast<int64_t>(a.n) * ho * wo * cv;
   const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(a.x);
@@ -226,6 +240,8 @@ __global__ void maxpool_fwd_kernel(pcgan_maxpool_args a) {
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pad, const uint8_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ dx, int dx_pad, int n_, int h, int w, int c) {
+  griddep_wait();
+  griddep_launch();
   const int ho = (h + 1) / 2, wo = (w + 1) / 2, cv = c >> 3;
   const int64_t total = static_cast<int64_t>(n_) * h * w * cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -262,6 +278,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_
 
 // ----------------------------------------------------------------------- loss
 __global__ void loss_kernel(pcgan_loss_args a) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float red[kThreads / 32];
   float acc = 0.f;
   const float invn = 1.f / static_cast<float>(a.n);
@@ -311,6 +329,8 @@ __global__ void loss_kernel(pcgan_loss_args a) {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, const float* lr_p, float b1, float b2, float eps,
                             const float* step_p) {
+  griddep_wait();
+  griddep_launch();
   const float lr = *lr_p, step = *step_p;
   const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   const float step_size = lr / bc1, rsq_bc2 = rsqrtf(bc2);
@@ -332,7 +352,7 @@ using namespace pcgan;
 extern "C" int pcgan_gather_cast_bf16(const float* src, const int32_t* idx, void* dst, int64_t n, pcgan_stream_t s) {
   if (!src || !idx || !dst || n < 0) return fail(PCGAN_ERR_INVALID, "gather_cast: bad argument");
   if (n == 0) return PCGAN_OK;
-  gather_cast_kernel<<<grid_for(n), kThreads, 0, STREAM(s)>>>(src, idx, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  PCGAN_CUDA_OK(launch_pdl(gather_cast_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, src, idx, reinterpret_cast<__nv_bfloat16*>(dst), n));
   PCGAN_LAUNCH_OK("gather_cast_kernel");
   return PCGAN_OK;
 }
@@ -341,7 +361,7 @@ extern "C" int pcgan_scatter_f32(const float* src, const int32_t* idx, float* ds
                                  pcgan_stream_t s) {
   if (!src || !idx || !dst || n < 0) return fail(PCGAN_ERR_INVALID, "scatter: bad argument");
   if (n == 0) return PCGAN_OK;
-  scatter_kernel<<<grid_for(n), kThreads, 0, STREAM(s)>>>(src, idx, dst, n, accumulate);
+  PCGAN_CUDA_OK(launch_pdl(scatter_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, src, idx, dst, n, accumulate));
   PCGAN_LAUNCH_OK("scatter_kernel");
   return PCGAN_OK;
 }
@@ -353,7 +373,7 @@ extern "C" int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t s) {
   if (a->halo == PCGAN_HALO_REFLECT && (a->pad >= a->ho || a->pad >= a->wo)) return fail(PCGAN_ERR_INVALID, "pack_nchw: reflect pad too large");
   if (a->mul_out && (a->ho != a->h || a->wo != a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "pack_nchw: mul_out with resize");
   const int64_t total = static_cast<int64_t>(a->n) * (a->ho + 2 * a->pad) * (a->wo + 2 * a->pad);
-  pack_nchw_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_CUDA_OK(launch_pdl(pack_nchw_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("pack_nchw_kernel");
   return PCGAN_OK;
 }
@@ -361,7 +381,7 @@ extern "C" int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t s) {
 extern "C" int pcgan_resize_nchw_fwd(const float* src, float* dst, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo,
                                      pcgan_stream_t s) {
   if (!src || !dst || planes < 1 || h < 1 || w < 1 || ho < 1 || wo < 1) return fail(PCGAN_ERR_INVALID, "resize_fwd: bad argument");
-  resize_nchw_fwd_kernel<<<grid_for(planes * ho * wo), kThreads, 0, STREAM(s)>>>(src, dst, planes, h, w, ho, wo);
+  PCGAN_CUDA_OK(launch_pdl(resize_nchw_fwd_kernel, dim3(grid_for(planes * ho * wo)), dim3(kThreads), 0, STREAM(s), 1, src, dst, planes, h, w, ho, wo));
   PCGAN_LAUNCH_OK("resize_nchw_fwd_kernel");
   return PCGAN_OK;
 }
@@ -369,7 +389,7 @@ extern "C" int pcgan_resize_nchw_fwd(const float* src, float* dst, int64_t plane
 extern "C" int pcgan_resize_nchw_bwd(const float* gdst, float* gsrc, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo,
                                      pcgan_stream_t s) {
   if (!gdst || !gsrc || planes < 1 || h < 1 || w < 1 || ho < 1 || wo < 1) return fail(PCGAN_ERR_INVALID, "resize_bwd: bad argument");
-  resize_nchw_bwd_kernel<<<grid_for(planes * h * w), kThreads, 0, STREAM(s)>>>(gdst, gsrc, planes, h, w, ho, wo);
+  PCGAN_CUDA_OK(launch_pdl(resize_nchw_bwd_kernel, dim3(grid_for(planes * h * w)), dim3(kThreads), 0, STREAM(s), 1, gdst, gsrc, planes, h, w, ho, wo));
   PCGAN_LAUNCH_OK("resize_nchw_bwd_kernel");
   return PCGAN_OK;
 }
@@ -378,7 +398,7 @@ extern "C" int pcgan_unpack_resize_bwd(const pcgan_unpack_args* a, pcgan_stream_
   if (!a || !a->g || !a->dst) return fail(PCGAN_ERR_INVALID, "unpack: null argument");
   if (a->cd < 1 || a->cd > 8 || a->cd > a->c) return fail(PCGAN_ERR_UNSUPPORTED, "unpack: cd=%d (1..8, <= c)", a->cd);
   const int64_t total = static_cast<int64_t>(a->n) * a->h * a->w;
-  unpack_resize_bwd_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_CUDA_OK(launch_pdl(unpack_resize_bwd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("unpack_resize_bwd_kernel");
   return PCGAN_OK;
 }
@@ -393,7 +413,7 @@ extern "C" int pcgan_maxpool3x3s2_fwd(const pcgan_maxpool_args* a, pcgan_stream_
   int rc = check_cvec(a->c, "maxpool");
   if (rc) return rc;
   const int64_t total = static_cast<int64_t>(a->n) * ((a->h + 1) / 2) * ((a->w + 1) / 2) * (a->c / 8);
-  maxpool_fwd_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_CUDA_OK(launch_pdl(maxpool_fwd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("maxpool_fwd_kernel");
   return PCGAN_OK;
 }
@@ -404,8 +424,8 @@ extern "C" int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint
   int rc = check_cvec(c, "maxpool_bwd");
   if (rc) return rc;
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
-  maxpool_bwd_kernel<<<grid_for(total), kThreads, 0, STREAM(s)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dy_pad, idx,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dx), dx_pad, n, h, w, c);
+  PCGAN_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pad, idx,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dx), dx_pad, n, h, w, c));
   PCGAN_LAUNCH_OK("maxpool_bwd_kernel");
   return PCGAN_OK;
 }
@@ -413,7 +433,7 @@ extern "C" int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint
 extern "C" int pcgan_loss(const pcgan_loss_args* a, pcgan_stream_t s) {
   if (!a || !a->p || !a->target || a->n < 1) return fail(PCGAN_ERR_INVALID, "loss: bad argument");
   if (a->kind < PCGAN_LOSS_BCE || a->kind > PCGAN_LOSS_ELO_NLL_SCORE) return fail(PCGAN_ERR_INVALID, "loss: bad kind");
-  loss_kernel<<<grid_for(a->n, kThreads, 2), kThreads, 0, STREAM(s)>>>(*a);
+  PCGAN_CUDA_OK(launch_pdl(loss_kernel, dim3(grid_for(a->n, kThreads, 2)), dim3(kThreads), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("loss_kernel");
   return PCGAN_OK;
 }
@@ -422,7 +442,7 @@ extern "C" int pcgan_adam(float* p, const float* g, float* m, float* v, int64_t 
                           float beta2, float eps, const float* step, pcgan_stream_t s) {
   if (!p || !g || !m || !v || !lr || !step || n < 0) return fail(PCGAN_ERR_INVALID, "adam: bad argument");
   if (n == 0) return PCGAN_OK;
-  adam_kernel<<<grid_for(n), kThreads, 0, STREAM(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step);
+  PCGAN_CUDA_OK(launch_pdl(adam_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, p, g, m, v, n, lr, beta1, beta2, eps, step));
   PCGAN_LAUNCH_OK("adam_kernel");
   return PCGAN_OK;
 }

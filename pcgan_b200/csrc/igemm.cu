@@ -538,6 +538,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   if (P.pair) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast or committed to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched no global data: under programmatic dependent launch it overlapped the previous kernel's tail
+  griddep_wait();
+  griddep_launch();
 
   const int32_t k_chunks_fwd = P.num_taps * P.cchunks;
   const int32_t total_kb = P.t_count[0] * P.t_count[1] * P.t_count[2] * P.t_count[3];  // WGRAD: pixel blocks
@@ -899,23 +902,10 @@ extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b
     ma = p->map_a; mb = p->map_b; dev = p->dev;
   }
   dev.out = out; dev.bias = bias; dev.stats = stats;
-  if (!p->desc.pair) {
-    igemm_kernel<<<p->grid, kNumThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, dev);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p->grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel, ma, mb, dev);
-    if (e != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaLaunchKernelEx(igemm_kernel, cluster 2): %s", cudaGetErrorString(e));
+  {
+    cudaError_t e = launch_pdl(igemm_kernel, dim3(p->grid), dim3(kNumThreads), kSmemBytes, static_cast<cudaStream_t>(stream),
+                               p->desc.pair ? 2 : 1, ma, mb, dev);
+    if (e != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaLaunchKernelEx(igemm_kernel): %s", cudaGetErrorString(e));
   }
   PCGAN_LAUNCH_OK("igemm_kernel");
   return PCGAN_OK;

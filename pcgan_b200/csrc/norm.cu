@@ -28,6 +28,8 @@ __device__ __forceinline__ void load_f8(const float* p, float (&v)[8]) {
 // block = 32 channels x 8 group lanes; one launch covers every (group, channel)
 __global__ void __launch_bounds__(kT) norm_finalize_kernel(pcgan_norm_finalize_args a) {
   __shared__ float sm[8][33], sv[8][33];
+  griddep_wait();
+  griddep_launch();
   const int cl = threadIdx.x & 31, gl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool combine = a.in_groups > a.groups;   // per-sample statistics folded into one batch statistic (groups == 1)
@@ -143,6 +145,8 @@ __device__ __forceinline__ Pipe<NT> pipe_init(uint8_t* smem) {
     fence_proxy_async();
   }
   __syncthreads();
+  griddep_wait();      // the barriers above were set up while the previous kernel drained (programmatic dependent launch)
+  griddep_launch();
   return p;
 }
 
@@ -320,6 +324,8 @@ __device__ __forceinline__ void folded_load(const __nv_bfloat16* g, int y, int x
 }
 
 __global__ void __launch_bounds__(kT) halo_fold_kernel(pcgan_fold_args a, int vec_per_block, int lcv) {
+  griddep_wait();
+  griddep_launch();
   const int n = blockIdx.y;
   const int cv = a.c >> 3;
   const int total = a.h * a.w * cv;
@@ -663,7 +669,7 @@ extern "C" int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stre
   if (!a || !a->stats || a->groups < 1 || a->c < 1 || a->count <= 0.f) return fail(PCGAN_ERR_INVALID, "norm_finalize: bad argument");
   if (a->in_groups > a->groups && a->groups != 1) return fail(PCGAN_ERR_INVALID, "norm_finalize: per-sample statistics combine into exactly one group");
   if (a->drop_mask && a->in_groups <= a->groups) return fail(PCGAN_ERR_INVALID, "norm_finalize: drop_mask needs per-sample statistics (in_groups = N)");
-  norm_finalize_kernel<<<(a->c + 31) / 32, kT, 0, STREAM(s)>>>(*a);
+  PCGAN_CUDA_OK(launch_pdl(norm_finalize_kernel, dim3((a->c + 31) / 32), dim3(kT), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("norm_finalize_kernel");
   return PCGAN_OK;
 }
@@ -682,8 +688,8 @@ extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, a->res ? 3 : 6, &per);
   const dim3 grid(chunks, a->n);
-  if (a->res) norm_apply_kernel<true><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
-  else norm_apply_kernel<false><<<grid, kStreamThreads, pipe_smem<1>(), STREAM(s)>>>(*a, sg, per, lcv);
+  if (a->res) PCGAN_CUDA_OK(launch_pdl(norm_apply_kernel<true>, grid, dim3(kStreamThreads), pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else PCGAN_CUDA_OK(launch_pdl(norm_apply_kernel<false>, grid, dim3(kStreamThreads), pipe_smem<1>(), STREAM(s), 1, *a, sg, per, lcv));
   PCGAN_LAUNCH_OK("norm_apply_kernel");
   return PCGAN_OK;
 }
@@ -698,7 +704,7 @@ extern "C" int pcgan_halo_fold(const pcgan_fold_args* a, pcgan_stream_t s) {
   if (static_cast<int64_t>(a->h + 2 * a->g_pad) * (a->w + 2 * a->g_pad) * a->c >= (1ll << 31)) return fail(PCGAN_ERR_UNSUPPORTED, "halo_fold: sample too large");
   int per;
   const int chunks = chunking(vps, a->n, kT, &per);
-  halo_fold_kernel<<<dim3(chunks, a->n), kT, 0, STREAM(s)>>>(*a, per, lcv);
+  PCGAN_CUDA_OK(launch_pdl(halo_fold_kernel, dim3(chunks, a->n), dim3(kT), 0, STREAM(s), 1, *a, per, lcv));
   PCGAN_LAUNCH_OK("halo_fold_kernel");
   return PCGAN_OK;
 }
@@ -729,9 +735,10 @@ extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
   const dim3 grid(chunks, a->n);
-  if (!gen) norm_bwd_reduce_kernel<false, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
-  else if (!res) norm_bwd_reduce_kernel<true, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
-  else norm_bwd_reduce_kernel<true, true><<<grid, kStreamThreads, pipe_smem<3>(), STREAM(s)>>>(*a, sg, per, lcv);
+  const dim3 blk(kStreamThreads);
+  if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<false, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<true, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<true, true>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
   PCGAN_LAUNCH_OK("norm_bwd_reduce_kernel");
   return PCGAN_OK;
 }
@@ -746,9 +753,10 @@ extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
   const dim3 grid(chunks, a->n);
-  if (!gen) norm_bwd_apply_kernel<false, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
-  else if (!res) norm_bwd_apply_kernel<true, false><<<grid, kStreamThreads, pipe_smem<2>(), STREAM(s)>>>(*a, sg, per, lcv);
-  else norm_bwd_apply_kernel<true, true><<<grid, kStreamThreads, pipe_smem<3>(), STREAM(s)>>>(*a, sg, per, lcv);
+  const dim3 blk(kStreamThreads);
+  if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<false, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, true>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
   PCGAN_LAUNCH_OK("norm_bwd_apply_kernel");
   return PCGAN_OK;
 }

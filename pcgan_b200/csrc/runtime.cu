@@ -1,5 +1,6 @@
 // Error plumbing and device queries shared by every entry point of the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "common.cuh"
@@ -30,6 +31,15 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PCGAN_PDL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
 }
 
 }  // namespace pcgan

@@ -257,10 +257,14 @@ class _GenProgram:
             ops.halo_fold(dfull, self.g_x0, gx, 0, halo=L.HALO_REFLECT)
             # channels [0, input_nc) are the image, channel input_nc is the constant embedding plane (networks.py:610-611)
             nc = self.mod.input_nc_img
-            dxz = torch.empty(N, nc + 1, S, S, device=self.dev)
-            ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dxz)
-            dx = dxz[:, :nc].contiguous() if need_dx else None
-            dz = dxz[:, nc].sum((1, 2)) if need_dz else None
+            if need_dz:
+                dxz = torch.empty(N, nc + 1, S, S, device=self.dev)
+                ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dxz)
+                dx = dxz[:, :nc].contiguous() if need_dx else None
+                dz = dxz[:, nc].sum((1, 2))
+            else:
+                dx = torch.empty(N, nc, S, S, device=self.dev)
+                ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dx)
         if need_w:
             # biases in front of an affine-less InstanceNorm have exactly zero gradient
             for c in self.convs[:-1]:
@@ -441,10 +445,14 @@ class _DiscProgram:
             gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
             self.convs[0].backward_data(dy, gx)
             nc = self.mod.input_nc_img      # channel nc is the embedding plane (networks.py:780-782)
-            dxz = torch.empty(N, nc + 1, self.S, self.S, device=self.dev)
-            ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dxz)
-            dx = dxz[:, :nc].contiguous() if need_dx else None
-            dz = dxz[:, nc].sum((1, 2)) if need_dz else None
+            if need_dz:
+                dxz = torch.empty(N, nc + 1, self.S, self.S, device=self.dev)
+                ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dxz)
+                dx = dxz[:, :nc].contiguous() if need_dx else None
+                dz = dxz[:, nc].sum((1, 2))
+            else:
+                dx = torch.empty(N, nc, self.S, self.S, device=self.dev)
+                ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dx)
         return dx, dz
 
 
