@@ -22,6 +22,17 @@ GFLOP_PER_IMAGE = 180.02   # algorithmic conv FLOPs of one step
 METRIC = "wsgan_emb_train_images_per_sec_128"
 
 
+WORKLOAD = ("wsgan_emb optimize_parameters, 128x128, ResNet-9 G + 3-layer PatchGAN D + ResNet-18 Elo E@224, lambda_IP 0 "
+            "(BASELINE configs[2])")
+
+
+def config_dict(B, S, world, launch):
+    """`config` of the JSON line: the same for both arms (the reference arm times a bounded sample of this workload)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "size": S, "parallelism": "dp%d" % world,
+            "l2": "4 distinct input batches; ~5 GB of activations per step >> 126 MB L2, no flush needed",
+            "launch": launch, "flops_per_image": GFLOP_PER_IMAGE * 1e9}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -108,8 +119,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": val, "unit": "images/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "wsgan_emb step 128x128, ResNet-9 G + 3-layer PatchGAN D + ResNet-18 Elo E@224, lambda_IP 0",
-                       "per_step_batch": B, "device": "host CPU"},
+            "config": config_dict(args.batch, S, args.gpus, "reference arm: torch CPU, %d pairs per step" % B),
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "%d steps of batch %d (oracle port of the reference step, fp32, torch CPU)" % (len(times), B)},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -126,7 +136,7 @@ def cpu_baseline(size, seconds_budget=25.0):
     B, n, t_total = 2, 0, 0.0
     a, b, label = O.synthetic_batch(B, size, 1234)
     m.optimize_parameters(a, b, label)  # warm-up
-    while n < 3 or (t_total < seconds_budget * 0.5 and n < 8):
+    while n < 2 or (t_total < seconds_budget * 0.5 and n < 8):
         a, b, label = O.synthetic_batch(B, size, 1235 + n)
         t0 = time.perf_counter()
         m.optimize_parameters(a, b, label)
@@ -277,11 +287,7 @@ def main():
         img = world * B * K
         line = {"metric": METRIC, "value": img / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "wsgan_emb optimize_parameters, 128x128, ResNet-9 G + 3-layer PatchGAN D + ResNet-18 Elo E@224, lambda_IP 0 (BASELINE configs[2])",
-                           "batch_per_gpu": B, "global_batch": world * B, "size": S, "parallelism": "dp%d" % world,
-                           "l2": "4 distinct input batches; ~5 GB of activations per step >> 126 MB L2, no flush needed",
-                           "launch": "CUDA graph replay of the captured step" if model.use_graph else "per-kernel launches from Python",
-                           "flops_per_image": GFLOP_PER_IMAGE * 1e9},
+                "config": config_dict(B, S, world, "CUDA graph replay of the captured step" if model.use_graph else "per-kernel launches from Python"),
                 "clocks": clocks,
                 "e2e": {"value": img / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 2 * B * 3 * S * S * 4, "d2h_bytes_per_step": 9 * 4,
                         "ms_per_step": ms_e2e / K},

@@ -622,11 +622,14 @@ static SegGeom seg_geom(int w, int c) {
   sg.seg_vec = best * (c / 8);
   return sg;
 }
-// segments per block: about two waves of blocks at `blocks_per_sm` resident blocks, at least one ring of segments each
+// segments per block: ONE wave of blocks (`blocks_per_sm` of them are resident per SM) whenever a block then still gets
+// a handful of segments — a second, partly filled wave costs a whole block time on these short kernels — and never
+// fewer than two rings of segments per block
 static int seg_chunking(int total_segs, int n, int blocks_per_sm, int* segs_per_block) {
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  const int64_t want_blocks = static_cast<int64_t>(sms) * blocks_per_sm * 2;
-  int64_t chunks = (want_blocks + n - 1) / n;
+  const int64_t slots = static_cast<int64_t>(sms) * blocks_per_sm;
+  int64_t chunks = slots / n;                 // chunks per sample that fit one wave
+  if (chunks < 1) chunks = 1;
   int64_t per = (total_segs + chunks - 1) / chunks;
   if (per < 2 * kStages) per = 2 * kStages;
   if (per > total_segs) per = total_segs;
@@ -733,7 +736,7 @@ extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_
   const bool gen = a->affine != 0 || a->drop_mask != nullptr || a->post_mask != nullptr || res;
   const SegGeom sg = seg_geom(a->w, a->c);
   int per;
-  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
+  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, gen ? 2 : 3, &per);
   const dim3 grid(chunks, a->n);
   const dim3 blk(kStreamThreads);
   if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<false, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
@@ -751,7 +754,7 @@ extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t
   const bool gen = a->affine != 0 || a->drop_mask != nullptr || a->post_mask != nullptr || res;
   const SegGeom sg = seg_geom(a->w, a->c);
   int per;
-  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, res ? 2 : 3, &per);
+  const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, 2, &per);
   const dim3 grid(chunks, a->n);
   const dim3 blk(kStreamThreads);
   if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<false, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));

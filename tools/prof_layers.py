@@ -1,7 +1,8 @@
 """A few representative igemm launches for ncu (one launch each after a warm-up launch):
   0 head dgrad (packed 8-ch dY -> 64 ch, padded grid)   1 stem fwd (packed 8 ch -> 64, stats)
   2 resblock wgrad                                     3 E.layer1 conv fwd (56x56x64 -> 64, BN stats)
-  4 head fwd (64 -> 3, tanh, NCHW)                      5 up2 phase fwd (ConvT 128 -> 64)"""
+  4 head fwd (64 -> 3, tanh, NCHW)                      5 up2 phase fwd (ConvT 128 -> 64)
+  6 resblock fwd 256 -> 256 3x3 with per-sample statistics (the flagship shape)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -55,4 +56,8 @@ if 5 in WHICH:
     xg, rg = Geom(N, 64, 64, 128, 1), Geom(N, S, S, 64, 0)
     plans = CV.conv_fwd_plans((128, 64, 3, 3), xg, 2, 1, OutMap.nhwc(rg), transposed=True, output_padding=1, stats=True, per_sample_stats=True, note="up2.fwd")
     run(plans[3:4], buf(xg), torch.zeros(rg.numel + 512, dtype=torch.bfloat16, device=DEV), bias=torch.zeros(64, device=DEV), stats=torch.zeros(N, 64, 2, device=DEV))
+if 6 in WHICH:
+    xg, rg = Geom(N, 32, 32, 256, 1), Geom(N, 32, 32, 256, 0)
+    run(CV.conv_fwd_plans((256, 256, 3, 3), xg, 1, 1, OutMap.nhwc(rg), stats=True, per_sample_stats=True, note="res.fwd"), buf(xg),
+        torch.zeros(rg.numel + 512, dtype=torch.bfloat16, device=DEV), bias=torch.zeros(256, device=DEV), stats=torch.zeros(N, 256, 2, device=DEV))
 print("done")
