@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 8
+#define PCGAN_ABI_VERSION 9
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -168,6 +168,18 @@ int pcgan_igemm_run(pcgan_igemm_plan* plan, const void* a, const void* b, void* 
 int pcgan_gather_cast_bf16(const float* src, const int32_t* idx, void* dst_bf16, int64_t n, pcgan_stream_t stream);
 /* dst[idx[i]] (+)= src[i] for idx[i] >= 0: packed fp32 weight gradient -> .grad in OIHW. */
 int pcgan_scatter_f32(const float* src, const int32_t* idx, float* dst, int64_t n, int32_t accumulate, pcgan_stream_t stream);
+
+/* The same two operations for many tensors in ONE launch: `items` is a device array of `count` descriptors (a network's
+ * whole set of packed operands after an optimizer step / of packed weight gradients after a backward pass);
+ * max_n = the largest items[i].n (sizes the grid). */
+typedef struct {
+  const float* src;   /* gather: fp32 master weight;  scatter: packed fp32 gradient            */
+  const int32_t* idx; /* n entries: index into the master-layout tensor, or -1                 */
+  void* dst;          /* gather: packed bf16 operand; scatter: fp32 master-layout .grad        */
+  int64_t n;
+} pcgan_batch_item;
+int pcgan_gather_cast_bf16_batched(const pcgan_batch_item* items, int32_t count, int64_t max_n, pcgan_stream_t stream);
+int pcgan_scatter_f32_batched(const pcgan_batch_item* items, int32_t count, int64_t max_n, int32_t accumulate, pcgan_stream_t stream);
 
 /* NCHW fp32 image [N][Cs][H][W] (+ optional per-sample scalar z[N] appended as
  * channel Cs: networks.py:610-611, :780-782 torch.cat((input, z_img), 1)),

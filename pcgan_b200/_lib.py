@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -48,6 +48,10 @@ class IgemmDesc(C.Structure):
         ("stats_mode", i32), ("stats_dim", i32), ("stats_comp", i32),
         ("m_valid", i32), ("wg_ncols", i32), ("ldo", i64), ("pair", i32), ("shift_taps", i32), ("shift_cpad", i32),
     ]
+
+
+class BatchItem(C.Structure):
+    _fields_ = [("src", vp), ("idx", vp), ("dst", vp), ("n", i64)]
 
 
 class PackArgs(C.Structure):
@@ -102,7 +106,7 @@ _STRUCTS = {
     "pcgan_tmap": TMap, "pcgan_comp": Comp, "pcgan_igemm_desc": IgemmDesc, "pcgan_pack_args": PackArgs,
     "pcgan_unpack_args": UnpackArgs, "pcgan_norm_finalize_args": NormFinalizeArgs,
     "pcgan_norm_apply_args": NormApplyArgs, "pcgan_fold_args": FoldArgs, "pcgan_norm_bwd_args": NormBwdArgs,
-    "pcgan_maxpool_args": MaxpoolArgs, "pcgan_loss_args": LossArgs,
+    "pcgan_maxpool_args": MaxpoolArgs, "pcgan_loss_args": LossArgs, "pcgan_batch_item": BatchItem,
 }
 
 # name -> (restype, argtypes); every symbol include/pcgan_kernels.h declares
@@ -115,6 +119,8 @@ SYMBOLS = {
     "pcgan_igemm_run": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "pcgan_gather_cast_bf16": (C.c_int, [vp, vp, vp, i64, vp]),
     "pcgan_scatter_f32": (C.c_int, [vp, vp, vp, i64, i32, vp]),
+    "pcgan_gather_cast_bf16_batched": (C.c_int, [vp, i32, i64, vp]),
+    "pcgan_scatter_f32_batched": (C.c_int, [vp, i32, i64, i32, vp]),
     "pcgan_pack_nchw": (C.c_int, [C.POINTER(PackArgs), vp]),
     "pcgan_resize_nchw_fwd": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "pcgan_resize_nchw_bwd": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp]),

@@ -37,6 +37,32 @@ __global__ void scatter_kernel(const float* __restrict__ src, const int32_t* __r
   }
 }
 
+// one launch for a whole network: blockIdx.y = tensor
+__global__ void gather_cast_batched_kernel(const pcgan_batch_item* __restrict__ items) {
+  griddep_wait();
+  griddep_launch();
+  const pcgan_batch_item it = items[blockIdx.y];
+  const float* __restrict__ src = it.src;
+  const int32_t* __restrict__ idx = it.idx;
+  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(it.dst);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < it.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
+  }
+}
+__global__ void scatter_batched_kernel(const pcgan_batch_item* __restrict__ items, int accumulate) {
+  griddep_wait();
+  griddep_launch();
+  const pcgan_batch_item it = items[blockIdx.y];
+  const float* __restrict__ src = it.src;
+  const int32_t* __restrict__ idx = it.idx;
+  float* __restrict__ dst = reinterpret_cast<float*>(it.dst);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < it.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    if (j >= 0) dst[j] = accumulate ? dst[j] + src[i] : src[i];
+  }
+}
+
 // ------------------------------------------------------------------ pack_nchw
 __device__ __forceinline__ void bilinear_setup(int o, int in, int out, int& i0, int& i1, float& l0, float& l1) {
   // torch.nn.functional.interpolate(mode='bilinear', align_corners=True): util/util.py:117
@@ -363,6 +389,38 @@ extern "C" int pcgan_scatter_f32(const float* src, const int32_t* idx, float* ds
   if (n == 0) return PCGAN_OK;
   PCGAN_CUDA_OK(launch_pdl(scatter_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, src, idx, dst, n, accumulate));
   PCGAN_LAUNCH_OK("scatter_kernel");
+  return PCGAN_OK;
+}
+
+static int batched_grid(int32_t count, int64_t max_n, dim3* grid) {
+  if (count < 1 || count > 65535 || max_n < 1) return fail(PCGAN_ERR_INVALID, "batched gather/scatter: count=%d max_n=%lld", count, (long long)max_n);
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int64_t bx = (max_n + kThreads * 4 - 1) / (kThreads * 4);      // about four elements per thread for the largest tensor
+  const int64_t cap = (static_cast<int64_t>(sms) * 16 + count - 1) / count;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  *grid = dim3(static_cast<unsigned>(bx), static_cast<unsigned>(count));
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_gather_cast_bf16_batched(const pcgan_batch_item* items, int32_t count, int64_t max_n, pcgan_stream_t s) {
+  if (!items) return fail(PCGAN_ERR_INVALID, "gather_cast_batched: null table");
+  dim3 grid;
+  int rc = batched_grid(count, max_n, &grid);
+  if (rc) return rc;
+  PCGAN_CUDA_OK(launch_pdl(gather_cast_batched_kernel, grid, dim3(kThreads), 0, STREAM(s), 1, items));
+  PCGAN_LAUNCH_OK("gather_cast_batched_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_scatter_f32_batched(const pcgan_batch_item* items, int32_t count, int64_t max_n, int32_t accumulate,
+                                         pcgan_stream_t s) {
+  if (!items) return fail(PCGAN_ERR_INVALID, "scatter_batched: null table");
+  dim3 grid;
+  int rc = batched_grid(count, max_n, &grid);
+  if (rc) return rc;
+  PCGAN_CUDA_OK(launch_pdl(scatter_batched_kernel, grid, dim3(kThreads), 0, STREAM(s), 1, items, static_cast<int>(accumulate)));
+  PCGAN_LAUNCH_OK("scatter_batched_kernel");
   return PCGAN_OK;
 }
 

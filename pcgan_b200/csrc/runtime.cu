@@ -61,5 +61,6 @@ extern "C" int64_t pcgan_sizeof(const char* name) {
   if (s == "pcgan_norm_bwd_args") return sizeof(pcgan_norm_bwd_args);
   if (s == "pcgan_maxpool_args") return sizeof(pcgan_maxpool_args);
   if (s == "pcgan_loss_args") return sizeof(pcgan_loss_args);
+  if (s == "pcgan_batch_item") return sizeof(pcgan_batch_item);
   return -1;
 }

@@ -30,6 +30,7 @@ class ConvRT:
                  act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, dyg: Optional[Geom] = None,
                  dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True):
         self.name, self.weight, self.bias = name, weight, bias
+        self.bank = None
         dev = weight.device
         self.dev = dev
         shape = tuple(weight.shape)
@@ -85,16 +86,99 @@ class ConvRT:
             g.run(dybuf, wbuf, dxout)
 
     def backward_weight(self, dybuf, xbuf):
-        """Accumulates into weight.grad (allocated on first use)."""
+        """Accumulates into weight.grad (allocated on first use).  Under a WeightBank in deferred mode the packed
+        gradient keeps accumulating across backward passes and the bank scatters all layers in one launch."""
         g, wm, packed = self.ensure_wgrad()
-        packed.zero_()
+        deferred = self.bank is not None and self.bank.deferred
+        if not deferred:
+            packed.zero_()
         if self.transposed or g.spec.swap_operands:
             g.run(xbuf, dybuf, packed)     # M side = input activations, N side = dY
         else:
             g.run(dybuf, xbuf, packed)
+        if deferred:
+            self.bank.dirty = True
+            return
         if self.weight.grad is None:
             self.weight.grad = torch.zeros_like(self.weight)
         ops.scatter_f32(packed, wm, self.weight.grad, accumulate=True)
+
+
+class WeightBank:
+    """All convolutions of one program: their packed bf16 operands are refreshed by ONE gather launch when any master
+    weight changed (optimizer step, load_state_dict), and — in deferred mode, which the training drivers switch on — their
+    packed fp32 weight gradients live in one arena that is cleared by one memset per optimizer step and scattered into the
+    .grad tensors by ONE launch per backward sweep (instead of a memset and a scatter per layer and pass)."""
+
+    def __init__(self, convs, dev):
+        self.convs, self.dev = list(convs), dev
+        for c in self.convs:
+            c.bank = self
+        self.deferred, self.dirty = False, False
+        self._gather = None          # (pointer signature, table, count, max_n)
+        self._versions = None
+        self._scatter = None
+        self._arena = None
+
+    # ------------------------------------------------------------ operands
+    def ensure_packed(self):
+        ver = tuple((c.weight._version, c.weight.data_ptr()) for c in self.convs)
+        if ver == self._versions:
+            return
+        items = [(c.weight.detach(), wm, buf) for c in self.convs for _, wm, buf in c.fwd + c.dgrad]
+        sig = tuple(t.data_ptr() for it in items for t in it)
+        if self._gather is None or self._gather[0] != sig:
+            table, max_n = ops.batch_table(items, self.dev)
+            self._gather = (sig, table, len(items), max_n)
+        _, table, count, max_n = self._gather
+        ops.gather_cast_bf16_batched(table, count, max_n)
+        self._versions = ver
+        for c, v in zip(self.convs, ver):
+            c._wver = v
+
+    # ----------------------------------------------------- weight gradients
+    def enable_deferred(self):
+        """Move every convolution's packed gradient into one flat fp32 arena (builds the weight-gradient plans)."""
+        if self.deferred:
+            return
+        trainable = [c for c in self.convs if c._wg_args[1] is not None]
+        sizes = []
+        for c in trainable:
+            g, wm, packed = c.ensure_wgrad()
+            sizes.append((packed.numel() + 3) // 4 * 4)
+        self._arena = torch.zeros(max(sum(sizes), 4), dtype=torch.float32, device=self.dev)
+        off = 0
+        for c, n in zip(trainable, sizes):
+            g, wm, packed = c.wgrad
+            c.wgrad = (g, wm, self._arena[off:off + packed.numel()])
+            off += n
+        self._trainable = trainable
+        self.deferred = True
+
+    def zero_wgrad(self):
+        if self.deferred:
+            self._arena.zero_()
+            self.dirty = False
+
+    def flush_wgrad(self):
+        """Scatter-accumulate the packed gradients of every trainable convolution into its weight.grad."""
+        if not (self.deferred and self.dirty):
+            return
+        convs = [c for c in self._trainable if c.weight.requires_grad]
+        if not convs:
+            self.dirty = False
+            return
+        for c in convs:
+            if c.weight.grad is None:
+                c.weight.grad = torch.zeros_like(c.weight)
+        items = [(c.wgrad[2], c.wgrad[1], c.weight.grad) for c in convs]
+        sig = tuple(t.data_ptr() for it in items for t in it)
+        if self._scatter is None or self._scatter[0] != sig:
+            table, max_n = ops.batch_table(items, self.dev)
+            self._scatter = (sig, table, len(items), max_n)
+        _, table, count, max_n = self._scatter
+        ops.scatter_f32_batched(table, count, max_n, accumulate=True)
+        self.dirty = False
 
 
 class Arena:

@@ -19,7 +19,7 @@ from torch.nn import init
 from . import _lib as L
 from . import custom_ops as CO
 from . import ops
-from .engine import Arena, ConvRT, NormState, Pool, accumulate_grad, zeros_act
+from .engine import Arena, ConvRT, NormState, Pool, WeightBank, accumulate_grad, zeros_act
 from .plan import Geom, OutMap
 
 EPS = 1e-5
@@ -127,6 +127,9 @@ class _GenProgram:
         self.scratch = _Scratch(dev)
         self.pool = Pool(lambda key: self._new_ws())
         self.convs = [self.stem, self.down1, self.down2] + [c for blk in self.blocks for c in blk[:2]] + [self.up1, self.up2, self.head]
+        self.bank = WeightBank(self.convs, dev)
+        if getattr(mod, "defer_wgrad", False):
+            self.bank.enable_deferred()
 
     def _new_ws(self):
         ws, dev, N = _GenWorkspace(), self.dev, self.N
@@ -154,6 +157,7 @@ class _GenProgram:
         m, S, N = self.mod.model, self.S, self.N
         ws = self.pool.take(0)
         h2, h4 = S // 2, S // 4
+        self.bank.ensure_packed()
         ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_REFLECT)
         _unit_forward(self.stem, ws.x0, ws.r1, ws.n1, S * S, rmean=m[2].running_mean, rvar=m[2].running_var)
@@ -188,6 +192,7 @@ class _GenProgram:
         m = self.mod.model
         nblk = len(self.blocks)
         R, Z = L.ACT_RELU, L.ACT_NONE
+        self.bank.ensure_packed()
         ws.sums_arena.zero()
         # head: d(pre-tanh) = dout * (1 - out^2)
         dyh = sc.get(self.g_dyh)
@@ -317,6 +322,16 @@ class ResnetGenerator(nn.Module):
             self._programs[k] = _GenProgram(self, n, s)
         return self._programs[k]
 
+    def zero_wgrad(self):
+        """Deferred weight gradients (defer_wgrad = True): clear the packed accumulators (optimizer.zero_grad time)."""
+        for prog in self._programs.values():
+            prog.bank.zero_wgrad()
+
+    def flush_wgrad(self):
+        """... and scatter them into the parameters' .grad after the backward sweeps of the step."""
+        for prog in self._programs.values():
+            prog.bank.flush_wgrad()
+
     def forward(self, input, z=None):
         _require_cuda(input, "ResnetGenerator")
         if input.shape[2] != input.shape[3] or input.shape[2] % 4:
@@ -373,6 +388,9 @@ class _DiscProgram:
                            dx_out=OutMap.nhwc(self.g_r[-1]))
         self.scratch = _Scratch(dev)
         self.pool = Pool(lambda key: self._new_ws())
+        self.bank = WeightBank(self.convs + [self.head], dev)
+        if getattr(mod, "defer_wgrad", False):
+            self.bank.enable_deferred()
 
     def _new_ws(self):
         ws, dev = _DiscWorkspace(), self.dev
@@ -390,6 +408,7 @@ class _DiscProgram:
     def forward(self, x, z):
         m, N = self.mod.model, self.N
         ws = self.pool.take(0)
+        self.bank.ensure_packed()
         ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_ZERO)
         self.convs[0].forward(ws.x0, ws.y[0])
@@ -407,6 +426,7 @@ class _DiscProgram:
 
     def backward(self, ws, out, dout, need_dx, need_w, need_dz=False):
         m, N, sc = self.mod.model, self.N, self.scratch
+        self.bank.ensure_packed()
         ws.sums_arena.zero()
         dyh = sc.get(self.g_dyh)
         if self.mod.use_sigmoid:
@@ -492,6 +512,16 @@ class NLayerDiscriminator(nn.Module):
         if k not in self._programs:
             self._programs[k] = _DiscProgram(self, n, s)
         return self._programs[k]
+
+    def zero_wgrad(self):
+        """Deferred weight gradients (defer_wgrad = True): clear the packed accumulators (optimizer.zero_grad time)."""
+        for prog in self._programs.values():
+            prog.bank.zero_wgrad()
+
+    def flush_wgrad(self):
+        """... and scatter them into the parameters' .grad after the backward sweeps of the step."""
+        for prog in self._programs.values():
+            prog.bank.flush_wgrad()
 
     def forward(self, input, z=None):
         _require_cuda(input, "NLayerDiscriminator")
@@ -880,6 +910,12 @@ class _EncProgram:
         self.head_drop = mod.head_dropout > 0
         self.scratch = _Scratch(dev)
         self.pool = Pool(lambda key: self._new_ws())
+        convs = [self.stem]
+        for b in self.blocks:
+            convs += [b.c1, b.c2] + ([b.ds] if b.ds is not None else [])
+        for h in self.heads:
+            convs += [h.c1, h.c2]
+        self.bank = WeightBank(convs, dev)
 
     def _new_ws(self):
         ws, dev = _EncWorkspace(), self.dev
@@ -907,6 +943,7 @@ class _EncProgram:
         mod, N = self.mod, self.N
         rn = mod.base.model
         ws = self.pool.take(0)
+        self.bank.ensure_packed()
         ws.stats_arena.zero()
         ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
         s2 = self.S // 2
@@ -926,6 +963,7 @@ class _EncProgram:
         """gys: one gradient (or None) per head output."""
         N, sc, hf = self.N, self.scratch, self.hf
         rn = self.mod.base.model
+        self.bank.ensure_packed()
         ws.sums_arena.zero()
         feats = ws.blk[-1].y
         g = None

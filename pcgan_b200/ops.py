@@ -108,6 +108,24 @@ def scatter_f32(src, idx, dst, accumulate=False):
         L.check(L.load().pcgan_scatter_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), int(accumulate), _stream()), "scatter_f32")
 
 
+def batch_table(items, device):
+    """Device table of pcgan_batch_item for the batched gather / scatter: items = [(src, idx, dst)] tensors."""
+    rows = [[t_src.data_ptr(), t_idx.data_ptr(), t_dst.data_ptr(), t_idx.numel()] for t_src, t_idx, t_dst in items]
+    return torch.tensor(rows, dtype=torch.int64).to(device), max(r[3] for r in rows)
+
+
+def gather_cast_bf16_batched(table, count, max_n):
+    _count()
+    with _Timed("gather_cast_bf16_batched"):
+        L.check(L.load().pcgan_gather_cast_bf16_batched(_ptr(table), count, max_n, _stream()), "gather_cast_bf16_batched")
+
+
+def scatter_f32_batched(table, count, max_n, accumulate=True):
+    _count()
+    with _Timed("scatter_f32_batched"):
+        L.check(L.load().pcgan_scatter_f32_batched(_ptr(table), count, max_n, int(accumulate), _stream()), "scatter_f32_batched")
+
+
 def pack_nchw(src, dst, g: Geom, *, z=None, mul_out=None, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO):
     """src: NCHW fp32 [n, cs, h, w] -> dst buffer of geometry g (resized to g.h x g.w when they differ)."""
     n, cs, h, w = src.shape

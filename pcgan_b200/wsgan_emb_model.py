@@ -174,6 +174,9 @@ class WSGANEmbModel(BaseModel):
             # one process per GPU: flat gradient buffers, averaged over ranks with one NCCL all-reduce per network
             self.sync_G = GradSync(list(self.netG.parameters()))
             self.sync_D = GradSync(list(self.netD.parameters()))
+            # weight gradients accumulate in packed form over the backward sweeps of an update and reach .grad in one launch
+            for net in (self.netG, self.netD):
+                self._unwrap(net).defer_wgrad = True
             self.sync_E = None
             if opt.lr_E > 0.0:      # wsgan_emb_model.py:159-163
                 if self.use_graph:
@@ -377,14 +380,18 @@ class WSGANEmbModel(BaseModel):
     def update_D(self):
         self.set_requires_grad(self.netD, True)
         self.sync_D.zero()                 # optimizer_D.zero_grad()
+        self._unwrap(self.netD).zero_wgrad()
         self.backward_D()
+        self._unwrap(self.netD).flush_wgrad()
         self.sync_D.all_reduce()
         self.optimizer_D.step()
 
     def update_G(self):
         self.set_requires_grad(self.netD, False)
         self.sync_G.zero()                 # optimizer_G.zero_grad()
+        self._unwrap(self.netG).zero_wgrad()
         self.backward_G()
+        self._unwrap(self.netG).flush_wgrad()
         self.sync_G.all_reduce()
         self.optimizer_G.step()
 
@@ -393,7 +400,9 @@ class WSGANEmbModel(BaseModel):
         self.set_requires_grad(self.netD, False)
         self.sync_G.zero()
         self.sync_E.zero()
+        self._unwrap(self.netG).zero_wgrad()
         self.backward_GE()
+        self._unwrap(self.netG).flush_wgrad()
         self.sync_G.all_reduce()
         self.sync_E.all_reduce()
         self.optimizer_G.step()
@@ -401,7 +410,9 @@ class WSGANEmbModel(BaseModel):
         if self.opt.lambda_z > 0.0:
             self.sync_G.zero()
             self.sync_E.zero()
+            self._unwrap(self.netG).zero_wgrad()
             self.backward_G_alone()
+            self._unwrap(self.netG).flush_wgrad()
             self.sync_G.all_reduce()
             self.optimizer_G.step()
 
@@ -419,13 +430,17 @@ class WSGANEmbModel(BaseModel):
         self.forward()
         self.set_requires_grad(self.netD, False)
         self.sync_G.zero()
+        self._unwrap(self.netG).zero_wgrad()
         self.backward_G()
+        self._unwrap(self.netG).flush_wgrad()
 
     def _seg_step_G_backward_D(self):
         self.optimizer_G.step()
         self.set_requires_grad(self.netD, True)
         self.sync_D.zero()
+        self._unwrap(self.netD).zero_wgrad()
         self.backward_D()
+        self._unwrap(self.netD).flush_wgrad()
 
     def _seg_step_D(self):
         self.optimizer_D.step()
