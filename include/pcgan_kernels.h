@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 9
+#define PCGAN_ABI_VERSION 10
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -255,8 +255,28 @@ typedef struct {
   int32_t act; float act_slope;
   const float* post_mask; /* optional [N][C]: multiplies the activation's output (nn.Dropout2d between BatchNorm and
                              LeakyReLU, networks.py:1021-1023: lrelu(m*v) == m*lrelu(v) for m >= 0) */
+  /* Fused finalize (stats != NULL; scale / shift above are then ignored): every block derives the scale / shift of its
+   * channels from the raw statistics [groups][c][2] exactly as pcgan_norm_finalize does, and the first block of each
+   * group stores mean / rstd / scale / shift [groups][c] for the backward pass.  The running statistics are updated by
+   * pcgan_norm_running_batched. */
+  const float* stats; float count, eps;
+  const float* gamma; const float* beta;
+  float* mean_out; float* rstd_out; float* scale_out; float* shift_out;
 } pcgan_norm_apply_args;
 int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t stream);
+
+/* Running-statistics EMA (and num_batches_tracked += 1) of every normalisation layer of a network pass in ONE launch:
+ * for each item, running_mean = (1-momentum)*running_mean + momentum*mean over groups of the group means, running_var
+ * likewise with the unbiased variance — what pcgan_norm_finalize does per layer (nn.InstanceNorm2d with
+ * track_running_stats=True / nn.BatchNorm2d in training mode).  `items` is a device array. */
+typedef struct {
+  const float* stats;      /* [groups][c][2] */
+  float* running_mean; float* running_var;   /* [c], may be NULL */
+  int64_t* num_batches_tracked;              /* scalar, may be NULL */
+  int32_t groups, c;
+  float count, momentum;
+} pcgan_running_item;
+int pcgan_norm_running_batched(const pcgan_running_item* items, int32_t count, int32_t max_c, pcgan_stream_t stream);
 
 /* out[N][H][W][C] (pad out_pad, zero halo kept) = fold(gpad) [+ add]: folds the gradient of a padded
  * buffer (reflect: halo gradients are added onto their mirror pixels; zero: halo

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -54,6 +54,11 @@ class BatchItem(C.Structure):
     _fields_ = [("src", vp), ("idx", vp), ("dst", vp), ("n", i64)]
 
 
+class RunningItem(C.Structure):
+    _fields_ = [("stats", vp), ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
+                ("groups", i32), ("c", i32), ("count", f32), ("momentum", f32)]
+
+
 class PackArgs(C.Structure):
     _fields_ = [("src", vp), ("z", vp), ("mul_out", vp), ("mul_kind", i32), ("dst", vp),
                 ("n", i32), ("cs", i32), ("h", i32), ("w", i32), ("ho", i32), ("wo", i32),
@@ -76,7 +81,9 @@ class NormApplyArgs(C.Structure):
                 ("n", i32), ("h", i32), ("w", i32), ("c", i32),
                 ("scale", vp), ("shift", vp), ("groups", i32),
                 ("res_scale", vp), ("res_shift", vp), ("res_groups", i32),
-                ("drop_mask", vp), ("act", i32), ("act_slope", f32), ("post_mask", vp)]
+                ("drop_mask", vp), ("act", i32), ("act_slope", f32), ("post_mask", vp),
+                ("stats", vp), ("count", f32), ("eps", f32), ("gamma", vp), ("beta", vp),
+                ("mean_out", vp), ("rstd_out", vp), ("scale_out", vp), ("shift_out", vp)]
 
 
 class FoldArgs(C.Structure):
@@ -106,7 +113,7 @@ _STRUCTS = {
     "pcgan_tmap": TMap, "pcgan_comp": Comp, "pcgan_igemm_desc": IgemmDesc, "pcgan_pack_args": PackArgs,
     "pcgan_unpack_args": UnpackArgs, "pcgan_norm_finalize_args": NormFinalizeArgs,
     "pcgan_norm_apply_args": NormApplyArgs, "pcgan_fold_args": FoldArgs, "pcgan_norm_bwd_args": NormBwdArgs,
-    "pcgan_maxpool_args": MaxpoolArgs, "pcgan_loss_args": LossArgs, "pcgan_batch_item": BatchItem,
+    "pcgan_maxpool_args": MaxpoolArgs, "pcgan_loss_args": LossArgs, "pcgan_batch_item": BatchItem, "pcgan_running_item": RunningItem,
 }
 
 # name -> (restype, argtypes); every symbol include/pcgan_kernels.h declares
@@ -127,6 +134,7 @@ SYMBOLS = {
     "pcgan_unpack_resize_bwd": (C.c_int, [C.POINTER(UnpackArgs), vp]),
     "pcgan_norm_finalize": (C.c_int, [C.POINTER(NormFinalizeArgs), vp]),
     "pcgan_norm_apply": (C.c_int, [C.POINTER(NormApplyArgs), vp]),
+    "pcgan_norm_running_batched": (C.c_int, [vp, i32, i32, vp]),
     "pcgan_halo_fold": (C.c_int, [C.POINTER(FoldArgs), vp]),
     "pcgan_norm_bwd_reduce": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
     "pcgan_norm_bwd_apply": (C.c_int, [C.POINTER(NormBwdArgs), vp]),

@@ -92,6 +92,31 @@ __global__ void __launch_bounds__(kT) norm_finalize_kernel(pcgan_norm_finalize_a
   }
 }
 
+// blockIdx.y = layer, one thread per channel; groups are walked in order (coalesced across channels)
+__global__ void __launch_bounds__(kT) norm_running_batched_kernel(const pcgan_running_item* __restrict__ items) {
+  griddep_wait();
+  griddep_launch();
+  const pcgan_running_item it = items[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && it.num_batches_tracked) *it.num_batches_tracked += 1;
+  if (c >= it.c) return;
+  float macc = 0.f, vacc = 0.f;
+  for (int g = 0; g < it.groups; ++g) {
+    const float2 s = reinterpret_cast<const float2*>(it.stats)[static_cast<int64_t>(g) * it.c + c];
+    const float mean = s.x / it.count;
+    float var = s.y / it.count - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    macc += mean;
+    vacc += var;
+  }
+  const float m = macc / it.groups, v = vacc / it.groups;
+  if (it.running_mean) it.running_mean[c] = (1.f - it.momentum) * it.running_mean[c] + it.momentum * m;
+  if (it.running_var) {
+    const float unbias = it.count > 1.f ? it.count / (it.count - 1.f) : 1.f;
+    it.running_var[c] = (1.f - it.momentum) * it.running_var[c] + it.momentum * (v * unbias);
+  }
+}
+
 // ------------------------------------------------------------- stream pipeline
 // The three hot kernels (norm_apply, norm_bwd_reduce, norm_bwd_apply) stream their inputs through shared memory
 // with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx): a producer warp keeps kStages segments of every
@@ -210,7 +235,36 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
   for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
 #pragma unroll
   for (int j = 0; j < (RES ? 8 : 1); ++j) { rsc[j] = 1.f; rsh[j] = 0.f; }
-  if (a.scale) {
+  if (a.stats) {
+    // fused finalize: the same arithmetic as norm_finalize_kernel, for this thread's 8 channels of its group
+    const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+    float st[16];
+    load_f8(a.stats + so * 2, *reinterpret_cast<float(*)[8]>(st));
+    load_f8(a.stats + so * 2 + 8, *reinterpret_cast<float(*)[8]>(st + 8));
+    float gam[8], bet[8], mean[8], rstd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gam[j] = 1.f; bet[j] = 0.f; }
+    if (a.gamma) load_f8(a.gamma + c0, gam);
+    if (a.beta) load_f8(a.beta + c0, bet);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = st[2 * j] / a.count;
+      float var = st[2 * j + 1] / a.count - mean[j] * mean[j];
+      var = var > 0.f ? var : 0.f;
+      rstd[j] = rsqrtf(var + a.eps);
+      sc[j] = gam[j] * rstd[j];
+      sh[j] = bet[j] - mean[j] * gam[j] * rstd[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < cv && (a.groups > 1 || n == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (a.mean_out) a.mean_out[so + j] = mean[j];
+        if (a.rstd_out) a.rstd_out[so + j] = rstd[j];
+        if (a.scale_out) a.scale_out[so + j] = sc[j];
+        if (a.shift_out) a.shift_out[so + j] = sh[j];
+      }
+    }
+  } else if (a.scale) {
     const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
     load_f8(a.scale + so, sc);
     load_f8(a.shift + so, sh);
@@ -677,8 +731,16 @@ extern "C" int pcgan_norm_finalize(const pcgan_norm_finalize_args* a, pcgan_stre
   return PCGAN_OK;
 }
 
+extern "C" int pcgan_norm_running_batched(const pcgan_running_item* items, int32_t count, int32_t max_c, pcgan_stream_t s) {
+  if (!items || count < 1 || count > 65535 || max_c < 1) return fail(PCGAN_ERR_INVALID, "norm_running_batched: bad argument");
+  PCGAN_CUDA_OK(launch_pdl(norm_running_batched_kernel, dim3((max_c + kT - 1) / kT, count), dim3(kT), 0, STREAM(s), 1, items));
+  PCGAN_LAUNCH_OK("norm_running_batched_kernel");
+  return PCGAN_OK;
+}
+
 extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s) {
   if (!a || !a->x || !a->y) return fail(PCGAN_ERR_INVALID, "norm_apply: null argument");
+  if (a->stats && a->count <= 0.f) return fail(PCGAN_ERR_INVALID, "norm_apply: fused finalize needs count > 0");
   int lcv, rc = check_c(a->c, "norm_apply", &lcv);
   if (rc) return rc;
   if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(PCGAN_ERR_INVALID, "norm_apply: scale and shift go together");

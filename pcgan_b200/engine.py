@@ -216,6 +216,32 @@ class _Slice:
         self.arena, self.off, self.shape, self.t = arena, off, shape, None
 
 
+class RunningStats:
+    """The running-statistics updates (and num_batches_tracked increments) of one network pass, issued as one launch at
+    the end of the pass: layers register in forward order; the device table is built once per workspace."""
+
+    def __init__(self, dev):
+        self.dev, self.items, self.table = dev, [], None
+
+    def begin(self):
+        self.items = []
+
+    def add(self, ns, count, running_mean, running_var, nbt=None, momentum=0.1):
+        self.items.append((ns.stats, running_mean, running_var, nbt, ns.stats.shape[0], ns.c, count, momentum))
+
+    def flush(self):
+        if not self.items:
+            return
+        sig = tuple((it[0].data_ptr(), 0 if it[1] is None else it[1].data_ptr(), 0 if it[3] is None else it[3].data_ptr(), it[6])
+                    for it in self.items)
+        if self.table is None or self.table[0] != sig:
+            t, max_c = ops.running_table(self.items, self.dev)
+            self.table = (sig, t, len(self.items), max_c)
+        _, t, n, max_c = self.table
+        ops.norm_running_batched(t, n, max_c)
+        self.items = []
+
+
 class NormState:
     """Per-call statistics of one normalisation layer: [groups][C] each (groups = N for instance norm, 1 for batch norm).
     With arenas, `stats` / `sums` are slices of the workspace's accumulator arenas (cleared once per pass by the program);
@@ -235,6 +261,15 @@ class NormState:
         self.rstd = torch.empty(groups, c, device=dev)
         self.scale = torch.empty(groups, c, device=dev)
         self.shift = torch.empty(groups, c, device=dev)
+        self.fused = None     # (count, gamma, beta): the consuming norm_apply finalizes the statistics itself
+
+    def apply_kw(self, eps=1e-5):
+        """Arguments of ops.norm_apply that describe this layer's normalisation."""
+        if self.fused is not None:
+            count, gamma, beta = self.fused
+            return dict(groups=self.groups, stats=self.stats, count=count, eps=eps, gamma=gamma, beta=beta, mean_out=self.mean,
+                        rstd_out=self.rstd, scale_out=self.scale, shift_out=self.shift)
+        return dict(groups=self.groups, scale=self.scale, shift=self.shift)
 
     @property
     def stats(self):

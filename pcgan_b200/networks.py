@@ -19,7 +19,7 @@ from torch.nn import init
 from . import _lib as L
 from . import custom_ops as CO
 from . import ops
-from .engine import Arena, ConvRT, NormState, Pool, WeightBank, accumulate_grad, zeros_act
+from .engine import Arena, ConvRT, NormState, Pool, RunningStats, WeightBank, accumulate_grad, zeros_act
 from .plan import Geom, OutMap
 
 EPS = 1e-5
@@ -29,14 +29,16 @@ MOMENTUM = 0.1
 # ---------------------------------------------------------------------------------------
 # small shared pieces
 # ---------------------------------------------------------------------------------------
-def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, *, gamma=None, beta=None, rmean=None, rvar=None):
-    """conv (+bias) with statistics in the epilogue, then the tiny finalize kernel."""
+def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, running: RunningStats, *, gamma=None, beta=None, rmean=None,
+                  rvar=None, nbt=None):
+    """conv (+bias) with statistics in the epilogue.  The statistics are finalized by the norm_apply that consumes them
+    (NormState.apply_kw) and the running statistics by the pass's one batched launch (`running`)."""
     if not ns.pooled:
         ns.stats.zero_()
     ns.affine = gamma is not None
     conv.forward(xbuf, rbuf, ns.stats)
-    ops.norm_finalize(ns.stats, ns.groups, ns.c, count, eps=EPS, momentum=MOMENTUM, gamma=gamma, beta=beta,
-                      mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, running_mean=rmean, running_var=rvar)
+    ns.fused = (count, gamma, beta)
+    running.add(ns, count, rmean, rvar, nbt, MOMENTUM)
 
 
 def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count, dx, dx_pad, *, res=None, res_pad=0,
@@ -150,6 +152,7 @@ class _GenProgram:
         ws.head_sums = ws.sums_arena.take((1, 8, 2))
         ws.stats_arena.finalize()
         ws.sums_arena.finalize()
+        ws.running = RunningStats(dev)
         return ws
 
     # ---------------------------------------------------------------- forward
@@ -159,30 +162,30 @@ class _GenProgram:
         h2, h4 = S // 2, S // 4
         self.bank.ensure_packed()
         ws.stats_arena.zero()
+        ws.running.begin()
         ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_REFLECT)
-        _unit_forward(self.stem, ws.x0, ws.r1, ws.n1, S * S, rmean=m[2].running_mean, rvar=m[2].running_var)
-        ops.norm_apply(ws.r1, self.g_r1, ws.a1, self.g_a1, y_halo=L.HALO_ZERO, scale=ws.n1.scale, shift=ws.n1.shift, groups=N, act=L.ACT_RELU)
-        _unit_forward(self.down1, ws.a1, ws.r2, ws.n2, h2 * h2, rmean=m[5].running_mean, rvar=m[5].running_var)
-        ops.norm_apply(ws.r2, self.g_r2, ws.a2, self.g_a2, y_halo=L.HALO_ZERO, scale=ws.n2.scale, shift=ws.n2.shift, groups=N, act=L.ACT_RELU)
-        _unit_forward(self.down2, ws.a2, ws.r3, ws.n3, h4 * h4, rmean=m[8].running_mean, rvar=m[8].running_var)
+        _unit_forward(self.stem, ws.x0, ws.r1, ws.n1, S * S, ws.running, rmean=m[2].running_mean, rvar=m[2].running_var)
+        ops.norm_apply(ws.r1, self.g_r1, ws.a1, self.g_a1, y_halo=L.HALO_ZERO, **ws.n1.apply_kw(), act=L.ACT_RELU)
+        _unit_forward(self.down1, ws.a1, ws.r2, ws.n2, h2 * h2, ws.running, rmean=m[5].running_mean, rvar=m[5].running_var)
+        ops.norm_apply(ws.r2, self.g_r2, ws.a2, self.g_a2, y_halo=L.HALO_ZERO, **ws.n2.apply_kw(), act=L.ACT_RELU)
+        _unit_forward(self.down2, ws.a2, ws.r3, ws.n3, h4 * h4, ws.running, rmean=m[8].running_mean, rvar=m[8].running_var)
         nblk = len(self.blocks)
-        ops.norm_apply(ws.r3, self.g_r3, ws.b[0], self.g_b, y_halo=L.HALO_REFLECT if nblk else L.HALO_ZERO, scale=ws.n3.scale,
-                       shift=ws.n3.shift, groups=N, act=L.ACT_RELU)
+        ops.norm_apply(ws.r3, self.g_r3, ws.b[0], self.g_b, y_halo=L.HALO_REFLECT if nblk else L.HALO_ZERO, **ws.n3.apply_kw(), act=L.ACT_RELU)
         for i, (ca, cb, na_mod, nb_mod) in enumerate(self.blocks):
-            _unit_forward(ca, ws.b[i], ws.ra[i], ws.na[i], h4 * h4, rmean=na_mod.running_mean, rvar=na_mod.running_var)
-            ops.norm_apply(ws.ra[i], self.g_r3, ws.h[i], self.g_b, y_halo=L.HALO_REFLECT, scale=ws.na[i].scale, shift=ws.na[i].shift,
-                           groups=N, act=L.ACT_RELU)
-            _unit_forward(cb, ws.h[i], ws.rb[i], ws.nb[i], h4 * h4, rmean=nb_mod.running_mean, rvar=nb_mod.running_var)
+            _unit_forward(ca, ws.b[i], ws.ra[i], ws.na[i], h4 * h4, ws.running, rmean=na_mod.running_mean, rvar=na_mod.running_var)
+            ops.norm_apply(ws.ra[i], self.g_r3, ws.h[i], self.g_b, y_halo=L.HALO_REFLECT, **ws.na[i].apply_kw(), act=L.ACT_RELU)
+            _unit_forward(cb, ws.h[i], ws.rb[i], ws.nb[i], h4 * h4, ws.running, rmean=nb_mod.running_mean, rvar=nb_mod.running_var)
             last = i == nblk - 1
             # x + conv_block(x) (networks.py:650-652): residual added after the norm, no activation
             ops.norm_apply(ws.rb[i], self.g_r3, ws.b[i + 1], self.g_b, y_halo=L.HALO_ZERO if last else L.HALO_REFLECT,
-                           scale=ws.nb[i].scale, shift=ws.nb[i].shift, groups=N, res=ws.b[i], res_pad=1, act=L.ACT_NONE)
-        _unit_forward(self.up1, ws.b[nblk], ws.u1r, ws.nu1, h2 * h2, rmean=m[self.i_up1 + 1].running_mean, rvar=m[self.i_up1 + 1].running_var)
-        ops.norm_apply(ws.u1r, self.g_u1r, ws.u1, self.g_u1, y_halo=L.HALO_ZERO, scale=ws.nu1.scale, shift=ws.nu1.shift, groups=N, act=L.ACT_RELU)
-        _unit_forward(self.up2, ws.u1, ws.u2r, ws.nu2, S * S, rmean=m[self.i_up2 + 1].running_mean, rvar=m[self.i_up2 + 1].running_var)
-        ops.norm_apply(ws.u2r, self.g_u2r, ws.u2, self.g_u2, y_halo=L.HALO_REFLECT, scale=ws.nu2.scale, shift=ws.nu2.shift, groups=N, act=L.ACT_RELU)
+                           **ws.nb[i].apply_kw(), res=ws.b[i], res_pad=1, act=L.ACT_NONE)
+        _unit_forward(self.up1, ws.b[nblk], ws.u1r, ws.nu1, h2 * h2, ws.running, rmean=m[self.i_up1 + 1].running_mean, rvar=m[self.i_up1 + 1].running_var)
+        ops.norm_apply(ws.u1r, self.g_u1r, ws.u1, self.g_u1, y_halo=L.HALO_ZERO, **ws.nu1.apply_kw(), act=L.ACT_RELU)
+        _unit_forward(self.up2, ws.u1, ws.u2r, ws.nu2, S * S, ws.running, rmean=m[self.i_up2 + 1].running_mean, rvar=m[self.i_up2 + 1].running_var)
+        ops.norm_apply(ws.u2r, self.g_u2r, ws.u2, self.g_u2, y_halo=L.HALO_REFLECT, **ws.nu2.apply_kw(), act=L.ACT_RELU)
         out = torch.empty(N, self.mod.output_nc, S, S, device=self.dev)
         self.head.forward(ws.u2, out)
+        ws.running.flush()
         return out, ws
 
     # --------------------------------------------------------------- backward
@@ -403,6 +406,7 @@ class _DiscProgram:
         ws.l0_sums = ws.sums_arena.take((1, self.chans[0], 2))
         ws.stats_arena.finalize()
         ws.sums_arena.finalize()
+        ws.running = RunningStats(dev)
         return ws
 
     def forward(self, x, z):
@@ -410,18 +414,18 @@ class _DiscProgram:
         ws = self.pool.take(0)
         self.bank.ensure_packed()
         ws.stats_arena.zero()
+        ws.running.begin()
         ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_ZERO)
         self.convs[0].forward(ws.x0, ws.y[0])
         for li in range(1, len(self.sizes)):
             bn = m[self.idx[li] + 1]
             cnt = N * self.sizes[li] ** 2
-            _unit_forward(self.convs[li], ws.y[li - 1], ws.r[li], ws.ns[li], cnt, gamma=bn.weight.detach(), beta=bn.bias.detach(),
-                          rmean=bn.running_mean, rvar=bn.running_var)
-            bn.num_batches_tracked += 1
-            ops.norm_apply(ws.r[li], self.g_r[li], ws.y[li], self.g_y[li], y_halo=L.HALO_ZERO, scale=ws.ns[li].scale,
-                           shift=ws.ns[li].shift, groups=1, act=L.ACT_LRELU, act_slope=0.2)
+            _unit_forward(self.convs[li], ws.y[li - 1], ws.r[li], ws.ns[li], cnt, ws.running, gamma=bn.weight.detach(),
+                          beta=bn.bias.detach(), rmean=bn.running_mean, rvar=bn.running_var, nbt=bn.num_batches_tracked)
+            ops.norm_apply(ws.r[li], self.g_r[li], ws.y[li], self.g_y[li], y_halo=L.HALO_ZERO, **ws.ns[li].apply_kw(), act=L.ACT_LRELU, act_slope=0.2)
         out = torch.empty(N, 1, self.so, self.so, device=self.dev)
         self.head.forward(ws.y[-1], out)
+        ws.running.flush()
         return out, ws
 
     def backward(self, ws, out, dout, need_dx, need_w, need_dz=False):
@@ -705,13 +709,21 @@ class _EncWorkspace:
     pass
 
 
-def _bn_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, bn, mask=None):
+def _bn_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, bn, running: RunningStats = None, mask=None):
     """conv -> [Dropout2d mask] -> BatchNorm2d statistics (training mode, running stats updated, resnet.py:57-59).
-    With a mask the convolution emits per-sample statistics that the finalize kernel combines with the mask."""
+    With `running` the statistics are finalized by the consuming norm_apply and the running statistics by the pass's
+    batched launch; without (the shortcut BatchNorm, whose scale / shift the block's last norm_apply needs as plain
+    arrays) or with a dropout mask (the convolution then emits per-sample statistics that are combined with the mask)
+    the separate finalize kernel runs."""
     ns.affine = True
     if not ns.pooled:
         ns.stats.zero_()
     conv.forward(xbuf, rbuf, ns.stats)
+    if running is not None and mask is None and ns.stats_groups == ns.groups:
+        ns.fused = (count, bn.weight.detach(), bn.bias.detach())
+        running.add(ns, count, bn.running_mean, bn.running_var, bn.num_batches_tracked, MOMENTUM)
+        return
+    ns.fused = None
     kw = dict(eps=EPS, momentum=MOMENTUM, gamma=bn.weight.detach(), beta=bn.bias.detach(), mean=ns.mean, rstd=ns.rstd,
               scale=ns.scale, shift=ns.shift, running_mean=bn.running_mean, running_var=bn.running_var)
     if ns.stats_groups > ns.groups:
@@ -763,19 +775,19 @@ class _EncBlock:
             w.rd, w.nd = zeros_act(self.g_r, dev), NormState(1, self.c, dev, stats_arena, sums_arena)
         return w
 
-    def forward(self, xbuf, w, masks=None):
+    def forward(self, xbuf, w, masks=None, running=None):
         hd, cnt = self.holder, self.N * self.h * self.h
         w.m1, w.m2 = masks if masks is not None else (None, None)
-        _bn_forward(self.c1, xbuf, w.ra, w.na, cnt, hd.bn1, w.m1)
-        ops.norm_apply(w.ra, self.g_r, w.h, self.g_y, y_halo=L.HALO_ZERO, scale=w.na.scale, shift=w.na.shift, groups=1,
+        _bn_forward(self.c1, xbuf, w.ra, w.na, cnt, hd.bn1, running, w.m1)
+        ops.norm_apply(w.ra, self.g_r, w.h, self.g_y, y_halo=L.HALO_ZERO, **w.na.apply_kw(),
                        drop_mask=w.m1, act=L.ACT_RELU)
-        _bn_forward(self.c2, w.h, w.rb, w.nb, cnt, hd.bn2, w.m2)
+        _bn_forward(self.c2, w.h, w.rb, w.nb, cnt, hd.bn2, running, w.m2)
         if self.ds is not None:
-            _bn_forward(self.ds, xbuf, w.rd, w.nd, cnt, hd.downsample[1])
-            ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, scale=w.nb.scale, shift=w.nb.shift, groups=1,
+            _bn_forward(self.ds, xbuf, w.rd, w.nd, cnt, hd.downsample[1])     # explicit finalize: res_scale / res_shift below
+            ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, **w.nb.apply_kw(),
                            drop_mask=w.m2, res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1, act=L.ACT_RELU)
         else:
-            ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, scale=w.nb.scale, shift=w.nb.shift, groups=1,
+            ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, **w.nb.apply_kw(),
                            drop_mask=w.m2, res=xbuf, res_pad=1, act=L.ACT_RELU)
         return w.y
 
@@ -843,11 +855,11 @@ class _EncHead:
         w.pm = None
         return w
 
-    def forward(self, fbuf, w, mask=None):
+    def forward(self, fbuf, w, mask=None, running=None):
         N, hf = self.N, self.hf
         w.pm = mask
-        _bn_forward(self.c1, fbuf, w.rh, w.nh, N * hf * hf, self.seq[1])
-        ops.norm_apply(w.rh, self.g_rh, w.hh, self.g_hh, y_halo=L.HALO_ZERO, scale=w.nh.scale, shift=w.nh.shift, groups=1,
+        _bn_forward(self.c1, fbuf, w.rh, w.nh, N * hf * hf, self.seq[1], running)
+        ops.norm_apply(w.rh, self.g_rh, w.hh, self.g_hh, y_halo=L.HALO_ZERO, **w.nh.apply_kw(),
                        act=L.ACT_LRELU, act_slope=self.slope, post_mask=mask)
         self.c2.forward(w.hh, w.fin, w.nfin.stats)
         return (w.nfin.stats[:, 0, 0] / float(hf * hf)).view(N, 1, 1, 1)
@@ -927,6 +939,7 @@ class _EncProgram:
         ws.heads = [h.new_ws(dev, ws.stats_arena, ws.sums_arena) for h in self.heads]
         ws.stats_arena.finalize()
         ws.sums_arena.finalize()
+        ws.running = RunningStats(dev)
         return ws
 
     def _mask(self, c, p):
@@ -945,18 +958,20 @@ class _EncProgram:
         ws = self.pool.take(0)
         self.bank.ensure_packed()
         ws.stats_arena.zero()
+        ws.running.begin()
         ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
         s2 = self.S // 2
-        _bn_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, rn.bn1)
-        ops.norm_apply(ws.r0, self.g_r0, ws.a0, self.g_a0, scale=ws.n0.scale, shift=ws.n0.shift, groups=1, act=L.ACT_RELU)
+        _bn_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, rn.bn1, ws.running)
+        ops.norm_apply(ws.r0, self.g_r0, ws.a0, self.g_a0, **ws.n0.apply_kw(), act=L.ACT_RELU)
         ops.maxpool_fwd(ws.a0, self.g_a0, ws.p, 1, ws.idx)
         cur = ws.p
         for blk, w in zip(self.blocks, ws.blk):
             masks = (self._mask(blk.c, self.p_drop), self._mask(blk.c, self.p_drop)) if self.p_drop > 0 else None
-            cur = blk.forward(cur, w, masks)
+            cur = blk.forward(cur, w, masks, ws.running)
         outs = []
         for h, w in zip(self.heads, ws.heads):
-            outs.append(h.forward(cur, w, self._mask(h.nf, mod.head_dropout) if self.head_drop else None))
+            outs.append(h.forward(cur, w, self._mask(h.nf, mod.head_dropout) if self.head_drop else None, ws.running))
+        ws.running.flush()
         return outs, ws
 
     def backward(self, ws, gys, need_dx, need_w):

@@ -126,6 +126,24 @@ def scatter_f32_batched(table, count, max_n, accumulate=True):
         L.check(L.load().pcgan_scatter_f32_batched(_ptr(table), count, max_n, int(accumulate), _stream()), "scatter_f32_batched")
 
 
+def running_table(items, device):
+    """Device table of pcgan_running_item: items = [(stats, running_mean, running_var, num_batches_tracked, groups, c, count,
+    momentum)] (tensors or None)."""
+    import struct
+    raw = bytearray()
+    for st, rm, rv, nbt, groups, c, count, mom in items:
+        raw += struct.pack("<qqqqiiff", st.data_ptr(), rm.data_ptr() if rm is not None else 0, rv.data_ptr() if rv is not None else 0,
+                           nbt.data_ptr() if nbt is not None else 0, groups, c, float(count), float(mom))
+    t = torch.frombuffer(raw, dtype=torch.uint8).clone().to(device)
+    return t, max(it[5] for it in items)
+
+
+def norm_running_batched(table, count, max_c):
+    _count()
+    with _Timed("norm_running_batched"):
+        L.check(L.load().pcgan_norm_running_batched(_ptr(table), count, max_c, _stream()), "norm_running_batched")
+
+
 def pack_nchw(src, dst, g: Geom, *, z=None, mul_out=None, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO):
     """src: NCHW fp32 [n, cs, h, w] -> dst buffer of geometry g (resized to g.h x g.w when they differ)."""
     n, cs, h, w = src.shape
@@ -160,12 +178,16 @@ def norm_finalize(stats, groups, c, count, *, eps=1e-5, momentum=0.1, gamma=None
 
 
 def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shift=None, groups=1, res=None, res_pad=0,
-               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, post_mask=None):
+               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, post_mask=None,
+               stats=None, count=0.0, eps=1e-5, gamma=None, beta=None, mean_out=None, rstd_out=None, scale_out=None, shift_out=None):
+    """stats given: the finalize (statistics -> scale / shift) is fused into this launch; scale / shift are ignored."""
     assert (xg.n, xg.h, xg.w, xg.c) == (yg.n, yg.h, yg.w, yg.c)
     a = L.NormApplyArgs(x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad, y=_ptr(y), y_pad=yg.pad, y_halo=y_halo,
                         n=xg.n, h=xg.h, w=xg.w, c=xg.c, scale=_ptr(scale), shift=_ptr(shift), groups=groups,
                         res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
-                        drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, post_mask=_ptr(post_mask))
+                        drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, post_mask=_ptr(post_mask),
+                        stats=_ptr(stats), count=float(count), eps=eps, gamma=_ptr(gamma), beta=_ptr(beta),
+                        mean_out=_ptr(mean_out), rstd_out=_ptr(rstd_out), scale_out=_ptr(scale_out), shift_out=_ptr(shift_out))
     _count()
     with _Timed("norm_apply"):
         L.check(L.load().pcgan_norm_apply(C.byref(a), _stream()), "norm_apply")
