@@ -75,51 +75,57 @@ __device__ __forceinline__ void bilinear_setup(int o, int in, int out, int& i0, 
   l0 = 1.f - l1;
 }
 
+// grid (x blocks, padded rows, samples): no per-thread division; one 16-byte store per 8 destination channels
 __global__ void pack_nchw_kernel(pcgan_pack_args a) {
   griddep_wait();
   griddep_launch();
   const int hp = a.ho + 2 * a.pad, wp = a.wo + 2 * a.pad;
-  const int64_t total = static_cast<int64_t>(a.n) * hp * wp;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y;
+  const int n = blockIdx.z;
+  if (px >= wp) return;
   const int64_t nstride = a.dst_n_stride ? a.dst_n_stride : static_cast<int64_t>(hp) * wp * a.cd;
   const bool resize = (a.ho != a.h) || (a.wo != a.w);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int px = static_cast<int>(i % wp);
-    const int py = static_cast<int>((i / wp) % hp);
-    const int n = static_cast<int>(i / (static_cast<int64_t>(wp) * hp));
-    int y = py - a.pad, x = px - a.pad;
-    const bool halo = y < 0 || y >= a.ho || x < 0 || x >= a.wo;
-    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(a.dst) + n * nstride + (static_cast<int64_t>(py) * wp + px) * a.cd;
-    if (halo && a.halo == PCGAN_HALO_ZERO) {
-      for (int c = 0; c < a.cd; c += 8) *reinterpret_cast<uint4*>(d + c) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    y = reflect_idx(y, a.ho);
-    x = reflect_idx(x, a.wo);
-    int y0 = y, y1 = y, x0 = x, x1 = x;
-    float ly0 = 1.f, ly1 = 0.f, lx0 = 1.f, lx1 = 0.f;
-    if (resize) {
-      bilinear_setup(y, a.h, a.ho, y0, y1, ly0, ly1);
-      bilinear_setup(x, a.w, a.wo, x0, x1, lx0, lx1);
-    }
-    for (int c = 0; c < a.cd; ++c) {
-      float v = 0.f;
+  int y = py - a.pad, x = px - a.pad;
+  const bool halo = y < 0 || y >= a.ho || x < 0 || x >= a.wo;
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(a.dst) + n * nstride + (static_cast<int64_t>(py) * wp + px) * a.cd;
+  if (halo && a.halo == PCGAN_HALO_ZERO) {
+    for (int c = 0; c < a.cd; c += 8) *reinterpret_cast<uint4*>(d + c) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  y = reflect_idx(y, a.ho);
+  x = reflect_idx(x, a.wo);
+  int y0 = y, y1 = y, x0 = x, x1 = x;
+  float ly0 = 1.f, ly1 = 0.f, lx0 = 1.f, lx1 = 0.f;
+  if (resize) {
+    bilinear_setup(y, a.h, a.ho, y0, y1, ly0, ly1);
+    bilinear_setup(x, a.w, a.wo, x0, x1, lx0, lx1);
+  }
+  const int64_t plane = static_cast<int64_t>(a.h) * a.w;
+  for (int cb = 0; cb < a.cd; cb += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb + j;
+      float t = 0.f;
       if (c < a.cs) {
-        const float* s = a.src + (static_cast<int64_t>(n) * a.cs + c) * a.h * a.w;
+        const float* s = a.src + (static_cast<int64_t>(n) * a.cs + c) * plane;
         if (resize) {
-          v = ly0 * (lx0 * s[y0 * a.w + x0] + lx1 * s[y0 * a.w + x1]) +
-              ly1 * (lx0 * s[y1 * a.w + x0] + lx1 * s[y1 * a.w + x1]);
+          t = ly0 * (lx0 * __ldg(s + y0 * a.w + x0) + lx1 * __ldg(s + y0 * a.w + x1)) +
+              ly1 * (lx0 * __ldg(s + y1 * a.w + x0) + lx1 * __ldg(s + y1 * a.w + x1));
         } else {
-          v = s[y * a.w + x];
+          t = __ldg(s + y * a.w + x);
           if (a.mul_out) {
-            const float t = a.mul_out[(static_cast<int64_t>(n) * a.cs + c) * a.h * a.w + y * a.w + x];
-            v *= a.mul_kind == PCGAN_ACT_SIGMOID ? t * (1.f - t) : 1.f - t * t;
+            const float o = __ldg(a.mul_out + (static_cast<int64_t>(n) * a.cs + c) * plane + y * a.w + x);
+            t *= a.mul_kind == PCGAN_ACT_SIGMOID ? o * (1.f - o) : 1.f - o * o;
           }
         }
       } else if (c == a.cs && a.z != nullptr) {
-        v = a.z[n];
+        t = a.z[n];
       }
-      d[c] = __float2bfloat16(v);
+      v[j] = t;
     }
+    store8(d + cb, v);
   }
 }
 
@@ -173,39 +179,40 @@ __global__ void unpack_resize_bwd_kernel(pcgan_unpack_args a) {
   }
 }
 
+// grid (x blocks, output rows, planes): the row coefficients are per block, no per-thread division
 __global__ void resize_nchw_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t planes, int h, int w,
                                        int ho, int wo) {
   griddep_wait();
   griddep_launch();
-  const int64_t total = planes * ho * wo;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = static_cast<int>(i % wo);
-    const int y = static_cast<int>((i / wo) % ho);
-    const int64_t pl = i / (static_cast<int64_t>(wo) * ho);
-    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
-    bilinear_setup(y, h, ho, y0, y1, ly0, ly1);
-    bilinear_setup(x, w, wo, x0, x1, lx0, lx1);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= wo) return;
+  int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+  bilinear_setup(y, h, ho, y0, y1, ly0, ly1);
+  bilinear_setup(x, w, wo, x0, x1, lx0, lx1);
+  for (int64_t pl = blockIdx.z; pl < planes; pl += gridDim.z) {
     const float* s = src + pl * h * w;
-    dst[i] = ly0 * (lx0 * s[y0 * w + x0] + lx1 * s[y0 * w + x1]) + ly1 * (lx0 * s[y1 * w + x0] + lx1 * s[y1 * w + x1]);
+    dst[(pl * ho + y) * wo + x] = ly0 * (lx0 * __ldg(s + y0 * w + x0) + lx1 * __ldg(s + y0 * w + x1)) +
+                                  ly1 * (lx0 * __ldg(s + y1 * w + x0) + lx1 * __ldg(s + y1 * w + x1));
   }
 }
 
+// adjoint: grid (x blocks, source rows, planes); every source pixel gathers the resized pixels whose footprint touches it
 __global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __restrict__ gsrc, int64_t planes, int h, int w,
                                        int ho, int wo) {
   griddep_wait();
   griddep_launch();
-  const int64_t total = planes * h * w;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
   const float sy = ho > 1 ? static_cast<float>(h - 1) / static_cast<float>(ho - 1) : 0.f;
   const float sx = wo > 1 ? static_cast<float>(w - 1) / static_cast<float>(wo - 1) : 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = static_cast<int>(i % w);
-    const int y = static_cast<int>((i / w) % h);
-    const int64_t pl = i / (static_cast<int64_t>(w) * h);
-    int ylo = sy > 0.f ? static_cast<int>(floorf((y - 1) / sy)) : 0;
-    int yhi = sy > 0.f ? static_cast<int>(ceilf((y + 1) / sy)) : ho - 1;
-    int xlo = sx > 0.f ? static_cast<int>(floorf((x - 1) / sx)) : 0;
-    int xhi = sx > 0.f ? static_cast<int>(ceilf((x + 1) / sx)) : wo - 1;
-    ylo = max(ylo, 0); xlo = max(xlo, 0); yhi = min(yhi, ho - 1); xhi = min(xhi, wo - 1);
+  int ylo = sy > 0.f ? static_cast<int>(floorf((y - 1) / sy)) : 0;
+  int yhi = sy > 0.f ? static_cast<int>(ceilf((y + 1) / sy)) : ho - 1;
+  int xlo = sx > 0.f ? static_cast<int>(floorf((x - 1) / sx)) : 0;
+  int xhi = sx > 0.f ? static_cast<int>(ceilf((x + 1) / sx)) : wo - 1;
+  ylo = max(ylo, 0); xlo = max(xlo, 0); yhi = min(yhi, ho - 1); xhi = min(xhi, wo - 1);
+  for (int64_t pl = blockIdx.z; pl < planes; pl += gridDim.z) {
     const float* g = gdst + pl * ho * wo;
     float acc = 0.f;
     for (int yy = ylo; yy <= yhi; ++yy) {
@@ -217,10 +224,10 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __
         int x0, x1; float m0, m1;
         bilinear_setup(xx, w, wo, x0, x1, m0, m1);
         const float wx = (x0 == x ? m0 : 0.f) + (x1 == x ? m1 : 0.f);
-        if (wx != 0.f) acc += wy * wx * g[yy * wo + xx];
+        if (wx != 0.f) acc += wy * wx * __ldg(g + yy * wo + xx);
       }
     }
-    gsrc[i] = acc;
+    gsrc[(pl * h + y) * w + x] = acc;
   }
 }
 
@@ -430,8 +437,10 @@ extern "C" int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t s) {
   if (a->n < 1 || a->h < 1 || a->w < 1 || a->ho < 1 || a->wo < 1 || a->pad < 0) return fail(PCGAN_ERR_INVALID, "pack_nchw: bad geometry");
   if (a->halo == PCGAN_HALO_REFLECT && (a->pad >= a->ho || a->pad >= a->wo)) return fail(PCGAN_ERR_INVALID, "pack_nchw: reflect pad too large");
   if (a->mul_out && (a->ho != a->h || a->wo != a->w)) return fail(PCGAN_ERR_UNSUPPORTED, "pack_nchw: mul_out with resize");
-  const int64_t total = static_cast<int64_t>(a->n) * (a->ho + 2 * a->pad) * (a->wo + 2 * a->pad);
-  PCGAN_CUDA_OK(launch_pdl(pack_nchw_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, *a));
+  if (a->n > 65535 || a->ho + 2 * a->pad > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "pack_nchw: n / rows out of range");
+  const int wp = a->wo + 2 * a->pad;
+  const int bx = wp >= 128 ? 128 : 64;
+  PCGAN_CUDA_OK(launch_pdl(pack_nchw_kernel, dim3((wp + bx - 1) / bx, a->ho + 2 * a->pad, a->n), dim3(bx), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("pack_nchw_kernel");
   return PCGAN_OK;
 }
@@ -439,7 +448,9 @@ extern "C" int pcgan_pack_nchw(const pcgan_pack_args* a, pcgan_stream_t s) {
 extern "C" int pcgan_resize_nchw_fwd(const float* src, float* dst, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo,
                                      pcgan_stream_t s) {
   if (!src || !dst || planes < 1 || h < 1 || w < 1 || ho < 1 || wo < 1) return fail(PCGAN_ERR_INVALID, "resize_fwd: bad argument");
-  PCGAN_CUDA_OK(launch_pdl(resize_nchw_fwd_kernel, dim3(grid_for(planes * ho * wo)), dim3(kThreads), 0, STREAM(s), 1, src, dst, planes, h, w, ho, wo));
+  if (ho > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "resize_fwd: ho out of range");
+  PCGAN_CUDA_OK(launch_pdl(resize_nchw_fwd_kernel, dim3((wo + 127) / 128, ho, static_cast<unsigned>(planes < 64 ? planes : 64)), dim3(128), 0, STREAM(s), 1,
+                           src, dst, planes, h, w, ho, wo));
   PCGAN_LAUNCH_OK("resize_nchw_fwd_kernel");
   return PCGAN_OK;
 }
@@ -447,7 +458,9 @@ extern "C" int pcgan_resize_nchw_fwd(const float* src, float* dst, int64_t plane
 extern "C" int pcgan_resize_nchw_bwd(const float* gdst, float* gsrc, int64_t planes, int32_t h, int32_t w, int32_t ho, int32_t wo,
                                      pcgan_stream_t s) {
   if (!gdst || !gsrc || planes < 1 || h < 1 || w < 1 || ho < 1 || wo < 1) return fail(PCGAN_ERR_INVALID, "resize_bwd: bad argument");
-  PCGAN_CUDA_OK(launch_pdl(resize_nchw_bwd_kernel, dim3(grid_for(planes * h * w)), dim3(kThreads), 0, STREAM(s), 1, gdst, gsrc, planes, h, w, ho, wo));
+  if (h > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "resize_bwd: h out of range");
+  PCGAN_CUDA_OK(launch_pdl(resize_nchw_bwd_kernel, dim3((w + 127) / 128, h, static_cast<unsigned>(planes < 64 ? planes : 64)), dim3(128), 0, STREAM(s), 1,
+                           gdst, gsrc, planes, h, w, ho, wo));
   PCGAN_LAUNCH_OK("resize_nchw_bwd_kernel");
   return PCGAN_OK;
 }
