@@ -176,3 +176,42 @@ def test_step_at_256_and_odd_batch():
                 assert 0.0 <= got[k] < 2e-2, (B, S, k, got[k], want[k])
             else:
                 assert abs(got[k] - want[k]) <= 0.04 * abs(want[k]) + 1e-5, (B, S, k, got[k], want[k])
+
+
+def test_checkpoint_round_trip_and_lr_schedule(tmp_path):
+    """save_networks / load_networks (base_model.py:96-136) and update_learning_rate (:72-76) around a captured step: the
+    learning rate lives on the device in graph mode and the scheduler still drives it."""
+    B, S = 2, 64
+    opt = default_options(batchSize=B, gpu_ids=[0], fineSize=S, loadSize=S, cuda_graph=True, cuda_graph_warmup=1, niter=2, niter_decay=4,
+                          checkpoints_dir=str(tmp_path), name="ckpt", which_model_netG="resnet_6blocks")
+    model = WSGANEmbModel()
+    model.initialize(opt)
+    model.setup(opt)
+    a, b, label = O.synthetic_batch(B, S, 950, device=DEV)
+    for _ in range(3):      # eager, capture, replay
+        model.set_input({"A": a, "B": b, "label": label})
+        model.optimize_parameters()
+    lr0 = float(model.optimizer_G.param_groups[0]["lr"])
+    model.update_learning_rate()
+    model.update_learning_rate()
+    lr1 = float(model.optimizer_G.param_groups[0]["lr"])
+    assert lr0 == pytest.approx(2e-4) and 0 < lr1 < lr0
+    w0 = model.netG.module.model[1].weight.detach().clone()
+    model.set_input({"A": a, "B": b, "label": label})
+    model.optimize_parameters()      # replay with the decayed rate
+    step = float((model.netG.module.model[1].weight.detach() - w0).abs().max())
+    assert 0 < step < 2 * lr0, (step, lr1)      # Adam: |update| is of the order of the learning rate
+    model.save_networks("latest")
+    other = WSGANEmbModel()
+    other.initialize(default_options(batchSize=B, gpu_ids=[0], fineSize=S, loadSize=S, checkpoints_dir=str(tmp_path), name="ckpt",
+                                     which_model_netG="resnet_6blocks"))
+    other.load_networks("latest")
+    for n in ("G", "D", "E"):
+        sa, sb = getattr(model, "net" + n).module.state_dict(), getattr(other, "net" + n).module.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), (n, k)
+    # the loaded model trains on (packed operands are rebuilt from the loaded master weights)
+    other.set_input({"A": a, "B": b, "label": label})
+    other.optimize_parameters()
+    assert all(v == v for v in other.get_current_losses().values())
