@@ -9,10 +9,13 @@
 // Everything that distinguishes one convolution from another (padding mode, stride,
 // transposed phases, reflect halos, packed stems) is data in pcgan_igemm_desc.
 //
-// Warp roles (256 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (384 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-7 and 8-11 = two epilogue groups, one per TMEM
+// accumulator stage (TMEM lane quarter = warp % 4).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
-// (MMA <-> epilogue), persistent tile loop with a static stride schedule.
+// (MMA <-> epilogue), persistent tile loop with a static stride schedule. With
+// desc.pair the grid runs as clusters of two CTAs on adjacent M tiles that share the
+// B operand: each CTA loads half of it and multicasts that half to its peer.
 #include <cuda.h>
 #include <mutex>
 #include <stdarg.h>

@@ -584,52 +584,9 @@ def wmap_small_cout(w_shape, k: int) -> torch.Tensor:
     return idx.reshape(-1).to(torch.int32)
 
 
-def plan_wgrad_flat(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[int, int, int]], *, note="") -> IgemmSpec:
-    """Weight gradient over the flattened padded grid shared by both tensors (same n, hp, wp):
-    out[m][kidx*n_ch + c] = sum_q M[q][m] * Nt[q + dy*Wp + dx][c].  M must be zero wherever it is not a real
-    output-gradient (zero halo), so wrapped / out-of-range positions contribute nothing."""
-    assert (mg.n, mg.hp, mg.wp) == (ng.n, ng.hp, ng.wp)
-    s = IgemmSpec(kind=L.IGEMM_WGRAD, note=note)
-    P = mg.n * mg.hp * mg.wp
-    s.block_n = min(256, _ceil(n_ch, 64) * 64)
-    s.n_tiles = _ceil(n_ch, s.block_n)
-    s.m_tiles = _ceil(m_ch, 128)
-    s.m_valid, s.wg_ncols = m_ch, n_ch
-    s.a_dims = [mg.c, P, 1, 1, 1]
-    s.a_strides = [0, mg.c * 2, P * mg.c * 2, P * mg.c * 2, P * mg.c * 2]
-    s.a_box = [64, 64, 1, 1, 1]
-    s.b_dims = [ng.c, P, 1, 1, 1]
-    s.b_strides = [0, ng.c * 2, P * ng.c * 2, P * ng.c * 2, P * ng.c * 2]
-    s.b_box = [64, 64, 1, 1, 1]
-    kb = _ceil(P, 64)
-    s.t_count = [kb, 1, 1, 1]
-    s.a_step[0][0] = 64
-    s.b_step[0][0] = 64
-    for (dy, dx, kidx) in taps:
-        s.tap_off.append([dy * ng.wp + dx, 0, 0, 0])
-        s.tap_c0.append(0)
-        s.tap_bk.append(kidx * n_ch)
-    nk = max(k for _, _, k in taps) + 1
-    s.ldo = nk * n_ch
-    s.b_rows, s.b_k = m_ch, s.ldo
-    s.ksplit = _ksplit_for(kb, len(taps) * s.m_tiles * s.n_tiles)
-    s.flops = 2 * kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
-    return s
-
-
 # ------------------------------------------------------------------------------------------
 # Weight index maps: packed[i] = W.flatten()[idx[i]] (or 0 when idx[i] < 0)
 # ------------------------------------------------------------------------------------------
-def index_map(shape, fn, rows, k) -> torch.Tensor:
-    """Build an int32 [rows*k] gather map by calling fn(row, col) -> flat index into a tensor of `shape` or -1.
-    Slow generic path, used once per layer at construction."""
-    idx = torch.full((rows, k), -1, dtype=torch.int32)
-    for r in range(rows):
-        for c in range(k):
-            idx[r, c] = fn(r, c)
-    return idx.reshape(-1)
-
-
 def wmap_taps(w_shape, rows, taps, cin, *, transposed_layout=False, swap=False) -> torch.Tensor:
     """Vectorised map for per-tap layouts: packed[row][kidx*cin + c] = W[...] with taps = [(r, s, kidx)].
     OIHW weights (nn.Conv2d): row = o, c = i  (swap=False)  -> W[o][i][r][s]
