@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 10
+#define PCGAN_ABI_VERSION 11
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -147,6 +147,12 @@ typedef struct {
    * so each activation row is fetched once per filter ROW instead of once per filter TAP.  n_valid <= shift_cpad <= 8,
    * shift_taps*shift_cpad <= 32 = block_n, no statistics. */
   int32_t shift_taps, shift_cpad;
+  /* KMAJOR windowed A (a_window == 8): for 8-channel inputs (image stems, gradients of 3-channel heads) whose filter row
+   * of up to 8 taps x 8 channels is one K chunk.  A is the plain tensor (a.dims[0] == a.box[0] == 8, 16-byte pixels);
+   * a.box[1] = rows + 7 consecutive pixels of one image row (or of the flattened grid) are fetched ONCE per filter row and
+   * row m of the tile reads the 64 elements starting at pixel m, through an overlapping shared-memory descriptor, instead
+   * of fetching every pixel 8 times.  Packed weights as for the overlapping-stride form: [cout][tap][8 pixels x 8]. */
+  int32_t a_window;
 } pcgan_igemm_desc;
 
 typedef struct pcgan_igemm_plan pcgan_igemm_plan;
@@ -353,6 +359,16 @@ int pcgan_loss(const pcgan_loss_args* a, pcgan_stream_t stream);
  * so the launch is graph-capturable. */
 int pcgan_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1, float beta2,
                float eps, const float* step, pcgan_stream_t stream);
+
+/* Multi-tensor form of pcgan_adam: one launch updates every tensor of a parameter group (the two Adam steps of
+ * wsgan_emb_model.py:451-461 walk 48 + 13 tensors).  `step` (device scalar) holds the number of updates already applied:
+ * the update uses step + 1 for the bias corrections and a second, one-thread launch behind it stores step + 1. */
+typedef struct {
+  float* p; const float* g; float* m; float* v;
+  int64_t n;
+} pcgan_adam_item;
+int pcgan_adam_batched(const pcgan_adam_item* items, int32_t count, int64_t max_n, const float* lr, float beta1, float beta2,
+                       float eps, float* step, pcgan_stream_t stream);
 
 #ifdef __cplusplus
 }

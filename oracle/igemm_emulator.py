@@ -14,8 +14,9 @@ ACT = {0: lambda x, s: x, 1: lambda x, s: torch.relu(x), 2: lambda x, s: torch.w
 
 def tma_gather(flat, dims, strides_bytes, box, coords):
     """flat: 1-D float tensor (bf16 values); coords: [T, 5] int64 start coordinates.
-    Returns [T, rows, 64]; rows enumerate box dims 1..4 with dim 1 fastest."""
+    Returns [T, rows, box[0]]; rows enumerate box dims 1..4 with dim 1 fastest."""
     T = coords.shape[0]
+    inner = box[0]
     rows = box[1] * box[2] * box[3] * box[4]
     r = torch.arange(rows)
     loc = []
@@ -23,9 +24,9 @@ def tma_gather(flat, dims, strides_bytes, box, coords):
     for d in range(1, 5):
         loc.append(rem % box[d])
         rem = rem // box[d]
-    k = torch.arange(64)
+    k = torch.arange(inner)
     # element coordinates
-    c0 = coords[:, 0].view(T, 1, 1) + k.view(1, 1, 64)
+    c0 = coords[:, 0].view(T, 1, 1) + k.view(1, 1, inner)
     valid = (c0 >= 0) & (c0 < dims[0])
     addr = c0.clone()
     for d in range(1, 5):
@@ -35,7 +36,7 @@ def tma_gather(flat, dims, strides_bytes, box, coords):
     addr = torch.where(valid, addr, torch.zeros_like(addr))
     if addr.numel() and (int(addr.max()) >= flat.numel() or int(addr.min()) < 0):
         raise IndexError("in-bounds TMA element outside the buffer: max %d numel %d" % (int(addr.max()), flat.numel()))
-    vals = flat[addr.reshape(-1)].reshape(T, rows, 64)
+    vals = flat[addr.reshape(-1)].reshape(T, rows, inner)
     return torch.where(valid, vals, torch.zeros_like(vals))
 
 
@@ -58,8 +59,12 @@ def run_kmajor(s, a_flat, b_flat, out_flat, bias=None, stats=None):
     mt = torch.arange(m_tiles)
     dig = _digits(mt, s.t_count)
     ac = _coords(dig, s.a_base, s.a_step)
-    a_rows = s.a_box[1] * s.a_box[2] * s.a_box[3] * s.a_box[4]
+    a_window = getattr(s, "a_window", 0)
+    a_rows = s.a_box[1] * s.a_box[2] * s.a_box[3] * s.a_box[4] - (7 if a_window else 0)
     assert 1 <= a_rows <= 128
+    if a_window:
+        assert a_window == 8 and s.a_box[0] == 8 and s.a_dims[0] == 8 and s.a_strides[1] == 16 and s.cchunks == 1
+        assert s.a_box[2] == s.a_box[3] == s.a_box[4] == 1
     # epilogue row map
     r = torch.arange(128)
     valid = (r < a_rows).view(1, 128).expand(m_tiles, 128).clone()
@@ -97,6 +102,9 @@ def run_kmajor(s, a_flat, b_flat, out_flat, bias=None, stats=None):
                 coords = torch.stack([torch.full((m_tiles,), s.tap_c0[t] + cc * 64, dtype=torch.int64)] +
                                      [ac[d] + s.tap_off[t][d] for d in range(4)], dim=1)
                 A = tma_gather(a_flat, s.a_dims, s.a_strides, s.a_box, coords)  # [T, rows, 64]
+                if a_window:
+                    # windowed A: the box holds rows + 7 plain pixels of 8 channels; row m reads pixels m .. m+7
+                    A = torch.cat([A[:, j:j + a_rows, :] for j in range(8)], dim=2)
                 bc = torch.tensor([[s.tap_bk[t] + cc * 64, nt * s.block_n, 0, 0, 0]], dtype=torch.int64)
                 B = tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, bc)[0]  # [block_n, 64]
                 acc[:, :a_rows] += A @ B.t()

@@ -377,6 +377,56 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Multi-tensor form: blockIdx.y = tensor.  `step` holds the number of updates already applied; this update is number
+// step + 1 and step_inc_kernel, launched behind it, stores that.
+__global__ void adam_batched_kernel(const pcgan_adam_item* __restrict__ items, const float* lr_p, float b1, float b2, float eps,
+                                    const float* step_p) {
+  griddep_wait();
+  griddep_launch();
+  const pcgan_adam_item it = items[blockIdx.y];
+  const float lr = *lr_p, step = *step_p + 1.f;
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  const float step_size = lr / bc1, rsq_bc2 = rsqrtf(bc2);
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(it.p) | reinterpret_cast<uintptr_t>(it.g) | reinterpret_cast<uintptr_t>(it.m) |
+                     reinterpret_cast<uintptr_t>(it.v)) & 15) == 0;
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = it.n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(it.p);
+    const float4* g4 = reinterpret_cast<const float4*>(it.g);
+    float4* m4 = reinterpret_cast<float4*>(it.m);
+    float4* v4 = reinterpret_cast<float4*>(it.v);
+    for (int64_t i = tid; i < n4; i += nthr) {
+      const float4 g = g4[i];
+      float4 m = m4[i], v = v4[i], p = p4[i];
+      m.x = b1 * m.x + c1 * g.x; m.y = b1 * m.y + c1 * g.y; m.z = b1 * m.z + c1 * g.z; m.w = b1 * m.w + c1 * g.w;
+      v.x = b2 * v.x + c2 * g.x * g.x; v.y = b2 * v.y + c2 * g.y * g.y; v.z = b2 * v.z + c2 * g.z * g.z; v.w = b2 * v.w + c2 * g.w * g.w;
+      p.x -= step_size * m.x / (sqrtf(v.x) * rsq_bc2 + eps);
+      p.y -= step_size * m.y / (sqrtf(v.y) * rsq_bc2 + eps);
+      p.z -= step_size * m.z / (sqrtf(v.z) * rsq_bc2 + eps);
+      p.w -= step_size * m.w / (sqrtf(v.w) * rsq_bc2 + eps);
+      m4[i] = m; v4[i] = v; p4[i] = p;
+    }
+    done = n4 << 2;
+  }
+  for (int64_t i = done + tid; i < it.n; i += nthr) {
+    const float g = it.g[i];
+    const float m = b1 * it.m[i] + c1 * g;
+    const float v = b2 * it.v[i] + c2 * g * g;
+    it.m[i] = m;
+    it.v[i] = v;
+    it.p[i] -= step_size * m / (sqrtf(v) * rsq_bc2 + eps);
+  }
+}
+
+__global__ void step_inc_kernel(float* step) {
+  griddep_wait();   // the update that reads the old value has completed
+  griddep_launch();
+  *step += 1.f;
+}
+
 }  // namespace pcgan
 
 using namespace pcgan;
@@ -515,5 +565,19 @@ extern "C" int pcgan_adam(float* p, const float* g, float* m, float* v, int64_t 
   if (n == 0) return PCGAN_OK;
   PCGAN_CUDA_OK(launch_pdl(adam_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, p, g, m, v, n, lr, beta1, beta2, eps, step));
   PCGAN_LAUNCH_OK("adam_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_adam_batched(const pcgan_adam_item* items, int32_t count, int64_t max_n, const float* lr, float beta1,
+                                  float beta2, float eps, float* step, pcgan_stream_t s) {
+  if (!items || !lr || !step) return fail(PCGAN_ERR_INVALID, "adam_batched: null argument");
+  dim3 grid;
+  int rc = batched_grid(count, max_n, &grid);
+  if (rc) return rc;
+  PCGAN_CUDA_OK(launch_pdl(adam_batched_kernel, grid, dim3(kThreads), 0, STREAM(s), 1, items, lr, beta1, beta2, eps,
+                           static_cast<const float*>(step)));
+  PCGAN_LAUNCH_OK("adam_batched_kernel");
+  PCGAN_CUDA_OK(launch_pdl(step_inc_kernel, dim3(1), dim3(1), 0, STREAM(s), 1, step));
+  PCGAN_LAUNCH_OK("step_inc_kernel");
   return PCGAN_OK;
 }

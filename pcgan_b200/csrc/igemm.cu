@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 
@@ -33,18 +34,24 @@ static constexpr int kTmemCols = 512;              // 2 accumulator stages x 256
 static constexpr int kAccCols = 256;
 static constexpr int kNumThreads = 384;            // warps 0-3: TMA / MMA / TMEM alloc / idle; 4-7 and 8-11: two epilogue groups
 static constexpr int kEpiGroups = 2;               // group g drains TMEM stage g (every other tile of the CTA)
-// tail after the ring: barriers (512 B) | bias [2 groups][256] f32 | statistics accumulators [2 groups][256][2] f32 |
-// per-warp transpose tiles [8 warps][32][17] f32
+// tail after the ring: barriers (512 B) | bias [2 groups][256] f32 | per-warp scratch [8 warps][32][17] f32: the
+// statistics partial sums [2][256] of each epilogue warp, or the row-exchange tile of the shift-sum epilogue
 static constexpr int kTailBias = 512;
-static constexpr int kTailAcc = kTailBias + kEpiGroups * 256 * 4;
-static constexpr int kTailTr = kTailAcc + kEpiGroups * 256 * 2 * 4;
-static constexpr int kTailBytes = kTailTr + 8 * 32 * 17 * 4;
+static constexpr int kTailTr = kTailBias + kEpiGroups * 256 * 4;
+static constexpr int kWarpScratch = 32 * 17 * 4;   // bytes per epilogue warp (>= 2 * 256 * 4)
+static constexpr int kTailBytes = kTailTr + 8 * kWarpScratch;
 static_assert(kDataBytes + 1024 + kTailBytes <= 227 * 1024, "shared memory budget");
 static constexpr int kSmemBytes = kDataBytes + 1024 /*align*/ + kTailBytes;
 
 struct DevParams {
   int32_t kind, block_n, a_rows, a_ch;
   int32_t num_stages, stage_bytes, a_alloc;
+  int32_t a_window;    // KMAJOR: A is the raw 8-channel pixel row, read through an overlapping no-swizzle descriptor
+  int32_t a_bytes;     // bytes one A box brings into a stage
+  int32_t b_res;       // KMAJOR, > 0: the whole B operand stays resident in front of the ring, b_res bytes per K chunk
+  int32_t ring_off;    // byte offset of the ring behind the resident B operand
+  int32_t dual;        // 1: two independent producer -> MMA -> epilogue pipelines (even / odd tiles of the CTA), each with
+                       //    num_stages stages of the ring and one TMEM accumulator
   int32_t t_count[4];
   int32_t a_base[4], a_step[4][4];
   int32_t b_base[4], b_step[4][4];
@@ -136,9 +143,8 @@ __device__ __forceinline__ void wgrad_item(const DevParams& P, const Sched& sc, 
 }
 
 struct EpiShared {
-  float* s_bias;       // this group's [256]
-  float* s_acc;        // this group's [256][2]
-  float* s_tr;         // this warp's [32][17]
+  uint32_t s_bias;     // shared address of this group's bias [256]
+  uint32_t s_tr;       // shared address of this warp's scratch: statistics partial sums [2][256] or exchange tile [32][17]
   uint64_t* tmem_full; // barrier of this group's TMEM stage
   uint64_t* tmem_empty;
   uint32_t group;      // 0 / 1: also the TMEM stage and the parity of the CTA-local tile index it handles
@@ -156,6 +162,43 @@ __device__ __forceinline__ float act_ct(float x, float slope) {
 // Forward / data-gradient epilogue of one epilogue group (4 warps = 128 accumulator rows): TMEM -> registers ->
 // (+bias, statistics, activation) -> global.  Thread = one accumulator row (output pixel), 32 fp32 columns per
 // tcgen05.ld.  The two groups of a CTA alternate tiles, each on its own TMEM stage.
+// x[i] = value of column i in this lane's row (zero for rows that are not stored; squared if SQ).  Returns, in lane l,
+// the sum over the warp's 32 rows of column l: at each step a lane keeps the half of its columns that matches its lane
+// bit and receives the partner's partial sums of that half.
+template <bool SQ>
+__device__ __forceinline__ float warp_column_sums(const float (&v)[32], bool valid, uint32_t lane) {
+  float a[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float lo = valid ? v[i] : 0.f, hi = valid ? v[i + 16] : 0.f;
+      if (SQ) { lo *= lo; hi *= hi; }
+      a[i] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+    }
+  }
+  float b[8];
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (up ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, up ? a[i] : a[i + 8], 8);
+  }
+  float c[4];
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (up ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, up ? b[i] : b[i + 4], 4);
+  }
+  float d[2];
+  {
+    const bool up = (lane & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (up ? c[i + 2] : c[i]) + __shfl_xor_sync(0xffffffffu, up ? c[i] : c[i + 2], 2);
+  }
+  const bool up = (lane & 1) != 0;
+  return (up ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, up ? d[0] : d[1], 1);
+}
+
 template <int ACT, bool BF16, bool STATS>
 __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiShared es, uint32_t tmem_base, const Sched sch) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,13 +206,13 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
   const uint32_t row = q * 32 + lane;
   const uint32_t et = (threadIdx.x - 128) & 127;
   const uint32_t bar_stats = 1 + es.group, bar_bias = 3 + es.group;
-  float* my_tr = es.s_tr;
-  const int32_t block_n = P.block_n, n_tiles = P.n_tiles, n_valid = P.n_valid;
+  const uint32_t my_part = es.s_tr;                      // this warp's column sums [256] | sums of squares [256]
+  const uint32_t group_part = es.s_tr - q * kWarpScratch;   // the group's four warps are contiguous
+  const int32_t block_n = P.block_n, n_valid = P.n_valid;
   const int64_t cs = P.out_cstride;
   const float* bias = P.bias;
   const float slope = P.act_slope;
-  float* s_bias = es.s_bias;
-  float* s_acc = es.s_acc;
+  const uint32_t s_bias = es.s_bias;
   uint32_t acc_phase = 0;
   int32_t cur_nt = -1, cur_group = -1;
 
@@ -189,11 +232,18 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
   auto flush_stats = [&](int32_t group, int32_t nt) {
     named_bar_sync(bar_stats, 128);
     float* gs = P.stats + static_cast<int64_t>(group) * n_valid * 2;
-    for (int32_t i = et; i < block_n * 2; i += 128) {
-      const int32_t ch = nt * block_n + (i >> 1);
-      const float v = s_acc[i];
-      s_acc[i] = 0.f;
-      if (ch < n_valid && v != 0.f) atomicAdd(gs + ch * 2 + (i & 1), v);
+    for (int32_t i = et; i < 512; i += 128) {
+      const int32_t col = i & 255, which = i >> 8;
+      if (col >= block_n) continue;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t a = group_part + w * kWarpScratch + i * 4;
+        v += lds_f32(a);
+        sts_f32(a, 0.f);
+      }
+      const int32_t ch = nt * block_n + col;
+      if (ch < n_valid && v != 0.f) atomicAdd(gs + ch * 2 + which, v);
     }
     named_bar_sync(bar_stats, 128);
   };
@@ -227,7 +277,7 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
         named_bar_sync(bar_bias, 128);   // everybody in the group is done with the previous tile's bias
         for (int32_t i = et; i < block_n; i += 128) {
           const int32_t ch = nt * block_n + i;
-          s_bias[i] = ch < n_valid ? __ldg(bias + ch) : 0.f;
+          sts_f32(s_bias + i * 4, ch < n_valid ? __ldg(bias + ch) : 0.f);
         }
         named_bar_sync(bar_bias, 128);
       }
@@ -250,37 +300,21 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
       if (bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = b4[i];
+          const float4 b = lds_f32x4(s_bias + (c0 + 4 * i) * 4);
           v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
       }
       if (STATS) {
-        // column sums over the warp's 32 rows, 16 columns at a time through a [32][17] shared tile: lane l sums
-        // 16 rows of column l % 16, the two half sums meet with one shuffle
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) my_tr[lane * 17 + i] = valid ? v[16 * h + i] : 0.f;
-          __syncwarp();
-          float s1 = 0.f, s2 = 0.f;
-          const float* col = my_tr + (lane >> 4) * (16 * 17) + (lane & 15);
-#pragma unroll
-          for (int r2 = 0; r2 < 16; ++r2) {
-            const float x = col[r2 * 17];
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-          }
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (lane < 16) {
-            atomicAdd(&s_acc[(c0 + 16 * h + lane) * 2 + 0], s1);
-            atomicAdd(&s_acc[(c0 + 16 * h + lane) * 2 + 1], s2);
-          }
-        }
+        // column sums over the warp's 32 rows: a butterfly of 31 shuffles leaves the total of column c0 + l in lane l
+        // (once for the values, once for their squares), which the lane adds to the warp's own partial sums: no
+        // shared-memory atomics, no transposes
+        const float s1 = warp_column_sums<false>(v, valid, lane);
+        const float s2 = warp_column_sums<true>(v, valid, lane);
+        const uint32_t a = my_part + (c0 + lane) * 4;
+        sts_f32(a, lds_f32(a) + s1);
+        sts_f32(a + 1024, lds_f32(a + 1024) + s2);
       }
       if (valid) {
         const int32_t ncols = ncol_limit - c0;
@@ -332,9 +366,8 @@ __device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShar
   const uint32_t q = warp & 3;
   const uint32_t row = q * 32 + lane;
   const uint32_t bar = 5 + es.group;
-  float* tr = es.s_tr - q * (32 * 17);     // the group's four warp tiles are contiguous: [128][17]
+  const uint32_t tr = es.s_tr - q * kWarpScratch;     // the group's four warp tiles are contiguous: [128][17]
   const int32_t kw = P.shift_taps, cp = P.shift_cpad, nv = P.n_valid;
-  const int32_t n_tiles = P.n_tiles;
   const int64_t cs = P.out_cstride;
   const float slope = P.act_slope;
   float bias[8];
@@ -388,20 +421,20 @@ __device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShar
     for (int h = 0; h < 2; ++h) {
       named_bar_sync(bar, 128);       // everybody has read the previous half
 #pragma unroll
-      for (int i = 0; i < 16; ++i) tr[row * 17 + i] = __uint_as_float(raw[16 * h + i]);
+      for (int i = 0; i < 16; ++i) sts_f32(tr + (row * 17 + i) * 4, __uint_as_float(raw[16 * h + i]));
       named_bar_sync(bar, 128);
       if (row_out) {
         if (cp == 4) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int32_t j = (16 * h + i) >> 2;             // static after unrolling: o[] stays in registers
-            if (j < kw) o[i & 3] += tr[(row + j) * 17 + i];
+            if (j < kw) o[i & 3] += lds_f32(tr + ((row + j) * 17 + i) * 4);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int32_t j = (16 * h + i) >> 3;
-            if (j < kw) o[i & 7] += tr[(row + j) * 17 + i];
+            if (j < kw) o[i & 7] += lds_f32(tr + ((row + j) * 17 + i) * 4);
           }
         }
       }
@@ -506,9 +539,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tail + kTailBias);
-  float* s_acc = reinterpret_cast<float*>(tail + kTailAcc);   // [2 groups][256][2]
-  float* s_tr = reinterpret_cast<float*>(tail + kTailTr);     // [8 warps][32][17]
+  uint64_t* bres_bar = tmem_empty + 3;
+  const uint32_t s_bias = smem_u32(tail + kTailBias);        // [2 groups][256] f32
+  const uint32_t s_tr = smem_u32(tail + kTailTr);            // [8 warps] x kWarpScratch
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -518,7 +551,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < nstages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], P.pair ? 2 : 1);   // paired: the peer multicasts into this stage too, both MMA warps release it
     }
@@ -526,6 +559,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 128);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -534,7 +568,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tmem_relinquish();
   }
   if (threadIdx.x >= 128) {
-    for (int i = threadIdx.x - 128; i < kEpiGroups * 256 * 2; i += kNumThreads - 128) s_acc[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 8 * kWarpScratch / 4; i += kNumThreads - 128) sts_f32(s_tr + i * 4, 0.f);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -552,13 +586,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   // per-sample statistics, usually the same sample, so the statistics are flushed once per sample, not per tile)
   const Sched sch = make_sched(P);
   const uint16_t pair_mask = 0x3;
+  // Single pipeline: warp 0 feeds warp 1, which alternates between the two accumulators.  Dual (P.dual): the single-thread
+  // issue loops, not the tensor pipe, bound tiles with little work per K chunk, so the CTA's even tiles run through
+  // warps 0 -> 1 -> epilogue group 0 and its odd tiles through warps 3 -> 2 -> epilogue group 1, each pipeline with its
+  // own half of the ring, its own barriers and its own accumulator.
+  const bool producer_warp = warp == 0 || (warp == 3 && P.dual);
+  const bool mma_warp = warp == 1 || (warp == 2 && P.dual);
+  const int32_t pipe = (P.dual && (warp == 2 || warp == 3)) ? 1 : 0;
+  const int32_t tile_step = P.dual ? 2 : 1;
+  uint8_t* ring = smem + P.ring_off + pipe * nstages * P.stage_bytes;
+  full_bar += pipe * (kMaxStages / 2);
+  empty_bar += pipe * (kMaxStages / 2);
 
-  if (warp == 0) {
+  if (producer_warp) {
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the (uniform) schedule; one elected lane issues the copies.
     int32_t stage = 0;
     uint32_t phase = 0;
-    for (int32_t tile = sch.begin; tile < sch.end; ++tile) {
+    if (P.b_res && pipe == 0 && sch.begin < sch.end) {
+      // small weight matrices (one N tile) are fetched once per CTA, not once per tile
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(k_chunks_fwd * P.block_n * 128));
+        for (int32_t tap = 0; tap < P.num_taps; ++tap)
+          for (int32_t cc = 0; cc < P.cchunks; ++cc)
+            tma_load_5d(smem + (tap * P.cchunks + cc) * P.b_res, &tma_b, bres_bar, P.tap_bk[tap] + cc * 64, 0, 0, 0, 0);
+      }
+      __syncwarp();
+    }
+    for (int32_t tile = sch.begin + pipe; tile < sch.end; tile += tile_step) {
       if (!wgrad) {
         int32_t mt, nt;
         bool tile_valid;
@@ -567,14 +622,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int32_t c[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
-        const uint32_t bytes = P.a_rows * 128 + P.block_n * 128;
+        const uint32_t bytes = P.a_bytes + (P.b_res ? 0 : P.block_n * 128);
         const int32_t half_rows = P.block_n >> 1;   // paired: this CTA fetches rows [rank*half, +half) of B for both
         for (int32_t tap = 0; tap < P.num_taps; ++tap) {
           const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
                         o3 = P.tap_off[tap][3];
           const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
           for (int32_t cc = 0; cc < P.cchunks; ++cc) {
-            uint8_t* sa = smem + stage * P.stage_bytes;
+            uint8_t* sa = ring + stage * P.stage_bytes;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full_bar[stage], bytes);
@@ -582,7 +637,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
               if (P.pair)
                 tma_load_5d_multicast(sa + P.a_alloc + sch.rank * half_rows * 128, &tma_b, &full_bar[stage], bk0 + cc * 64,
                                       nt * P.block_n + sch.rank * half_rows, 0, 0, 0, pair_mask);
-              else
+              else if (!P.b_res)
                 tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
             }
             __syncwarp();
@@ -602,7 +657,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count);
         const int32_t a_boxes = (P.a_ch - mt * 128 + 63) / 64;   // 64-channel boxes of this M tile that exist (1 or 2)
         for (int32_t kb = kb0; kb < kb1; ++kb) {
-          uint8_t* sa = smem + stage * P.stage_bytes;
+          uint8_t* sa = ring + stage * P.stage_bytes;
           const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
                         a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
           const int32_t b0 = coord(d, P.b_base, P.b_step, 0) + o0, b1 = coord(d, P.b_base, P.b_step, 1) + o1,
@@ -636,7 +691,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (mma_warp) {
     // -------------------------------------------------------------- MMA issuer
     // Converged warp, one elected lane issues tcgen05.mma / commit (always the same lane, so the commits track its MMAs).
     const uint32_t idesc = make_idesc_bf16(128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
@@ -646,8 +701,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t sbo = 1024;
     const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
     int32_t stage = 0;
-    uint32_t phase = 0, acc = 0, acc_phase = 0;
-    for (int32_t tile = sch.begin; tile < sch.end; ++tile) {
+    uint32_t phase = 0, acc = static_cast<uint32_t>(pipe), acc_phase = 0;
+    if (P.b_res && sch.begin + pipe < sch.end) mbar_wait(bres_bar, 0);
+    for (int32_t tile = sch.begin + pipe; tile < sch.end; tile += tile_step) {
       int32_t nk;
       if (!wgrad) {
         nk = k_chunks_fwd;
@@ -662,9 +718,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       for (int32_t kc = 0; kc < nk; ++kc) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
-        const uint64_t da = make_smem_desc(sa, lbo, sbo);
-        const uint64_t db = make_smem_desc(sa + P.a_alloc, lbo, sbo);
+        const uint32_t sa = smem_u32(ring + stage * P.stage_bytes);
+        // windowed A: pixel rows of 16 B; row m of K chunk j (8 channels of window pixel j) sits at (m + j) * 16, so the
+        // core matrices overlap: 16 B between the two K chunks of one MMA, 128 B between 8-row groups
+        const uint64_t da = P.a_window ? make_smem_desc_noswizzle(sa, 16, 128) : make_smem_desc(sa, lbo, sbo);
+        const uint64_t db = make_smem_desc(P.b_res ? smem_u32(smem) + kc * P.b_res : sa + P.a_alloc, lbo, sbo);
         if (elect_one_sync()) {
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k)
@@ -677,12 +735,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       }
       if (elect_one_sync()) tcgen05_commit(&tmem_full[acc]);
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (P.dual) { acc_phase ^= 1; }
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const uint32_t eg = (warp - 4) >> 2;
-    EpiShared es{s_bias + eg * 256, s_acc + eg * 512, s_tr + (warp - 4) * (32 * 17), &tmem_full[eg], &tmem_empty[eg], eg};
+    EpiShared es{s_bias + eg * 1024, s_tr + (warp - 4) * kWarpScratch, &tmem_full[eg], &tmem_empty[eg], eg};
     if (wgrad) {
       epilogue_wgrad(P, es, tmem_base, sch, total_kb, kb_per_split);
     } else {
@@ -727,7 +786,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base) {
+static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base, bool swizzle = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(PCGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5], strides[4];
@@ -739,7 +798,8 @@ static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base) 
   }
   for (int i = 0; i < 4; ++i) strides[i] = t.strides[i + 1];
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(PCGAN_ERR_CUDA,
@@ -766,8 +826,28 @@ struct pcgan_igemm_plan {
 
 using namespace pcgan;
 
-static int validate_tmap(const pcgan_tmap& t, const char* name) {
-  if (t.box[0] != 64) return fail(PCGAN_ERR_INVALID, "%s.box[0] must be 64 (one 128-byte swizzle row)", name);
+// PCGAN_BRES=0 turns the resident weight operand off (measurement only).
+static bool resident_b_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PCGAN_BRES");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+// PCGAN_DUAL=0 turns the second pipeline off (measurement only).
+static bool dual_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PCGAN_DUAL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+static int validate_tmap(const pcgan_tmap& t, const char* name, uint32_t inner = 64) {
+  if (t.box[0] != inner) return fail(PCGAN_ERR_INVALID, "%s.box[0] must be %u", name, inner);
   for (int i = 0; i < 5; ++i) {
     if (t.dims[i] == 0 || t.dims[i] > (1ull << 32)) return fail(PCGAN_ERR_INVALID, "%s.dims[%d] out of range", name, i);
     if (t.box[i] == 0 || t.box[i] > 256) return fail(PCGAN_ERR_INVALID, "%s.box[%d] out of range", name, i);
@@ -787,9 +867,16 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     return fail(PCGAN_ERR_UNSUPPORTED, "block_n=%d must be a multiple of 16 in [16,256]", d->block_n);
   if (wg && d->block_n % 64 != 0) return fail(PCGAN_ERR_UNSUPPORTED, "WGRAD block_n=%d must be a multiple of 64", d->block_n);
   int rc;
-  if ((rc = validate_tmap(d->a, "a")) != PCGAN_OK) return rc;
+  if (d->a_window != 0 && d->a_window != 8) return fail(PCGAN_ERR_INVALID, "a_window must be 0 or 8");
+  if ((rc = validate_tmap(d->a, "a", d->a_window ? 8 : 64)) != PCGAN_OK) return rc;
   if ((rc = validate_tmap(d->b, "b")) != PCGAN_OK) return rc;
-  const int64_t a_rows = (int64_t)d->a.box[1] * d->a.box[2] * d->a.box[3] * d->a.box[4];
+  if (d->a_window) {
+    if (wg || d->a.dims[0] != 8 || d->a.strides[1] != 16 || d->a.box[1] < 8 || d->a.box[2] != 1 || d->a.box[3] != 1 ||
+        d->a.box[4] != 1 || d->cchunks != 1 || d->pair)
+      return fail(PCGAN_ERR_INVALID, "windowed A: KMAJOR, 8-channel tensor with 16-byte pixels, a single-row box of rows + 7 pixels, cchunks == 1, no pairing");
+  }
+  // windowed A: the box holds the tile's rows plus the 7 pixels the last row's window reaches into
+  const int64_t a_rows = (int64_t)d->a.box[1] * d->a.box[2] * d->a.box[3] * d->a.box[4] - (d->a_window ? 7 : 0);
   const int64_t b_rows = (int64_t)d->b.box[1] * d->b.box[2] * d->b.box[3] * d->b.box[4];
   if (!wg) {
     if (a_rows < 1 || a_rows > 128) return fail(PCGAN_ERR_INVALID, "A box has %lld rows (1..128)", (long long)a_rows);
@@ -832,12 +919,24 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   {
     // operand ring: as many stages as fit (small tiles get a deep ring, which is what hides the TMA latency
     // between the many short tiles of the tiny-K layers)
-    const int32_t a_alloc = wg ? 2 * kBoxBytesMN : (int32_t)((a_rows * 128 + 1023) / 1024 * 1024);
+    v.a_window = d->a_window;
+    v.a_bytes = d->a_window ? (int32_t)(a_rows + 7) * 16 : (int32_t)a_rows * 128;
+    const int32_t a_alloc = wg ? 2 * kBoxBytesMN : (v.a_bytes + 1023) / 1024 * 1024;
     const int32_t b_alloc = wg ? (d->block_n / 64) * kBoxBytesMN : (d->block_n * 128 + 1023) / 1024 * 1024;
+    // a weight matrix of one N tile that fits in half of the operand memory is fetched once per CTA and stays
+    const int64_t b_total = (int64_t)d->num_taps * d->cchunks * b_alloc;
+    const bool resident = resident_b_enabled() && !wg && !d->pair && d->n_tiles == 1 && b_total <= kDataBytes / 2;
     v.a_alloc = a_alloc;
-    v.stage_bytes = a_alloc + b_alloc;
-    int32_t ns = kDataBytes / v.stage_bytes;
-    v.num_stages = ns > kMaxStages ? kMaxStages : (ns < 2 ? 2 : ns);
+    v.b_res = resident ? b_alloc : 0;
+    v.ring_off = resident ? (int32_t)b_total : 0;
+    v.stage_bytes = resident ? a_alloc : a_alloc + b_alloc;
+    int32_t ns = (kDataBytes - v.ring_off) / v.stage_bytes;
+    // two pipelines when each still gets at least two stages and the plan is not paired (the pair protocol multicasts
+    // into the peer's ring in lock step)
+    v.dual = dual_enabled() && !d->pair && ns >= 4 ? 1 : 0;
+    if (v.dual) ns /= 2;
+    const int32_t cap = v.dual ? kMaxStages / 2 : kMaxStages;
+    v.num_stages = ns > cap ? cap : (ns < 2 ? 2 : ns);
   }
   memcpy(v.t_count, d->t_count, sizeof(v.t_count));
   memcpy(v.a_base, d->a_base, sizeof(v.a_base)); memcpy(v.a_step, d->a_step, sizeof(v.a_step));
@@ -881,7 +980,7 @@ extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b
   {
     std::lock_guard<std::mutex> lock(p->mu);
     if (p->cached_a != a) {
-      int rc = encode_tmap(&p->map_a, p->desc.a, a);
+      int rc = encode_tmap(&p->map_a, p->desc.a, a, p->desc.a_window == 0);
       if (rc != PCGAN_OK) return rc;
       p->cached_a = a;
     }

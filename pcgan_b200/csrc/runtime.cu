@@ -63,5 +63,6 @@ extern "C" int64_t pcgan_sizeof(const char* name) {
   if (s == "pcgan_loss_args") return sizeof(pcgan_loss_args);
   if (s == "pcgan_batch_item") return sizeof(pcgan_batch_item);
   if (s == "pcgan_running_item") return sizeof(pcgan_running_item);
+  if (s == "pcgan_adam_item") return sizeof(pcgan_adam_item);
   return -1;
 }

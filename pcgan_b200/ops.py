@@ -261,6 +261,19 @@ def loss(kind, p, target, *, per_sample=0, weight=1.0, weight_dev=None, loss_out
         L.check(L.load().pcgan_loss(C.byref(a), _stream()), "loss")
 
 
+def adam_table(items, device):
+    """Device table of pcgan_adam_item: items = [(p, g, m, v)] fp32 tensors of equal numel."""
+    rows = [[p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()] for p, g, m, v in items]
+    return torch.tensor(rows, dtype=torch.int64).to(device), max(r[4] for r in rows)
+
+
+def adam_batched(table, count, max_n, lr, beta1, beta2, eps, step):
+    """One Adam update of every tensor in the table (+ the one-thread launch that advances `step`)."""
+    _count(2)
+    with _Timed("adam_batched"):
+        L.check(L.load().pcgan_adam_batched(_ptr(table), count, max_n, _ptr(lr), beta1, beta2, eps, _ptr(step), _stream()), "adam_batched")
+
+
 def adam(p, g, m, v, lr, beta1, beta2, eps, step):
     _count()
     with _Timed("adam"):

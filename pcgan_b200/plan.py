@@ -124,6 +124,7 @@ class IgemmSpec:
     shift_taps: int = 0        # shift-sum epilogue: horizontal taps carried in N (include/pcgan_kernels.h)
     shift_cpad: int = 0
     pair: int = 0              # CTA pairs sharing the B operand through TMA multicast (include/pcgan_kernels.h)
+    a_window: int = 0          # 8: A is the plain 8-channel tensor read through an overlapping descriptor (pcgan_kernels.h)
     swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
 
     @property
@@ -159,6 +160,7 @@ class IgemmSpec:
         d.m_valid, d.wg_ncols, d.ldo = self.m_valid, self.wg_ncols, self.ldo
         d.pair = self.pair
         d.shift_taps, d.shift_cpad = self.shift_taps, self.shift_cpad
+        d.a_window = self.a_window
         return d
 
 
@@ -181,6 +183,7 @@ def _block_n(cout):
 
 
 PAIRING = True   # CTA pairs with a multicast B operand where it pays (large N tiles, enough M tiles)
+WINDOW = True    # 8-channel inputs: windowed A operand (pcgan_igemm_desc.a_window) instead of overlapping-stride TMA boxes
 
 
 def _pair_kmajor(s: "IgemmSpec", m_tiles: int) -> int:
@@ -405,8 +408,51 @@ def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho
     s.cchunks = win // 64
     bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride == 2)
     tx, ty, tn = _ceil(wo, bw), _ceil(ho, bh), _ceil(N, bn)
-    s.t_count = [tx, ty, tn, 1]
-    if stride == 1:
+    window = WINDOW and stride == 1 and C == 8 and kw <= 8 and wo >= 64
+    flat_tiles = _ceil(N * Hp * Wp, 128)
+    if window and not stats and flat_tiles < _ceil(wo, 128) * ho * N:
+        # windowed form over the flattened padded grid: position q = (n, Y, X) computes output (Y, X) from the window
+        # starting at q + (r + off)*Wp + off; rows that run over the end of an image row read the next row's pixels
+        # and are not stored
+        s.a_window = 8
+        P = N * Hp * Wp
+        s.t_count = [flat_tiles, 1, 1, 1]
+        s.a_dims = [8, P, 1, 1, 1]
+        s.a_strides = [0, 16, P * 16, P * 16, P * 16]
+        s.a_box = [8, 128 + 7, 1, 1, 1]
+        s.a_step[0][0] = 128
+        for r in range(kh):
+            s.tap_off.append([(r + off) * Wp + off, 0, 0, 0])
+            s.tap_c0.append(0)
+            s.tap_bk.append(r * win)
+        s.e_step[0][0] = 128
+        s.e_p1[0], s.e_p2[0] = Hp * Wp, Wp
+        s.e_comp = [[(0, N, out.sn), (0, ho, out.sy), (0, wo, out.sx)], [ONE, ANY, ONE], [ONE, ANY, ONE], [ONE, ANY, ONE]]
+        tx, ty, tn = flat_tiles, 1, 1
+    elif window:
+        # windowed form, one tile = up to 128 consecutive pixels of one output row
+        s.a_window = 8
+        bw = min(wo, 128)
+        tx, ty, tn = _ceil(wo, bw), ho, N
+        s.t_count = [tx, ty, tn, 1]
+        s.a_dims = [8, Wp, Hp, N, 1]
+        s.a_strides = [0, 16, Wp * 16, Hp * Wp * 16, N * Hp * Wp * 16]
+        s.a_box = [8, bw + 7, 1, 1, 1]
+        s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, 1, 1
+        for r in range(kh):
+            s.tap_off.append([off, r + off, 0, 0])
+            s.tap_c0.append(0)
+            s.tap_bk.append(r * win)
+        s.e_step[0][0], s.e_step[1][1], s.e_step[2][2] = bw, 1, 1
+        s.e_comp = [[ONE, (0, wo, out.sx), ONE], [ONE, (0, ho, out.sy), ONE], [ONE, (0, N, out.sn), ONE], [ONE, ANY, ONE]]
+        if stats:
+            s.stats_mode = L.STATS_ON
+            s.stats_dim, s.stats_comp = (2, 1) if per_sample_stats else (-1, 1)
+    else:
+        s.t_count = [tx, ty, tn, 1]
+    if window:
+        pass
+    elif stride == 1:
         s.a_dims = [win, Wp, Hp, N, 1]
         s.a_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
         s.a_box = [64, bw, bh, bn, 1]

@@ -41,6 +41,8 @@ FWD_CASES = [
     ("d4x4_s2", 64, 64, 128, 4, 2, 1, "zero", 1, 16, 16, 2),
     ("d4x4_s1", 64, 64, 80, 4, 1, 1, "zero", 1, 9, 9, 2),
     ("stem7x7_packed", 4, 8, 64, 7, 1, 3, "reflect", 3, 16, 16, 2),
+    ("stem7x7_window", 4, 8, 64, 7, 1, 3, "reflect", 3, 6, 64, 2),          # windowed A operand, one row per tile
+    ("stem7x7_window_wide", 4, 8, 64, 7, 1, 3, "reflect", 3, 5, 150, 1),    # two tiles per row, the second ragged
     ("dstem4x4_s2_packed", 4, 8, 64, 4, 2, 1, "zero", 1, 16, 16, 2),
     ("estem7x7_s2_packed", 3, 8, 64, 7, 2, 3, "zero", 3, 32, 32, 2),
     ("head7x7_n3", 64, 64, 3, 7, 1, 3, "reflect", 3, 16, 16, 1),
@@ -116,6 +118,8 @@ DGRAD_CASES = [
     ("res3x3_flat_full", 64, 64, 64, 3, 1, 1, 1, True, 16, 2, 1),
     ("res3x3_flat_interior", 64, 64, 64, 3, 1, 1, 1, False, 16, 2, 1),
     ("head7x7_packed_full", 64, 3, 8, 7, 1, 3, 3, True, 16, 2, 6),
+    ("head7x7_window_flat_full", 64, 3, 8, 7, 1, 3, 3, True, 64, 2, 6),   # windowed A over the flattened padded grid
+    ("head7x7_window_interior", 64, 3, 8, 7, 1, 3, 3, False, 64, 1, 3),
     ("dhead4x4_packed", 64, 1, 8, 4, 1, 1, 1, False, 9, 2, 2),
     ("d4x4_s1_box", 64, 64, 64, 4, 1, 1, 1, False, 9, 2, 0),
     ("down3x3_s2", 64, 128, 128, 3, 2, 1, 1, False, 16, 2, 0),

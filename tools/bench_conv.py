@@ -84,6 +84,33 @@ def main():
     o = torch.zeros(ru.numel + 512, dtype=torch.bfloat16, device=DEV)
     p = CV.conv_fwd_plans((256, 128, 3, 3), xb, 2, 1, OutMap.nhwc(ru), transposed=True, output_padding=1)
     res.append(report("up1 fwd convT 256->128 (4 phases)", time_plans(p, xbb, o), N * 32 * 32 * 256 * 128 * 9))
+    # 8-channel layers: windowed A operand against the overlapping-stride boxes
+    from pcgan_b200 import plan as PL
+    st1 = torch.zeros(N, 64, 2, device=DEV)
+    b64 = torch.zeros(64, device=DEV)
+    dyg, xg64 = Geom(N, S, S, 8, 6), Geom(N, S, S, 64, 3)
+    fullg = Geom(N, S + 6, S + 6, 64, 0)
+    dy8 = torch.randn(dyg.numel + 512, device=DEV).to(torch.bfloat16)
+    ofull = torch.zeros(fullg.numel + 512, dtype=torch.bfloat16, device=DEV)
+    for flag in (False, True):
+        PL.WINDOW = flag
+        tag = "window" if flag else "overlap"
+        p = CV.conv_fwd_plans((64, 4, 7, 7), xg0, 1, 3, OutMap.nhwc(r1), stats=True, per_sample_stats=True)
+        res.append(report("stem fwd +stats [%s]" % tag, time_plans(p, x0, o1, stats=st1, bias=b64), N * S * S * 64 * 4 * 49))
+        p = CV.conv_dgrad_plans((3, 64, 7, 7), dyg, xg64, 1, 3, OutMap.nhwc(fullg), full_padded=True)
+        res.append(report("head dgrad 3->64 padded [%s]" % tag, time_plans(p, dy8, ofull), N * S * S * 64 * 3 * 49))
+    # stem weight gradient (dY 64 ch x packed window) and an encoder 64->64 convolution with batch statistics
+    dy64 = Geom(N, S, S, 64, 0)
+    dyb = torch.randn(dy64.numel + 512, device=DEV).to(torch.bfloat16)
+    sp, wm = CV.conv_wgrad_plan((64, 4, 7, 7), dy64, xg0, 1, 3)
+    packed = torch.zeros(sp.b_rows * sp.b_k, device=DEV)
+    res.append(report("stem wgrad 7x7 4->64 ksplit=%d" % sp.ksplit, time_plans([(sp, wm)], dyb, packed, extra=x0), N * S * S * 64 * 4 * 49))
+    xe, re_ = Geom(N, 56, 56, 64, 1), Geom(N, 56, 56, 64, 0)
+    xeb = torch.randn(xe.numel + 512, device=DEV).to(torch.bfloat16)
+    oe = torch.zeros(re_.numel + 512, dtype=torch.bfloat16, device=DEV)
+    ste = torch.zeros(1, 64, 2, device=DEV)
+    p = CV.conv_fwd_plans((64, 64, 3, 3), xe, 1, 1, OutMap.nhwc(re_), stats=True)
+    res.append(report("E.layer1 fwd 3x3 64->64 @56 +BN stats", time_plans(p, xeb, oe, stats=ste), N * 56 * 56 * 64 * 64 * 9))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_conv.json", "w"), indent=1)
 
