@@ -135,9 +135,10 @@ typedef struct {
   int32_t m_valid;     /* Cout                                             */
   int32_t wg_ncols;    /* valid columns per tap (Cin or packed row width)  */
   int64_t ldo;         /* output row pitch in elements                     */
-  /* 1: launch as thread-block clusters of two CTAs that take two M tiles of the same N tile (tap, K split) and share the
-   * B operand: each CTA fetches half of it and TMA-multicasts it into both, which cuts the L2 -> shared-memory traffic
-   * of a 128x256 tile from 48 to 32 KB per K chunk (the L2 read bandwidth, not the tensor pipe, bounds these tiles).
+  /* 1: launch as thread-block clusters of two CTAs that take two M tiles of the same N tile (tap, K split) and issue
+   * ONE tcgen05.mma.cta_group::2 of M = 256 per K step: each CTA fetches its own A tile and half of the B tile, so the
+   * shared-memory operand traffic of a 128x256 tile drops from 48 to 32 KB per K chunk per SM (shared-memory bandwidth,
+   * not the tensor pipe, bounds these tiles), and drains its own 128 accumulator rows.
    * KMAJOR: any shape (an odd M-tile count recomputes and drops one tile); WGRAD: m_tiles and block_n/64 must be even. */
   int32_t pair;
   /* KMAJOR shift-sum epilogue (shift_taps > 0): for convolutions with very few output channels (generator head 64 -> 3,

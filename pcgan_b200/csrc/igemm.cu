@@ -14,8 +14,10 @@
 // accumulator stage (TMEM lane quarter = warp % 4).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
 // (MMA <-> epilogue), persistent tile loop with a static stride schedule. With
-// desc.pair the grid runs as clusters of two CTAs on adjacent M tiles that share the
-// B operand: each CTA loads half of it and multicasts that half to its peer.
+// desc.pair the grid runs as clusters of two CTAs on adjacent M tiles of the same N
+// tile: each CTA loads its own A tile and half of the B tile, the leader issues one
+// tcgen05.mma.cta_group::2 of M = 256 per K step (operand reads from shared memory
+// are halved per SM), and each CTA drains its own 128 accumulator rows.
 #include <cuda.h>
 #include <mutex>
 #include <stdarg.h>
@@ -57,7 +59,7 @@ struct DevParams {
   int32_t b_base[4], b_step[4][4];
   int32_t n_tiles, m_tiles, ksplit, num_m_tiles, total_tiles;
   int32_t shift_taps, shift_cpad;   // shift-sum epilogue (include/pcgan_kernels.h)
-  int32_t pair;        // 1: launched as clusters of 2 CTAs that work on two M tiles of the same N tile and share the B operand
+  int32_t pair;        // 1: clusters of 2 CTAs on two M tiles of the same N tile, one tcgen05.mma.cta_group::2 for both
   int32_t sched_items; // work items per CTA slot schedule: tiles, or pair-tiles when pair
   int32_t num_taps, cchunks;
   int32_t tap_off[PCGAN_MAX_TAPS][4];
@@ -149,6 +151,12 @@ struct EpiShared {
   uint64_t* tmem_empty;
   uint32_t group;      // 0 / 1: also the TMEM stage and the parity of the CTA-local tile index it handles
 };
+
+// The accumulator stage is drained: tell the MMA warp (the pair's leader's when paired).
+__device__ __forceinline__ void epi_release(const DevParams& P, const EpiShared& es) {
+  if (P.pair) mbar_arrive_leader(es.tmem_empty);
+  else mbar_arrive(es.tmem_empty);
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_ct(float x, float slope) {
@@ -352,7 +360,7 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
     }
     // accumulator drained: hand the TMEM stage back to the MMA warp
     tcgen05_fence_before();
-    mbar_arrive(es.tmem_empty);
+    epi_release(P, es);
     acc_phase ^= 1;
   }
   if (STATS && cur_group >= 0) flush_stats(cur_group, cur_nt);
@@ -412,7 +420,7 @@ __device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShar
     tmem_ld_wait();
     // the accumulator is in registers: hand the TMEM stage back before the exchange
     tcgen05_fence_before();
-    mbar_arrive(es.tmem_empty);
+    epi_release(P, es);
     acc_phase ^= 1;
     float o[8];
 #pragma unroll
@@ -523,11 +531,14 @@ __device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShar
       }
     }
     tcgen05_fence_before();
-    mbar_arrive(es.tmem_empty);
+    epi_release(P, es);
     acc_phase ^= 1;
   }
 }
 
+// kPair: the instantiation launched as clusters of two CTAs (desc.pair).  The cta_group::2 instructions live only in it: a
+// kernel that contains them cannot be launched without a cluster.
+template <bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ DevParams P) {
@@ -553,26 +564,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], P.pair ? 2 : 1);   // paired: the peer multicasts into this stage too, both MMA warps release it
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], kPair ? 256 : 128);   // paired: the leader's MMA warp waits for both CTAs' epilogues
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc_2cta(tmem_slot, kTmemCols); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   if (threadIdx.x >= 128) {
     for (int i = threadIdx.x - 128; i < 8 * kWarpScratch / 4; i += kNumThreads - 128) sts_f32(s_tr + i * 4, 0.f);
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (P.pair) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast or committed to them
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched no global data: under programmatic dependent launch it overlapped the previous kernel's tail
@@ -622,8 +633,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int32_t c[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
-        const uint32_t bytes = P.a_bytes + (P.b_res ? 0 : P.block_n * 128);
-        const int32_t half_rows = P.block_n >> 1;   // paired: this CTA fetches rows [rank*half, +half) of B for both
+        const int32_t half_rows = P.block_n >> 1;   // paired: this CTA holds rows [rank*half, +half) of the B tile
+        // paired: both CTAs' copies (own A tile + own half of B each) are counted on the leader's barrier
+        const uint32_t bytes = kPair ? 2 * (P.a_bytes + half_rows * 128) : P.a_bytes + (P.b_res ? 0 : P.block_n * 128);
         for (int32_t tap = 0; tap < P.num_taps; ++tap) {
           const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
                         o3 = P.tap_off[tap][3];
@@ -632,13 +644,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             uint8_t* sa = ring + stage * P.stage_bytes;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&full_bar[stage], bytes);
-              tma_load_5d(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
-              if (P.pair)
-                tma_load_5d_multicast(sa + P.a_alloc + sch.rank * half_rows * 128, &tma_b, &full_bar[stage], bk0 + cc * 64,
-                                      nt * P.block_n + sch.rank * half_rows, 0, 0, 0, pair_mask);
-              else if (!P.b_res)
-                tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+              if (kPair) {
+                if (sch.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                tma_load_5d_2cta(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                tma_load_5d_2cta(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64,
+                                 nt * P.block_n + sch.rank * half_rows, 0, 0, 0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                tma_load_5d(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                if (!P.b_res)
+                  tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+              }
             }
             __syncwarp();
             if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -655,7 +671,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
         // pixel blocks kb0 .. kb1-1 are consecutive: the mixed-radix digits are stepped, not re-divided, per block
         Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count);
-        const int32_t a_boxes = (P.a_ch - mt * 128 + 63) / 64;   // 64-channel boxes of this M tile that exist (1 or 2)
+        // 64-channel boxes of this M tile (and of the peer's) that exist: 1 or 2
+        const int32_t a_boxes = min((P.a_ch - mt * 128 + 63) / 64, 2);
+        const int32_t peer_boxes = min((P.a_ch - (mt ^ 1) * 128 + 63) / 64, 2);
         for (int32_t kb = kb0; kb < kb1; ++kb) {
           uint8_t* sa = ring + stage * P.stage_bytes;
           const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
@@ -673,15 +691,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           if (elect_one_sync()) {
             // a box that lies entirely beyond the tensor's channels is not fetched: its rows of the tile are >= m_valid
             // and never stored, whatever the shared memory holds
-            mbar_arrive_expect_tx(&full_bar[stage], a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
+            if (kPair) {
+              // both CTAs' copies are counted on the leader's barrier; this CTA holds its own M tile and half of the X boxes
+              const int32_t hb = nb >> 1;
+              if (sch.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + peer_boxes + nb) * kBoxBytesMN);
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
-            if (P.pair) {   // the X boxes are the same for both M tiles: each CTA fetches every other one for both
-              for (int j = static_cast<int>(sch.rank); j < nb; j += 2)
-                tma_load_5d_multicast(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3,
-                                      pair_mask);
+              for (int j = 0; j < 2; ++j)
+                if (j < a_boxes) tma_load_5d_2cta(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
+              for (int j = 0; j < hb; ++j)
+                tma_load_5d_2cta(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage],
+                                 bc0 + (static_cast<int>(sch.rank) * hb + j) * 64, b0, b1, b2, b3);
             } else {
+              mbar_arrive_expect_tx(&full_bar[stage], a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
               for (int j = 0; j < nb; ++j)
                 tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3);
             }
@@ -694,7 +718,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   } else if (mma_warp) {
     // -------------------------------------------------------------- MMA issuer
     // Converged warp, one elected lane issues tcgen05.mma / commit (always the same lane, so the commits track its MMAs).
-    const uint32_t idesc = make_idesc_bf16(128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
+    // paired: one tcgen05.mma.cta_group::2 of M = 256 per K step, issued by the leader; the peer's MMA warp has nothing to do
+    const uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
     // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the swizzled row.
     // MN-major: 64-element column groups one box (8192 B) apart, 8 K-rows = 1024 B; UMMA_K = 16 rows = 2048 B.
     const uint32_t lbo = wgrad ? kBoxBytesMN : 16;
@@ -703,7 +728,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     int32_t stage = 0;
     uint32_t phase = 0, acc = static_cast<uint32_t>(pipe), acc_phase = 0;
     if (P.b_res && sch.begin + pipe < sch.end) mbar_wait(bres_bar, 0);
-    for (int32_t tile = sch.begin + pipe; tile < sch.end; tile += tile_step) {
+    const int32_t mma_end = (kPair && sch.rank != 0) ? sch.begin : sch.end;
+    for (int32_t tile = sch.begin + pipe; tile < mma_end; tile += tile_step) {
       int32_t nk;
       if (!wgrad) {
         nk = k_chunks_fwd;
@@ -724,16 +750,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const uint64_t da = P.a_window ? make_smem_desc_noswizzle(sa, 16, 128) : make_smem_desc(sa, lbo, sbo);
         const uint64_t db = make_smem_desc(P.b_res ? smem_u32(smem) + kc * P.b_res : sa + P.a_alloc, lbo, sbo);
         if (elect_one_sync()) {
+          if (kPair) {
 #pragma unroll
-          for (uint32_t k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
-          if (P.pair) tcgen05_commit_multicast(&empty_bar[stage], pair_mask);
-          else tcgen05_commit(&empty_bar[stage]);
+            for (uint32_t k = 0; k < 4; ++k)
+              umma_bf16_2cta(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
+            tcgen05_commit_2cta(&empty_bar[stage], pair_mask);   // frees the stage in both CTAs
+          } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+              umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
+            tcgen05_commit(&empty_bar[stage]);
+          }
         }
         __syncwarp();
         if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one_sync()) tcgen05_commit(&tmem_full[acc]);
+      if (elect_one_sync()) {
+        if (kPair) tcgen05_commit_2cta(&tmem_full[acc], pair_mask);   // both CTAs' epilogues drain their half of the rows
+        else tcgen05_commit(&tmem_full[acc]);
+      }
       __syncwarp();
       if (P.dual) { acc_phase ^= 1; }
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -761,10 +796,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 
   tcgen05_fence_before();
   __syncthreads();
-  if (P.pair) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (kPair) cluster_sync_all();   // no CTA leaves while the pair's MMAs may still read its operands or arrive on its barriers
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -922,7 +958,9 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     v.a_window = d->a_window;
     v.a_bytes = d->a_window ? (int32_t)(a_rows + 7) * 16 : (int32_t)a_rows * 128;
     const int32_t a_alloc = wg ? 2 * kBoxBytesMN : (v.a_bytes + 1023) / 1024 * 1024;
-    const int32_t b_alloc = wg ? (d->block_n / 64) * kBoxBytesMN : (d->block_n * 128 + 1023) / 1024 * 1024;
+    // paired: each CTA holds half of the B tile (tcgen05.mma.cta_group::2 reads the other half from the peer)
+    const int32_t b_rows_cta = d->pair ? d->block_n / 2 : d->block_n;
+    const int32_t b_alloc = wg ? (b_rows_cta / 64) * kBoxBytesMN : (b_rows_cta * 128 + 1023) / 1024 * 1024;
     // a weight matrix of one N tile that fits in half of the operand memory is fetched once per CTA and stays
     const int64_t b_total = (int64_t)d->num_taps * d->cchunks * b_alloc;
     const bool resident = resident_b_enabled() && !wg && !d->pair && d->n_tiles == 1 && b_total <= kDataBytes / 2;
@@ -931,8 +969,8 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     v.ring_off = resident ? (int32_t)b_total : 0;
     v.stage_bytes = resident ? a_alloc : a_alloc + b_alloc;
     int32_t ns = (kDataBytes - v.ring_off) / v.stage_bytes;
-    // two pipelines when each still gets at least two stages and the plan is not paired (the pair protocol multicasts
-    // into the peer's ring in lock step)
+    // two pipelines when each still gets at least two stages and the plan is not paired (a pair already shares one MMA
+    // stream between two SMs)
     v.dual = dual_enabled() && !d->pair && ns >= 4 ? 1 : 0;
     if (v.dual) ns /= 2;
     const int32_t cap = v.dual ? kMaxStages / 2 : kMaxStages;
@@ -972,7 +1010,9 @@ extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, []() {
-    attr_err = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    attr_err = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
   if (attr_err != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   CUtensorMap ma, mb;
@@ -1005,8 +1045,9 @@ extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b
   }
   dev.out = out; dev.bias = bias; dev.stats = stats;
   {
-    cudaError_t e = launch_pdl(igemm_kernel, dim3(p->grid), dim3(kNumThreads), kSmemBytes, static_cast<cudaStream_t>(stream),
-                               p->desc.pair ? 2 : 1, ma, mb, dev);
+    cudaError_t e = p->desc.pair
+                        ? launch_pdl(igemm_kernel<true>, dim3(p->grid), dim3(kNumThreads), kSmemBytes, static_cast<cudaStream_t>(stream), 2, ma, mb, dev)
+                        : launch_pdl(igemm_kernel<false>, dim3(p->grid), dim3(kNumThreads), kSmemBytes, static_cast<cudaStream_t>(stream), 1, ma, mb, dev);
     if (e != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaLaunchKernelEx(igemm_kernel): %s", cudaGetErrorString(e));
   }
   PCGAN_LAUNCH_OK("igemm_kernel");
