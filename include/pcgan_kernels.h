@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 11
+#define PCGAN_ABI_VERSION 12
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -154,6 +154,11 @@ typedef struct {
    * row m of the tile reads the 64 elements starting at pixel m, through an overlapping shared-memory descriptor, instead
    * of fetching every pixel 8 times.  Packed weights as for the overlapping-stride form: [cout][tap][8 pixels x 8]. */
   int32_t a_window;
+  /* WGRAD filter rows in N (wg_box_dim = 1..4, 0 = off): the nb = block_n/64 boxes of N tile nt are not 64-channel slices of
+   * one pixel box but the same channels (tap_c0) at coordinate nt*nb + j along B tensor dim wg_box_dim (a filter-row
+   * dimension with the image-row stride, added to the view by the planner; boxes beyond its extent read zeros).  With
+   * num_taps = 1 the M operand is fetched once per N tile instead of once per filter row. */
+  int32_t wg_box_dim;
 } pcgan_igemm_desc;
 
 typedef struct pcgan_igemm_plan pcgan_igemm_plan;
@@ -368,8 +373,8 @@ typedef struct {
   float* p; const float* g; float* m; float* v;
   int64_t n;
 } pcgan_adam_item;
-int pcgan_adam_batched(const pcgan_adam_item* items, int32_t count, int64_t max_n, const float* lr, float beta1, float beta2,
-                       float eps, float* step, pcgan_stream_t stream);
+int pcgan_adam_batched(const pcgan_adam_item* items, int32_t count, int64_t max_n, const float* lr, double beta1, double beta2,
+                       double eps, float* step, pcgan_stream_t stream);
 
 #ifdef __cplusplus
 }

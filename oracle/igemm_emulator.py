@@ -159,9 +159,14 @@ def run_wgrad(s, a_flat, b_flat, out_flat):
             A = torch.cat(As, dim=2)
             for nt in range(s.n_tiles):
                 Bs = []
+                bdim = getattr(s, "wg_box_dim", 0)
                 for j in range(nb):
-                    coords = torch.stack([torch.full((total_kb,), s.tap_c0[t] + nt * s.block_n + j * 64, dtype=torch.int64)] +
-                                         [bc[d] + s.tap_off[t][d] for d in range(4)], dim=1)
+                    if bdim:   # filter rows in N: box nt*nb + j along tensor dim bdim, same channels
+                        coords = torch.stack([torch.full((total_kb,), s.tap_c0[t], dtype=torch.int64)] +
+                                             [bc[d] + s.tap_off[t][d] + (nt * nb + j if d + 1 == bdim else 0) for d in range(4)], dim=1)
+                    else:
+                        coords = torch.stack([torch.full((total_kb,), s.tap_c0[t] + nt * s.block_n + j * 64, dtype=torch.int64)] +
+                                             [bc[d] + s.tap_off[t][d] for d in range(4)], dim=1)
                     Bs.append(tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, coords))
                 B = torch.cat(Bs, dim=2)  # [kb, 64, block_n]
                 D = torch.einsum("kpm,kpn->mn", A, B)  # [128, block_n]

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -47,7 +47,7 @@ class IgemmDesc(C.Structure):
         ("out_dtype", i32), ("act", i32), ("act_slope", f32), ("n_valid", i32), ("out_cstride", i64),
         ("stats_mode", i32), ("stats_dim", i32), ("stats_comp", i32),
         ("m_valid", i32), ("wg_ncols", i32), ("ldo", i64), ("pair", i32), ("shift_taps", i32), ("shift_cpad", i32),
-        ("a_window", i32),
+        ("a_window", i32), ("wg_box_dim", i32),
     ]
 
 
@@ -148,7 +148,7 @@ SYMBOLS = {
     "pcgan_maxpool3x3s2_bwd": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]),
     "pcgan_loss": (C.c_int, [C.POINTER(LossArgs), vp]),
     "pcgan_adam": (C.c_int, [vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, vp]),
-    "pcgan_adam_batched": (C.c_int, [vp, i32, i64, vp, f32, f32, f32, vp, vp]),
+    "pcgan_adam_batched": (C.c_int, [vp, i32, i64, vp, C.c_double, C.c_double, C.c_double, vp, vp]),
 }
 
 _lib = None

@@ -198,7 +198,8 @@ def conv_wgrad_plan(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, *, trans
     assert (dyg.h, dyg.w) == (ho, wo) or (dyg.h >= ho and dyg.w >= wo)
     if (stride == 1 and xg.c == 64 and cin == 64 and cout <= 8 and dyg.c == 8 and k <= 8 and dyg.pad >= o + k - 1
             and 2 * xg.pad - o <= dyg.pad and (dyg.h, dyg.w) == (ho, wo)):
-        return plan_wgrad_small_cout(xg, cin, dyg, k, o, note=note), wmap_small_cout(w_shape, k)
+        sp = plan_wgrad_small_cout(xg, cin, dyg, k, o, note=note)
+        return sp, wmap_small_cout(w_shape, k, sp.box_taps)
     if xg.c >= 64:
         assert xg.c == cin
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]

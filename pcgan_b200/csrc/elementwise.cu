@@ -379,15 +379,14 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 // Multi-tensor form: blockIdx.y = tensor.  `step` holds the number of updates already applied; this update is number
 // step + 1 and step_inc_kernel, launched behind it, stores that.
-__global__ void adam_batched_kernel(const pcgan_adam_item* __restrict__ items, const float* lr_p, float b1, float b2, float eps,
-                                    const float* step_p) {
+__global__ void adam_batched_kernel(const pcgan_adam_item* __restrict__ items, const float* lr_p, float b1, float b2, float c1,
+                                    float c2, float eps, const float* step_p) {
   griddep_wait();
   griddep_launch();
   const pcgan_adam_item it = items[blockIdx.y];
   const float lr = *lr_p, step = *step_p + 1.f;
   const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
   const float step_size = lr / bc1, rsq_bc2 = rsqrtf(bc2);
-  const float c1 = 1.f - b1, c2 = 1.f - b2;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
   const bool vec = ((reinterpret_cast<uintptr_t>(it.p) | reinterpret_cast<uintptr_t>(it.g) | reinterpret_cast<uintptr_t>(it.m) |
                      reinterpret_cast<uintptr_t>(it.v)) & 15) == 0;
@@ -568,14 +567,16 @@ extern "C" int pcgan_adam(float* p, const float* g, float* m, float* v, int64_t 
   return PCGAN_OK;
 }
 
-extern "C" int pcgan_adam_batched(const pcgan_adam_item* items, int32_t count, int64_t max_n, const float* lr, float beta1,
-                                  float beta2, float eps, float* step, pcgan_stream_t s) {
+extern "C" int pcgan_adam_batched(const pcgan_adam_item* items, int32_t count, int64_t max_n, const float* lr, double beta1,
+                                  double beta2, double eps, float* step, pcgan_stream_t s) {
   if (!items || !lr || !step) return fail(PCGAN_ERR_INVALID, "adam_batched: null argument");
   dim3 grid;
   int rc = batched_grid(count, max_n, &grid);
   if (rc) return rc;
-  PCGAN_CUDA_OK(launch_pdl(adam_batched_kernel, grid, dim3(kThreads), 0, STREAM(s), 1, items, lr, beta1, beta2, eps,
-                           static_cast<const float*>(step)));
+  // 1 - beta is rounded from double, as torch.optim.Adam's `value=1 - beta2` is
+  PCGAN_CUDA_OK(launch_pdl(adam_batched_kernel, grid, dim3(kThreads), 0, STREAM(s), 1, items, lr, static_cast<float>(beta1),
+                           static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2),
+                           static_cast<float>(eps), static_cast<const float*>(step)));
   PCGAN_LAUNCH_OK("adam_batched_kernel");
   PCGAN_CUDA_OK(launch_pdl(step_inc_kernel, dim3(1), dim3(1), 0, STREAM(s), 1, step));
   PCGAN_LAUNCH_OK("step_inc_kernel");

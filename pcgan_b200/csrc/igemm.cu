@@ -52,6 +52,7 @@ struct DevParams {
   int32_t a_bytes;     // bytes one A box brings into a stage
   int32_t b_res;       // KMAJOR, > 0: the whole B operand stays resident in front of the ring, b_res bytes per K chunk
   int32_t ring_off;    // byte offset of the ring behind the resident B operand
+  int32_t wg_box_dim;  // WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N), 0 = channels
   int32_t dual;        // 1: two independent producer -> MMA -> epilogue pipelines (even / odd tiles of the CTA), each with
                        //    num_stages stages of the ring and one TMEM accumulator
   int32_t t_count[4];
@@ -668,7 +669,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t nb = P.block_n >> 6;
         const uint32_t bytes = (2 + nb) * kBoxBytesMN;
         const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2], o3 = P.tap_off[tap][3];
-        const int32_t bc0 = P.tap_c0[tap] + nt * P.block_n;
+        // the nb boxes of this N tile: 64-channel slices of one pixel box, or (filter rows in N) the same channels at
+        // box coordinates nt*nb + j along dim wg_box_dim
+        const int32_t bdim = P.wg_box_dim;
+        const int32_t bc0 = P.tap_c0[tap] + (bdim ? 0 : nt * P.block_n), bcs = bdim ? 0 : 64;
+        const int32_t box0 = bdim ? nt * nb : 0;
+        const int32_t e0 = bdim == 1, e1 = bdim == 2, e2 = bdim == 3, e3 = bdim == 4;
         // pixel blocks kb0 .. kb1-1 are consecutive: the mixed-radix digits are stepped, not re-divided, per block
         Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count);
         // 64-channel boxes of this M tile (and of the peer's) that exist: 1 or 2
@@ -698,16 +704,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 2; ++j)
                 if (j < a_boxes) tma_load_5d_2cta(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
-              for (int j = 0; j < hb; ++j)
-                tma_load_5d_2cta(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage],
-                                 bc0 + (static_cast<int>(sch.rank) * hb + j) * 64, b0, b1, b2, b3);
+              for (int j = 0; j < hb; ++j) {
+                const int32_t jj = static_cast<int>(sch.rank) * hb + j, bx = bdim ? box0 + jj : 0;
+                tma_load_5d_2cta(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + jj * bcs, b0 + e0 * bx,
+                                 b1 + e1 * bx, b2 + e2 * bx, b3 + e3 * bx);
+              }
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
 #pragma unroll
               for (int j = 0; j < 2; ++j)
                 if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
-              for (int j = 0; j < nb; ++j)
-                tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * 64, b0, b1, b2, b3);
+              for (int j = 0; j < nb; ++j) {
+                const int32_t bx = bdim ? box0 + j : 0;
+                tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * bcs, b0 + e0 * bx, b1 + e1 * bx,
+                            b2 + e2 * bx, b3 + e3 * bx);
+              }
             }
           }
           __syncwarp();
@@ -944,6 +955,8 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
         a_rows <= d->shift_taps - 1)
       return fail(PCGAN_ERR_INVALID, "shift-sum epilogue: KMAJOR, block_n == 32, one N tile, shift_taps*shift_cpad <= 32, n_valid <= shift_cpad in {4, 8}, no statistics");
   }
+  if (d->wg_box_dim != 0 && (!wg || d->wg_box_dim < 1 || d->wg_box_dim > 4 || d->num_taps != 1))
+    return fail(PCGAN_ERR_INVALID, "wg_box_dim: WGRAD with num_taps == 1, dim 1..4");
   if (d->pair && wg && (d->m_tiles % 2 != 0 || (d->block_n / 64) % 2 != 0))
     return fail(PCGAN_ERR_INVALID, "paired WGRAD needs an even m_tiles and an even number of 64-column B boxes");
 
@@ -983,6 +996,7 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   v.num_m_tiles = (int32_t)tiles; v.total_tiles = (int32_t)total;
   v.pair = d->pair;
   v.shift_taps = d->shift_taps; v.shift_cpad = d->shift_cpad;
+  v.wg_box_dim = d->wg_box_dim;
   v.sched_items = !d->pair ? (int32_t)total : (wg ? (int32_t)(total / 2) : (int32_t)(((tiles + 1) / 2) * d->n_tiles));
   v.num_taps = d->num_taps; v.cchunks = d->cchunks;
   memcpy(v.tap_off, d->tap_off, sizeof(v.tap_off)); memcpy(v.tap_c0, d->tap_c0, sizeof(v.tap_c0));

@@ -118,6 +118,14 @@ class FusedAdam(torch.optim.Adam):
             ops.adam_batched(table, b["count"], b["max_n"], self._lr(b, group["lr"]), float(beta1), float(beta2), float(group["eps"]), b["step"])
         return loss
 
+    def state_dict(self):
+        """torch.optim.Adam's layout with private copies: the moments are views of this optimizer's arenas and the step
+        counter is one tensor shared by a whole group, neither of which another optimizer may alias."""
+        sd = super().state_dict()
+        sd["state"] = {k: {kk: (vv.clone() if isinstance(vv, torch.Tensor) else vv) for kk, vv in st.items()}
+                       for k, st in sd["state"].items()}
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._groups = {}     # re-bind from the loaded tensors at the next step

@@ -125,7 +125,9 @@ class IgemmSpec:
     shift_cpad: int = 0
     pair: int = 0              # CTA pairs sharing the B operand through TMA multicast (include/pcgan_kernels.h)
     a_window: int = 0          # 8: A is the plain 8-channel tensor read through an overlapping descriptor (pcgan_kernels.h)
+    wg_box_dim: int = 0        # WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N)
     swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
+    box_taps: Optional[List[int]] = None   # wg_box_dim: kidx of the filter row held by 64-column box i of the output
 
     @property
     def num_taps(self):
@@ -161,6 +163,7 @@ class IgemmSpec:
         d.pair = self.pair
         d.shift_taps, d.shift_cpad = self.shift_taps, self.shift_cpad
         d.a_window = self.a_window
+        d.wg_box_dim = self.wg_box_dim
         return d
 
 
@@ -183,6 +186,7 @@ def _block_n(cout):
 
 
 PAIRING = True   # CTA pairs with a multicast B operand where it pays (large N tiles, enough M tiles)
+TAPBOX = True    # packed-window weight gradients: the filter rows ride in N, the 64-channel operand is read once per N tile
 WINDOW = True    # 8-channel inputs: windowed A operand (pcgan_igemm_desc.a_window) instead of overlapping-stride TMA boxes
 
 
@@ -554,6 +558,33 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
     C, Hp, Wp = ng.c, ng.hp, ng.wp
     d0 = n_packed_win if n_packed_win else C
+    dys = sorted(dy for dy, _, _ in taps)
+    kh = len(taps)
+    if (TAPBOX and n_packed_win == 64 and n_stride == 1 and kh > 1 and len(set(dx for _, dx, _ in taps)) == 1
+            and dys == list(range(dys[0], dys[0] + kh)) and ph + dys[0] + kh - 1 <= Hp and dys[0] >= 0):
+        # filter rows in N: the B view gets a filter-row dimension (same stride as the image row) and 64-column box i of
+        # the N tiles is the window of row dys[0] + i, so the 64-channel M operand is fetched once per N tile of four
+        # filter rows instead of once per row.  Output column = i*64 + window element; s.box_taps[i] = kidx of box i.
+        by_dy = {dy: kidx for dy, _, kidx in taps}
+        s.box_taps = [by_dy[dys[0] + i] for i in range(kh)]
+        s.wg_box_dim = 2
+        s.block_n = 256
+        s.n_tiles = _ceil(kh * 64, 256)
+        s.wg_ncols = kh * 64
+        s.b_dims = [64, Wp, kh, Hp - (kh - 1), N]
+        s.b_strides = [0, C * 2, Wp * C * 2, Wp * C * 2, Hp * Wp * C * 2]
+        s.b_box = [64, bw, 1, bh, 1]
+        s.b_step[0][0], s.b_step[1][2], s.b_step[2][3] = bw, bh, bn
+        s.tap_off.append([taps[0][1], 0, dys[0], 0])
+        s.tap_c0.append(0)
+        s.tap_bk.append(0)
+        s.ldo = kh * 64
+        s.b_rows, s.b_k = m_ch, s.ldo
+        total_kb = tx * ty * tn
+        s.ksplit = _ksplit_for(total_kb, s.m_tiles * s.n_tiles)
+        s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n
+        s.pair = int(PAIRING and s.m_tiles % 2 == 0)
+        return s
     if n_stride == 1:
         s.b_dims = [d0, Wp, Hp, N, 1]
         s.b_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
@@ -616,12 +647,13 @@ def plan_wgrad_small_cout(xg: Geom, cin: int, dyg: Geom, k: int, o: int, *, note
     return s
 
 
-def wmap_small_cout(w_shape, k: int) -> torch.Tensor:
-    """Scatter map of plan_wgrad_small_cout: packed[ci][r*64 + j*8 + co] -> W[co][ci][r][k-1-j]."""
+def wmap_small_cout(w_shape, k: int, box_taps=None) -> torch.Tensor:
+    """Scatter map of plan_wgrad_small_cout: packed[ci][i*64 + j*8 + co] -> W[co][ci][r][k-1-j] with r = i, or
+    r = box_taps[i] when the filter rows ride in N (IgemmSpec.box_taps)."""
     cout, cin = w_shape[0], w_shape[1]
     idx = torch.full((cin, k, 8, 8), -1, dtype=torch.int64)
     ci = torch.arange(cin).view(-1, 1, 1, 1)
-    r = torch.arange(k).view(1, -1, 1, 1)
+    r = torch.tensor(list(box_taps) if box_taps is not None else list(range(k))).view(1, -1, 1, 1)
     j = torch.arange(8).view(1, 1, -1, 1)
     co = torch.arange(8).view(1, 1, 1, -1)
     flat = ((co * cin + ci) * k + r) * k + (k - 1 - j)

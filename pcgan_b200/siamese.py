@@ -6,7 +6,7 @@ of BASELINE config 2 (siamese.py:590-686) and the model factory it uses (siamese
     loss = trainer.train_step(img0, img1, label)     # label in {0, 1, 2}: img0 loses / draw / wins (LUT 0, .5, 1)
 
 Forward and backward (data, weight and BatchNorm-parameter gradients of the whole ResNet-18 + head) run on
-libpcgan_kernels.so; torch.optim.Adam updates the fp32 master weights, as in the reference.
+libpcgan_kernels.so; FusedAdam (torch.optim.Adam's semantics, one launch) updates the fp32 master weights.
 """
 import itertools
 
@@ -14,6 +14,7 @@ import torch
 from torch.nn import init
 
 from . import networks
+from .optim import FusedAdam
 
 
 def weights_init(m):
@@ -51,7 +52,7 @@ class EloTrainer:
         self.net = net
         self.criterion = networks.BinaryNLLLoss()
         params = itertools.chain(net.base.parameters(), net.cnn.parameters())     # siamese.py:544-549 (no cxn, no fc)
-        self.optimizer = torch.optim.Adam(params, lr=lr)
+        self.optimizer = FusedAdam(params, lr=lr)
         self.bayesian, self.T_train = bayesian, T_train
         if net._noisy:
             raise NotImplementedError("the noisy (aleatoric) trainer branches of siamese.py:606-660 are not implemented")

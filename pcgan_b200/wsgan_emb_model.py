@@ -25,6 +25,7 @@ from torch.optim import lr_scheduler
 from . import networks
 from .dist import GradSync
 from .networks import compute_mu_and_var, resample, upsample2d
+from .optim import FusedAdam
 
 
 def default_options(**overrides):
@@ -160,16 +161,15 @@ class WSGANEmbModel(BaseModel):
             self.criterionRec = networks.mse_loss
             self.criterionCycle = networks.l1_loss
             # --cuda_graph: the whole optimize_parameters() (about 950 kernel launches) is captured once and replayed, so
-            # the step costs one graph launch of host time.  Adam then keeps lr / step on the device (capturable).
+            # the step costs one graph launch of host time; the learning rate then lives in a device scalar the schedulers fill.
             self.use_graph = bool(getattr(opt, "cuda_graph", False))
             self._graphs, self._eager_steps, self._side = {}, 0, None
+            # FusedAdam is torch.optim.Adam (same state, same schedulers) whose step() is one multi-tensor launch
             adam_kw = dict(betas=(opt.beta1, 0.999))
-            if self.use_graph:
-                adam_kw.update(capturable=True, foreach=True)
             lr = torch.tensor(float(opt.lr), device=self.device) if self.use_graph else opt.lr
-            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=lr, **adam_kw)
+            self.optimizer_G = FusedAdam(self.netG.parameters(), lr=lr, **adam_kw)
             lr = torch.tensor(float(opt.lr), device=self.device) if self.use_graph else opt.lr
-            self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=lr, **adam_kw)
+            self.optimizer_D = FusedAdam(self.netD.parameters(), lr=lr, **adam_kw)
             self.optimizers = [self.optimizer_G, self.optimizer_D]
             # one process per GPU: flat gradient buffers, averaged over ranks with one NCCL all-reduce per network
             self.sync_G = GradSync(list(self.netG.parameters()))
@@ -181,7 +181,7 @@ class WSGANEmbModel(BaseModel):
             if opt.lr_E > 0.0:      # wsgan_emb_model.py:159-163
                 if self.use_graph:
                     raise NotImplementedError("--cuda_graph with --lr_E > 0 (two generator updates per step) is not supported")
-                self.optimizer_E = torch.optim.Adam(self.netE.parameters(), lr=opt.lr_E, betas=(opt.beta1, 0.999))
+                self.optimizer_E = FusedAdam(self.netE.parameters(), lr=opt.lr_E, betas=(opt.beta1, 0.999))
                 self.optimizers.append(self.optimizer_E)
                 self.sync_E = GradSync(list(self.netE.parameters()))
                 # backward_GE keeps the graph (retain_graph=True, :369) and backward_G_alone walks G's first pass and

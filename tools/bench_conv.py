@@ -99,6 +99,22 @@ def main():
         res.append(report("stem fwd +stats [%s]" % tag, time_plans(p, x0, o1, stats=st1, bias=b64), N * S * S * 64 * 4 * 49))
         p = CV.conv_dgrad_plans((3, 64, 7, 7), dyg, xg64, 1, 3, OutMap.nhwc(fullg), full_padded=True)
         res.append(report("head dgrad 3->64 padded [%s]" % tag, time_plans(p, dy8, ofull), N * S * S * 64 * 3 * 49))
+    PL.WINDOW = True
+    # N = 128 layers: CTA pairs (one cta_group::2 MMA) against unpaired CTAs with two pipelines
+    for flag in (True, False):
+        PL.PAIRING = flag
+        tag = "pair" if flag else "dual"
+        p = CV.conv_fwd_plans((128, 64, 3, 3), xa1, 2, 1, OutMap.nhwc(r2))
+        res.append(report("down1 fwd 64->128 s2 [%s]" % tag, time_plans(p, xa, o), N * (S // 2) ** 2 * 64 * 128 * 9))
+        o_up = torch.zeros(ru.numel + 512, dtype=torch.bfloat16, device=DEV)
+        p = CV.conv_fwd_plans((256, 128, 3, 3), xb, 2, 1, OutMap.nhwc(ru), transposed=True, output_padding=1)
+        res.append(report("up1 fwd convT 256->128 [%s]" % tag, time_plans(p, xbb, o_up), N * 32 * 32 * 256 * 128 * 9))
+        xd, rd = Geom(N, 32, 32, 128, 1), Geom(N, 16, 16, 256, 0)
+        xdb = torch.randn(xd.numel + 512, device=DEV).to(torch.bfloat16)
+        od = torch.zeros(rd.numel + 512, dtype=torch.bfloat16, device=DEV)
+        p = CV.conv_fwd_plans((256, 128, 4, 4), xd, 2, 1, OutMap.nhwc(rd), stats=True)
+        res.append(report("D.5 fwd 4x4 s2 128->256 +BN [%s]" % tag, time_plans(p, xdb, od, stats=torch.zeros(1, 256, 2, device=DEV)), N * 16 * 16 * 128 * 256 * 16))
+    PL.PAIRING = True
     # stem weight gradient (dY 64 ch x packed window) and an encoder 64->64 convolution with batch statistics
     dy64 = Geom(N, S, S, 64, 0)
     dyb = torch.randn(dy64.numel + 512, device=DEV).to(torch.bfloat16)
