@@ -116,6 +116,9 @@ class FusedAdam(torch.optim.Adam):
             table = self._table(b)
             beta1, beta2 = group["betas"]
             ops.adam_batched(table, b["count"], b["max_n"], self._lr(b, group["lr"]), float(beta1), float(beta2), float(group["eps"]), b["step"])
+            # the kernel wrote through raw pointers: tell autograd (and the engine's packed-operand cache, which keys on
+            # Tensor._version) that the parameters changed
+            torch.autograd.graph.increment_version(b["params"])
         return loss
 
     def state_dict(self):

@@ -42,6 +42,7 @@ def test_matches_torch_adam_over_steps_and_lr_schedule():
             assert ob.param_groups[0]["lr"] == pytest.approx(oa.param_groups[0]["lr"])
     for a, b in zip(pa, pb):
         assert float((a - b).abs().max()) <= 2e-6 * (1.0 + float(a.abs().max()))     # fp32 rounding of a different op order
+    assert all(b._version >= 12 for b in pb)       # in-place updates are visible to autograd / version-keyed caches
     st = ob.state[pb[0]]
     assert set(st) >= {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 12.0
     assert torch.allclose(st["exp_avg"], oa.state[pa[0]]["exp_avg"], rtol=1e-5, atol=1e-8)
