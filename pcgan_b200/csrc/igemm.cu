@@ -53,6 +53,7 @@ struct DevParams {
   int32_t b_res;       // KMAJOR, > 0: the whole B operand stays resident in front of the ring, b_res bytes per K chunk
   int32_t ring_off;    // byte offset of the ring behind the resident B operand
   int32_t wg_box_dim;  // WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N), 0 = channels
+  int32_t acc_sub;     // 1 (dual, block_n <= 128): each pipeline double-buffers its accumulator in two 128-column halves
   int32_t dual;        // 1: two independent producer -> MMA -> epilogue pipelines (even / odd tiles of the CTA), each with
                        //    num_stages stages of the ring and one TMEM accumulator
   int32_t t_count[4];
@@ -148,15 +149,20 @@ __device__ __forceinline__ void wgrad_item(const DevParams& P, const Sched& sc, 
 struct EpiShared {
   uint32_t s_bias;     // shared address of this group's bias [256]
   uint32_t s_tr;       // shared address of this warp's scratch: statistics partial sums [2][256] or exchange tile [32][17]
-  uint64_t* tmem_full; // barrier of this group's TMEM stage
+  uint64_t* tmem_full; // barriers of this group's accumulator(s): [2], the second one used when P.acc_sub
   uint64_t* tmem_empty;
   uint32_t group;      // 0 / 1: also the TMEM stage and the parity of the CTA-local tile index it handles
 };
 
 // The accumulator stage is drained: tell the MMA warp (the pair's leader's when paired).
-__device__ __forceinline__ void epi_release(const DevParams& P, const EpiShared& es) {
-  if (P.pair) mbar_arrive_leader(es.tmem_empty);
-  else mbar_arrive(es.tmem_empty);
+__device__ __forceinline__ void epi_release(const DevParams& P, const EpiShared& es, uint32_t sub) {
+  if (P.pair) mbar_arrive_leader(es.tmem_empty + sub);
+  else mbar_arrive(es.tmem_empty + sub);
+}
+// Accumulator of a group's j-th tile: which half (0 unless P.acc_sub) and the parity of its barriers' phase.
+__device__ __forceinline__ void acc_slot(const DevParams& P, uint32_t j, uint32_t& sub, uint32_t& phase) {
+  sub = P.acc_sub ? (j & 1u) : 0u;
+  phase = P.acc_sub ? ((j >> 1) & 1u) : (j & 1u);
 }
 
 template <int ACT>
@@ -222,7 +228,7 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
   const float* bias = P.bias;
   const float slope = P.act_slope;
   const uint32_t s_bias = es.s_bias;
-  uint32_t acc_phase = 0;
+  uint32_t jt = 0;   // tiles this group has drained
   int32_t cur_nt = -1, cur_group = -1;
 
   // box-local index of this row along the four outer box dims (tile-invariant)
@@ -297,9 +303,11 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
     OutT* orow = reinterpret_cast<OutT*>(P.out) + off + static_cast<int64_t>(nt) * block_n * cs;
     const bool fast_rows = cs == 1 && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
 
-    mbar_wait(es.tmem_full, acc_phase);
+    uint32_t sub, acc_phase;
+    acc_slot(P, jt, sub, acc_phase);
+    mbar_wait(es.tmem_full + sub, acc_phase);
     tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols;
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols + sub * 128u;
 
     for (int32_t c0 = 0; c0 < ncol_limit; c0 += 32) {
       uint32_t raw[32];
@@ -361,8 +369,8 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
     }
     // accumulator drained: hand the TMEM stage back to the MMA warp
     tcgen05_fence_before();
-    epi_release(P, es);
-    acc_phase ^= 1;
+    epi_release(P, es, sub);
+    ++jt;
   }
   if (STATS && cur_group >= 0) flush_stats(cur_group, cur_nt);
 }
@@ -393,7 +401,7 @@ __device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShar
     }
   }
   const bool row_out = static_cast<int32_t>(row) < P.a_rows - (kw - 1);
-  uint32_t acc_phase = 0;
+  uint32_t jt = 0;   // tiles this group has drained
   for (int32_t tile = sch.begin + static_cast<int32_t>(es.group); tile < sch.end; tile += kEpiGroups) {
     int32_t mt, nt;
     bool tile_valid;
@@ -413,16 +421,18 @@ __device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShar
       valid = valid && g >= 0 && k0 >= m0.lo && k0 < m0.hi && k1 >= m1.lo && k1 < m1.hi && k2 >= m2.lo && k2 < m2.hi;
       off += (k0 - m0.lo) * m0.stride + (k1 - m1.lo) * m1.stride + (k2 - m2.lo) * m2.stride;
     }
-    mbar_wait(es.tmem_full, acc_phase);
+    uint32_t sub, acc_phase;
+    acc_slot(P, jt, sub, acc_phase);
+    mbar_wait(es.tmem_full + sub, acc_phase);
     tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols;
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols + sub * 128u;
     uint32_t raw[32];
     tmem_ld_32x32(taddr, raw);
     tmem_ld_wait();
     // the accumulator is in registers: hand the TMEM stage back before the exchange
     tcgen05_fence_before();
-    epi_release(P, es);
-    acc_phase ^= 1;
+    epi_release(P, es, sub);
+    ++jt;
     float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) o[c] = 0.f;
@@ -500,7 +510,7 @@ __device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShar
   const uint32_t q = warp & 3;
   const uint32_t row = q * 32 + lane;
   const int32_t block_n = P.block_n;
-  uint32_t acc_phase = 0;
+  uint32_t jt = 0;   // tiles this group has drained
   for (int32_t tile = sch.begin + static_cast<int32_t>(es.group); tile < sch.end; tile += kEpiGroups) {
     int32_t ks, nt, mt, tap;
     wgrad_item(P, sch, tile, ks, nt, mt, tap);
@@ -509,9 +519,11 @@ __device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShar
     const int32_t ncol_limit = min(P.wg_ncols - nt * block_n, block_n);
     float* orow = reinterpret_cast<float*>(P.out) + static_cast<int64_t>(grow) * P.ldo + P.tap_bk[tap] + nt * block_n;
     const bool aligned = (reinterpret_cast<uintptr_t>(orow) & 15) == 0;
-    mbar_wait(es.tmem_full, acc_phase);
+    uint32_t sub, acc_phase;
+    acc_slot(P, jt, sub, acc_phase);
+    mbar_wait(es.tmem_full + sub, acc_phase);
     tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols;
+    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + es.group * kAccCols + sub * 128u;
     for (int32_t c0 = 0; c0 < ncol_limit; c0 += 32) {
       uint32_t raw[32];
       tmem_ld_32x32(taddr + c0, raw);
@@ -532,8 +544,8 @@ __device__ __forceinline__ void epilogue_wgrad(const DevParams& P, const EpiShar
       }
     }
     tcgen05_fence_before();
-    epi_release(P, es);
-    acc_phase ^= 1;
+    epi_release(P, es, sub);
+    ++jt;
   }
 }
 
@@ -549,9 +561,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* bres_bar = tmem_empty + 3;
+  uint64_t* tmem_empty = tmem_full + 4;    // [group][half]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
+  uint64_t* bres_bar = tmem_empty + 5;
   const uint32_t s_bias = smem_u32(tail + kTailBias);        // [2 groups][256] f32
   const uint32_t s_tr = smem_u32(tail + kTailTr);            // [8 warps] x kWarpScratch
 
@@ -567,7 +579,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kPair ? 256 : 128);   // paired: the leader's MMA warp waits for both CTAs' epilogues
     }
@@ -737,7 +749,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t sbo = 1024;
     const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
     int32_t stage = 0;
-    uint32_t phase = 0, acc = static_cast<uint32_t>(pipe), acc_phase = 0;
+    uint32_t phase = 0, jt = 0;   // jt: tiles this warp has issued
     if (P.b_res && sch.begin + pipe < sch.end) mbar_wait(bres_bar, 0);
     const int32_t mma_end = (kPair && sch.rank != 0) ? sch.begin : sch.end;
     for (int32_t tile = sch.begin + pipe; tile < mma_end; tile += tile_step) {
@@ -749,9 +761,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t kb0 = ks * kb_per_split;
         nk = max(min(kb0 + kb_per_split, total_kb) - kb0, 0);
       }
+      // single pipeline: tiles alternate between the two groups' accumulators; dual: this pipeline's own group
+      const uint32_t group = P.dual ? static_cast<uint32_t>(pipe) : (jt & 1u);
+      uint32_t sub, acc_phase;
+      acc_slot(P, P.dual ? jt : (jt >> 1), sub, acc_phase);
+      const uint32_t acc = group * 2 + sub;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * kAccCols;
+      const uint32_t tmem_d = tmem_base + group * kAccCols + sub * 128u;
       for (int32_t kc = 0; kc < nk; ++kc) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -781,13 +798,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         else tcgen05_commit(&tmem_full[acc]);
       }
       __syncwarp();
-      if (P.dual) { acc_phase ^= 1; }
-      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      ++jt;
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const uint32_t eg = (warp - 4) >> 2;
-    EpiShared es{s_bias + eg * 1024, s_tr + (warp - 4) * kWarpScratch, &tmem_full[eg], &tmem_empty[eg], eg};
+    EpiShared es{s_bias + eg * 1024, s_tr + (warp - 4) * kWarpScratch, &tmem_full[eg * 2], &tmem_empty[eg * 2], eg};
     if (wgrad) {
       epilogue_wgrad(P, es, tmem_base, sch, total_kb, kb_per_split);
     } else {
@@ -986,6 +1002,7 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     // stream between two SMs)
     v.dual = dual_enabled() && !d->pair && ns >= 4 ? 1 : 0;
     if (v.dual) ns /= 2;
+    v.acc_sub = v.dual && d->block_n <= 128 ? 1 : 0;
     const int32_t cap = v.dual ? kMaxStages / 2 : kMaxStages;
     v.num_stages = ns > cap ? cap : (ns < 2 ? 2 : ns);
   }
