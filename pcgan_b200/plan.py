@@ -191,9 +191,9 @@ WINDOW = True    # 8-channel inputs: windowed A operand (pcgan_igemm_desc.a_wind
 
 
 def _pair_kmajor(s: "IgemmSpec", m_tiles: int) -> int:
-    """Pair two M tiles when the shared B tile is at least as large as an A tile (block_n >= 128) and every SM still
-    gets work."""
-    return int(PAIRING and s.block_n >= 128 and m_tiles * s.n_tiles >= 2)
+    """Pair two M tiles (one tcgen05.mma.cta_group::2 of M = 256) for full-width N tiles; narrower tiles run faster
+    unpaired through two pipelines with double-buffered accumulators (measured: tools/bench_conv.py, [pair] / [dual])."""
+    return int(PAIRING and s.block_n >= 256 and m_tiles * s.n_tiles >= 2)
 
 
 ANY = (0, 1 << 30, 0)
