@@ -100,24 +100,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same on 32-bit shared addresses (hot loops keep the addresses of their ring barriers in registers).
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
+__device__ __forceinline__ void tcgen05_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2cta_addr(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // TMA tiled loads, completion on an mbarrier (bytes counted by complete_tx).
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+// (destination and barrier are 32-bit shared addresses: the producer loops step them per ring stage)
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
                                             int32_t c2, int32_t c3, int32_t c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // CTA pair sharing one tcgen05.mma.cta_group::2: shared-memory addresses of a CTA in a cluster carry its rank in bit 24;
 // clearing it names the same offset in the pair's leader (rank 0).
 __device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+__device__ __forceinline__ uint32_t leader_addr(uint32_t a) { return a & 0xFEFFFFFFu; }
 // Tiled load into THIS CTA's shared memory whose bytes are counted on the LEADER's mbarrier (issued by both CTAs).
-__device__ __forceinline__ void tma_load_5d_2cta(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+__device__ __forceinline__ void tma_load_5d_2cta(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1,
                                                  int32_t c2, int32_t c3, int32_t c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_dst),
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }

@@ -627,13 +627,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     // The whole warp walks the (uniform) schedule; one elected lane issues the copies.
     int32_t stage = 0;
     uint32_t phase = 0;
+    // shared addresses of ring stage 0 and of its barriers; the loops step them
+    const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t stage_bytes = static_cast<uint32_t>(P.stage_bytes), a_alloc = static_cast<uint32_t>(P.a_alloc);
+    uint32_t sa = ring0, full_a = full0, empty_a = empty0;
     if (P.b_res && pipe == 0 && sch.begin < sch.end) {
       // small weight matrices (one N tile) are fetched once per CTA, not once per tile
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(k_chunks_fwd * P.block_n * 128));
         for (int32_t tap = 0; tap < P.num_taps; ++tap)
           for (int32_t cc = 0; cc < P.cchunks; ++cc)
-            tma_load_5d(smem + (tap * P.cchunks + cc) * P.b_res, &tma_b, bres_bar, P.tap_bk[tap] + cc * 64, 0, 0, 0, 0);
+            tma_load_5d(smem_u32(smem) + (tap * P.cchunks + cc) * P.b_res, &tma_b, smem_u32(bres_bar), P.tap_bk[tap] + cc * 64, 0, 0, 0, 0);
       }
       __syncwarp();
     }
@@ -649,28 +653,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t half_rows = P.block_n >> 1;   // paired: this CTA holds rows [rank*half, +half) of the B tile
         // paired: both CTAs' copies (own A tile + own half of B each) are counted on the leader's barrier
         const uint32_t bytes = kPair ? 2 * (P.a_bytes + half_rows * 128) : P.a_bytes + (P.b_res ? 0 : P.block_n * 128);
+        const bool b_resident = P.b_res != 0;
         for (int32_t tap = 0; tap < P.num_taps; ++tap) {
           const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
                         o3 = P.tap_off[tap][3];
           const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
           for (int32_t cc = 0; cc < P.cchunks; ++cc) {
-            uint8_t* sa = ring + stage * P.stage_bytes;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_addr(empty_a, phase ^ 1);
             if (elect_one_sync()) {
               if (kPair) {
-                if (sch.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                tma_load_5d_2cta(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
-                tma_load_5d_2cta(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64,
-                                 nt * P.block_n + sch.rank * half_rows, 0, 0, 0);
+                if (sch.rank == 0) mbar_arrive_expect_tx_addr(full_a, bytes);
+                tma_load_5d_2cta(sa, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                tma_load_5d_2cta(sa + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n + sch.rank * half_rows, 0, 0, 0);
               } else {
-                mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                tma_load_5d(sa, &tma_a, &full_bar[stage], ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
-                if (!P.b_res)
-                  tma_load_5d(sa + P.a_alloc, &tma_b, &full_bar[stage], bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+                mbar_arrive_expect_tx_addr(full_a, bytes);
+                tma_load_5d(sa, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                if (!b_resident) tma_load_5d(sa + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
               }
             }
             __syncwarp();
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
+            if (++stage == nstages) { stage = 0; phase ^= 1; sa = ring0; full_a = full0; empty_a = empty0; }
+            else { sa += stage_bytes; full_a += 8; empty_a += 8; }
           }
         }
       } else {
@@ -693,7 +696,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t a_boxes = min((P.a_ch - mt * 128 + 63) / 64, 2);
         const int32_t peer_boxes = min((P.a_ch - (mt ^ 1) * 128 + 63) / 64, 2);
         for (int32_t kb = kb0; kb < kb1; ++kb) {
-          uint8_t* sa = ring + stage * P.stage_bytes;
           const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
                         a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
           const int32_t b0 = coord(d, P.b_base, P.b_step, 0) + o0, b1 = coord(d, P.b_base, P.b_step, 1) + o1,
@@ -705,36 +707,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
               if (++d.t[2] == P.t_count[2]) { d.t[2] = 0; ++d.t[3]; }
             }
           }
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_addr(empty_a, phase ^ 1);
           if (elect_one_sync()) {
             // a box that lies entirely beyond the tensor's channels is not fetched: its rows of the tile are >= m_valid
             // and never stored, whatever the shared memory holds
             if (kPair) {
               // both CTAs' copies are counted on the leader's barrier; this CTA holds its own M tile and half of the X boxes
               const int32_t hb = nb >> 1;
-              if (sch.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + peer_boxes + nb) * kBoxBytesMN);
+              if (sch.rank == 0) mbar_arrive_expect_tx_addr(full_a, (a_boxes + peer_boxes + nb) * kBoxBytesMN);
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                if (j < a_boxes) tma_load_5d_2cta(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
+                if (j < a_boxes) tma_load_5d_2cta(sa + j * kBoxBytesMN, &tma_a, full_a, mt * 128 + j * 64, a0, a1, a2, a3);
               for (int j = 0; j < hb; ++j) {
                 const int32_t jj = static_cast<int>(sch.rank) * hb + j, bx = bdim ? box0 + jj : 0;
-                tma_load_5d_2cta(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + jj * bcs, b0 + e0 * bx,
-                                 b1 + e1 * bx, b2 + e2 * bx, b3 + e3 * bx);
+                tma_load_5d_2cta(sa + a_alloc + j * kBoxBytesMN, &tma_b, full_a, bc0 + jj * bcs, b0 + e0 * bx, b1 + e1 * bx,
+                                 b2 + e2 * bx, b3 + e3 * bx);
               }
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
+              mbar_arrive_expect_tx_addr(full_a, a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, &full_bar[stage], mt * 128 + j * 64, a0, a1, a2, a3);
+                if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, full_a, mt * 128 + j * 64, a0, a1, a2, a3);
               for (int j = 0; j < nb; ++j) {
                 const int32_t bx = bdim ? box0 + j : 0;
-                tma_load_5d(sa + P.a_alloc + j * kBoxBytesMN, &tma_b, &full_bar[stage], bc0 + j * bcs, b0 + e0 * bx, b1 + e1 * bx,
-                            b2 + e2 * bx, b3 + e3 * bx);
+                tma_load_5d(sa + a_alloc + j * kBoxBytesMN, &tma_b, full_a, bc0 + j * bcs, b0 + e0 * bx, b1 + e1 * bx, b2 + e2 * bx,
+                            b3 + e3 * bx);
               }
             }
           }
           __syncwarp();
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; sa = ring0; full_a = full0; empty_a = empty0; }
+          else { sa += stage_bytes; full_a += 8; empty_a += 8; }
         }
       }
     }
@@ -750,6 +753,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
     int32_t stage = 0;
     uint32_t phase = 0, jt = 0;   // jt: tiles this warp has issued
+    // descriptors and barrier addresses of ring stage 0; the loop steps them (the 14-bit address field cannot overflow:
+    // shared addresses are below 256 KB)
+    const uint32_t ring_a = smem_u32(ring);
+    const uint64_t da0 = P.a_window ? make_smem_desc_noswizzle(ring_a, 16, 128) : make_smem_desc(ring_a, lbo, sbo);
+    const uint64_t db0 = make_smem_desc(P.b_res ? smem_u32(smem) : ring_a + P.a_alloc, lbo, sbo);
+    const uint32_t dstage = static_cast<uint32_t>(P.stage_bytes) >> 4, dres = static_cast<uint32_t>(P.b_res) >> 4;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const bool b_res = P.b_res != 0;
+    uint64_t da = da0, db_ring = db0;
+    uint32_t full_a = full0, empty_a = empty0;
     if (P.b_res && sch.begin + pipe < sch.end) mbar_wait(bres_bar, 0);
     const int32_t mma_end = (kPair && sch.rank != 0) ? sch.begin : sch.end;
     for (int32_t tile = sch.begin + pipe; tile < mma_end; tile += tile_step) {
@@ -769,29 +782,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + group * kAccCols + sub * 128u;
+      // windowed A (da0 without swizzle): pixel rows of 16 B; row m of K chunk j (8 channels of window pixel j) sits at
+      // (m + j) * 16, so the core matrices overlap: 16 B between the two K chunks of one MMA, 128 B between 8-row groups
+      uint64_t db_res = db0;   // resident B: K chunk kc of the tile
       for (int32_t kc = 0; kc < nk; ++kc) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_addr(full_a, phase);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(ring + stage * P.stage_bytes);
-        // windowed A: pixel rows of 16 B; row m of K chunk j (8 channels of window pixel j) sits at (m + j) * 16, so the
-        // core matrices overlap: 16 B between the two K chunks of one MMA, 128 B between 8-row groups
-        const uint64_t da = P.a_window ? make_smem_desc_noswizzle(sa, 16, 128) : make_smem_desc(sa, lbo, sbo);
-        const uint64_t db = make_smem_desc(P.b_res ? smem_u32(smem) + kc * P.b_res : sa + P.a_alloc, lbo, sbo);
+        const uint64_t db = b_res ? db_res : db_ring;
         if (elect_one_sync()) {
           if (kPair) {
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k)
               umma_bf16_2cta(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
-            tcgen05_commit_2cta(&empty_bar[stage], pair_mask);   // frees the stage in both CTAs
+            tcgen05_commit_2cta_addr(empty_a, pair_mask);   // frees the stage in both CTAs
           } else {
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k)
               umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
-            tcgen05_commit(&empty_bar[stage]);
+            tcgen05_commit_addr(empty_a);
           }
         }
         __syncwarp();
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        db_res += dres;
+        if (++stage == nstages) {
+          stage = 0; phase ^= 1;
+          da = da0; db_ring = db0; full_a = full0; empty_a = empty0;
+        } else {
+          da += dstage; db_ring += dstage; full_a += 8; empty_a += 8;
+        }
       }
       if (elect_one_sync()) {
         if (kPair) tcgen05_commit_2cta(&tmem_full[acc], pair_mask);   // both CTAs' epilogues drain their half of the rows
