@@ -75,3 +75,25 @@ def test_unsupported_variants_and_cpu_fail_loudly():
         with pytest.raises(RuntimeError):
             m = WSGANEmbModel()
             m.initialize(default_options(gpu_ids=[0]))
+
+
+def test_fused_adam_is_a_torch_adam_and_has_no_cpu_path():
+    """pcgan_b200.optim.FusedAdam keeps torch.optim.Adam's constructor / param_groups / schedulers (the reference builds
+    its optimizers at models/wsgan_emb_model.py:153-163) and refuses what it does not implement instead of falling back."""
+    import torch
+    from pcgan_b200.optim import FusedAdam
+    p = [torch.nn.Parameter(torch.zeros(4, 3))]
+    o = FusedAdam(p, lr=2e-4, betas=(0.5, 0.999))
+    assert isinstance(o, torch.optim.Adam) and o.param_groups[0]["lr"] == 2e-4 and o.param_groups[0]["betas"] == (0.5, 0.999)
+    sched = torch.optim.lr_scheduler.LambdaLR(o, lr_lambda=lambda e: 0.5)
+    assert o.param_groups[0]["lr"] == pytest.approx(1e-4)
+    del sched
+    with pytest.raises(NotImplementedError):
+        FusedAdam(p, weight_decay=1e-2)
+    with pytest.raises(NotImplementedError):
+        FusedAdam(p, amsgrad=True)
+    p[0].grad = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        o.step()
+    assert o.state_dict()["state"] == {}          # nothing was allocated or stepped on the CPU
+
