@@ -123,7 +123,7 @@ class IgemmSpec:
     note: str = ""
     shift_taps: int = 0        # shift-sum epilogue: horizontal taps carried in N (include/pcgan_kernels.h)
     shift_cpad: int = 0
-    pair: int = 0              # CTA pairs sharing the B operand through TMA multicast (include/pcgan_kernels.h)
+    pair: int = 0              # CTA pairs issuing one tcgen05.mma.cta_group::2 of M = 256 (include/pcgan_kernels.h)
     a_window: int = 0          # 8: A is the plain 8-channel tensor read through an overlapping descriptor (pcgan_kernels.h)
     wg_box_dim: int = 0        # WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N)
     swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
@@ -185,7 +185,7 @@ def _block_n(cout):
     return best[1]
 
 
-PAIRING = True   # CTA pairs with a multicast B operand where it pays (large N tiles, enough M tiles)
+PAIRING = True   # CTA pairs (one cta_group::2 MMA for two M tiles) where it pays: full-width N tiles, enough M tiles
 TAPBOX = True    # packed-window weight gradients: the filter rows ride in N, the 64-channel operand is read once per N tile
 WINDOW = True    # 8-channel inputs: windowed A operand (pcgan_igemm_desc.a_window) instead of overlapping-stride TMA boxes
 
