@@ -14,6 +14,10 @@ from pcgan_b200 import conv as CV
 from pcgan_b200 import ops
 from pcgan_b200.plan import Geom, OutMap
 from tests.test_plan_cpu import DGRAD_CASES, FWD_CASES, WGRAD_CASES, rel
+from tests.test_plan_sweep_cpu import DGRAD_SWEEP, FWD_SWEEP, WGRAD_SWEEP
+
+# the benchmark's shapes plus the seeded sweep of ragged geometries (tests/test_plan_sweep_cpu.py)
+FWD_ALL, DGRAD_ALL, WGRAD_ALL = FWD_CASES + FWD_SWEEP, DGRAD_CASES + DGRAD_SWEEP, WGRAD_CASES + WGRAD_SWEEP
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -40,7 +44,7 @@ def run_plans(plans, a_flat, w, out, bias=None, stats=None):
     return out
 
 
-@pytest.mark.parametrize("case", FWD_CASES, ids=[c[0] for c in FWD_CASES])
+@pytest.mark.parametrize("case", FWD_ALL, ids=[c[0] for c in FWD_ALL])
 def test_conv_forward(case):
     _, cin, cbuf, cout, k, stride, cp, halo, xpad, H, W, N = case
     torch.manual_seed(0)
@@ -100,7 +104,7 @@ def test_conv_transpose_forward():
     assert rel(stats.cpu()[..., 0], ref.sum((2, 3))) < 1e-4
 
 
-@pytest.mark.parametrize("case", DGRAD_CASES, ids=[c[0] for c in DGRAD_CASES])
+@pytest.mark.parametrize("case", DGRAD_ALL, ids=[c[0] for c in DGRAD_ALL])
 def test_conv_dgrad(case):
     _, cin, cout, cobuf, k, stride, cp, xpad, full, H, N, dypad = case
     torch.manual_seed(3)
@@ -150,7 +154,7 @@ def _wgrad(sp, wm, m_flat, n_flat, numel):
     return dw.cpu()
 
 
-@pytest.mark.parametrize("case", WGRAD_CASES, ids=[c[0] for c in WGRAD_CASES])
+@pytest.mark.parametrize("case", WGRAD_ALL, ids=[c[0] for c in WGRAD_ALL])
 def test_conv_wgrad(case):
     _, cin, cbuf, cout, cobuf, k, stride, cp, halo, xpad, H, N, dypad = case
     torch.manual_seed(5)
