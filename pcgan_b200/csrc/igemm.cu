@@ -9,15 +9,17 @@
 // Everything that distinguishes one convolution from another (padding mode, stride,
 // transposed phases, reflect halos, packed stems) is data in pcgan_igemm_desc.
 //
-// Warp roles (384 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4-7 and 8-11 = two epilogue groups, one per TMEM
-// accumulator stage (TMEM lane quarter = warp % 4).
-// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
-// (MMA <-> epilogue), persistent tile loop with a static stride schedule. With
-// desc.pair the grid runs as clusters of two CTAs on adjacent M tiles of the same N
-// tile: each CTA loads its own A tile and half of the B tile, the leader issues one
-// tcgen05.mma.cta_group::2 of M = 256 per K step (operand reads from shared memory
-// are halved per SM), and each CTA drains its own 128 accumulator rows.
+// 384 threads, 1 CTA / SM.  Warps 4-7 and 8-11 are two epilogue groups (TMEM lane quarter = warp % 4); warp 2
+// allocates TMEM.  Two instantiations of the kernel:
+//   igemm_kernel<true>  (desc.pair, full-width N tiles): clusters of two CTAs on adjacent M tiles of the same N tile.
+//     Warp 0 of each CTA loads its own A tile and half of the B tile, warp 1 of the leader issues one
+//     tcgen05.mma.cta_group::2 of M = 256 per K step for both (operand traffic through shared memory is halved per
+//     SM), tiles alternate between two 256-column accumulators, each CTA's epilogue groups drain their own 128 rows.
+//   igemm_kernel<false> (everything narrower): the single-thread issue loops, not the tensor pipe, bound small tiles,
+//     so the CTA runs two independent pipelines: warps 0 -> 1 -> group 0 on its even tiles, warps 3 -> 2 -> group 1 on
+//     its odd tiles, each with half of the ring, its own barriers and (N <= 128) a double-buffered accumulator.
+// Barriers: ring full / empty (TMA <-> MMA), accumulator full / empty (MMA <-> epilogue); persistent tile loop over a
+// static contiguous schedule.
 #include <cuda.h>
 #include <mutex>
 #include <stdarg.h>
@@ -32,10 +34,10 @@ namespace pcgan {
 static constexpr int kMaxStages = 16;
 static constexpr int kDataBytes = 192 * 1024;      // operand ring: num_stages x (A + B) chosen per plan
 static constexpr int kBoxBytesMN = 64 * 128;       // one MN-major box: 64 K-rows x 128 B
-static constexpr int kTmemCols = 512;              // 2 accumulator stages x 256 fp32 columns
+static constexpr int kTmemCols = 512;              // 2 accumulators x 256 fp32 columns (or 4 x 128: DevParams::acc_sub)
 static constexpr int kAccCols = 256;
-static constexpr int kNumThreads = 384;            // warps 0-3: TMA / MMA / TMEM alloc / idle; 4-7 and 8-11: two epilogue groups
-static constexpr int kEpiGroups = 2;               // group g drains TMEM stage g (every other tile of the CTA)
+static constexpr int kNumThreads = 384;            // warps 0-3: TMA, MMA, TMEM alloc (+ MMA 2), TMA 2; 4-7 and 8-11: two epilogue groups
+static constexpr int kEpiGroups = 2;               // group g drains accumulator g (every other tile of the CTA)
 // tail after the ring: barriers (512 B) | bias [2 groups][256] f32 | per-warp scratch [8 warps][32][17] f32: the
 // statistics partial sums [2][256] of each epilogue warp, or the row-exchange tile of the shift-sum epilogue
 static constexpr int kTailBias = 512;
