@@ -518,8 +518,11 @@ def _pix_box64(w, h):
     return bw, bh
 
 
-def _ksplit_for(total_kb, out_tiles, sms=148):
-    ks = max(1, min(total_kb, sms // max(out_tiles, 1)))
+def _ksplit_for(total_kb, out_tiles, paired=False, sms=148):
+    """Split of the pixel loop: one work item per SM for paired plans (a pair shares one MMA stream), two per SM
+    otherwise, so that both pipelines of an unpaired CTA have a tile."""
+    slots = sms if paired else 2 * sms
+    ks = max(1, min(total_kb, slots // max(out_tiles, 1)))
     # keep at least 8 K blocks per split so the pipeline fills
     while ks > 1 and total_kb // ks < 8:
         ks -= 1
@@ -581,9 +584,9 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
         s.ldo = kh * 64
         s.b_rows, s.b_k = m_ch, s.ldo
         total_kb = tx * ty * tn
-        s.ksplit = _ksplit_for(total_kb, s.m_tiles * s.n_tiles)
-        s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n
         s.pair = int(PAIRING and s.m_tiles % 2 == 0)
+        s.ksplit = _ksplit_for(total_kb, s.m_tiles * s.n_tiles, bool(s.pair))
+        s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n
         return s
     if n_stride == 1:
         s.b_dims = [d0, Wp, Hp, N, 1]
@@ -622,9 +625,9 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     s.ldo = nk * ncols
     s.b_rows, s.b_k = m_ch, s.ldo
     total_kb = tx * ty * tn
-    s.ksplit = _ksplit_for(total_kb, len(taps) * s.m_tiles * s.n_tiles)
-    s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
     s.pair = int(PAIRING and s.m_tiles % 2 == 0 and (s.block_n // 64) % 2 == 0)
+    s.ksplit = _ksplit_for(total_kb, len(taps) * s.m_tiles * s.n_tiles, bool(s.pair))
+    s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
     return s
 
 
