@@ -9,6 +9,7 @@ from oracle import igemm_emulator as emu
 from oracle.layout import bf16_round, from_padded_nhwc, to_padded_nhwc
 from pcgan_b200 import _lib as L
 from pcgan_b200 import conv as CV
+from pcgan_b200 import ops
 from pcgan_b200.plan import Geom, OutMap
 
 
@@ -22,7 +23,7 @@ def pack_weights(w, wmap, rows, k):
 def run_fwd(plans, xflat, w, out_numel, bias=None, stats=None, groups=1):
     out = torch.zeros(out_numel)
     for sp, wm in plans:
-        sp.to_desc()  # exercises the ctypes conversion
+        ops.Igemm(sp)  # ctypes conversion + the C side's validation of the descriptor (pcgan_igemm_plan_create, host only)
         b = pack_weights(w, wm, sp.b_rows, sp.b_k)
         view = out[sp.out_elem_offset:]
         emu.run_kmajor(sp, xflat[sp.a_elem_offset:], b, view, bias=bias, stats=stats)
@@ -197,7 +198,7 @@ def test_conv_wgrad_plan(case):
     dy = torch.randn(N, cout, ho, ho)
     xg, dyg = Geom(N, H, H, cbuf, xpad), Geom(N, ho, ho, cobuf, dypad)
     sp, wm = CV.conv_wgrad_plan((cout, cin, k, k), dyg, xg, stride, cp)
-    sp.to_desc()
+    ops.Igemm(sp)   # the C side accepts the descriptor
     packed = torch.zeros(sp.b_rows * sp.b_k)
     dyb, xb = to_padded_nhwc(dy, dypad, "zero", cobuf), to_padded_nhwc(x, xpad, halo, cbuf)
     if sp.swap_operands:   # few output channels: activations on the M side, dY (packed window) on the N side
@@ -228,3 +229,43 @@ def test_conv_transpose_wgrad_plan():
     wref = torch.zeros(cin, cout, 3, 3, requires_grad=True)
     F.conv_transpose2d(bf16_round(x), wref, stride=2, padding=1, output_padding=1).backward(bf16_round(dy))
     assert rel(dw.view(cin, cout, 3, 3), wref.grad) < 1e-5
+
+
+def test_plan_create_rejects_inconsistent_descriptors():
+    """pcgan_igemm_plan_create validates on the host (no GPU): a descriptor the kernel cannot run is refused with a
+    message, never launched."""
+    from pcgan_b200._lib import PcganError
+
+    def stem():
+        xg, og = Geom(2, 6, 64, 8, 3), Geom(2, 6, 64, 64, 1)
+        return CV.conv_fwd_plans((64, 4, 7, 7), xg, 1, 3, OutMap.nhwc(og))[0][0]
+
+    def res():
+        xg, og = Geom(2, 16, 16, 256, 1), Geom(2, 16, 16, 256, 0)
+        return CV.conv_fwd_plans((256, 256, 3, 3), xg, 1, 1, OutMap.nhwc(og))[0][0]
+
+    sp = stem()
+    assert sp.a_window == 8 and sp.pair == 0
+    ops.Igemm(sp)
+    for field, value in (("pair", 1), ("cchunks", 2), ("block_n", 20), ("ksplit", 2), ("a_window", 4), ("wg_box_dim", 2), ("n_valid", 0)):
+        bad = stem()
+        setattr(bad, field, value)
+        with pytest.raises(PcganError):
+            ops.Igemm(bad)
+    sp = res()
+    assert sp.pair == 1 and sp.block_n == 256
+    ops.Igemm(sp)
+    for field, value in (("pair", 2), ("shift_taps", 3), ("stats_dim", 7)):
+        bad = res()
+        setattr(bad, field, value)
+        if field == "stats_dim":
+            bad.stats_mode = L.STATS_ON
+        with pytest.raises(PcganError):
+            ops.Igemm(bad)
+    sp, _ = CV.conv_wgrad_plan((64, 4, 7, 7), Geom(2, 16, 16, 64, 0), Geom(2, 16, 16, 8, 3), 1, 3)
+    assert sp.wg_box_dim == 2 and sp.num_taps == 1
+    ops.Igemm(sp)
+    sp.wg_box_dim = 5
+    with pytest.raises(PcganError):
+        ops.Igemm(sp)
+
