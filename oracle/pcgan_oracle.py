@@ -359,7 +359,7 @@ class WSGANEmbOracle:
     def __init__(self, sd_g, sd_d, sd_e, *, lr=2e-4, beta1=0.5, lambda_z=1.0, lambda_a=0.5, lambda_l1=0.0,
                  lambda_a_gan=0.0, fine_size_e=224, relabel_d=(0, 1, 0), emb_mean=0.0, emb_std=1.0, n_blocks=9,
                  n_layers_d=3, detach_fake_b=False, bayesian=False, noisy=False, noisy_var_type="", bnn_T=10,
-                 noisy_d=True, noisy_rec=True, dropout=False, drop_masks=None, eps_queue=None):
+                 noisy_d=True, noisy_rec=True, dropout=False, drop_masks=None, eps_queue=None, use_real_a=False):
         """bayesian / noisy / noisy_var_type / bnn_T / noisy_D / noisy_rec: the encoder modes of forward() (:218-240)
         and backward_G (:408-430).  Randomness is injected, never drawn: `drop_masks` is a list of Dropout2d masks
         [N, C] consumed in module order (dropout=True places them where the reference has nn.Dropout2d), `eps_queue`
@@ -378,6 +378,7 @@ class WSGANEmbOracle:
         self.fe, self.relabel = fine_size_e, list(relabel_d)
         self.mean, self.std = emb_mean, emb_std
         self.nb, self.nld, self.detach_fake_b = n_blocks, n_layers_d, detach_fake_b
+        self.use_real_a = use_real_a     # --use_real_A (:309-322): D's real pairs are built from real_A
         self.losses = {}
 
     def _drop(self, t):
@@ -496,9 +497,10 @@ class WSGANEmbOracle:
         self.opt_d.zero_grad()
         L = {}
         L["D_fake"] = gan_loss(discriminator_forward(self.d, self.fake_b.detach(), self.cond_b, self.nld), False)
-        L["D_real_right"] = gan_loss(discriminator_forward(self.d, self.real_b, self.emb_b, self.nld), True)
+        img, right, wrong = (self.real_a, self.emb_a, self.emb_b) if self.use_real_a else (self.real_b, self.emb_b, self.emb_a)
+        L["D_real_right"] = gan_loss(discriminator_forward(self.d, img, right, self.nld), True)
         target = [self.relabel[int(l)] for l in label]
-        L["D_real_wrong"] = gan_loss(discriminator_forward(self.d, self.real_b, self.emb_a, self.nld), target)
+        L["D_real_wrong"] = gan_loss(discriminator_forward(self.d, img, wrong, self.nld), target)
         total = (L["D_fake"] + (L["D_real_right"] + L["D_real_wrong"]) * 0.5) * 0.5
         total.backward()
         self.opt_d.step()

@@ -280,7 +280,49 @@ def golden_step_bayesian():
     print("bayesian step:", losses, len(masks), "masks", len(eps), "eps")
 
 
+def golden_step_variants():
+    """One WSGANEmbModel.optimize_parameters() with the non-default branches of the step switched on:
+    --lambda_A_GAN 0.5 (:340-342, 380-382) --lambda_L1 0.3 (:343-347, 384-388) --detach_fake_B (:256-259) --use_real_A
+    (:309-322), at a small size (64 x 64, fineSize_E 64, resnet_6blocks)."""
+    from models import networks
+    tmp = tempfile.mkdtemp()
+    e0 = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7, gpu_ids=[])
+    pth = os.path.join(tmp, "e.pth")
+    torch.save(e0.state_dict(), pth)
+    argv = sys.argv
+    sys.argv = ["x", "--model", "wsgan_emb", "--gpu_ids", "-1", "--which_model_netG", "resnet_6blocks", "--n_layers_D", "3",
+                "--batchSize", "2", "--lambda_IP", "0", "--pretrained_model_path_E", pth, "--sourcefile_A", pth, "--dataroot", tmp,
+                "--embedding_bins", "[-2,-1,0,1,2]", "--checkpoints_dir", tmp, "--name", "golden_v", "--fineSize", "64", "--loadSize", "64",
+                "--fineSize_E", "64", "--lambda_A_GAN", "0.5", "--lambda_L1", "0.3", "--detach_fake_B", "--use_real_A"]
+    try:
+        from options.train_options import TrainOptions
+        from models import create_model
+        opt = TrainOptions().parse()
+        model = create_model(opt)
+        model.setup(opt)
+    finally:
+        sys.argv = argv
+    O.fill_state_dict_(model.netG.state_dict(), 51)
+    O.fill_state_dict_(model.netD.state_dict(), 52)
+    O.fill_state_dict_(model.netE.state_dict(), 53)
+    a, b, label = O.synthetic_batch(2, 64, 600)
+    model.set_input({"A": a, "B": b, "label": label, "A_paths": ["a"] * 2, "B_paths": ["b"] * 2})
+    model.optimize_parameters()
+    losses = {k: float(v) for k, v in model.get_current_losses().items()}
+    torch.save({"seeds": (51, 52, 53), "batch_seed": 600, "losses": losses,
+                "flags": {"lambda_A_GAN": 0.5, "lambda_L1": 0.3, "detach_fake_B": True, "use_real_A": True},
+                "fake_b_sub": sub(model.fake_B.detach(), 4),
+                "g_w_after": model.netG.state_dict()["model.10.conv_block.1.weight"][:4, :4].clone(),
+                "g_stem_w_after": model.netG.state_dict()["model.1.weight"][:4].clone(),
+                "d_w_after": model.netD.state_dict()["model.2.weight"][:4, :4].clone()},
+               os.path.join(HERE, "step_variants.pt"))
+    print("variant step:", losses)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        golden_step_variants()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "new":     # only the fixtures added later (the others are unchanged)
         golden_encoder_dropout()
         golden_siamese_step()
@@ -294,6 +336,7 @@ if __name__ == "__main__":
     golden_encoder_dropout()
     golden_siamese_step()
     golden_step_bayesian()
+    golden_step_variants()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -177,3 +177,26 @@ def test_bayesian_noisy_step_matches_reference():
     assert close(m.y_b, fx["y_b"], 1e-3)
     assert close(m.fake_b.detach()[..., ::4, ::4], fx["fake_b_sub"], 1e-3)
     assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["g_w_after"], 1e-3)
+
+
+def test_variant_flags_step_matches_reference():
+    """The non-default branches of the step — --lambda_A_GAN, --lambda_L1, --detach_fake_B, --use_real_A
+    (models/wsgan_emb_model.py:256-259, 309-322, 340-347, 380-388) — against the reference's own optimize_parameters."""
+    fx = load("step_variants.pt")
+    torch.set_num_threads(8)
+    sg, sd_, se = fx["seeds"]
+    fl = fx["flags"]
+    m = O.WSGANEmbOracle(O.make_state_dict(O.generator_keys(n_blocks=6), sg, requires_grad=True),
+                         O.make_state_dict(O.discriminator_keys(), sd_, requires_grad=True),
+                         O.make_state_dict(O.encoder_keys(), se), n_blocks=6, fine_size_e=64,
+                         lambda_a_gan=fl["lambda_A_GAN"], lambda_l1=fl["lambda_L1"], detach_fake_b=fl["detach_fake_B"],
+                         use_real_a=fl["use_real_A"])
+    a, b, label = O.synthetic_batch(2, 64, fx["batch_seed"])
+    got = m.optimize_parameters(a, b, label)
+    for k in ("G_GAN", "G_GAN_cycle", "G_L1", "G_cycle", "z_rec", "D_real_right", "D_real_wrong", "D_fake"):
+        assert abs(got[k] - fx["losses"][k]) <= 2e-4 * abs(fx["losses"][k]) + 1e-7, (k, got[k], fx["losses"][k])
+    assert close(m.fake_b.detach()[..., ::4, ::4], fx["fake_b_sub"], 1e-4)
+    assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["g_w_after"], 1e-4)
+    assert close(m.g["model.1.weight"][:4], fx["g_stem_w_after"], 1e-4)
+    assert close(m.d["model.2.weight"][:4, :4], fx["d_w_after"], 1e-4)
+

@@ -55,6 +55,39 @@ def test_single_step_losses():
     assert float((wg - wr).abs().max()) < 4.1e-4   # at most two Adam steps of lr 2e-4 apart
 
 
+def test_variant_flags_step_losses():
+    """The non-default branches of the step (--lambda_A_GAN, --lambda_L1, --detach_fake_B, --use_real_A:
+    models/wsgan_emb_model.py:256-259, 309-322, 340-347, 380-388) against the oracle, whose same branches are pinned to the
+    reference by tests/golden/step_variants.pt."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = 4
+    flags = dict(lambda_A_GAN=0.5, lambda_L1=0.3, detach_fake_B=True, use_real_A=True)
+    sds = [O.make_state_dict(k, s, device=DEV, requires_grad=rg) for k, s, rg in
+           ((O.generator_keys(), 51, True), (O.discriminator_keys(), 52, True), (O.encoder_keys(), 53, False))]
+    model = WSGANEmbModel()
+    opt = default_options(batchSize=B, gpu_ids=[0], **flags)
+    model.initialize(opt)
+    model.setup(opt)
+    for net, sd in zip((model.netG, model.netD, model.netE), sds):
+        net.module.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
+    oracle = O.WSGANEmbOracle(*sds, lambda_a_gan=0.5, lambda_l1=0.3, detach_fake_b=True, use_real_a=True)
+    a, b, label = O.synthetic_batch(B, 128, 600, device=DEV)
+    model.set_input({"A": a, "B": b, "label": label})
+    model.optimize_parameters()
+    got = model.get_current_losses()
+    want = oracle.optimize_parameters(a, b, label)
+    keys = KEYS + ("G_GAN_cycle", "G_L1")
+    print("variant step losses:", {k: "%.5f/%.5f" % (got[k], want[k]) for k in keys})
+    for k in keys:
+        tol = 0.6 if k == "z_rec" else (0.05 if k == "G_GAN_cycle" else 0.03)     # z_rec: see test_single_step_losses
+        assert abs(got[k] - want[k]) <= tol * abs(want[k]) + 1e-5, (k, got[k], want[k])
+    # detach_fake_B: the cycle terms reach the generator only through its second pass, yet every layer still moved
+    wg = model.netG.module.model[1].weight.detach()
+    wr = oracle.g["model.1.weight"].detach()
+    assert float((wg - wr).abs().max()) < 4.1e-4
+
+
 @pytest.mark.skipif(os.environ.get("PCGAN_SKIP_TRAJ") == "1", reason="trajectory test disabled")
 def test_loss_trajectories_200_steps():
     steps, B = 200, 16
