@@ -8,6 +8,7 @@ One step = WSGANEmbModel.optimize_parameters() (models/wsgan_emb_model.py:478-48
 + data-gradient x1, the GAN / cycle / embedding-reconstruction losses and both Adam steps.  Prints ONE JSON line.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -171,8 +172,9 @@ def main():
     torch.manual_seed(1234 + rank)
     opt = default_options(batchSize=B, gpu_ids=[local], fineSize=S, loadSize=S, cuda_graph=not args.no_graph)
     model = WSGANEmbModel()
-    model.initialize(opt)
-    model.setup(opt)
+    with contextlib.redirect_stdout(sys.stderr):   # the factories print like the reference's do; stdout carries only the JSON line
+        model.initialize(opt)
+        model.setup(opt)
     if world > 1:   # identical replicas: broadcast rank 0's random init
         for net in (model.netG, model.netD, model.netE):
             for t in list(net.parameters()) + list(net.buffers()):
