@@ -130,6 +130,8 @@ class FusedAdam(torch.optim.Adam):
         return sd
 
     def load_state_dict(self, state_dict):
+        """Loaded moments are copied into fresh arenas at the next step(); a CUDA graph captured before the load still
+        points at the old ones and must be captured again (the reference never saves optimizer state: base_model.py:96-107)."""
         super().load_state_dict(state_dict)
         self._groups = {}     # re-bind from the loaded tensors at the next step
 
