@@ -55,6 +55,9 @@ struct DevParams {
   int32_t b_res;       // KMAJOR, > 0: the whole B operand stays resident in front of the ring, b_res bytes per K chunk
   int32_t ring_off;    // byte offset of the ring behind the resident B operand
   int32_t wg_box_dim;  // WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N), 0 = channels
+  int32_t split_prod;  // paired WGRAD: warp 3 issues the X boxes, warp 0 the dY boxes
+  int32_t kps;         // KMAJOR, unpaired: K chunks per ring stage (one barrier round trip and one commit for all of them)
+  int32_t sub_bytes;   //   bytes of one chunk's slot inside a stage (stage_bytes = kps * sub_bytes)
   int32_t acc_sub;     // 1 (dual, block_n <= 128): each pipeline double-buffers its accumulator in two 128-column halves
   int32_t dual;        // 1: two independent producer -> MMA -> epilogue pipelines (even / odd tiles of the CTA), each with
                        //    num_stages stages of the ring and one TMEM accumulator
@@ -616,7 +619,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   // issue loops, not the tensor pipe, bound tiles with little work per K chunk, so the CTA's even tiles run through
   // warps 0 -> 1 -> epilogue group 0 and its odd tiles through warps 3 -> 2 -> epilogue group 1, each pipeline with its
   // own half of the ring, its own barriers and its own accumulator.
-  const bool producer_warp = warp == 0 || (warp == 3 && P.dual);
+  // paired weight gradients: the MMA warp waits for TMA while the ring never fills (one warp issues four boxes per K chunk
+  // and steps the pixel-block digits), so the otherwise idle warp 3 issues the X boxes and warp 0 the dY boxes
+  const bool split_producer = kPair && wgrad && P.split_prod;
+  const bool producer_warp = warp == 0 || (warp == 3 && (P.dual || split_producer));
   const bool mma_warp = warp == 1 || (warp == 2 && P.dual);
   const int32_t pipe = (P.dual && (warp == 2 || warp == 3)) ? 1 : 0;
   const int32_t tile_step = P.dual ? 2 : 1;
@@ -656,26 +662,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         // paired: both CTAs' copies (own A tile + own half of B each) are counted on the leader's barrier
         const uint32_t bytes = kPair ? 2 * (P.a_bytes + half_rows * 128) : P.a_bytes + (P.b_res ? 0 : P.block_n * 128);
         const bool b_resident = P.b_res != 0;
+        const int32_t kps = P.kps;                      // 1 when paired
+        const uint32_t sub_bytes = static_cast<uint32_t>(P.sub_bytes);
+        int32_t kc = 0, slot = 0;                       // K chunk of the tile, its slot in the current stage
         for (int32_t tap = 0; tap < P.num_taps; ++tap) {
           const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2],
                         o3 = P.tap_off[tap][3];
           const int32_t ac0 = P.tap_c0[tap], bk0 = P.tap_bk[tap];
           for (int32_t cc = 0; cc < P.cchunks; ++cc) {
-            mbar_wait_addr(empty_a, phase ^ 1);
+            // a stage holds kps consecutive K chunks of the tile (the last stage of a tile may hold fewer): one wait and
+            // one expectation for all of them
+            if (slot == 0) mbar_wait_addr(empty_a, phase ^ 1);
             if (elect_one_sync()) {
               if (kPair) {
                 if (sch.rank == 0) mbar_arrive_expect_tx_addr(full_a, bytes);
                 tma_load_5d_2cta(sa, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
                 tma_load_5d_2cta(sa + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n + sch.rank * half_rows, 0, 0, 0);
               } else {
-                mbar_arrive_expect_tx_addr(full_a, bytes);
-                tma_load_5d(sa, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
-                if (!b_resident) tma_load_5d(sa + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+                if (slot == 0) mbar_arrive_expect_tx_addr(full_a, bytes * static_cast<uint32_t>(min(kps, k_chunks_fwd - kc)));
+                const uint32_t dst = sa + static_cast<uint32_t>(slot) * sub_bytes;
+                tma_load_5d(dst, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                if (!b_resident) tma_load_5d(dst + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
               }
             }
             __syncwarp();
-            if (++stage == nstages) { stage = 0; phase ^= 1; sa = ring0; full_a = full0; empty_a = empty0; }
-            else { sa += stage_bytes; full_a += 8; empty_a += 8; }
+            ++kc;
+            if (++slot == kps || kc == k_chunks_fwd) {
+              slot = 0;
+              if (++stage == nstages) { stage = 0; phase ^= 1; sa = ring0; full_a = full0; empty_a = empty0; }
+              else { sa += stage_bytes; full_a += 8; empty_a += 8; }
+            }
           }
         }
       } else {
@@ -714,12 +730,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             // a box that lies entirely beyond the tensor's channels is not fetched: its rows of the tile are >= m_valid
             // and never stored, whatever the shared memory holds
             if (kPair) {
-              // both CTAs' copies are counted on the leader's barrier; this CTA holds its own M tile and half of the X boxes
-              const int32_t hb = nb >> 1;
-              if (sch.rank == 0) mbar_arrive_expect_tx_addr(full_a, (a_boxes + peer_boxes + nb) * kBoxBytesMN);
+              // both CTAs' copies are counted on the leader's barrier; this CTA holds its own M tile and half of the X boxes.
+              // warp 0: the expectation (all bytes of both CTAs and both warps) and the dY boxes; warp 3: the X boxes, whose
+              // bytes may land before the expectation is posted (the barrier's pending arrival keeps the phase open)
+              const bool w_a = warp == 0, w_b = split_producer ? warp == 3 : true;
+              const int32_t hb = w_b ? (nb >> 1) : 0;
+              if (sch.rank == 0 && warp == 0) mbar_arrive_expect_tx_addr(full_a, (a_boxes + peer_boxes + nb) * kBoxBytesMN);
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                if (j < a_boxes) tma_load_5d_2cta(sa + j * kBoxBytesMN, &tma_a, full_a, mt * 128 + j * 64, a0, a1, a2, a3);
+                if (w_a && j < a_boxes) tma_load_5d_2cta(sa + j * kBoxBytesMN, &tma_a, full_a, mt * 128 + j * 64, a0, a1, a2, a3);
               for (int j = 0; j < hb; ++j) {
                 const int32_t jj = static_cast<int>(sch.rank) * hb + j, bx = bdim ? box0 + jj : 0;
                 tma_load_5d_2cta(sa + a_alloc + j * kBoxBytesMN, &tma_b, full_a, bc0 + jj * bcs, b0 + e0 * bx, b1 + e1 * bx,
@@ -761,6 +780,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const uint64_t da0 = P.a_window ? make_smem_desc_noswizzle(ring_a, 16, 128) : make_smem_desc(ring_a, lbo, sbo);
     const uint64_t db0 = make_smem_desc(P.b_res ? smem_u32(smem) : ring_a + P.a_alloc, lbo, sbo);
     const uint32_t dstage = static_cast<uint32_t>(P.stage_bytes) >> 4, dres = static_cast<uint32_t>(P.b_res) >> 4;
+    const uint32_t dsub = static_cast<uint32_t>(P.sub_bytes) >> 4;
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const bool b_res = P.b_res != 0;
     uint64_t da = da0, db_ring = db0;
@@ -787,25 +807,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       // windowed A (da0 without swizzle): pixel rows of 16 B; row m of K chunk j (8 channels of window pixel j) sits at
       // (m + j) * 16, so the core matrices overlap: 16 B between the two K chunks of one MMA, 128 B between 8-row groups
       uint64_t db_res = db0;   // resident B: K chunk kc of the tile
-      for (int32_t kc = 0; kc < nk; ++kc) {
+      const int32_t kps = (wgrad || kPair) ? 1 : P.kps;   // K chunks per stage
+      for (int32_t kc = 0; kc < nk; kc += kps) {
         mbar_wait_addr(full_a, phase);
         tcgen05_fence_after();
-        const uint64_t db = b_res ? db_res : db_ring;
+        const int32_t nchunk = min(kps, nk - kc);
         if (elect_one_sync()) {
           if (kPair) {
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k)
-              umma_bf16_2cta(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_bf16_2cta(tmem_d, da + k * kstep, db_ring + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
             tcgen05_commit_2cta_addr(empty_a, pair_mask);   // frees the stage in both CTAs
           } else {
+            for (int32_t j = 0; j < nchunk; ++j) {
+              const uint64_t daj = da + static_cast<uint32_t>(j) * dsub;
+              const uint64_t dbj = b_res ? db_res + static_cast<uint32_t>(j) * dres : db_ring + static_cast<uint32_t>(j) * dsub;
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)
-              umma_bf16(tmem_d, da + k * kstep, db + k * kstep, idesc, (kc | k) != 0 ? 1u : 0u);
+              for (uint32_t k = 0; k < 4; ++k)
+                umma_bf16(tmem_d, daj + k * kstep, dbj + k * kstep, idesc, (kc | j | k) != 0 ? 1u : 0u);
+            }
             tcgen05_commit_addr(empty_a);
           }
         }
         __syncwarp();
-        db_res += dres;
+        db_res += static_cast<uint32_t>(nchunk) * dres;
         if (++stage == nstages) {
           stage = 0; phase ^= 1;
           da = da0; db_ring = db0; full_a = full0; empty_a = empty0;
@@ -919,6 +944,26 @@ static bool resident_b_enabled() {
   return cached == 1;
 }
 
+// PCGAN_KPS=0 keeps one K chunk per ring stage (measurement only).
+static bool kps_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PCGAN_KPS");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+// PCGAN_SPLITP=0 keeps one producer warp for paired weight gradients (measurement only).
+static bool splitp_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PCGAN_SPLITP");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 // PCGAN_DUAL=0 turns the second pipeline off (measurement only).
 static bool dual_enabled() {
   static int cached = -1;
@@ -1016,7 +1061,18 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     v.a_alloc = a_alloc;
     v.b_res = resident ? b_alloc : 0;
     v.ring_off = resident ? (int32_t)b_total : 0;
-    v.stage_bytes = resident ? a_alloc : a_alloc + b_alloc;
+    v.sub_bytes = resident ? a_alloc : a_alloc + b_alloc;
+    // K chunks per stage (unpaired forward / data gradient): as many as leave each pipeline three stages, at most 8; the
+    // single-thread issue loops pay their barrier round trip once per stage
+    int32_t kps = 1;
+    if (!wg && !d->pair && kps_enabled()) {
+      const int64_t per_pipe = (kDataBytes - v.ring_off) / 2;
+      const int64_t k_total = (int64_t)d->num_taps * d->cchunks;
+      while (kps < 8 && kps < k_total && (int64_t)(kps + 1) * v.sub_bytes * 3 <= per_pipe) ++kps;
+    }
+    v.kps = kps;
+    v.split_prod = (wg && d->pair && splitp_enabled()) ? 1 : 0;
+    v.stage_bytes = kps * v.sub_bytes;
     int32_t ns = (kDataBytes - v.ring_off) / v.stage_bytes;
     // two pipelines when each still gets at least two stages and the plan is not paired (a pair already shares one MMA
     // stream between two SMs)

@@ -9,6 +9,7 @@ A network at a fixed input geometry is a static program over padded NHWC bf16 bu
            training step allocates nothing after warm-up
 Only torch tensors (device memory) and the C ABI are used; there is no fallback path.
 """
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -17,6 +18,41 @@ from . import _lib as L
 from . import conv as CV
 from . import ops
 from .plan import Geom, OutMap, SLACK
+
+
+PHASE_STREAMS = os.environ.get("PCGAN_PHASE_STREAMS", "0") != "0"    # launch the sub-pixel phases of a strided data gradient / transposed convolution on forked streams
+_SIDE = {}
+
+
+def _fan_out(launchers):
+    """Run independent launches (the phases of one convolution write disjoint outputs) concurrently: the first on the
+    current stream, the others on side streams forked from it and joined back.  Under graph capture the fork / join
+    events become parallel branches of the graph."""
+    if len(launchers) == 1 or not PHASE_STREAMS:
+        for fn in launchers:
+            fn()
+        return
+    main = torch.cuda.current_stream()
+    dev = main.device
+    pool = _SIDE.setdefault(dev, [])
+    while len(pool) < len(launchers) - 1:
+        pool.append(torch.cuda.Stream(device=dev))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    joins = []
+    for i, fn in enumerate(launchers):
+        if i == 0:
+            fn()
+            continue
+        side = pool[i - 1]
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        joins.append(ev)
+    for ev in joins:
+        main.wait_event(ev)
 
 
 class ConvRT:
@@ -30,6 +66,10 @@ class ConvRT:
                  act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, dyg: Optional[Geom] = None,
                  dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True):
         self.name, self.weight, self.bias = name, weight, bias
+        # the convolution this runtime was planned for (tests/test_bench_geometry_gpu.py replays every plan against F.conv2d)
+        self.geometry = dict(xg=xg, stride=stride, cp=cp, out=out, transposed=transposed, output_padding=output_padding,
+                             act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats, dyg=dyg,
+                             dx_out=dx_out, full_padded=full_padded)
         self.bank = None
         dev = weight.device
         self.dev = dev
@@ -77,13 +117,11 @@ class ConvRT:
     def forward(self, xbuf, out, stats=None):
         self.pack()
         b = self.bias.detach() if self.bias is not None else None
-        for g, _, wbuf in self.fwd:
-            g.run(xbuf, wbuf, out, b, stats)
+        _fan_out([(lambda g=g, wbuf=wbuf: g.run(xbuf, wbuf, out, b, stats)) for g, _, wbuf in self.fwd])
 
     def backward_data(self, dybuf, dxout):
         self.pack()
-        for g, _, wbuf in self.dgrad:
-            g.run(dybuf, wbuf, dxout)
+        _fan_out([(lambda g=g, wbuf=wbuf: g.run(dybuf, wbuf, dxout)) for g, _, wbuf in self.dgrad])
 
     def backward_weight(self, dybuf, xbuf):
         """Accumulates into weight.grad (allocated on first use).  Under a WeightBank in deferred mode the packed

@@ -127,6 +127,7 @@ class _GenProgram:
                            OutMap.nchw(N, mod.output_nc, S, S), act=L.ACT_TANH, dyg=self.g_dyh,
                            dx_out=OutMap.nhwc(self.g_u2full), full_padded=True)
         self.scratch = _Scratch(dev)
+        self.keep_scratch = False
         self.pool = Pool(lambda key: self._new_ws())
         self.convs = [self.stem, self.down1, self.down2] + [c for blk in self.blocks for c in blk[:2]] + [self.up1, self.up2, self.head]
         self.bank = WeightBank(self.convs, dev)
@@ -224,19 +225,22 @@ class _GenProgram:
         # residual blocks, last to first; gb = gradient of the block output
         for i in range(nblk - 1, -1, -1):
             ca, cb, _, _ = self.blocks[i]
-            dyb = sc.get(self.g_b, "dyb")
+            # the blocks share their backward buffers; keep_scratch (tests) gives every block its own so that the whole
+            # chain can be inspected afterwards
+            t = str(i) if self.keep_scratch else ""
+            dyb = sc.get(self.g_b, "dyb" + t)
             _norm_backward(gb, 0, ws.rb[i], self.g_r3, ws.nb[i], Z, 0.0, h4 * h4, dyb, 1, res=ws.b[i], res_pad=1)
             if need_w:
                 cb.backward_weight(dyb, ws.h[i])
-            dfull = sc.get(self.g_bfull, "dfull")
+            dfull = sc.get(self.g_bfull, "dfull" + t)
             cb.backward_data(dyb, dfull)
-            dya = sc.get(self.g_b, "dya")
+            dya = sc.get(self.g_b, "dya" + t)
             _norm_backward(dfull, 1, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1, dy_fold=2)
             if need_w:
                 ca.backward_weight(dya, ws.b[i])
-            dfull2 = sc.get(self.g_bfull, "dfull2")
+            dfull2 = sc.get(self.g_bfull, "dfull2" + t)
             ca.backward_data(dya, dfull2)
-            gprev = sc.get(self.g_r3, "gb%d" % ((nblk - i) % 2))
+            gprev = sc.get(self.g_r3, ("gbk%d" % i) if self.keep_scratch else "gb%d" % ((nblk - i) % 2))
             ops.halo_fold(dfull2, self.g_b, gprev, 0, halo=L.HALO_REFLECT, add=gb, add_pad=0)
             gb = gprev
         # down2 unit (its output buffer ws.b[0])
@@ -567,12 +571,12 @@ class GANLoss(nn.Module):
         if isinstance(target_label, torch.Tensor):
             return target_label.to(device=input.device, dtype=torch.float32).reshape(-1).contiguous()
         if not isinstance(target_label, list):
-            key = (float(int(target_label)), input.size(0), input.device)
+            key = (float(target_label), input.size(0), input.device)
             t = self._const.get(key)
             if t is None:
                 t = self._const[key] = torch.full((input.size(0),), key[0], device=input.device)
             return t
-        vals = [float(int(t)) for t in target_label]
+        vals = [float(t) for t in target_label]      # bools become 1 / 0, anything else passes through (:399-403)
         return torch.tensor(np.array(vals, dtype=np.float32), device=input.device)
 
     def __call__(self, inputs, target_label):

@@ -16,6 +16,10 @@ def _ptr(t, elem_offset=0):
         return None
     if not t.is_cuda:
         raise L.PcganError("pcgan ops need CUDA tensors (no CPU fallback); got %s" % t.device)
+    if t.device.index != torch.cuda.current_device():
+        # kernels go to the current device's stream (and the library sizes grids for the current device)
+        raise L.PcganError("tensor on %s but the current CUDA device is %d: call torch.cuda.set_device (BaseModel.initialize does)"
+                           % (t.device, torch.cuda.current_device()))
     return t.data_ptr() + elem_offset * t.element_size()
 
 
@@ -38,10 +42,11 @@ def _count(n=1):
 
 
 class _Timed:
-    """When Stats.op_events is a list, every wrapped launch is bracketed by CUDA events (bench.py's per-kernel table)."""
+    """When Stats.op_events is a list, every wrapped launch is bracketed by CUDA events (bench.py's per-kernel table);
+    nbytes = the launch's algorithmic HBM traffic (tensors it must read and write once), for the HBM roofline."""
 
-    def __init__(self, name):
-        self.name, self.e0 = name, None
+    def __init__(self, name, nbytes=0):
+        self.name, self.e0, self.nbytes = name, None, int(nbytes)
 
     def __enter__(self):
         if Stats.op_events is not None:
@@ -53,7 +58,7 @@ class _Timed:
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            Stats.op_events.append((self.name, self.e0, e1))
+            Stats.op_events.append((self.name, self.e0, e1, self.nbytes))
         return False
 
 
@@ -151,7 +156,7 @@ def pack_nchw(src, dst, g: Geom, *, z=None, mul_out=None, mul_kind=L.ACT_TANH, h
     a = L.PackArgs(src=_ptr(src), z=_ptr(z), mul_out=_ptr(mul_out), mul_kind=mul_kind, dst=_ptr(dst), n=n, cs=cs, h=h, w=w,
                    ho=g.h, wo=g.w, cd=g.c, pad=g.pad, halo=halo, dst_n_stride=0)
     _count()
-    with _Timed("pack_nchw"):
+    with _Timed("pack_nchw", src.numel() * 4 * (1 + (mul_out is not None)) + g.numel * 2):
         L.check(L.load().pcgan_pack_nchw(C.byref(a), _stream()), "pack_nchw")
 
 
@@ -162,7 +167,7 @@ def unpack_resize_bwd(gbuf, g: Geom, dst, *, accumulate=False, scale=1.0):
     a = L.UnpackArgs(g=_ptr(gbuf), dst=_ptr(dst), n=n, c=g.c, hs=g.h, ws=g.w, pad=g.pad, cd=cd, h=h, w=w,
                      accumulate=int(accumulate), scale=scale)
     _count()
-    with _Timed("unpack_resize_bwd"):
+    with _Timed("unpack_resize_bwd", g.numel * 2 + dst.numel() * 4):
         L.check(L.load().pcgan_unpack_resize_bwd(C.byref(a), _stream()), "unpack_resize_bwd")
 
 
@@ -189,7 +194,8 @@ def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shif
                         stats=_ptr(stats), count=float(count), eps=eps, gamma=_ptr(gamma), beta=_ptr(beta),
                         mean_out=_ptr(mean_out), rstd_out=_ptr(rstd_out), scale_out=_ptr(scale_out), shift_out=_ptr(shift_out))
     _count()
-    with _Timed("norm_apply"):
+    elems = xg.n * xg.h * xg.w * xg.c
+    with _Timed("norm_apply", elems * 2 * (2 + (res is not None))):
         L.check(L.load().pcgan_norm_apply(C.byref(a), _stream()), "norm_apply")
 
 
@@ -197,7 +203,7 @@ def halo_fold(gpad, gg: Geom, out, out_pad, *, halo=L.HALO_REFLECT, add=None, ad
     a = L.FoldArgs(gpad=_ptr(gpad), g_pad=gg.pad, halo=halo, add=_ptr(add), add_pad=add_pad, out=_ptr(out),
                    out_pad=out_pad, n=gg.n, h=gg.h, w=gg.w, c=gg.c)
     _count()
-    with _Timed("halo_fold"):
+    with _Timed("halo_fold", 2 * gg.n * gg.c * (gg.hp * gg.wp + gg.h * gg.w * (1 + (add is not None)))):
         L.check(L.load().pcgan_halo_fold(C.byref(a), _stream()), "halo_fold")
 
 
@@ -215,41 +221,43 @@ def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, s
 def norm_bwd_reduce(dy, dy_pad, x, xg, **kw):
     a = _bwd_args(dy, dy_pad, x, xg, **kw)
     _count()
-    with _Timed("norm_bwd_reduce"):
+    elems = xg.n * xg.h * xg.w * xg.c
+    with _Timed("norm_bwd_reduce", elems * 2 * (2 + (kw.get("res") is not None))):
         L.check(L.load().pcgan_norm_bwd_reduce(C.byref(a), _stream()), "norm_bwd_reduce")
 
 
 def norm_bwd_apply(dy, dy_pad, x, xg, **kw):
     a = _bwd_args(dy, dy_pad, x, xg, **kw)
     _count()
-    with _Timed("norm_bwd_apply"):
+    elems = xg.n * xg.h * xg.w * xg.c
+    with _Timed("norm_bwd_apply", elems * 2 * (3 + (kw.get("res") is not None) + (kw.get("dres") is not None))):
         L.check(L.load().pcgan_norm_bwd_apply(C.byref(a), _stream()), "norm_bwd_apply")
 
 
 def maxpool_fwd(x, xg: Geom, y, y_pad, idx):
     a = L.MaxpoolArgs(x=_ptr(x), x_pad=xg.pad, y=_ptr(y), y_pad=y_pad, idx=_ptr(idx), n=xg.n, h=xg.h, w=xg.w, c=xg.c)
     _count()
-    with _Timed("maxpool_fwd"):
+    with _Timed("maxpool_fwd", xg.n * xg.h * xg.w * xg.c * 2 + xg.n * xg.h * xg.w * xg.c * 3 // 4):
         L.check(L.load().pcgan_maxpool3x3s2_fwd(C.byref(a), _stream()), "maxpool_fwd")
 
 
 def maxpool_bwd(dy, dy_pad, idx, dx, dx_pad, n, h, w, c):
     _count()
-    with _Timed("maxpool_bwd"):
+    with _Timed("maxpool_bwd", n * h * w * c * 2 + n * h * w * c * 3 // 4):
         L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, _stream()), "maxpool_bwd")
 
 
 def resize_nchw_fwd(src, dst):
     n, c, h, w = src.shape
     _count()
-    with _Timed("resize_nchw_fwd"):
+    with _Timed("resize_nchw_fwd", (src.numel() + dst.numel()) * 4):
         L.check(L.load().pcgan_resize_nchw_fwd(_ptr(src), _ptr(dst), n * c, h, w, dst.shape[2], dst.shape[3], _stream()), "resize_nchw_fwd")
 
 
 def resize_nchw_bwd(gdst, gsrc):
     n, c, h, w = gsrc.shape
     _count()
-    with _Timed("resize_nchw_bwd"):
+    with _Timed("resize_nchw_bwd", (gdst.numel() + gsrc.numel()) * 4):
         L.check(L.load().pcgan_resize_nchw_bwd(_ptr(gdst), _ptr(gsrc), n * c, h, w, gdst.shape[2], gdst.shape[3], _stream()), "resize_nchw_bwd")
 
 

@@ -20,6 +20,7 @@ from collections import OrderedDict
 
 import numpy as np
 import torch
+import torch.distributed as dist
 from torch.optim import lr_scheduler
 
 from . import networks
@@ -42,13 +43,42 @@ def default_options(**overrides):
         embedding_bins="[]", display_visuals=False, noisy=False, noisy_D=True, noisy_rec=True, noisy_var_type="",
         bayesian=False, bnn_dropout=0.0, bnn_T=10, attr_bins=[],
         lambda_L1=0.0, lambda_IP=0.0, lambda_z=1.0, lambda_A=0.5, lambda_A_GAN=0.0, lr_E=0.0, use_real_A=False,
-        relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False,
+        relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False, update_logvar_E=False,
         no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5, lr_policy="lambda", niter=50, niter_decay=50, epoch_count=1,
         lr_decay_iters=50, continue_train=False, which_epoch="latest", load_model_names=[], verbose=False,
         cuda_graph=False, cuda_graph_warmup=3, cuda_graph_segments=None)
     for k, v in overrides.items():
         setattr(opt, k, v)
     return opt
+
+
+def str2bool(v):
+    """util.str2bool (util/util.py:94-106)."""
+    import argparse
+    if isinstance(v, bool):
+        return v
+    if v.lower() in ("yes", "true", "t", "y", "1"):
+        return True
+    if v.lower() in ("no", "false", "f", "n", "0"):
+        return False
+    raise argparse.ArgumentTypeError("Boolean value expected.")
+
+
+def str2list(v):
+    """util.str2list (util/util.py): the string form of a list ('[-2,-1,0,1,2]') or an existing list."""
+    if isinstance(v, (list, tuple)):
+        return list(v)
+    import ast
+    v = v.strip()
+    return list(ast.literal_eval(v)) if v else []
+
+
+def _dist_ready():
+    return dist.is_available() and dist.is_initialized()
+
+
+def _rank():
+    return dist.get_rank() if _dist_ready() else 0
 
 
 def get_scheduler(optimizer, opt):
@@ -77,6 +107,12 @@ class BaseModel:
             raise RuntimeError("pcgan_b200 has no CPU path: run with --gpu_ids <local device> on a CUDA machine")
         self.isTrain = opt.isTrain
         self.device = torch.device("cuda:{}".format(self.gpu_ids[0]))
+        # the reference selects the device in BaseOptions.parse (options/base_options.py: torch.cuda.set_device); the
+        # kernels are launched on the current device's stream, so it must be the one the tensors live on
+        torch.cuda.set_device(self.device)
+        # one process per GPU (torchrun ... --gpu_ids $LOCAL_RANK): join the job's process group if the launcher set one up
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and dist.is_available() and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.device)
         self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
         self.loss_names, self.model_names, self.load_model_names, self.visual_names, self.image_paths = [], [], [], [], []
         self.current_iter = 0
@@ -87,10 +123,43 @@ class BaseModel:
             self.schedulers = [get_scheduler(o, opt) for o in self.optimizers]
         if not self.isTrain or opt.continue_train:
             self.load_networks(opt.which_epoch)
+        self.broadcast_replicas()
+        if _rank() == 0:
+            self.print_networks(opt.verbose)
 
     def update_learning_rate(self):
         for s in self.schedulers:
             s.step()
+        print("learning rate = %.7f" % float(self.optimizers[0].param_groups[0]["lr"]))
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    def eval(self):
+        for n in self.model_names:
+            if isinstance(n, str):
+                getattr(self, "net" + n).eval()
+
+    def print_networks(self, verbose):
+        print("---------- Networks initialized -------------")
+        for n in self.model_names:
+            if isinstance(n, str):
+                net = getattr(self, "net" + n)
+                if verbose:
+                    print(net)
+                print("[Network %s] Total number of parameters : %.3f M" % (n, sum(p.numel() for p in net.parameters()) / 1e6))
+        print("-----------------------------------------------")
+
+    def broadcast_replicas(self):
+        """Data-parallel replicas start identical (what nn.DataParallel's per-call replicate, networks.py:100, guarantees
+        in the reference): every parameter and buffer of every network is broadcast from rank 0."""
+        if not _dist_ready() or dist.get_world_size() == 1:
+            return
+        for n in self.model_names:
+            if isinstance(n, str):
+                net = getattr(self, "net" + n)
+                for t in list(net.parameters()) + list(net.buffers()):
+                    dist.broadcast(t.data, 0)
 
     def get_current_visuals(self):
         return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str))
@@ -106,6 +175,8 @@ class BaseModel:
         return net.module if isinstance(net, torch.nn.DataParallel) else net
 
     def save_networks(self, which_epoch):
+        if _rank() != 0:      # replicas are identical: one writer
+            return
         os.makedirs(self.save_dir, exist_ok=True)
         for n in self.model_names:
             if isinstance(n, str):
@@ -119,6 +190,14 @@ class BaseModel:
                 path = os.path.join(self.save_dir, "%s_net_%s.pth" % (which_epoch, n))
                 sd = torch.load(path, map_location=str(self.device))
                 self._unwrap(getattr(self, "net" + n)).load_state_dict(sd)
+        self.invalidate_graphs()
+
+    def invalidate_graphs(self):
+        """Captured steps read packed bf16 operands that are refreshed by launches recorded at capture time; a weight
+        change from outside the optimizers (checkpoint load, manual edit) needs a new capture."""
+        if getattr(self, "_graphs", None):
+            self._graphs = {}
+            self._eager_steps = 0
 
     def set_requires_grad(self, nets, requires_grad=False):
         if not isinstance(nets, list):
@@ -129,13 +208,61 @@ class BaseModel:
                     p.requires_grad = requires_grad
 
 
+# The flags `--model wsgan_emb` adds to the parser (wsgan_emb_model.py:21-66): (name, type, default[, extra argparse kw]).
+_COMMON_FLAGS = [
+    ("norm_G", str, "instance"), ("norm_D", str, "batch"), ("embedding_nc", int, 1), ("which_model_netE", str, "resnet18"),
+    ("pooling_E", str, "avg"), ("cnn_dim_E", int, [32, 1], dict(nargs="+")), ("no_cnn_E", None, False), ("cnn_pad_E", int, 1),
+    ("cnn_relu_slope_E", float, 0.7), ("fineSize_E", int, 224),
+    ("pretrained_model_path_E", str, "pretrained_models/embedding_encoder.pth"),
+    ("embedding_mean", float, [0.0], dict(nargs="*")), ("embedding_std", float, [1.0], dict(nargs="*")),
+    ("embedding_bins", str, "[]"), ("display_visuals", None, False), ("noisy", str2bool, False), ("noisy_D", str2bool, True),
+    ("noisy_rec", str2bool, True), ("noisy_var_type", str, ""), ("bayesian", str2bool, False), ("bnn_dropout", float, 0.0),
+    ("bnn_T", int, 10), ("use_projection", str2bool, True), ("sample_embedding_B", str2bool, False),
+]
+_TRAIN_FLAGS = [
+    ("lambda_L1", float, 0.0), ("lambda_IP", float, 1.0), ("lambda_z", float, 1.0), ("lambda_A", float, 0.5),
+    ("lambda_A_GAN", float, 0.0), ("lambda_theta_D", float, 0.0), ("lambda_theta_E", float, 0.0),
+    ("which_model_netIP", str, "alexnet"), ("pretrained_model_path_IP", str, "pretrained_models/alexnet-owt-4df8aa71.pth"),
+    ("fineSize_IP", int, 224), ("lr_E", float, 0.0), ("use_real_A", None, False),
+    ("identity_preserving_criterion", str, "mse"), ("relabel_D", int, [0, 1, 0], dict(nargs="*")),
+    ("no_mixed_label_D", None, False), ("weight_label_D", float, [0.5, 0, 0.5], dict(nargs="*")),
+    ("detach_fake_B", None, False), ("update_logvar_E", str2bool, False),
+]
+# defaults the model overrides on the base parser (wsgan_emb_model.py:68-80)
+_DEFAULT_OVERRIDES = dict(pool_size=0, no_lsgan=True, norm="instance", dataset_mode="wsgan_emb", which_model_netG="unet_128",
+                          which_model_netD="n_layers", n_layers_D=4, batchSize=10, loadSize=128, fineSize=128,
+                          display_visuals=True, save_epoch_freq=2)
+
+
 class WSGANEmbModel(BaseModel):
     def name(self):
         return "WSGANEmbModel"
 
+    @staticmethod
+    def modify_commandline_options(parser, is_train=True):
+        """The same flags and defaults as the reference's model class (wsgan_emb_model.py:20-80), plus --cuda_graph."""
+        for spec in _COMMON_FLAGS + (_TRAIN_FLAGS if is_train else []):
+            name, typ, default = spec[:3]
+            kw = dict(spec[3]) if len(spec) > 3 else {}
+            if typ is None:
+                parser.add_argument("--" + name, action="store_true")
+            else:
+                parser.add_argument("--" + name, type=typ, default=default, **kw)
+        if is_train:
+            parser.add_argument("--cuda_graph", type=str2bool, default=False,
+                                help="pcgan_b200: capture optimize_parameters() into a CUDA graph after a few eager steps and replay it")
+        parser.set_defaults(**_DEFAULT_OVERRIDES)
+        return parser
+
     def initialize(self, opt):
         BaseModel.initialize(self, opt)
         assert opt.input_nc == opt.output_nc
+        self.attr_bins = getattr(opt, "attr_bins", [])
+        self.embedding_bins = str2list(getattr(opt, "embedding_bins", "[]"))
+        if "a" in opt.noisy_var_type and not opt.noisy:
+            raise RuntimeError("Aleatoric only available when noisy is True.")
+        if "e" in opt.noisy_var_type and not opt.bayesian:
+            raise RuntimeError("Epistemic only available when bayesian is True.")
         if opt.isTrain and opt.lambda_IP > 0.0:
             raise NotImplementedError("the identity-preserving AlexNet loss (netIP) is outside the named hot path: use --lambda_IP 0")
         if opt.no_cnn_E:
@@ -181,9 +308,18 @@ class WSGANEmbModel(BaseModel):
             if opt.lr_E > 0.0:      # wsgan_emb_model.py:159-163
                 if self.use_graph:
                     raise NotImplementedError("--cuda_graph with --lr_E > 0 (two generator updates per step) is not supported")
-                self.optimizer_E = FusedAdam(self.netE.parameters(), lr=opt.lr_E, betas=(opt.beta1, 0.999))
+                if getattr(opt, "update_logvar_E", False):      # :157-158: only the log-variance head is trained
+                    assert opt.noisy
+                    params_E = list(self._unwrap(self.netE).cnn_logvar.parameters())
+                    trained = {id(p) for p in params_E}
+                    for p in self.netE.parameters():
+                        if id(p) not in trained:
+                            p.requires_grad = False
+                else:
+                    params_E = list(self.netE.parameters())
+                self.optimizer_E = FusedAdam(params_E, lr=opt.lr_E, betas=(opt.beta1, 0.999))
                 self.optimizers.append(self.optimizer_E)
-                self.sync_E = GradSync(list(self.netE.parameters()))
+                self.sync_E = GradSync(params_E)
                 # backward_GE keeps the graph (retain_graph=True, :369) and backward_G_alone walks G's first pass and
                 # E(real_B) again: their workspaces must outlive the first backward
                 for net in (self.netG, self.netE):
@@ -199,7 +335,14 @@ class WSGANEmbModel(BaseModel):
             else:
                 self.weight_label_D = None
         self.embedding_normalize = lambda x: (x - opt.embedding_mean[0]) / opt.embedding_std[0]
+        if getattr(opt, "display_visuals", False):
+            self.pre_generate_embeddings(self.embedding_bins)
         self.transform_E = networks.Normalize((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))
+
+    def pre_generate_embeddings(self, embeddings_list):
+        """wsgan_emb_model.py:184-191: the normalised embeddings the aging visuals are generated for."""
+        self.fixed_embeddings = [self.embedding_normalize(torch.tensor([[[[float(v)]]]], device=self.device))
+                                 for v in np.array(embeddings_list).reshape(-1)]
 
     # ------------------------------------------------------------------ data
     def _stage(self, name, src):
@@ -238,6 +381,7 @@ class WSGANEmbModel(BaseModel):
             self.image_paths = input.get("A_paths", [])
             if "B" in input:
                 self.real_B = input["B"].to(self.device)
+                self.image_paths = input.get("B_paths", self.image_paths)     # :208-210
         self.current_iter += 1
         self.current_batch_size = int(self.real_A.size(0))
 
@@ -288,11 +432,24 @@ class WSGANEmbModel(BaseModel):
         self.rec_A = self.netG(src, self.embedding_A)
 
     def test(self):
+        """wsgan_emb_model.py:261-277."""
         with torch.no_grad():
             if hasattr(self, "real_B"):
-                y_B, _ = self._encode(upsample2d(self.real_B, self.opt.fineSize_E))
-                self.embedding_B = self.embedding_normalize(y_B.detach())
-                self.fake_B = self.netG(self.real_A, self.embedding_B)
+                if "real_B" not in self.visual_names:
+                    self.visual_names += ["real_B", "fake_B"]
+                self.fake_B = self.sample_from_prior()
+
+    def sample_from_prior(self):
+        """wsgan_emb_model.py:279-292: A -> B with the embedding the encoder reads off real_B."""
+        y_B, _ = self._encode(upsample2d(self.real_B, self.opt.fineSize_E))
+        self.embedding_B = self.embedding_normalize(y_B.detach())
+        return self.netG(self.real_A, self.embedding_B)
+
+    def sample_from_label(self, label):
+        """wsgan_emb_model.py:294-298."""
+        emb = torch.tensor([[[[float(self.embedding_bins[label])]]]], device=self.device)
+        n = self.real_A.size(0)
+        return self.netG(self.real_A, self.embedding_normalize(emb).expand(n, 1, 1, 1).contiguous())
 
     # -------------------------------------------------------------- backward
     def _cond_B(self):
@@ -351,6 +508,7 @@ class WSGANEmbModel(BaseModel):
                 if "e" in opt.noisy_var_type:
                     y_var = y_var + y_var_
                 y_logvar = torch.log(y_var + 1e-20)
+            self.pred_y = pred_y.detach()      # kept for inspection (tests check the loss arithmetic on it)
             if opt.noisy_var_type and opt.noisy_rec:
                 self.loss_z_rec = ((pred_y - self.y_B).pow(2) / y_var.detach() + y_logvar.detach()).sum() / pred_y.size(0) * 0.5 * opt.lambda_z
             else:
@@ -507,4 +665,12 @@ class WSGANEmbModel(BaseModel):
         self._graphs[key] = graphs
 
     def get_current_visuals(self):
-        return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str) and hasattr(self, n))
+        """wsgan_emb_model.py:486-497: the step's images plus, with --display_visuals, real_A[0] aged to every fixed
+        embedding (generator passes without gradients)."""
+        out = OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str) and hasattr(self, n))
+        if getattr(self.opt, "display_visuals", False):
+            self.set_requires_grad(self.netG, False)
+            for i, emb in enumerate(self.fixed_embeddings):
+                out["attr_%d" % i] = self.netG(self.real_A[0:1, ...].contiguous(), emb)
+            self.set_requires_grad(self.netG, True)
+        return out
