@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 12
+#define PCGAN_ABI_VERSION 13
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -329,6 +329,13 @@ typedef struct {
 } pcgan_norm_bwd_args;
 int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
 int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
+/* Both passes in ONE launch for the lean InstanceNorm path (affine == 0, no masks, dx only): a thread-block cluster
+ * per sample keeps dy and x resident in shared memory and reduces the per-channel sums through distributed shared
+ * memory (3 tensor passes over HBM instead of 5).  `sums` is not written.  _supported() tells (1 / 0) whether the
+ * arguments qualify (image rows split evenly over the cluster and fit its shared memory); otherwise use the two passes. */
+int pcgan_norm_bwd_fused_supported(const pcgan_norm_bwd_args* a);
+int pcgan_norm_bwd_fused(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
+int pcgan_norm_bwd_fused_active_clusters(void);   /* diagnostic: resident clusters (cudaOccupancyMaxActiveClusters), -1 before the first launch */
 
 /* 3x3 stride-2 pad-1 max pooling on padded NHWC bf16 (resnet.py:137); idx keeps the
  * window position (0..8) of the maximum for the backward pass. */

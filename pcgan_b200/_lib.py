@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -144,6 +144,9 @@ SYMBOLS = {
     "pcgan_halo_fold": (C.c_int, [C.POINTER(FoldArgs), vp]),
     "pcgan_norm_bwd_reduce": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
     "pcgan_norm_bwd_apply": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
+    "pcgan_norm_bwd_fused_supported": (C.c_int, [C.POINTER(NormBwdArgs)]),
+    "pcgan_norm_bwd_fused": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
+    "pcgan_norm_bwd_fused_active_clusters": (C.c_int, []),
     "pcgan_maxpool3x3s2_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), vp]),
     "pcgan_maxpool3x3s2_bwd": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]),
     "pcgan_loss": (C.c_int, [C.POINTER(LossArgs), vp]),

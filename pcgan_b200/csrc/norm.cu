@@ -639,6 +639,153 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_no
   }
 }
 
+// ------------------------------------------------------ one-pass norm backward
+// Lean InstanceNorm path (affine == 0, no masks; the generator's ResnetBlocks, networks.py:621-652).  The two-pass
+// backward reads dy and x twice (reduce, then apply: 5 tensor passes over HBM); here a CLUSTER of kFusedCL CTAs owns one
+// sample, each CTA keeps its h / kFusedCL image rows of dy and x in shared memory (bulk async copies, read from HBM
+// once), the per-channel sums are reduced across the cluster through distributed shared memory, and dx is produced from
+// the resident copies: 3 tensor passes, one launch.  Under dy_fold == 2 the streamed dy is the interior of a padded-grid
+// gradient and the mirrored halo values are added from global memory (L2) for the few border pixels, exactly as in the
+// two-pass kernels.
+static constexpr int kFusedCL = 8;
+static constexpr int kFusedT = 1024;  // 32 warps: one CTA per SM holds 128 KB of rows, so the warps of that one CTA must hide the latencies
+static constexpr int kFusedMaxTensorBytes = 64 * 1024;   // per CTA and tensor
+
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 dsmem_ld_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(kFusedT, 1) norm_bwd_fused_kernel(pcgan_norm_bwd_args a, int rows, int lcv) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int n = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();
+  const int y0 = static_cast<int>(rank) * rows;
+  const int cv = a.c >> 3;
+  const int row_vec = a.w * cv;            // 16-byte vectors per image row
+  const int nvec = rows * row_vec;
+  uint4* sX = reinterpret_cast<uint4*>(smem_raw);
+  uint4* sG = sX + nvec;
+  float* red = reinterpret_cast<float*>(sG + nvec);            // [kFusedT][16]
+  float* part = red + kFusedT * 16;                            // [c][2]: this CTA's (sum g, sum g*xhat)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + a.c * 2);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  griddep_wait();
+  griddep_launch();
+  const int wdp = a.w + 2 * a.dy_pad, wxp = a.w + 2 * a.x_pad;
+  const __nv_bfloat16* dyn = reinterpret_cast<const __nv_bfloat16*>(a.dy) + static_cast<int64_t>(n) * (a.h + 2 * a.dy_pad) * wdp * a.c;
+  const __nv_bfloat16* xn = reinterpret_cast<const __nv_bfloat16*>(a.x) + static_cast<int64_t>(n) * (a.h + 2 * a.x_pad) * wxp * a.c;
+  if (threadIdx.x == 0) {
+    const uint32_t row_bytes = static_cast<uint32_t>(row_vec) * 16u;
+    mbar_arrive_expect_tx(bar, 2u * row_bytes * rows);
+    for (int r = 0; r < rows; ++r) {
+      const int y = y0 + r;
+      bulk_load(sX + r * row_vec, xn + (static_cast<int64_t>(y + a.x_pad) * wxp + a.x_pad) * a.c, row_bytes, bar);
+      bulk_load(sG + r * row_vec, dyn + (static_cast<int64_t>(y + a.dy_pad) * wdp + a.dy_pad) * a.c, row_bytes, bar);
+    }
+  }
+  const int c0 = (threadIdx.x & (cv - 1)) << 3;
+  float sc[8], sh[8];
+  {
+    const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+    load_f8(a.scale + so, sc);
+    load_f8(a.shift + so, sh);
+  }
+  const bool fold = a.dy_fold == 2;
+  const bool relu = a.act == PCGAN_ACT_RELU, lrelu = a.act == PCGAN_ACT_LRELU;
+  const __nv_bfloat16* dyg = dyn + c0;
+  mbar_wait(bar, 0);
+
+  // g = dy * act'(pre) and xhat = pre for vector v of this CTA's rows
+  auto grad = [&](int v, float (&g)[8], float (&xh)[8]) {
+    unpack8(sG[v], g);
+    if (fold) {
+      const int pix = v >> lcv;
+      const int r = pix / a.w;
+      folded_load(dyg, y0 + r, pix - r * a.w, a.h, a.w, a.dy_pad, a.c, true, g, true);
+    }
+    float x8[8];
+    unpack8(sX[v], x8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xh[j] = fmaf(sc[j], x8[j], sh[j]);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = xh[j] > 0.f ? g[j] : 0.f;
+    } else if (lrelu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = xh[j] > 0.f ? g[j] : g[j] * a.act_slope;
+    }
+  };
+
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int v = threadIdx.x; v < nvec; v += kFusedT) {
+    float g[8], xh[8];
+    grad(v, g, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], xh[j], s2[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  __syncthreads();
+  const int lanes = kFusedT / cv;
+  for (int t = threadIdx.x; t < cv * 16; t += kFusedT) {
+    const int c = t >> 4, slot = t & 15;
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += red[(l * cv + c) * 16 + slot];
+    part[((c << 3) + (slot & 7)) * 2 + (slot >> 3)] = sum;
+  }
+  cluster_sync_all();      // every CTA's partial sums are in place (release / acquire at cluster scope)
+  // a few threads fetch the peers' partial sums (remote shared-memory requests are expensive: one float4 per thread and
+  // peer, not one set per consumer thread) and leave the cluster totals / count in local shared memory
+  float* tot = red;        // the block-reduction scratch is free again
+  if (static_cast<int>(threadIdx.x) * 4 < a.c * 2) {
+    const uint32_t mine = smem_u32(part + threadIdx.x * 4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (uint32_t r = 0; r < kFusedCL; ++r) {
+      const float4 t = dsmem_ld_f32x4(dsmem_addr(mine, r));
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    const float inv = 1.f / a.count;
+    reinterpret_cast<float4*>(tot)[threadIdx.x] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+  cluster_sync_all();      // nobody overwrites or leaves while a peer may still read its partial sums; `tot` is visible
+  float A[8], B[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = reinterpret_cast<const float4*>(tot + c0 * 2)[q];
+    A[2 * q] = t.x; B[2 * q] = t.y; A[2 * q + 1] = t.z; B[2 * q + 1] = t.w;
+  }
+  const int wop = a.w + 2 * a.dx_pad;
+  __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx) + static_cast<int64_t>(n) * (a.h + 2 * a.dx_pad) * wop * a.c + c0;
+  for (int v = threadIdx.x; v < nvec; v += kFusedT) {
+    float g[8], xh[8], o[8];
+    grad(v, g, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (g[j] - A[j] - xh[j] * B[j]) * sc[j];
+    const int pix = v >> lcv;
+    const int r = pix / a.w;
+    store8(dx + (static_cast<int64_t>(y0 + r + a.dx_pad) * wop + (pix - r * a.w) + a.dx_pad) * a.c, o);
+  }
+}
+
+static size_t fused_smem(int rows, int w, int c) {
+  return 2 * static_cast<size_t>(rows) * w * c * 2 + kFusedT * 16 * sizeof(float) + static_cast<size_t>(c) * 2 * sizeof(float) + 16;
+}
+
 // ----------------------------------------------------------------------- host
 static int log2_pow2(int v) {
   int l = 0;
@@ -823,5 +970,57 @@ extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t
   else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
   else PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, true>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
   PCGAN_LAUNCH_OK("norm_bwd_apply_kernel");
+  return PCGAN_OK;
+}
+
+static int fused_active_clusters = -1;
+/* clusters of the one-pass kernel the device holds at once at the ResnetBlock shape (diagnostic; -1 before the first launch) */
+extern "C" int pcgan_norm_bwd_fused_active_clusters(void) { return fused_active_clusters; }
+
+extern "C" int pcgan_norm_bwd_fused_supported(const pcgan_norm_bwd_args* a) {
+  if (!a || !a->dy || !a->x || !a->dx || a->dres) return 0;
+  if (a->affine != 0 || a->drop_mask || a->post_mask || !a->scale || !a->shift || a->count <= 0.f) return 0;
+  if (a->res && a->act != PCGAN_ACT_NONE) return 0;
+  if (a->act != PCGAN_ACT_NONE && a->act != PCGAN_ACT_RELU && a->act != PCGAN_ACT_LRELU) return 0;
+  if (a->dy_fold != 0 && a->dy_fold != 2) return 0;
+  if (a->c < 8 || a->c % 8 != 0 || log2_pow2(a->c / 8) < 0 || a->c / 8 > kFusedT || a->c > 2048) return 0;
+  if (a->h % kFusedCL != 0 || a->n < 1 || a->n > 65535) return 0;
+  const int rows = a->h / kFusedCL;
+  if (static_cast<int64_t>(rows) * a->w * a->c * 2 > kFusedMaxTensorBytes) return 0;
+  if (a->dy_fold == 2 && (2 * a->dy_pad + 1 > a->h || 2 * a->dy_pad + 1 > a->w)) return 0;
+  return 1;
+}
+
+extern "C" int pcgan_norm_bwd_fused(const pcgan_norm_bwd_args* a, pcgan_stream_t s) {
+  int lcv, rc = check_bwd(a, &lcv);
+  if (rc) return rc;
+  if (!pcgan_norm_bwd_fused_supported(a)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd_fused: lean InstanceNorm path, h %% %d == 0, %d KB of rows per CTA", kFusedCL, kFusedMaxTensorBytes / 1024);
+  const int rows = a->h / kFusedCL;
+  const size_t smem = fused_smem(rows, a->w, a->c);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    // two resident tensors + the block-reduction scratch + per-channel partial sums of up to 2048 channels
+    attr_err = cudaFuncSetAttribute(norm_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    2 * kFusedMaxTensorBytes + kFusedT * 16 * 4 + 2048 * 2 * 4 + 16);
+    if (attr_err == cudaSuccess && kFusedCL > 8)
+      attr_err = cudaFuncSetAttribute(norm_bwd_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (attr_err == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kFusedCL, 64);
+      cfg.blockDim = dim3(kFusedT);
+      cfg.dynamicSmemBytes = 2 * kFusedMaxTensorBytes + kFusedT * 16 * 4 + 256 * 2 * 4 + 16;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = kFusedCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, norm_bwd_fused_kernel, &cfg) == cudaSuccess) fused_active_clusters = nc;
+      else (void)cudaGetLastError();
+    }
+  });
+  if (attr_err != cudaSuccess) return fail(PCGAN_ERR_CUDA, "cudaFuncSetAttribute(norm_bwd_fused): %s", cudaGetErrorString(attr_err));
+  PCGAN_CUDA_OK(launch_pdl(norm_bwd_fused_kernel, dim3(kFusedCL, a->n), dim3(kFusedT), smem, STREAM(s), kFusedCL, *a, rows, lcv));
+  PCGAN_LAUNCH_OK("norm_bwd_fused_kernel");
   return PCGAN_OK;
 }

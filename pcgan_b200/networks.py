@@ -50,8 +50,7 @@ def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count,
               sums=ns.sums, dy_fold=dy_fold, affine=ns.affine, drop_mask=drop_mask, post_mask=post_mask)
     if not ns.pooled:
         ns.sums.zero_()
-    ops.norm_bwd_reduce(gy, gy_pad, rbuf, rg, **kw)
-    ops.norm_bwd_apply(gy, gy_pad, rbuf, rg, dx=dx, dx_pad=dx_pad, dres=dres, dres_pad=dres_pad, **kw)
+    ops.norm_bwd(gy, gy_pad, rbuf, rg, dx=dx, dx_pad=dx_pad, dres=dres, dres_pad=dres_pad, **kw)
 
 
 class _Scratch:

@@ -252,3 +252,58 @@ def test_norm_backward_fused_fold_and_lean_variant(C, H, pad):
         e = rel(got, rr.grad)
         print("%s: %.3e" % (name, e))
         assert e < (2e-2 if "separate" in name else 1e-2), name   # the separate fold rounds the folded gradient to bf16 once more
+
+
+@pytest.mark.parametrize("C,H,pad,act,fold", [(256, 32, 1, "relu", True), (256, 32, 1, "none", False), (64, 16, 3, "relu", True), (128, 8, 0, "lrelu", False)])
+def test_norm_backward_one_pass_cluster_kernel(C, H, pad, act, fold):
+    """pcgan_norm_bwd_fused (one launch, thread-block cluster per sample, sums reduced through distributed shared memory)
+    against fp32 autograd of act(instance_norm(x)) and against the two-pass kernels on the same operands; the first case
+    is the ResnetBlock shape of the 128 x 128 step (networks.py:621-652)."""
+    from pcgan_b200.engine import NormState
+    torch.manual_seed(12)
+    N = 5
+    A = {"relu": L.ACT_RELU, "none": L.ACT_NONE, "lrelu": L.ACT_LRELU}[act]
+    gr, gp = Geom(N, H, H, C, 0), Geom(N, H, H, C, max(pad, 1))
+    r = bf(torch.randn(N, C, H, H, device=DEV) * 1.5 + 0.3)
+    rbuf = to_buf(r, 0)
+    if fold:
+        gsrc = bf(torch.randn(N, C, H + 2 * pad, H + 2 * pad, device=DEV))
+        gbuf, gy_pad = to_buf(gsrc, 0), pad
+        xi = torch.zeros(N, C, H, H, device=DEV, requires_grad=True)
+        F.pad(xi, (pad,) * 4, mode="reflect").backward(gsrc)
+        gy = xi.grad
+    else:
+        gy = bf(torch.randn(N, C, H, H, device=DEV))
+        gbuf, gy_pad = to_buf(gy, 0), 0
+    ns = NormState(N, C, DEV)
+    st = torch.stack([r.sum((2, 3)), (r * r).sum((2, 3))], -1).contiguous()
+    ops.norm_finalize(st, N, C, H * H, mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift)
+    rr = r.clone().requires_grad_(True)
+    pre = F.instance_norm(rr)
+    y = torch.relu(pre) if act == "relu" else (F.leaky_relu(pre, 0.2) if act == "lrelu" else pre)
+    y.backward(gy)
+    kw = dict(mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift, groups=N, act=A, act_slope=0.2, count=H * H, sums=ns.sums, affine=0,
+              dy_fold=2 if fold else 0)
+    a = ops._bwd_args(gbuf, gy_pad, rbuf, gr, dx=torch.zeros(8, dtype=torch.bfloat16, device=DEV), dx_pad=gp.pad, **kw)
+    import ctypes
+    assert L.load().pcgan_norm_bwd_fused_supported(ctypes.byref(a)) == 1
+    outs = {}
+    default = ops.NORM_FUSED
+    for fused in (True, False):
+        ns.sums.zero_()
+        dx = torch.zeros(gp.numel + 512, dtype=torch.bfloat16, device=DEV)
+        ops.NORM_FUSED = fused
+        before = ops.Stats.launches
+        ops.norm_bwd(gbuf, gy_pad, rbuf, gr, dx=dx, dx_pad=gp.pad, **kw)
+        assert ops.Stats.launches - before == (1 if fused else 2)
+        outs[fused] = from_buf(dx, gp)
+        halo = dx[: gp.numel].view(N, gp.hp, gp.wp, C).float().clone()
+        halo[:, gp.pad:gp.pad + H, gp.pad:gp.pad + H] = 0
+        assert float(halo.abs().max()) == 0.0, "the halo of dx must stay zero"
+    ops.NORM_FUSED = default
+    e1, e2, e12 = rel(outs[True], rr.grad), rel(outs[False], rr.grad), rel(outs[True], outs[False])
+    print("one-pass %.3e two-pass %.3e one-pass vs two-pass %.3e; resident clusters %d" % (e1, e2, e12, L.load().pcgan_norm_bwd_fused_active_clusters()))
+    assert e1 < 4e-3 and e2 < 4e-3 and e12 < 2e-3
+    # shapes that do not qualify fall back to the two passes
+    a2 = ops._bwd_args(gbuf, gy_pad, rbuf, Geom(N, H, H, C, 0), dx=dx, dx_pad=gp.pad, **dict(kw, affine=1))
+    assert L.load().pcgan_norm_bwd_fused_supported(ctypes.byref(a2)) == 0

@@ -106,12 +106,12 @@ def test_siamese_training_step_gradients_and_update():
     assert abs(float(loss2) - lref2) < 3e-2 * abs(lref2)
 
 
-def _models(B, S, seeds, **flags):
+def _models(B, S, seeds, n_blocks=6, fine_e=64, **flags):
     noisy = bool(flags.get("noisy", False))
     sds = [O.make_state_dict(k, s, device=DEV, requires_grad=rg) for k, s, rg in
-           ((O.generator_keys(n_blocks=6), seeds[0], True), (O.discriminator_keys(), seeds[1], True),
+           ((O.generator_keys(n_blocks=n_blocks), seeds[0], True), (O.discriminator_keys(), seeds[1], True),
             (O.encoder_keys(noisy=noisy), seeds[2], flags.get("lr_E", 0.0) > 0))]
-    opt = default_options(batchSize=B, gpu_ids=[0], fineSize=S, loadSize=S, fineSize_E=64, which_model_netG="resnet_6blocks", **flags)
+    opt = default_options(batchSize=B, gpu_ids=[0], fineSize=S, loadSize=S, fineSize_E=fine_e, which_model_netG="resnet_%dblocks" % n_blocks, **flags)
     model = WSGANEmbModel()
     model.initialize(opt)
     model.setup(opt)
@@ -120,13 +120,16 @@ def _models(B, S, seeds, **flags):
     return model, sds
 
 
-def test_bayesian_noisy_step_matches_oracle():
-    B, S, T, p = 4, 64, 2, 0.2
-    model, sds = _models(B, S, (61, 62, 63), bayesian=True, noisy=True, noisy_var_type="ae", bnn_dropout=p, bnn_T=T)
+@pytest.mark.parametrize("B,S,T,nb,fe", [(4, 64, 2, 6, 64), (8, 128, 10, 9, 224)], ids=["small_T2", "config4_T10_E224"])
+def test_bayesian_noisy_step_matches_oracle(B, S, T, nb, fe):
+    """BASELINE configs[3]: --bayesian true --noisy true --noisy_var_type ae --bnn_dropout 0.2; the second case runs it with
+    the reference's T = 10 Monte-Carlo passes, the 9-block generator and the encoder at 224 x 224."""
+    p = 0.2
+    model, sds = _models(B, S, (61, 62, 63), n_blocks=nb, fine_e=fe, bayesian=True, noisy=True, noisy_var_type="ae", bnn_dropout=p, bnn_T=T)
     masks = _masks(B, p, True, 3 * T, 9)
     g = torch.Generator().manual_seed(10)
     eps = [torch.randn(B, 1, 1, 1, generator=g) for _ in range(2)]
-    oracle = O.WSGANEmbOracle(*sds, n_blocks=6, fine_size_e=64, bayesian=True, noisy=True, noisy_var_type="ae", bnn_T=T, dropout=True,
+    oracle = O.WSGANEmbOracle(*sds, n_blocks=nb, fine_size_e=fe, bayesian=True, noisy=True, noisy_var_type="ae", bnn_T=T, dropout=True,
                               drop_masks=[m.clone() for m in masks], eps_queue=[e.clone() for e in eps])
     model.netE.module.dropout_masks = [m.clone() for m in masks]
     NW.NOISE_QUEUE[:] = [e.clone() for e in eps]

@@ -100,7 +100,7 @@ def test_variant_flags_step_losses():
 
 @pytest.mark.skipif(os.environ.get("PCGAN_SKIP_TRAJ") == "1", reason="trajectory test disabled")
 def test_loss_trajectories_200_steps():
-    steps, B = 200, 16
+    steps, B = 200, int(os.environ.get("PCGAN_TRAJ_BATCH", "64"))      # BASELINE configs[2]: 64 pairs per GPU
     model, oracle = build_pair(B)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -205,7 +205,7 @@ def test_step_at_256_and_odd_batch():
     for net, sd in zip((model.netG, model.netD, model.netE), sds):
         net.module.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
     oracle = O.WSGANEmbOracle(*sds)
-    for B, S, seed in ((2, 256, 900), (3, 128, 901)):
+    for B, S, seed in ((2, 256, 900), (3, 128, 901), (32, 256, 902)):      # the last one: BASELINE configs[4] as quoted
         a, b, label = O.synthetic_batch(B, S, seed, device=DEV)
         model.set_input({"A": a, "B": b, "label": label})
         model.optimize_parameters()
@@ -214,7 +214,9 @@ def test_step_at_256_and_odd_batch():
         print("B=%d S=%d:" % (B, S), {k: "%.5f/%.5f" % (got[k], want[k]) for k in KEYS})
         assert tuple(model.fake_B.shape) == (B, 3, S, S)
         for k in KEYS:
-            if k == "z_rec":    # ~1e-3 of loss_G: the squared difference of two ~0.05 outputs of a random-init bf16 encoder whose
+            if k == "z_rec" and B > 3:
+                assert 0.0 <= got[k] < 10 * want[k] + 1e-3
+            elif k == "z_rec":    # ~1e-3 of loss_G: the squared difference of two ~0.05 outputs of a random-init bf16 encoder whose
                 # BatchNorms see 2-3 samples; it moves by several 1e-3 from run to run (atomics order): bounded, not matched
                 assert 0.0 <= got[k] < 2e-2, (B, S, k, got[k], want[k])
             else:
