@@ -424,8 +424,16 @@ def main():
         if not args.no_cpu_baseline and world == 1 and args.workload == "c128":
             line["cpu_baseline"] = cpu_baseline(S)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # the captured step holds NCCL work: drop the graphs and leave without tearing the communicator down (a
+        # destroy_process_group with captured collectives alive can block forever)
+        if run.model is not None:
+            run.model._graphs.clear()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -124,6 +124,8 @@ def _net_setup(ctx, inputs, output):
     ctx.key = key
     ctx.need_dx, ctx.need_dz = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     ctx.need_w = any(p.requires_grad for p in params)
+    if ctx.need_w:
+        ctx.lease.prog.bank.pending += 1      # one more weight-gradient sweep to come (WeightBank.begin_backward)
     ctx.n_params, ctx.z_shape = len(params), z.shape
     ctx.save_for_backward(output)
 

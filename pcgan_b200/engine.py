@@ -136,6 +136,7 @@ class ConvRT:
             g.run(dybuf, xbuf, packed)
         if deferred:
             self.bank.dirty = True
+            self.bank.layer_done(self)
             return
         if self.weight.grad is None:
             self.weight.grad = torch.zeros_like(self.weight)
@@ -155,8 +156,13 @@ class WeightBank:
         self.deferred, self.dirty = False, False
         self._gather = None          # (pointer signature, table, count, max_n)
         self._versions = None
-        self._scatter = None
+        self._scatter = {}           # bucket (or None = all) -> (pointer signature, table, count, max_n)
         self._arena = None
+        # overlap of the gradient all-reduce with the backward sweep (pcgan_b200.dist.GradSync): `pending` counts the
+        # forward calls of this program whose weight-gradient backward is still to come; during the LAST of them every
+        # bucket of the flat gradient buffer is scattered and handed to the collective as soon as its layers are done
+        self.sync, self.pending, self.final = None, 0, False
+        self._left, self._flushed = {}, set()
 
     # ------------------------------------------------------------ operands
     def ensure_packed(self):
@@ -197,25 +203,68 @@ class WeightBank:
         if self.deferred:
             self._arena.zero_()
             self.dirty = False
+        # `pending` is NOT reset here: the forward calls of the update may already have run (the generator's do, in
+        # WSGANEmbModel.forward()); flush_wgrad() resets it at the end of the update
+        self.final = False
+        self._flushed = set()
 
-    def flush_wgrad(self):
-        """Scatter-accumulate the packed gradients of every trainable convolution into its weight.grad."""
-        if not (self.deferred and self.dirty):
+    def attach_sync(self, sync):
+        """sync: the GradSync whose flat buffer holds the .grad views of this program's parameters (None: no overlap)."""
+        self.sync = sync
+
+    def begin_backward(self):
+        """Called by the program at the start of a backward sweep that produces weight gradients."""
+        self.pending -= 1
+        self.final = bool(self.deferred and self.sync is not None and self.pending == 0 and self.sync.world_size() > 1)
+        if self.final:
+            self._left = {}
+            for c in self._trainable:
+                if c.weight.requires_grad:
+                    b = self.sync.bucket_of[id(c.weight)]
+                    self._left[b] = self._left.get(b, 0) + 1
+
+    def layer_done(self, conv):
+        """The weight gradient of `conv` has been launched; in the final sweep, a bucket whose layers are all done is
+        scattered into the flat buffer and its all-reduce starts while the sweep continues."""
+        if not self.final:
             return
-        convs = [c for c in self._trainable if c.weight.requires_grad]
+        b = self.sync.bucket_of[id(conv.weight)]
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            self._flush(b)
+            self.sync.bucket_ready(b)
+
+    def _flush(self, bucket):
+        live = [c for c in self._trainable if c.weight.requires_grad]
+        if bucket is not None:
+            convs = [c for c in live if self.sync.bucket_of[id(c.weight)] == bucket]
+            self._flushed.add(bucket)
+        elif self._flushed:      # what the buckets of the final sweep have not scattered already
+            convs = [c for c in live if self.sync.bucket_of[id(c.weight)] not in self._flushed]
+        else:
+            convs = live
         if not convs:
-            self.dirty = False
             return
         for c in convs:
             if c.weight.grad is None:
                 c.weight.grad = torch.zeros_like(c.weight)
         items = [(c.wgrad[2], c.wgrad[1], c.weight.grad) for c in convs]
         sig = tuple(t.data_ptr() for it in items for t in it)
-        if self._scatter is None or self._scatter[0] != sig:
+        key = bucket if bucket is not None else ("rest", tuple(sorted(self._flushed)))
+        cached = self._scatter.get(key)
+        if cached is None or cached[0] != sig:
             table, max_n = ops.batch_table(items, self.dev)
-            self._scatter = (sig, table, len(items), max_n)
-        _, table, count, max_n = self._scatter
+            cached = self._scatter[key] = (sig, table, len(items), max_n)
+        _, table, count, max_n = cached
         ops.scatter_f32_batched(table, count, max_n, accumulate=True)
+
+    def flush_wgrad(self):
+        """Scatter-accumulate the packed gradients of every trainable convolution (that no bucket has flushed yet) into
+        its weight.grad."""
+        self.pending, self.final = 0, False
+        if not (self.deferred and self.dirty):
+            return
+        self._flush(None)
         self.dirty = False
 
 

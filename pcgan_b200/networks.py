@@ -197,14 +197,22 @@ class _GenProgram:
         R, Z = L.ACT_RELU, L.ACT_NONE
         self.bank.ensure_packed()
         ws.sums_arena.zero()
+        if need_w:
+            self.bank.begin_backward()
+            # biases in front of an affine-less InstanceNorm have exactly zero gradient (SURVEY appendix A.7)
+            for c in self.convs[:-1]:
+                if c.bias is not None and c.bias.grad is None:
+                    c.bias.grad = torch.zeros_like(c.bias)
         # head: d(pre-tanh) = dout * (1 - out^2)
         dyh = sc.get(self.g_dyh)
         ops.pack_nchw(dout, dyh, self.g_dyh, mul_out=out, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO)
         if need_w:
-            self.head.backward_weight(dyh, ws.u2)
+            # every non-convolution gradient of a layer is in place before the layer's weight gradient is launched: that
+            # launch may complete a bucket of the gradient all-reduce (WeightBank.layer_done)
             hs = ws.head_sums.t
             ops.norm_bwd_reduce(dyh, 6, dyh, self.g_dyh, sums=hs, count=0.0)
             accumulate_grad(self.head.bias, hs[0, : self.mod.output_nc, 0])
+            self.head.backward_weight(dyh, ws.u2)
         dfull = sc.get(self.g_u2full)
         self.head.backward_data(dyh, dfull)
         # up2 unit; the reflect-pad fold of the head's data gradient happens while it is read
@@ -276,11 +284,6 @@ class _GenProgram:
             else:
                 dx = torch.empty(N, nc, S, S, device=self.dev)
                 ops.unpack_resize_bwd(gx, Geom(N, S, S, 8, 0), dx)
-        if need_w:
-            # biases in front of an affine-less InstanceNorm have exactly zero gradient (SURVEY appendix A.7)
-            for c in self.convs[:-1]:
-                if c.bias is not None and c.bias.grad is None:
-                    c.bias.grad = torch.zeros_like(c.bias)
         return dx, dz
 
 
@@ -435,16 +438,18 @@ class _DiscProgram:
         m, N, sc = self.mod.model, self.N, self.scratch
         self.bank.ensure_packed()
         ws.sums_arena.zero()
+        if need_w:
+            self.bank.begin_backward()
         dyh = sc.get(self.g_dyh)
         if self.mod.use_sigmoid:
             ops.pack_nchw(dout, dyh, self.g_dyh, mul_out=out, mul_kind=L.ACT_SIGMOID, halo=L.HALO_ZERO)
         else:
             ops.pack_nchw(dout, dyh, self.g_dyh, halo=L.HALO_ZERO)
         if need_w:
-            self.head.backward_weight(dyh, ws.y[-1])
             hs = ws.head_sums.t
             ops.norm_bwd_reduce(dyh, 2, dyh, self.g_dyh, sums=hs, count=0.0)
-            accumulate_grad(self.head.bias, hs[0, :1, 0])
+            accumulate_grad(self.head.bias, hs[0, :1, 0])      # before the layer's weight gradient (see _GenProgram.backward)
+            self.head.backward_weight(dyh, ws.y[-1])
         g = sc.get(self.g_r[-1], "g%d" % (len(self.sizes) - 1))
         self.head.backward_data(dyh, g)
         for li in range(len(self.sizes) - 1, 0, -1):

@@ -73,6 +73,22 @@ def str2list(v):
     return list(ast.literal_eval(v)) if v else []
 
 
+def param_layers(net):
+    """The parameters of `net` grouped into layers in forward order: a new layer starts at every convolution, the
+    parameters of what follows it (its BatchNorm) belong to it.  Gradient buckets are unions of such layers: the backward
+    sweep produces a layer's non-convolution gradients before it launches the layer's weight gradient."""
+    layers = []
+    for m in net.modules():
+        own = list(m.parameters(recurse=False))
+        if not own:
+            continue
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)) or not layers:
+            layers.append(own)
+        else:
+            layers[-1].extend(own)
+    return layers
+
+
 def _dist_ready():
     return dist.is_available() and dist.is_initialized()
 
@@ -299,8 +315,8 @@ class WSGANEmbModel(BaseModel):
             self.optimizer_D = FusedAdam(self.netD.parameters(), lr=lr, **adam_kw)
             self.optimizers = [self.optimizer_G, self.optimizer_D]
             # one process per GPU: flat gradient buffers, averaged over ranks with one NCCL all-reduce per network
-            self.sync_G = GradSync(list(self.netG.parameters()))
-            self.sync_D = GradSync(list(self.netD.parameters()))
+            self.sync_G = GradSync(list(self.netG.parameters()), layers=param_layers(self.netG))
+            self.sync_D = GradSync(list(self.netD.parameters()), layers=param_layers(self.netD))
             # weight gradients accumulate in packed form over the backward sweeps of an update and reach .grad in one launch
             for net in (self.netG, self.netD):
                 self._unwrap(net).defer_wgrad = True
@@ -535,22 +551,38 @@ class WSGANEmbModel(BaseModel):
         else:
             self.loss_z_rec = 0.0
 
-    def update_D(self):
+    def _attach(self, net, sync):
+        """hand the network's programs the GradSync whose buckets their backward sweeps complete"""
+        for prog in self._unwrap(net)._programs.values():
+            prog.bank.attach_sync(sync)
+
+    def _grads_D(self):
+        """zero_grad + backward_D; the gradient all-reduce is started bucket by bucket during the sweep, not waited for"""
         self.set_requires_grad(self.netD, True)
         self.sync_D.zero()                 # optimizer_D.zero_grad()
         self._unwrap(self.netD).zero_wgrad()
+        self._attach(self.netD, self.sync_D)
         self.backward_D()
         self._unwrap(self.netD).flush_wgrad()
-        self.sync_D.all_reduce()
-        self.optimizer_D.step()
+        self.sync_D.start()
 
-    def update_G(self):
+    def _grads_G(self):
         self.set_requires_grad(self.netD, False)
         self.sync_G.zero()                 # optimizer_G.zero_grad()
         self._unwrap(self.netG).zero_wgrad()
+        self._attach(self.netG, self.sync_G)
         self.backward_G()
         self._unwrap(self.netG).flush_wgrad()
-        self.sync_G.all_reduce()
+        self.sync_G.start()
+
+    def update_D(self):
+        self._grads_D()
+        self.sync_D.finish()
+        self.optimizer_D.step()
+
+    def update_G(self):
+        self._grads_G()
+        self.sync_G.finish()
         self.optimizer_G.step()
 
     def update_G_and_E(self):
@@ -575,20 +607,30 @@ class WSGANEmbModel(BaseModel):
             self.optimizer_G.step()
 
     def _step(self):
+        """optimize_parameters (:478-484).  update_D reads fake_B (made by forward(), before G's update) and netD only, so
+        G's optimizer step commutes with D's backward: the sweeps of both updates are enqueued first, G's gradient
+        all-reduce (started bucket by bucket inside its own sweep) runs under D's forward / backward, and D's under G's
+        Adam step; each optimizer waits only for its own collective."""
         self.forward()
         if self.opt.lr_E > 0.0:
             self.update_G_and_E()
-        else:
-            self.update_G()
-        self.update_D()
+            self.update_D()
+            return
+        self._grads_G()
+        self._grads_D()
+        self.sync_G.finish()
+        self.optimizer_G.step()
+        self.sync_D.finish()
+        self.optimizer_D.step()
 
-    # The step as three collective-free segments (multi-GPU graph mode): the two gradient all-reduces run between
-    # them as ordinary NCCL calls, so no collective is ever part of a captured graph.
+    # Fallback (--cuda_graph_segments true): the step as three collective-free graphs with the two gradient all-reduces
+    # between them as ordinary NCCL calls, for NCCL builds whose collectives cannot be captured.
     def _seg_forward_backward_G(self):
         self.forward()
         self.set_requires_grad(self.netD, False)
         self.sync_G.zero()
         self._unwrap(self.netG).zero_wgrad()
+        self._attach(self.netG, None)
         self.backward_G()
         self._unwrap(self.netG).flush_wgrad()
 
@@ -597,6 +639,7 @@ class WSGANEmbModel(BaseModel):
         self.set_requires_grad(self.netD, True)
         self.sync_D.zero()
         self._unwrap(self.netD).zero_wgrad()
+        self._attach(self.netD, None)
         self.backward_D()
         self._unwrap(self.netD).flush_wgrad()
 
@@ -613,7 +656,8 @@ class WSGANEmbModel(BaseModel):
     def optimize_parameters(self):
         """wsgan_emb_model.py:478-484.  With --cuda_graph the step is captured after a few eager steps (plans built,
         workspaces pooled, Adam state allocated) and replayed from then on; one capture per batch shape.  On one GPU
-        the whole step is one graph; with several ranks it is three graphs with the NCCL all-reduces between them."""
+        The whole step, including the bucketed NCCL all-reduces of a multi-rank job, is ONE graph (captured in thread-local
+        mode: NCCL's watchdog thread polls events while the capture is open)."""
         if not self.use_graph:
             return self._step()
         key = (tuple(self.real_A.shape), tuple(self.real_B.shape))
@@ -637,12 +681,10 @@ class WSGANEmbModel(BaseModel):
             cur.wait_stream(self._side)
             return
         torch.cuda.synchronize()
-        segmented = getattr(self.opt, "cuda_graph_segments", None)
-        if segmented is None:
-            segmented = self.sync_G.world_size() > 1
+        segmented = bool(getattr(self.opt, "cuda_graph_segments", None))
         if not segmented:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self._side):
+            with torch.cuda.graph(g, stream=self._side, capture_error_mode="thread_local"):
                 self._step()
             self._graphs[key] = g
             g.replay()      # the capture itself executes nothing: run the step that was asked for
