@@ -180,7 +180,7 @@ class StepRunner:
         if self.kind == "siamese":
             from pcgan_b200 import siamese as SI
             self.net = SI.get_model(gpu_ids=[local])
-            self.trainer = SI.EloTrainer(self.net, lr=2e-4)
+            self.trainer = SI.EloTrainer(self.net, lr=2e-4, cuda_graph=not args.no_graph)
             self.model, self.loss = None, None
             self.n_losses = 1
             return
@@ -193,11 +193,13 @@ class StepRunner:
 
     @property
     def use_graph(self):
-        return bool(self.model is not None and self.model.use_graph)
+        return bool(self.model.use_graph if self.model is not None else self.trainer.use_graph)
 
     def set_graph(self, on):
         if self.model is not None:
             self.model.use_graph = on
+        else:
+            self.trainer.use_graph = on
 
     def step(self, batch):
         if self.model is not None:
@@ -280,7 +282,7 @@ def main():
 
     torch.manual_seed(1234 + rank)
     run = StepRunner(args, dev, local)
-    W_eff = W + (4 if run.use_graph else 0)   # graph mode: 3 eager steps + the capture step come before the W replayed warm-ups
+    W_eff = W + ((4 if run.model is not None else 3) if run.use_graph else 0)   # graph mode: 3 eager steps + the capture step come before the W replayed warm-ups
 
     # synthetic UTKFace-shaped pool in pinned host memory; distinct batches so nothing is cached
     pool = 4

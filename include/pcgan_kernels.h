@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 13
+#define PCGAN_ABI_VERSION 14
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -337,16 +337,27 @@ int pcgan_norm_bwd_fused_supported(const pcgan_norm_bwd_args* a);
 int pcgan_norm_bwd_fused(const pcgan_norm_bwd_args* a, pcgan_stream_t stream);
 int pcgan_norm_bwd_fused_active_clusters(void);   /* diagnostic: resident clusters (cudaOccupancyMaxActiveClusters), -1 before the first launch */
 
-/* 3x3 stride-2 pad-1 max pooling on padded NHWC bf16 (resnet.py:137); idx keeps the
- * window position (0..8) of the maximum for the backward pass. */
+/* 3x3 stride-2 max pooling on padded NHWC bf16, pooling padding pool_pad = 1 (nn.MaxPool2d(3, 2, 1), resnet.py:137) or
+ * 0 (nn.MaxPool2d(3, 2), the AlexNet feature extractor, networks.py:1224-1236); idx keeps the window position (0..8)
+ * of the maximum for the backward pass. */
 typedef struct {
   const void* x; int32_t x_pad; void* y; int32_t y_pad; uint8_t* idx;
-  int32_t n, h, w, c; /* input geometry; output is ceil(h/2) x ceil(w/2) */
+  int32_t n, h, w, c; /* input geometry; output is floor((h + 2*pool_pad - 3) / 2) + 1 squared */
+  int32_t pool_pad;
 } pcgan_maxpool_args;
 int pcgan_maxpool3x3s2_fwd(const pcgan_maxpool_args* a, pcgan_stream_t stream);
 /* dx (input geometry, pad x_pad, zero halo) from dy (output geometry, pad y_pad). */
 int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint8_t* idx, void* dx, int32_t dx_pad,
-                           int32_t n, int32_t h, int32_t w, int32_t c, pcgan_stream_t stream);
+                           int32_t n, int32_t h, int32_t w, int32_t c, int32_t pool_pad, pcgan_stream_t stream);
+
+/* Backward of an activation fused into a convolution epilogue, from the sign of the stored output y:
+ * dx = y > 0 ? dy : slope * dy (nn.ReLU: slope 0; networks.py:1223-1235).  Any channel count that is a multiple of 8. */
+int pcgan_act_bwd(const void* dy, int32_t dy_pad, const void* y, int32_t y_pad, void* dx, int32_t dx_pad,
+                  int32_t n, int32_t h, int32_t w, int32_t c, float slope, pcgan_stream_t stream);
+/* to_f32 = 1: interior of a padded NHWC bf16 buffer -> contiguous NHWC fp32 (the feature map a torch loss consumes);
+ * to_f32 = 0: the reverse (its gradient). */
+int pcgan_nhwc_cast(const void* src, void* dst, int32_t pad, int32_t n, int32_t h, int32_t w, int32_t c, int32_t to_f32,
+                    pcgan_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Losses: vectorised, coalesced reductions (GANLoss networks.py:386-420 ->

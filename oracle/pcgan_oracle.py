@@ -104,6 +104,15 @@ def encoder_keys(cnn_dim=(32, 1), noisy=False):
     return k
 
 
+def alexnet_keys():
+    """state_dict layout of AlexNetFeature (models/networks.py:1218-1240): name -> shape."""
+    k = OrderedDict()
+    for idx, (co, ci, ks) in ((0, (64, 3, 11)), (3, (192, 64, 5)), (6, (384, 192, 3)), (8, (256, 384, 3)), (10, (256, 256, 3))):
+        k["features.%d.weight" % idx] = (co, ci, ks, ks)
+        k["features.%d.bias" % idx] = (co,)
+    return k
+
+
 def fill_state_dict_(sd, seed, bias_std=0.02):
     """Deterministic fill in key order, in the spirit of init_weights('normal') (models/networks.py:72-93):
     conv weights ~ N(0, 0.02), norm weights ~ N(1, 0.02); biases get N(0, bias_std) (the reference zeroes them;
@@ -327,6 +336,18 @@ def encoder_forward(sd, x, cnn_dim=(32, 1), cnn_relu_slope=0.7, noisy=False, dro
     return y
 
 
+def alexnet_forward(sd, x):
+    """AlexNetFeature.forward with pooling 'None' (models/networks.py:1218-1248): the torchvision AlexNet feature stack."""
+    h = F.relu(F.conv2d(x, sd["features.0.weight"], sd["features.0.bias"], stride=4, padding=2))
+    h = F.max_pool2d(h, 3, 2)
+    h = F.relu(F.conv2d(h, sd["features.3.weight"], sd["features.3.bias"], padding=2))
+    h = F.max_pool2d(h, 3, 2)
+    h = F.relu(F.conv2d(h, sd["features.6.weight"], sd["features.6.bias"], padding=1))
+    h = F.relu(F.conv2d(h, sd["features.8.weight"], sd["features.8.bias"], padding=1))
+    h = F.relu(F.conv2d(h, sd["features.10.weight"], sd["features.10.bias"], padding=1))
+    return F.max_pool2d(h, 3, 2)
+
+
 def upsample2d(x, size):
     """util/util.py:111-117"""
     if size <= 0 or x.size(2) == size:
@@ -359,7 +380,8 @@ class WSGANEmbOracle:
     def __init__(self, sd_g, sd_d, sd_e, *, lr=2e-4, beta1=0.5, lambda_z=1.0, lambda_a=0.5, lambda_l1=0.0,
                  lambda_a_gan=0.0, fine_size_e=224, relabel_d=(0, 1, 0), emb_mean=0.0, emb_std=1.0, n_blocks=9,
                  n_layers_d=3, detach_fake_b=False, bayesian=False, noisy=False, noisy_var_type="", bnn_T=10,
-                 noisy_d=True, noisy_rec=True, dropout=False, drop_masks=None, eps_queue=None, use_real_a=False):
+                 noisy_d=True, noisy_rec=True, dropout=False, drop_masks=None, eps_queue=None, use_real_a=False,
+                 sd_ip=None, lambda_ip=0.0, fine_size_ip=224, ip_criterion="mse"):
         """bayesian / noisy / noisy_var_type / bnn_T / noisy_D / noisy_rec: the encoder modes of forward() (:218-240)
         and backward_G (:408-430).  Randomness is injected, never drawn: `drop_masks` is a list of Dropout2d masks
         [N, C] consumed in module order (dropout=True places them where the reference has nn.Dropout2d), `eps_queue`
@@ -379,6 +401,8 @@ class WSGANEmbOracle:
         self.mean, self.std = emb_mean, emb_std
         self.nb, self.nld, self.detach_fake_b = n_blocks, n_layers_d, detach_fake_b
         self.use_real_a = use_real_a     # --use_real_A (:309-322): D's real pairs are built from real_A
+        # identity-preserving loss (:130-135, 353-356, 393-396): AlexNet features of fake_B against those of real_A
+        self.ip, self.lip, self.fip, self.ip_crit = sd_ip, lambda_ip, fine_size_ip, ip_criterion
         self.losses = {}
 
     def _drop(self, t):
@@ -443,7 +467,7 @@ class WSGANEmbOracle:
         self.rec_a = generator_forward(self.g, src, self.emb_a, self.nb)
 
     def backward_g(self):
-        """WSGANEmbModel.backward_G (:371-437) with lambda_IP = 0."""
+        """WSGANEmbModel.backward_G (:371-437)."""
         for t in self.pd:
             t.requires_grad_(False)   # set_requires_grad(netD, False) (:458)
         self.opt_g.zero_grad()
@@ -454,6 +478,12 @@ class WSGANEmbOracle:
         if self.lag > 0:
             L["G_GAN_cycle"] = gan_loss(discriminator_forward(self.d, self.rec_a, self.emb_a, self.nld), True) * self.lag
             total = total + L["G_GAN_cycle"]
+        if self.lip > 0:
+            with torch.no_grad():
+                feat_a = alexnet_forward(self.ip, upsample2d(self.real_a, self.fip))
+            feat_f = alexnet_forward(self.ip, upsample2d(self.fake_b, self.fip))
+            L["G_IP"] = (F.mse_loss if self.ip_crit == "mse" else F.l1_loss)(feat_f, feat_a) * self.lip
+            total = total + L["G_IP"]
         if self.l1 > 0:
             L["G_L1"] = F.l1_loss(self.fake_b, self.real_a) * self.l1
             total = total + L["G_L1"]

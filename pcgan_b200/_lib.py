@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -102,7 +102,7 @@ class NormBwdArgs(C.Structure):
 
 class MaxpoolArgs(C.Structure):
     _fields_ = [("x", vp), ("x_pad", i32), ("y", vp), ("y_pad", i32), ("idx", vp),
-                ("n", i32), ("h", i32), ("w", i32), ("c", i32)]
+                ("n", i32), ("h", i32), ("w", i32), ("c", i32), ("pool_pad", i32)]
 
 
 class LossArgs(C.Structure):
@@ -148,7 +148,9 @@ SYMBOLS = {
     "pcgan_norm_bwd_fused": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
     "pcgan_norm_bwd_fused_active_clusters": (C.c_int, []),
     "pcgan_maxpool3x3s2_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), vp]),
-    "pcgan_maxpool3x3s2_bwd": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "pcgan_maxpool3x3s2_bwd": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "pcgan_act_bwd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "pcgan_nhwc_cast": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "pcgan_loss": (C.c_int, [C.POINTER(LossArgs), vp]),
     "pcgan_adam": (C.c_int, [vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, vp]),
     "pcgan_adam_batched": (C.c_int, [vp, i32, i64, vp, C.c_double, C.c_double, C.c_double, vp, vp]),

@@ -136,11 +136,12 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
         off = u0 - (k - 1) - o + dyg.pad
         sp = plan_packed(dyg, k, k, 1, off, cin, hu, wu, out, note=note)
         return [(sp, wmap_packed(w_shape, cin, k, k, dyg.c, sp.b_k // k, flip=True, swap=True))]
-    # stride 2: input row iy = 2u + py receives taps r with (py + cp - r) even from dY row u + (py + cp - r)/2
-    assert stride == 2 and dyg.c >= 64 and dyg.c == cout and not full_padded
+    # stride st: input row iy = st*u + py receives the taps r with (py + cp - r) a multiple of st from dY row u + (py + cp - r)/st
+    st = stride
+    assert st in (2, 4) and dyg.c >= 64 and dyg.c == cout and not full_padded
     plans = []
-    reach = max(abs((p_ + cp - r) // 2) for p_ in range(2) for r in range(k) if (p_ + cp - r) % 2 == 0) if k > 1 else 0
-    if cin <= 4 and xg.c == 8 and 2 <= k <= 8 and dyg.pad >= max(reach, 1) and out.sc == 1:
+    reach = max(abs((p_ + cp - r) // st) for p_ in range(st) for r in range(k) if (p_ + cp - r) % st == 0) if k > 1 else 0
+    if st == 2 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and dyg.pad >= max(reach, 1) and out.sc == 1:
         # gradient towards a 3/4-channel image through a strided convolution (encoder stem, resnet.py:134): one
         # shift-sum launch per sub-pixel phase over the zero-haloed dY grid
         P = dyg.pad
@@ -157,20 +158,20 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
                                      out_shift=-dxo[0], note=note)
                 plans.append((sp, wmap_shift(w_shape, k, cout, dgrad=True, rows=rows, cols=cols)))
         return plans
-    for py in range(2):
-        for px in range(2):
+    for py in range(st):
+        for px in range(st):
             taps, wt = [], []
             for r in range(k):
-                if (py + cp - r) % 2:
+                if (py + cp - r) % st:
                     continue
                 for s in range(k):
-                    if (px + cp - s) % 2:
+                    if (px + cp - s) % st:
                         continue
                     kidx = len(taps)
-                    taps.append(((py + cp - r) // 2 + dyg.pad, (px + cp - s) // 2 + dyg.pad, kidx))
+                    taps.append(((py + cp - r) // st + dyg.pad, (px + cp - s) // st + dyg.pad, kidx))
                     wt.append((r, s, kidx))
-            hph, wph = _ceil(xg.h - py, 2), _ceil(xg.w - px, 2)
-            om = OutMap(base=out.base + py * out.sy + px * out.sx, sn=out.sn, sy=2 * out.sy, sx=2 * out.sx, sc=out.sc, dtype=out.dtype)
+            hph, wph = _ceil(xg.h - py, st), _ceil(xg.w - px, st)
+            om = OutMap(base=out.base + py * out.sy + px * out.sx, sn=out.sn, sy=st * out.sy, sx=st * out.sx, sc=out.sc, dtype=out.dtype)
             if not taps:  # k == 1: odd phases receive nothing; the caller pre-zeroes dX
                 continue
             sp = plan_box(dyg, taps, cout, cin, hph, wph, 1, om, note=note)

@@ -235,7 +235,8 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ gdst, float* __
 __global__ void maxpool_fwd_kernel(pcgan_maxpool_args a) {
   griddep_wait();
   griddep_launch();
-  const int ho = (a.h + 1) / 2, wo = (a.w + 1) / 2, cv = a.c >> 3;
+  const int pp = a.pool_pad;
+  const int ho = (a.h + 2 * pp - 3) / 2 + 1, wo = (a.w + 2 * pp - 3) / 2 + 1, cv = a.c >> 3;
   const int64_t total = static_cast<int64_t>(a.n) * ho * wo * cv;
   const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(a.x);
   __nv_bfloat16* yout = reinterpret_cast<__nv_bfloat16*>(a.y);
@@ -250,10 +251,10 @@ __global__ void maxpool_fwd_kernel(pcgan_maxpool_args a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 4; }
     for (int r = 0; r < 3; ++r) {
-      const int y = 2 * oy - 1 + r;
+      const int y = 2 * oy - pp + r;
       if (y < 0 || y >= a.h) continue;
       for (int s = 0; s < 3; ++s) {
-        const int x = 2 * ox - 1 + s;
+        const int x = 2 * ox - pp + s;
         if (x < 0 || x >= a.w) continue;
         float v[8];
         load8(xin + pix_off(n, y, x, a.h, a.w, a.c, a.x_pad) + c0, v);
@@ -272,10 +273,10 @@ __global__ void maxpool_fwd_kernel(pcgan_maxpool_args a) {
 }
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pad, const uint8_t* __restrict__ idx,
-                                   __nv_bfloat16* __restrict__ dx, int dx_pad, int n_, int h, int w, int c) {
+                                   __nv_bfloat16* __restrict__ dx, int dx_pad, int n_, int h, int w, int c, int pp) {
   griddep_wait();
   griddep_launch();
-  const int ho = (h + 1) / 2, wo = (w + 1) / 2, cv = c >> 3;
+  const int ho = (h + 2 * pp - 3) / 2 + 1, wo = (w + 2 * pp - 3) / 2 + 1, cv = c >> 3;
   const int64_t total = static_cast<int64_t>(n_) * h * w * cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c0 = static_cast<int>(i % cv) << 3;
@@ -286,13 +287,14 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int oy = y / 2; oy <= (y + 1) / 2; ++oy) {
+    // windows that contain (y, x): 2*o - pp <= coordinate <= 2*o - pp + 2
+    for (int oy = max(y + pp - 2, 0) / 2; oy <= (y + pp) / 2; ++oy) {
       if (oy >= ho) continue;
-      const int r = y - (2 * oy - 1);
+      const int r = y - (2 * oy - pp);
       if (r < 0 || r > 2) continue;
-      for (int ox = x / 2; ox <= (x + 1) / 2; ++ox) {
+      for (int ox = max(x + pp - 2, 0) / 2; ox <= (x + pp) / 2; ++ox) {
         if (ox >= wo) continue;
-        const int s = x - (2 * ox - 1);
+        const int s = x - (2 * ox - pp);
         if (s < 0 || s > 2) continue;
         const int pos = r * 3 + s;
         const uint2 packed = *reinterpret_cast<const uint2*>(idx + ((static_cast<int64_t>(n) * ho + oy) * wo + ox) * c + c0);
@@ -306,6 +308,66 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_
       }
     }
     store8(dx + pix_off(n, y, x, h, w, c, dx_pad) + c0, acc);
+  }
+}
+
+// ---------------------------------------------------- activation backward / cast
+// dx = dy where the stored post-activation output y is positive, else slope * dy (nn.ReLU / nn.LeakyReLU backward from
+// the sign of the output), any channel count that is a multiple of 8; the three buffers carry their own halo widths.
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_pad, const __nv_bfloat16* __restrict__ y, int y_pad,
+                               __nv_bfloat16* __restrict__ dx, int dx_pad, int n_, int h, int w, int c, float slope) {
+  griddep_wait();
+  griddep_launch();
+  const int cv = c >> 3;
+  const int64_t total = static_cast<int64_t>(n_) * h * w * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % w); q /= w;
+    const int yy = static_cast<int>(q % h);
+    const int n = static_cast<int>(q / h);
+    float g[8], o[8];
+    load8(dy + pix_off(n, yy, x, h, w, c, dy_pad) + c0, g);
+    load8(y + pix_off(n, yy, x, h, w, c, y_pad) + c0, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : g[j] * slope;
+    store8(dx + pix_off(n, yy, x, h, w, c, dx_pad) + c0, g);
+  }
+}
+
+// NHWC bf16 (padded) <-> contiguous NHWC fp32: the feature map a frozen network hands to a torch loss, and its gradient
+__global__ void nhwc_cast_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int pad, int n_, int h, int w, int c) {
+  griddep_wait();
+  griddep_launch();
+  const int cv = c >> 3;
+  const int64_t total = static_cast<int64_t>(n_) * h * w * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % w); q /= w;
+    const int yy = static_cast<int>(q % h);
+    const int n = static_cast<int>(q / h);
+    float v[8];
+    load8(src + pix_off(n, yy, x, h, w, c, pad) + c0, v);
+    float4* d = reinterpret_cast<float4*>(dst + i * 8);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+__global__ void nhwc_uncast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int pad, int n_, int h, int w, int c) {
+  griddep_wait();
+  griddep_launch();
+  const int cv = c >> 3;
+  const int64_t total = static_cast<int64_t>(n_) * h * w * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = static_cast<int>(i % cv) << 3;
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % w); q /= w;
+    const int yy = static_cast<int>(q % h);
+    const int n = static_cast<int>(q / h);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + i * 8)), b = __ldg(reinterpret_cast<const float4*>(src + i * 8) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    store8(dst + pix_off(n, yy, x, h, w, c, pad) + c0, v);
   }
 }
 
@@ -532,21 +594,49 @@ extern "C" int pcgan_maxpool3x3s2_fwd(const pcgan_maxpool_args* a, pcgan_stream_
   if (!a || !a->x || !a->y || !a->idx) return fail(PCGAN_ERR_INVALID, "maxpool: null argument");
   int rc = check_cvec(a->c, "maxpool");
   if (rc) return rc;
-  const int64_t total = static_cast<int64_t>(a->n) * ((a->h + 1) / 2) * ((a->w + 1) / 2) * (a->c / 8);
+  if (a->pool_pad != 0 && a->pool_pad != 1) return fail(PCGAN_ERR_INVALID, "maxpool: pool_pad must be 0 or 1");
+  if (a->h + 2 * a->pool_pad < 3 || a->w + 2 * a->pool_pad < 3) return fail(PCGAN_ERR_INVALID, "maxpool: image smaller than the window");
+  const int64_t total = static_cast<int64_t>(a->n) * ((a->h + 2 * a->pool_pad - 3) / 2 + 1) * ((a->w + 2 * a->pool_pad - 3) / 2 + 1) * (a->c / 8);
   PCGAN_CUDA_OK(launch_pdl(maxpool_fwd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, *a));
   PCGAN_LAUNCH_OK("maxpool_fwd_kernel");
   return PCGAN_OK;
 }
 
 extern "C" int pcgan_maxpool3x3s2_bwd(const void* dy, int32_t dy_pad, const uint8_t* idx, void* dx, int32_t dx_pad,
-                                      int32_t n, int32_t h, int32_t w, int32_t c, pcgan_stream_t s) {
+                                      int32_t n, int32_t h, int32_t w, int32_t c, int32_t pool_pad, pcgan_stream_t s) {
   if (!dy || !idx || !dx) return fail(PCGAN_ERR_INVALID, "maxpool_bwd: null argument");
+  if (pool_pad != 0 && pool_pad != 1) return fail(PCGAN_ERR_INVALID, "maxpool_bwd: pool_pad must be 0 or 1");
   int rc = check_cvec(c, "maxpool_bwd");
   if (rc) return rc;
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
   PCGAN_CUDA_OK(launch_pdl(maxpool_bwd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pad, idx,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dx), dx_pad, n, h, w, c));
+                                                                 reinterpret_cast<__nv_bfloat16*>(dx), dx_pad, n, h, w, c, pool_pad));
   PCGAN_LAUNCH_OK("maxpool_bwd_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_act_bwd(const void* dy, int32_t dy_pad, const void* y, int32_t y_pad, void* dx, int32_t dx_pad, int32_t n, int32_t h,
+                             int32_t w, int32_t c, float slope, pcgan_stream_t s) {
+  if (!dy || !y || !dx || n < 1 || h < 1 || w < 1) return fail(PCGAN_ERR_INVALID, "act_bwd: bad argument");
+  int rc = check_cvec(c, "act_bwd");
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
+  PCGAN_CUDA_OK(launch_pdl(act_bwd_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pad,
+                           reinterpret_cast<const __nv_bfloat16*>(y), y_pad, reinterpret_cast<__nv_bfloat16*>(dx), dx_pad, n, h, w, c, slope));
+  PCGAN_LAUNCH_OK("act_bwd_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_nhwc_cast(const void* src, void* dst, int32_t pad, int32_t n, int32_t h, int32_t w, int32_t c, int32_t to_f32, pcgan_stream_t s) {
+  if (!src || !dst || n < 1 || h < 1 || w < 1) return fail(PCGAN_ERR_INVALID, "nhwc_cast: bad argument");
+  int rc = check_cvec(c, "nhwc_cast");
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
+  if (to_f32) PCGAN_CUDA_OK(launch_pdl(nhwc_cast_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, reinterpret_cast<const __nv_bfloat16*>(src),
+                                       reinterpret_cast<float*>(dst), pad, n, h, w, c));
+  else PCGAN_CUDA_OK(launch_pdl(nhwc_uncast_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, reinterpret_cast<const float*>(src),
+                                reinterpret_cast<__nv_bfloat16*>(dst), pad, n, h, w, c));
+  PCGAN_LAUNCH_OK("nhwc_cast_kernel");
   return PCGAN_OK;
 }
 

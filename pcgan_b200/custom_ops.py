@@ -12,11 +12,21 @@ torch.library.register_autograd and shape inference with register_fake, so the o
     pcgan::upsample_bilinear_ac(x, size)                    util.upsample2d           (util/util.py:111-117)
   and their *_backward companions.
 
+Statefulness, stated plainly: the loss and resize operators are pure functions (torch.library.opcheck passes on them,
+tests/test_opcheck_gpu.py).  The three network operators are not: like an nn.Module in training mode they update the
+module's running statistics (and num_batches_tracked) in place, lease a pooled workspace that their backward gives back,
+and their backward accumulates parameter gradients in packed form that the program scatters into .grad at the end of the
+update instead of returning them through autograd.  torch.library accepts autograd formulas only for operators whose
+schema declares no mutation, so these side effects are NOT in the schemas (`mutates_args=()`): the operators are meant
+for eager execution and CUDA-graph capture, not for functionalising tracers (torch.compile would reorder or drop the
+buffer updates).  Leases live in per-thread tables, so concurrent calls from several threads do not cross.
+
 A network operator works on a whole network at once (one static program of kernel launches per input geometry) rather
 than on single layers: the per-layer state (padded NHWC buffers, statistics, plans) lives in the program's pooled
 workspace, which the forward leases and the backward gives back.  `key` identifies the module instance.
 """
 import itertools
+import threading
 import weakref
 from typing import List, Sequence, Tuple
 
@@ -28,7 +38,18 @@ from . import ops
 
 _MODULES = {}            # key -> weakref(module)
 _KEYS = itertools.count(1)
-_PENDING = {}            # key -> lease of the most recent forward (claimed by setup_context or released by the caller)
+
+
+class _PerThread(threading.local):
+    """key -> lease tables, one per thread: a forward and the setup_context / finish_forward that claims its lease run on
+    the same thread back to back, and a backward sets and reads its lease on the autograd worker it runs on, so calls of
+    one module from several threads cannot take each other's workspaces."""
+
+    def __init__(self):
+        self.pending, self.bwd = {}, {}
+
+
+_TLS = _PerThread()
 
 
 def register_module(mod) -> int:
@@ -68,13 +89,13 @@ class Lease:
 
 def finish_forward(key, out):
     """Called by the module right after its operator: a forward nobody will differentiate returns its workspace now."""
-    lease = _PENDING.pop(key, None)
+    lease = _TLS.pending.pop(key, None)
     if lease is not None and not (torch.is_grad_enabled() and out.requires_grad):
         lease.release()
 
 
 def _claim(ctx, key):
-    ctx.lease = _PENDING.pop(key)
+    ctx.lease = _TLS.pending.pop(key)
 
 
 def _after_backward(ctx):
@@ -92,7 +113,7 @@ def resnet_generator(x: Tensor, z: Tensor, params: Sequence[Tensor], key: int) -
     mod = _module(key)
     prog = mod._program(x.shape[0], x.shape[2])
     out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
-    _PENDING[key] = Lease(prog, ws)
+    _TLS.pending[key] = Lease(prog, ws)
     return out
 
 
@@ -103,7 +124,7 @@ def _(x, z, params, key):
 
 @torch.library.custom_op("pcgan::resnet_generator_backward", mutates_args=())
 def resnet_generator_backward(dout: Tensor, out: Tensor, key: int, need_dx: bool, need_dz: bool, need_w: bool) -> Tuple[Tensor, Tensor]:
-    lease = _BWD[key]
+    lease = _TLS.bwd[key]
     dx, dz = lease.prog.backward(lease.ws, out, dout.contiguous(), need_dx, need_w, need_dz)
     return (dx if dx is not None else _empty(dout)), (dz if dz is not None else _empty(dout))
 
@@ -115,7 +136,6 @@ def _(dout, out, key, need_dx, need_dz, need_w):
     return (out.new_empty((n, mod.input_nc_img, s, s)) if need_dx else out.new_empty(0)), (out.new_empty(n) if need_dz else out.new_empty(0))
 
 
-_BWD = {}   # key -> lease of the backward in flight (set by the autograd glue right before the backward operator runs)
 
 
 def _net_setup(ctx, inputs, output):
@@ -133,12 +153,14 @@ def _net_setup(ctx, inputs, output):
 def _net_backward(op):
     def backward(ctx, dout):
         (out,) = ctx.saved_tensors
-        _BWD[ctx.key] = ctx.lease
+        _TLS.bwd[ctx.key] = ctx.lease
         try:
             dx, dz = op(dout, out, ctx.key, ctx.need_dx, ctx.need_dz, ctx.need_w)
         finally:
-            _BWD.pop(ctx.key, None)
+            _TLS.bwd.pop(ctx.key, None)
         _after_backward(ctx)
+        # parameter gradients do not travel through autograd: the weight-gradient kernels accumulate them in packed form
+        # over all backward sweeps of an update and the program scatters them into .grad (WeightBank.flush_wgrad)
         return (dx if ctx.need_dx else None), (dz.view(ctx.z_shape) if ctx.need_dz else None), [None] * ctx.n_params, None
     return backward
 
@@ -152,7 +174,7 @@ def nlayer_discriminator(x: Tensor, z: Tensor, params: Sequence[Tensor], key: in
     mod = _module(key)
     prog = mod._program(x.shape[0], x.shape[2])
     out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
-    _PENDING[key] = Lease(prog, ws)
+    _TLS.pending[key] = Lease(prog, ws)
     return out
 
 
@@ -164,7 +186,7 @@ def _(x, z, params, key):
 
 @torch.library.custom_op("pcgan::nlayer_discriminator_backward", mutates_args=())
 def nlayer_discriminator_backward(dout: Tensor, out: Tensor, key: int, need_dx: bool, need_dz: bool, need_w: bool) -> Tuple[Tensor, Tensor]:
-    lease = _BWD[key]
+    lease = _TLS.bwd[key]
     dx, dz = lease.prog.backward(lease.ws, out, dout.contiguous(), need_dx, need_w, need_dz)
     return (dx if dx is not None else _empty(dout)), (dz if dz is not None else _empty(dout))
 
@@ -187,7 +209,7 @@ def siamese_feature(x: Tensor, params: Sequence[Tensor], key: int) -> Tuple[Tens
     mod = _module(key)
     prog = mod._program(x.shape[0], x.shape[2])
     outs, ws = prog.forward(x.contiguous().float())
-    _PENDING[key] = Lease(prog, ws)
+    _TLS.pending[key] = Lease(prog, ws)
     return outs[0], (outs[1] if len(outs) > 1 else _empty(x))
 
 
@@ -200,7 +222,7 @@ def _(x, params, key):
 @torch.library.custom_op("pcgan::siamese_feature_backward", mutates_args=())
 def siamese_feature_backward(gy: Tensor, glogvar: Tensor, key: int, need_dx: bool, need_w: bool) -> Tensor:
     """empty gy / glogvar = that head received no gradient"""
-    lease = _BWD[key]
+    lease = _TLS.bwd[key]
     gys = [gy if gy.numel() else None]
     if len(lease.prog.heads) > 1:
         gys.append(glogvar if glogvar.numel() else None)
@@ -227,16 +249,70 @@ def _enc_setup(ctx, inputs, output):
 
 def _enc_backward(ctx, gy, glv):
     e = torch.empty(0, device=ctx.dev)
-    _BWD[ctx.key] = ctx.lease
+    _TLS.bwd[ctx.key] = ctx.lease
     try:
         dx = siamese_feature_backward(gy if gy is not None else e, glv if glv is not None else e, ctx.key, ctx.need_dx, ctx.need_w)
     finally:
-        _BWD.pop(ctx.key, None)
+        _TLS.bwd.pop(ctx.key, None)
     _after_backward(ctx)
     return (dx if ctx.need_dx else None), [None] * ctx.n_params, None
 
 
 torch.library.register_autograd("pcgan::siamese_feature", _enc_backward, setup_context=_enc_setup)
+
+
+# ------------------------------------------------------------------- identity-preserving net
+@torch.library.custom_op("pcgan::alexnet_feature", mutates_args=())
+def alexnet_feature(x: Tensor, key: int) -> Tensor:
+    """AlexNetFeature.forward (models/networks.py:1242-1248), pooling 'None': [N, 3, S, S] -> [N, 256, h, h] (frozen)"""
+    mod = _module(key)
+    prog = mod._program(x.shape[0], x.shape[2])
+    out, ws = prog.forward(x.contiguous().float())
+    _TLS.pending[key] = Lease(prog, ws)
+    return out.contiguous()
+
+
+def _alex_side(s):
+    h = (s + 4 - 11) // 4 + 1
+    for _ in range(3):
+        h = (h - 3) // 2 + 1
+    return h
+
+
+@alexnet_feature.register_fake
+def _(x, key):
+    h = _alex_side(x.shape[2])
+    return x.new_empty((x.shape[0], 256, h, h), dtype=torch.float32)
+
+
+@torch.library.custom_op("pcgan::alexnet_feature_backward", mutates_args=())
+def alexnet_feature_backward(dfeat: Tensor, key: int, size: int) -> Tensor:
+    lease = _TLS.bwd[key]
+    return lease.prog.backward(lease.ws, dfeat)
+
+
+@alexnet_feature_backward.register_fake
+def _(dfeat, key, size):
+    return dfeat.new_empty((dfeat.shape[0], 3, size, size), dtype=torch.float32)
+
+
+def _alex_setup(ctx, inputs, output):
+    x, key = inputs
+    _claim(ctx, key)
+    ctx.key, ctx.size = key, x.shape[2]
+
+
+def _alex_backward(ctx, dfeat):
+    _TLS.bwd[ctx.key] = ctx.lease
+    try:
+        dx = alexnet_feature_backward(dfeat, ctx.key, ctx.size)
+    finally:
+        _TLS.bwd.pop(ctx.key, None)
+    _after_backward(ctx)
+    return dx, None
+
+
+torch.library.register_autograd("pcgan::alexnet_feature", _alex_backward, setup_context=_alex_setup)
 
 
 # --------------------------------------------------------------------------------- losses

@@ -20,6 +20,9 @@ from . import ops
 from .plan import Geom, OutMap, SLACK
 
 
+# PCGAN_BUCKET_OVERLAP=0: no bucket is handed to the collective inside the backward sweep; every bucket is issued (still
+# asynchronously) when the sweep has finished (measurement switch)
+BUCKET_OVERLAP = os.environ.get("PCGAN_BUCKET_OVERLAP", "1") != "0"
 PHASE_STREAMS = os.environ.get("PCGAN_PHASE_STREAMS", "0") != "0"    # launch the sub-pixel phases of a strided data gradient / transposed convolution on forked streams
 _SIDE = {}
 
@@ -215,7 +218,7 @@ class WeightBank:
     def begin_backward(self):
         """Called by the program at the start of a backward sweep that produces weight gradients."""
         self.pending -= 1
-        self.final = bool(self.deferred and self.sync is not None and self.pending == 0 and self.sync.world_size() > 1)
+        self.final = bool(BUCKET_OVERLAP and self.deferred and self.sync is not None and self.pending == 0 and self.sync.world_size() > 1)
         if self.final:
             self._left = {}
             for c in self._trainable:

@@ -1183,6 +1183,169 @@ def define_E(which_model_netE, input_nc=3, init_type="kaiming", pooling="max", c
     return init_net(net, init_type, gpu_ids)
 
 
+# ---------------------------------------------------------------------------------------
+# Identity-preserving network: AlexNetFeature (networks.py:1218-1255), define_IP (:179-193)
+# ---------------------------------------------------------------------------------------
+class _IPWorkspace:
+    pass
+
+
+class _IPProgram:
+    """AlexNet feature extractor (pooling 'None') at fixed (N, S): conv11x11 s4 p2 + ReLU, pool, conv5x5 p2 + ReLU, pool,
+    three 3x3 convolutions + ReLU, pool (nn.MaxPool2d(3, 2): no padding); frozen: forward and input gradient only.  The
+    ReLUs are fused into the convolution epilogues; their backward reads the sign of the stored outputs."""
+
+    def __init__(self, mod, N, S):
+        if (S + 4) % 4:
+            raise NotImplementedError("AlexNetFeature input side must be a multiple of 4 (got %d)" % S)
+        self.mod, self.N, self.S = mod, N, S
+        f = mod.features
+        dev = f[0].weight.device
+        self.dev = dev
+        G = Geom
+        h1 = (S + 4 - 11) // 4 + 1
+        p1, p2 = ops.pool_out(h1, 0), ops.pool_out(ops.pool_out(h1, 0), 0)
+        p3 = ops.pool_out(p2, 0)
+        self.h1, self.p1, self.p2, self.p3 = h1, p1, p2, p3
+        self.g_x0 = G(N, S, S, 8, 2)
+        self.g_r1, self.g_d1 = G(N, h1, h1, 64, 0), G(N, h1, h1, 64, 2)
+        self.g_p1, self.g_p1r = G(N, p1, p1, 64, 2), G(N, p1, p1, 64, 0)
+        self.g_r2, self.g_d2 = G(N, p1, p1, 192, 0), G(N, p1, p1, 192, 2)
+        self.g_p2, self.g_p2r = G(N, p2, p2, 192, 1), G(N, p2, p2, 192, 0)
+        self.g_y3, self.g_y3r = G(N, p2, p2, 384, 1), G(N, p2, p2, 384, 0)
+        self.g_y4, self.g_y4r = G(N, p2, p2, 256, 1), G(N, p2, p2, 256, 0)
+        self.g_r5 = G(N, p2, p2, 256, 0)
+        self.g_p3 = G(N, p3, p3, 256, 0)
+        R = dict(act=L.ACT_RELU, want_wgrad=False)
+        self.c1 = ConvRT("IP.features.0", f[0].weight, f[0].bias, self.g_x0, 4, 2, OutMap.nhwc(self.g_r1), dyg=self.g_d1,
+                         dx_out=OutMap.nhwc(G(N, S, S, 8, 0)), **R)
+        self.c2 = ConvRT("IP.features.3", f[3].weight, f[3].bias, self.g_p1, 1, 2, OutMap.nhwc(self.g_r2), dyg=self.g_d2,
+                         dx_out=OutMap.nhwc(self.g_p1r), **R)
+        self.c3 = ConvRT("IP.features.6", f[6].weight, f[6].bias, self.g_p2, 1, 1, OutMap.nhwc(self.g_y3), dyg=self.g_y3,
+                         dx_out=OutMap.nhwc(self.g_p2r), **R)
+        self.c4 = ConvRT("IP.features.8", f[8].weight, f[8].bias, self.g_y3, 1, 1, OutMap.nhwc(self.g_y4), dyg=self.g_y4,
+                         dx_out=OutMap.nhwc(self.g_y3r), **R)
+        self.c5 = ConvRT("IP.features.10", f[10].weight, f[10].bias, self.g_y4, 1, 1, OutMap.nhwc(self.g_r5), dyg=self.g_y4,
+                         dx_out=OutMap.nhwc(self.g_y4r), **R)
+        self.scratch = _Scratch(dev)
+        self.pool = Pool(lambda key: self._new_ws())
+        self.bank = WeightBank([self.c1, self.c2, self.c3, self.c4, self.c5], dev)
+
+    def _new_ws(self):
+        ws, dev = _IPWorkspace(), self.dev
+        z = lambda g: zeros_act(g, dev)
+        ws.x0, ws.r1, ws.p1, ws.r2, ws.p2 = z(self.g_x0), z(self.g_r1), z(self.g_p1), z(self.g_r2), z(self.g_p2)
+        ws.y3, ws.y4, ws.r5, ws.p3 = z(self.g_y3), z(self.g_y4), z(self.g_r5), z(self.g_p3)
+        ws.i1 = torch.zeros(self.g_p1r.numel, dtype=torch.uint8, device=dev)
+        ws.i2 = torch.zeros(self.g_p2r.numel, dtype=torch.uint8, device=dev)
+        ws.i3 = torch.zeros(self.g_p3.numel, dtype=torch.uint8, device=dev)
+        return ws
+
+    def forward(self, x):
+        ws = self.pool.take(0)
+        self.bank.ensure_packed()
+        ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
+        self.c1.forward(ws.x0, ws.r1)
+        ops.maxpool_fwd(ws.r1, self.g_r1, ws.p1, self.g_p1.pad, ws.i1, pool_pad=0)
+        self.c2.forward(ws.p1, ws.r2)
+        ops.maxpool_fwd(ws.r2, self.g_r2, ws.p2, self.g_p2.pad, ws.i2, pool_pad=0)
+        self.c3.forward(ws.p2, ws.y3)
+        self.c4.forward(ws.y3, ws.y4)
+        self.c5.forward(ws.y4, ws.r5)
+        ops.maxpool_fwd(ws.r5, self.g_r5, ws.p3, 0, ws.i3, pool_pad=0)
+        feat = torch.empty(self.N, self.p3, self.p3, 256, device=self.dev)
+        ops.nhwc_to_f32(ws.p3, self.g_p3, feat)
+        return feat.permute(0, 3, 1, 2), ws          # [N, 256, p3, p3] view of the NHWC feature map
+
+    def backward(self, ws, dfeat):
+        """dfeat: gradient of the [N, 256, p3, p3] feature map -> gradient of the input image [N, 3, S, S]."""
+        N, sc = self.N, self.scratch
+        self.bank.ensure_packed()
+        g3 = sc.get(self.g_p3, "g3")
+        ops.f32_to_nhwc(dfeat.permute(0, 2, 3, 1).contiguous().float(), g3, self.g_p3)
+        g = sc.get(self.g_r5, "gr5")
+        ops.maxpool_bwd(g3, 0, ws.i3, g, 0, N, self.p2, self.p2, 256, pool_pad=0)
+        dy = sc.get(self.g_y4, "dy5")
+        ops.act_bwd(g, 0, ws.r5, 0, dy, 1, self.g_r5)
+        g = sc.get(self.g_y4r, "g4")
+        self.c5.backward_data(dy, g)
+        dy = sc.get(self.g_y4, "dy4")
+        ops.act_bwd(g, 0, ws.y4, 1, dy, 1, self.g_y4r)
+        g = sc.get(self.g_y3r, "g3r")
+        self.c4.backward_data(dy, g)
+        dy = sc.get(self.g_y3, "dy3")
+        ops.act_bwd(g, 0, ws.y3, 1, dy, 1, self.g_y3r)
+        g = sc.get(self.g_p2r, "gp2")
+        self.c3.backward_data(dy, g)
+        gr = sc.get(self.g_r2, "gr2")
+        ops.maxpool_bwd(g, 0, ws.i2, gr, 0, N, self.p1, self.p1, 192, pool_pad=0)
+        dy = sc.get(self.g_d2, "dy2")
+        ops.act_bwd(gr, 0, ws.r2, 0, dy, 2, self.g_r2)
+        g = sc.get(self.g_p1r, "gp1")
+        self.c2.backward_data(dy, g)
+        gr = sc.get(self.g_r1, "gr1")
+        ops.maxpool_bwd(g, 0, ws.i1, gr, 0, N, self.h1, self.h1, 64, pool_pad=0)
+        dy = sc.get(self.g_d1, "dy1")
+        ops.act_bwd(gr, 0, ws.r1, 0, dy, 2, self.g_r1)
+        gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
+        self.c1.backward_data(dy, gx)
+        dx = torch.empty(N, 3, self.S, self.S, device=self.dev)
+        ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dx)
+        return dx
+
+
+class AlexNetFeature(nn.Module):
+    """Same constructor / forward / load_pretrained / state_dict keys (features.{0,3,6,8,10}.*) as
+    models/networks.py:1218-1255 with pooling 'None' (what define_IP builds); frozen: no weight gradients."""
+
+    def __init__(self, input_nc=3, pooling="None"):
+        super().__init__()
+        if input_nc != 3 or pooling not in ("None", None, ""):
+            raise NotImplementedError("pcgan_b200 AlexNetFeature: RGB input, pooling 'None' (the wsgan_emb configuration)")
+        self.pooling = pooling
+        I = nn.Identity
+        self.features = nn.Sequential(nn.Conv2d(3, 64, 11, stride=4, padding=2), I(), I(), nn.Conv2d(64, 192, 5, padding=2), I(), I(),
+                                      nn.Conv2d(192, 384, 3, padding=1), I(), nn.Conv2d(384, 256, 3, padding=1), I(),
+                                      nn.Conv2d(256, 256, 3, padding=1), I(), I())
+        self.feature_dim = 256
+        self._programs = {}
+        self._key = CO.register_module(self)
+
+    def _program(self, n, s):
+        k = (n, s, self.features[0].weight.device)
+        if k not in self._programs:
+            self._programs[k] = _IPProgram(self, n, s)
+        return self._programs[k]
+
+    def forward(self, x):
+        _require_cuda(x, "AlexNetFeature")
+        if x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise NotImplementedError("square RGB inputs")
+        out = torch.ops.pcgan.alexnet_feature(x, self._key)
+        CO.finish_forward(self._key, out)
+        return out
+
+    def load_pretrained(self, state_dict):
+        if isinstance(state_dict, str):
+            state_dict = torch.load(state_dict)
+        for key in list(state_dict.keys()):
+            if key.startswith("classifier"):
+                state_dict.pop(key)
+        self.load_state_dict(state_dict, strict=True)
+
+
+def define_IP(which_model_netIP, input_nc, gpu_ids=[]):
+    """networks.define_IP (networks.py:179-193): no weight initialisation here, the weights are loaded."""
+    if which_model_netIP != "alexnet":
+        raise NotImplementedError("Identity-preserving model [%s] is outside the wsgan_emb hot path (alexnet)" % which_model_netIP)
+    net = AlexNetFeature(input_nc=input_nc, pooling="None")
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.to(gpu_ids[0])
+        net = LocalDataParallel(net, gpu_ids)
+    return net
+
+
 class Normalize(nn.Module):
     """networks.py:2421-2439 as called by WSGANEmbModel: `mean or std` is truthy, so it is the identity."""
 

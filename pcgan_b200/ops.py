@@ -256,17 +256,42 @@ def norm_bwd(dy, dy_pad, x, xg, **kw):
     norm_bwd_apply(dy, dy_pad, x, xg, **kw)
 
 
-def maxpool_fwd(x, xg: Geom, y, y_pad, idx):
-    a = L.MaxpoolArgs(x=_ptr(x), x_pad=xg.pad, y=_ptr(y), y_pad=y_pad, idx=_ptr(idx), n=xg.n, h=xg.h, w=xg.w, c=xg.c)
+def pool_out(h, pool_pad=1):
+    """output side of the 3x3 stride-2 max pooling of an h x h map"""
+    return (h + 2 * pool_pad - 3) // 2 + 1
+
+
+def maxpool_fwd(x, xg: Geom, y, y_pad, idx, pool_pad=1):
+    a = L.MaxpoolArgs(x=_ptr(x), x_pad=xg.pad, y=_ptr(y), y_pad=y_pad, idx=_ptr(idx), n=xg.n, h=xg.h, w=xg.w, c=xg.c, pool_pad=pool_pad)
     _count()
     with _Timed("maxpool_fwd", xg.n * xg.h * xg.w * xg.c * 2 + xg.n * xg.h * xg.w * xg.c * 3 // 4):
         L.check(L.load().pcgan_maxpool3x3s2_fwd(C.byref(a), _stream()), "maxpool_fwd")
 
 
-def maxpool_bwd(dy, dy_pad, idx, dx, dx_pad, n, h, w, c):
+def maxpool_bwd(dy, dy_pad, idx, dx, dx_pad, n, h, w, c, pool_pad=1):
     _count()
     with _Timed("maxpool_bwd", n * h * w * c * 2 + n * h * w * c * 3 // 4):
-        L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, _stream()), "maxpool_bwd")
+        L.check(L.load().pcgan_maxpool3x3s2_bwd(_ptr(dy), dy_pad, _ptr(idx), _ptr(dx), dx_pad, n, h, w, c, pool_pad, _stream()), "maxpool_bwd")
+
+
+def act_bwd(dy, dy_pad, y, y_pad, dx, dx_pad, g: Geom, slope=0.0):
+    """dx = y > 0 ? dy : slope * dy over the interior of geometry g (the three buffers have their own halo widths)"""
+    _count()
+    with _Timed("act_bwd", g.n * g.h * g.w * g.c * 2 * 3):
+        L.check(L.load().pcgan_act_bwd(_ptr(dy), dy_pad, _ptr(y), y_pad, _ptr(dx), dx_pad, g.n, g.h, g.w, g.c, float(slope), _stream()), "act_bwd")
+
+
+def nhwc_to_f32(buf, g: Geom, dst):
+    """interior of the padded NHWC bf16 buffer -> contiguous fp32 [n, h, w, c]"""
+    _count()
+    with _Timed("nhwc_cast", g.n * g.h * g.w * g.c * 6):
+        L.check(L.load().pcgan_nhwc_cast(_ptr(buf), _ptr(dst), g.pad, g.n, g.h, g.w, g.c, 1, _stream()), "nhwc_cast")
+
+
+def f32_to_nhwc(src, buf, g: Geom):
+    _count()
+    with _Timed("nhwc_cast", g.n * g.h * g.w * g.c * 6):
+        L.check(L.load().pcgan_nhwc_cast(_ptr(src), _ptr(buf), g.pad, g.n, g.h, g.w, g.c, 0, _stream()), "nhwc_cast")
 
 
 def resize_nchw_fwd(src, dst):

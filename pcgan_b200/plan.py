@@ -410,7 +410,7 @@ def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho
     s.n_valid = cout
     win = _ceil(kw * C, 64) * 64
     s.cchunks = win // 64
-    bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride == 2)
+    bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride >= 2)
     tx, ty, tn = _ceil(wo, bw), _ceil(ho, bh), _ceil(N, bn)
     window = WINDOW and stride == 1 and C == 8 and kw <= 8 and wo >= 64
     flat_tiles = _ceil(N * Hp * Wp, 128)
@@ -471,17 +471,18 @@ def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho
             s.stats_mode = L.STATS_ON
             s.stats_dim, s.stats_comp = (2, 1) if per_sample_stats else (-1, 1)
     else:
-        assert stride == 2 and Hp % 2 == 0
-        # dims: (window, X [2 pixels per step], py, Y (+ n*Hp/2)); the x offset `off` goes into the base pointer
-        s.a_dims = [win, Wp // 2, 2, (Hp // 2) * N, 1]
-        s.a_strides = [0, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2, (Hp // 2) * N * 2 * Wp * C * 2]
+        st = stride
+        assert st in (2, 4) and Hp % st == 0 and Wp % st == 0, "strided packed rows need padded extents that are multiples of the stride"
+        # dims: (window, X [st pixels per step], row phase, Y (+ n*Hp/st)); the x offset `off` goes into the base pointer
+        s.a_dims = [win, Wp // st, st, (Hp // st) * N, 1]
+        s.a_strides = [0, st * C * 2, Wp * C * 2, st * Wp * C * 2, (Hp // st) * N * st * Wp * C * 2]
         s.a_box = [64, bw, 1, bh, 1]
         s.a_elem_offset = off * C
         s.a_step[0][0] = bw
         s.a_step[1][2] = bh
-        s.a_step[2][2] = Hp // 2
+        s.a_step[2][2] = Hp // st
         for r in range(kh):
-            s.tap_off.append([0, (r + off) % 2, (r + off) // 2, 0])
+            s.tap_off.append([0, (r + off) % st, (r + off) // st, 0])
             s.tap_c0.append(0)
             s.tap_bk.append(r * win)
         period = ty * bh

@@ -9,7 +9,7 @@ checkpoint I/O, control flow.  One process per GPU; gradients are averaged acros
 pcgan_b200.dist.GradSync (the reference's nn.DataParallel replaced by NCCL all-reduce).
 
 Supported flags: the wsgan_emb configuration with --which_model_netG resnet_9blocks (or
-resnet_6blocks), --which_model_netD n_layers/basic, --lambda_IP 0, plus --lambda_L1,
+resnet_6blocks), --which_model_netD n_layers/basic, --lambda_IP (the AlexNet identity-preserving loss), --lambda_L1,
 --lambda_A_GAN, --detach_fake_B, --use_real_A, --no_mixed_label_D, the four encoder modes
 (--bayesian / --noisy with --noisy_var_type, --bnn_dropout, --bnn_T, --noisy_D, --noisy_rec) and
 --lr_E > 0 (update_G_and_E).
@@ -42,6 +42,7 @@ def default_options(**overrides):
         cnn_relu_slope_E=0.7, fineSize_E=224, pretrained_model_path_E="", embedding_mean=[0.0], embedding_std=[1.0],
         embedding_bins="[]", display_visuals=False, noisy=False, noisy_D=True, noisy_rec=True, noisy_var_type="",
         bayesian=False, bnn_dropout=0.0, bnn_T=10, attr_bins=[],
+        which_model_netIP="alexnet", pretrained_model_path_IP="", fineSize_IP=224, identity_preserving_criterion="mse",
         lambda_L1=0.0, lambda_IP=0.0, lambda_z=1.0, lambda_A=0.5, lambda_A_GAN=0.0, lr_E=0.0, use_real_A=False,
         relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False, update_logvar_E=False,
         no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5, lr_policy="lambda", niter=50, niter_decay=50, epoch_count=1,
@@ -279,8 +280,6 @@ class WSGANEmbModel(BaseModel):
             raise RuntimeError("Aleatoric only available when noisy is True.")
         if "e" in opt.noisy_var_type and not opt.bayesian:
             raise RuntimeError("Epistemic only available when bayesian is True.")
-        if opt.isTrain and opt.lambda_IP > 0.0:
-            raise NotImplementedError("the identity-preserving AlexNet loss (netIP) is outside the named hot path: use --lambda_IP 0")
         if opt.no_cnn_E:
             opt.cnn_dim_E = []
         self.loss_names = ["G_GAN", "G_GAN_cycle", "G_IP", "G_L1", "G_cycle", "z_rec", "D_real_right", "D_real_wrong", "D_fake"]
@@ -298,6 +297,18 @@ class WSGANEmbModel(BaseModel):
         if self.isTrain:
             self.netD = networks.define_D(opt.output_nc, opt.embedding_nc, opt.ndf, opt.which_model_netD, opt.n_layers_D, opt.norm_D,
                                           opt.no_lsgan, opt.init_type, num_Ds=opt.num_Ds, gpu_ids=self.gpu_ids)
+            # the identity-preserving network, which is not saved (:129-135); built only when its loss is on
+            self.netIP = None
+            if opt.lambda_IP > 0.0:
+                self.netIP = networks.define_IP(getattr(opt, "which_model_netIP", "alexnet"), opt.input_nc, self.gpu_ids)
+                path = getattr(opt, "pretrained_model_path_IP", "")
+                if path:
+                    self._unwrap(self.netIP).load_pretrained(path)
+                self.set_requires_grad(self.netIP, False)     # never optimised: its weight gradients are not computed
+            crit = getattr(opt, "identity_preserving_criterion", "mse").lower()
+            if crit not in ("mse", "l1"):
+                raise NotImplementedError("Not Implemented")
+            self.criterionIP = networks.mse_loss if crit == "mse" else networks.l1_loss
             assert opt.pool_size == 0
             self.criterionGAN = networks.GANLoss(use_lsgan=not opt.no_lsgan)
             self.criterionL1 = networks.l1_loss
@@ -350,6 +361,7 @@ class WSGANEmbModel(BaseModel):
                 self.weight_label_D = [w / sum(opt.weight_label_D) for w in opt.weight_label_D]
             else:
                 self.weight_label_D = None
+        self.transform_IP = networks.Normalize((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))
         self.embedding_normalize = lambda x: (x - opt.embedding_mean[0]) / opt.embedding_std[0]
         if getattr(opt, "display_visuals", False):
             self.pre_generate_embeddings(self.embedding_bins)
@@ -427,6 +439,9 @@ class WSGANEmbModel(BaseModel):
     def forward(self):
         """wsgan_emb_model.py:214-259."""
         opt = self.opt
+        ip = self.isTrain and opt.lambda_IP > 0.0
+        if ip:
+            self.real_A_IP = upsample2d(self.real_A, opt.fineSize_IP)      # :215
         self.real_A_E = upsample2d(self.real_A, opt.fineSize_E)
         self.real_B_E = upsample2d(self.real_B, opt.fineSize_E)
         y_A, var_A = self._encode(self.real_A_E)
@@ -444,6 +459,8 @@ class WSGANEmbModel(BaseModel):
                 self.resample_A, self.resample_B = self.resample_A.detach(), self.resample_B.detach()
         self.fake_B = self.netG(self.real_A, self.embedding_B)
         self.fake_B_E = upsample2d(self.fake_B, opt.fineSize_E)
+        if ip:
+            self.fake_B_IP = upsample2d(self.fake_B, opt.fineSize_IP)      # :254
         src = self.fake_B.detach() if opt.detach_fake_B else self.fake_B
         self.rec_A = self.netG(src, self.embedding_A)
 
@@ -486,7 +503,7 @@ class WSGANEmbModel(BaseModel):
         self.loss_D.backward()
 
     def _generator_losses(self):
-        """the terms backward_G and backward_GE share (:333-364, 372-404), lambda_IP = 0"""
+        """the terms backward_G and backward_GE share (:333-364, 372-404)"""
         opt = self.opt
         self.loss_G_GAN = self.criterionGAN(self.netD(self.fake_B, self._cond_B()), True)
         if opt.lambda_A_GAN > 0.0:
@@ -494,7 +511,12 @@ class WSGANEmbModel(BaseModel):
         else:
             self.loss_G_GAN_cycle = 0.0
         self.loss_G_L1 = self.criterionL1(self.fake_B, self.real_A) * opt.lambda_L1 if opt.lambda_L1 > 0.0 else 0.0
-        self.loss_G_IP = 0.0
+        if opt.lambda_IP > 0.0:      # :353-356, 393-396
+            with torch.no_grad():
+                feature_A = self.netIP(self.transform_IP(self.real_A_IP))
+            self.loss_G_IP = self.criterionIP(self.netIP(self.transform_IP(self.fake_B_IP)), feature_A) * opt.lambda_IP
+        else:
+            self.loss_G_IP = 0.0
         self.loss_G_cycle = self.criterionCycle(self.rec_A, self.real_A) * opt.lambda_A if opt.lambda_A > 0.0 else 0.0
         return self.loss_G_GAN + self.loss_G_IP + self.loss_G_L1 + self.loss_G_cycle + self.loss_G_GAN_cycle
 

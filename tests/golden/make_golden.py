@@ -319,7 +319,53 @@ def golden_step_variants():
     print("variant step:", losses)
 
 
+def golden_step_ip():
+    """The AlexNet feature extractor alone (networks.py:1218-1255) and one WSGANEmbModel.optimize_parameters() with the
+    identity-preserving loss on (--lambda_IP 1, the reference default: :130-135, 353-356, 393-396), fineSize_IP 224, at a
+    small image size (64 x 64, fineSize_E 64, resnet_6blocks)."""
+    from models import networks
+    ip0 = networks.define_IP("alexnet", 3, [])
+    sd_ip = ip0.state_dict()
+    O.fill_state_dict_(sd_ip, 64)
+    x, _, _ = O.synthetic_batch(2, 224, 701)
+    with torch.no_grad():
+        feat = ip0(x)
+    tmp = tempfile.mkdtemp()
+    e0 = networks.define_E("resnet18", 3, init_type="normal", pooling="avg", cnn_dim=[32, 1], cnn_pad=1, cnn_relu_slope=0.7, gpu_ids=[])
+    pth, pth_ip = os.path.join(tmp, "e.pth"), os.path.join(tmp, "ip.pth")
+    torch.save(e0.state_dict(), pth)
+    torch.save(sd_ip, pth_ip)
+    argv = sys.argv
+    sys.argv = ["x", "--model", "wsgan_emb", "--gpu_ids", "-1", "--which_model_netG", "resnet_6blocks", "--n_layers_D", "3",
+                "--batchSize", "2", "--lambda_IP", "1.0", "--pretrained_model_path_IP", pth_ip, "--pretrained_model_path_E", pth,
+                "--sourcefile_A", pth, "--dataroot", tmp, "--embedding_bins", "[-2,-1,0,1,2]", "--checkpoints_dir", tmp, "--name", "golden_ip",
+                "--fineSize", "64", "--loadSize", "64", "--fineSize_E", "64"]
+    try:
+        from options.train_options import TrainOptions
+        from models import create_model
+        opt = TrainOptions().parse()
+        model = create_model(opt)
+        model.setup(opt)
+    finally:
+        sys.argv = argv
+    O.fill_state_dict_(model.netG.state_dict(), 61)
+    O.fill_state_dict_(model.netD.state_dict(), 62)
+    O.fill_state_dict_(model.netE.state_dict(), 63)
+    a, b, label = O.synthetic_batch(2, 64, 700)
+    model.set_input({"A": a, "B": b, "label": label, "A_paths": ["a"] * 2, "B_paths": ["b"] * 2})
+    model.optimize_parameters()
+    losses = {k: float(v) for k, v in model.get_current_losses().items()}
+    torch.save({"seeds": (61, 62, 63, 64), "batch_seed": 700, "feat_seed": 701, "feat_sub": feat[:, ::16].clone(), "feat_mean": feat.mean(),
+                "keys": list(sd_ip.keys()), "losses": losses, "fake_b_sub": sub(model.fake_B.detach(), 4),
+                "g_w_after": model.netG.state_dict()["model.10.conv_block.1.weight"][:4, :4].clone()},
+               os.path.join(HERE, "step_ip.pt"))
+    print("IP step:", losses)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ip":
+        golden_step_ip()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         golden_step_variants()
         sys.exit(0)
@@ -337,6 +383,7 @@ if __name__ == "__main__":
     golden_siamese_step()
     golden_step_bayesian()
     golden_step_variants()
+    golden_step_ip()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

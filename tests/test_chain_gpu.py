@@ -370,3 +370,75 @@ def test_encoder_chain_teacher_forced(N, S):
     log.check("input pack", x0, bf(a), 1e-6)
     log.report("E chain N=%d S=%d" % (N, S))
     assert len(log.rows) >= 90
+
+
+# ---------------------------------------------------------------------------------- identity-preserving net
+@pytest.mark.parametrize("N,S", [(3, 64), (16, 224)], ids=["b3_s64", "b16_s224"])
+def test_alexnet_chain_teacher_forced(N, S):
+    """AlexNetFeature (models/networks.py:1218-1255; frozen: forward and input gradient), stage by stage: conv11x11 s4 p2,
+    the three un-padded 3x3 s2 max pools, conv5x5 p2, the 3x3 convolutions, every fused ReLU and its backward."""
+    sd = O.make_state_dict(O.alexnet_keys(), 64, device=DEV)
+    net = NW.define_IP("alexnet", 3, [0])
+    mod = net.module
+    mod.load_state_dict({k: v.clone() for k, v in sd.items()})
+    P = mod._program(N, S)
+    a, _, _ = O.synthetic_batch(N, S, 305, device=DEV)
+    feat, ws = P.forward(a.contiguous())
+    dfeat = torch.randn(N, 256, P.p3, P.p3, device=DEV)
+    dx = P.backward(ws, dfeat)
+    torch.cuda.synchronize()
+    sc, log, f = P.scratch, Log(), mod.features
+    with torch.no_grad():
+        log.check("features vs oracle (end to end)", feat, O.alexnet_forward(sd, a), 3e-2)
+
+    def conv_relu_stage(name, x, conv, stride, pad, my_y, dy_masked, my_dx):
+        """y = relu(conv(x) + b): forward from the stored input; the data gradient from the kernels' own masked dy"""
+        xx = x.clone().requires_grad_(True)
+        pre = F.conv2d(xx, bf(conv.weight.detach()), conv.bias.detach(), stride=stride, padding=pad)
+        log.check(name + ".fwd", my_y, torch.relu(pre))
+        pre.backward(dy_masked)
+        log.check(name + ".dgrad", my_dx, xx.grad)
+
+    def pool_stage(name, x, gy, my_y, my_dx):
+        xx = x.clone().requires_grad_(True)
+        y = F.max_pool2d(xx, 3, 2)
+        log.check(name + ".fwd", my_y, y, 1e-6)
+        y.backward(gy)
+        log.check(name + ".bwd", my_dx, xx.grad)       # overlapping windows: up to four gradients summed, then one bf16 rounding
+
+    def relu_bwd(name, g, y, my_dy):
+        log.check(name + ".drelu", my_dy, torch.where(y > 0, g, torch.zeros_like(g)), 1e-6)
+
+    S0 = NW.Geom(N, S, S, 8, 0)
+    g3 = inner(sc.get(P.g_p3, "g3"), P.g_p3)
+    log.check("dfeat cast", g3, bf(dfeat))
+    r5, gr5 = inner(ws.r5, P.g_r5), inner(sc.get(P.g_r5, "gr5"), P.g_r5)
+    pool_stage("pool3", r5, g3, inner(ws.p3, P.g_p3), gr5)
+    dy5 = inner(sc.get(P.g_y4, "dy5"), P.g_y4)
+    relu_bwd("conv5", gr5, r5, dy5)
+    y4, g4 = inner(ws.y4, P.g_y4), inner(sc.get(P.g_y4r, "g4"), P.g_y4r)
+    conv_relu_stage("conv5", y4, f[10], 1, 1, r5, dy5, g4)
+    dy4 = inner(sc.get(P.g_y4, "dy4"), P.g_y4)
+    relu_bwd("conv4", g4, y4, dy4)
+    y3, g3r = inner(ws.y3, P.g_y3), inner(sc.get(P.g_y3r, "g3r"), P.g_y3r)
+    conv_relu_stage("conv4", y3, f[8], 1, 1, y4, dy4, g3r)
+    dy3 = inner(sc.get(P.g_y3, "dy3"), P.g_y3)
+    relu_bwd("conv3", g3r, y3, dy3)
+    p2, gp2 = inner(ws.p2, P.g_p2), inner(sc.get(P.g_p2r, "gp2"), P.g_p2r)
+    conv_relu_stage("conv3", p2, f[6], 1, 1, y3, dy3, gp2)
+    r2, gr2 = inner(ws.r2, P.g_r2), inner(sc.get(P.g_r2, "gr2"), P.g_r2)
+    pool_stage("pool2", r2, gp2, p2, gr2)
+    dy2 = inner(sc.get(P.g_d2, "dy2"), P.g_d2)
+    relu_bwd("conv2", gr2, r2, dy2)
+    p1, gp1 = inner(ws.p1, P.g_p1), inner(sc.get(P.g_p1r, "gp1"), P.g_p1r)
+    conv_relu_stage("conv2", p1, f[3], 1, 2, r2, dy2, gp1)
+    r1, gr1 = inner(ws.r1, P.g_r1), inner(sc.get(P.g_r1, "gr1"), P.g_r1)
+    pool_stage("pool1", r1, gp1, p1, gr1)
+    dy1 = inner(sc.get(P.g_d1, "dy1"), P.g_d1)
+    relu_bwd("conv1", gr1, r1, dy1)
+    x0 = inner(ws.x0, P.g_x0)[:, :3]
+    conv_relu_stage("conv1", x0, f[0], 4, 2, r1, dy1, inner(sc.get(S0, "gx"), S0)[:, :3])
+    log.check("conv1.dgrad -> dx", dx, inner(sc.get(S0, "gx"), S0)[:, :3], 1e-6)
+    log.check("input pack", x0, bf(a), 1e-6)
+    log.report("IP chain N=%d S=%d" % (N, S))
+    assert len(log.rows) >= 24

@@ -106,6 +106,57 @@ def test_siamese_training_step_gradients_and_update():
     assert abs(float(loss2) - lref2) < 3e-2 * abs(lref2)
 
 
+def test_siamese_noisy_branch_matches_oracle():
+    """siamese.py:654-659 (--noisy true, no rsample): score / sqrt(exp(logvar1) + exp(logvar2)), second Adam over cnn_logvar."""
+    N, S = 8, 64
+    sd = O.make_state_dict(O.encoder_keys(noisy=True), 54, device=DEV, requires_grad=True)
+    net = SI.get_model(noisy=True, gpu_ids=[0])
+    net.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
+    trainer = SI.EloTrainer(net, lr=2e-4, lr_sigma=1e-4)
+    a, b, label = O.synthetic_batch(N, S, 611, device=DEV)
+    w0 = net.cnn_logvar[4].weight.detach().clone()
+    loss, prob = trainer.train_step(a, b, label.to(DEV))
+    y1, lv1 = O.encoder_forward(sd, a, cnn_relu_slope=0.7, noisy=True)
+    y2, lv2 = O.encoder_forward(sd, b, cnn_relu_slope=0.7, noisy=True)
+    pref = torch.sigmoid((y1 - y2) / (torch.sqrt(torch.exp(lv1) + torch.exp(lv2)) + 1e-20))
+    lref = O.elo_nll(pref, label.to(DEV))
+    lref.backward()
+    print("noisy siamese step: loss %.5f / %.5f, prob %.3e" % (float(loss), float(lref), rel(prob, pref)))
+    assert abs(float(loss) - float(lref)) < 2e-2 * abs(float(lref))
+    named = dict(net.named_parameters())
+    errs = {k: rel(named[k].grad, sd[k].grad) for k in ("cnn_logvar.4.bias", "cnn_logvar.4.weight", "cnn.4.bias")}
+    print({k: "%.2e" % v for k, v in errs.items()})
+    assert errs["cnn_logvar.4.bias"] < 2e-2 and errs["cnn.4.bias"] < 2e-2 and errs["cnn_logvar.4.weight"] < 1.5e-1
+    moved = float((net.cnn_logvar[4].weight.detach() - w0).abs().max())
+    assert 2e-5 < moved < 2.1e-4, moved        # the sigma optimizer stepped with lr_sigma = 1e-4
+
+
+@pytest.mark.parametrize("mode", ["plain", "rsample_mc"])
+def test_siamese_graph_replay_matches_eager(mode):
+    """EloTrainer(cuda_graph=True): the captured iteration computes what the per-launch iteration computes."""
+    N, S = 8, 64
+    kw = dict(noisy=True, rsample=True) if mode == "rsample_mc" else {}
+    tr = []
+    for graph in (False, True):
+        sd = O.make_state_dict(O.encoder_keys(noisy=bool(kw)), 55, device=DEV)
+        net = SI.get_model(gpu_ids=[0], **kw)
+        net.load_state_dict({k: v.clone() for k, v in sd.items()})
+        tr.append(SI.EloTrainer(net, lr=2e-4, cuda_graph=graph, M=2, lb_or_mc="mc"))
+    w0 = tr[1].net.base.model.conv1.weight.detach().clone()
+    for it in range(5):
+        a, b, label = O.synthetic_batch(N, S, 640 + it, device=DEV)
+        torch.manual_seed(it)
+        le, _ = tr[0].train_step(a, b, label.to(DEV))
+        torch.manual_seed(it)
+        lg, _ = tr[1].train_step(a, b, label.to(DEV))
+        print(mode, it, float(le), float(lg))
+        if mode == "plain":      # the reparameterisation draws of the captured graph come from the graph's own Philox offsets
+            assert abs(float(le) - float(lg)) <= 0.03 * abs(float(le)) + 1e-4
+        assert float(lg) == float(lg)
+    assert tr[1]._graph is not None and tr[0]._graph is None
+    assert float((tr[1].net.base.model.conv1.weight.detach() - w0).abs().max()) > 1e-4
+
+
 def _models(B, S, seeds, n_blocks=6, fine_e=64, **flags):
     noisy = bool(flags.get("noisy", False))
     sds = [O.make_state_dict(k, s, device=DEV, requires_grad=rg) for k, s, rg in

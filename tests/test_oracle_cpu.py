@@ -200,3 +200,26 @@ def test_variant_flags_step_matches_reference():
     assert close(m.g["model.1.weight"][:4], fx["g_stem_w_after"], 1e-4)
     assert close(m.d["model.2.weight"][:4, :4], fx["d_w_after"], 1e-4)
 
+
+
+def test_identity_preserving_step_matches_reference():
+    """AlexNetFeature (models/networks.py:1218-1255) and the step with --lambda_IP 1 (:130-135, 353-356, 393-396) against
+    the reference's own modules (tests/golden/step_ip.pt)."""
+    fx = load("step_ip.pt")
+    torch.set_num_threads(8)
+    sg, sd_, se, sip = fx["seeds"]
+    assert list(O.alexnet_keys().keys()) == fx["keys"]
+    ip = O.make_state_dict(O.alexnet_keys(), sip)
+    x, _, _ = O.synthetic_batch(2, 224, fx["feat_seed"])
+    with torch.no_grad():
+        feat = O.alexnet_forward(ip, x)
+    assert close(feat[:, ::16], fx["feat_sub"], 1e-4) and abs(float(feat.mean()) - float(fx["feat_mean"])) < 1e-5
+    m = O.WSGANEmbOracle(O.make_state_dict(O.generator_keys(n_blocks=6), sg, requires_grad=True),
+                         O.make_state_dict(O.discriminator_keys(), sd_, requires_grad=True),
+                         O.make_state_dict(O.encoder_keys(), se), n_blocks=6, fine_size_e=64, sd_ip=ip, lambda_ip=1.0, fine_size_ip=224)
+    a, b, label = O.synthetic_batch(2, 64, fx["batch_seed"])
+    got = m.optimize_parameters(a, b, label)
+    for k in ("G_GAN", "G_IP", "G_cycle", "z_rec", "D_real_right", "D_real_wrong", "D_fake"):
+        assert abs(got[k] - fx["losses"][k]) <= 2e-4 * abs(fx["losses"][k]) + 1e-7, (k, got[k], fx["losses"][k])
+    assert close(m.fake_b.detach()[..., ::4, ::4], fx["fake_b_sub"], 1e-4)
+    assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["g_w_after"], 1e-4)

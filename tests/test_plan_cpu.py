@@ -52,6 +52,10 @@ FWD_CASES = [
     ("e1x1_s2", 64, 64, 128, 1, 2, 0, "zero", 1, 8, 8, 2),
     ("tail3x3_c32_packed", 32, 32, 1, 3, 1, 1, "zero", 1, 7, 7, 3),
     ("wide_n512", 64, 64, 512, 3, 1, 1, "zero", 1, 8, 8, 1),
+    # AlexNet feature extractor of the identity-preserving loss (networks.py:1218-1240)
+    ("alex11x11_s4_packed", 3, 8, 64, 11, 4, 2, "zero", 2, 28, 28, 2),
+    ("alex5x5_p2_n192", 64, 64, 192, 5, 1, 2, "zero", 2, 11, 11, 2),
+    ("alex3x3_c192_n384", 192, 192, 384, 3, 1, 1, "zero", 1, 13, 13, 2),
 ]
 
 
@@ -130,6 +134,9 @@ DGRAD_CASES = [
     ("estem7x7_s2_to3_shift", 3, 64, 64, 7, 2, 3, 3, False, 32, 2, 2),      # zero-haloed dY: shift-sum phases
     ("e1x1_s2", 64, 128, 128, 1, 2, 0, 1, False, 8, 2, 0),
     ("stem7x7_to4_full", 4, 64, 64, 7, 1, 3, 3, True, 16, 1, 0),
+    ("alex11x11_s4_to3", 3, 64, 64, 11, 4, 2, 2, False, 28, 2, 2),         # 16 phases of a stride-4 convolution
+    ("alex5x5_p2_flat", 64, 192, 192, 5, 1, 2, 2, False, 11, 2, 2),
+    ("alex3x3_n384_flat", 192, 384, 384, 3, 1, 1, 1, False, 13, 2, 1),
 ]
 
 

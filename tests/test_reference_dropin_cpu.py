@@ -51,7 +51,7 @@ def test_every_reference_flag_is_read_with_its_default(ref_front_end, monkeypatc
     ref = vars(_parse(monkeypatch, "wsgan_emb"))
     mine = vars(default_options())
     north_star = dict(which_model_netG="resnet_9blocks", n_layers_D=3, lambda_IP=0.0, gpu_ids=[0], display_visuals=False,
-                      embedding_bins="[]", pretrained_model_path_E="", batchSize=10, upsample="bilinear", attr_bins=[], num_Ds=1,
+                      embedding_bins="[]", pretrained_model_path_E="", pretrained_model_path_IP="", batchSize=10, upsample="bilinear", attr_bins=[], num_Ds=1,
                       checkpoints_dir="", name="", isTrain=True)
     for k, v in mine.items():
         if k in north_star or k.startswith("cuda_graph") or k not in ref:

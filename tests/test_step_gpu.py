@@ -98,6 +98,35 @@ def test_variant_flags_step_losses():
     assert float((wg - wr).abs().max()) < 4.1e-4
 
 
+def test_identity_preserving_step_losses():
+    """--lambda_IP 1 (the reference's default: models/wsgan_emb_model.py:130-135, 353-356, 393-396): the AlexNet feature
+    loss between fake_B and real_A, forward and gradient through the frozen feature extractor into the generator."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = 4
+    sds = [O.make_state_dict(k, s, device=DEV, requires_grad=rg) for k, s, rg in
+           ((O.generator_keys(), 61, True), (O.discriminator_keys(), 62, True), (O.encoder_keys(), 63, False))]
+    ip = O.make_state_dict(O.alexnet_keys(), 64, device=DEV)
+    model = WSGANEmbModel()
+    opt = default_options(batchSize=B, gpu_ids=[0], lambda_IP=1.0)
+    model.initialize(opt)
+    model.setup(opt)
+    for net, sd in zip((model.netG, model.netD, model.netE, model.netIP), sds + [ip]):
+        net.module.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
+    oracle = O.WSGANEmbOracle(*sds, sd_ip=ip, lambda_ip=1.0, fine_size_ip=224)
+    a, b, label = O.synthetic_batch(B, 128, 710, device=DEV)
+    model.set_input({"A": a, "B": b, "label": label})
+    model.optimize_parameters()
+    got = model.get_current_losses()
+    want = oracle.optimize_parameters(a, b, label)
+    print("IP step losses:", {k: "%.6f/%.6f" % (got[k], want[k]) for k in KEYS + ("G_IP",)})
+    for k in ("G_GAN", "G_cycle", "D_real_right", "D_real_wrong", "D_fake", "G_IP"):
+        assert abs(got[k] - want[k]) <= 0.03 * abs(want[k]) + 1e-6, (k, got[k], want[k])
+    wg = model.netG.module.model[26].weight.detach()
+    assert float((wg - oracle.g["model.26.weight"].detach()).abs().max()) < 4.1e-4
+    assert all(p.grad is None for p in model.netIP.parameters())      # frozen: no weight gradients are computed
+
+
 @pytest.mark.skipif(os.environ.get("PCGAN_SKIP_TRAJ") == "1", reason="trajectory test disabled")
 def test_loss_trajectories_200_steps():
     steps, B = 200, int(os.environ.get("PCGAN_TRAJ_BATCH", "64"))      # BASELINE configs[2]: 64 pairs per GPU
