@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 14
+#define PCGAN_ABI_VERSION 15
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -159,6 +159,11 @@ typedef struct {
    * dimension with the image-row stride, added to the view by the planner; boxes beyond its extent read zeros).  With
    * num_taps = 1 the M operand is fetched once per N tile instead of once per filter row. */
   int32_t wg_box_dim;
+  /* 0: bf16 operands (tcgen05.mma.kind::f16), K chunks of 64 elements.  1: fp32 operands multiplied as TF32
+   * (tcgen05.mma.kind::tf32, 10-bit mantissa products, fp32 accumulate): both tensor maps are fp32, a K chunk is 32
+   * elements (still 128 bytes), WGRAD boxes are 64 pixels x 32 channels, box[0] of both maps is 32; no pairing, no
+   * windowed A.  Everything else (tap tables, tile maps, epilogue) is unchanged. */
+  int32_t tf32;
 } pcgan_igemm_desc;
 
 typedef struct pcgan_igemm_plan pcgan_igemm_plan;

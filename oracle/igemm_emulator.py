@@ -12,7 +12,7 @@ ACT = {0: lambda x, s: x, 1: lambda x, s: torch.relu(x), 2: lambda x, s: torch.w
        3: lambda x, s: torch.tanh(x), 4: lambda x, s: torch.sigmoid(x)}
 
 
-def tma_gather(flat, dims, strides_bytes, box, coords):
+def tma_gather(flat, dims, strides_bytes, box, coords, esz=2):
     """flat: 1-D float tensor (bf16 values); coords: [T, 5] int64 start coordinates.
     Returns [T, rows, box[0]]; rows enumerate box dims 1..4 with dim 1 fastest."""
     T = coords.shape[0]
@@ -32,7 +32,7 @@ def tma_gather(flat, dims, strides_bytes, box, coords):
     for d in range(1, 5):
         cd = coords[:, d].view(T, 1, 1) + loc[d - 1].view(1, rows, 1)
         valid = valid & (cd >= 0) & (cd < dims[d])
-        addr = addr + cd * (strides_bytes[d] // 2)
+        addr = addr + cd * (strides_bytes[d] // esz)
     addr = torch.where(valid, addr, torch.zeros_like(addr))
     if addr.numel() and (int(addr.max()) >= flat.numel() or int(addr.min()) < 0):
         raise IndexError("in-bounds TMA element outside the buffer: max %d numel %d" % (int(addr.max()), flat.numel()))
@@ -60,6 +60,8 @@ def run_kmajor(s, a_flat, b_flat, out_flat, bias=None, stats=None):
     dig = _digits(mt, s.t_count)
     ac = _coords(dig, s.a_base, s.a_step)
     a_window = getattr(s, "a_window", 0)
+    tf32 = bool(getattr(s, "tf32", False))
+    kc, esz = (32, 4) if tf32 else (64, 2)      # elements of a 128-byte K chunk, bytes per element
     a_rows = s.a_box[1] * s.a_box[2] * s.a_box[3] * s.a_box[4] - (7 if a_window else 0)
     assert 1 <= a_rows <= 128
     if a_window:
@@ -99,14 +101,14 @@ def run_kmajor(s, a_flat, b_flat, out_flat, bias=None, stats=None):
         acc = torch.zeros(m_tiles, 128, s.block_n, dtype=torch.float32)
         for t in range(s.num_taps):
             for cc in range(s.cchunks):
-                coords = torch.stack([torch.full((m_tiles,), s.tap_c0[t] + cc * 64, dtype=torch.int64)] +
+                coords = torch.stack([torch.full((m_tiles,), s.tap_c0[t] + cc * kc, dtype=torch.int64)] +
                                      [ac[d] + s.tap_off[t][d] for d in range(4)], dim=1)
-                A = tma_gather(a_flat, s.a_dims, s.a_strides, s.a_box, coords)  # [T, rows, 64]
+                A = tma_gather(a_flat, s.a_dims, s.a_strides, s.a_box, coords, esz)  # [T, rows, kc]
                 if a_window:
                     # windowed A: the box holds rows + 7 plain pixels of 8 channels; row m reads pixels m .. m+7
                     A = torch.cat([A[:, j:j + a_rows, :] for j in range(8)], dim=2)
-                bc = torch.tensor([[s.tap_bk[t] + cc * 64, nt * s.block_n, 0, 0, 0]], dtype=torch.int64)
-                B = tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, bc)[0]  # [block_n, 64]
+                bc = torch.tensor([[s.tap_bk[t] + cc * kc, nt * s.block_n, 0, 0, 0]], dtype=torch.int64)
+                B = tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, bc, esz)[0]  # [block_n, kc]
                 acc[:, :a_rows] += A @ B.t()
         if getattr(s, "shift_taps", 0):
             # shift-sum epilogue: out[i][c] = sum_j acc[i + j][j*cpad + c]; the last shift_taps - 1 rows store nothing
@@ -147,15 +149,17 @@ def run_wgrad(s, a_flat, b_flat, out_flat):
     dig = _digits(kb, s.t_count)
     ac = _coords(dig, s.a_base, s.a_step)
     bc = _coords(dig, s.b_base, s.b_step)
-    nb = s.block_n // 64
+    tf32 = bool(getattr(s, "tf32", False))
+    kc, esz = (32, 4) if tf32 else (64, 2)
+    nb = s.block_n // kc
     out = out_flat.view(-1)
     for t in range(s.num_taps):
         for mt in range(s.m_tiles):
             # A: [kb, 64 px, 128 ch]
             As = []
-            for j in range(2):
-                coords = torch.stack([torch.full((total_kb,), mt * 128 + j * 64, dtype=torch.int64)] + ac, dim=1)
-                As.append(tma_gather(a_flat, s.a_dims, s.a_strides, s.a_box, coords))
+            for j in range(128 // kc):
+                coords = torch.stack([torch.full((total_kb,), mt * 128 + j * kc, dtype=torch.int64)] + ac, dim=1)
+                As.append(tma_gather(a_flat, s.a_dims, s.a_strides, s.a_box, coords, esz))
             A = torch.cat(As, dim=2)
             for nt in range(s.n_tiles):
                 Bs = []
@@ -165,9 +169,9 @@ def run_wgrad(s, a_flat, b_flat, out_flat):
                         coords = torch.stack([torch.full((total_kb,), s.tap_c0[t], dtype=torch.int64)] +
                                              [bc[d] + s.tap_off[t][d] + (nt * nb + j if d + 1 == bdim else 0) for d in range(4)], dim=1)
                     else:
-                        coords = torch.stack([torch.full((total_kb,), s.tap_c0[t] + nt * s.block_n + j * 64, dtype=torch.int64)] +
+                        coords = torch.stack([torch.full((total_kb,), s.tap_c0[t] + nt * s.block_n + j * kc, dtype=torch.int64)] +
                                              [bc[d] + s.tap_off[t][d] for d in range(4)], dim=1)
-                    Bs.append(tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, coords))
+                    Bs.append(tma_gather(b_flat, s.b_dims, s.b_strides, s.b_box, coords, esz))
                 B = torch.cat(Bs, dim=2)  # [kb, 64, block_n]
                 D = torch.einsum("kpm,kpn->mn", A, B)  # [128, block_n]
                 rows = min(s.m_valid - mt * 128, 128)

@@ -34,23 +34,25 @@ def out_size(h, k, stride, cp, transposed=False, output_padding=0):
 
 # --------------------------------------------------------------------------------- forward
 def conv_fwd_plans(w_shape, xg: Geom, stride: int, cp: int, out: OutMap, *, transposed=False, output_padding=0,
-                   act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, note="") -> List[Tuple[IgemmSpec, torch.Tensor]]:
-    """Forward plans.  w_shape: reference weight shape (OIHW; IOHW when transposed)."""
+                   act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, note="", tf32=False) -> List[Tuple[IgemmSpec, torch.Tensor]]:
+    """Forward plans.  w_shape: reference weight shape (OIHW; IOHW when transposed).  tf32: the buffers and the packed
+    weights hold fp32 and the MMAs run as kind::tf32 (K chunks of 32 channels; no shift-sum / windowed special forms)."""
     kh, kw = w_shape[2], w_shape[3]
     assert kh == kw
     k = kh
-    epi = dict(act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats, note=note)
+    epi = dict(act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats, note=note, tf32=tf32)
+    KC = 32 if tf32 else 64
     if not transposed:
         cout, cin = w_shape[0], w_shape[1]
         ho, wo = out_size(xg.h, k, stride, cp), out_size(xg.w, k, stride, cp)
         o = xg.pad - cp
         assert o >= 0, "input buffer pad %d < conv padding %d" % (xg.pad, cp)
-        if stride == 1 and xg.c == cin and cin % 64 == 0 and cout <= 4 and 2 <= k <= 8 and not stats:
+        if stride == 1 and xg.c == cin and cin % 64 == 0 and cout <= 4 and 2 <= k <= 8 and not stats and not tf32:
             # few output channels (generator head, networks.py:603-605): horizontal taps in N, shift-sum epilogue
             sp = plan_shift_flat(xg, k, k, cin, cout, [(r + o, o, r) for r in range(k)], out, (o, o + ho), (o, o + wo),
                                  act=act, act_slope=act_slope, note=note)
             return [(sp, wmap_shift(w_shape, k, cin))]
-        if xg.c >= 64:
+        if xg.c >= 64 or (tf32 and xg.c == cin and cin % KC == 0):
             assert xg.c == cin
             taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
             sp = plan_box(xg, taps, cin, cout, ho, wo, stride, out, **epi)
@@ -86,13 +88,14 @@ def conv_fwd_plans(w_shape, xg: Geom, stride: int, cp: int, out: OutMap, *, tran
 
 # --------------------------------------------------------------------------- data gradient
 def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: OutMap, *, transposed=False,
-                     full_padded=False, note="") -> List[Tuple[IgemmSpec, torch.Tensor]]:
+                     full_padded=False, note="", tf32=False) -> List[Tuple[IgemmSpec, torch.Tensor]]:
     """Data-gradient plans.  dyg: geometry of the dY buffer (zero halo).  xg: geometry of the convolution's
     input buffer (used for sizes; channels = buffer channels of dX).  `out` maps pixel (n, y, x) of the
     computed region: the interior of the input (full_padded=False) or its whole padded grid
     (full_padded=True, reflect-padded inputs; fold the halo afterwards with pcgan_halo_fold)."""
     kh, kw = w_shape[2], w_shape[3]
     k = kh
+    T = dict(note=note, tf32=tf32)
     if transposed:
         # dX[iy][ix][ci] = sum dY[2iy - cp + r][2ix - cp + s][co] W[ci][co][r][s]: a stride-2 convolution of dY
         cin, cout = w_shape[0], w_shape[1]
@@ -100,7 +103,7 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
         o = dyg.pad - cp
         assert o >= 0
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
-        sp = plan_box(dyg, taps, cout, cin, xg.h, xg.w, 2, out, note=note)
+        sp = plan_box(dyg, taps, cout, cin, xg.h, xg.w, 2, out, **T)
         wt = [(r, s, r * k + s) for r in range(k) for s in range(k)]
         return [(sp, wmap_taps(w_shape, cin, wt, cout, transposed_layout=True, swap=True))]
     cout, cin = w_shape[0], w_shape[1]
@@ -112,11 +115,11 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
         else:
             u0, v0, hu, wu = xg.pad, xg.pad, xg.h, xg.w
         same = (dyg.h, dyg.w, dyg.pad) == (xg.h, xg.w, xg.pad)
-        if dyg.c >= 64:
+        if dyg.c >= 64 or (tf32 and dyg.c == cout and cout % 32 == 0):
             assert dyg.c == cout
             wt = [(r, s, r * k + s) for r in range(k) for s in range(k)]
             wm = wmap_taps(w_shape, cin, wt, cout, swap=True)
-            if same and 2 * cp == k - 1 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and out.sc == 1:
+            if same and 2 * cp == k - 1 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and out.sc == 1 and not tf32:
                 # gradient towards a 3/4-channel image (generator stem, networks.py:578-579): shift-sum form over the
                 # shared padded grid; row t of the GEMM feeds output position t + (k - 1 - cp)
                 sp = plan_shift_flat(dyg, k, k, cout, cin, [(-(r - cp), 0, r) for r in range(k)], out, (u0, u0 + hu), (v0, v0 + wu),
@@ -125,23 +128,23 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
             if same and 2 * cp == k - 1:
                 # flat form over the shared padded grid: dY pixel (y, x) sits at padded (y + pad, x + pad)
                 taps = [(-(r - cp), -(s - cp), r * k + s) for r in range(k) for s in range(k)]
-                sp = plan_flat(dyg, taps, cout, cin, out, (u0, u0 + hu), (v0, v0 + wu), note=note)
+                sp = plan_flat(dyg, taps, cout, cin, out, (u0, u0 + hu), (v0, v0 + wu), **T)
                 return [(sp, wm)]
             taps = [(u0 - r - o + dyg.pad, v0 - s - o + dyg.pad, r * k + s) for r in range(k) for s in range(k)]
-            sp = plan_box(dyg, taps, cout, cin, hu, wu, 1, out, note=note)
+            sp = plan_box(dyg, taps, cout, cin, hu, wu, 1, out, **T)
             return [(sp, wm)]
         # packed: window j <-> s = k-1-j, row tap i <-> r = k-1-i; needs real zero padding around dY
         need = (k - 1 + o) if full_padded else (k - 1 - cp)
         assert dyg.pad >= need, "packed data-gradient needs dY pad >= %d (got %d)" % (need, dyg.pad)
         off = u0 - (k - 1) - o + dyg.pad
-        sp = plan_packed(dyg, k, k, 1, off, cin, hu, wu, out, note=note)
+        sp = plan_packed(dyg, k, k, 1, off, cin, hu, wu, out, **T)
         return [(sp, wmap_packed(w_shape, cin, k, k, dyg.c, sp.b_k // k, flip=True, swap=True))]
     # stride st: input row iy = st*u + py receives the taps r with (py + cp - r) a multiple of st from dY row u + (py + cp - r)/st
     st = stride
-    assert st in (2, 4) and dyg.c >= 64 and dyg.c == cout and not full_padded
+    assert st in (2, 4) and (dyg.c >= 64 or tf32) and dyg.c == cout and not full_padded
     plans = []
     reach = max(abs((p_ + cp - r) // st) for p_ in range(st) for r in range(k) if (p_ + cp - r) % st == 0) if k > 1 else 0
-    if st == 2 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and dyg.pad >= max(reach, 1) and out.sc == 1:
+    if st == 2 and cin <= 4 and xg.c == 8 and 2 <= k <= 8 and dyg.pad >= max(reach, 1) and out.sc == 1 and not tf32:
         # gradient towards a 3/4-channel image through a strided convolution (encoder stem, resnet.py:134): one
         # shift-sum launch per sub-pixel phase over the zero-haloed dY grid
         P = dyg.pad
@@ -174,13 +177,13 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
             om = OutMap(base=out.base + py * out.sy + px * out.sx, sn=out.sn, sy=st * out.sy, sx=st * out.sx, sc=out.sc, dtype=out.dtype)
             if not taps:  # k == 1: odd phases receive nothing; the caller pre-zeroes dX
                 continue
-            sp = plan_box(dyg, taps, cout, cin, hph, wph, 1, om, note=note)
+            sp = plan_box(dyg, taps, cout, cin, hph, wph, 1, om, **T)
             plans.append((sp, wmap_taps(w_shape, cin, wt, cout, swap=True)))
     return plans
 
 
 # ------------------------------------------------------------------------- weight gradient
-def conv_wgrad_plan(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, *, transposed=False, note="") -> Tuple[IgemmSpec, torch.Tensor]:
+def conv_wgrad_plan(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, *, transposed=False, note="", tf32=False) -> Tuple[IgemmSpec, torch.Tensor]:
     """Weight-gradient plan: fp32 [rows][ldo] accumulated with atomics (zero it first), plus the index map that
     scatters it into the reference layout."""
     kh, kw = w_shape[2], w_shape[3]
@@ -190,23 +193,23 @@ def conv_wgrad_plan(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, *, trans
         assert stride == 2 and dyg.c == cout and xg.c == cin
         o = dyg.pad - cp
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
-        sp = plan_wgrad_box(xg, cin, dyg, cout, taps, xg.h, xg.w, 2, m_origin=(xg.pad, xg.pad), note=note)
+        sp = plan_wgrad_box(xg, cin, dyg, cout, taps, xg.h, xg.w, 2, m_origin=(xg.pad, xg.pad), note=note, tf32=tf32)
         wt = [(r, s, r * k + s) for r in range(k) for s in range(k)]
         return sp, wmap_taps(w_shape, cin, wt, cout, transposed_layout=True, swap=True)
     cout, cin = w_shape[0], w_shape[1]
     o = xg.pad - cp
     ho, wo = out_size(xg.h, k, stride, cp), out_size(xg.w, k, stride, cp)
     assert (dyg.h, dyg.w) == (ho, wo) or (dyg.h >= ho and dyg.w >= wo)
-    if (stride == 1 and xg.c == 64 and cin == 64 and cout <= 8 and dyg.c == 8 and k <= 8 and dyg.pad >= o + k - 1
+    if (not tf32 and stride == 1 and xg.c == 64 and cin == 64 and cout <= 8 and dyg.c == 8 and k <= 8 and dyg.pad >= o + k - 1
             and 2 * xg.pad - o <= dyg.pad and (dyg.h, dyg.w) == (ho, wo)):
         sp = plan_wgrad_small_cout(xg, cin, dyg, k, o, note=note)
         return sp, wmap_small_cout(w_shape, k, sp.box_taps)
-    if xg.c >= 64:
+    if xg.c >= 64 or (tf32 and xg.c == cin and cin % 32 == 0):
         assert xg.c == cin
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
-        sp = plan_wgrad_box(dyg, cout, xg, cin, taps, ho, wo, stride, m_origin=(dyg.pad, dyg.pad), note=note)
+        sp = plan_wgrad_box(dyg, cout, xg, cin, taps, ho, wo, stride, m_origin=(dyg.pad, dyg.pad), note=note, tf32=tf32)
         return sp, wmap_taps(w_shape, cout, [(r, s, r * k + s) for r in range(k) for s in range(k)], cin)
     win = _ceil(k * xg.c, 64) * 64
     taps = [(r + o, o, r) for r in range(k)]
-    sp = plan_wgrad_box(dyg, cout, xg, cin, taps, ho, wo, stride, m_origin=(dyg.pad, dyg.pad), n_packed_win=win, note=note)
+    sp = plan_wgrad_box(dyg, cout, xg, cin, taps, ho, wo, stride, m_origin=(dyg.pad, dyg.pad), n_packed_win=win, note=note, tf32=tf32)
     return sp, wmap_packed(w_shape, cout, k, k, xg.c, win)

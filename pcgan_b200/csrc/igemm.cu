@@ -55,6 +55,8 @@ struct DevParams {
   int32_t b_res;       // KMAJOR, > 0: the whole B operand stays resident in front of the ring, b_res bytes per K chunk
   int32_t ring_off;    // byte offset of the ring behind the resident B operand
   int32_t wg_box_dim;  // WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N), 0 = channels
+  int32_t tf32;        // fp32 operands, tcgen05.mma.kind::tf32
+  int32_t kc;          // elements of one 128-byte K chunk: 64 (bf16) or 32 (tf32)
   int32_t split_prod;  // paired WGRAD: warp 3 issues the X boxes, warp 0 the dY boxes
   int32_t kps;         // KMAJOR, unpaired: K chunks per ring stage (one barrier round trip and one commit for all of them)
   int32_t sub_bytes;   //   bytes of one chunk's slot inside a stage (stage_bytes = kps * sub_bytes)
@@ -645,7 +647,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(k_chunks_fwd * P.block_n * 128));
         for (int32_t tap = 0; tap < P.num_taps; ++tap)
           for (int32_t cc = 0; cc < P.cchunks; ++cc)
-            tma_load_5d(smem_u32(smem) + (tap * P.cchunks + cc) * P.b_res, &tma_b, smem_u32(bres_bar), P.tap_bk[tap] + cc * 64, 0, 0, 0, 0);
+            tma_load_5d(smem_u32(smem) + (tap * P.cchunks + cc) * P.b_res, &tma_b, smem_u32(bres_bar), P.tap_bk[tap] + cc * P.kc, 0, 0, 0, 0);
       }
       __syncwarp();
     }
@@ -676,13 +678,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             if (elect_one_sync()) {
               if (kPair) {
                 if (sch.rank == 0) mbar_arrive_expect_tx_addr(full_a, bytes);
-                tma_load_5d_2cta(sa, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                tma_load_5d_2cta(sa, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);      // pairs: bf16 only
                 tma_load_5d_2cta(sa + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n + sch.rank * half_rows, 0, 0, 0);
               } else {
                 if (slot == 0) mbar_arrive_expect_tx_addr(full_a, bytes * static_cast<uint32_t>(min(kps, k_chunks_fwd - kc)));
                 const uint32_t dst = sa + static_cast<uint32_t>(slot) * sub_bytes;
-                tma_load_5d(dst, &tma_a, full_a, ac0 + cc * 64, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
-                if (!b_resident) tma_load_5d(dst + a_alloc, &tma_b, full_a, bk0 + cc * 64, nt * P.block_n, 0, 0, 0);
+                tma_load_5d(dst, &tma_a, full_a, ac0 + cc * P.kc, c[0] + o0, c[1] + o1, c[2] + o2, c[3] + o3);
+                if (!b_resident) tma_load_5d(dst + a_alloc, &tma_b, full_a, bk0 + cc * P.kc, nt * P.block_n, 0, 0, 0);
               }
             }
             __syncwarp();
@@ -699,20 +701,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         wgrad_item(P, sch, tile, ks, nt, mt, tap);
         const int32_t kb0 = ks * kb_per_split;
         const int32_t kb1 = min(kb0 + kb_per_split, total_kb);
-        const int32_t nb = P.block_n >> 6;
-        const uint32_t bytes = (2 + nb) * kBoxBytesMN;
+        const int32_t kc = P.kc;                    // channels per box: 64 (bf16) or 32 (tf32)
+        const int32_t nb = P.block_n / kc;
+        const int32_t amax = 128 / kc;              // boxes of one 128-channel M tile
         const int32_t o0 = P.tap_off[tap][0], o1 = P.tap_off[tap][1], o2 = P.tap_off[tap][2], o3 = P.tap_off[tap][3];
         // the nb boxes of this N tile: 64-channel slices of one pixel box, or (filter rows in N) the same channels at
         // box coordinates nt*nb + j along dim wg_box_dim
         const int32_t bdim = P.wg_box_dim;
-        const int32_t bc0 = P.tap_c0[tap] + (bdim ? 0 : nt * P.block_n), bcs = bdim ? 0 : 64;
+        const int32_t bc0 = P.tap_c0[tap] + (bdim ? 0 : nt * P.block_n), bcs = bdim ? 0 : kc;
         const int32_t box0 = bdim ? nt * nb : 0;
         const int32_t e0 = bdim == 1, e1 = bdim == 2, e2 = bdim == 3, e3 = bdim == 4;
         // pixel blocks kb0 .. kb1-1 are consecutive: the mixed-radix digits are stepped, not re-divided, per block
         Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count);
-        // 64-channel boxes of this M tile (and of the peer's) that exist: 1 or 2
-        const int32_t a_boxes = min((P.a_ch - mt * 128 + 63) / 64, 2);
-        const int32_t peer_boxes = min((P.a_ch - (mt ^ 1) * 128 + 63) / 64, 2);
+        // kc-channel boxes of this M tile (and of the peer's) that exist
+        const int32_t a_boxes = min((P.a_ch - mt * 128 + kc - 1) / kc, amax);
+        const int32_t peer_boxes = min((P.a_ch - (mt ^ 1) * 128 + kc - 1) / kc, amax);
         for (int32_t kb = kb0; kb < kb1; ++kb) {
           const int32_t a0 = coord(d, P.a_base, P.a_step, 0), a1 = coord(d, P.a_base, P.a_step, 1),
                         a2 = coord(d, P.a_base, P.a_step, 2), a3 = coord(d, P.a_base, P.a_step, 3);
@@ -745,10 +748,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                                  b2 + e2 * bx, b3 + e3 * bx);
               }
             } else {
-              mbar_arrive_expect_tx_addr(full_a, a_boxes >= 2 ? bytes : bytes - kBoxBytesMN);
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-                if (j < a_boxes) tma_load_5d(sa + j * kBoxBytesMN, &tma_a, full_a, mt * 128 + j * 64, a0, a1, a2, a3);
+              mbar_arrive_expect_tx_addr(full_a, (a_boxes + nb) * kBoxBytesMN);
+              for (int j = 0; j < a_boxes; ++j)
+                tma_load_5d(sa + j * kBoxBytesMN, &tma_a, full_a, mt * 128 + j * kc, a0, a1, a2, a3);
               for (int j = 0; j < nb; ++j) {
                 const int32_t bx = bdim ? box0 + j : 0;
                 tma_load_5d(sa + a_alloc + j * kBoxBytesMN, &tma_b, full_a, bc0 + j * bcs, b0 + e0 * bx, b1 + e1 * bx, b2 + e2 * bx,
@@ -766,19 +768,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     // -------------------------------------------------------------- MMA issuer
     // Converged warp, one elected lane issues tcgen05.mma / commit (always the same lane, so the commits track its MMAs).
     // paired: one tcgen05.mma.cta_group::2 of M = 256 per K step, issued by the leader; the peer's MMA warp has nothing to do
-    const uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
+    const uint32_t idesc = P.tf32 ? make_idesc_tf32(128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u)
+                                  : make_idesc_bf16(kPair ? 256 : 128, P.block_n, wgrad ? 1u : 0u, wgrad ? 1u : 0u);
     // K-major: 8-row groups 1024 B apart; one UMMA_K (16 bf16) = 32 B along the swizzled row.
     // MN-major: 64-element column groups one box (8192 B) apart, 8 K-rows = 1024 B; UMMA_K = 16 rows = 2048 B.
+    // TF32, MN-major: the 32-bit-granular layout (128-byte rows swizzled in 32-byte units over groups of 4 K rows:
+    // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B on the TMA side, descriptor layout type 1), K step 8 pixel rows = 1024 B.
+    const bool tf32 = P.tf32 != 0;
     const uint32_t lbo = wgrad ? kBoxBytesMN : 16;
-    const uint32_t sbo = 1024;
-    const uint32_t kstep = wgrad ? (2048 >> 4) : (32 >> 4);
+    const uint32_t sbo = (wgrad && tf32) ? 512 : 1024;
+    const uint32_t kstep = wgrad ? ((tf32 ? 1024 : 2048) >> 4) : (32 >> 4);
+    const uint32_t ksteps = (wgrad && tf32) ? 8u : 4u;       // MMAs per ring stage
+    const uint64_t ltype = (wgrad && tf32) ? (1ull << 61) ^ (2ull << 61) : 0ull;   // swaps layout type 2 (SWIZZLE_128B) for 1
     int32_t stage = 0;
     uint32_t phase = 0, jt = 0;   // jt: tiles this warp has issued
     // descriptors and barrier addresses of ring stage 0; the loop steps them (the 14-bit address field cannot overflow:
     // shared addresses are below 256 KB)
     const uint32_t ring_a = smem_u32(ring);
-    const uint64_t da0 = P.a_window ? make_smem_desc_noswizzle(ring_a, 16, 128) : make_smem_desc(ring_a, lbo, sbo);
-    const uint64_t db0 = make_smem_desc(P.b_res ? smem_u32(smem) : ring_a + P.a_alloc, lbo, sbo);
+    const uint64_t da0 = (P.a_window ? make_smem_desc_noswizzle(ring_a, 16, 128) : make_smem_desc(ring_a, lbo, sbo)) ^ ltype;
+    const uint64_t db0 = make_smem_desc(P.b_res ? smem_u32(smem) : ring_a + P.a_alloc, lbo, sbo) ^ ltype;
     const uint32_t dstage = static_cast<uint32_t>(P.stage_bytes) >> 4, dres = static_cast<uint32_t>(P.b_res) >> 4;
     const uint32_t dsub = static_cast<uint32_t>(P.sub_bytes) >> 4;
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
@@ -822,9 +830,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             for (int32_t j = 0; j < nchunk; ++j) {
               const uint64_t daj = da + static_cast<uint32_t>(j) * dsub;
               const uint64_t dbj = b_res ? db_res + static_cast<uint32_t>(j) * dres : db_ring + static_cast<uint32_t>(j) * dsub;
+              if (tf32) {
+#pragma unroll 4
+                for (uint32_t k = 0; k < ksteps; ++k)
+                  umma_tf32(tmem_d, daj + k * kstep, dbj + k * kstep, idesc, (kc | j | k) != 0 ? 1u : 0u);
+              } else {
 #pragma unroll
-              for (uint32_t k = 0; k < 4; ++k)
-                umma_bf16(tmem_d, daj + k * kstep, dbj + k * kstep, idesc, (kc | j | k) != 0 ? 1u : 0u);
+                for (uint32_t k = 0; k < 4; ++k)
+                  umma_bf16(tmem_d, daj + k * kstep, dbj + k * kstep, idesc, (kc | j | k) != 0 ? 1u : 0u);
+              }
             }
             tcgen05_commit_addr(empty_a);
           }
@@ -894,7 +908,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base, bool swizzle = true) {
+// mode: 0 no swizzle, 1 SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B (MN-major fp32 operands)
+static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base, int mode = 1, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(PCGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5], strides[4];
@@ -905,8 +920,9 @@ static int encode_tmap(CUtensorMap* out, const pcgan_tmap& t, const void* base, 
     estr[i] = 1;
   }
   for (int i = 0; i < 4; ++i) strides[i] = t.strides[i + 1];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+  const CUtensorMapSwizzle sw = mode == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : (mode == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -974,7 +990,8 @@ static bool dual_enabled() {
   return cached == 1;
 }
 
-static int validate_tmap(const pcgan_tmap& t, const char* name, uint32_t inner = 64) {
+static int validate_tmap(const pcgan_tmap& t, const char* name, uint32_t inner = 64, uint64_t esz = 2) {
+  (void)esz;
   if (t.box[0] != inner) return fail(PCGAN_ERR_INVALID, "%s.box[0] must be %u", name, inner);
   for (int i = 0; i < 5; ++i) {
     if (t.dims[i] == 0 || t.dims[i] > (1ull << 32)) return fail(PCGAN_ERR_INVALID, "%s.dims[%d] out of range", name, i);
@@ -996,8 +1013,12 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   if (wg && d->block_n % 64 != 0) return fail(PCGAN_ERR_UNSUPPORTED, "WGRAD block_n=%d must be a multiple of 64", d->block_n);
   int rc;
   if (d->a_window != 0 && d->a_window != 8) return fail(PCGAN_ERR_INVALID, "a_window must be 0 or 8");
-  if ((rc = validate_tmap(d->a, "a", d->a_window ? 8 : 64)) != PCGAN_OK) return rc;
-  if ((rc = validate_tmap(d->b, "b")) != PCGAN_OK) return rc;
+  if (d->tf32 != 0 && d->tf32 != 1) return fail(PCGAN_ERR_INVALID, "tf32 must be 0 or 1");
+  if (d->tf32 && (d->pair || d->a_window)) return fail(PCGAN_ERR_UNSUPPORTED, "TF32 plans: no pairing, no windowed A");
+  const uint32_t kc = d->tf32 ? 32 : 64;       // elements of a 128-byte K chunk
+  const uint64_t esz = d->tf32 ? 4 : 2;
+  if ((rc = validate_tmap(d->a, "a", d->a_window ? 8 : kc, esz)) != PCGAN_OK) return rc;
+  if ((rc = validate_tmap(d->b, "b", kc, esz)) != PCGAN_OK) return rc;
   if (d->a_window) {
     if (wg || d->a.dims[0] != 8 || d->a.strides[1] != 16 || d->a.box[1] < 8 || d->a.box[2] != 1 || d->a.box[3] != 1 ||
         d->a.box[4] != 1 || d->cchunks != 1 || d->pair)
@@ -1051,10 +1072,10 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     // between the many short tiles of the tiny-K layers)
     v.a_window = d->a_window;
     v.a_bytes = d->a_window ? (int32_t)(a_rows + 7) * 16 : (int32_t)a_rows * 128;
-    const int32_t a_alloc = wg ? 2 * kBoxBytesMN : (v.a_bytes + 1023) / 1024 * 1024;
+    const int32_t a_alloc = wg ? (128 / (int32_t)kc) * kBoxBytesMN : (v.a_bytes + 1023) / 1024 * 1024;
     // paired: each CTA holds half of the B tile (tcgen05.mma.cta_group::2 reads the other half from the peer)
     const int32_t b_rows_cta = d->pair ? d->block_n / 2 : d->block_n;
-    const int32_t b_alloc = wg ? (b_rows_cta / 64) * kBoxBytesMN : (b_rows_cta * 128 + 1023) / 1024 * 1024;
+    const int32_t b_alloc = wg ? (b_rows_cta / (int32_t)kc) * kBoxBytesMN : (b_rows_cta * 128 + 1023) / 1024 * 1024;
     // a weight matrix of one N tile that fits in half of the operand memory is fetched once per CTA and stays
     const int64_t b_total = (int64_t)d->num_taps * d->cchunks * b_alloc;
     const bool resident = resident_b_enabled() && !wg && !d->pair && d->n_tiles == 1 && b_total <= kDataBytes / 2;
@@ -1072,6 +1093,8 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
     }
     v.kps = kps;
     v.split_prod = (wg && d->pair && splitp_enabled()) ? 1 : 0;
+    v.tf32 = d->tf32;
+    v.kc = (int32_t)kc;
     v.stage_bytes = kps * v.sub_bytes;
     int32_t ns = (kDataBytes - v.ring_off) / v.stage_bytes;
     // two pipelines when each still gets at least two stages and the plan is not paired (a pair already shares one MMA
@@ -1127,14 +1150,17 @@ extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b
   {
     std::lock_guard<std::mutex> lock(p->mu);
     if (p->cached_a != a) {
-      int rc = encode_tmap(&p->map_a, p->desc.a, a, p->desc.a_window == 0);
+      const bool f32 = p->desc.tf32 != 0;
+      const int mode = p->desc.a_window ? 0 : ((f32 && p->desc.kind == PCGAN_IGEMM_WGRAD) ? 2 : 1);
+      int rc = encode_tmap(&p->map_a, p->desc.a, a, mode, f32);
       if (rc != PCGAN_OK) return rc;
       p->cached_a = a;
     }
     if (p->cached_b != b) {
       pcgan_tmap tb = p->desc.b;
       if (p->desc.pair && p->desc.kind == PCGAN_IGEMM_KMAJOR) tb.box[1] = p->desc.block_n / 2;   // each CTA of a pair fetches half of B
-      int rc = encode_tmap(&p->map_b, tb, b);
+      const bool f32 = p->desc.tf32 != 0;
+      int rc = encode_tmap(&p->map_b, tb, b, (f32 && p->desc.kind == PCGAN_IGEMM_WGRAD) ? 2 : 1, f32);
       if (rc != PCGAN_OK) return rc;
       p->cached_b = b;
     }

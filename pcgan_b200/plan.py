@@ -126,12 +126,22 @@ class IgemmSpec:
     pair: int = 0              # CTA pairs issuing one tcgen05.mma.cta_group::2 of M = 256 (include/pcgan_kernels.h)
     a_window: int = 0          # 8: A is the plain 8-channel tensor read through an overlapping descriptor (pcgan_kernels.h)
     wg_box_dim: int = 0        # WGRAD: the 64-column boxes of an N tile step along this B tensor dim (filter rows in N)
+    tf32: bool = False         # operands are fp32 tensors multiplied as TF32 (tcgen05.mma.kind::tf32): K chunks of 32 elements
     swap_operands: bool = False  # WGRAD: M side = input activations, N side = dY (ConvRT.backward_weight passes them so)
     box_taps: Optional[List[int]] = None   # wg_box_dim: kidx of the filter row held by 64-column box i of the output
 
     @property
     def num_taps(self):
         return len(self.tap_off)
+
+    @property
+    def kc(self):
+        """elements of one 128-byte K chunk"""
+        return 32 if self.tf32 else 64
+
+    @property
+    def esz(self):
+        return 4 if self.tf32 else 2
 
     def to_desc(self) -> L.IgemmDesc:
         d = L.IgemmDesc()
@@ -164,6 +174,7 @@ class IgemmSpec:
         d.shift_taps, d.shift_cpad = self.shift_taps, self.shift_cpad
         d.a_window = self.a_window
         d.wg_box_dim = self.wg_box_dim
+        d.tf32 = int(self.tf32)
         return d
 
 
@@ -192,8 +203,9 @@ WINDOW = True    # 8-channel inputs: windowed A operand (pcgan_igemm_desc.a_wind
 
 def _pair_kmajor(s: "IgemmSpec", m_tiles: int) -> int:
     """Pair two M tiles (one tcgen05.mma.cta_group::2 of M = 256) for full-width N tiles; narrower tiles run faster
-    unpaired through two pipelines with double-buffered accumulators (measured: tools/bench_conv.py, [pair] / [dual])."""
-    return int(PAIRING and s.block_n >= 256 and m_tiles * s.n_tiles >= 2)
+    unpaired through two pipelines with double-buffered accumulators (measured: tools/bench_conv.py, [pair] / [dual]).
+    TF32 plans run unpaired."""
+    return int(PAIRING and not s.tf32 and s.block_n >= 256 and m_tiles * s.n_tiles >= 2)
 
 
 ANY = (0, 1 << 30, 0)
@@ -201,9 +213,10 @@ ONE = (0, 1, 0)
 
 
 def _set_weights_tmap(s: IgemmSpec, rows: int, k: int):
+    E = s.esz
     s.b_dims = [k, rows, 1, 1, 1]
-    s.b_strides = [0, k * 2, k * 2 * max(rows, 1), k * 2 * max(rows, 1), k * 2 * max(rows, 1)]
-    s.b_box = [64, s.block_n, 1, 1, 1]
+    s.b_strides = [0, k * E, k * E * max(rows, 1), k * E * max(rows, 1), k * E * max(rows, 1)]
+    s.b_box = [s.kc, s.block_n, 1, 1, 1]
     s.b_rows, s.b_k = rows, k
 
 
@@ -221,27 +234,28 @@ def _choose_box(wo, ho, n, single_image):
 
 def plan_box(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, ho: int, wo: int, stride: int,
              out: OutMap, *, act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False,
-             note="") -> IgemmSpec:
+             note="", tf32=False) -> IgemmSpec:
     """Generic "box" plan.  Output pixel (n, y, x) = sum over taps (dy, dx, kidx) and channels of
     Xpadded[n][stride*y + dy][stride*x + dx][:] . Wpacked[:, kidx*cin : (kidx+1)*cin]   (dy, dx >= 0 are
     coordinates in the PADDED buffer).  Requires cin % 64 == 0 and xg.c == cin.
     stride 1 uses a 4-D view (c, x, y, n); stride 2 a 5-D phase view (c, px, X, py, Y*n).
     """
-    assert xg.c == cin and cin % 64 == 0, (xg, cin)
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note, tf32=tf32)
+    kc, E = s.kc, s.esz
+    assert xg.c == cin and cin % kc == 0, (xg, cin)
     assert stride in (1, 2)
-    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
     s.block_n = _block_n(cout)
     s.n_tiles = _ceil(cout, s.block_n)
     s.n_valid = cout
-    s.cchunks = cin // 64
+    s.cchunks = cin // kc
     C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
     bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride == 2)
     tx, ty, tn = _ceil(wo, bw), _ceil(ho, bh), _ceil(N, bn)
     s.t_count = [tx, ty, tn, 1]
     if stride == 1:
         s.a_dims = [C, Wp, Hp, N, 1]
-        s.a_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
-        s.a_box = [64, bw, bh, bn, 1]
+        s.a_strides = [0, C * E, Wp * C * E, Hp * Wp * C * E, N * Hp * Wp * C * E]
+        s.a_box = [kc, bw, bh, bn, 1]
         s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
         for (dy, dx, kidx) in taps:
             s.tap_off.append([dx, dy, 0, 0])
@@ -256,8 +270,8 @@ def plan_box(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, ho
     else:
         assert Hp % 2 == 0 and Wp % 2 == 0, "stride-2 phase view needs even padded extents"
         s.a_dims = [C, 2, Wp // 2, 2, (Hp // 2) * N]
-        s.a_strides = [0, C * 2, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2]
-        s.a_box = [64, 1, bw, 1, bh]
+        s.a_strides = [0, C * E, 2 * C * E, Wp * C * E, 2 * Wp * C * E]
+        s.a_box = [kc, 1, bw, 1, bh]
         # outer dims: d0 = px, d1 = X, d2 = py, d3 = Y (+ n * Hp/2)
         s.a_step[0][1] = bw
         s.a_step[1][3] = bh
@@ -286,23 +300,24 @@ def plan_box(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, ho
 
 def plan_flat(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, out: OutMap,
               yr: Tuple[int, int], xr: Tuple[int, int], *, act=L.ACT_NONE, act_slope=0.0, stats=False,
-              note="") -> IgemmSpec:
+              note="", tf32=False) -> IgemmSpec:
     """"Flat" plan over the flattened padded grid of xg: for every padded position q = (n, Y, X)
     out(q) = sum over taps (dy, dx, kidx) of Xpadded[q + dy*Wp + dx] . W[:, kidx*cin:...]   (dy, dx may be
     negative; rows wrap into neighbouring rows/images, which is harmless when the wrapped reads hit a zero
     halo or the wrapped outputs are masked).  Only positions with yr[0] <= Y < yr[1], xr[0] <= X < xr[1] are
     stored, at out(n, Y - yr[0], X - xr[0]).  Statistics are per channel over all stored rows (batch norm)."""
-    assert xg.c == cin and cin % 64 == 0
-    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note, tf32=tf32)
+    kc, E = s.kc, s.esz
+    assert xg.c == cin and cin % kc == 0
     s.block_n = _block_n(cout)
     s.n_tiles = _ceil(cout, s.block_n)
     s.n_valid = cout
-    s.cchunks = cin // 64
+    s.cchunks = cin // kc
     C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
     P = N * Hp * Wp
     s.a_dims = [C, P, 1, 1, 1]
-    s.a_strides = [0, C * 2, P * C * 2, P * C * 2, P * C * 2]
-    s.a_box = [64, 128, 1, 1, 1]
+    s.a_strides = [0, C * E, P * C * E, P * C * E, P * C * E]
+    s.a_box = [kc, 128, 1, 1, 1]
     # only tiles that intersect stored rows: positions from first valid to last valid
     q_lo = yr[0] * Wp + xr[0]
     q_hi = (N - 1) * Hp * Wp + (yr[1] - 1) * Wp + xr[1]
@@ -331,7 +346,7 @@ def plan_flat(xg: Geom, taps: List[Tuple[int, int, int]], cin: int, cout: int, o
 
 
 def plan_shift_flat(xg: Geom, kh: int, kw: int, cin: int, cout: int, row_taps: List[Tuple[int, int, int]], out: OutMap,
-                    yr: Tuple[int, int], xr: Tuple[int, int], *, out_shift=0, act=L.ACT_NONE, act_slope=0.0, note="") -> IgemmSpec:
+                    yr: Tuple[int, int], xr: Tuple[int, int], *, out_shift=0, act=L.ACT_NONE, act_slope=0.0, note="", tf32=False) -> IgemmSpec:
     """Few-output-channel convolution over the flattened padded grid of xg with the horizontal taps moved into N
     ("shift-sum" epilogue): for GEMM row position t
         partial[t][j*4 + c] = sum over filter rows (dy, dx, r) in row_taps and channels of
@@ -339,17 +354,18 @@ def plan_shift_flat(xg: Geom, kh: int, kw: int, cin: int, cout: int, row_taps: L
     and the value stored at flat position g = t + out_shift is sum_j partial[t + j][j*4 + c], j < kw.  Tiles are 128 rows
     stepping by 128 - (kw - 1).  Positions with yr[0] <= Y < yr[1], xr[0] <= X < xr[1] are stored at
     out(n, Y - yr[0], X - xr[0]).  Every activation row is fetched kh times instead of kh*kw times."""
-    assert xg.c == cin and cin % 64 == 0 and cout <= 4 and kw * 4 <= 32
-    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note, tf32=tf32)
+    kc, E = s.kc, s.esz
+    assert xg.c == cin and cin % kc == 0 and cout <= 4 and kw * 4 <= 32
     s.block_n, s.n_tiles, s.n_valid = 32, 1, cout
     s.shift_taps, s.shift_cpad = kw, 4
-    s.cchunks = cin // 64
+    s.cchunks = cin // kc
     C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
     P = N * Hp * Wp
     S = 128 - (kw - 1)
     s.a_dims = [C, P, 1, 1, 1]
-    s.a_strides = [0, C * 2, P * C * 2, P * C * 2, P * C * 2]
-    s.a_box = [64, 128, 1, 1, 1]
+    s.a_strides = [0, C * E, P * C * E, P * C * E, P * C * E]
+    s.a_box = [kc, 128, 1, 1, 1]
     q_lo = yr[0] * Wp + xr[0]
     q_hi = (N - 1) * Hp * Wp + (yr[1] - 1) * Wp + xr[1]
     tiles = _ceil(q_hi - q_lo, S)
@@ -397,22 +413,23 @@ def wmap_shift(w_shape, k: int, kdim: int, *, dgrad=False, rows=None, cols=None)
 
 
 def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho: int, wo: int, out: OutMap, *,
-                act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, note="") -> IgemmSpec:
+                act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, note="", tf32=False) -> IgemmSpec:
     """Small-Cin plan ("packed rows"): one K chunk covers a whole filter row, because in NHWC the kw taps x C
     channels of a row are contiguous: window = Xpadded[n][stride*y + r + off][stride*x + off ...][0 : kw*C].
     The A view has overlapping strides (dim 1 advances by stride pixels, dim 0 spans 64*cchunks elements).
     Packed weights: W[co][r][s*C + c], zero beyond kw*C.  xg.c in {8, 16, 32}."""
     C, Hp, Wp, N = xg.c, xg.hp, xg.wp, xg.n
+    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note, tf32=tf32)
+    kc, E = s.kc, s.esz
     assert C % 8 == 0 and C < 64
-    s = IgemmSpec(kind=L.IGEMM_KMAJOR, note=note)
     s.block_n = _block_n(cout)
     s.n_tiles = _ceil(cout, s.block_n)
     s.n_valid = cout
-    win = _ceil(kw * C, 64) * 64
-    s.cchunks = win // 64
+    win = _ceil(kw * C, kc) * kc
+    s.cchunks = win // kc
     bw, bh, bn = _choose_box(wo, ho, N, per_sample_stats or stride >= 2)
     tx, ty, tn = _ceil(wo, bw), _ceil(ho, bh), _ceil(N, bn)
-    window = WINDOW and stride == 1 and C == 8 and kw <= 8 and wo >= 64
+    window = WINDOW and not tf32 and stride == 1 and C == 8 and kw <= 8 and wo >= 64
     flat_tiles = _ceil(N * Hp * Wp, 128)
     if window and not stats and flat_tiles < _ceil(wo, 128) * ho * N:
         # windowed form over the flattened padded grid: position q = (n, Y, X) computes output (Y, X) from the window
@@ -458,8 +475,8 @@ def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho
         pass
     elif stride == 1:
         s.a_dims = [win, Wp, Hp, N, 1]
-        s.a_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
-        s.a_box = [64, bw, bh, bn, 1]
+        s.a_strides = [0, C * E, Wp * C * E, Hp * Wp * C * E, N * Hp * Wp * C * E]
+        s.a_box = [kc, bw, bh, bn, 1]
         s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
         for r in range(kh):
             s.tap_off.append([off, r + off, 0, 0])
@@ -475,8 +492,8 @@ def plan_packed(xg: Geom, kh: int, kw: int, stride: int, off: int, cout: int, ho
         assert st in (2, 4) and Hp % st == 0 and Wp % st == 0, "strided packed rows need padded extents that are multiples of the stride"
         # dims: (window, X [st pixels per step], row phase, Y (+ n*Hp/st)); the x offset `off` goes into the base pointer
         s.a_dims = [win, Wp // st, st, (Hp // st) * N, 1]
-        s.a_strides = [0, st * C * 2, Wp * C * 2, st * Wp * C * 2, (Hp // st) * N * st * Wp * C * 2]
-        s.a_box = [64, bw, 1, bh, 1]
+        s.a_strides = [0, st * C * E, Wp * C * E, st * Wp * C * E, (Hp // st) * N * st * Wp * C * E]
+        s.a_box = [kc, bw, 1, bh, 1]
         s.a_elem_offset = off * C
         s.a_step[0][0] = bw
         s.a_step[1][2] = bh
@@ -532,7 +549,7 @@ def _ksplit_for(total_kb, out_tiles, paired=False, sms=148):
 
 def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[int, int, int]], ph: int, pw: int,
                    n_stride: int, *, m_origin=(0, 0), n_packed_win: int = 0, m_packed_win: int = 0, pix_box=None,
-                   note="") -> IgemmSpec:
+                   note="", tf32=False) -> IgemmSpec:
     """Weight gradient over a ph x pw pixel grid per sample.
     M side: tensor mg (padded NHWC), pixel (n, y, x) read at padded (y + m_origin[0], x + m_origin[1]), m_ch channels.
     N side: tensor ng, pixel read at padded (n_stride*y + dy, n_stride*x + dx) for tap (dy, dx, kidx);
@@ -541,7 +558,8 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     m_packed_win > 0: the M side is read as a window of that many contiguous elements starting at the pixel (rows
     beyond m_ch are the following pixels' channels; they are computed and dropped).  pix_box = (bw, bh) overrides
     the 64-pixel box shape."""
-    s = IgemmSpec(kind=L.IGEMM_WGRAD, note=note)
+    s = IgemmSpec(kind=L.IGEMM_WGRAD, note=note, tf32=tf32)
+    kc, E = s.kc, s.esz          # TF32: boxes of 64 pixels x 32 channels (128 bytes), K step of the MMA = 8 pixels
     bw, bh = pix_box if pix_box else _pix_box64(pw, ph)
     assert bw * bh == 64
     bn = 1
@@ -556,15 +574,15 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     s.t_count = [tx, ty, tn, 1]
     # M-side view (c, x, y, n)
     s.a_dims = [m_packed_win if m_packed_win else mg.c, mg.wp, mg.hp, N, 1]
-    s.a_strides = [0, mg.c * 2, mg.wp * mg.c * 2, mg.hp * mg.wp * mg.c * 2, N * mg.hp * mg.wp * mg.c * 2]
-    s.a_box = [64, bw, bh, bn, 1]
+    s.a_strides = [0, mg.c * E, mg.wp * mg.c * E, mg.hp * mg.wp * mg.c * E, N * mg.hp * mg.wp * mg.c * E]
+    s.a_box = [kc, bw, bh, bn, 1]
     s.a_base = [m_origin[1], m_origin[0], 0, 0]
     s.a_step[0][0], s.a_step[1][1], s.a_step[2][2] = bw, bh, bn
     C, Hp, Wp = ng.c, ng.hp, ng.wp
     d0 = n_packed_win if n_packed_win else C
     dys = sorted(dy for dy, _, _ in taps)
     kh = len(taps)
-    if (TAPBOX and n_packed_win == 64 and n_stride == 1 and kh > 1 and len(set(dx for _, dx, _ in taps)) == 1
+    if (TAPBOX and not tf32 and n_packed_win == 64 and n_stride == 1 and kh > 1 and len(set(dx for _, dx, _ in taps)) == 1
             and dys == list(range(dys[0], dys[0] + kh)) and ph + dys[0] + kh - 1 <= Hp and dys[0] >= 0):
         # filter rows in N: the B view gets a filter-row dimension (same stride as the image row) and 64-column box i of
         # the N tiles is the window of row dys[0] + i, so the 64-channel M operand is fetched once per N tile of four
@@ -591,8 +609,8 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
         return s
     if n_stride == 1:
         s.b_dims = [d0, Wp, Hp, N, 1]
-        s.b_strides = [0, C * 2, Wp * C * 2, Hp * Wp * C * 2, N * Hp * Wp * C * 2]
-        s.b_box = [64, bw, bh, bn, 1]
+        s.b_strides = [0, C * E, Wp * C * E, Hp * Wp * C * E, N * Hp * Wp * C * E]
+        s.b_box = [kc, bw, bh, bn, 1]
         s.b_step[0][0], s.b_step[1][1], s.b_step[2][2] = bw, bh, bn
         for (dy, dx, kidx) in taps:
             s.tap_off.append([dx, dy, 0, 0])
@@ -602,8 +620,8 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
         assert n_stride == 2 and Hp % 2 == 0 and bn == 1
         if n_packed_win:
             s.b_dims = [d0, Wp // 2, 2, (Hp // 2) * N, 1]
-            s.b_strides = [0, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2, (Hp // 2) * N * 2 * Wp * C * 2]
-            s.b_box = [64, bw, 1, bh, 1]
+            s.b_strides = [0, 2 * C * E, Wp * C * E, 2 * Wp * C * E, (Hp // 2) * N * 2 * Wp * C * E]
+            s.b_box = [kc, bw, 1, bh, 1]
             s.b_step[0][0], s.b_step[1][2], s.b_step[2][2] = bw, bh, Hp // 2
             xoffs = set(dx for _, dx, _ in taps)
             assert len(xoffs) == 1
@@ -615,8 +633,8 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
         else:
             assert Wp % 2 == 0
             s.b_dims = [d0, 2, Wp // 2, 2, (Hp // 2) * N]
-            s.b_strides = [0, C * 2, 2 * C * 2, Wp * C * 2, 2 * Wp * C * 2]
-            s.b_box = [64, 1, bw, 1, bh]
+            s.b_strides = [0, C * E, 2 * C * E, Wp * C * E, 2 * Wp * C * E]
+            s.b_box = [kc, 1, bw, 1, bh]
             s.b_step[0][1], s.b_step[1][3], s.b_step[2][3] = bw, bh, Hp // 2
             for (dy, dx, kidx) in taps:
                 s.tap_off.append([dx % 2, dx // 2, dy % 2, dy // 2])
@@ -626,7 +644,7 @@ def plan_wgrad_box(mg: Geom, m_ch: int, ng: Geom, n_ch: int, taps: List[Tuple[in
     s.ldo = nk * ncols
     s.b_rows, s.b_k = m_ch, s.ldo
     total_kb = tx * ty * tn
-    s.pair = int(PAIRING and s.m_tiles % 2 == 0 and (s.block_n // 64) % 2 == 0)
+    s.pair = int(PAIRING and not tf32 and s.m_tiles % 2 == 0 and (s.block_n // 64) % 2 == 0)
     s.ksplit = _ksplit_for(total_kb, len(taps) * s.m_tiles * s.n_tiles, bool(s.pair))
     s.flops = 2 * total_kb * 64 * 128 * s.m_tiles * s.n_tiles * s.block_n * len(taps)
     return s

@@ -276,3 +276,94 @@ def test_plan_create_rejects_inconsistent_descriptors():
     with pytest.raises(PcganError):
         ops.Igemm(sp)
 
+
+
+# ------------------------------------------------------------------------------------------- TF32 plans
+# The same planner with tf32=True (fp32 operands, K chunks of 32 elements, 64 x 32 weight-gradient boxes): the emulator
+# reads the descriptors with 4-byte elements.  (Arithmetic here is exact fp32 either way: this validates the planning.)
+TF32_FWD = [c for c in FWD_CASES if c[0] in ("res3x3_reflect", "down3x3_s2", "d4x4_s2", "d4x4_s1", "stem7x7_packed", "dstem4x4_s2_packed",
+                                             "head7x7_n3", "e3x3_7", "e1x1_s2", "wide_n512")]
+
+
+@pytest.mark.parametrize("case", TF32_FWD, ids=[c[0] for c in TF32_FWD])
+def test_conv_forward_plan_tf32(case):
+    _, cin, cbuf, cout, k, stride, cp, halo, xpad, H, W, N = case
+    torch.manual_seed(0)
+    x, w, bias = torch.randn(N, cin, H, W), torch.randn(cout, cin, k, k) * 0.1, torch.randn(cout)
+    xg = Geom(N, H, W, cbuf, xpad)
+    ho, wo = CV.out_size(H, k, stride, cp), CV.out_size(W, k, stride, cp)
+    og = Geom(N, ho, wo, max(8, -(-cout // 8) * 8), 1)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, stride, cp, OutMap.nhwc(og, dtype=L.DT_F32), stats=True, tf32=True)
+    assert all(sp.tf32 and sp.a_box[0] == 32 and not sp.pair and not sp.a_window for sp, _ in plans)
+    stats = torch.zeros(1, cout, 2)
+    out = run_fwd(plans, to_padded_nhwc(x, xpad, halo, cbuf), w, og.numel, bias=bias, stats=stats)
+    got = from_padded_nhwc(out, N, ho, wo, og.c, 1)[:, :cout]
+    xr = F.pad(bf16_round(x), (cp,) * 4, mode="reflect" if halo == "reflect" else "constant")
+    ref = F.conv2d(xr, bf16_round(w), bias, stride=stride)
+    assert rel(got, ref) < 1e-5
+    assert rel(stats[0, :, 1], (ref * ref).sum((0, 2, 3))) < 1e-4
+
+
+def test_conv_transpose_forward_plan_tf32():
+    torch.manual_seed(2)
+    N, cin, cout, H = 2, 128, 64, 8
+    x, w = torch.randn(N, cin, H, H), torch.randn(cin, cout, 3, 3) * 0.1
+    xg, og = Geom(N, H, H, cin, 1), Geom(N, 2 * H, 2 * H, cout, 0)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, 2, 1, OutMap.nhwc(og, dtype=L.DT_F32), transposed=True, output_padding=1, tf32=True)
+    out = run_fwd(plans, to_padded_nhwc(x, 1, "zero"), w, og.numel)
+    ref = F.conv_transpose2d(bf16_round(x), bf16_round(w), stride=2, padding=1, output_padding=1)
+    assert rel(from_padded_nhwc(out, N, 2 * H, 2 * H, cout, 0), ref) < 1e-5
+
+
+TF32_DGRAD = [c for c in DGRAD_CASES if c[0] in ("res3x3_flat_full", "res3x3_flat_interior", "head7x7_packed_full", "d4x4_s1_box", "down3x3_s2",
+                                                 "d4x4_s2", "dstem4x4_s2_to4", "stem7x7_to4_full")]
+
+
+@pytest.mark.parametrize("case", TF32_DGRAD, ids=[c[0] for c in TF32_DGRAD])
+def test_conv_dgrad_plan_tf32(case):
+    _, cin, cout, cobuf, k, stride, cp, xpad, full, H, N, dypad = case
+    torch.manual_seed(3)
+    w = torch.randn(cout, cin, k, k) * 0.1
+    ho = CV.out_size(H, k, stride, cp)
+    dy = torch.randn(N, cout, ho, ho)
+    cibuf = max(8, -(-cin // 8) * 8)
+    xg = Geom(N, H, H, cibuf, xpad)
+    flat_same = stride == 1 and ho == H and cobuf >= 64
+    dyg = Geom(N, ho, ho, cobuf, xpad if flat_same else dypad)
+    og = Geom(N, H + 2 * xpad, H + 2 * xpad, cibuf, 0) if full else Geom(N, H, H, cibuf, 0)
+    plans = CV.conv_dgrad_plans(tuple(w.shape), dyg, xg, stride, cp, OutMap.nhwc(og, dtype=L.DT_F32), full_padded=full, tf32=True)
+    assert all(sp.tf32 for sp, _ in plans)
+    out = run_fwd(plans, to_padded_nhwc(dy, dyg.pad, "zero", cobuf), w, og.numel)
+    got = from_padded_nhwc(out, N, og.h, og.w, cibuf, 0)[:, :cin]
+    xp = torch.zeros(N, cin, H + 2 * xpad, H + 2 * xpad, requires_grad=True)
+    o = xpad - cp
+    xin = xp[:, :, o:H + 2 * xpad - o, o:H + 2 * xpad - o] if o > 0 else xp
+    F.conv2d(xin, bf16_round(w), stride=stride).backward(bf16_round(dy))
+    ref = xp.grad if full else xp.grad[:, :, xpad:xpad + H, xpad:xpad + H]
+    assert rel(got, ref) < 1e-5
+
+
+TF32_WGRAD = [c for c in WGRAD_CASES if c[0] in ("res3x3", "res3x3_c256", "down3x3_s2", "d4x4_s2", "d4x4_s1_odd", "stem7x7_packed", "head7x7_cout3")]
+
+
+@pytest.mark.parametrize("case", TF32_WGRAD, ids=[c[0] for c in TF32_WGRAD])
+def test_conv_wgrad_plan_tf32(case):
+    _, cin, cbuf, cout, cobuf, k, stride, cp, halo, xpad, H, N, dypad = case
+    torch.manual_seed(5)
+    x = torch.randn(N, cin, H, H)
+    ho = CV.out_size(H, k, stride, cp)
+    dy = torch.randn(N, cout, ho, ho)
+    xg, dyg = Geom(N, H, H, cbuf, xpad), Geom(N, ho, ho, cobuf, dypad)
+    sp, wm = CV.conv_wgrad_plan((cout, cin, k, k), dyg, xg, stride, cp, tf32=True)
+    assert sp.tf32 and not sp.pair and not sp.swap_operands and sp.a_box[0] == 32
+    ops.Igemm(sp)
+    packed = torch.zeros(sp.b_rows * sp.b_k)
+    dyb, xb = to_padded_nhwc(dy, dypad, "zero", cobuf), to_padded_nhwc(x, xpad, halo, cbuf)
+    emu.run_wgrad(sp, dyb[sp.a_elem_offset:], xb[sp.b_elem_offset:], packed)
+    dw = torch.zeros(cout * cin * k * k)
+    idx = wm.long()
+    dw[idx[idx >= 0]] = packed[idx >= 0]
+    xr = F.pad(bf16_round(x), (cp,) * 4, mode="reflect" if halo == "reflect" else "constant")
+    wref = torch.zeros(cout, cin, k, k, requires_grad=True)
+    F.conv2d(xr, wref, stride=stride).backward(bf16_round(dy))
+    assert rel(dw.view(cout, cin, k, k), wref.grad) < 1e-5
