@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 15
+#define PCGAN_ABI_VERSION 16
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -184,6 +184,8 @@ int pcgan_igemm_run(pcgan_igemm_plan* plan, const void* a, const void* b, void* 
  * [rows][K] bf16 operand of a plan. */
 int pcgan_gather_cast_bf16(const float* src, const int32_t* idx, void* dst_bf16, int64_t n, pcgan_stream_t stream);
 /* dst[idx[i]] (+)= src[i] for idx[i] >= 0: packed fp32 weight gradient -> .grad in OIHW. */
+/* packed fp32 operand of a TF32 plan: dst[i] = idx[i] >= 0 ? round_to_nearest_tf32(src[idx[i]]) : 0 */
+int pcgan_gather_tf32(const float* src, const int32_t* idx, float* dst, int64_t n, pcgan_stream_t stream);
 int pcgan_scatter_f32(const float* src, const int32_t* idx, float* dst, int64_t n, int32_t accumulate, pcgan_stream_t stream);
 
 /* The same two operations for many tensors in ONE launch: `items` is a device array of `count` descriptors (a network's

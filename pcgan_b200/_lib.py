@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -131,6 +131,7 @@ SYMBOLS = {
     "pcgan_igemm_plan_destroy": (None, [vp]),
     "pcgan_igemm_run": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "pcgan_gather_cast_bf16": (C.c_int, [vp, vp, vp, i64, vp]),
+    "pcgan_gather_tf32": (C.c_int, [vp, vp, vp, i64, vp]),
     "pcgan_scatter_f32": (C.c_int, [vp, vp, vp, i64, i32, vp]),
     "pcgan_gather_cast_bf16_batched": (C.c_int, [vp, i32, i64, vp]),
     "pcgan_scatter_f32_batched": (C.c_int, [vp, i32, i64, i32, vp]),

@@ -27,6 +27,19 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, const int32_t*
     dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
   }
 }
+// the fp32 packed operand of a TF32 plan, rounded to nearest TF32 here so that the tensor core's truncation of the low
+// mantissa bits loses nothing more
+__global__ void gather_tf32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst, int64_t n) {
+  griddep_wait();
+  griddep_launch();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    uint32_t r;
+    const float v = j >= 0 ? src[j] : 0.f;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    dst[i] = __uint_as_float(r);
+  }
+}
 __global__ void scatter_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
                                int64_t n, int accumulate) {
   griddep_wait();
@@ -498,6 +511,14 @@ extern "C" int pcgan_gather_cast_bf16(const float* src, const int32_t* idx, void
   if (n == 0) return PCGAN_OK;
   PCGAN_CUDA_OK(launch_pdl(gather_cast_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, src, idx, reinterpret_cast<__nv_bfloat16*>(dst), n));
   PCGAN_LAUNCH_OK("gather_cast_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_gather_tf32(const float* src, const int32_t* idx, float* dst, int64_t n, pcgan_stream_t s) {
+  if (!src || !idx || !dst || n < 0) return fail(PCGAN_ERR_INVALID, "gather_tf32: bad argument");
+  if (n == 0) return PCGAN_OK;
+  PCGAN_CUDA_OK(launch_pdl(gather_tf32_kernel, dim3(grid_for(n)), dim3(kThreads), 0, STREAM(s), 1, src, idx, dst, n));
+  PCGAN_LAUNCH_OK("gather_tf32_kernel");
   return PCGAN_OK;
 }
 

@@ -67,13 +67,20 @@ class ConvRT:
 
     def __init__(self, name, weight, bias, xg: Geom, stride, cp, out: OutMap, *, transposed=False, output_padding=0,
                  act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, dyg: Optional[Geom] = None,
-                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True):
+                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True, tf32=False):
+        """tf32=True: the activation / gradient buffers passed to forward / backward_* hold fp32 (same padded NHWC
+        geometry), the packed weights are fp32 rounded to TF32, and the kernels issue tcgen05.mma.kind::tf32 (per-layer
+        error 3e-4 .. 8e-4 instead of 2.4e-3 in bf16).  The network programs of this package run their normalisation
+        kernels on bf16 buffers, so they build their convolutions with tf32=False; a TF32 runtime is what a caller with
+        fp32 activations (or a per-layer precision study) uses."""
         self.name, self.weight, self.bias = name, weight, bias
         # the convolution this runtime was planned for (tests/test_bench_geometry_gpu.py replays every plan against F.conv2d)
         self.geometry = dict(xg=xg, stride=stride, cp=cp, out=out, transposed=transposed, output_padding=output_padding,
                              act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats, dyg=dyg,
                              dx_out=dx_out, full_padded=full_padded)
         self.bank = None
+        self.tf32 = bool(tf32)
+        wdt = torch.float32 if tf32 else torch.bfloat16
         dev = weight.device
         self.dev = dev
         shape = tuple(weight.shape)
@@ -81,13 +88,13 @@ class ConvRT:
         self.fwd = []
         for sp, wm in CV.conv_fwd_plans(shape, xg, stride, cp, out, transposed=transposed, output_padding=output_padding,
                                         act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats,
-                                        note=name + ".fwd"):
-            self.fwd.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=torch.bfloat16, device=dev)))
+                                        note=name + ".fwd", tf32=tf32):
+            self.fwd.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=wdt, device=dev)))
         self.dgrad = []
         if want_dgrad and dyg is not None and dx_out is not None:
             for sp, wm in CV.conv_dgrad_plans(shape, dyg, xg, stride, cp, dx_out, transposed=transposed,
-                                              full_padded=full_padded, note=name + ".dgrad"):
-                self.dgrad.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=torch.bfloat16, device=dev)))
+                                              full_padded=full_padded, note=name + ".dgrad", tf32=tf32):
+                self.dgrad.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=wdt, device=dev)))
         self.wgrad = None
         self._wg_args = (shape, dyg, xg, stride, cp, transposed, name)
         if want_wgrad and dyg is not None:
@@ -101,7 +108,7 @@ class ConvRT:
             shape, dyg, xg, stride, cp, transposed, name = self._wg_args
             if dyg is None:
                 raise L.PcganError("%s: no output-gradient geometry was planned, cannot build a weight gradient" % name)
-            sp, wm = CV.conv_wgrad_plan(shape, dyg, xg, stride, cp, transposed=transposed, note=name + ".wgrad")
+            sp, wm = CV.conv_wgrad_plan(shape, dyg, xg, stride, cp, transposed=transposed, note=name + ".wgrad", tf32=self.tf32)
             self.wgrad = (ops.Igemm(sp), wm.to(self.dev), torch.zeros(sp.b_rows * sp.b_k, dtype=torch.float32, device=self.dev))
         return self.wgrad
 
@@ -111,10 +118,11 @@ class ConvRT:
         if v == self._wver:
             return
         w = self.weight.detach()
+        gather = ops.gather_tf32 if self.tf32 else ops.gather_cast_bf16
         for _, wm, buf in self.fwd:
-            ops.gather_cast_bf16(w, wm, buf)
+            gather(w, wm, buf)
         for _, wm, buf in self.dgrad:
-            ops.gather_cast_bf16(w, wm, buf)
+            gather(w, wm, buf)
         self._wver = v
 
     def forward(self, xbuf, out, stats=None):
@@ -154,6 +162,8 @@ class WeightBank:
 
     def __init__(self, convs, dev):
         self.convs, self.dev = list(convs), dev
+        if any(c.tf32 for c in self.convs):
+            raise L.PcganError("WeightBank batches bf16 operands; TF32 convolutions repack themselves (ConvRT.pack)")
         for c in self.convs:
             c.bank = self
         self.deferred, self.dirty = False, False

@@ -107,6 +107,13 @@ def gather_cast_bf16(src, idx, dst):
         L.check(L.load().pcgan_gather_cast_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_cast_bf16")
 
 
+def gather_tf32(src, idx, dst):
+    """fp32 packed operand of a TF32 plan (values rounded to nearest TF32)"""
+    _count()
+    with _Timed("gather_tf32"):
+        L.check(L.load().pcgan_gather_tf32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_tf32")
+
+
 def scatter_f32(src, idx, dst, accumulate=False):
     _count()
     with _Timed("scatter_f32"):

@@ -34,16 +34,27 @@ def bf(t):
     return t.to(torch.bfloat16).float()
 
 
-def rand_buf(g, halo_zero, valid_c, gen):
-    """Padded NHWC bf16 buffer of geometry g: random interior (channels >= valid_c zero), random or zero halo."""
+def tf32_round(t):
+    """fp32 -> nearest TF32 (10-bit mantissa), ties away from zero: what cvt.rna.tf32.f32 does.  A TF32-mode producer
+    stores its activations this way (the tensor core then truncates nothing), exactly as cuDNN rounds its fp32 inputs."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def rand_buf(g, halo_zero, valid_c, gen, dtype=torch.bfloat16):
+    """Padded NHWC buffer of geometry g (bf16, or fp32 for TF32 plans): random interior (channels >= valid_c zero),
+    random or zero halo."""
     t = torch.randn(g.n, g.hp, g.wp, g.c, device=DEV, generator=gen)
     t[..., valid_c:] = 0
     if halo_zero and g.pad:
         m = torch.zeros(g.hp, g.wp, device=DEV)
         m[g.pad:g.pad + g.h, g.pad:g.pad + g.w] = 1
         t = t * m.view(1, g.hp, g.wp, 1)
-    flat = torch.cat([t.to(torch.bfloat16).reshape(-1), torch.zeros(SLACK, dtype=torch.bfloat16, device=DEV)])
-    return flat, t.to(torch.bfloat16).float().permute(0, 3, 1, 2)      # flat buffer, [N, C, Hp, Wp] fp32 view of it
+    if dtype == torch.float32:      # TF32 mode: the buffer holds TF32-rounded values, the reference sees the fp32 originals
+        flat = torch.cat([tf32_round(t).reshape(-1), torch.zeros(SLACK, dtype=dtype, device=DEV)])
+        return flat, t.permute(0, 3, 1, 2)
+    flat = torch.cat([t.to(dtype).reshape(-1), torch.zeros(SLACK, dtype=dtype, device=DEV)])
+    return flat, t.to(dtype).float().permute(0, 3, 1, 2)      # flat buffer, [N, C, Hp, Wp] fp32 view of it
 
 
 def alloc_out(om, n, c, h, w):
@@ -67,13 +78,27 @@ def act_ref(y, act, slope):
     return y
 
 
-def check_conv(conv, gen, log):
+def tf32_twin(conv):
+    """The same convolution as a TF32 runtime: fp32 buffers and outputs, tcgen05.mma.kind::tf32."""
+    from dataclasses import replace
+    from pcgan_b200.engine import ConvRT
     q = conv.geometry
+    f32 = lambda om: replace(om, dtype=L.DT_F32) if om is not None else None
+    return ConvRT(conv.name + "[tf32]", conv.weight, conv.bias, q["xg"], q["stride"], q["cp"], f32(q["out"]), transposed=q["transposed"],
+                  output_padding=q["output_padding"], act=q["act"], act_slope=q["act_slope"], stats=q["stats"],
+                  per_sample_stats=q["per_sample_stats"], dyg=q["dyg"], dx_out=f32(q["dx_out"]), full_padded=q["full_padded"], tf32=True)
+
+
+def check_conv(conv, gen, log, tf32=False):
+    q = conv.geometry
+    dt = torch.float32 if tf32 else torch.bfloat16
+    # bf16: products are exact, only summation order differs.  TF32: BASELINE.json's per-layer gate, 1e-3.
+    T_OUT16, T_OUT32, T_W, T_S = (1e-3, 1e-3, 1e-3, 2e-3) if tf32 else (4e-3, 2e-5, 4e-5, 1e-4)
     xg, stride, cp, tr = q["xg"], q["stride"], q["cp"], q["transposed"]
     w = conv.weight.detach()
     k = w.shape[2]
     cin, cout = (w.shape[0], w.shape[1]) if tr else (w.shape[1], w.shape[0])
-    wq = bf(w).clone().requires_grad_(True)
+    wq = (w if tf32 else bf(w)).clone().requires_grad_(True)
     bias = conv.bias.detach() if conv.bias is not None else None
     o = xg.pad - cp
 
@@ -85,7 +110,7 @@ def check_conv(conv, gen, log):
         return F.conv2d(xi, wq, bias, stride=stride)
 
     # ---- forward
-    xbuf, xfull = rand_buf(xg, halo_zero=tr, valid_c=cin, gen=gen)
+    xbuf, xfull = rand_buf(xg, halo_zero=tr, valid_c=cin, gen=gen, dtype=dt)
     ho = out_size(xg.h, k, stride, cp, tr, q["output_padding"])
     om = q["out"]
     out = alloc_out(om, xg.n, cout, ho, ho)
@@ -97,7 +122,7 @@ def check_conv(conv, gen, log):
         pre = fwd_ref(xfull)
     e = rel(read_out(out, om, xg.n, cout, ho, ho), act_ref(pre, q["act"], q["act_slope"]))
     log.append((conv.name + ".fwd", e))
-    assert e < (4e-3 if om.dtype == L.DT_BF16 else 2e-5), (conv.name, "fwd", e)
+    assert e < (T_OUT16 if om.dtype == L.DT_BF16 else T_OUT32), (conv.name, "fwd", e)
     if stats is not None:
         dims = (2, 3) if q["per_sample_stats"] else (0, 2, 3)
         s1, s2 = pre.sum(dims).view(groups, cout), (pre * pre).sum(dims).view(groups, cout)
@@ -106,12 +131,12 @@ def check_conv(conv, gen, log):
         # sums of ~1e4-1e6 fp32 terms in a different order; sum(x) of a zero-mean channel is a cancellation, so it is
         # bounded against sqrt(count * sum(x^2)) >= |sum(x)|
         cnt = ho * ho * (xg.n // groups)
-        assert e2 < 1e-4 and bool(((stats[..., 0] - s1).abs() <= 1e-4 * (cnt * s2).sqrt() + 1e-6).all()), (conv.name, "stats", e1, e2)
+        assert e2 < T_S and bool(((stats[..., 0] - s1).abs() <= T_S * (cnt * s2).sqrt() + 1e-6).all()), (conv.name, "stats", e1, e2)
     # ---- backward operands
     dyg = q["dyg"]
     if dyg is None:
         return
-    dybuf, dyfull = rand_buf(dyg, halo_zero=True, valid_c=cout, gen=gen)
+    dybuf, dyfull = rand_buf(dyg, halo_zero=True, valid_c=cout, gen=gen, dtype=dt)
     assert dyg.h == ho, (conv.name, dyg, ho)
     dy = dyfull[:, :cout, dyg.pad:dyg.pad + dyg.h, dyg.pad:dyg.pad + dyg.w].contiguous()
     # the backward reference runs in fp64 (its own fp32 summation error over ~1e6 pixels would be as large as ours)
@@ -131,14 +156,14 @@ def check_conv(conv, gen, log):
         conv.backward_data(dybuf, dx)
         e = rel(read_out(dx, dm, xg.n, cb, hh, hh)[:, :cin], want)
         log.append((conv.name + ".dgrad", e))
-        assert e < (4e-3 if dm.dtype == L.DT_BF16 else 2e-5), (conv.name, "dgrad", e)
+        assert e < (T_OUT16 if dm.dtype == L.DT_BF16 else T_OUT32), (conv.name, "dgrad", e)
     # ---- weight gradient
     conv.weight.grad = None
     conv.weight.requires_grad_(True)
     conv.backward_weight(dybuf, xbuf)
     e = rel(conv.weight.grad, wq.grad)
     log.append((conv.name + ".wgrad", e))
-    assert e < 4e-5, (conv.name, "wgrad", e)
+    assert e < T_W, (conv.name, "wgrad", e)
     conv.weight.grad = None
 
 
@@ -176,3 +201,19 @@ def test_every_plan_of_the_step(B, S, SE):
     worst = sorted(log, key=lambda t: -t[1])[:8]
     print("B=%d S=%d: %d convolutions, %d checks; worst:" % (B, S, n, len(log)), ["%s %.2e" % t for t in worst])
     assert n >= 20
+
+
+@pytest.mark.parametrize("B,S,SE", [(64, 128, 224), (3, 64, 96)], ids=["c128_b64", "ragged_b3"])
+def test_every_plan_of_the_step_tf32(B, S, SE):
+    """The same sweep in TF32 mode: every convolution of G, D and E re-planned with tf32=True (fp32 buffers, fp32 packed
+    weights rounded to TF32, tcgen05.mma.kind::tf32) within BASELINE.json's per-layer TF32 gate of 1e-3."""
+    gen = torch.Generator(device=DEV).manual_seed(B * 1000 + S + 1)
+    log, n = [], 0
+    for prog in _programs(B, S, SE):
+        for conv in _distinct(prog.bank.convs):
+            check_conv(tf32_twin(conv), gen, log, tf32=True)
+            n += 1
+    torch.cuda.synchronize()
+    worst = sorted(log, key=lambda t: -t[1])[:8]
+    print("TF32 B=%d S=%d: %d convolutions, %d checks; worst:" % (B, S, n, len(log)), ["%s %.2e" % t for t in worst])
+    assert n >= 20 and max(e for name, e in log if not name.endswith(".stats")) > 1e-5      # really TF32 products, not fp32
