@@ -58,6 +58,12 @@ def main():
             ops.norm_bwd_reduce(g, 0, r, gr, **kw)
             ops.norm_bwd_apply(g, 0, r, gr, dx=dx, dx_pad=pad, **kw)
         report("reduce->apply back to back " + tag, timeit(both), el * 10)
+        if H == 32:      # the one-launch cluster kernel (off by default in the step: see pcgan_b200/ops.py)
+            def fused():
+                ops.NORM_FUSED = True
+                ops.norm_bwd(g, 0, r, gr, dx=dx, dx_pad=pad, **kw)
+                ops.NORM_FUSED = False
+            report("norm_bwd one-pass cluster kernel " + tag, timeit(fused), el * 6)
         report("halo_fold(+add) " + tag, timeit(lambda: ops.halo_fold(gpad, gp, dx, 0, halo=L.HALO_REFLECT, add=g, add_pad=0)), el * 4 + gfull.numel * 2)
         report("norm_finalize [%d][%d]" % (N, C), timeit(lambda: ops.norm_finalize(ns.stats, N, C, H * H, mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift)), N * C * 24)
     a = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)

@@ -6,7 +6,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[0]
 col = {h: i for i, h in enumerate(hdr)}
-names = {0x30000: "full(MMA waits TMA)", 0x30080: "empty(TMA waits MMA)", 0x30100: "tmem_full(epi waits MMA)", 0x30110: "tmem_empty(MMA waits epi)"}
+names = {0x30000: "full(MMA waits TMA)", 0x30080: "empty(TMA waits MMA)", 0x30100: "tmem_full(epi waits MMA)", 0x30120: "tmem_empty(MMA waits epi)"}
 for k, r in enumerate(rows[2:]):
     dur = r[col["gpu__time_duration.sum"]]
     tp = r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]
