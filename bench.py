@@ -184,7 +184,8 @@ class StepRunner:
             self.model, self.loss = None, None
             self.n_losses = 1
             return
-        opt = default_options(batchSize=B, gpu_ids=[local], fineSize=S, loadSize=S, cuda_graph=not args.no_graph, **WORKLOADS[self.kind]["flags"])
+        opt = default_options(batchSize=B, gpu_ids=[local], fineSize=S, loadSize=S, cuda_graph=not args.no_graph,
+                              group_passes=os.environ.get("PCGAN_GROUP", "1") != "0", **WORKLOADS[self.kind]["flags"])
         self.model = WSGANEmbModel()
         with contextlib.redirect_stdout(sys.stderr):   # the factories print like the reference's do; stdout carries only the JSON line
             self.model.initialize(opt)

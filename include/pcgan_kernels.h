@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 16
+#define PCGAN_ABI_VERSION 17
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -164,6 +164,9 @@ typedef struct {
    * elements (still 128 bytes), WGRAD boxes are 64 pixels x 32 channels, box[0] of both maps is 32; no pairing, no
    * windowed A.  Everything else (tap tables, tile maps, epilogue) is unchanged. */
   int32_t tf32;
+  /* statistics group = (sample index selected by stats_dim / stats_comp) / stats_div; 0 or 1: the sample itself.
+   * stats_div = samples per group batches several BatchNorm batches (passes of a network) into one launch. */
+  int32_t stats_div;
 } pcgan_igemm_desc;
 
 typedef struct pcgan_igemm_plan pcgan_igemm_plan;
@@ -294,6 +297,9 @@ typedef struct {
   int64_t* num_batches_tracked;              /* scalar, may be NULL */
   int32_t groups, c;
   float count, momentum;
+  int32_t sequential;   /* 0: the groups are the samples of one pass (InstanceNorm: batch mean of the instance statistics);
+                           1: the groups are successive BatchNorm batches, one momentum step each, in order */
+  int32_t reserved_;
 } pcgan_running_item;
 int pcgan_norm_running_batched(const pcgan_running_item* items, int32_t count, int32_t max_c, pcgan_stream_t stream);
 

@@ -97,6 +97,8 @@ def run_kmajor(s, a_flat, b_flat, out_flat, bias=None, stats=None):
             sr = g0 % p1 if p1 > 0 else g0
             s1 = torch.div(sr, p2, rounding_mode="floor") if p2 > 0 else sr
             group = s0 if s.stats_comp == 0 else s1
+            if getattr(s, "stats_div", 0) > 1:
+                group = torch.div(group, s.stats_div, rounding_mode="floor")
     for nt in range(s.n_tiles):
         acc = torch.zeros(m_tiles, 128, s.block_n, dtype=torch.float32)
         for t in range(s.num_taps):

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -47,7 +47,7 @@ class IgemmDesc(C.Structure):
         ("out_dtype", i32), ("act", i32), ("act_slope", f32), ("n_valid", i32), ("out_cstride", i64),
         ("stats_mode", i32), ("stats_dim", i32), ("stats_comp", i32),
         ("m_valid", i32), ("wg_ncols", i32), ("ldo", i64), ("pair", i32), ("shift_taps", i32), ("shift_cpad", i32),
-        ("a_window", i32), ("wg_box_dim", i32), ("tf32", i32),
+        ("a_window", i32), ("wg_box_dim", i32), ("tf32", i32), ("stats_div", i32),
     ]
 
 
@@ -57,7 +57,7 @@ class BatchItem(C.Structure):
 
 class RunningItem(C.Structure):
     _fields_ = [("stats", vp), ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
-                ("groups", i32), ("c", i32), ("count", f32), ("momentum", f32)]
+                ("groups", i32), ("c", i32), ("count", f32), ("momentum", f32), ("sequential", i32), ("reserved_", i32)]
 
 
 class PackArgs(C.Structure):

@@ -81,7 +81,7 @@ struct DevParams {
   float act_slope;
   int32_t n_valid;
   int64_t out_cstride;
-  int32_t stats_mode, stats_dim, stats_comp;
+  int32_t stats_mode, stats_dim, stats_comp, stats_div;
   int32_t m_valid, wg_ncols;
   int64_t ldo;
   void* out;
@@ -115,7 +115,8 @@ __device__ __forceinline__ int32_t tile_group(const DevParams& P, const Digits& 
   int32_t s0 = 0, srem = g0, s1;
   if (P.e_p1[dim] > 0) { s0 = g0 / P.e_p1[dim]; srem = g0 % P.e_p1[dim]; }
   if (P.e_p2[dim] > 0) { s1 = srem / P.e_p2[dim]; } else { s1 = srem; }
-  return P.stats_comp == 0 ? s0 : s1;
+  const int32_t smp = P.stats_comp == 0 ? s0 : s1;
+  return P.stats_div > 1 ? smp / P.stats_div : smp;
 }
 
 // ------------------------------------------------------------------ schedule
@@ -1122,7 +1123,7 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   memcpy(v.e_p1, d->e_p1, sizeof(v.e_p1)); memcpy(v.e_p2, d->e_p2, sizeof(v.e_p2));
   memcpy(v.e_comp, d->e_comp, sizeof(v.e_comp));
   v.out_dtype = d->out_dtype; v.act = d->act; v.act_slope = d->act_slope; v.n_valid = d->n_valid;
-  v.out_cstride = d->out_cstride; v.stats_mode = d->stats_mode; v.stats_dim = d->stats_dim; v.stats_comp = d->stats_comp;
+  v.out_cstride = d->out_cstride; v.stats_mode = d->stats_mode; v.stats_dim = d->stats_dim; v.stats_comp = d->stats_comp; v.stats_div = d->stats_div;
   v.m_valid = d->m_valid; v.wg_ncols = d->wg_ncols; v.ldo = d->ldo;
   *out = p;
   return PCGAN_OK;

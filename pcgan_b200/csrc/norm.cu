@@ -14,6 +14,10 @@ namespace pcgan {
 
 static constexpr int kT = 256;   // threads per block
 
+// Statistics group of sample n: one per sample (InstanceNorm), one for the batch (BatchNorm), or `groups` equal runs of
+// consecutive samples (several independent BatchNorm batches in one launch: the passes of a network batched together)
+__device__ __forceinline__ int group_of(int n, int groups, int n_total) { return groups > 1 ? n / (n_total / groups) : 0; }
+
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void unpack8(const uint4 u, float (&v)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -98,8 +102,24 @@ __global__ void __launch_bounds__(kT) norm_running_batched_kernel(const pcgan_ru
   griddep_launch();
   const pcgan_running_item it = items[blockIdx.y];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && it.num_batches_tracked) *it.num_batches_tracked += 1;
+  if (c == 0 && it.num_batches_tracked) *it.num_batches_tracked += it.sequential ? it.groups : 1;
   if (c >= it.c) return;
+  const float unbias_ = it.count > 1.f ? it.count / (it.count - 1.f) : 1.f;
+  if (it.sequential) {
+    // the groups are successive BatchNorm batches (passes of the network batched into one launch): one EMA step each, in order
+    float rm = it.running_mean ? it.running_mean[c] : 0.f, rv = it.running_var ? it.running_var[c] : 0.f;
+    for (int g = 0; g < it.groups; ++g) {
+      const float2 s = reinterpret_cast<const float2*>(it.stats)[static_cast<int64_t>(g) * it.c + c];
+      const float mean = s.x / it.count;
+      float var = s.y / it.count - mean * mean;
+      var = var > 0.f ? var : 0.f;
+      rm = (1.f - it.momentum) * rm + it.momentum * mean;
+      rv = (1.f - it.momentum) * rv + it.momentum * (var * unbias_);
+    }
+    if (it.running_mean) it.running_mean[c] = rm;
+    if (it.running_var) it.running_var[c] = rv;
+    return;
+  }
   float macc = 0.f, vacc = 0.f;
   for (int g = 0; g < it.groups; ++g) {
     const float2 s = reinterpret_cast<const float2*>(it.stats)[static_cast<int64_t>(g) * it.c + c];
@@ -237,7 +257,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
   for (int j = 0; j < (RES ? 8 : 1); ++j) { rsc[j] = 1.f; rsh[j] = 0.f; }
   if (a.stats) {
     // fused finalize: the same arithmetic as norm_finalize_kernel, for this thread's 8 channels of its group
-    const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+    const int64_t so = static_cast<int64_t>(group_of(n, a.groups, a.n)) * a.c + c0;
     float st[16];
     load_f8(a.stats + so * 2, *reinterpret_cast<float(*)[8]>(st));
     load_f8(a.stats + so * 2 + 8, *reinterpret_cast<float(*)[8]>(st + 8));
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
       }
     }
   } else if (a.scale) {
-    const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+    const int64_t so = static_cast<int64_t>(group_of(n, a.groups, a.n)) * a.c + c0;
     load_f8(a.scale + so, sc);
     load_f8(a.shift + so, sh);
   }
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
   }
   if constexpr (RES) {
     if (a.res_scale) {
-      const int64_t ro = static_cast<int64_t>(a.res_groups > 1 ? n : 0) * a.c + c0;
+      const int64_t ro = static_cast<int64_t>(group_of(n, a.res_groups, a.n)) * a.c + c0;
       load_f8(a.res_scale + ro, rsc);
       load_f8(a.res_shift + ro, rsh);
     }
@@ -446,7 +466,7 @@ struct BwdCtx {
     for (int j = 0; j < (GEN ? 8 : 1); ++j) { mean[j] = 0.f; rstd[j] = 0.f; mk[j] = 1.f; pm[j] = 1.f; }
 #pragma unroll
     for (int j = 0; j < (RES ? 8 : 1); ++j) { rsc[j] = 1.f; rsh[j] = 0.f; }
-    const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+    const int64_t so = static_cast<int64_t>(group_of(n, a.groups, a.n)) * a.c + c0;
     if (a.scale) { load_f8(a.scale + so, sc); load_f8(a.shift + so, sh); }
     if constexpr (GEN) {
       if (a.mean) { load_f8(a.mean + so, mean); load_f8(a.rstd + so, rstd); }
@@ -455,7 +475,7 @@ struct BwdCtx {
     }
     if constexpr (RES) {
       if (a.res_scale) {
-        const int64_t ro = static_cast<int64_t>(a.res_groups > 1 ? n : 0) * a.c + c0;
+        const int64_t ro = static_cast<int64_t>(group_of(n, a.res_groups, a.n)) * a.c + c0;
         load_f8(a.res_scale + ro, rsc);
         load_f8(a.res_shift + ro, rsh);
       }
@@ -563,7 +583,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_reduce_kernel(pcgan_n
       float sum = 0.f;
       for (int l = 0; l < lanes; ++l) sum += red[(l * cv + c) * 16 + slot];
       const int ch = (c << 3) + (slot & 7);
-      const int64_t o = (static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + ch) * 2 + (slot >> 3);
+      const int64_t o = (static_cast<int64_t>(group_of(n, a.groups, a.n)) * a.c + ch) * 2 + (slot >> 3);
       atomicAdd(a.sums + o, sum);
     }
   }
@@ -595,7 +615,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_no
 #pragma unroll
   for (int j = 0; j < 8; ++j) { A[j] = 0.f; B[j] = 0.f; }
   if (a.count > 0.f) {
-    const int64_t so = (static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0) * 2;
+    const int64_t so = (static_cast<int64_t>(group_of(n, a.groups, a.n)) * a.c + c0) * 2;
     float t0[8], t1[8];
     load_f8(a.sums + so, t0);
     load_f8(a.sums + so + 8, t1);
@@ -698,7 +718,7 @@ __global__ void __launch_bounds__(kFusedT, 1) norm_bwd_fused_kernel(pcgan_norm_b
   const int c0 = (threadIdx.x & (cv - 1)) << 3;
   float sc[8], sh[8];
   {
-    const int64_t so = static_cast<int64_t>(a.groups > 1 ? n : 0) * a.c + c0;
+    const int64_t so = static_cast<int64_t>(group_of(n, a.groups, a.n)) * a.c + c0;
     load_f8(a.scale + so, sc);
     load_f8(a.shift + so, sh);
   }

@@ -67,7 +67,7 @@ class ConvRT:
 
     def __init__(self, name, weight, bias, xg: Geom, stride, cp, out: OutMap, *, transposed=False, output_padding=0,
                  act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, dyg: Optional[Geom] = None,
-                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True, tf32=False):
+                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True, tf32=False, stats_div=0):
         """tf32=True: the activation / gradient buffers passed to forward / backward_* hold fp32 (same padded NHWC
         geometry), the packed weights are fp32 rounded to TF32, and the kernels issue tcgen05.mma.kind::tf32 (per-layer
         error 3e-4 .. 8e-4 instead of 2.4e-3 in bf16).  The network programs of this package run their normalisation
@@ -89,6 +89,7 @@ class ConvRT:
         for sp, wm in CV.conv_fwd_plans(shape, xg, stride, cp, out, transposed=transposed, output_padding=output_padding,
                                         act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats,
                                         note=name + ".fwd", tf32=tf32):
+            sp.stats_div = int(stats_div)      # > 1: per-sample statistics plans emit one statistic per run of stats_div samples
             self.fwd.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=wdt, device=dev)))
         self.dgrad = []
         if want_dgrad and dyg is not None and dx_out is not None:
@@ -326,13 +327,15 @@ class RunningStats:
     def begin(self):
         self.items = []
 
-    def add(self, ns, count, running_mean, running_var, nbt=None, momentum=0.1):
-        self.items.append((ns.stats, running_mean, running_var, nbt, ns.stats.shape[0], ns.c, count, momentum))
+    def add(self, ns, count, running_mean, running_var, nbt=None, momentum=0.1, sequential=False):
+        """sequential: the groups of ns are successive BatchNorm batches (one momentum step each, in order), not the
+        samples of one InstanceNorm pass (whose instance statistics are averaged)."""
+        self.items.append((ns.stats, running_mean, running_var, nbt, ns.stats.shape[0], ns.c, count, momentum, int(sequential)))
 
     def flush(self):
         if not self.items:
             return
-        sig = tuple((it[0].data_ptr(), 0 if it[1] is None else it[1].data_ptr(), 0 if it[3] is None else it[3].data_ptr(), it[6])
+        sig = tuple((it[0].data_ptr(), 0 if it[1] is None else it[1].data_ptr(), 0 if it[3] is None else it[3].data_ptr(), it[6], it[8])
                     for it in self.items)
         if self.table is None or self.table[0] != sig:
             t, max_c = ops.running_table(self.items, self.dev)

@@ -30,7 +30,7 @@ MOMENTUM = 0.1
 # small shared pieces
 # ---------------------------------------------------------------------------------------
 def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, running: RunningStats, *, gamma=None, beta=None, rmean=None,
-                  rvar=None, nbt=None):
+                  rvar=None, nbt=None, sequential=False):
     """conv (+bias) with statistics in the epilogue.  The statistics are finalized by the norm_apply that consumes them
     (NormState.apply_kw) and the running statistics by the pass's one batched launch (`running`)."""
     if not ns.pooled:
@@ -38,7 +38,7 @@ def _unit_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, running: Runni
     ns.affine = gamma is not None
     conv.forward(xbuf, rbuf, ns.stats)
     ns.fused = (count, gamma, beta)
-    running.add(ns, count, rmean, rvar, nbt, MOMENTUM)
+    running.add(ns, count, rmean, rvar, nbt, MOMENTUM, sequential)
 
 
 def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count, dx, dx_pad, *, res=None, res_pad=0,
@@ -363,8 +363,12 @@ class _DiscProgram:
     """NLayerDiscriminator(n_layers=3) at fixed (N, S): conv4x4s2+LReLU, 2x (conv4x4s2 + BN + LReLU),
     conv4x4s1 + BN + LReLU, conv4x4s1 -> 1 (+ sigmoid) (networks.py:745-777)."""
 
-    def __init__(self, mod, N, S):
-        self.mod, self.N, self.S = mod, N, S
+    def __init__(self, mod, N, S, groups=1):
+        """groups > 1: the N samples are `groups` independent passes of the network batched into one (each run of
+        N / groups samples keeps its own BatchNorm batch: statistics, running-statistics step, backward sums)."""
+        if N % groups:
+            raise L.PcganError("NLayerDiscriminator: batch %d is not divisible into %d groups" % (N, groups))
+        self.mod, self.N, self.S, self.groups = mod, N, S, groups
         m = mod.model
         dev = m[0].weight.device
         self.dev = dev
@@ -389,8 +393,9 @@ class _DiscProgram:
                                  act_slope=0.2, dyg=self.g_r[0], dx_out=OutMap.nhwc(G(N, S, S, 8, 0))))
         for li in range(1, len(sizes)):
             stride = 2 if li < len(sizes) - 1 else 1
+            grp = dict(per_sample_stats=True, stats_div=N // groups) if groups > 1 else {}
             self.convs.append(ConvRT("D.model.%d" % self.idx[li], m[self.idx[li]].weight, None, self.g_y[li - 1], stride, 1,
-                                     OutMap.nhwc(self.g_r[li]), stats=True, dyg=self.g_r[li], dx_out=OutMap.nhwc(self.g_r[li - 1])))
+                                     OutMap.nhwc(self.g_r[li]), stats=True, dyg=self.g_r[li], dx_out=OutMap.nhwc(self.g_r[li - 1]), **grp))
         self.g_dyh = G(N, so, so, 8, 2)
         self.head = ConvRT("D.model.%d" % self.i_head, m[self.i_head].weight, m[self.i_head].bias, self.g_y[-1], 1, 1,
                            OutMap.nchw(N, 1, so, so), act=L.ACT_SIGMOID if mod.use_sigmoid else L.ACT_NONE, dyg=self.g_dyh,
@@ -407,7 +412,7 @@ class _DiscProgram:
         ws.y = [zeros_act(g, dev) for g in self.g_y]
         ws.r = [None] + [zeros_act(g, dev) for g in self.g_r[1:]]
         ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
-        ws.ns = [None] + [NormState(1, c, dev, ws.stats_arena, ws.sums_arena) for c in self.chans[1:]]
+        ws.ns = [None] + [NormState(self.groups, c, dev, ws.stats_arena, ws.sums_arena) for c in self.chans[1:]]
         ws.head_sums = ws.sums_arena.take((1, 8, 2))
         ws.l0_sums = ws.sums_arena.take((1, self.chans[0], 2))
         ws.stats_arena.finalize()
@@ -425,9 +430,10 @@ class _DiscProgram:
         self.convs[0].forward(ws.x0, ws.y[0])
         for li in range(1, len(self.sizes)):
             bn = m[self.idx[li] + 1]
-            cnt = N * self.sizes[li] ** 2
+            cnt = (N // self.groups) * self.sizes[li] ** 2
             _unit_forward(self.convs[li], ws.y[li - 1], ws.r[li], ws.ns[li], cnt, ws.running, gamma=bn.weight.detach(),
-                          beta=bn.bias.detach(), rmean=bn.running_mean, rvar=bn.running_var, nbt=bn.num_batches_tracked)
+                          beta=bn.bias.detach(), rmean=bn.running_mean, rvar=bn.running_var, nbt=bn.num_batches_tracked,
+                          sequential=self.groups > 1)
             ops.norm_apply(ws.r[li], self.g_r[li], ws.y[li], self.g_y[li], y_halo=L.HALO_ZERO, **ws.ns[li].apply_kw(), act=L.ACT_LRELU, act_slope=0.2)
         out = torch.empty(N, 1, self.so, self.so, device=self.dev)
         self.head.forward(ws.y[-1], out)
@@ -454,12 +460,13 @@ class _DiscProgram:
         self.head.backward_data(dyh, g)
         for li in range(len(self.sizes) - 1, 0, -1):
             bn = m[self.idx[li] + 1]
-            cnt = N * self.sizes[li] ** 2
+            cnt = (N // self.groups) * self.sizes[li] ** 2
             dy = sc.get(self.g_r[li], "dy%d" % li)
             _norm_backward(g, 0, ws.r[li], self.g_r[li], ws.ns[li], L.ACT_LRELU, 0.2, cnt, dy, 0)
             if need_w:
-                accumulate_grad(bn.weight, ws.ns[li].sums[0, :, 1])
-                accumulate_grad(bn.bias, ws.ns[li].sums[0, :, 0])
+                sums = ws.ns[li].sums[0] if self.groups == 1 else ws.ns[li].sums.sum(0)     # gamma / beta are shared by the groups
+                accumulate_grad(bn.weight, sums[:, 1])
+                accumulate_grad(bn.bias, sums[:, 0])
                 self.convs[li].backward_weight(dy, ws.y[li - 1])
             g = sc.get(self.g_r[li - 1], "g%d" % (li - 1))
             self.convs[li].backward_data(dy, g)
@@ -510,6 +517,7 @@ class NLayerDiscriminator(nn.Module):
             seq += [nn.Identity()]
         self.model = nn.Sequential(*seq)
         self._programs = {}
+        self._groups = 1
         self._key = CO.register_module(self)
 
     def out_size(self, s):
@@ -520,10 +528,16 @@ class NLayerDiscriminator(nn.Module):
         return (so + 2) * (2 ** self.n_layers)
 
     def _program(self, n, s):
-        k = (n, s, self.model[0].weight.device)
+        k = (n, s, self.model[0].weight.device, self._groups)
         if k not in self._programs:
-            self._programs[k] = _DiscProgram(self, n, s)
+            self._programs[k] = _DiscProgram(self, n, s, self._groups)
         return self._programs[k]
+
+    def grouped(self, groups):
+        """Context manager: the next forward calls treat their batch as `groups` independent passes batched together
+        (cat of the inputs along dim 0): each run of N / groups samples has its own BatchNorm batch, exactly as separate
+        calls would, but every layer is one launch."""
+        return _Grouped(self, groups)
 
     def zero_wgrad(self):
         """Deferred weight gradients (defer_wgrad = True): clear the packed accumulators (optimizer.zero_grad time)."""
@@ -544,6 +558,19 @@ class NLayerDiscriminator(nn.Module):
         out = torch.ops.pcgan.nlayer_discriminator(input, z, list(self.parameters()), self._key)
         CO.finish_forward(self._key, out)
         return out
+
+
+class _Grouped:
+    def __init__(self, mod, groups):
+        self.mod, self.groups, self.prev = mod, int(groups), 1
+
+    def __enter__(self):
+        self.prev, self.mod._groups = self.mod._groups, self.groups
+        return self.mod
+
+    def __exit__(self, *exc):
+        self.mod._groups = self.prev
+        return False
 
 
 # ---------------------------------------------------------------------------------------
@@ -717,20 +744,29 @@ class _EncWorkspace:
     pass
 
 
-def _bn_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, bn, running: RunningStats = None, mask=None):
+def _bn_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, bn, running: RunningStats = None, mask=None, explicit=False):
     """conv -> [Dropout2d mask] -> BatchNorm2d statistics (training mode, running stats updated, resnet.py:57-59).
-    With `running` the statistics are finalized by the consuming norm_apply and the running statistics by the pass's
-    batched launch; without (the shortcut BatchNorm, whose scale / shift the block's last norm_apply needs as plain
-    arrays) or with a dropout mask (the convolution then emits per-sample statistics that are combined with the mask)
-    the separate finalize kernel runs."""
+    Normally the statistics are finalized by the consuming norm_apply and the running statistics by the pass's batched
+    launch (`running`).  explicit=True (the shortcut BatchNorm, whose scale / shift the block's last norm_apply needs as
+    plain arrays) runs the finalize kernel for scale / shift and still leaves the running statistics to `running`; with a
+    dropout mask the convolution emits per-sample statistics that the finalize kernel combines with the mask (and then
+    updates the running statistics itself).  ns.groups > 1: each group of samples is its own BatchNorm batch."""
     ns.affine = True
     if not ns.pooled:
         ns.stats.zero_()
     conv.forward(xbuf, rbuf, ns.stats)
-    if running is not None and mask is None and ns.stats_groups == ns.groups:
-        ns.fused = (count, bn.weight.detach(), bn.bias.detach())
-        running.add(ns, count, bn.running_mean, bn.running_var, bn.num_batches_tracked, MOMENTUM)
+    seq = ns.groups > 1
+    if mask is None and ns.stats_groups == ns.groups and running is not None:
+        running.add(ns, count, bn.running_mean, bn.running_var, bn.num_batches_tracked, MOMENTUM, seq)
+        if not explicit:
+            ns.fused = (count, bn.weight.detach(), bn.bias.detach())
+            return
+        ns.fused = None
+        ops.norm_finalize(ns.stats, ns.groups, ns.c, count, eps=EPS, momentum=MOMENTUM, gamma=bn.weight.detach(), beta=bn.bias.detach(),
+                          mean=ns.mean, rstd=ns.rstd, scale=ns.scale, shift=ns.shift)
         return
+    if seq:
+        raise L.PcganError("grouped passes with channel dropout are not supported (run the passes one by one)")
     ns.fused = None
     kw = dict(eps=EPS, momentum=MOMENTUM, gamma=bn.weight.detach(), beta=bn.bias.detach(), mean=ns.mean, rstd=ns.rstd,
               scale=ns.scale, shift=ns.shift, running_mean=bn.running_mean, running_var=bn.running_var)
@@ -743,57 +779,62 @@ def _bn_forward(conv: ConvRT, xbuf, rbuf, ns: NormState, count, bn, running: Run
 
 
 def _bn_param_grads(bn, ns: NormState):
-    """dgamma = sum g*xhat, dbeta = sum g: by-products of the backward reduction."""
+    """dgamma = sum g*xhat, dbeta = sum g: by-products of the backward reduction (summed over the groups of a grouped pass)."""
+    sums = ns.sums[0] if ns.groups == 1 else ns.sums.sum(0)
     if bn.weight.requires_grad:
-        accumulate_grad(bn.weight, ns.sums[0, :, 1])
+        accumulate_grad(bn.weight, sums[:, 1])
     if bn.bias.requires_grad:
-        accumulate_grad(bn.bias, ns.sums[0, :, 0])
+        accumulate_grad(bn.bias, sums[:, 0])
 
 
 class _EncBlock:
     """One BasicBlock (resnet.py:31-73) at fixed geometry: conv3x3(stride) [drop] BN ReLU conv3x3 [drop] BN
     (+ 1x1 stride-s conv BN) add ReLU.  dropout=True plans per-sample statistics for the two dropped convolutions."""
 
-    def __init__(self, name, holder, N, hin, cin, c, stride, dropout=False):
+    def __init__(self, name, holder, N, hin, cin, c, stride, dropout=False, groups=1):
         G = Geom
         h = hin // stride
         self.name, self.holder, self.N, self.hin, self.cin, self.h, self.c, self.stride = name, holder, N, hin, cin, h, c, stride
-        self.dropout = dropout
+        self.dropout, self.groups = dropout, groups
+        if dropout and groups > 1:
+            raise L.PcganError("grouped passes with channel dropout are not supported")
+        grp = dict(per_sample_stats=True, stats_div=N // groups) if groups > 1 else dict(per_sample_stats=dropout)
         self.g_x, self.g_xr = G(N, hin, hin, cin, 1), G(N, hin, hin, cin, 0)
         self.g_r, self.g_y = G(N, h, h, c, 0), G(N, h, h, c, 1)
         dy1 = self.g_y if stride == 1 else self.g_r
         self.c1 = ConvRT(name + ".conv1", holder.conv1.weight, None, self.g_x, stride, 1, OutMap.nhwc(self.g_r), stats=True,
-                         per_sample_stats=dropout, dyg=dy1, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
+                         dyg=dy1, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False, **grp)
         self.c2 = ConvRT(name + ".conv2", holder.conv2.weight, None, self.g_y, 1, 1, OutMap.nhwc(self.g_r), stats=True,
-                         per_sample_stats=dropout, dyg=self.g_y, dx_out=OutMap.nhwc(self.g_r), want_wgrad=False)
+                         dyg=self.g_y, dx_out=OutMap.nhwc(self.g_r), want_wgrad=False, **grp)
         self.dy1_pad = dy1.pad
         self.ds = None
         if holder.downsample is not None:
+            gd = dict(per_sample_stats=True, stats_div=N // groups) if groups > 1 else {}
             self.ds = ConvRT(name + ".downsample.0", holder.downsample[0].weight, None, self.g_x, stride, 0, OutMap.nhwc(self.g_r),
-                             stats=True, dyg=self.g_r, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False)
+                             stats=True, dyg=self.g_r, dx_out=OutMap.nhwc(self.g_xr), want_wgrad=False, **gd)
 
     def new_ws(self, dev, stats_arena=None, sums_arena=None):
         w = _EncWorkspace()
         w.ra, w.h, w.rb, w.y = zeros_act(self.g_r, dev), zeros_act(self.g_y, dev), zeros_act(self.g_r, dev), zeros_act(self.g_y, dev)
         sg = self.N if self.dropout else None
-        w.na = NormState(1, self.c, dev, stats_arena, sums_arena, stats_groups=sg)
-        w.nb = NormState(1, self.c, dev, stats_arena, sums_arena, stats_groups=sg)
+        w.na = NormState(self.groups, self.c, dev, stats_arena, sums_arena, stats_groups=sg)
+        w.nb = NormState(self.groups, self.c, dev, stats_arena, sums_arena, stats_groups=sg)
         w.m1 = w.m2 = None
         if self.ds is not None:
-            w.rd, w.nd = zeros_act(self.g_r, dev), NormState(1, self.c, dev, stats_arena, sums_arena)
+            w.rd, w.nd = zeros_act(self.g_r, dev), NormState(self.groups, self.c, dev, stats_arena, sums_arena)
         return w
 
     def forward(self, xbuf, w, masks=None, running=None):
-        hd, cnt = self.holder, self.N * self.h * self.h
+        hd, cnt = self.holder, (self.N // self.groups) * self.h * self.h
         w.m1, w.m2 = masks if masks is not None else (None, None)
         _bn_forward(self.c1, xbuf, w.ra, w.na, cnt, hd.bn1, running, w.m1)
         ops.norm_apply(w.ra, self.g_r, w.h, self.g_y, y_halo=L.HALO_ZERO, **w.na.apply_kw(),
                        drop_mask=w.m1, act=L.ACT_RELU)
         _bn_forward(self.c2, w.h, w.rb, w.nb, cnt, hd.bn2, running, w.m2)
         if self.ds is not None:
-            _bn_forward(self.ds, xbuf, w.rd, w.nd, cnt, hd.downsample[1])     # explicit finalize: res_scale / res_shift below
+            _bn_forward(self.ds, xbuf, w.rd, w.nd, cnt, hd.downsample[1], running, explicit=True)     # res_scale / res_shift below
             ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, **w.nb.apply_kw(),
-                           drop_mask=w.m2, res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1, act=L.ACT_RELU)
+                           drop_mask=w.m2, res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=self.groups, act=L.ACT_RELU)
         else:
             ops.norm_apply(w.rb, self.g_r, w.y, self.g_y, y_halo=L.HALO_ZERO, **w.nb.apply_kw(),
                            drop_mask=w.m2, res=xbuf, res_pad=1, act=L.ACT_RELU)
@@ -802,11 +843,11 @@ class _EncBlock:
     def backward(self, xbuf, w, gy, sc, need_w=False):
         """gy: gradient of the block output (unpadded).  Returns the gradient of the block input (unpadded);
         need_w: also accumulate the weight / BatchNorm parameter gradients."""
-        hd, cnt = self.holder, self.N * self.h * self.h
+        hd, cnt = self.holder, (self.N // self.groups) * self.h * self.h
         dyb = sc.get(self.g_y, self.name + "dyb")
         gres = sc.get(self.g_r, self.name + "gres")
         if self.ds is not None:
-            res_kw = dict(res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=1)
+            res_kw = dict(res=w.rd, res_pad=0, res_scale=w.nd.scale, res_shift=w.nd.shift, res_groups=self.groups)
         else:
             res_kw = dict(res=xbuf, res_pad=1)
         _norm_backward(gy, 0, w.rb, self.g_r, w.nb, L.ACT_RELU, 0.0, cnt, dyb, 1, dres=gres, dres_pad=0, drop_mask=w.m2, **res_kw)
@@ -841,16 +882,17 @@ class _EncHead:
     """conv3x3 512->nf (+bias) BN [drop] LeakyReLU conv3x3 nf->1 (+bias) global average pool (networks.py:1014-1027,
     1056-1057); instantiated for `cnn` and, in noisy mode, for the twin `cnn_logvar` (:1034-1049, 1060-1066)."""
 
-    def __init__(self, name, seq, N, hf, slope):
+    def __init__(self, name, seq, N, hf, slope, groups=1):
         G = Geom
-        self.name, self.seq, self.N, self.hf, self.slope = name, seq, N, hf, slope
+        self.name, self.seq, self.N, self.hf, self.slope, self.groups = name, seq, N, hf, slope, groups
+        grp = dict(per_sample_stats=True, stats_div=N // groups) if groups > 1 else {}
         nf = seq[0].weight.shape[0]
         self.nf = nf
         self.g_f = G(N, hf, hf, 512, 1)
         self.g_rh, self.g_hh = G(N, hf, hf, nf, 0), G(N, hf, hf, nf, 1)
         self.g_fin, self.g_dyfin = G(N, hf, hf, 8, 0), G(N, hf, hf, 8, 1)
         self.c1 = ConvRT(name + ".0", seq[0].weight, seq[0].bias, self.g_f, 1, 1, OutMap.nhwc(self.g_rh), stats=True,
-                         dyg=self.g_hh, dx_out=OutMap.nhwc(G(N, hf, hf, 512, 0)), want_wgrad=False)
+                         dyg=self.g_hh, dx_out=OutMap.nhwc(G(N, hf, hf, 512, 0)), want_wgrad=False, **grp)
         # last conv: the global average pool is its per-sample statistics (sum over the map) / (h*w)
         self.c2 = ConvRT(name + ".4", seq[4].weight, seq[4].bias, self.g_hh, 1, 1, OutMap.nhwc(self.g_fin), stats=True,
                          per_sample_stats=True, dyg=self.g_dyfin, dx_out=OutMap.nhwc(self.g_rh), want_wgrad=False)
@@ -858,7 +900,7 @@ class _EncHead:
     def new_ws(self, dev, stats_arena, sums_arena):
         w = _EncWorkspace()
         w.rh, w.hh, w.fin = zeros_act(self.g_rh, dev), zeros_act(self.g_hh, dev), zeros_act(self.g_fin, dev)
-        w.nh = NormState(1, self.nf, dev, stats_arena, sums_arena)
+        w.nh = NormState(self.groups, self.nf, dev, stats_arena, sums_arena)
         w.nfin = NormState(self.N, 1, dev, stats_arena, sums_arena)
         w.pm = None
         return w
@@ -866,7 +908,7 @@ class _EncHead:
     def forward(self, fbuf, w, mask=None, running=None):
         N, hf = self.N, self.hf
         w.pm = mask
-        _bn_forward(self.c1, fbuf, w.rh, w.nh, N * hf * hf, self.seq[1], running)
+        _bn_forward(self.c1, fbuf, w.rh, w.nh, (N // self.groups) * hf * hf, self.seq[1], running)
         ops.norm_apply(w.rh, self.g_rh, w.hh, self.g_hh, y_halo=L.HALO_ZERO, **w.nh.apply_kw(),
                        act=L.ACT_LRELU, act_slope=self.slope, post_mask=mask)
         self.c2.forward(w.hh, w.fin, w.nfin.stats)
@@ -885,7 +927,7 @@ class _EncHead:
         ghh = sc.get(self.g_rh, self.name + "ghh")
         self.c2.backward_data(dyf, ghh)
         dyh = sc.get(self.g_hh, self.name + "dyh")
-        _norm_backward(ghh, 0, w.rh, self.g_rh, w.nh, L.ACT_LRELU, self.slope, N * hf * hf, dyh, 1, post_mask=w.pm)
+        _norm_backward(ghh, 0, w.rh, self.g_rh, w.nh, L.ACT_LRELU, self.slope, (N // self.groups) * hf * hf, dyh, 1, post_mask=w.pm)
         if need_w:
             _bn_param_grads(self.seq[1], w.nh)
             self.c1.backward_weight(dyh, fbuf)
@@ -896,10 +938,14 @@ class _EncHead:
 
 
 class _EncProgram:
-    def __init__(self, mod, N, S):
+    def __init__(self, mod, N, S, groups=1):
+        """groups > 1: N samples = `groups` independent passes batched together (own BatchNorm batch per run of N / groups
+        samples), as _DiscProgram; not available with channel dropout (the Monte-Carlo passes draw masks per pass)."""
         if S % 32:
             raise NotImplementedError("encoder input side must be a multiple of 32 (got %d)" % S)
-        self.mod, self.N, self.S = mod, N, S
+        if N % groups:
+            raise L.PcganError("SiameseFeature: batch %d is not divisible into %d groups" % (N, groups))
+        self.mod, self.N, self.S, self.groups = mod, N, S, groups
         rn = mod.base.model
         dev = rn.conv1.weight.device
         self.dev = dev
@@ -911,22 +957,25 @@ class _EncProgram:
         self.g_r0, self.g_a0 = G(N, s2, s2, 64, 0), G(N, s2, s2, 64, 0)
         self.g_dy0 = G(N, s2, s2, 64, 2)     # zero-haloed: the stem's data gradient runs in shift-sum form over this grid
         self.g_p, self.g_pr = G(N, s4, s4, 64, 1), G(N, s4, s4, 64, 0)
+        grp = dict(per_sample_stats=True, stats_div=N // groups) if groups > 1 else {}
         self.stem = ConvRT("E.conv1", rn.conv1.weight, None, self.g_x0, 2, 3, OutMap.nhwc(self.g_r0), stats=True, dyg=self.g_dy0,
-                           dx_out=OutMap.nhwc(G(N, S, S, 8, 0)), want_wgrad=False)
+                           dx_out=OutMap.nhwc(G(N, S, S, 8, 0)), want_wgrad=False, **grp)
         self.blocks = []
         hin, cin = s4, 64
         for li, c in enumerate((64, 128, 256, 512), start=1):
             layer = getattr(rn, "layer%d" % li)
             for bi in range(2):
                 stride = 2 if (li > 1 and bi == 0) else 1
-                blk = _EncBlock("E.layer%d.%d" % (li, bi), layer[bi], N, hin, cin, c, stride, dropout=drop)
+                blk = _EncBlock("E.layer%d.%d" % (li, bi), layer[bi], N, hin, cin, c, stride, dropout=drop, groups=groups)
                 self.blocks.append(blk)
                 hin, cin = hin // stride, c
         self.hf = hin
         self.g_ff = G(N, hin, hin, 512, 0)
-        self.heads = [_EncHead("E.cnn", mod.cnn, N, hin, mod.cnn_relu_slope)]
+        self.heads = [_EncHead("E.cnn", mod.cnn, N, hin, mod.cnn_relu_slope, groups)]
         if mod._noisy:
-            self.heads.append(_EncHead("E.cnn_logvar", mod.cnn_logvar, N, hin, mod.cnn_relu_slope))
+            self.heads.append(_EncHead("E.cnn_logvar", mod.cnn_logvar, N, hin, mod.cnn_relu_slope, groups))
+        if groups > 1 and mod.head_dropout > 0:
+            raise L.PcganError("grouped passes with channel dropout are not supported")
         self.head_drop = mod.head_dropout > 0
         self.scratch = _Scratch(dev)
         self.pool = Pool(lambda key: self._new_ws())
@@ -942,7 +991,7 @@ class _EncProgram:
         ws.x0, ws.r0, ws.a0, ws.p = zeros_act(self.g_x0, dev), zeros_act(self.g_r0, dev), zeros_act(self.g_a0, dev), zeros_act(self.g_p, dev)
         ws.idx = torch.zeros(self.g_pr.numel, dtype=torch.uint8, device=dev)
         ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
-        ws.n0 = NormState(1, 64, dev, ws.stats_arena, ws.sums_arena)
+        ws.n0 = NormState(self.groups, 64, dev, ws.stats_arena, ws.sums_arena)
         ws.blk = [b.new_ws(dev, ws.stats_arena, ws.sums_arena) for b in self.blocks]
         ws.heads = [h.new_ws(dev, ws.stats_arena, ws.sums_arena) for h in self.heads]
         ws.stats_arena.finalize()
@@ -969,7 +1018,7 @@ class _EncProgram:
         ws.running.begin()
         ops.pack_nchw(x, ws.x0, self.g_x0, halo=L.HALO_ZERO)
         s2 = self.S // 2
-        _bn_forward(self.stem, ws.x0, ws.r0, ws.n0, N * s2 * s2, rn.bn1, ws.running)
+        _bn_forward(self.stem, ws.x0, ws.r0, ws.n0, (N // self.groups) * s2 * s2, rn.bn1, ws.running)
         ops.norm_apply(ws.r0, self.g_r0, ws.a0, self.g_a0, **ws.n0.apply_kw(), act=L.ACT_RELU)
         ops.maxpool_fwd(ws.a0, self.g_a0, ws.p, 1, ws.idx)
         cur = ws.p
@@ -1010,7 +1059,7 @@ class _EncProgram:
         ga0 = sc.get(self.g_a0, "ga0")
         ops.maxpool_bwd(g, 0, ws.idx, ga0, 0, N, s2, s2, 64)
         dy0 = sc.get(self.g_dy0, "dy0")
-        _norm_backward(ga0, 0, ws.r0, self.g_r0, ws.n0, L.ACT_RELU, 0.0, N * s2 * s2, dy0, self.g_dy0.pad)
+        _norm_backward(ga0, 0, ws.r0, self.g_r0, ws.n0, L.ACT_RELU, 0.0, (N // self.groups) * s2 * s2, dy0, self.g_dy0.pad)
         if need_w:
             _bn_param_grads(rn.bn1, ws.n0)
             self.stem.backward_weight(dy0, ws.x0)
@@ -1099,14 +1148,23 @@ class SiameseFeature(nn.Module):
         self.feature_dim = 1
         self.dropout_masks = []      # test hook: explicit Dropout2d draws, consumed in module order
         self._programs = {}
+        self._groups = 1
         self._key = CO.register_module(self)
         self._last_size = 0
 
     def _program(self, n, s):
-        k = (n, s, self.cnn[0].weight.device)
+        k = (n, s, self.cnn[0].weight.device, self._groups)
         if k not in self._programs:
-            self._programs[k] = _EncProgram(self, n, s)
+            self._programs[k] = _EncProgram(self, n, s, self._groups)
         return self._programs[k]
+
+    def grouped(self, groups):
+        """Context manager: see NLayerDiscriminator.grouped."""
+        return _Grouped(self, groups)
+
+    def can_group(self):
+        """Passes can be batched unless they draw Dropout2d masks (each Monte-Carlo pass has its own)."""
+        return float(self.base.dropout) == 0.0 and self.head_dropout == 0.0
 
     def _run(self, x):
         _require_cuda(x, "SiameseFeature")

@@ -143,9 +143,11 @@ def running_table(items, device):
     momentum)] (tensors or None)."""
     import struct
     raw = bytearray()
-    for st, rm, rv, nbt, groups, c, count, mom in items:
-        raw += struct.pack("<qqqqiiff", st.data_ptr(), rm.data_ptr() if rm is not None else 0, rv.data_ptr() if rv is not None else 0,
-                           nbt.data_ptr() if nbt is not None else 0, groups, c, float(count), float(mom))
+    for it in items:
+        st, rm, rv, nbt, groups, c, count, mom = it[:8]
+        seq = int(it[8]) if len(it) > 8 else 0
+        raw += struct.pack("<qqqqiiffii", st.data_ptr(), rm.data_ptr() if rm is not None else 0, rv.data_ptr() if rv is not None else 0,
+                           nbt.data_ptr() if nbt is not None else 0, groups, c, float(count), float(mom), seq, 0)
     t = torch.frombuffer(raw, dtype=torch.uint8).clone().to(device)
     return t, max(it[5] for it in items)
 

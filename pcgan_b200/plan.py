@@ -110,6 +110,7 @@ class IgemmSpec:
     stats_mode: int = L.STATS_NONE
     stats_dim: int = -1
     stats_comp: int = 1
+    stats_div: int = 0         # > 1: statistics group = sample // stats_div (several BatchNorm batches in one launch)
     m_valid: int = 1
     wg_ncols: int = 1
     ldo: int = 1
@@ -175,6 +176,7 @@ class IgemmSpec:
         d.a_window = self.a_window
         d.wg_box_dim = self.wg_box_dim
         d.tf32 = int(self.tf32)
+        d.stats_div = int(self.stats_div)
         return d
 
 

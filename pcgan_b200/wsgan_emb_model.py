@@ -47,7 +47,7 @@ def default_options(**overrides):
         relabel_D=[0, 1, 0], no_mixed_label_D=False, weight_label_D=[0.5, 0, 0.5], detach_fake_B=False, update_logvar_E=False,
         no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5, lr_policy="lambda", niter=50, niter_decay=50, epoch_count=1,
         lr_decay_iters=50, continue_train=False, which_epoch="latest", load_model_names=[], verbose=False,
-        cuda_graph=False, cuda_graph_warmup=3, cuda_graph_segments=None)
+        cuda_graph=False, cuda_graph_warmup=3, cuda_graph_segments=None, group_passes=True)
     for k, v in overrides.items():
         setattr(opt, k, v)
     return opt
@@ -268,6 +268,9 @@ class WSGANEmbModel(BaseModel):
         if is_train:
             parser.add_argument("--cuda_graph", type=str2bool, default=False,
                                 help="pcgan_b200: capture optimize_parameters() into a CUDA graph after a few eager steps and replay it")
+            parser.add_argument("--group_passes", type=str2bool, default=True,
+                                help="pcgan_b200: run the independent passes of a network (the three discriminator passes of backward_D, "
+                                     "the two real-image encoder passes of forward) as one batch with one BatchNorm batch per pass")
         parser.set_defaults(**_DEFAULT_OVERRIDES)
         return parser
 
@@ -442,10 +445,24 @@ class WSGANEmbModel(BaseModel):
         ip = self.isTrain and opt.lambda_IP > 0.0
         if ip:
             self.real_A_IP = upsample2d(self.real_A, opt.fineSize_IP)      # :215
-        self.real_A_E = upsample2d(self.real_A, opt.fineSize_E)
-        self.real_B_E = upsample2d(self.real_B, opt.fineSize_E)
-        y_A, var_A = self._encode(self.real_A_E)
-        y_B, var_B = self._encode(self.real_B_E)
+        netE = self._unwrap(self.netE)
+        if getattr(opt, "group_passes", False) and opt.lr_E <= 0.0 and not opt.bayesian and netE.can_group():
+            # the two real-image encoder passes as one batch of 2 N samples with one BatchNorm batch per image set
+            n = self.real_A.size(0)
+            both = upsample2d(torch.cat([self.real_A, self.real_B], 0), opt.fineSize_E)
+            self.real_A_E, self.real_B_E = both[:n], both[n:]
+            with netE.grouped(2):
+                out = self.netE(self.transform_E(both))
+            y, logvar = out if opt.noisy else (out, None)
+            y_A, y_B = y[:n], y[n:]
+            var_A = var_B = None
+            if opt.noisy and "a" in opt.noisy_var_type:
+                var_A, var_B = torch.exp(logvar[:n]), torch.exp(logvar[n:])
+        else:
+            self.real_A_E = upsample2d(self.real_A, opt.fineSize_E)
+            self.real_B_E = upsample2d(self.real_B, opt.fineSize_E)
+            y_A, var_A = self._encode(self.real_A_E)
+            y_B, var_B = self._encode(self.real_B_E)
         if var_A is not None:
             self.resample_A = self.embedding_normalize(resample(y_A, var_A))
             self.resample_B = self.embedding_normalize(resample(y_B, var_B))
@@ -490,15 +507,27 @@ class WSGANEmbModel(BaseModel):
         return self.resample_B if (self.opt.noisy_var_type and self.opt.noisy_D) else self.embedding_B
 
     def backward_D(self):
-        """wsgan_emb_model.py:300-329."""
+        """wsgan_emb_model.py:300-329.  The three discriminator passes are independent (detached inputs, separate
+        BatchNorm batches); with --group_passes they run as ONE batch of 3 N samples whose groups of N keep their own
+        BatchNorm statistics, running-statistics step and backward sums, in the reference's order (fake, right, wrong)."""
         opt = self.opt
-        pred_fake = self.netD(self.fake_B.detach(), self._cond_B().detach())
-        self.loss_D_fake = self.criterionGAN(pred_fake, False)
         img = self.real_A if opt.use_real_A else self.real_B
         emb_right, emb_wrong = (self.embedding_A, self.embedding_B) if opt.use_real_A else (self.embedding_B, self.embedding_A)
-        self.loss_D_real_right = self.criterionGAN(self.netD(img, emb_right.detach()), True)
         target_label = self._relabel_lut[self._label_dev]      # [relabel_D[l] for l in label_AB] (:324), on the device
-        self.loss_D_real_wrong = self.criterionGAN(self.netD(img, emb_wrong.detach()), target_label)
+        if getattr(opt, "group_passes", False):
+            n = img.size(0)
+            x = torch.cat([self.fake_B.detach(), img, img], 0)
+            z = torch.cat([self._cond_B().detach().reshape(n, -1), emb_right.detach().reshape(n, -1), emb_wrong.detach().reshape(n, -1)], 0)
+            with self._unwrap(self.netD).grouped(3):
+                pred = self.netD(x, z.view(3 * n, -1, 1, 1))
+            pred_fake, pred_right, pred_wrong = pred[:n], pred[n:2 * n], pred[2 * n:]
+        else:
+            pred_fake = self.netD(self.fake_B.detach(), self._cond_B().detach())
+            pred_right = self.netD(img, emb_right.detach())
+            pred_wrong = self.netD(img, emb_wrong.detach())
+        self.loss_D_fake = self.criterionGAN(pred_fake, False)
+        self.loss_D_real_right = self.criterionGAN(pred_right, True)
+        self.loss_D_real_wrong = self.criterionGAN(pred_wrong, target_label)
         self.loss_D = (self.loss_D_fake + (self.loss_D_real_right + self.loss_D_real_wrong) * 0.5) * 0.5
         self.loss_D.backward()
 

@@ -38,7 +38,7 @@ def test_model_resolves_and_options_match_the_reference(ref_front_end, monkeypat
     cls = ref_front_end.find_model_using_name("wsgan_emb_b200")
     assert issubclass(cls, WSGANEmbModel) and issubclass(cls, ref_front_end.BaseModel)
     ours, ref = vars(_parse(monkeypatch, "wsgan_emb_b200")), vars(_parse(monkeypatch, "wsgan_emb"))
-    assert ours.pop("cuda_graph") is False
+    assert ours.pop("cuda_graph") is False and ours.pop("group_passes") is True      # the two flags this package adds
     for k in ("model", "name"):
         ours.pop(k), ref.pop(k)
     assert ours == ref
@@ -54,7 +54,7 @@ def test_every_reference_flag_is_read_with_its_default(ref_front_end, monkeypatc
                       embedding_bins="[]", pretrained_model_path_E="", pretrained_model_path_IP="", batchSize=10, upsample="bilinear", attr_bins=[], num_Ds=1,
                       checkpoints_dir="", name="", isTrain=True)
     for k, v in mine.items():
-        if k in north_star or k.startswith("cuda_graph") or k not in ref:
+        if k in north_star or k.startswith("cuda_graph") or k == "group_passes" or k not in ref:
             continue
         assert ref[k] == v, (k, ref[k], v)
 
