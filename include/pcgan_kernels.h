@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 17
+#define PCGAN_ABI_VERSION 18
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -371,6 +371,27 @@ int pcgan_act_bwd(const void* dy, int32_t dy_pad, const void* y, int32_t y_pad, 
  * to_f32 = 0: the reverse (its gradient). */
 int pcgan_nhwc_cast(const void* src, void* dst, int32_t pad, int32_t n, int32_t h, int32_t w, int32_t c, int32_t to_f32,
                     pcgan_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Input pipeline (data/base_dataset.py:24-64, data/wsgan_emb_dataset.py:36-49):
+ * transforms.Resize([load, load], BICUBIC) -> RandomCrop(fine) -> RandomHorizontalFlip
+ * -> ToTensor -> Normalize(0.5, 0.5) of n decoded RGB images (uint8 HWC in device
+ * memory, any sizes) into dst fp32 [n][3][fine][fine] in one launch.  The resize is
+ * PIL's: antialiased bicubic (a = -0.5, support scaled by the down-scaling factor), the
+ * horizontal pass rounded to 8 bits before the vertical pass.  The random draws (crop
+ * origin in the resized image, flip) are the caller's.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const uint8_t* src; int32_t h, w;     /* decoded image, row-major RGB */
+  int32_t crop_y, crop_x;               /* crop origin in the load x load image */
+  int32_t flip;
+  int32_t reserved_;
+} pcgan_image_item;
+typedef struct {
+  const pcgan_image_item* items;        /* device array [n] */
+  float* dst; int32_t n, load, fine;
+} pcgan_augment_args;
+int pcgan_augment(const pcgan_augment_args* a, pcgan_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * Losses: vectorised, coalesced reductions (GANLoss networks.py:386-420 ->

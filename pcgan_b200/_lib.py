@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -100,6 +100,14 @@ class NormBwdArgs(C.Structure):
                 ("count", f32), ("sums", vp), ("dx", vp), ("dx_pad", i32), ("dres", vp), ("dres_pad", i32), ("dy_fold", i32), ("post_mask", vp), ("affine", i32)]
 
 
+class ImageItem(C.Structure):
+    _fields_ = [("src", vp), ("h", i32), ("w", i32), ("crop_y", i32), ("crop_x", i32), ("flip", i32), ("reserved_", i32)]
+
+
+class AugmentArgs(C.Structure):
+    _fields_ = [("items", vp), ("dst", vp), ("n", i32), ("load", i32), ("fine", i32)]
+
+
 class MaxpoolArgs(C.Structure):
     _fields_ = [("x", vp), ("x_pad", i32), ("y", vp), ("y_pad", i32), ("idx", vp),
                 ("n", i32), ("h", i32), ("w", i32), ("c", i32), ("pool_pad", i32)]
@@ -118,7 +126,7 @@ _STRUCTS = {
     "pcgan_tmap": TMap, "pcgan_comp": Comp, "pcgan_igemm_desc": IgemmDesc, "pcgan_pack_args": PackArgs,
     "pcgan_unpack_args": UnpackArgs, "pcgan_norm_finalize_args": NormFinalizeArgs,
     "pcgan_norm_apply_args": NormApplyArgs, "pcgan_fold_args": FoldArgs, "pcgan_norm_bwd_args": NormBwdArgs,
-    "pcgan_maxpool_args": MaxpoolArgs, "pcgan_loss_args": LossArgs, "pcgan_batch_item": BatchItem, "pcgan_running_item": RunningItem,
+    "pcgan_maxpool_args": MaxpoolArgs, "pcgan_image_item": ImageItem, "pcgan_augment_args": AugmentArgs, "pcgan_loss_args": LossArgs, "pcgan_batch_item": BatchItem, "pcgan_running_item": RunningItem,
     "pcgan_adam_item": AdamItem,
 }
 
@@ -152,6 +160,7 @@ SYMBOLS = {
     "pcgan_maxpool3x3s2_bwd": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "pcgan_act_bwd": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, f32, vp]),
     "pcgan_nhwc_cast": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "pcgan_augment": (C.c_int, [C.POINTER(AugmentArgs), vp]),
     "pcgan_loss": (C.c_int, [C.POINTER(LossArgs), vp]),
     "pcgan_adam": (C.c_int, [vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, vp]),
     "pcgan_adam_batched": (C.c_int, [vp, i32, i64, vp, C.c_double, C.c_double, C.c_double, vp, vp]),

@@ -384,6 +384,72 @@ __global__ void nhwc_uncast_kernel(const float* __restrict__ src, __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------- input pipeline
+// Resize (PIL's antialiased bicubic: two separable passes with 8-bit intermediate rounding) + crop + horizontal flip +
+// ToTensor + Normalize(0.5, 0.5) of one decoded RGB image per blockIdx.y, straight into the fp32 NCHW batch tensor
+// (data/base_dataset.py:24-64).  Thread = one output pixel, three channels.
+__device__ __forceinline__ float bicubic_w(float x) {
+  const float a = -0.5f;
+  x = fabsf(x);
+  if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+  if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+  return 0.f;
+}
+// the source range [lo, lo + cnt) and filter scale of output coordinate r when `in` samples are resized to `out`
+__device__ __forceinline__ void resample_window(int r, int in, int out, int& lo, int& cnt, float& center, float& ss) {
+  const float scale = static_cast<float>(in) / static_cast<float>(out);
+  const float fs = scale > 1.f ? scale : 1.f;
+  const float support = 2.f * fs;
+  center = (r + 0.5f) * scale;
+  ss = 1.f / fs;
+  lo = static_cast<int>(center - support + 0.5f);
+  if (lo < 0) lo = 0;
+  int hi = static_cast<int>(center + support + 0.5f);
+  if (hi > in) hi = in;
+  cnt = hi - lo;
+}
+__device__ __forceinline__ float clip8(float v) {
+  v = floorf(v + 0.5f);
+  return v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+}
+
+__global__ void augment_kernel(pcgan_augment_args a) {
+  griddep_wait();
+  griddep_launch();
+  const pcgan_image_item it = a.items[blockIdx.y];
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= a.fine * a.fine) return;
+  const int oy = pix / a.fine, ox = pix - oy * a.fine;
+  const int ry = oy + it.crop_y;
+  const int rx = (it.flip ? a.fine - 1 - ox : ox) + it.crop_x;
+  int x0, xn, y0, yn;
+  float cx, sx, cy, sy;
+  resample_window(rx, it.w, a.load, x0, xn, cx, sx);
+  resample_window(ry, it.h, a.load, y0, yn, cy, sy);
+  float wxs = 0.f, wys = 0.f;
+  for (int i = 0; i < xn; ++i) wxs += bicubic_w((i + x0 - cx + 0.5f) * sx);
+  for (int j = 0; j < yn; ++j) wys += bicubic_w((j + y0 - cy + 0.5f) * sy);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < yn; ++j) {
+    const uint8_t* row = it.src + (static_cast<int64_t>(y0 + j) * it.w + x0) * 3;
+    float h[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < xn; ++i) {
+      const float wgt = bicubic_w((i + x0 - cx + 0.5f) * sx);
+      h[0] = fmaf(wgt, static_cast<float>(row[3 * i]), h[0]);
+      h[1] = fmaf(wgt, static_cast<float>(row[3 * i + 1]), h[1]);
+      h[2] = fmaf(wgt, static_cast<float>(row[3 * i + 2]), h[2]);
+    }
+    const float wy = bicubic_w((j + y0 - cy + 0.5f) * sy) / wys;
+    // the horizontal pass is stored as 8-bit pixels before the vertical pass runs (PIL's ImagingResample)
+    acc[0] = fmaf(wy, clip8(h[0] / wxs), acc[0]);
+    acc[1] = fmaf(wy, clip8(h[1] / wxs), acc[1]);
+    acc[2] = fmaf(wy, clip8(h[2] / wxs), acc[2]);
+  }
+  float* dst = a.dst + static_cast<int64_t>(blockIdx.y) * 3 * a.fine * a.fine + pix;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[static_cast<int64_t>(c) * a.fine * a.fine] = (clip8(acc[c]) / 255.f - 0.5f) / 0.5f;
+}
+
 // ----------------------------------------------------------------------- loss
 __global__ void loss_kernel(pcgan_loss_args a) {
   griddep_wait();
@@ -658,6 +724,15 @@ extern "C" int pcgan_nhwc_cast(const void* src, void* dst, int32_t pad, int32_t 
   else PCGAN_CUDA_OK(launch_pdl(nhwc_uncast_kernel, dim3(grid_for(total)), dim3(kThreads), 0, STREAM(s), 1, reinterpret_cast<const float*>(src),
                                 reinterpret_cast<__nv_bfloat16*>(dst), pad, n, h, w, c));
   PCGAN_LAUNCH_OK("nhwc_cast_kernel");
+  return PCGAN_OK;
+}
+
+extern "C" int pcgan_augment(const pcgan_augment_args* a, pcgan_stream_t s) {
+  if (!a || !a->items || !a->dst || a->n < 1 || a->n > 65535 || a->load < 1 || a->fine < 1 || a->fine > a->load)
+    return fail(PCGAN_ERR_INVALID, "augment: bad argument");
+  const int px = a->fine * a->fine;
+  PCGAN_CUDA_OK(launch_pdl(augment_kernel, dim3((px + kThreads - 1) / kThreads, a->n), dim3(kThreads), 0, STREAM(s), 1, *a));
+  PCGAN_LAUNCH_OK("augment_kernel");
   return PCGAN_OK;
 }
 

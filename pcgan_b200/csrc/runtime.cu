@@ -64,5 +64,7 @@ extern "C" int64_t pcgan_sizeof(const char* name) {
   if (s == "pcgan_batch_item") return sizeof(pcgan_batch_item);
   if (s == "pcgan_running_item") return sizeof(pcgan_running_item);
   if (s == "pcgan_adam_item") return sizeof(pcgan_adam_item);
+  if (s == "pcgan_image_item") return sizeof(pcgan_image_item);
+  if (s == "pcgan_augment_args") return sizeof(pcgan_augment_args);
   return -1;
 }
