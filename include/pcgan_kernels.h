@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 18
+#define PCGAN_ABI_VERSION 19
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -284,6 +284,10 @@ typedef struct {
   const float* stats; float count, eps;
   const float* gamma; const float* beta;
   float* mean_out; float* rstd_out; float* scale_out; float* shift_out;
+  /* The output may be a channel slice of a wider buffer (the skip concatenations of UnetGenerator,
+   * networks.py:722-733): y holds y_c >= c channels per pixel and this launch writes channels [y_c0, y_c0 + c).
+   * y_c == 0: a buffer of exactly c channels.  Zero halo only. */
+  int32_t y_c, y_c0;
 } pcgan_norm_apply_args;
 int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t stream);
 

@@ -104,6 +104,61 @@ def encoder_keys(cnn_dim=(32, 1), noisy=False):
     return k
 
 
+def unet_keys(input_nc=3, output_nc=3, nz=1, ngf=64, num_downs=7):
+    """state_dict layout of UnetGenerator with InstanceNorm2d(track_running_stats=True) (models/networks.py:659-733):
+    nested UnetSkipConnectionBlocks, name -> shape, in the reference's order."""
+    k = OrderedDict()
+    inner = [ngf, ngf * 2, ngf * 4] + [ngf * 8] * (num_downs - 3)
+
+    def inorm(name, c):
+        k[name + ".running_mean"] = (c,); k[name + ".running_var"] = (c,); k[name + ".num_batches_tracked"] = ()
+
+    def block(p, level):
+        cin = input_nc + nz if level == 0 else inner[level - 1]
+        outer = output_nc if level == 0 else inner[level - 1]
+        ci = inner[level]
+        if level == 0:
+            k[p + ".0.weight"] = (ci, cin, 4, 4); k[p + ".0.bias"] = (ci,)
+            block(p + ".1.model", 1)
+            k[p + ".3.weight"] = (2 * ci, outer, 4, 4); k[p + ".3.bias"] = (outer,)
+        elif level == num_downs - 1:
+            k[p + ".1.weight"] = (ci, cin, 4, 4); k[p + ".1.bias"] = (ci,)
+            k[p + ".3.weight"] = (ci, outer, 4, 4); k[p + ".3.bias"] = (outer,)
+            inorm(p + ".4", outer)
+        else:
+            k[p + ".1.weight"] = (ci, cin, 4, 4); k[p + ".1.bias"] = (ci,)
+            inorm(p + ".2", ci)
+            block(p + ".3.model", level + 1)
+            k[p + ".5.weight"] = (2 * ci, outer, 4, 4); k[p + ".5.bias"] = (outer,)
+            inorm(p + ".6", outer)
+
+    block("model.model", 0)
+    return k
+
+
+def unet_forward(sd, x, z, num_downs=7):
+    """UnetGenerator.forward (networks.py:677-680) over UnetSkipConnectionBlock.forward (:728-733).  The blocks' LeakyReLU
+    is in place (nn.LeakyReLU(0.2, True), :695), so the tensor that is concatenated as the skip connection is
+    LeakyReLU(x), not x."""
+    def conv(t, name):
+        return F.conv2d(t, sd[name + ".weight"], sd[name + ".bias"], stride=2, padding=1)
+
+    def convt(t, name):
+        return F.conv_transpose2d(t, sd[name + ".weight"], sd[name + ".bias"], stride=2, padding=1)
+
+    def block(p, t, level):
+        a = F.leaky_relu(t, 0.2)
+        if level == num_downs - 1:
+            u = _inorm(convt(F.relu(conv(a, p + ".1")), p + ".3"), sd, p + ".4")
+        else:
+            d = _inorm(conv(a, p + ".1"), sd, p + ".2")
+            u = _inorm(convt(F.relu(block(p + ".3.model", d, level + 1)), p + ".5"), sd, p + ".6")
+        return torch.cat([a, u], 1)
+
+    d = conv(_zcat(x, z), "model.model.0")
+    return torch.tanh(convt(F.relu(block("model.model.1.model", d, 1)), "model.model.3"))
+
+
 def alexnet_keys():
     """state_dict layout of AlexNetFeature (models/networks.py:1218-1240): name -> shape."""
     k = OrderedDict()
@@ -381,8 +436,9 @@ class WSGANEmbOracle:
                  lambda_a_gan=0.0, fine_size_e=224, relabel_d=(0, 1, 0), emb_mean=0.0, emb_std=1.0, n_blocks=9,
                  n_layers_d=3, detach_fake_b=False, bayesian=False, noisy=False, noisy_var_type="", bnn_T=10,
                  noisy_d=True, noisy_rec=True, dropout=False, drop_masks=None, eps_queue=None, use_real_a=False,
-                 sd_ip=None, lambda_ip=0.0, fine_size_ip=224, ip_criterion="mse"):
-        """bayesian / noisy / noisy_var_type / bnn_T / noisy_D / noisy_rec: the encoder modes of forward() (:218-240)
+                 sd_ip=None, lambda_ip=0.0, fine_size_ip=224, ip_criterion="mse", generator="resnet", num_downs=7):
+        """generator: "resnet" (--which_model_netG resnet_9blocks, n_blocks) or "unet" (unet_128 / unet_256, num_downs).
+        bayesian / noisy / noisy_var_type / bnn_T / noisy_D / noisy_rec: the encoder modes of forward() (:218-240)
         and backward_G (:408-430).  Randomness is injected, never drawn: `drop_masks` is a list of Dropout2d masks
         [N, C] consumed in module order (dropout=True places them where the reference has nn.Dropout2d), `eps_queue`
         the standard-normal draws of util.resample (util/util.py:136-139) in call order."""
@@ -403,7 +459,13 @@ class WSGANEmbOracle:
         self.use_real_a = use_real_a     # --use_real_A (:309-322): D's real pairs are built from real_A
         # identity-preserving loss (:130-135, 353-356, 393-396): AlexNet features of fake_B against those of real_A
         self.ip, self.lip, self.fip, self.ip_crit = sd_ip, lambda_ip, fine_size_ip, ip_criterion
+        self.generator, self.num_downs = generator, num_downs
         self.losses = {}
+
+    def _G(self, x, z):
+        if self.generator == "unet":
+            return unet_forward(self.g, x, z, self.num_downs)
+        return generator_forward(self.g, x, z, self.nb)
 
     def _drop(self, t):
         m = self.drop_masks.pop(0).to(t.device, t.dtype)
@@ -462,9 +524,9 @@ class WSGANEmbOracle:
         self.emb_a, self.emb_b = self._norm(self.y_a), self._norm(self.y_b)
         self.cond_b = self.res_b if (self.nvt and self.noisy_d) else self.emb_b
         self.real_a, self.real_b = real_a, real_b
-        self.fake_b = generator_forward(self.g, real_a, self.emb_b, self.nb)
+        self.fake_b = self._G(real_a, self.emb_b)
         src = self.fake_b.detach() if self.detach_fake_b else self.fake_b
-        self.rec_a = generator_forward(self.g, src, self.emb_a, self.nb)
+        self.rec_a = self._G(src, self.emb_a)
 
     def backward_g(self):
         """WSGANEmbModel.backward_G (:371-437)."""

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -84,7 +84,7 @@ class NormApplyArgs(C.Structure):
                 ("res_scale", vp), ("res_shift", vp), ("res_groups", i32),
                 ("drop_mask", vp), ("act", i32), ("act_slope", f32), ("post_mask", vp),
                 ("stats", vp), ("count", f32), ("eps", f32), ("gamma", vp), ("beta", vp),
-                ("mean_out", vp), ("rstd_out", vp), ("scale_out", vp), ("shift_out", vp)]
+                ("mean_out", vp), ("rstd_out", vp), ("scale_out", vp), ("shift_out", vp), ("y_c", i32), ("y_c0", i32)]
 
 
 class FoldArgs(C.Structure):

@@ -99,9 +99,16 @@ def conv_dgrad_plans(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, out: Ou
     if transposed:
         # dX[iy][ix][ci] = sum dY[2iy - cp + r][2ix - cp + s][co] W[ci][co][r][s]: a stride-2 convolution of dY
         cin, cout = w_shape[0], w_shape[1]
-        assert stride == 2 and dyg.c == cout and cout % 64 == 0 and not full_padded
+        assert stride == 2 and not full_padded
         o = dyg.pad - cp
         assert o >= 0
+        if dyg.c < 64:
+            # few output channels (the outermost up convolution of UnetGenerator, networks.py:699-701): dY is an 8-channel
+            # buffer read as packed filter rows, exactly like the forward of a stride-2 convolution over an image
+            assert cout <= dyg.c and not tf32
+            sp = plan_packed(dyg, k, k, 2, o, cin, xg.h, xg.w, out, note=note)
+            return [(sp, wmap_packed(w_shape, cin, k, k, dyg.c, sp.b_k // k))]
+        assert dyg.c == cout and cout % 64 == 0
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
         sp = plan_box(dyg, taps, cout, cin, xg.h, xg.w, 2, out, **T)
         wt = [(r, s, r * k + s) for r in range(k) for s in range(k)]
@@ -190,7 +197,7 @@ def conv_wgrad_plan(w_shape, dyg: Geom, xg: Geom, stride: int, cp: int, *, trans
     k = kh
     if transposed:
         cin, cout = w_shape[0], w_shape[1]
-        assert stride == 2 and dyg.c == cout and xg.c == cin
+        assert stride == 2 and dyg.c >= cout and xg.c == cin
         o = dyg.pad - cp
         taps = [(r + o, s + o, r * k + s) for r in range(k) for s in range(k)]
         sp = plan_wgrad_box(xg, cin, dyg, cout, taps, xg.h, xg.w, 2, m_origin=(xg.pad, xg.pad), note=note, tf32=tf32)

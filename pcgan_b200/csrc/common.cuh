@@ -19,10 +19,17 @@ int fail(int code, const char* fmt, ...);
     cudaError_t _e = (expr);                                                                  \
     if (_e != cudaSuccess) return ::pcgan::fail(PCGAN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+// PCGAN_SYNC=1 (debugging): every launch is followed by a device synchronisation, so an asynchronous fault is reported
+// by the entry point (and plan) that caused it.  Never set it under CUDA-graph capture.
+bool sync_launches();
 #define PCGAN_LAUNCH_OK(name)                                                                 \
   do {                                                                                        \
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) return ::pcgan::fail(PCGAN_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+    if (::pcgan::sync_launches()) {                                                           \
+      _e = cudaDeviceSynchronize();                                                           \
+      if (_e != cudaSuccess) return ::pcgan::fail(PCGAN_ERR_CUDA, "kernel %s faulted: %s", name, cudaGetErrorString(_e)); \
+    }                                                                                         \
   } while (0)
 
 int sm_count();

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
   const bool has_pm = a.post_mask != nullptr;
   if (has_pm) load_f8(a.post_mask + static_cast<int64_t>(n) * a.c + c0, pm);
   const int p = a.y_pad, wp = a.w + 2 * p;
-  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + static_cast<int64_t>(n) * (a.h + 2 * p) * wp * a.c + c0;
+  const int ych = a.y_c > 0 ? a.y_c : a.c;       // channels per pixel of the output buffer (a channel slice of a wider one)
+  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + static_cast<int64_t>(n) * (a.h + 2 * p) * wp * ych + a.y_c0 + c0;
   const bool reflect = a.y_halo == PCGAN_HALO_REFLECT && p > 0;
   int s = 0;
   uint32_t ph = 0;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
       w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
       const int x = x0 + (v >> lcv);
       const int xa = x + p;
-      *reinterpret_cast<uint4*>(ys + (ya * wp + xa) * a.c) = w;
+      *reinterpret_cast<uint4*>(ys + (ya * wp + xa) * ych) = w;
       if (reflect) {
         const int xb = (x >= 1 && x <= p) ? p - x : -1;
         const int xc = (x <= a.w - 2 && x >= a.w - 1 - p) ? p + 2 * (a.w - 1) - x : -1;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
             for (int ix = 0; ix < 3; ++ix) {
               const int xx = ix == 0 ? xa : (ix == 1 ? xb : xc);
               if (xx < 0 || (iy == 0 && ix == 0)) continue;
-              *reinterpret_cast<uint4*>(ys + (yy * wp + xx) * a.c) = w;
+              *reinterpret_cast<uint4*>(ys + (yy * wp + xx) * ych) = w;
             }
           }
         }
@@ -913,8 +914,10 @@ extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s
   if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(PCGAN_ERR_INVALID, "norm_apply: scale and shift go together");
   if (a->y_halo == PCGAN_HALO_REFLECT && (2 * a->y_pad + 1 > a->h || 2 * a->y_pad + 1 > a->w)) return fail(PCGAN_ERR_INVALID, "norm_apply: image smaller than 2*pad+1 under reflect halo");
   if (a->n < 1 || a->n > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: n=%d (1..65535)", a->n);
+  if (a->y_c != 0 && (a->y_c < a->c + a->y_c0 || a->y_c % 8 != 0 || a->y_c0 % 8 != 0 || a->y_c0 < 0))
+    return fail(PCGAN_ERR_INVALID, "norm_apply: channel slice [%d, %d) of %d channels", a->y_c0, a->y_c0 + a->c, a->y_c);
   const int mp = a->y_pad > a->x_pad ? (a->y_pad > a->res_pad ? a->y_pad : a->res_pad) : (a->x_pad > a->res_pad ? a->x_pad : a->res_pad);
-  if (static_cast<int64_t>(a->h + 2 * mp) * (a->w + 2 * mp) * a->c >= (1ll << 31)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: sample too large");
+  if (static_cast<int64_t>(a->h + 2 * mp) * (a->w + 2 * mp) * (a->y_c > a->c ? a->y_c : a->c) >= (1ll << 31)) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: sample too large");
   if ((rc = norm_kernels_ready())) return rc;
   const SegGeom sg = seg_geom(a->w, a->c);
   int per;

@@ -33,6 +33,15 @@ int sm_count() {
   return cached[dev];
 }
 
+bool sync_launches() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PCGAN_SYNC");
+    cached = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 bool pdl_enabled() {
   static int cached = -1;
   if (cached < 0) {

@@ -168,6 +168,25 @@ def _net_backward(op):
 torch.library.register_autograd("pcgan::resnet_generator", _net_backward(resnet_generator_backward), setup_context=_net_setup)
 
 
+# --------------------------------------------------------------------------- unet generator
+@torch.library.custom_op("pcgan::unet_generator", mutates_args=())
+def unet_generator(x: Tensor, z: Tensor, params: Sequence[Tensor], key: int) -> Tensor:
+    """UnetGenerator.forward (models/networks.py:677-680)"""
+    mod = _module(key)
+    prog = mod._program(x.shape[0], x.shape[2])
+    out, ws = prog.forward(x.contiguous().float(), z.contiguous().float().view(-1))
+    _TLS.pending[key] = Lease(prog, ws)
+    return out
+
+
+@unet_generator.register_fake
+def _(x, z, params, key):
+    return x.new_empty((x.shape[0], _module(key).output_nc, x.shape[2], x.shape[3]), dtype=torch.float32)
+
+
+torch.library.register_autograd("pcgan::unet_generator", _net_backward(resnet_generator_backward), setup_context=_net_setup)
+
+
 # -------------------------------------------------------------------------- discriminator
 @torch.library.custom_op("pcgan::nlayer_discriminator", mutates_args=())
 def nlayer_discriminator(x: Tensor, z: Tensor, params: Sequence[Tensor], key: int) -> Tensor:

@@ -67,8 +67,10 @@ class ConvRT:
 
     def __init__(self, name, weight, bias, xg: Geom, stride, cp, out: OutMap, *, transposed=False, output_padding=0,
                  act=L.ACT_NONE, act_slope=0.0, stats=False, per_sample_stats=False, dyg: Optional[Geom] = None,
-                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True, tf32=False, stats_div=0):
-        """tf32=True: the activation / gradient buffers passed to forward / backward_* hold fp32 (same padded NHWC
+                 dx_out: Optional[OutMap] = None, full_padded=False, want_dgrad=True, want_wgrad=True, tf32=False, stats_div=0,
+                 want_fwd=True, trainable=True):
+        """trainable=False: a helper runtime over a view of another convolution's weight (never asked for a weight gradient).
+        tf32=True: the activation / gradient buffers passed to forward / backward_* hold fp32 (same padded NHWC
         geometry), the packed weights are fp32 rounded to TF32, and the kernels issue tcgen05.mma.kind::tf32 (per-layer
         error 3e-4 .. 8e-4 instead of 2.4e-3 in bf16).  The network programs of this package run their normalisation
         kernels on bf16 buffers, so they build their convolutions with tf32=False; a TF32 runtime is what a caller with
@@ -79,6 +81,7 @@ class ConvRT:
                              act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats, dyg=dyg,
                              dx_out=dx_out, full_padded=full_padded)
         self.bank = None
+        self.trainable = bool(trainable)
         self.tf32 = bool(tf32)
         wdt = torch.float32 if tf32 else torch.bfloat16
         dev = weight.device
@@ -86,9 +89,9 @@ class ConvRT:
         shape = tuple(weight.shape)
         self._wver = None
         self.fwd = []
-        for sp, wm in CV.conv_fwd_plans(shape, xg, stride, cp, out, transposed=transposed, output_padding=output_padding,
-                                        act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats,
-                                        note=name + ".fwd", tf32=tf32):
+        for sp, wm in (CV.conv_fwd_plans(shape, xg, stride, cp, out, transposed=transposed, output_padding=output_padding,
+                                         act=act, act_slope=act_slope, stats=stats, per_sample_stats=per_sample_stats,
+                                         note=name + ".fwd", tf32=tf32) if want_fwd else []):
             sp.stats_div = int(stats_div)      # > 1: per-sample statistics plans emit one statistic per run of stats_div samples
             self.fwd.append((ops.Igemm(sp), wm.to(dev), torch.zeros(sp.b_rows * sp.b_k + 64, dtype=wdt, device=dev)))
         self.dgrad = []
@@ -199,7 +202,7 @@ class WeightBank:
         """Move every convolution's packed gradient into one flat fp32 arena (builds the weight-gradient plans)."""
         if self.deferred:
             return
-        trainable = [c for c in self.convs if c._wg_args[1] is not None]
+        trainable = [c for c in self.convs if c._wg_args[1] is not None and c.trainable]
         sizes = []
         for c in trainable:
             g, wm, packed = c.ensure_wgrad()

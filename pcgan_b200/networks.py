@@ -353,6 +353,296 @@ class ResnetGenerator(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------
+# UnetGenerator (networks.py:655-733): the default G of wsgan_emb (unet_128)
+# ---------------------------------------------------------------------------------------
+class _UnetWorkspace:
+    pass
+
+
+class _UnetProgram:
+    """UnetGenerator(num_downs = D) at fixed (N, S) with InstanceNorm (wsgan_emb: --norm_G instance).
+
+    Level k = 0 .. D-1 (0 outermost): down convolution k (4x4 s2 p1) takes the image (k = 0) or A[k-1] = LeakyReLU(n_{k-1});
+    n_k = InstanceNorm(conv_k) for 0 < k < D-1, the raw convolution for k = 0 and k = D-1.  The reference's LeakyReLU is
+    in place, so the skip connection carries LeakyReLU(n_k) and the up path's ReLU turns it into ReLU(n_k)
+    (networks.py:692-733).  The concatenation consumed by up convolution k is ONE buffer B[k] of 2 C_k channels: its first
+    half ReLU(n_k) and its second half ReLU(InstanceNorm(upconv_{k+1})) are written by two norm_apply launches with a
+    channel offset, so no concat pass exists.  Backward: the data gradient of an up convolution is launched once per half
+    of its input channels (two weight views), so each half lands in its own dense buffer."""
+
+    def __init__(self, mod, N, S):
+        self.mod, self.N, self.S = mod, N, S
+        D = mod.num_downs
+        if S % (1 << D) or S < (1 << D):
+            raise NotImplementedError("UnetGenerator(num_downs=%d) needs a side that is a multiple of %d" % (D, 1 << D))
+        self.D = D
+        dev = mod.down[0].weight.device
+        self.dev = dev
+        G = Geom
+        C = mod.inner
+        sz = [S >> (k + 1) for k in range(D)]
+        self.sz, self.C = sz, C
+        self.g_x0 = G(N, S, S, 8, 1)
+        self.g_r = [G(N, sz[k], sz[k], C[k], 0) for k in range(D)]             # raw conv outputs / dense gradients
+        self.g_A = [G(N, sz[k], sz[k], C[k], 1) for k in range(D)]             # activation buffers (A[k], R at k = D-1), dY of up conv k+1
+        self.g_B = [G(N, sz[k], sz[k], 2 * C[k], 1) for k in range(D - 1)]     # concat buffers
+        ps = dict(stats=True, per_sample_stats=True)
+        self.down, self.up, self.up_ds, self.up_du = [], [], [], []
+        for k in range(D):
+            cv = mod.down[k]
+            xg = self.g_x0 if k == 0 else self.g_A[k - 1]
+            dx_out = OutMap.nhwc(G(N, S, S, 8, 0)) if k == 0 else OutMap.nhwc(self.g_r[k - 1])
+            if k == 0:
+                kw = dict(act=L.ACT_LRELU, act_slope=0.2)
+                out = OutMap.nhwc(self.g_A[0])
+            elif k == D - 1:
+                kw = dict(act=L.ACT_RELU)
+                out = OutMap.nhwc(self.g_A[k])
+            else:
+                kw, out = ps, OutMap.nhwc(self.g_r[k])
+            self.down.append(ConvRT("Gu.down%d" % k, cv.weight, cv.bias, xg, 2, 1, out, dyg=self.g_r[k], dx_out=dx_out, **kw))
+        for k in range(D):
+            cv = mod.up[k]
+            xg = self.g_A[k] if k == D - 1 else self.g_B[k]
+            so = S if k == 0 else sz[k - 1]
+            co = mod.output_nc if k == 0 else C[k - 1]
+            if k == 0:
+                out, kw, dyg = OutMap.nchw(N, co, S, S), dict(act=L.ACT_TANH), G(N, S, S, 8, 1)
+            else:
+                out, kw, dyg = OutMap.nhwc(self.g_r[k - 1]), ps, self.g_A[k - 1]
+            name = "Gu.up%d" % k
+            if k == D - 1:
+                self.up.append(ConvRT(name, cv.weight, cv.bias, xg, 2, 1, out, transposed=True, dyg=dyg, dx_out=OutMap.nhwc(self.g_r[k]), **kw))
+                self.up_ds.append(None); self.up_du.append(None)
+            else:
+                self.up.append(ConvRT(name, cv.weight, cv.bias, xg, 2, 1, out, transposed=True, dyg=dyg, want_dgrad=False, **kw))
+                # the data gradient, one launch set per half of the input channels (views of the IOHW weight)
+                half = dict(transposed=True, dyg=dyg, dx_out=OutMap.nhwc(self.g_r[k]), want_wgrad=False, want_fwd=False, trainable=False)
+                dummy = OutMap.nhwc(G(N, so, so, max(8, co), 0))
+                self.up_ds.append(ConvRT(name + ".dskip", cv.weight[:C[k]], None, self.g_A[k], 2, 1, dummy, **half))
+                self.up_du.append(ConvRT(name + ".dup", cv.weight[C[k]:], None, self.g_A[k], 2, 1, dummy, **half))
+        self.scratch = _Scratch(dev)
+        self.pool = Pool(lambda key: self._new_ws())
+        self.convs = self.down + self.up
+        extra = [c for c in self.up_ds + self.up_du if c is not None]
+        self.bank = WeightBank(self.convs + extra, dev)
+        if getattr(mod, "defer_wgrad", False):
+            self.bank.enable_deferred()
+
+    def _new_ws(self):
+        ws, dev, N, D = _UnetWorkspace(), self.dev, self.N, self.D
+        z = lambda g: zeros_act(g, dev)
+        ws.x0 = z(self.g_x0)
+        ws.A = [z(g) for g in self.g_A]
+        ws.B = [z(g) for g in self.g_B]
+        ws.r = [None] + [z(self.g_r[k]) for k in range(1, D - 1)] + [None]        # raw down outputs that are normalised
+        ws.u = [None] + [z(self.g_r[k - 1]) for k in range(1, D)]                  # raw up outputs u[k] (geometry of level k-1)
+        ws.stats_arena, ws.sums_arena = Arena(dev), Arena(dev)
+        NS = lambda c: NormState(N, c, dev, ws.stats_arena, ws.sums_arena)
+        ws.nd = [None] + [NS(self.C[k]) for k in range(1, D - 1)] + [None]
+        ws.nu = [None] + [NS(self.C[k - 1]) for k in range(1, D)]
+        ws.b_sums = [ws.sums_arena.take((1, c, 2)) for c in (self.C[0], self.C[D - 1], 8)]
+        ws.stats_arena.finalize()
+        ws.sums_arena.finalize()
+        ws.running = RunningStats(dev)
+        return ws
+
+    def forward(self, x, z):
+        mod, N, D, sz = self.mod, self.N, self.D, self.sz
+        ws = self.pool.take(0)
+        self.bank.ensure_packed()
+        ws.stats_arena.zero()
+        ws.running.begin()
+        ops.pack_nchw(x, ws.x0, self.g_x0, z=z, halo=L.HALO_ZERO)
+        ident = dict(scale=None, shift=None, groups=1)
+        # ---- down path
+        self.down[0].forward(ws.x0, ws.A[0])                                   # LeakyReLU(conv + bias) in the epilogue
+        ops.norm_apply(ws.A[0], self.g_A[0], ws.B[0], self.g_B[0], act=L.ACT_RELU, y_c0=0, **ident)
+        for k in range(1, D - 1):
+            nm = mod.down_norm[k]
+            _unit_forward(self.down[k], ws.A[k - 1], ws.r[k], ws.nd[k], sz[k] * sz[k], ws.running, rmean=nm.running_mean, rvar=nm.running_var)
+            ops.norm_apply(ws.r[k], self.g_r[k], ws.A[k], self.g_A[k], y_halo=L.HALO_ZERO, **ws.nd[k].apply_kw(), act=L.ACT_LRELU, act_slope=0.2)
+            ops.norm_apply(ws.r[k], self.g_r[k], ws.B[k], self.g_B[k], scale=ws.nd[k].scale, shift=ws.nd[k].shift, groups=N, act=L.ACT_RELU, y_c0=0)
+        self.down[D - 1].forward(ws.A[D - 2], ws.A[D - 1])                     # innermost: ReLU(conv + bias) (uprelu follows downconv directly)
+        # ---- up path
+        for k in range(D - 1, 0, -1):
+            nm = mod.up_norm[k]
+            src = ws.A[k] if k == D - 1 else ws.B[k]
+            _unit_forward(self.up[k], src, ws.u[k], ws.nu[k], sz[k - 1] * sz[k - 1], ws.running, rmean=nm.running_mean, rvar=nm.running_var)
+            ops.norm_apply(ws.u[k], self.g_r[k - 1], ws.B[k - 1], self.g_B[k - 1], **ws.nu[k].apply_kw(), act=L.ACT_RELU, y_c0=self.C[k - 1])
+        out = torch.empty(N, mod.output_nc, self.S, self.S, device=self.dev)
+        self.up[0].forward(ws.B[0], out)
+        ws.running.flush()
+        return out, ws
+
+    def _bias_grad(self, conv, dy, dy_pad, g: Geom, sums):
+        ops.norm_bwd_reduce(dy, dy_pad, dy, g, sums=sums, count=0.0)
+        accumulate_grad(conv.bias, sums[0, : conv.bias.numel(), 0])
+
+    def backward(self, ws, out, dout, need_dx, need_w, need_dz=False):
+        mod, N, D, sz, C, sc = self.mod, self.N, self.D, self.sz, self.C, self.scratch
+        self.bank.ensure_packed()
+        ws.sums_arena.zero()
+        if need_w:
+            self.bank.begin_backward()
+            for c in self.down[1:D - 1] + self.up[1:]:      # biases in front of an affine-less InstanceNorm: zero gradient
+                if c.bias is not None and c.bias.grad is None:
+                    c.bias.grad = torch.zeros_like(c.bias)
+        # ---- outermost up convolution: d(pre-tanh) = dout * (1 - out^2)
+        g_dyh = Geom(N, self.S, self.S, 8, 1)
+        dyh = sc.get(g_dyh, "dyh")
+        ops.pack_nchw(dout, dyh, g_dyh, mul_out=out, mul_kind=L.ACT_TANH, halo=L.HALO_ZERO)
+        if need_w:
+            self._bias_grad(self.up[0], dyh, 1, g_dyh, ws.b_sums[2].t)
+            self.up[0].backward_weight(dyh, ws.B[0])
+        gs, gu = sc.get(self.g_r[0], "gs0"), sc.get(self.g_r[0], "gu0")
+        self.up_ds[0].backward_data(dyh, gs)
+        self.up_du[0].backward_data(dyh, gu)
+        skip = [None] * D          # skip[k]: gradient of ReLU(n_k) through the concatenation
+        skip[0] = gs
+        # ---- up path, outermost to innermost: level k's up convolution produced the second half of B[k-1]
+        for k in range(1, D):
+            dyu = sc.get(self.g_A[k - 1], "dyu%d" % k)
+            _norm_backward(gu, 0, ws.u[k], self.g_r[k - 1], ws.nu[k], L.ACT_RELU, 0.0, sz[k - 1] * sz[k - 1], dyu, 1)
+            src = ws.A[k] if k == D - 1 else ws.B[k]
+            if need_w:
+                self.up[k].backward_weight(dyu, src)
+            if k == D - 1:
+                gR = sc.get(self.g_r[k], "gR")
+                self.up[k].backward_data(dyu, gR)
+            else:
+                gs, gu = sc.get(self.g_r[k], "gs%d" % k), sc.get(self.g_r[k], "gu%d" % k)
+                self.up_ds[k].backward_data(dyu, gs)
+                self.up_du[k].backward_data(dyu, gu)
+                skip[k] = gs
+        # ---- innermost down convolution: ReLU in its epilogue
+        k = D - 1
+        dy = sc.get(self.g_r[k], "dy%d" % k)
+        ops.act_bwd(gR, 0, ws.A[k], 1, dy, 0, self.g_r[k], 0.0)
+        if need_w:
+            self._bias_grad(self.down[k], dy, 0, self.g_r[k], ws.b_sums[1].t)
+            self.down[k].backward_weight(dy, ws.A[k - 1])
+        dA = sc.get(self.g_r[k - 1], "dA%d" % (k - 1))
+        self.down[k].backward_data(dy, dA)
+        # ---- down path, inner to outer: n_k receives the skip gradient through ReLU and dA[k] through LeakyReLU(0.2); both
+        # masks are the sign of n_k, so dy_eff = dA + skip * [n_k > 0] followed by the LeakyReLU backward gives their sum
+        for k in range(D - 2, -1, -1):
+            tmp = sc.get(self.g_r[k], "tmp%d" % k)
+            ops.act_bwd(skip[k], 0, ws.A[k], 1, tmp, 0, self.g_r[k], 0.0)
+            eff = sc.get(self.g_r[k], "eff%d" % k)
+            ops.halo_fold(tmp, self.g_r[k], eff, 0, halo=L.HALO_ZERO, add=dA, add_pad=0)
+            dy = sc.get(self.g_r[k], "dy%d" % k)
+            if k > 0:
+                _norm_backward(eff, 0, ws.r[k], self.g_r[k], ws.nd[k], L.ACT_LRELU, 0.2, sz[k] * sz[k], dy, 0)
+                if need_w:
+                    self.down[k].backward_weight(dy, ws.A[k - 1])
+                dA = sc.get(self.g_r[k - 1], "dA%d" % (k - 1))
+                self.down[k].backward_data(dy, dA)
+            else:
+                ops.act_bwd(eff, 0, ws.A[0], 1, dy, 0, self.g_r[0], 0.2)
+                if need_w:
+                    self._bias_grad(self.down[0], dy, 0, self.g_r[0], ws.b_sums[0].t)
+                    self.down[0].backward_weight(dy, ws.x0)
+        dx = dz = None
+        if need_dx or need_dz:
+            gx = sc.get(Geom(N, self.S, self.S, 8, 0), "gx")
+            self.down[0].backward_data(dy, gx)
+            nc = mod.input_nc_img
+            if need_dz:
+                dxz = torch.empty(N, nc + 1, self.S, self.S, device=self.dev)
+                ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dxz)
+                dx = dxz[:, :nc].contiguous() if need_dx else None
+                dz = dxz[:, nc].sum((1, 2))
+            else:
+                dx = torch.empty(N, nc, self.S, self.S, device=self.dev)
+                ops.unpack_resize_bwd(gx, Geom(N, self.S, self.S, 8, 0), dx)
+        return dx, dz
+
+
+class _UnetBlockHolder(nn.Module):
+    """Parameter holder with the reference's nesting and names (UnetSkipConnectionBlock.model, networks.py:685-733):
+    outermost [downconv, submodule, uprelu, upconv, tanh]; innermost [downrelu, downconv, uprelu, upconv, upnorm]; otherwise
+    [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]."""
+
+    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False, norm_layer=None):
+        super().__init__()
+        input_nc = outer_nc if input_nc is None else input_nc
+        I = nn.Identity
+        self.downconv = nn.Conv2d(input_nc, inner_nc, 4, 2, 1, bias=True)
+        self.downnorm = self.upnorm = None
+        if outermost:
+            self.upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, 4, 2, 1)
+            seq = [self.downconv, submodule, I(), self.upconv, I()]
+        elif innermost:
+            self.upconv = nn.ConvTranspose2d(inner_nc, outer_nc, 4, 2, 1, bias=True)
+            self.upnorm = norm_layer(outer_nc)
+            seq = [I(), self.downconv, I(), self.upconv, self.upnorm]
+        else:
+            self.upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, 4, 2, 1, bias=True)
+            self.downnorm, self.upnorm = norm_layer(inner_nc), norm_layer(outer_nc)
+            seq = [I(), self.downconv, self.downnorm, submodule, I(), self.upconv, self.upnorm]
+        # the convolutions / norms are registered once, under the Sequential (the attributes above are plain references)
+        for name in ("downconv", "upconv", "downnorm", "upnorm"):
+            object.__setattr__(self, "_" + name, self._modules.pop(name, None) if name in self._modules else getattr(self, name, None))
+        self.model = nn.Sequential(*seq)
+
+
+class UnetGenerator(nn.Module):
+    """Same constructor, forward signature and state_dict keys as models/networks.py:659-682 (norm = InstanceNorm2d with
+    running statistics, no dropout: the wsgan_emb configuration); the math runs in _UnetProgram."""
+
+    def __init__(self, input_nc, output_nc, nz=0, num_downs=7, ngf=64, norm_layer=nn.BatchNorm2d, dropout=0):
+        super().__init__()
+        func = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
+        if func is not nn.InstanceNorm2d or dropout:
+            raise NotImplementedError("pcgan_b200 UnetGenerator: instance norm, no dropout (the wsgan_emb configuration)")
+        if ngf % 64 != 0 or input_nc + nz > 8 or output_nc > 8 or nz != 1 or num_downs < 5:
+            raise NotImplementedError("ngf must be a multiple of 64, nz == 1, input_nc + nz and output_nc <= 8, num_downs >= 5")
+        self.input_nc_img, self.output_nc, self.nz, self.ngf, self.num_downs = input_nc, output_nc, nz, ngf, num_downs
+        self.inner = [ngf, ngf * 2, ngf * 4] + [ngf * 8] * (num_downs - 3)
+        blk = _UnetBlockHolder(ngf * 8, ngf * 8, norm_layer=norm_layer, innermost=True)
+        blocks = [blk]
+        for _ in range(num_downs - 5):
+            blk = _UnetBlockHolder(ngf * 8, ngf * 8, submodule=blk, norm_layer=norm_layer)
+            blocks.append(blk)
+        for outer, inner in ((ngf * 4, ngf * 8), (ngf * 2, ngf * 4), (ngf, ngf * 2)):
+            blk = _UnetBlockHolder(outer, inner, submodule=blk, norm_layer=norm_layer)
+            blocks.append(blk)
+        blk = _UnetBlockHolder(output_nc, ngf, input_nc=input_nc + nz, submodule=blk, outermost=True, norm_layer=norm_layer)
+        blocks.append(blk)
+        self.model = blk
+        levels = blocks[::-1]                  # level 0 = outermost
+        object.__setattr__(self, "down", [b._downconv for b in levels])
+        object.__setattr__(self, "up", [b._upconv for b in levels])
+        object.__setattr__(self, "down_norm", [b._downnorm for b in levels])
+        object.__setattr__(self, "up_norm", [b._upnorm for b in levels])
+        self._programs = {}
+        self._key = CO.register_module(self)
+
+    def _program(self, n, s):
+        k = (n, s, self.down[0].weight.device)
+        if k not in self._programs:
+            self._programs[k] = _UnetProgram(self, n, s)
+        return self._programs[k]
+
+    def zero_wgrad(self):
+        for prog in self._programs.values():
+            prog.bank.zero_wgrad()
+
+    def flush_wgrad(self):
+        for prog in self._programs.values():
+            prog.bank.flush_wgrad()
+
+    def forward(self, input, z=None):
+        _require_cuda(input, "UnetGenerator")
+        if z is None or input.shape[2] != input.shape[3]:
+            raise NotImplementedError("UnetGenerator needs square inputs and the 1-channel embedding z")
+        out = torch.ops.pcgan.unet_generator(input, z, list(self.parameters()), self._key)
+        CO.finish_forward(self._key, out)
+        return out
+
+
+# ---------------------------------------------------------------------------------------
 # NLayerDiscriminator
 # ---------------------------------------------------------------------------------------
 class _DiscWorkspace:
@@ -720,8 +1010,11 @@ def define_G(input_nc, output_nc, nz, ngf, which_model_netG="unet_128", norm="ba
         net = ResnetGenerator(input_nc, output_nc, nz, ngf, norm_layer=norm_layer, dropout=dropout, n_blocks=9)
     elif which_model_netG == "resnet_6blocks":
         net = ResnetGenerator(input_nc, output_nc, nz, ngf, norm_layer=norm_layer, dropout=dropout, n_blocks=6)
+    elif which_model_netG in ("unet_128", "unet_256", "unet"):
+        downs = {"unet_128": 7, "unet_256": 8, "unet": n_layers_G}[which_model_netG]
+        net = UnetGenerator(input_nc, output_nc, nz, downs, ngf, norm_layer=norm_layer, dropout=dropout)
     else:
-        raise NotImplementedError("Generator [%s] is outside the wsgan_emb hot path (resnet_9blocks / resnet_6blocks)" % which_model_netG)
+        raise NotImplementedError("Generator [%s] is outside the wsgan_emb hot path (resnet_9blocks / resnet_6blocks / unet_128 / unet_256 / unet)" % which_model_netG)
     return init_net(net, init_type, gpu_ids)
 
 

@@ -193,15 +193,23 @@ def norm_finalize(stats, groups, c, count, *, eps=1e-5, momentum=0.1, gamma=None
 
 def norm_apply(x, xg: Geom, y, yg: Geom, *, y_halo=L.HALO_ZERO, scale=None, shift=None, groups=1, res=None, res_pad=0,
                res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, post_mask=None,
-               stats=None, count=0.0, eps=1e-5, gamma=None, beta=None, mean_out=None, rstd_out=None, scale_out=None, shift_out=None):
-    """stats given: the finalize (statistics -> scale / shift) is fused into this launch; scale / shift are ignored."""
-    assert (xg.n, xg.h, xg.w, xg.c) == (yg.n, yg.h, yg.w, yg.c)
+               stats=None, count=0.0, eps=1e-5, gamma=None, beta=None, mean_out=None, rstd_out=None, scale_out=None, shift_out=None,
+               y_c0=None):
+    """stats given: the finalize (statistics -> scale / shift) is fused into this launch; scale / shift are ignored.
+    y_c0 given: y is a buffer of yg.c >= xg.c channels and the xg.c output channels go to [y_c0, y_c0 + xg.c)."""
+    if y_c0 is None:
+        assert (xg.n, xg.h, xg.w, xg.c) == (yg.n, yg.h, yg.w, yg.c)
+        y_c, y_c0 = 0, 0
+    else:
+        assert (xg.n, xg.h, xg.w) == (yg.n, yg.h, yg.w) and y_c0 + xg.c <= yg.c
+        y_c = yg.c
     a = L.NormApplyArgs(x=_ptr(x), x_pad=xg.pad, res=_ptr(res), res_pad=res_pad, y=_ptr(y), y_pad=yg.pad, y_halo=y_halo,
                         n=xg.n, h=xg.h, w=xg.w, c=xg.c, scale=_ptr(scale), shift=_ptr(shift), groups=groups,
                         res_scale=_ptr(res_scale), res_shift=_ptr(res_shift), res_groups=res_groups,
                         drop_mask=_ptr(drop_mask), act=act, act_slope=act_slope, post_mask=_ptr(post_mask),
                         stats=_ptr(stats), count=float(count), eps=eps, gamma=_ptr(gamma), beta=_ptr(beta),
-                        mean_out=_ptr(mean_out), rstd_out=_ptr(rstd_out), scale_out=_ptr(scale_out), shift_out=_ptr(shift_out))
+                        mean_out=_ptr(mean_out), rstd_out=_ptr(rstd_out), scale_out=_ptr(scale_out), shift_out=_ptr(shift_out),
+                        y_c=y_c, y_c0=y_c0)
     _count()
     elems = xg.n * xg.h * xg.w * xg.c
     with _Timed("norm_apply", elems * 2 * (2 + (res is not None))):

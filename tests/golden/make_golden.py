@@ -362,7 +362,33 @@ def golden_step_ip():
     print("IP step:", losses)
 
 
+def golden_unet():
+    """UnetGenerator(unet_128, instance norm), the default G of wsgan_emb (networks.py:659-733): output and a few
+    gradients on seeded weights and inputs."""
+    from models import networks
+    net = networks.define_G(3, 3, 1, 64, "unet_128", "instance", "relu", 0, "normal", [])
+    sd = net.state_dict()
+    O.fill_state_dict_(sd, 71)
+    x, _, _ = O.synthetic_batch(2, 128, 801)
+    x.requires_grad_(True)
+    z = torch.tensor([0.3, -0.8]).view(2, 1, 1, 1)
+    out = net(x, z)
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    named = dict(net.named_parameters())
+    torch.save({"seed": 71, "x_seed": 801, "z": z, "keys": list(sd.keys()), "out_sub": sub(out.detach(), 8), "out_mean": out.mean().detach(),
+                "dx_sub": sub(x.grad, 8), "g_down0": named["model.model.0.weight"].grad[:4].clone(),
+                "g_up0": named["model.model.3.weight"].grad[:4].clone(),
+                "g_inner_down": named["model.model.1.model.3.model.3.model.3.model.3.model.3.model.1.weight"].grad[:2, :2].clone(),
+                "g_inner_bias": named["model.model.1.model.3.model.3.model.3.model.3.model.3.model.1.bias"].grad[:8].clone(),
+                "rm": sd["model.model.1.model.2.running_mean"][:8].clone()}, os.path.join(HERE, "unet.pt"))
+    print("unet:", float(out.mean()), float(out.std()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "unet":
+        golden_unet()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ip":
         golden_step_ip()
         sys.exit(0)
@@ -384,6 +410,7 @@ if __name__ == "__main__":
     golden_step_bayesian()
     golden_step_variants()
     golden_step_ip()
+    golden_unet()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -79,7 +79,7 @@ def conv_stage(log, name, x, w, fn, gy, my_y, my_dx, my_dw, tol_y=TOL):
 
 
 def norm_stage(log, name, r, gy, my_y, my_dr, ns, *, kind, act="relu", slope=0.0, gamma=None, beta=None, res=None, my_dres=None,
-               my_dgamma=None, my_dbeta=None, res_mine=None):
+               my_dgamma=None, my_dbeta=None, res_mine=None, tol_bwd=TOL):
     """Instance / batch normalisation (+ residual) (+ ReLU / LeakyReLU), forward and backward, by fp32 autograd from the
     stored bf16 pre-norm tensor `r`.  The kernels normalise with the statistics of the fp32 accumulators, the reference
     here with those of the bf16-rounded tensor: that 1e-4 difference flips the mask of ~1e-3 of the elements (3e-2 in the
@@ -106,7 +106,11 @@ def norm_stage(log, name, r, gy, my_y, my_dr, ns, *, kind, act="relu", slope=0.0
         y = torch.where(mine > 0, pre, neg * pre)
     log.check(name + ".fwd", my_y, y_ref)
     y.backward(gy)
-    log.check(name + ".bwd", my_dr, rr.grad)
+    if kind == "instance" and r.size(2) * r.size(3) <= 16:
+        # an instance norm over <= 16 pixels divides by the standard deviation of a handful of bf16-rounded values: the
+        # statistics of the fp32 accumulators (kernels) and of the stored bf16 tensor (this reference) differ by 1e-3 there
+        tol_bwd = 2 * tol_bwd
+    log.check(name + ".bwd", my_dr, rr.grad, tol_bwd)
     if res is not None and my_dres is not None:
         log.check(name + ".dres", my_dres, res.grad)
     if my_dgamma is not None:
@@ -442,3 +446,94 @@ def test_alexnet_chain_teacher_forced(N, S):
     log.check("input pack", x0, bf(a), 1e-6)
     log.report("IP chain N=%d S=%d" % (N, S))
     assert len(log.rows) >= 24
+
+
+# ------------------------------------------------------------------------------------------ unet generator
+@pytest.mark.parametrize("N,S,D", [(2, 128, 7), (16, 128, 7), (2, 64, 5)], ids=["b2_unet128", "b16_unet128", "b2_s64_5downs"])
+def test_unet_chain_teacher_forced(N, S, D):
+    """UnetGenerator (models/networks.py:659-733; the default G of wsgan_emb), every stage: down convolutions with their
+    InstanceNorm + in-place LeakyReLU, the skip halves (ReLU of the LeakyReLU'd tensor) and up halves of the concatenation
+    buffers, up convolutions with InstanceNorm + ReLU, tanh; backward: the two halves of every up convolution's data
+    gradient, the skip + down-path sum at every level, all weight and bias gradients."""
+    sd = O.make_state_dict(O.unet_keys(num_downs=D), 71, device=DEV)
+    net = NW.init_net(NW.UnetGenerator(3, 3, 1, D, 64, norm_layer=NW.get_norm_layer("instance")), "normal", [0])
+    mod = net.module
+    mod.load_state_dict({k: v.clone() for k, v in sd.items()})
+    P = mod._program(N, S)
+    a, _, _ = O.synthetic_batch(N, S, 306, device=DEV)
+    z = torch.linspace(-1, 1, N, device=DEV).view(N, 1, 1, 1)
+    out, ws = P.forward(a.contiguous(), z.view(-1).contiguous())
+    dout = torch.randn_like(out)
+    dx, _ = P.backward(ws, out, dout, True, True)
+    torch.cuda.synchronize()
+    sc, log, C, sz = P.scratch, Log(), P.C, P.sz
+    dn, up = mod.down, mod.up
+    get = lambda g, tag: inner(sc.get(g, tag), g)
+    with torch.no_grad():
+        log.check("output vs oracle (end to end)", out, O.unet_forward(sd, a, z, D), 5e-2)
+    # ---- outermost up convolution + tanh
+    g_dyh = NW.Geom(N, S, S, 8, 1)
+    dyh = get(g_dyh, "dyh")[:, :3]
+    log.check("up0.dtanh", dyh, dout * (1 - out * out))
+    B0 = inner(ws.B[0], P.g_B[0])
+    gB0 = conv_stage(log, "up0", B0, up[0].weight, lambda x, w: F.conv_transpose2d(x, w, stride=2, padding=1), dyh, None, None, up[0].weight.grad)
+    with torch.no_grad():
+        log.check("up0.fwd", out, torch.tanh(F.conv_transpose2d(B0, bf(up[0].weight.detach()), up[0].bias.detach(), stride=2, padding=1)), 1e-4)
+    log.check("up0.bias_grad", up[0].bias.grad, dyh.sum((0, 2, 3)), 1e-3)
+    log.check("up0.dgrad.skip", get(P.g_r[0], "gs0"), gB0[:, :C[0]])
+    log.check("up0.dgrad.up", get(P.g_r[0], "gu0"), gB0[:, C[0]:])
+    # ---- up path
+    for k in range(1, D):
+        gu = get(P.g_r[k - 1], "gu%d" % (k - 1))
+        dyu = get(P.g_A[k - 1], "dyu%d" % k)
+        norm_stage(log, "up%d.norm" % k, inner(ws.u[k], P.g_r[k - 1]), gu, inner(ws.B[k - 1], P.g_B[k - 1])[:, C[k - 1]:], dyu, ws.nu[k], kind="instance")
+        src = inner(ws.A[k], P.g_A[k]) if k == D - 1 else inner(ws.B[k], P.g_B[k])
+        gsrc = conv_stage(log, "up%d.conv" % k, src, up[k].weight, lambda x, w: F.conv_transpose2d(x, w, up[k].bias.detach(), stride=2, padding=1),
+                          dyu, inner(ws.u[k], P.g_r[k - 1]), None, up[k].weight.grad)
+        if k == D - 1:
+            log.check("up%d.dgrad" % k, get(P.g_r[k], "gR"), gsrc)
+        else:
+            log.check("up%d.dgrad.skip" % k, get(P.g_r[k], "gs%d" % k), gsrc[:, :C[k]])
+            log.check("up%d.dgrad.up" % k, get(P.g_r[k], "gu%d" % k), gsrc[:, C[k]:])
+    # ---- innermost down convolution (ReLU in the epilogue, no norm)
+    k = D - 1
+    R, gR, dyk = inner(ws.A[k], P.g_A[k]), get(P.g_r[k], "gR"), get(P.g_r[k], "dy%d" % k)
+    log.check("down%d.drelu" % k, dyk, torch.where(R > 0, gR, torch.zeros_like(gR)), 1e-6)
+    xin = inner(ws.A[k - 1], P.g_A[k - 1])
+    xx = xin.clone().requires_grad_(True)
+    wq = bf(dn[k].weight.detach()).clone().requires_grad_(True)
+    bq = dn[k].bias.detach().clone().requires_grad_(True)
+    pre = F.conv2d(xx, wq, bq, stride=2, padding=1)
+    log.check("down%d.fwd" % k, R, torch.relu(pre))
+    pre.backward(dyk)
+    log.check("down%d.wgrad" % k, dn[k].weight.grad, wq.grad)
+    log.check("down%d.bias_grad" % k, dn[k].bias.grad, bq.grad, 1e-3)
+    log.check("down%d.dgrad" % k, get(P.g_r[k - 1], "dA%d" % (k - 1)), xx.grad)
+    # ---- down path, inner to outer
+    for k in range(D - 2, -1, -1):
+        A_k = inner(ws.A[k], P.g_A[k])
+        skip, dA = get(P.g_r[k], "gs%d" % k), get(P.g_r[k], "dA%d" % k)
+        eff = get(P.g_r[k], "eff%d" % k)
+        log.check("down%d.skip+path" % k, eff, dA + torch.where(A_k > 0, skip, torch.zeros_like(skip)))
+        log.check("down%d.skip half" % k, inner(ws.B[k], P.g_B[k])[:, :C[k]], torch.relu(A_k), 1e-6)
+        dyk = get(P.g_r[k], "dy%d" % k)
+        if k > 0:
+            norm_stage(log, "down%d.norm" % k, inner(ws.r[k], P.g_r[k]), eff, A_k, dyk, ws.nd[k], kind="instance", act="lrelu", slope=0.2)
+            conv_stage(log, "down%d.conv" % k, inner(ws.A[k - 1], P.g_A[k - 1]), dn[k].weight,
+                       lambda x, w: F.conv2d(x, w, dn[k].bias.detach(), stride=2, padding=1), dyk, inner(ws.r[k], P.g_r[k]),
+                       get(P.g_r[k - 1], "dA%d" % (k - 1)), dn[k].weight.grad)
+        else:
+            log.check("down0.dlrelu", dyk, torch.where(A_k > 0, eff, 0.2 * eff))
+            x0 = inner(ws.x0, P.g_x0)[:, :4].clone().requires_grad_(True)
+            wq = bf(dn[0].weight.detach()).clone().requires_grad_(True)
+            bq = dn[0].bias.detach().clone().requires_grad_(True)
+            pre = F.conv2d(x0, wq, bq, stride=2, padding=1)
+            log.check("down0.fwd", A_k, F.leaky_relu(pre, 0.2))
+            pre.backward(dyk)
+            log.check("down0.wgrad", dn[0].weight.grad, wq.grad)
+            log.check("down0.bias_grad", dn[0].bias.grad, bq.grad, 1e-3)
+            log.check("down0.dgrad -> dx", dx, x0.grad[:, :3])
+    xz = torch.cat([a, z.expand(N, 1, S, S)], 1)
+    log.check("input pack", inner(ws.x0, P.g_x0)[:, :4], bf(xz), 1e-6)
+    log.report("Unet chain N=%d S=%d downs=%d" % (N, S, D))
+    assert len(log.rows) >= 10 * D

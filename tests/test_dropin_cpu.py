@@ -62,7 +62,7 @@ def test_factory_signatures_match_the_reference():
 
 def test_unsupported_variants_and_cpu_fail_loudly():
     with pytest.raises(NotImplementedError):
-        NW.define_G(3, 3, 1, 64, "unet_128", "instance", gpu_ids=[])
+        NW.define_G(3, 3, 1, 64, "unet_128_input", "instance", gpu_ids=[])
     with pytest.raises(NotImplementedError):
         NW.define_D(3, 1, 64, "pixel", 3, "batch", True, gpu_ids=[])
     with pytest.raises(NotImplementedError):

@@ -223,3 +223,26 @@ def test_identity_preserving_step_matches_reference():
         assert abs(got[k] - fx["losses"][k]) <= 2e-4 * abs(fx["losses"][k]) + 1e-7, (k, got[k], fx["losses"][k])
     assert close(m.fake_b.detach()[..., ::4, ::4], fx["fake_b_sub"], 1e-4)
     assert close(m.g["model.10.conv_block.1.weight"][:4, :4], fx["g_w_after"], 1e-4)
+
+
+def test_unet_generator_matches_reference():
+    """UnetGenerator (unet_128, InstanceNorm with running statistics; models/networks.py:659-733), incl. the in-place
+    LeakyReLU that the skip connections carry, against the reference's module (tests/golden/unet.pt)."""
+    fx = load("unet.pt")
+    torch.set_num_threads(8)
+    keys = O.unet_keys()
+    assert list(keys.keys()) == fx["keys"]
+    sd = O.make_state_dict(keys, fx["seed"], requires_grad=True)
+    x, _, _ = O.synthetic_batch(2, 128, fx["x_seed"])
+    x.requires_grad_(True)
+    out = O.unet_forward(sd, x, fx["z"])
+    assert close(out.detach()[..., ::8, ::8], fx["out_sub"], 1e-4) and abs(float(out.mean()) - float(fx["out_mean"])) < 1e-5
+    w = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * w).sum().backward()
+    assert close(x.grad[..., ::8, ::8], fx["dx_sub"], 2e-3)
+    assert close(sd["model.model.0.weight"].grad[:4], fx["g_down0"], 2e-3)
+    assert close(sd["model.model.3.weight"].grad[:4], fx["g_up0"], 2e-3)
+    inner = "model.model.1.model.3.model.3.model.3.model.3.model.3.model.1"
+    assert close(sd[inner + ".weight"].grad[:2, :2], fx["g_inner_down"], 2e-3)
+    assert close(sd[inner + ".bias"].grad[:8], fx["g_inner_bias"], 2e-3)
+    assert close(sd["model.model.1.model.2.running_mean"][:8], fx["rm"], 1e-4)

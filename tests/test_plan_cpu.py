@@ -367,3 +367,47 @@ def test_conv_wgrad_plan_tf32(case):
     wref = torch.zeros(cout, cin, k, k, requires_grad=True)
     F.conv2d(xr, wref, stride=stride).backward(bf16_round(dy))
     assert rel(dw.view(cout, cin, k, k), wref.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------- UnetGenerator shapes
+@pytest.mark.parametrize("cin,cout,H,N", [(128, 3, 8, 2), (512, 512, 1, 3), (256, 64, 4, 2)], ids=["outermost_128to3", "innermost_1x1", "mid"])
+def test_unet_conv_transpose_4x4_plans(cin, cout, H, N):
+    """nn.ConvTranspose2d(cin, cout, 4, 2, 1) (networks.py:699-713): forward by sub-pixel phases, data gradient (for few
+    output channels: packed filter rows of the 8-channel dY) and weight gradient, down to a 1 x 1 input."""
+    torch.manual_seed(8)
+    x, w = torch.randn(N, cin, H, H), torch.randn(cin, cout, 4, 4) * 0.1
+    cob = max(8, -(-cout // 8) * 8)
+    xg, og = Geom(N, H, H, cin, 1), Geom(N, 2 * H, 2 * H, cob, 0)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, 2, 1, OutMap.nhwc(og, dtype=L.DT_F32), transposed=True)
+    out = run_fwd(plans, to_padded_nhwc(x, 1, "zero"), w, og.numel)
+    ref = F.conv_transpose2d(bf16_round(x), bf16_round(w), stride=2, padding=1)
+    assert rel(from_padded_nhwc(out, N, 2 * H, 2 * H, cob, 0)[:, :cout], ref) < 1e-5
+    dy = torch.randn(N, cout, 2 * H, 2 * H)
+    dyg, dxg = Geom(N, 2 * H, 2 * H, cob, 1), Geom(N, H, H, cin, 0)
+    plans = CV.conv_dgrad_plans(tuple(w.shape), dyg, xg, 2, 1, OutMap.nhwc(dxg, dtype=L.DT_F32), transposed=True)
+    out = run_fwd(plans, to_padded_nhwc(dy, 1, "zero", cob), w, dxg.numel)
+    xr = torch.zeros(N, cin, H, H, requires_grad=True)
+    F.conv_transpose2d(xr, bf16_round(w), stride=2, padding=1).backward(bf16_round(dy))
+    assert rel(from_padded_nhwc(out, N, H, H, cin, 0), xr.grad) < 1e-5
+    # weight gradient: M side = the input activations, N side = dY
+    sp, wm = CV.conv_wgrad_plan(tuple(w.shape), dyg, xg, 2, 1, transposed=True)
+    ops.Igemm(sp)
+    packed = torch.zeros(sp.b_rows * sp.b_k)
+    emu.run_wgrad(sp, to_padded_nhwc(x, 1, "zero")[sp.a_elem_offset:], to_padded_nhwc(dy, 1, "zero", cob)[sp.b_elem_offset:], packed)
+    dw = torch.zeros(w.numel())
+    idx = wm.long()
+    dw[idx[idx >= 0]] = packed[idx >= 0]
+    wr = torch.zeros_like(w, requires_grad=True)
+    F.conv_transpose2d(bf16_round(x), wr, stride=2, padding=1).backward(bf16_round(dy))
+    assert rel(dw.view_as(w), wr.grad) < 1e-5
+
+
+def test_unet_down_conv_to_1x1_plan():
+    torch.manual_seed(9)
+    N, C = 3, 128
+    x, w, b = torch.randn(N, C, 2, 2), torch.randn(64, C, 4, 4) * 0.1, torch.randn(64)
+    xg, og = Geom(N, 2, 2, C, 1), Geom(N, 1, 1, 64, 1)
+    plans = CV.conv_fwd_plans(tuple(w.shape), xg, 2, 1, OutMap.nhwc(og, dtype=L.DT_F32), act=L.ACT_RELU)
+    out = run_fwd(plans, to_padded_nhwc(x, 1, "zero"), w, og.numel, bias=b)
+    ref = torch.relu(F.conv2d(bf16_round(x), bf16_round(w), b, stride=2, padding=1))
+    assert rel(from_padded_nhwc(out, N, 1, 1, 64, 1), ref) < 1e-5
