@@ -24,3 +24,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_every_test():
+    """Each test draws from the same RNG state wherever it runs in the suite (the data, not the order, decides)."""
+    try:
+        import torch
+        torch.manual_seed(20260)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed_all(20260)
+    except Exception:
+        pass
+    yield

@@ -106,11 +106,19 @@ def norm_stage(log, name, r, gy, my_y, my_dr, ns, *, kind, act="relu", slope=0.0
         y = torch.where(mine > 0, pre, neg * pre)
     log.check(name + ".fwd", my_y, y_ref)
     y.backward(gy)
-    if kind == "instance" and r.size(2) * r.size(3) <= 16:
-        # an instance norm over <= 16 pixels divides by the standard deviation of a handful of bf16-rounded values: the
-        # statistics of the fp32 accumulators (kernels) and of the stored bf16 tensor (this reference) differ by 1e-3 there
-        tol_bwd = 2 * tol_bwd
-    log.check(name + ".bwd", my_dr, rr.grad, tol_bwd)
+    want_dr = rr.grad
+    if kind == "instance" and r.size(2) * r.size(3) <= 16 and res is None:
+        # An instance norm over <= 16 pixels is ill-conditioned in the stored tensor: where a channel's mean is far from 0
+        # relative to the spread of its handful of values, the statistics of the bf16-rounded tensor (autograd above) and of
+        # the fp32 accumulators (kernels) give visibly different x_hat (up to 3e-2 in the gradient, data dependent).  Like
+        # the masks, the statistics are therefore teacher-forced here: the closed-form backward with the kernels' own
+        # mean / rstd,  dx = rstd (g - mean(g) - x_hat mean(g x_hat)).
+        mk, rk = ns.mean.view(groups, -1, 1, 1), ns.rstd.view(groups, -1, 1, 1)
+        xh = (r - mk) * rk
+        neg = slope if act == "lrelu" else 0.0
+        g = gy if act == "none" else torch.where(mine > 0, gy, neg * gy)
+        want_dr = rk * (g - g.mean((2, 3), keepdim=True) - xh * (g * xh).mean((2, 3), keepdim=True))
+    log.check(name + ".bwd", my_dr, want_dr, tol_bwd)
     if res is not None and my_dres is not None:
         log.check(name + ".dres", my_dres, res.grad)
     if my_dgamma is not None:
@@ -463,7 +471,7 @@ def test_unet_chain_teacher_forced(N, S, D):
     a, _, _ = O.synthetic_batch(N, S, 306, device=DEV)
     z = torch.linspace(-1, 1, N, device=DEV).view(N, 1, 1, 1)
     out, ws = P.forward(a.contiguous(), z.view(-1).contiguous())
-    dout = torch.randn_like(out)
+    dout = torch.randn(out.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(307))
     dx, _ = P.backward(ws, out, dout, True, True)
     torch.cuda.synchronize()
     sc, log, C, sz = P.scratch, Log(), P.C, P.sz

@@ -310,4 +310,6 @@ def test_grouped_passes_equal_separate_passes():
         if "tracked" in k:
             assert int(b1[k]) == int(b2[k]) == 2, k
         else:
-            assert rel(b2[k], b1[k]) < 2e-3, k
+            # deep layers inherit the run-to-run difference of the activations (above): 2e-3 at layer4; statistics taken
+            # over the wrong batch, or momentum steps merged / reordered, would be off by > 1e-1
+            assert rel(b2[k], b1[k]) < 1e-2, k
