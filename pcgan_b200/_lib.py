@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcgan_kernels.so")
+# PCGAN_KERNELS_LIB: another build of the same library (A/B measurements of a kernel change: tools/norm_bench.py)
+LIB_PATH = os.environ.get("PCGAN_KERNELS_LIB") or os.path.join(_HERE, "libpcgan_kernels.so")
 
 ABI_VERSION = 19
 MAX_TAPS = 64

@@ -144,8 +144,13 @@ __global__ void __launch_bounds__(kT) norm_running_batched_kernel(const pcgan_ru
 // (~45 KB in flight per SM at full bandwidth).  A segment = seg_px consecutive pixels of one image row
 // (<= 8 KB per stream); 8 consumer warps process it (thread = 16-byte vector, fixed 8 channels) and hand the stage
 // back through an "empty" mbarrier.
-static constexpr int kConsumers = 256;                    // consumer threads
+static constexpr int kConsumers = 256;                    // consumer threads of the backward kernels
 static constexpr int kStreamThreads = kConsumers + 32;    // + producer warp
+// norm_apply keeps half as many consumer threads: its per-thread state is small, so four vectors per thread and segment
+// (instead of two) halve the per-segment bookkeeping and the per-block prologue, which is what bounds it at the
+// ResnetBlock shape (33 MB, L2 resident: 16.1 -> 13.2 us; profiles/README.md, round 2)
+static constexpr int kApplyConsumers = 128;
+static constexpr int kApplyThreads = kApplyConsumers + 32;
 static constexpr int kStages = 4;
 static constexpr int kSegBytes = 8192;
 
@@ -176,7 +181,7 @@ struct Pipe {
 };
 
 template <int NT>
-__device__ __forceinline__ Pipe<NT> pipe_init(uint8_t* smem) {
+__device__ __forceinline__ Pipe<NT> pipe_init(uint8_t* smem, int consumers = kConsumers) {
   Pipe<NT> p;
   p.data = smem;
   p.full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kStages) * NT * kSegBytes);
@@ -184,7 +189,7 @@ __device__ __forceinline__ Pipe<NT> pipe_init(uint8_t* smem) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&p.full[i], 1);
-      mbar_init(&p.empty[i], kConsumers / 32);
+      mbar_init(&p.empty[i], consumers / 32);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -229,11 +234,24 @@ __device__ __forceinline__ void pipe_produce(const Pipe<NT>& p, const SegGeom& s
 // y = act(sc*x + sh [+ rsc*res + rsh]) into the interior of y; under reflect halo every interior pixel within `pad`
 // of a border is also stored at its mirror positions (a zero halo is never written: the buffer is allocated zeroed
 // and only interiors are ever stored).
-template <bool RES>
-__global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_apply_args a, SegGeom sg, int segs_per_block, int lcv) {
+// x within `p` of a border but not on it: the pixels ReflectionPad2d copies into the halo (x in [1, p] or [w-1-p, w-2])
+__device__ __forceinline__ bool mirrored(int x, int w, int p) {
+  return static_cast<unsigned>(x - 1) < static_cast<unsigned>(p) || static_cast<unsigned>(x - (w - 1 - p)) < static_cast<unsigned>(p);
+}
+// ACT >= 0: the activation is fixed at compile time (the hot instantiations); ACT < 0: taken from the arguments
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, int act, float slope) {
+  if constexpr (ACT == PCGAN_ACT_NONE) return v;
+  else if constexpr (ACT == PCGAN_ACT_RELU) return fmaxf(v, 0.f);
+  else if constexpr (ACT == PCGAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  else return apply_act(v, act, slope);
+}
+
+template <bool RES, int ACT>
+__global__ void __launch_bounds__(kApplyThreads) norm_apply_kernel(pcgan_norm_apply_args a, SegGeom sg, int segs_per_block, int lcv) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int NT = RES ? 2 : 1;
-  Pipe<NT> pipe = pipe_init<NT>(smem_raw);
+  Pipe<NT> pipe = pipe_init<NT>(smem_raw, kApplyConsumers);
   const int n = blockIdx.y;
   const int32_t total_segs = a.h * sg.segs_per_row;
   const int32_t g0 = blockIdx.x * segs_per_block, g1 = min(g0 + segs_per_block, total_segs);
@@ -245,8 +263,8 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
     src[1].pad = a.res_pad; src[1].wp = a.w + 2 * a.res_pad;
     src[1].base = reinterpret_cast<const __nv_bfloat16*>(a.res) + static_cast<int64_t>(n) * (a.h + 2 * a.res_pad) * src[1].wp * a.c;
   }
-  if (threadIdx.x >= kConsumers) {
-    if (threadIdx.x == kConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
+  if (threadIdx.x >= kApplyConsumers) {
+    if (threadIdx.x == kApplyConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
     return;
   }
   const int c0 = (threadIdx.x & (cv - 1)) << 3;
@@ -307,23 +325,29 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
   for (int j = 0; j < 8; ++j) pm[j] = 1.f;
   const bool has_pm = a.post_mask != nullptr;
   if (has_pm) load_f8(a.post_mask + static_cast<int64_t>(n) * a.c + c0, pm);
-  const int p = a.y_pad, wp = a.w + 2 * p;
+  // Everything the per-vector loop needs, in registers: the loop itself is what bounds this kernel (issue slots, not HBM:
+  // profiles/README.md), so no divisions, no 64-bit index arithmetic and no halo tests for interior pixels in it.
+  const int p = a.y_pad, wp = a.w + 2 * p, w = a.w, h = a.h;
   const int ych = a.y_c > 0 ? a.y_c : a.c;       // channels per pixel of the output buffer (a channel slice of a wider one)
-  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + static_cast<int64_t>(n) * (a.h + 2 * p) * wp * ych + a.y_c0 + c0;
+  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(a.y) + static_cast<int64_t>(n) * (h + 2 * p) * wp * ych + a.y_c0 + c0;
   const bool reflect = a.y_halo == PCGAN_HALO_REFLECT && p > 0;
+  const int act = a.act;
+  const float slope = a.act_slope;
+  const int px0 = threadIdx.x >> lcv, dpx = kApplyConsumers >> lcv;    // this thread's pixels within a segment: px0, px0 + dpx, ...
+  const int seg_vec = sg.seg_vec, seg_px = sg.seg_px;
+  int32_t y = g0 / sg.segs_per_row;
+  int32_t x0 = (g0 - y * sg.segs_per_row) * seg_px;
   int s = 0;
   uint32_t ph = 0;
   for (int32_t g = g0; g < g1; ++g) {
-    const int32_t y = g / sg.segs_per_row;
-    const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
-    // padded rows this image row is stored to: itself and (reflect) its mirrors
-    const int ya = y + p;
-    const int yb = (reflect && y >= 1 && y <= p) ? p - y : -1;
-    const int yc = (reflect && y <= a.h - 2 && y >= a.h - 1 - p) ? p + 2 * (a.h - 1) - y : -1;
+    __nv_bfloat16* yrow = ys + ((y + p) * wp + x0 + p) * ych;      // element offsets fit 31 bits (checked on the host)
+    const bool rowm = reflect && mirrored(y, h, p);
     PIPE_CONSUME_BEGIN(pipe, s, ph);
     const uint4* sx = pipe.stage(s, 0);
     const uint4* sr = RES ? pipe.stage(s, 1) : nullptr;
-    for (int v = threadIdx.x; v < sg.seg_vec; v += kConsumers) {
+    int px = px0;
+#pragma unroll 2
+    for (int v = threadIdx.x; v < seg_vec; v += kApplyConsumers, px += dpx) {
       float x8[8], o[8];
       unpack8(sx[v], x8);
 #pragma unroll
@@ -335,20 +359,23 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
         for (int j = 0; j < 8; ++j) o[j] += fmaf(rsc[j], r8[j], rsh[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = apply_act(o[j], a.act, a.act_slope);
+      for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(o[j], act, slope);
       if (has_pm) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] *= pm[j];
       }
-      uint4 w;
-      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-      const int x = x0 + (v >> lcv);
-      const int xa = x + p;
-      *reinterpret_cast<uint4*>(ys + (ya * wp + xa) * ych) = w;
+      uint4 wv;
+      wv.x = pack_bf16x2(o[0], o[1]); wv.y = pack_bf16x2(o[2], o[3]); wv.z = pack_bf16x2(o[4], o[5]); wv.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yrow + px * ych) = wv;
       if (reflect) {
-        const int xb = (x >= 1 && x <= p) ? p - x : -1;
-        const int xc = (x <= a.w - 2 && x >= a.w - 1 - p) ? p + 2 * (a.w - 1) - x : -1;
-        if ((yb & yc & xb & xc) != -1) {
+        const int x = x0 + px;
+        if (rowm || mirrored(x, w, p)) {
+          // a pixel within `pad` of a border is also stored at its mirror positions in the halo
+          const int ya = y + p, xa = x + p;
+          const int yb = (y >= 1 && y <= p) ? p - y : -1;
+          const int yc = (y <= h - 2 && y >= h - 1 - p) ? p + 2 * (h - 1) - y : -1;
+          const int xb = (x >= 1 && x <= p) ? p - x : -1;
+          const int xc = (x <= w - 2 && x >= w - 1 - p) ? p + 2 * (w - 1) - x : -1;
 #pragma unroll
           for (int iy = 0; iy < 3; ++iy) {
             const int yy = iy == 0 ? ya : (iy == 1 ? yb : yc);
@@ -357,13 +384,15 @@ __global__ void __launch_bounds__(kStreamThreads) norm_apply_kernel(pcgan_norm_a
             for (int ix = 0; ix < 3; ++ix) {
               const int xx = ix == 0 ? xa : (ix == 1 ? xb : xc);
               if (xx < 0 || (iy == 0 && ix == 0)) continue;
-              *reinterpret_cast<uint4*>(ys + (yy * wp + xx) * ych) = w;
+              *reinterpret_cast<uint4*>(ys + (yy * wp + xx) * ych) = wv;
             }
           }
         }
       }
     }
     PIPE_CONSUME_END(pipe, s, ph);
+    x0 += seg_px;
+    if (x0 >= w) { x0 = 0; ++y; }
   }
 }
 
@@ -376,7 +405,7 @@ __device__ __forceinline__ void folded_load(const __nv_bfloat16* g, int y, int x
   const int wp = w + 2 * p;
   const int ya = y + p, xa = x + p;
   if (!have_center) unpack8(ldg16(g + (ya * wp + xa) * c), acc);
-  if (!reflect) return;
+  if (!reflect || !(mirrored(y, h, p) || mirrored(x, w, p))) return;   // interior pixel: nothing mirrors onto it (the common case)
   const int yb = (y >= 1 && y <= p) ? p - y : -1;
   const int yc = (y <= h - 2 && y >= h - 1 - p) ? p + 2 * (h - 1) - y : -1;
   const int xb = (x >= 1 && x <= p) ? p - x : -1;
@@ -873,8 +902,13 @@ static int norm_kernels_ready() {
   static int rc = PCGAN_OK;
   std::call_once(once, []() {
     int r;
-    if ((r = set_smem(norm_apply_kernel<false>, pipe_smem<1>(), "norm_apply<0>"))) { rc = r; return; }
-    if ((r = set_smem(norm_apply_kernel<true>, pipe_smem<2>(), "norm_apply<1>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<false, -1>, pipe_smem<1>(), "norm_apply<0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<false, PCGAN_ACT_NONE>, pipe_smem<1>(), "norm_apply<0,none>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<false, PCGAN_ACT_RELU>, pipe_smem<1>(), "norm_apply<0,relu>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<false, PCGAN_ACT_LRELU>, pipe_smem<1>(), "norm_apply<0,lrelu>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<true, -1>, pipe_smem<2>(), "norm_apply<1>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<true, PCGAN_ACT_NONE>, pipe_smem<2>(), "norm_apply<1,none>"))) { rc = r; return; }
+    if ((r = set_smem(norm_apply_kernel<true, PCGAN_ACT_RELU>, pipe_smem<2>(), "norm_apply<1,relu>"))) { rc = r; return; }
     if ((r = set_smem(norm_bwd_reduce_kernel<false, false>, pipe_smem<2>(), "norm_bwd_reduce<0,0>"))) { rc = r; return; }
     if ((r = set_smem(norm_bwd_reduce_kernel<true, false>, pipe_smem<2>(), "norm_bwd_reduce<1,0>"))) { rc = r; return; }
     if ((r = set_smem(norm_bwd_reduce_kernel<true, true>, pipe_smem<3>(), "norm_bwd_reduce<1,1>"))) { rc = r; return; }
@@ -911,6 +945,7 @@ extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s
   if (a->stats && a->count <= 0.f) return fail(PCGAN_ERR_INVALID, "norm_apply: fused finalize needs count > 0");
   int lcv, rc = check_c(a->c, "norm_apply", &lcv);
   if (rc) return rc;
+  if (a->c / 8 > kApplyConsumers) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: channels=%d (<= %d)", a->c, 8 * kApplyConsumers);
   if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(PCGAN_ERR_INVALID, "norm_apply: scale and shift go together");
   if (a->y_halo == PCGAN_HALO_REFLECT && (2 * a->y_pad + 1 > a->h || 2 * a->y_pad + 1 > a->w)) return fail(PCGAN_ERR_INVALID, "norm_apply: image smaller than 2*pad+1 under reflect halo");
   if (a->n < 1 || a->n > 65535) return fail(PCGAN_ERR_UNSUPPORTED, "norm_apply: n=%d (1..65535)", a->n);
@@ -923,8 +958,19 @@ extern "C" int pcgan_norm_apply(const pcgan_norm_apply_args* a, pcgan_stream_t s
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, a->res ? 3 : 6, &per);
   const dim3 grid(chunks, a->n);
-  if (a->res) PCGAN_CUDA_OK(launch_pdl(norm_apply_kernel<true>, grid, dim3(kStreamThreads), pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
-  else PCGAN_CUDA_OK(launch_pdl(norm_apply_kernel<false>, grid, dim3(kStreamThreads), pipe_smem<1>(), STREAM(s), 1, *a, sg, per, lcv));
+  const dim3 blk(kApplyThreads);
+#define PCGAN_APPLY(RES, ACT, NT) PCGAN_CUDA_OK(launch_pdl(norm_apply_kernel<RES, ACT>, grid, blk, pipe_smem<NT>(), STREAM(s), 1, *a, sg, per, lcv))
+  if (a->res) {
+    if (a->act == PCGAN_ACT_NONE) PCGAN_APPLY(true, PCGAN_ACT_NONE, 2);
+    else if (a->act == PCGAN_ACT_RELU) PCGAN_APPLY(true, PCGAN_ACT_RELU, 2);
+    else PCGAN_APPLY(true, -1, 2);
+  } else {
+    if (a->act == PCGAN_ACT_NONE) PCGAN_APPLY(false, PCGAN_ACT_NONE, 1);
+    else if (a->act == PCGAN_ACT_RELU) PCGAN_APPLY(false, PCGAN_ACT_RELU, 1);
+    else if (a->act == PCGAN_ACT_LRELU) PCGAN_APPLY(false, PCGAN_ACT_LRELU, 1);
+    else PCGAN_APPLY(false, -1, 1);
+  }
+#undef PCGAN_APPLY
   PCGAN_LAUNCH_OK("norm_apply_kernel");
   return PCGAN_OK;
 }
