@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCGAN_ABI_VERSION 19
+#define PCGAN_ABI_VERSION 20
 #define PCGAN_MAX_TAPS 64
 
 typedef void* pcgan_stream_t; /* a cudaStream_t */
@@ -318,6 +318,11 @@ typedef struct {
   int32_t n, h, w, c;
 } pcgan_fold_args;
 int pcgan_halo_fold(const pcgan_fold_args* a, pcgan_stream_t stream);
+/* The same reflect fold IN PLACE on the padded gradient gpad: the interior pixels within g_pad of a border receive
+ * the halo values that ReflectionPad2d copied from them (add / out are ignored; the halo itself is left as it is).
+ * Afterwards the interior of gpad is the folded gradient: consumers read it with a dropped halo (norm backward
+ * dy_fold = 1, pcgan_halo_fold with PCGAN_HALO_ZERO).  Touches 2*g_pad rows and columns only. */
+int pcgan_halo_accumulate(const pcgan_fold_args* a, pcgan_stream_t stream);
 
 /* Backward of y = act(scale*x + shift (+res...)): with g = dy * act'(y),
  * pass 1 accumulates sums[g][c][2] = (sum g, sum g*xhat); pass 2 writes

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PCGAN_KERNELS_LIB: another build of the same library (A/B measurements of a kernel change: tools/norm_bench.py)
 LIB_PATH = os.environ.get("PCGAN_KERNELS_LIB") or os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
@@ -152,6 +152,7 @@ SYMBOLS = {
     "pcgan_norm_apply": (C.c_int, [C.POINTER(NormApplyArgs), vp]),
     "pcgan_norm_running_batched": (C.c_int, [vp, i32, i32, vp]),
     "pcgan_halo_fold": (C.c_int, [C.POINTER(FoldArgs), vp]),
+    "pcgan_halo_accumulate": (C.c_int, [C.POINTER(FoldArgs), vp]),
     "pcgan_norm_bwd_reduce": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
     "pcgan_norm_bwd_apply": (C.c_int, [C.POINTER(NormBwdArgs), vp]),
     "pcgan_norm_bwd_fused_supported": (C.c_int, [C.POINTER(NormBwdArgs)]),

@@ -10,6 +10,7 @@ which_model_* raise NotImplementedError.  There is no CPU path: modules must liv
 CUDA device (gpu_ids non-empty), otherwise forward raises.
 """
 import functools
+import os
 
 import numpy as np
 import torch
@@ -51,6 +52,20 @@ def _norm_backward(gy, gy_pad, rbuf, rg: Geom, ns: NormState, act, slope, count,
     if not ns.pooled:
         ns.sums.zero_()
     ops.norm_bwd(gy, gy_pad, rbuf, rg, dx=dx, dx_pad=dx_pad, dres=dres, dres_pad=dres_pad, **kw)
+
+
+# PCGAN_FOLD_PREPASS=0: fold reflect-padded gradients on the fly inside the streaming consumers (the round-1 scheme)
+FOLD_PREPASS = os.environ.get("PCGAN_FOLD_PREPASS", "1") != "0"
+
+
+def _fold_in_place(gfull, gpad: Geom):
+    """The gradient of a reflect-padded buffer (geometry gpad) straight out of a data-gradient kernel: add the mirrored halo
+    values onto the interior border pixels with one small launch (ops.halo_accumulate) and tell the consumer to drop the
+    halo (dy_fold = 1) — or, without the pre-pass, to fold while it streams (dy_fold = 2)."""
+    if not FOLD_PREPASS or 2 * gpad.pad + 2 > min(gpad.h, gpad.w):
+        return 2
+    ops.halo_accumulate(gfull, gpad)
+    return 1
 
 
 class _Scratch:
@@ -217,7 +232,7 @@ class _GenProgram:
         self.head.backward_data(dyh, dfull)
         # up2 unit; the reflect-pad fold of the head's data gradient happens while it is read
         dy = sc.get(self.g_a1, "dy")
-        _norm_backward(dfull, 3, ws.u2r, self.g_u2r, ws.nu2, R, 0.0, S * S, dy, 1, dy_fold=2)
+        _norm_backward(dfull, 3, ws.u2r, self.g_u2r, ws.nu2, R, 0.0, S * S, dy, 1, dy_fold=_fold_in_place(dfull, self.g_u2))
         if need_w:
             self.up2.backward_weight(dy, ws.u1)
         g = sc.get(self.g_u1r, "g_u1")
@@ -242,13 +257,14 @@ class _GenProgram:
             dfull = sc.get(self.g_bfull, "dfull" + t)
             cb.backward_data(dyb, dfull)
             dya = sc.get(self.g_b, "dya" + t)
-            _norm_backward(dfull, 1, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1, dy_fold=2)
+            _norm_backward(dfull, 1, ws.ra[i], self.g_r3, ws.na[i], R, 0.0, h4 * h4, dya, 1, dy_fold=_fold_in_place(dfull, self.g_b))
             if need_w:
                 ca.backward_weight(dya, ws.b[i])
             dfull2 = sc.get(self.g_bfull, "dfull2" + t)
             ca.backward_data(dya, dfull2)
             gprev = sc.get(self.g_r3, ("gbk%d" % i) if self.keep_scratch else "gb%d" % ((nblk - i) % 2))
-            ops.halo_fold(dfull2, self.g_b, gprev, 0, halo=L.HALO_REFLECT, add=gb, add_pad=0)
+            folded = _fold_in_place(dfull2, self.g_b) == 1
+            ops.halo_fold(dfull2, self.g_b, gprev, 0, halo=L.HALO_ZERO if folded else L.HALO_REFLECT, add=gb, add_pad=0)
             gb = gprev
         # down2 unit (its output buffer ws.b[0])
         dy = sc.get(self.g_r3, "dy3")

@@ -224,6 +224,17 @@ def halo_fold(gpad, gg: Geom, out, out_pad, *, halo=L.HALO_REFLECT, add=None, ad
         L.check(L.load().pcgan_halo_fold(C.byref(a), _stream()), "halo_fold")
 
 
+def halo_accumulate(gpad, gg: Geom):
+    """Reflect fold in place: afterwards the interior of the padded gradient `gpad` is the gradient of the un-padded tensor
+    (consumers drop the halo: norm backward dy_fold=1, halo_fold(halo=HALO_ZERO))."""
+    a = L.FoldArgs(gpad=_ptr(gpad), g_pad=gg.pad, halo=L.HALO_REFLECT, add=None, add_pad=0, out=None, out_pad=0,
+                   n=gg.n, h=gg.h, w=gg.w, c=gg.c)
+    _count()
+    band = 2 * gg.pad * (gg.w + gg.h - 2 * gg.pad)
+    with _Timed("halo_accumulate", 2 * gg.n * gg.c * band * 3):
+        L.check(L.load().pcgan_halo_accumulate(C.byref(a), _stream()), "halo_accumulate")
+
+
 def _bwd_args(dy, dy_pad, x, xg, *, res=None, res_pad=0, mean=None, rstd=None, scale=None, shift=None, groups=1,
               res_scale=None, res_shift=None, res_groups=1, drop_mask=None, act=L.ACT_NONE, act_slope=0.0, count=0.0,
               sums=None, dx=None, dx_pad=0, dres=None, dres_pad=0, dy_fold=0, affine=1, post_mask=None):

@@ -155,17 +155,31 @@ def test_generator_chain_teacher_forced(N, S, nb):
         F.pad(xi, (p,) * 4, mode="reflect").backward(gfull)
         return xi.grad.detach()
 
+    PRE = NW.FOLD_PREPASS    # the reflect fold has been applied in place: interior of the padded gradient = folded, halo = raw
+
+    def check_padded_grad(name, mine_full, ref_full, c, s, p):
+        """data gradient on the padded grid; returns the folded gradient the next stage receives"""
+        if not PRE:
+            log.check(name + ".dgrad", mine_full, ref_full)
+            return fold(mine_full, c, s, p)
+        halo = torch.ones_like(ref_full, dtype=torch.bool)
+        halo[:, :, p:p + s, p:p + s] = False
+        log.check(name + ".dgrad (halo)", mine_full[halo], ref_full[halo])
+        mine = mine_full[:, :, p:p + s, p:p + s].contiguous()
+        log.check(name + ".dgrad + fold", mine, fold(ref_full, c, s, p))
+        return mine
+
     # ---- head: conv7x7 over the reflect-padded buffer + tanh
     kh = "model.%d" % (b + 7)
     dyh = inner(sc.get(P.g_dyh), P.g_dyh)[:, :3]
     log.check("head.dtanh", dyh, dout * (1 - out * out))
     u2p = full(ws.u2, P.g_u2)
-    conv_stage(log, "head", u2p, Wt(kh + ".weight"), lambda x, w: F.conv2d(x, w), dyh, None,
-               full(sc.get(P.g_u2full), P.g_u2full), grad(kh + ".weight"))
+    ref_full = conv_stage(log, "head", u2p, Wt(kh + ".weight"), lambda x, w: F.conv2d(x, w), dyh, None, None, grad(kh + ".weight"))
     with torch.no_grad():
         log.check("head.fwd", out, torch.tanh(F.conv2d(u2p, bf(Wt(kh + ".weight").detach()), B(kh + ".bias"))), 1e-4)
     log.check("head.bias_grad", grad(kh + ".bias"), dyh.sum((0, 2, 3)), 1e-3)
-    g_u2 = fold(full(sc.get(P.g_u2full), P.g_u2full), 64, S, 3)   # the fold is fused into the up2 norm backward (dy_fold=2)
+    # the fold is a small in-place pre-pass (or, PCGAN_FOLD_PREPASS=0, fused into the up2 norm backward: dy_fold=2)
+    g_u2 = check_padded_grad("head", full(sc.get(P.g_u2full), P.g_u2full), ref_full, 64, S, 3)
     # ---- up2, up1: ConvTranspose2d + IN + ReLU
     norm_stage(log, "up2.norm", inner(ws.u2r, P.g_u2r), g_u2, inner(ws.u2, P.g_u2), inner(sc.get(P.g_a1, "dy"), P.g_a1), ws.nu2, kind="instance")
     k = "model.%d" % (b + 3)
@@ -187,15 +201,17 @@ def test_generator_chain_teacher_forced(N, S, nb):
         norm_stage(log, t + ".norm2+res", inner(ws.rb[i], P.g_r3), gb, inner(ws.b[i + 1], P.g_b), dyb, ws.nb[i], kind="instance",
                    act="none", res=xres)
         dfull = full(sc.get(P.g_bfull, "dfull%d" % i), P.g_bfull)
-        conv_stage(log, t + ".conv2", full(ws.h[i], P.g_b), Wt(p + ".5.weight"), lambda x, w: F.conv2d(x, w, B(p + ".5.bias")),
-                   dyb, inner(ws.rb[i], P.g_r3), dfull, grad(p + ".5.weight"))
+        ref_full = conv_stage(log, t + ".conv2", full(ws.h[i], P.g_b), Wt(p + ".5.weight"), lambda x, w: F.conv2d(x, w, B(p + ".5.bias")),
+                              dyb, inner(ws.rb[i], P.g_r3), None, grad(p + ".5.weight"))
+        g_ra = check_padded_grad(t + ".conv2", dfull, ref_full, 256, h4, 1)
         dya = inner(sc.get(P.g_b, "dya%d" % i), P.g_b)
-        norm_stage(log, t + ".norm1", inner(ws.ra[i], P.g_r3), fold(dfull, 256, h4, 1), inner(ws.h[i], P.g_b), dya, ws.na[i], kind="instance")
+        norm_stage(log, t + ".norm1", inner(ws.ra[i], P.g_r3), g_ra, inner(ws.h[i], P.g_b), dya, ws.na[i], kind="instance")
         dfull2 = full(sc.get(P.g_bfull, "dfull2%d" % i), P.g_bfull)
-        conv_stage(log, t + ".conv1", full(ws.b[i], P.g_b), Wt(p + ".1.weight"), lambda x, w: F.conv2d(x, w, B(p + ".1.bias")),
-                   dya, inner(ws.ra[i], P.g_r3), dfull2, grad(p + ".1.weight"))
+        ref_full = conv_stage(log, t + ".conv1", full(ws.b[i], P.g_b), Wt(p + ".1.weight"), lambda x, w: F.conv2d(x, w, B(p + ".1.bias")),
+                              dya, inner(ws.ra[i], P.g_r3), None, grad(p + ".1.weight"))
+        g_b = check_padded_grad(t + ".conv1", dfull2, ref_full, 256, h4, 1)
         gprev = inner(sc.get(P.g_r3, "gbk%d" % i), P.g_r3)
-        log.check(t + ".fold+skip", gprev, fold(dfull2, 256, h4, 1) + gb)
+        log.check(t + ".fold+skip", gprev, g_b + gb)
         gb = gprev
     # ---- down2, down1 (stride 2, zero padding), stem
     dy3 = inner(sc.get(P.g_r3, "dy3"), P.g_r3)

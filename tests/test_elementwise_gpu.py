@@ -109,6 +109,35 @@ def test_halo_fold_is_adjoint_of_padding(pad, halo):
     assert rel(from_buf(out, Geom(N, H, W, C, 0)), x.grad + add) < 4e-3
 
 
+@pytest.mark.parametrize("pad,H,W,C", [(1, 9, 8, 64), (3, 16, 12, 64), (1, 4, 4, 256), (3, 8, 8, 8), (2, 11, 7, 128)])
+def test_halo_accumulate_folds_in_place(pad, H, W, C):
+    """ops.halo_accumulate: after it the INTERIOR of the padded gradient is nn.ReflectionPad2d's backward (every interior
+    pixel within `pad` of a border has received its mirrored halo values, once) and the halo is untouched."""
+    torch.manual_seed(3)
+    N = 3
+    x = torch.zeros(N, C, H, W, device=DEV, requires_grad=True)
+    gp = bf(torch.randn(N, C, H + 2 * pad, W + 2 * pad, device=DEV))
+    F.pad(x, (pad,) * 4, mode="reflect").backward(gp)
+    gbuf = to_buf(gp, 0)
+    g = Geom(N, H, W, C, pad)
+    ops.halo_accumulate(gbuf, g)
+    got = gbuf[: N * (H + 2 * pad) * (W + 2 * pad) * C].view(N, H + 2 * pad, W + 2 * pad, C).permute(0, 3, 1, 2).float()
+    inner = got[:, :, pad:pad + H, pad:pad + W]
+    assert rel(inner, x.grad) < 4e-3
+    # pixels that nothing mirrors onto are bit-identical to the input, and so is the halo
+    same = torch.ones(H + 2 * pad, W + 2 * pad, dtype=torch.bool, device=DEV)
+    yy = torch.arange(H, device=DEV).view(-1, 1).expand(H, W)
+    xx = torch.arange(W, device=DEV).view(1, -1).expand(H, W)
+    mir = ((yy >= 1) & (yy <= pad)) | ((yy <= H - 2) & (yy >= H - 1 - pad)) | ((xx >= 1) & (xx <= pad)) | ((xx <= W - 2) & (xx >= W - 1 - pad))
+    same[pad:pad + H, pad:pad + W] = ~mir
+    assert torch.equal(got[:, :, same], gp[:, :, same])
+    # and the two-step form equals the one-step fold
+    add = bf(torch.randn(N, C, H, W, device=DEV))
+    out = torch.zeros(N * H * W * C + 512, dtype=torch.bfloat16, device=DEV)
+    ops.halo_fold(gbuf, g, out, 0, halo=L.HALO_ZERO, add=to_buf(add, 0), add_pad=0)
+    assert rel(from_buf(out, Geom(N, H, W, C, 0)), x.grad + add) < 6e-3
+
+
 def test_maxpool_forward_backward():
     torch.manual_seed(2)
     N, C, H, W = 2, 64, 14, 12
