@@ -150,6 +150,7 @@ static constexpr int kStreamThreads = kConsumers + 32;    // + producer warp
 // (instead of two) halve the per-segment bookkeeping and the per-block prologue, which is what bounds it at the
 // ResnetBlock shape (33 MB, L2 resident: 16.1 -> 13.2 us; profiles/README.md, round 2)
 static constexpr int kApplyConsumers = 128;
+static constexpr int kReduceConsumers = 128;              // norm_bwd_reduce: no stores, small state: as norm_apply
 static constexpr int kApplyThreads = kApplyConsumers + 32;
 static constexpr int kStages = 4;
 static constexpr int kSegBytes = 8192;
@@ -597,19 +598,19 @@ __device__ __forceinline__ void bwd_sources(const pcgan_norm_bwd_args& a, int n,
   }
 }
 
-template <bool GEN, bool RES>
-__global__ void __launch_bounds__(kStreamThreads) norm_bwd_reduce_kernel(pcgan_norm_bwd_args a, SegGeom sg, int segs_per_block, int lcv) {
+template <bool GEN, bool RES, int NC>
+__global__ void __launch_bounds__(NC + 32) norm_bwd_reduce_kernel(pcgan_norm_bwd_args a, SegGeom sg, int segs_per_block, int lcv) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int NT = RES ? 3 : 2;
-  Pipe<NT> pipe = pipe_init<NT>(smem_raw);
+  Pipe<NT> pipe = pipe_init<NT>(smem_raw, NC);
   const int n = blockIdx.y;
   const int32_t total_segs = a.h * sg.segs_per_row;
   const int32_t g0 = blockIdx.x * segs_per_block, g1 = min(g0 + segs_per_block, total_segs);
   const int cv = a.c >> 3;
   StreamSrc src[NT];
   bwd_sources<RES>(a, n, src);
-  if (threadIdx.x >= kConsumers) {
-    if (threadIdx.x == kConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
+  if (threadIdx.x >= NC) {
+    if (threadIdx.x == NC) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
   } else {
     const int c0 = (threadIdx.x & (cv - 1)) << 3;
     BwdCtx<GEN, RES> k;
@@ -617,31 +618,37 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_reduce_kernel(pcgan_n
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    const int px0 = threadIdx.x >> lcv, dpx = NC >> lcv;
+    const int seg_vec = sg.seg_vec, seg_px = sg.seg_px, w = a.w;
+    int32_t y = g0 / sg.segs_per_row;
+    int32_t x0 = (g0 - y * sg.segs_per_row) * seg_px;
     int s = 0;
     uint32_t ph = 0;
     for (int32_t g = g0; g < g1; ++g) {
-      const int32_t y = g / sg.segs_per_row;
-      const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
       PIPE_CONSUME_BEGIN(pipe, s, ph);
       const uint4* sd = pipe.stage(s, 0);
       const uint4* sx = pipe.stage(s, 1);
       const uint4* sr = RES ? pipe.stage(s, 2) : sx;
-      for (int v = threadIdx.x; v < sg.seg_vec; v += kConsumers) {
+      int px = px0;
+#pragma unroll 2
+      for (int v = threadIdx.x; v < seg_vec; v += NC, px += dpx) {
         float gv[8], xh[8];
-        k.grad(a, y, x0 + (v >> lcv), sd[v], sx[v], sr[v], gv, xh);
+        k.grad(a, y, x0 + px, sd[v], sx[v], sr[v], gv, xh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s1[j] += gv[j]; s2[j] = fmaf(gv[j], xh[j], s2[j]); }
       }
       PIPE_CONSUME_END(pipe, s, ph);
+      x0 += seg_px;
+      if (x0 >= w) { x0 = 0; ++y; }
     }
-    // all segments consumed: the ring is free, reuse its first 16 KB for the block reduction
-    named_bar_sync(1, kConsumers);
+    // all segments consumed: the ring is free, reuse its first NC * 64 bytes for the block reduction
+    named_bar_sync(1, NC);
     float* red = reinterpret_cast<float*>(smem_raw);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
-    named_bar_sync(1, kConsumers);
-    const int lanes = kConsumers / cv;
-    for (int t = threadIdx.x; t < cv * 16; t += kConsumers) {
+    named_bar_sync(1, NC);
+    const int lanes = NC / cv;
+    for (int t = threadIdx.x; t < cv * 16; t += NC) {
       const int c = t >> 4, slot = t & 15;
       float sum = 0.f;
       for (int l = 0; l < lanes; ++l) sum += red[(l * cv + c) * 16 + slot];
@@ -652,11 +659,11 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_reduce_kernel(pcgan_n
   }
 }
 
-template <bool GEN, bool RES>
-__global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_norm_bwd_args a, SegGeom sg, int segs_per_block, int lcv) {
+template <bool GEN, bool RES, int NC>
+__global__ void __launch_bounds__(NC + 32) norm_bwd_apply_kernel(pcgan_norm_bwd_args a, SegGeom sg, int segs_per_block, int lcv) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int NT = RES ? 3 : 2;
-  Pipe<NT> pipe = pipe_init<NT>(smem_raw);
+  Pipe<NT> pipe = pipe_init<NT>(smem_raw, NC);
   // blocks walk the samples (and chunks) in the opposite order to the reduce pass: what that pass read last is
   // still in L2 when this one starts
   const int n = gridDim.y - 1 - blockIdx.y;
@@ -666,8 +673,8 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_no
   const int cv = a.c >> 3;
   StreamSrc src[NT];
   bwd_sources<RES>(a, n, src);
-  if (threadIdx.x >= kConsumers) {
-    if (threadIdx.x == kConsumers) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
+  if (threadIdx.x >= NC) {
+    if (threadIdx.x == NC) pipe_produce<NT>(pipe, sg, src, a.c, g0, g1);
     return;
   }
   const int c0 = (threadIdx.x & (cv - 1)) << 3;
@@ -689,24 +696,30 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_no
     }
   }
   const bool scaled = a.scale != nullptr;
-  const int wop = a.w + 2 * a.dx_pad, wsp = a.w + 2 * a.dres_pad;
-  __nv_bfloat16* dx = a.dx ? reinterpret_cast<__nv_bfloat16*>(a.dx) + static_cast<int64_t>(n) * (a.h + 2 * a.dx_pad) * wop * a.c + c0 : nullptr;
-  __nv_bfloat16* dres = a.dres ? reinterpret_cast<__nv_bfloat16*>(a.dres) + static_cast<int64_t>(n) * (a.h + 2 * a.dres_pad) * wsp * a.c + c0 : nullptr;
+  const int wop = a.w + 2 * a.dx_pad, wsp = a.w + 2 * a.dres_pad, c = a.c, w = a.w;
+  __nv_bfloat16* dx = a.dx ? reinterpret_cast<__nv_bfloat16*>(a.dx) + static_cast<int64_t>(n) * (a.h + 2 * a.dx_pad) * wop * c + c0 : nullptr;
+  __nv_bfloat16* dres = a.dres ? reinterpret_cast<__nv_bfloat16*>(a.dres) + static_cast<int64_t>(n) * (a.h + 2 * a.dres_pad) * wsp * c + c0 : nullptr;
+  const int px0 = threadIdx.x >> lcv, dpx = NC >> lcv;
+  const int seg_vec = sg.seg_vec, seg_px = sg.seg_px;
+  int32_t y = g0 / sg.segs_per_row;
+  int32_t x0 = (g0 - y * sg.segs_per_row) * seg_px;
   int s = 0;
   uint32_t ph = 0;
   for (int32_t g = g0; g < g1; ++g) {
-    const int32_t y = g / sg.segs_per_row;
-    const int32_t x0 = (g - y * sg.segs_per_row) * sg.seg_px;
+    // element offsets fit 31 bits (checked on the host)
+    __nv_bfloat16* dxrow = dx ? dx + ((y + a.dx_pad) * wop + x0 + a.dx_pad) * c : nullptr;
+    __nv_bfloat16* drrow = dres ? dres + ((y + a.dres_pad) * wsp + x0 + a.dres_pad) * c : nullptr;
     PIPE_CONSUME_BEGIN(pipe, s, ph);
     const uint4* sd = pipe.stage(s, 0);
     const uint4* sx = pipe.stage(s, 1);
     const uint4* sr = RES ? pipe.stage(s, 2) : sx;
-    for (int v = threadIdx.x; v < sg.seg_vec; v += kConsumers) {
+    int px = px0;
+#pragma unroll 2
+    for (int v = threadIdx.x; v < seg_vec; v += NC, px += dpx) {
       float gv[8], xh[8];
-      const int x = x0 + (v >> lcv);
-      k.grad(a, y, x, sd[v], sx[v], sr[v], gv, xh);
-      if (dres) store8(dres + ((y + a.dres_pad) * wsp + x + a.dres_pad) * a.c, gv);
-      if (dx) {
+      k.grad(a, y, x0 + px, sd[v], sx[v], sr[v], gv, xh);
+      if (drrow) store8(drrow + px * c, gv);
+      if (dxrow) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -715,10 +728,12 @@ __global__ void __launch_bounds__(kStreamThreads) norm_bwd_apply_kernel(pcgan_no
           if constexpr (GEN) t *= k.mk[j];
           o[j] = t;
         }
-        store8(dx + ((y + a.dx_pad) * wop + x + a.dx_pad) * a.c, o);
+        store8(dxrow + px * c, o);
       }
     }
     PIPE_CONSUME_END(pipe, s, ph);
+    x0 += seg_px;
+    if (x0 >= w) { x0 = 0; ++y; }
   }
 }
 
@@ -942,12 +957,12 @@ static int norm_kernels_ready() {
     if ((r = set_smem(norm_apply_kernel<true, -1>, pipe_smem<2>(), "norm_apply<1>"))) { rc = r; return; }
     if ((r = set_smem(norm_apply_kernel<true, PCGAN_ACT_NONE>, pipe_smem<2>(), "norm_apply<1,none>"))) { rc = r; return; }
     if ((r = set_smem(norm_apply_kernel<true, PCGAN_ACT_RELU>, pipe_smem<2>(), "norm_apply<1,relu>"))) { rc = r; return; }
-    if ((r = set_smem(norm_bwd_reduce_kernel<false, false>, pipe_smem<2>(), "norm_bwd_reduce<0,0>"))) { rc = r; return; }
-    if ((r = set_smem(norm_bwd_reduce_kernel<true, false>, pipe_smem<2>(), "norm_bwd_reduce<1,0>"))) { rc = r; return; }
-    if ((r = set_smem(norm_bwd_reduce_kernel<true, true>, pipe_smem<3>(), "norm_bwd_reduce<1,1>"))) { rc = r; return; }
-    if ((r = set_smem(norm_bwd_apply_kernel<false, false>, pipe_smem<2>(), "norm_bwd_apply<0,0>"))) { rc = r; return; }
-    if ((r = set_smem(norm_bwd_apply_kernel<true, false>, pipe_smem<2>(), "norm_bwd_apply<1,0>"))) { rc = r; return; }
-    if ((r = set_smem(norm_bwd_apply_kernel<true, true>, pipe_smem<3>(), "norm_bwd_apply<1,1>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_reduce_kernel<false, false, kReduceConsumers>, pipe_smem<2>(), "norm_bwd_reduce<0,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_reduce_kernel<true, false, kReduceConsumers>, pipe_smem<2>(), "norm_bwd_reduce<1,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_reduce_kernel<true, true, kReduceConsumers>, pipe_smem<3>(), "norm_bwd_reduce<1,1>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_apply_kernel<false, false, kConsumers>, pipe_smem<2>(), "norm_bwd_apply<0,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_apply_kernel<true, false, kConsumers>, pipe_smem<2>(), "norm_bwd_apply<1,0>"))) { rc = r; return; }
+    if ((r = set_smem(norm_bwd_apply_kernel<true, true, kConsumers>, pipe_smem<3>(), "norm_bwd_apply<1,1>"))) { rc = r; return; }
   });
   return rc;
 }
@@ -1064,10 +1079,11 @@ extern "C" int pcgan_norm_bwd_reduce(const pcgan_norm_bwd_args* a, pcgan_stream_
   int per;
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, gen ? 2 : 3, &per);
   const dim3 grid(chunks, a->n);
-  const dim3 blk(kStreamThreads);
-  if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<false, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
-  else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<true, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
-  else PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<true, true>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
+  const dim3 blk(kReduceConsumers + 32);
+  if (a->c / 8 > kReduceConsumers) return fail(PCGAN_ERR_UNSUPPORTED, "norm_bwd_reduce: channels=%d (<= %d)", a->c, 8 * kReduceConsumers);
+  if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<false, false, kReduceConsumers>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<true, false, kReduceConsumers>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else PCGAN_CUDA_OK(launch_pdl(norm_bwd_reduce_kernel<true, true, kReduceConsumers>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
   PCGAN_LAUNCH_OK("norm_bwd_reduce_kernel");
   return PCGAN_OK;
 }
@@ -1083,9 +1099,9 @@ extern "C" int pcgan_norm_bwd_apply(const pcgan_norm_bwd_args* a, pcgan_stream_t
   const int chunks = seg_chunking(a->h * sg.segs_per_row, a->n, 2, &per);
   const dim3 grid(chunks, a->n);
   const dim3 blk(kStreamThreads);
-  if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<false, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
-  else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, false>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
-  else PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, true>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
+  if (!gen) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<false, false, kConsumers>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else if (!res) PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, false, kConsumers>, grid, blk, pipe_smem<2>(), STREAM(s), 1, *a, sg, per, lcv));
+  else PCGAN_CUDA_OK(launch_pdl(norm_bwd_apply_kernel<true, true, kConsumers>, grid, blk, pipe_smem<3>(), STREAM(s), 1, *a, sg, per, lcv));
   PCGAN_LAUNCH_OK("norm_bwd_apply_kernel");
   return PCGAN_OK;
 }
