@@ -133,3 +133,52 @@ class GpuPairLoader:
             nxt = self._stage(batches[i + 1]) if i + 1 < len(batches) else None      # one batch ahead of the step
             torch.cuda.current_stream(self.device).wait_event(ev)
             yield cur
+
+
+class DevicePrefetcher:
+    """Batches that are already tensors on the host (a torch DataLoader with pin_memory=True, as data/__init__.py:64-70 of
+    the reference builds): the host -> device copy of batch i + 1 is issued on a side stream while step i runs, so the copy
+    is off the critical path of the step that consumes it.
+
+        for batch in DevicePrefetcher(loader, device):        # dict of device tensors (non-tensor values pass through)
+            model.set_input(batch); model.optimize_parameters()
+
+    Pinned source tensors copy asynchronously; pageable ones still work, the copy is then synchronous (as in torch)."""
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self._next = self._ready = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            b = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        if not self.cuda:
+            self._next = b
+            return
+        with torch.cuda.stream(self.stream):
+            self._next = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
+            self._ready = torch.cuda.Event()
+            self._ready.record(self.stream)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        batch = self._next
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._ready)
+            for v in batch.values():
+                if torch.is_tensor(v):
+                    v.record_stream(cur)       # allocated on the side stream, consumed on the caller's
+        self._preload()
+        return batch

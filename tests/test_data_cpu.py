@@ -27,3 +27,15 @@ def test_rank_shards_partition_every_global_batch():
     assert all(len(b) == B for s in shards for b in s[:-1])
     assert rank_indices(n, B, 0, W, drop_last=True)[-1][-1] < (n // (B * W)) * B * W
     assert rank_indices(16, 8, 1, 2) == [[8, 9, 10, 11, 12, 13, 14, 15]]
+
+
+def test_device_prefetcher_passes_batches_through_in_order():
+    """DevicePrefetcher on the CPU device degenerates to the plain iterator (same objects, same order, StopIteration)."""
+    import torch
+    from pcgan_b200.data import DevicePrefetcher
+    batches = [{"A": torch.full((2, 3), float(i)), "label": torch.tensor([i]), "paths": ["p%d" % i]} for i in range(4)]
+    got = list(DevicePrefetcher(batches, "cpu"))
+    assert len(got) == 4
+    for i, b in enumerate(got):
+        assert float(b["A"][0, 0]) == i and int(b["label"]) == i and b["paths"] == ["p%d" % i]
+    assert list(DevicePrefetcher([], "cpu")) == []

@@ -65,3 +65,22 @@ def test_loader_shards_and_prefetches(tmp_path):
             assert float(batch["A"].abs().max()) <= 1.0 and batch["label"].dtype == torch.int64
             seen += batch["A_paths"]
     assert sorted(seen) == sorted(str(tmp_path / ("a%d.png" % i)) for i in range(12))      # the two ranks cover every pair exactly once
+
+
+def test_device_prefetcher_copies_ahead_on_a_side_stream():
+    """Every batch arrives on the device bit-identical and in order while the consumer keeps the GPU busy; non-tensor
+    entries pass through."""
+    from pcgan_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(5)
+    host = [{"A": torch.rand(8, 3, 64, 64, generator=g).pin_memory(), "label": torch.randint(0, 3, (8,), generator=g).pin_memory(),
+             "B_paths": ["x%d" % i]} for i in range(6)]
+    busy = torch.randn(2048, 2048, device="cuda")
+    seen = []
+    for i, b in enumerate(DevicePrefetcher(iter(host), "cuda")):
+        assert b["A"].is_cuda and b["label"].is_cuda and b["B_paths"] == ["x%d" % i]
+        busy = busy @ busy * 1e-3                     # work on the current stream that overlaps the next copy
+        seen.append((b["A"].clone(), b["label"].clone()))
+    torch.cuda.synchronize()
+    assert len(seen) == 6
+    for (a, l), h in zip(seen, host):
+        assert torch.equal(a.cpu(), h["A"]) and torch.equal(l.cpu(), h["label"])
