@@ -143,14 +143,22 @@ class DevicePrefetcher:
         for batch in DevicePrefetcher(loader, device):        # dict of device tensors (non-tensor values pass through)
             model.set_input(batch); model.optimize_parameters()
 
-    Pinned source tensors copy asynchronously; pageable ones still work, the copy is then synchronous (as in torch)."""
+    The device tensors live in three rotating sets of persistent buffers (no allocation per step): a yielded batch stays
+    valid until two more batches have been requested.  Pinned source tensors copy asynchronously; pageable ones still
+    work, the copy is then synchronous (as in torch)."""
+
+    SLOTS = 3
 
     def __init__(self, batches, device):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
         self.stream = torch.cuda.Stream(self.device) if self.cuda else None
-        self._next = self._ready = None
+        self._bufs = [dict() for _ in range(self.SLOTS)]
+        self._ready = [None] * self.SLOTS
+        self._used = [None] * self.SLOTS          # event: the consumer's stream is done with the slot
+        self._i = 0
+        self._next = None
         self._preload()
 
     def _preload(self):
@@ -160,12 +168,27 @@ class DevicePrefetcher:
             self._next = None
             return
         if not self.cuda:
-            self._next = b
+            self._next = (b, -1)
             return
+        slot = self._i % self.SLOTS
+        self._i += 1
         with torch.cuda.stream(self.stream):
-            self._next = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
-            self._ready = torch.cuda.Event()
-            self._ready.record(self.stream)
+            if self._used[slot] is not None:
+                self.stream.wait_event(self._used[slot])
+            out = {}
+            for k, v in b.items():
+                if torch.is_tensor(v):
+                    buf = self._bufs[slot].get(k)
+                    if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                        buf = self._bufs[slot][k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    buf.copy_(v, non_blocking=True)
+                    out[k] = buf
+                else:
+                    out[k] = v
+            if self._ready[slot] is None:
+                self._ready[slot] = torch.cuda.Event()
+            self._ready[slot].record(self.stream)
+        self._next = (out, slot)
 
     def __iter__(self):
         return self
@@ -173,12 +196,14 @@ class DevicePrefetcher:
     def __next__(self):
         if self._next is None:
             raise StopIteration
-        batch = self._next
+        batch, slot = self._next
         if self.cuda:
             cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(self._ready)
-            for v in batch.values():
-                if torch.is_tensor(v):
-                    v.record_stream(cur)       # allocated on the side stream, consumed on the caller's
+            cur.wait_event(self._ready[slot])
+            # the slot that was handed out two batches ago is refilled next: the consumer's work queued so far covers it
+            nxt = self._i % self.SLOTS
+            if self._used[nxt] is None:
+                self._used[nxt] = torch.cuda.Event()
+            self._used[nxt].record(cur)
         self._preload()
         return batch

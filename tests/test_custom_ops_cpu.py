@@ -5,7 +5,7 @@ from torch._subclasses.fake_tensor import FakeTensorMode
 
 from pcgan_b200 import networks as NW
 
-OPS = ["resnet_generator", "resnet_generator_backward", "nlayer_discriminator", "nlayer_discriminator_backward", "siamese_feature",
+OPS = ["resnet_generator", "resnet_generator_backward", "unet_generator", "alexnet_feature", "alexnet_feature_backward", "nlayer_discriminator", "nlayer_discriminator_backward", "siamese_feature",
        "siamese_feature_backward", "reduce_loss", "reduce_loss_backward", "upsample_bilinear_ac", "upsample_bilinear_ac_backward"]
 
 

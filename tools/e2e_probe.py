@@ -32,6 +32,15 @@ def direct():
         run.losses()
 
 
+resident = [{"A": h["A"].to(dev), "B": h["B"].to(dev), "label": h["label"]} for h in host]
+
+
+def resident_sync():
+    for i in range(K):
+        run.step(resident[i % 4])
+        run.losses()
+
+
 def direct_nosync():
     for i in range(K):
         run.step(host[i % 4])
@@ -72,7 +81,8 @@ def manual_after():
         run.losses()
 
 
-for rep in range(2):
+for rep in range(3):
+    timed("device-resident inputs", resident_sync)
     timed("direct (H2D on the step's stream)", direct)
     timed("direct, no per-step loss read", direct_nosync)
     timed("DevicePrefetcher", pref)
