@@ -68,6 +68,12 @@ def _fold_in_place(gfull, gpad: Geom):
     return 1
 
 
+def _add_interior(x, xg: Geom, add, add_pad, out):
+    """out (un-padded) = interior(x) + add as one streamed pass: norm_apply with identity scale and `add` as the residual
+    (faster than the gather-style halo_fold with a dropped halo: tools/norm_bench.py)."""
+    ops.norm_apply(x, xg, out, Geom(xg.n, xg.h, xg.w, xg.c, 0), scale=None, shift=None, groups=1, res=add, res_pad=add_pad, act=L.ACT_NONE)
+
+
 class _Scratch:
     """Backward-only buffers of a program, created on first use and reused by every call (one backward at a time)."""
 
@@ -263,8 +269,11 @@ class _GenProgram:
             dfull2 = sc.get(self.g_bfull, "dfull2" + t)
             ca.backward_data(dya, dfull2)
             gprev = sc.get(self.g_r3, ("gbk%d" % i) if self.keep_scratch else "gb%d" % ((nblk - i) % 2))
-            folded = _fold_in_place(dfull2, self.g_b) == 1
-            ops.halo_fold(dfull2, self.g_b, gprev, 0, halo=L.HALO_ZERO if folded else L.HALO_REFLECT, add=gb, add_pad=0)
+            if _fold_in_place(dfull2, self.g_b) != 1:
+                ops.halo_fold(dfull2, self.g_b, gprev, 0, halo=L.HALO_REFLECT, add=gb, add_pad=0)
+            else:
+                # 18.8 us at the block shape against 27 us for halo_fold with a dropped halo: 20.76 -> 20.57 ms per step
+                _add_interior(dfull2, self.g_b, gb, 0, gprev)
             gb = gprev
         # down2 unit (its output buffer ws.b[0])
         dy = sc.get(self.g_r3, "dy3")
@@ -546,7 +555,7 @@ class _UnetProgram:
             tmp = sc.get(self.g_r[k], "tmp%d" % k)
             ops.act_bwd(skip[k], 0, ws.A[k], 1, tmp, 0, self.g_r[k], 0.0)
             eff = sc.get(self.g_r[k], "eff%d" % k)
-            ops.halo_fold(tmp, self.g_r[k], eff, 0, halo=L.HALO_ZERO, add=dA, add_pad=0)
+            _add_interior(tmp, self.g_r[k], dA, 0, eff)
             dy = sc.get(self.g_r[k], "dy%d" % k)
             if k > 0:
                 _norm_backward(eff, 0, ws.r[k], self.g_r[k], ws.nd[k], L.ACT_LRELU, 0.2, sz[k] * sz[k], dy, 0)
@@ -1181,9 +1190,9 @@ class _EncBlock:
                 self.ds.backward_weight(dyd, xbuf)
             gx2 = sc.get(self.g_xr, self.name + "gx2")  # odd phases of a 1x1 stride-2 conv receive nothing: stay zero
             self.ds.backward_data(dyd, gx2)
-            ops.halo_fold(gx1, self.g_xr, gx, 0, halo=L.HALO_ZERO, add=gx2, add_pad=0)
+            _add_interior(gx1, self.g_xr, gx2, 0, gx)
         else:
-            ops.halo_fold(gx1, self.g_xr, gx, 0, halo=L.HALO_ZERO, add=gres, add_pad=0)
+            _add_interior(gx1, self.g_xr, gres, 0, gx)
         return gx
 
 
