@@ -185,7 +185,8 @@ class BaseModel:
         out = OrderedDict()
         for n in self.loss_names:
             if isinstance(n, str):
-                out[n] = float(getattr(self, "loss_" + n))
+                v = getattr(self, "loss_" + n)
+                out[n] = float(v.detach()) if torch.is_tensor(v) else float(v)
         return out
 
     def _unwrap(self, net):
