@@ -81,10 +81,8 @@ def manual_after():
         run.losses()
 
 
-for rep in range(3):
+K = int(os.environ.get("PROBE_K", 200))
+for rep in range(int(os.environ.get("PROBE_REPS", 5))):
     timed("device-resident inputs", resident_sync)
     timed("direct (H2D on the step's stream)", direct)
-    timed("direct, no per-step loss read", direct_nosync)
     timed("DevicePrefetcher", pref)
-    timed("DevicePrefetcher, label stays on host", pref_images_only)
-    timed("manual double buffer, issue after step", manual_after)
