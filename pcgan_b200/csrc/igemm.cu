@@ -47,6 +47,27 @@ static constexpr int kTailBytes = kTailTr + 8 * kWarpScratch;
 static_assert(kDataBytes + 1024 + kTailBytes <= 227 * 1024, "shared memory budget");
 static constexpr int kSmemBytes = kDataBytes + 1024 /*align*/ + kTailBytes;
 
+// Division by a divisor that is fixed per plan, for 0 <= x < 2^31: q = (umulhi(x, mul) + x) >> shift with
+// shift = ceil(log2 d), mul = floor(2^32 (2^shift - d) / d) + 1 (Granlund-Montgomery).  The per-tile coordinate arithmetic
+// of every role (digits of the tile index, components of the output coordinate) is on the critical path of tiles with
+// little work: a hardware integer division is ~20 dependent instructions, this is three.
+struct FastDiv {
+  uint32_t mul, shift;
+};
+static FastDiv make_fastdiv(int32_t d) {
+  FastDiv f{1u, 0u};
+  if (d <= 1) return f;
+  uint32_t sh = 0;
+  while ((1ull << sh) < static_cast<uint64_t>(d)) ++sh;
+  f.shift = sh;
+  f.mul = static_cast<uint32_t>((((1ull << sh) - static_cast<uint64_t>(d)) << 32) / static_cast<uint64_t>(d)) + 1u;
+  return f;
+}
+__device__ __forceinline__ int32_t fdiv(int32_t x, const FastDiv& f) {
+  const uint32_t u = static_cast<uint32_t>(x);
+  return static_cast<int32_t>((__umulhi(u, f.mul) + u) >> f.shift);
+}
+
 struct DevParams {
   int32_t kind, block_n, a_rows, a_ch;
   int32_t num_stages, stage_bytes, a_alloc;
@@ -64,6 +85,7 @@ struct DevParams {
   int32_t dual;        // 1: two independent producer -> MMA -> epilogue pipelines (even / odd tiles of the CTA), each with
                        //    num_stages stages of the ring and one TMEM accumulator
   int32_t t_count[4];
+  FastDiv fd_t[4], fd_nt, fd_p1[4], fd_p2[4], fd_sdiv;   // t_count, n_tiles, e_p1, e_p2, stats_div
   int32_t a_base[4], a_step[4][4];
   int32_t b_base[4], b_step[4][4];
   int32_t n_tiles, m_tiles, ksplit, num_m_tiles, total_tiles;
@@ -92,13 +114,13 @@ struct DevParams {
 struct Digits {
   int32_t t[4];
 };
-__device__ __forceinline__ Digits decompose(int32_t idx, const int32_t (&count)[4]) {
+__device__ __forceinline__ Digits decompose(int32_t idx, const int32_t (&count)[4], const FastDiv (&fd)[4]) {
   Digits d;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    int32_t c = count[j];
-    d.t[j] = idx % c;
-    idx /= c;
+    const int32_t q = fdiv(idx, fd[j]);
+    d.t[j] = idx - q * count[j];
+    idx = q;
   }
   return d;
 }
@@ -113,10 +135,16 @@ __device__ __forceinline__ int32_t tile_group(const DevParams& P, const Digits& 
   const int dim = P.stats_dim;
   const int32_t g0 = coord(d, P.e_base, P.e_step, dim);
   int32_t s0 = 0, srem = g0, s1;
-  if (P.e_p1[dim] > 0) { s0 = g0 / P.e_p1[dim]; srem = g0 % P.e_p1[dim]; }
-  if (P.e_p2[dim] > 0) { s1 = srem / P.e_p2[dim]; } else { s1 = srem; }
+  if (g0 < 0) {   // never for a plan with statistics; keeps the exact semantics if it ever happens
+    if (P.e_p1[dim] > 0) { s0 = g0 / P.e_p1[dim]; srem = g0 % P.e_p1[dim]; }
+    if (P.e_p2[dim] > 0) { s1 = srem / P.e_p2[dim]; } else { s1 = srem; }
+    const int32_t smp_ = P.stats_comp == 0 ? s0 : s1;
+    return P.stats_div > 1 ? smp_ / P.stats_div : smp_;
+  }
+  if (P.e_p1[dim] > 0) { s0 = fdiv(g0, P.fd_p1[dim]); srem = g0 - s0 * P.e_p1[dim]; }
+  if (P.e_p2[dim] > 0) { s1 = fdiv(srem, P.fd_p2[dim]); } else { s1 = srem; }
   const int32_t smp = P.stats_comp == 0 ? s0 : s1;
-  return P.stats_div > 1 ? smp / P.stats_div : smp;
+  return P.stats_div > 1 ? fdiv(smp, P.fd_sdiv) : smp;
 }
 
 // ------------------------------------------------------------------ schedule
@@ -137,7 +165,7 @@ __device__ __forceinline__ Sched make_sched(const DevParams& P) {
   return s;
 }
 __device__ __forceinline__ void kmajor_item(const DevParams& P, const Sched& sc, int32_t item, int32_t& mt, int32_t& nt, bool& valid) {
-  const int32_t q = item / P.n_tiles;
+  const int32_t q = fdiv(item, P.fd_nt);
   nt = item - q * P.n_tiles;
   mt = P.pair ? 2 * q + static_cast<int32_t>(sc.rank) : q;
   valid = mt < P.num_m_tiles;
@@ -275,15 +303,16 @@ __device__ __forceinline__ void epilogue_kmajor(const DevParams& P, const EpiSha
     int32_t mt, nt;
     bool tile_valid;
     kmajor_item(P, sch, tile, mt, nt, tile_valid);
-    const Digits d = decompose(mt, P.t_count);
+    const Digits d = decompose(mt, P.t_count, P.fd_t);
     bool valid = row_in_box && tile_valid;
     int64_t off = 0;
 #pragma unroll
     for (int dim = 0; dim < 4; ++dim) {
       const int32_t g = coord(d, P.e_base, P.e_step, dim) + il[dim];
       int32_t k0 = 0, rem = g, k1, k2 = 0;
-      if (P.e_p1[dim] > 0) { k0 = g / P.e_p1[dim]; rem = g - k0 * P.e_p1[dim]; }
-      if (P.e_p2[dim] > 0) { k1 = rem / P.e_p2[dim]; k2 = rem - k1 * P.e_p2[dim]; } else { k1 = rem; }
+      // g < 0 (a row outside the output) gives garbage components here; `valid` below is false for it
+      if (P.e_p1[dim] > 0) { k0 = fdiv(g, P.fd_p1[dim]); rem = g - k0 * P.e_p1[dim]; }
+      if (P.e_p2[dim] > 0) { k1 = fdiv(rem, P.fd_p2[dim]); k2 = rem - k1 * P.e_p2[dim]; } else { k1 = rem; }
       const pcgan_comp& m0 = P.e_comp[dim][0];
       const pcgan_comp& m1 = P.e_comp[dim][1];
       const pcgan_comp& m2 = P.e_comp[dim][2];
@@ -414,15 +443,16 @@ __device__ __forceinline__ void epilogue_shift(const DevParams& P, const EpiShar
     int32_t mt, nt;
     bool tile_valid;
     kmajor_item(P, sch, tile, mt, nt, tile_valid);
-    const Digits d = decompose(mt, P.t_count);
+    const Digits d = decompose(mt, P.t_count, P.fd_t);
     bool valid = row_out && tile_valid;
     int64_t off = 0;
 #pragma unroll
     for (int dim = 0; dim < 4; ++dim) {
       const int32_t g = coord(d, P.e_base, P.e_step, dim) + il[dim];
       int32_t k0 = 0, rem = g, k1, k2 = 0;
-      if (P.e_p1[dim] > 0) { k0 = g / P.e_p1[dim]; rem = g - k0 * P.e_p1[dim]; }
-      if (P.e_p2[dim] > 0) { k1 = rem / P.e_p2[dim]; k2 = rem - k1 * P.e_p2[dim]; } else { k1 = rem; }
+      // g < 0 (a row outside the output) gives garbage components here; `valid` below is false for it
+      if (P.e_p1[dim] > 0) { k0 = fdiv(g, P.fd_p1[dim]); rem = g - k0 * P.e_p1[dim]; }
+      if (P.e_p2[dim] > 0) { k1 = fdiv(rem, P.fd_p2[dim]); k2 = rem - k1 * P.e_p2[dim]; } else { k1 = rem; }
       const pcgan_comp& m0 = P.e_comp[dim][0];
       const pcgan_comp& m1 = P.e_comp[dim][1];
       const pcgan_comp& m2 = P.e_comp[dim][2];
@@ -657,7 +687,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int32_t mt, nt;
         bool tile_valid;
         kmajor_item(P, sch, tile, mt, nt, tile_valid);
-        const Digits d = decompose(mt, P.t_count);
+        const Digits d = decompose(mt, P.t_count, P.fd_t);
         int32_t c[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[q] = coord(d, P.a_base, P.a_step, q);
@@ -713,7 +743,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int32_t box0 = bdim ? nt * nb : 0;
         const int32_t e0 = bdim == 1, e1 = bdim == 2, e2 = bdim == 3, e3 = bdim == 4;
         // pixel blocks kb0 .. kb1-1 are consecutive: the mixed-radix digits are stepped, not re-divided, per block
-        Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count);
+        Digits d = decompose(kb0 < total_kb ? kb0 : 0, P.t_count, P.fd_t);
         // kc-channel boxes of this M tile (and of the peer's) that exist
         const int32_t a_boxes = min((P.a_ch - mt * 128 + kc - 1) / kc, amax);
         const int32_t peer_boxes = min((P.a_ch - (mt ^ 1) * 128 + kc - 1) / kc, amax);
@@ -1121,6 +1151,13 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
   for (int i = 0; i < 4; ++i) v.box[i] = d->a.box[i + 1];
   memcpy(v.e_base, d->e_base, sizeof(v.e_base)); memcpy(v.e_step, d->e_step, sizeof(v.e_step));
   memcpy(v.e_p1, d->e_p1, sizeof(v.e_p1)); memcpy(v.e_p2, d->e_p2, sizeof(v.e_p2));
+  for (int i = 0; i < 4; ++i) {
+    v.fd_t[i] = make_fastdiv(v.t_count[i]);
+    v.fd_p1[i] = make_fastdiv(v.e_p1[i]);
+    v.fd_p2[i] = make_fastdiv(v.e_p2[i]);
+  }
+  v.fd_nt = make_fastdiv(v.n_tiles);
+  v.fd_sdiv = make_fastdiv(d->stats_div);
   memcpy(v.e_comp, d->e_comp, sizeof(v.e_comp));
   v.out_dtype = d->out_dtype; v.act = d->act; v.act_slope = d->act_slope; v.n_valid = d->n_valid;
   v.out_cstride = d->out_cstride; v.stats_mode = d->stats_mode; v.stats_dim = d->stats_dim; v.stats_comp = d->stats_comp; v.stats_div = d->stats_div;
