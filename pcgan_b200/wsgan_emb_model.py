@@ -182,12 +182,16 @@ class BaseModel:
         return OrderedDict((n, getattr(self, n)) for n in self.visual_names if isinstance(n, str))
 
     def get_current_losses(self):
-        out = OrderedDict()
-        for n in self.loss_names:
-            if isinstance(n, str):
-                v = getattr(self, "loss_" + n)
-                out[n] = float(v.detach()) if torch.is_tensor(v) else float(v)
-        return out
+        """base_model.py:77-83 (float(getattr(self, 'loss_' + name)) per name); here the device scalars are read back with
+        ONE device -> host copy instead of one synchronising copy per loss."""
+        names = [n for n in self.loss_names if isinstance(n, str)]
+        vals = [getattr(self, "loss_" + n) for n in names]
+        dev = [i for i, v in enumerate(vals) if torch.is_tensor(v) and v.is_cuda]
+        if len(dev) > 1:
+            host = torch.stack([vals[i].detach().float().reshape(()) for i in dev]).tolist()
+            for i, h in zip(dev, host):
+                vals[i] = h
+        return OrderedDict((n, float(v.detach()) if torch.is_tensor(v) else float(v)) for n, v in zip(names, vals))
 
     def _unwrap(self, net):
         return net.module if isinstance(net, torch.nn.DataParallel) else net
