@@ -174,6 +174,9 @@ typedef struct pcgan_igemm_plan pcgan_igemm_plan;
 /* Validates the descriptor (host only, no GPU needed) and copies it. */
 int pcgan_igemm_plan_create(const pcgan_igemm_desc* desc, pcgan_igemm_plan** plan);
 void pcgan_igemm_plan_destroy(pcgan_igemm_plan* plan);
+/* Host-only self-test of the magic-number divisions the kernel uses for its per-tile coordinate arithmetic (the same
+ * formula evaluated on the host against x / d): returns the number of mismatches over `iters` random divisors. */
+int64_t pcgan_selftest_fastdiv(uint32_t seed, int32_t iters);
 /* a, b: operand base pointers (16-byte aligned); out: output base; bias: f32
  * [n_valid] or NULL; stats: f32 [groups][n_valid][2] or NULL. */
 int pcgan_igemm_run(pcgan_igemm_plan* plan, const void* a, const void* b, void* out,

@@ -138,6 +138,7 @@ SYMBOLS = {
     "pcgan_sizeof": (i64, [C.c_char_p]),
     "pcgan_igemm_plan_create": (C.c_int, [C.POINTER(IgemmDesc), C.POINTER(vp)]),
     "pcgan_igemm_plan_destroy": (None, [vp]),
+    "pcgan_selftest_fastdiv": (C.c_int64, [C.c_uint32, C.c_int32]),
     "pcgan_igemm_run": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "pcgan_gather_cast_bf16": (C.c_int, [vp, vp, vp, i64, vp]),
     "pcgan_gather_tf32": (C.c_int, [vp, vp, vp, i64, vp]),

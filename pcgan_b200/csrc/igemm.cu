@@ -67,6 +67,12 @@ __device__ __forceinline__ int32_t fdiv(int32_t x, const FastDiv& f) {
   const uint32_t u = static_cast<uint32_t>(x);
   return static_cast<int32_t>((__umulhi(u, f.mul) + u) >> f.shift);
 }
+// the same arithmetic on the host (pcgan_selftest_fastdiv)
+static int32_t fdiv_host(int32_t x, const FastDiv& f) {
+  const uint32_t u = static_cast<uint32_t>(x);
+  const uint32_t hi = static_cast<uint32_t>((static_cast<uint64_t>(u) * f.mul) >> 32);
+  return static_cast<int32_t>((hi + u) >> f.shift);
+}
 
 struct DevParams {
   int32_t kind, block_n, a_rows, a_ch;
@@ -1167,6 +1173,33 @@ extern "C" int pcgan_igemm_plan_create(const pcgan_igemm_desc* d, pcgan_igemm_pl
 }
 
 extern "C" void pcgan_igemm_plan_destroy(pcgan_igemm_plan* p) { delete p; }
+
+extern "C" int64_t pcgan_selftest_fastdiv(uint32_t seed, int32_t iters) {
+  // divisors: small, plan-like (image sizes, tile counts), powers of two and their neighbours, up to 2^31 - 1;
+  // dividends: 0, multiples of the divisor and their neighbours, random values below 2^31
+  uint64_t st = seed ? seed : 1u;
+  auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return static_cast<uint32_t>(st >> 33); };
+  int64_t bad = 0;
+  for (int32_t it = 0; it < iters; ++it) {
+    int32_t d;
+    switch (it & 3) {
+      case 0: d = 1 + static_cast<int32_t>(rnd() % 70000u); break;
+      case 1: d = static_cast<int32_t>(1u << (rnd() % 31u)) + static_cast<int32_t>(rnd() % 3u) - 1; break;
+      case 2: d = 1 + static_cast<int32_t>(rnd() % 0x7fffffffu); break;
+      default: { static const int32_t k[] = {3, 7, 49, 98, 112, 134, 224, 230, 12544, 17956, 16384, 65536}; d = k[rnd() % 12u]; }
+    }
+    if (d < 1) d = 1;
+    const FastDiv f = make_fastdiv(d);
+    const uint32_t m = rnd() % 100000u;
+    const int64_t xs[6] = {0, static_cast<int64_t>(rnd()) & 0x7fffffff, static_cast<int64_t>(d) * m, static_cast<int64_t>(d) * m - 1,
+                           static_cast<int64_t>(d) * m + 1, 0x7fffffff};
+    for (int64_t x : xs) {
+      if (x < 0 || x > 0x7fffffff) continue;
+      if (fdiv_host(static_cast<int32_t>(x), f) != static_cast<int32_t>(x / d)) ++bad;
+    }
+  }
+  return bad;
+}
 
 extern "C" int pcgan_igemm_run(pcgan_igemm_plan* p, const void* a, const void* b, void* out, const float* bias,
                                float* stats, pcgan_stream_t stream) {

@@ -411,3 +411,12 @@ def test_unet_down_conv_to_1x1_plan():
     out = run_fwd(plans, to_padded_nhwc(x, 1, "zero"), w, og.numel, bias=b)
     ref = torch.relu(F.conv2d(bf16_round(x), bf16_round(w), b, stride=2, padding=1))
     assert rel(from_padded_nhwc(out, N, 1, 1, 64, 1), ref) < 1e-5
+
+
+def test_magic_number_divisions_are_exact():
+    """The kernel divides tile indices and output coordinates by per-plan constants with (umulhi(x, mul) + x) >> shift
+    (csrc/igemm.cu FastDiv); the library's host-only self-test evaluates the same formula against x / d for plan-like,
+    power-of-two, neighbouring and random divisors up to 2^31 - 1 and dividends up to 2^31 - 1."""
+    lib = L.load()
+    for seed in (1, 2, 20260):
+        assert lib.pcgan_selftest_fastdiv(seed, 200000) == 0
