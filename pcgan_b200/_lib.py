@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PCGAN_KERNELS_LIB: another build of the same library (A/B measurements of a kernel change: tools/norm_bench.py)
 LIB_PATH = os.environ.get("PCGAN_KERNELS_LIB") or os.path.join(_HERE, "libpcgan_kernels.so")
 
-ABI_VERSION = 20
+ABI_VERSION = 21
 MAX_TAPS = 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
