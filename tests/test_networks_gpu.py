@@ -76,10 +76,11 @@ def test_generator_forward_backward(N, S, nb):
         assert rel(mod.state_dict()[k], sd[k]) < 2e-2, k
 
 
-@pytest.mark.parametrize("N,S", [(3, 32), (4, 128)])
-def test_discriminator_forward_backward_with_ganloss(N, S):
-    sd = O.make_state_dict(O.discriminator_keys(), 42, device=DEV, requires_grad=True)
-    net = NW.define_D(3, 1, 64, "n_layers", 3, "batch", True, "normal", gpu_ids=[0])
+@pytest.mark.parametrize("N,S,NL", [(3, 32, 3), (4, 128, 3), (3, 128, 4)])
+def test_discriminator_forward_backward_with_ganloss(N, S, NL):
+    """NL = 4: --n_layers_D 4 (the 4-layer discriminator), one more stride-2 convolution + BatchNorm."""
+    sd = O.make_state_dict(O.discriminator_keys(n_layers=NL), 42, device=DEV, requires_grad=True)
+    net = NW.define_D(3, 1, 64, "n_layers", NL, "batch", True, "normal", gpu_ids=[0])
     mod = load_into(net, sd)
     a, _, _ = O.synthetic_batch(N, S, 301, device=DEV)
     z = torch.linspace(-1, 1, N, device=DEV).view(N, 1, 1, 1)
@@ -91,9 +92,9 @@ def test_discriminator_forward_backward_with_ganloss(N, S):
     mine = {k: p.grad.clone() for k, p in mod.named_parameters()}
     res = {}
     for tag, q in (("exact", O.Quant(False)), ("emul", O.Quant(True))):
-        sdq = O.make_state_dict(O.discriminator_keys(), 42, device=DEV, requires_grad=True)
+        sdq = O.make_state_dict(O.discriminator_keys(n_layers=NL), 42, device=DEV, requires_grad=True)
         a2 = a.clone().requires_grad_(True)
-        ref = O.discriminator_forward(sdq, a2, z, q=q)
+        ref = O.discriminator_forward(sdq, a2, z, n_layers=NL, q=q)
         lref = O.gan_loss(ref, target)
         lref.backward()
         res[tag] = (rel(out, ref), rel(a1.grad, a2.grad), {k: rel(mine[k], sdq[k].grad) for k in mine})
